@@ -1,0 +1,576 @@
+// gds_api.cu — C ABI (include/gds.h) and host-side orchestration of the device pipeline.
+// No CPU fallback exists: without a usable CUDA device every entry point fails.
+#include "../../include/gds.h"
+
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "graph.cuh"
+#include "maxflow.cuh"
+#include "prep.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+#include "select.cuh"
+
+using namespace gds;
+
+namespace {
+enum Ev { EV_BEGIN = 0, EV_H2D, EV_FILTER, EV_GRAPH, EV_MAXFLOW, EV_SELECT, EV_VERIFY, EV_END, EV_COUNT };
+}
+
+struct gds_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    cudaEvent_t ev[EV_COUNT] = {};
+    void* pinned = nullptr;  // small readback area
+    static constexpr size_t kPinnedBytes = 1 << 16;
+
+    DevBuf in_start, in_end, in_mapq, in_len;
+    DevBuf off_d, reflen_d, base_d, foff_d, amp_s, amp_e;
+    DevBuf pair_pass, flag32, fS, fE;
+    DevBuf small;  // uint32 stats[8] + u64 totals[4]
+    DevBuf keysA, keysB, valsA, valsB, tile_counts;
+    RadixTemp radix;
+    ScanTemp scan;
+    DevBuf b_first, b_key, b_s, b_t, b_mult, b_f;
+    DevBuf diff, outdeg, indeg, excl;
+    DevBuf tkA, tkB, tvA, tvB;
+    DevBuf n_dcur, n_dsnap, n_e, n_eadd, n_snk, n_g, n_stamp;
+    DevBuf comp_start, comp_end, comp_sidx, comp_eidx, comp_lo, comp_hi;
+    DevBuf qF, qT, qN, work_counter, comp_stats;
+    DevBuf bitmap, cov_tmp, dem_tmp, vdiff, vexcl;
+    bool mf_attr_set = false;
+
+    void release_all() {
+        DevBuf* all[] = {&in_start, &in_end, &in_mapq, &in_len, &off_d, &reflen_d, &base_d, &foff_d,
+                         &amp_s, &amp_e, &pair_pass, &flag32, &fS, &fE, &small, &keysA, &keysB,
+                         &valsA, &valsB, &tile_counts, &radix.hist, &radix.scan.l1, &radix.scan.l2,
+                         &scan.l1, &scan.l2, &b_first, &b_key, &b_s, &b_t, &b_mult, &b_f, &diff,
+                         &outdeg, &indeg, &excl, &tkA, &tkB, &tvA, &tvB, &n_dcur, &n_dsnap, &n_e,
+                         &n_eadd, &n_snk, &n_g, &n_stamp, &comp_start, &comp_end, &comp_sidx,
+                         &comp_eidx, &comp_lo, &comp_hi, &qF, &qT, &qN, &work_counter, &comp_stats,
+                         &bitmap, &cov_tmp, &dem_tmp, &vdiff, &vexcl};
+        for (DevBuf* b : all) b->release();
+    }
+};
+
+namespace {
+
+int fail(gds_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+int fail_cuda(gds_ctx* ctx, const CudaFail& f) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s failed: %s (%s:%d)", f.what, cudaGetErrorString(f.err), f.file,
+             f.line);
+    ctx->err = buf;
+    cudaGetLastError();  // clear sticky-free errors
+    return f.err == cudaErrorMemoryAllocation ? GDS_ERR_NOMEM : GDS_ERR_CUDA;
+}
+
+template <typename T>
+void d2h_sync(gds_ctx* c, T* host_dst, const T* dev_src, size_t n) {
+    size_t bytes = n * sizeof(T);
+    if (bytes <= gds_ctx::kPinnedBytes) {
+        GDS_CUDA(cudaMemcpyAsync(c->pinned, dev_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+        GDS_CUDA(cudaStreamSynchronize(c->stream));
+        memcpy(host_dst, c->pinned, bytes);
+    } else {
+        GDS_CUDA(cudaMemcpyAsync(host_dst, dev_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+        GDS_CUDA(cudaStreamSynchronize(c->stream));
+    }
+}
+
+// copy a device array to the caller's buffer (host or device)
+template <typename T>
+void deliver(gds_ctx* c, T* dst, const T* dev_src, size_t n, bool dst_on_device) {
+    if (!dst || n == 0 || dst == dev_src) return;
+    GDS_CUDA(cudaMemcpyAsync(dst, dev_src, n * sizeof(T),
+                             dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                             c->stream));
+}
+
+template <typename K>
+void build_bundles(gds_ctx* c, const uint32_t* S, const uint32_t* E, const uint64_t* off_dev,
+                   const uint32_t* base_dev, uint32_t n_samples, size_t N, uint32_t n_nodes,
+                   int nodebits, int lenbits, uint32_t minlen, uint32_t& B_out,
+                   uint32_t*& sorted_idx_out, int& passes_out) {
+    cudaStream_t st = c->stream;
+    K* kA = c->keysA.get<K>(N);
+    K* kB = c->keysB.get<K>(N);
+    uint32_t* vA = c->valsA.get<uint32_t>(N);
+    uint32_t* vB = c->valsB.get<uint32_t>(N);
+    ReadKeys<K> rk{S, E, off_dev, base_dev, n_samples, lenbits, minlen};
+    int where = radix_sort_pairs<K, ReadKeys<K>>(kA, vA, kB, vB, N, nodebits + lenbits, true,
+                                                 c->radix, st, &passes_out, &rk);
+    const K* keys = where ? kB : kA;
+    sorted_idx_out = where ? vB : vA;
+    // bundle heads
+    uint32_t n_tiles = (uint32_t)((N + kHeadTile - 1) / kHeadTile);
+    uint32_t* tc = c->tile_counts.get<uint32_t>(n_tiles + 1);
+    GDS_CUDA(cudaMemsetAsync(tc + n_tiles, 0, sizeof(uint32_t), st));
+    k_heads_count<K><<<n_tiles, kHeadThreads, 0, st>>>(keys, N, tc);
+    GDS_KERNEL_CHECK();
+    exclusive_scan_u32(tc, tc, n_tiles + 1, c->scan, st);
+    uint32_t B = 0;
+    d2h_sync(c, &B, tc + n_tiles, 1);
+    B_out = B;
+    uint32_t* b_first = c->b_first.get<uint32_t>(B + 1);
+    K* b_key = c->b_key.get<K>(B + 1);
+    k_heads_write<K><<<n_tiles, kHeadThreads, 0, st>>>(keys, N, tc, b_first, b_key);
+    GDS_KERNEL_CHECK();
+    uint32_t* b_s = c->b_s.get<uint32_t>(B + 1);
+    uint32_t* b_t = c->b_t.get<uint32_t>(B + 1);
+    uint32_t* b_mult = c->b_mult.get<uint32_t>(B + 1);
+    int32_t* diff = c->diff.get<int32_t>(n_nodes + 1);
+    uint32_t* outdeg = c->outdeg.get<uint32_t>(n_nodes + 1);
+    uint32_t* indeg = c->indeg.get<uint32_t>(n_nodes + 1);
+    GDS_CUDA(cudaMemsetAsync(diff, 0, (n_nodes + 1) * sizeof(int32_t), st));
+    GDS_CUDA(cudaMemsetAsync(outdeg, 0, (n_nodes + 1) * sizeof(uint32_t), st));
+    GDS_CUDA(cudaMemsetAsync(indeg, 0, (n_nodes + 1) * sizeof(uint32_t), st));
+    if (B) {
+        k_bundle_fill<K><<<div_up(B, 256), 256, 0, st>>>(b_key, b_first, B, (uint32_t)N, lenbits,
+                                                         minlen, b_s, b_t, b_mult, diff, outdeg,
+                                                         indeg);
+        GDS_KERNEL_CHECK();
+    }
+}
+
+}  // namespace
+
+extern "C" int gds_abi_version(void) { return GDS_ABI_VERSION; }
+
+extern "C" int gds_create(int device, gds_ctx** out) {
+    if (!out) return GDS_ERR_ARG;
+    *out = nullptr;
+    gds_ctx* c = new (std::nothrow) gds_ctx();
+    if (!c) return GDS_ERR_NOMEM;
+    c->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMallocHost(&c->pinned, gds_ctx::kPinnedBytes);
+    for (int i = 0; i < EV_COUNT && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+    if (e != cudaSuccess) {
+        // no device, no driver, wrong arch: there is no CPU path to fall back to
+        fprintf(stderr, "gds_create: CUDA device %d unusable: %s\n", device, cudaGetErrorString(e));
+        cudaGetLastError();
+        delete c;
+        return GDS_ERR_CUDA;
+    }
+    c->stream = c->own_stream;
+    *out = c;
+    return GDS_OK;
+}
+
+extern "C" void gds_destroy(gds_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    c->release_all();
+    for (int i = 0; i < EV_COUNT; ++i)
+        if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+extern "C" const char* gds_last_error(const gds_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+extern "C" int gds_set_stream(gds_ctx* c, void* cuda_stream) {
+    if (!c) return GDS_ERR_ARG;
+    c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return GDS_OK;
+}
+
+extern "C" uint64_t gds_bitmap_to_indices(const uint32_t* bitmap, uint64_t n_bits,
+                                          uint64_t* indices, uint64_t cap) {
+    uint64_t cnt = 0;
+    uint64_t words = (n_bits + 31) / 32;
+    for (uint64_t w = 0; w < words; ++w) {
+        uint32_t x = bitmap[w];
+        while (x) {
+            int bit = __builtin_ctz(x);
+            x &= x - 1;
+            uint64_t i = w * 32 + bit;
+            if (i >= n_bits) break;
+            if (cnt < cap && indices) indices[cnt] = i;
+            ++cnt;
+        }
+    }
+    return cnt;
+}
+
+extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
+                         uint32_t max_coverage, const gds_params* prm, uint32_t flags,
+                         gds_result* out) {
+    if (!c) return GDS_ERR_ARG;
+    c->err.clear();
+    if (!rd || !out || rd->n_samples == 0 || !rd->read_off || !rd->ref_len)
+        return fail(c, GDS_ERR_ARG, "null reads/result or n_samples == 0");
+    const uint32_t ns = rd->n_samples;
+    const uint64_t P = rd->read_off[ns];
+    if (rd->read_off[0] != 0) return fail(c, GDS_ERR_ARG, "read_off[0] must be 0");
+    for (uint32_t k = 0; k < ns; ++k)
+        if (rd->read_off[k + 1] < rd->read_off[k])
+            return fail(c, GDS_ERR_ARG, "read_off must be non-decreasing");
+    if (P > 0 && (!rd->start || !rd->end)) return fail(c, GDS_ERR_ARG, "null start/end");
+    if (P >= (1ull << 32) - 64) return fail(c, GDS_ERR_RANGE, "more than 2^32 reads in one call");
+    const bool use_filter = flt != nullptr;
+    if (use_filter) {
+        if (P > 0 && (!rd->mapq || !rd->seq_len))
+            return fail(c, GDS_ERR_ARG, "filter needs mapq and seq_len");
+        for (uint32_t k = 0; k <= ns; ++k)
+            if (rd->read_off[k] & 1)
+                return fail(c, GDS_ERR_ARG, "filter needs an even read count per sample (mates adjacent)");
+        if (flt->n_amplicons && (!flt->amp_start || !flt->amp_end))
+            return fail(c, GDS_ERR_ARG, "null amplicon table");
+    }
+    uint64_t nn64 = 0;
+    std::vector<uint32_t> base(ns + 1, 0);
+    for (uint32_t k = 0; k < ns; ++k) {
+        nn64 += (uint64_t)rd->ref_len[k] + 1;
+        if (nn64 >= kLabelInf) return fail(c, GDS_ERR_RANGE, "total reference length beyond 2^30 nodes");
+        base[k + 1] = (uint32_t)nn64;
+    }
+    const uint32_t n_nodes = (uint32_t)nn64;
+    const bool in_dev = flags & GDS_INPUT_ON_DEVICE;
+    const bool out_dev = flags & GDS_OUTPUT_ON_DEVICE;
+    SolveParams sp{64, 150, 1, 0};
+    if (prm && (prm->gr_interval_min | prm->gr_levels_pct | prm->gr_relabel_pct | prm->max_rounds)) {
+        sp.gr_interval_min = prm->gr_interval_min;
+        sp.gr_levels_pct = prm->gr_levels_pct;
+        sp.gr_relabel_pct = prm->gr_relabel_pct;
+        sp.max_rounds = prm->max_rounds;
+    }
+    // scalars of the result start clean (buffers are left alone)
+    {
+        gds_result keep = *out;
+        memset(out, 0, sizeof *out);
+        out->kept_bitmap = keep.kept_bitmap;
+        out->pair_pass = keep.pair_pass;
+        out->filt_off = keep.filt_off;
+        out->cov_capped = keep.cov_capped;
+        out->demand = keep.demand;
+    }
+    out->n_reads_in = P;
+    out->n_nodes = n_nodes;
+
+    try {
+        GDS_CUDA(cudaSetDevice(c->device));
+        cudaStream_t st = c->stream;
+        GDS_CUDA(cudaEventRecord(c->ev[EV_BEGIN], st));
+
+        // ---------------- inputs ----------------
+        const uint32_t *dS, *dE, *dLen = nullptr;
+        const uint8_t* dQ = nullptr;
+        if (in_dev || P == 0) {
+            dS = rd->start;
+            dE = rd->end;
+            dQ = rd->mapq;
+            dLen = rd->seq_len;
+        } else {
+            uint32_t* s = c->in_start.get<uint32_t>(P);
+            uint32_t* e = c->in_end.get<uint32_t>(P);
+            GDS_CUDA(cudaMemcpyAsync(s, rd->start, P * 4, cudaMemcpyHostToDevice, st));
+            GDS_CUDA(cudaMemcpyAsync(e, rd->end, P * 4, cudaMemcpyHostToDevice, st));
+            dS = s;
+            dE = e;
+            if (use_filter) {
+                uint8_t* q = c->in_mapq.get<uint8_t>(P);
+                uint32_t* l = c->in_len.get<uint32_t>(P);
+                GDS_CUDA(cudaMemcpyAsync(q, rd->mapq, P, cudaMemcpyHostToDevice, st));
+                GDS_CUDA(cudaMemcpyAsync(l, rd->seq_len, P * 4, cudaMemcpyHostToDevice, st));
+                dQ = q;
+                dLen = l;
+            }
+        }
+        uint64_t* off_d = c->off_d.get<uint64_t>(ns + 1);
+        uint32_t* reflen_d = c->reflen_d.get<uint32_t>(ns);
+        uint32_t* base_d = c->base_d.get<uint32_t>(ns + 1);
+        GDS_CUDA(cudaMemcpyAsync(off_d, rd->read_off, (ns + 1) * 8, cudaMemcpyHostToDevice, st));
+        GDS_CUDA(cudaMemcpyAsync(reflen_d, rd->ref_len, ns * 4, cudaMemcpyHostToDevice, st));
+        GDS_CUDA(cudaMemcpyAsync(base_d, base.data(), (ns + 1) * 4, cudaMemcpyHostToDevice, st));
+        uint32_t* stats = c->small.get<uint32_t>(32);
+        unsigned long long* totals = reinterpret_cast<unsigned long long*>(stats + 8);
+        {
+            uint32_t init[32] = {};
+            init[0] = 0xffffffffu;
+            memcpy(c->pinned, init, sizeof init);
+            GDS_CUDA(cudaMemcpyAsync(stats, c->pinned, sizeof init, cudaMemcpyHostToDevice, st));
+        }
+        GDS_CUDA(cudaEventRecord(c->ev[EV_H2D], st));
+
+        // ---------------- K1: filter ----------------
+        const uint32_t* S = dS;
+        const uint32_t* E = dE;
+        const uint64_t* foff_dev = off_d;
+        uint64_t N = P;
+        std::vector<uint64_t> foff_host(rd->read_off, rd->read_off + ns + 1);
+        if (use_filter && P > 0) {
+            const size_t n_pairs = P / 2;
+            FilterArgs fa{flt->min_seq_length, flt->min_mapq, flt->n_amplicons, nullptr, nullptr};
+            std::vector<uint32_t> as, ae;  // must outlive the async upload
+            if (flt->n_amplicons) {
+                std::vector<std::pair<uint32_t, uint32_t>> amps(flt->n_amplicons);
+                for (uint32_t i = 0; i < flt->n_amplicons; ++i)
+                    amps[i] = {flt->amp_start[i], flt->amp_end[i]};
+                std::sort(amps.begin(), amps.end());
+                as.resize(amps.size());
+                ae.resize(amps.size());
+                uint32_t run = 0;
+                for (size_t i = 0; i < amps.size(); ++i) {
+                    run = std::max(run, amps[i].second);
+                    as[i] = amps[i].first;
+                    ae[i] = run;
+                }
+                uint32_t* das = c->amp_s.get<uint32_t>(as.size());
+                uint32_t* dae = c->amp_e.get<uint32_t>(ae.size());
+                GDS_CUDA(cudaMemcpy(das, as.data(), as.size() * 4, cudaMemcpyHostToDevice));
+                GDS_CUDA(cudaMemcpy(dae, ae.data(), ae.size() * 4, cudaMemcpyHostToDevice));
+                fa.amp_start_sorted = das;
+                fa.amp_end_runmax = dae;
+            }
+            uint8_t* pp = (out_dev && out->pair_pass) ? out->pair_pass
+                                                      : c->pair_pass.get<uint8_t>(n_pairs);
+            uint32_t* f32 = c->flag32.get<uint32_t>(n_pairs);
+            int grid = std::min<long long>(div_up(n_pairs, 256), kNumSMs * 16);
+            k_filter_flags<<<grid, 256, 0, st>>>(dS, dE, dQ, dLen, n_pairs, fa, pp, f32);
+            GDS_KERNEL_CHECK();
+            exclusive_scan_u32(f32, f32, n_pairs, c->scan, st);
+            uint64_t* foff = c->foff_d.get<uint64_t>(ns + 1);
+            k_filter_offsets<<<div_up(ns + 1, 128), 128, 0, st>>>(off_d, ns, f32, pp, n_pairs, foff);
+            GDS_KERNEL_CHECK();
+            d2h_sync(c, foff_host.data(), foff, ns + 1);
+            N = foff_host[ns];
+            uint32_t* fS = c->fS.get<uint32_t>(N);
+            uint32_t* fE = c->fE.get<uint32_t>(N);
+            k_filter_compact<<<grid, 256, 0, st>>>(dS, dE, pp, f32, n_pairs, fS, fE);
+            GDS_KERNEL_CHECK();
+            S = fS;
+            E = fE;
+            foff_dev = foff;
+            if (!out_dev) deliver(c, out->pair_pass, pp, n_pairs, false);
+        }
+        out->n_filtered = N;
+        if (out->filt_off) memcpy(out->filt_off, foff_host.data(), (ns + 1) * 8);
+        GDS_CUDA(cudaEventRecord(c->ev[EV_FILTER], st));
+
+        // ---------------- K2: coverage flow graph ----------------
+        uint32_t B = 0, n_comp = 0;
+        uint32_t* sorted_idx = nullptr;
+        int sort_passes = 0;
+        uint32_t minlen = 1;
+        int lenbits = 0;
+        const int nodebits = bits_for(n_nodes ? n_nodes - 1 : 0);
+        if (N > 0) {
+            int grid = std::min<long long>(div_up(N, 256 * 8), kNumSMs * 16);
+            k_validate<<<grid, 256, 0, st>>>(S, E, N, foff_dev, reflen_d, ns, stats);
+            GDS_KERNEL_CHECK();
+            uint32_t hstats[3];
+            d2h_sync(c, hstats, stats, 3);
+            if (hstats[2] != 0) {
+                char buf[128];
+                snprintf(buf, sizeof buf, "%u reads with start > end or end >= ref_len", hstats[2]);
+                return fail(c, GDS_ERR_RANGE, buf);
+            }
+            minlen = hstats[0];
+            lenbits = bits_for(hstats[1] - hstats[0]);
+            out->key_bits = nodebits + lenbits;
+            if (nodebits + lenbits <= 32)
+                build_bundles<uint32_t>(c, S, E, foff_dev, base_d, ns, N, n_nodes, nodebits, lenbits,
+                                        minlen, B, sorted_idx, sort_passes);
+            else
+                build_bundles<unsigned long long>(c, S, E, foff_dev, base_d, ns, N, n_nodes,
+                                                  nodebits, lenbits, minlen, B, sorted_idx,
+                                                  sort_passes);
+        } else {
+            int32_t* diff = c->diff.get<int32_t>(n_nodes + 1);
+            uint32_t* outdeg = c->outdeg.get<uint32_t>(n_nodes + 1);
+            uint32_t* indeg = c->indeg.get<uint32_t>(n_nodes + 1);
+            GDS_CUDA(cudaMemsetAsync(diff, 0, (n_nodes + 1) * 4, st));
+            GDS_CUDA(cudaMemsetAsync(outdeg, 0, (n_nodes + 1) * 4, st));
+            GDS_CUDA(cudaMemsetAsync(indeg, 0, (n_nodes + 1) * 4, st));
+            c->b_first.get<uint32_t>(1);
+            c->b_s.get<uint32_t>(1);
+            c->b_t.get<uint32_t>(1);
+            c->b_mult.get<uint32_t>(1);
+        }
+        out->n_bundles = B;
+        out->sort_passes = sort_passes;
+        int32_t* diff = c->diff.as<int32_t>();
+        uint32_t* out_ptr = c->outdeg.as<uint32_t>();
+        uint32_t* in_ptr = c->indeg.as<uint32_t>();
+        uint32_t* excl = c->excl.get<uint32_t>(n_nodes + 1);
+        exclusive_scan_u32(reinterpret_cast<const uint32_t*>(diff), excl, n_nodes + 1, c->scan, st);
+        exclusive_scan_u32(out_ptr, out_ptr, n_nodes + 1, c->scan, st);
+        exclusive_scan_u32(in_ptr, in_ptr, n_nodes + 1, c->scan, st);
+        NodeArrays na;
+        na.d_cur = c->n_dcur.get<uint32_t>(n_nodes);
+        na.d_snap = c->n_dsnap.get<uint32_t>(n_nodes);
+        na.e = c->n_e.get<int32_t>(n_nodes);
+        na.eadd = c->n_eadd.get<int32_t>(n_nodes);
+        na.snk = c->n_snk.get<int32_t>(n_nodes);
+        na.g = c->n_g.get<int32_t>(n_nodes);
+        na.stamp = c->n_stamp.get<uint32_t>(n_nodes);
+        uint32_t* cstart = c->comp_start.get<uint32_t>(n_nodes + 1);
+        uint32_t* cend = c->comp_end.get<uint32_t>(n_nodes + 1);
+        GDS_CUDA(cudaMemsetAsync(cstart + n_nodes, 0, 4, st));
+        GDS_CUDA(cudaMemsetAsync(cend + n_nodes, 0, 4, st));
+        uint32_t* cov_dev = nullptr;
+        int32_t* dem_dev = nullptr;
+        if (out->cov_capped) cov_dev = out_dev ? out->cov_capped : c->cov_tmp.get<uint32_t>(n_nodes);
+        if (out->demand) dem_dev = out_dev ? out->demand : c->dem_tmp.get<int32_t>(n_nodes);
+        k_node_finalize<<<div_up(n_nodes, 256), 256, 0, st>>>(excl, diff, n_nodes, max_coverage, na,
+                                                              cstart, cend, cov_dev, dem_dev, totals);
+        GDS_KERNEL_CHECK();
+        uint32_t* sidx = c->comp_sidx.get<uint32_t>(n_nodes + 1);
+        uint32_t* eidx = c->comp_eidx.get<uint32_t>(n_nodes + 1);
+        exclusive_scan_u32(cstart, sidx, n_nodes + 1, c->scan, st);
+        exclusive_scan_u32(cend, eidx, n_nodes + 1, c->scan, st);
+        d2h_sync(c, &n_comp, sidx + n_nodes, 1);
+        out->n_components = n_comp;
+        uint32_t* comp_lo = c->comp_lo.get<uint32_t>(n_comp + 1);
+        uint32_t* comp_hi = c->comp_hi.get<uint32_t>(n_comp + 1);
+        if (n_comp) {
+            k_comp_write<<<div_up(n_nodes, 256), 256, 0, st>>>(cstart, cend, sidx, eidx, n_nodes,
+                                                               comp_lo, comp_hi);
+            GDS_KERNEL_CHECK();
+        }
+        // in-CSR: bundle ids ordered by (end node, start node) = stable sort of ids by b_t
+        uint32_t* in_bid = nullptr;
+        uint32_t* f = c->b_f.get<uint32_t>(B + 1);
+        GDS_CUDA(cudaMemsetAsync(f, 0, (B + 1) * 4, st));
+        if (B) {
+            uint32_t* tkA = c->tkA.get<uint32_t>(B);
+            uint32_t* tkB = c->tkB.get<uint32_t>(B);
+            uint32_t* tvA = c->tvA.get<uint32_t>(B);
+            uint32_t* tvB = c->tvB.get<uint32_t>(B);
+            GDS_CUDA(cudaMemcpyAsync(tkA, c->b_t.as<uint32_t>(), (size_t)B * 4,
+                                     cudaMemcpyDeviceToDevice, st));
+            int w = radix_sort_pairs<uint32_t>(tkA, tvA, tkB, tvB, B, nodebits, true, c->radix, st);
+            in_bid = w ? tvB : tvA;
+        }
+        if (!out_dev) {
+            deliver(c, out->cov_capped, cov_dev, n_nodes, false);
+            deliver(c, out->demand, dem_dev, n_nodes, false);
+        }
+        GDS_CUDA(cudaEventRecord(c->ev[EV_GRAPH], st));
+
+        // ---------------- K3: max flow ----------------
+        BundleGraph bg{c->b_s.as<uint32_t>(), c->b_t.as<uint32_t>(), c->b_mult.as<uint32_t>(), f,
+                       out_ptr, in_ptr, in_bid};
+        CompStats* cstats = c->comp_stats.get<CompStats>(n_comp + 1);
+        const bool do_solve = !(flags & GDS_NO_SOLVE);
+        if (do_solve && n_comp) {
+            uint32_t* qF = c->qF.get<uint32_t>(n_nodes);
+            uint32_t* qT = c->qT.get<uint32_t>(n_nodes);
+            uint32_t* qN = c->qN.get<uint32_t>(n_nodes);
+            uint32_t* wc = c->work_counter.get<uint32_t>(1);
+            GDS_CUDA(cudaMemsetAsync(wc, 0, 4, st));
+            if (!c->mf_attr_set) {
+                GDS_CUDA(cudaFuncSetAttribute(k_maxflow, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)sizeof(MfShared)));
+                c->mf_attr_set = true;
+            }
+            int grid = std::min<uint32_t>(n_comp, kNumSMs);
+            k_maxflow<<<grid, kMfThreads, sizeof(MfShared), st>>>(na, bg, comp_lo, comp_hi, n_comp,
+                                                                  wc, qF, qT, qN, sp, cstats);
+            GDS_KERNEL_CHECK();
+        }
+        GDS_CUDA(cudaEventRecord(c->ev[EV_MAXFLOW], st));
+
+        // ---------------- K5: selection ----------------
+        const size_t n_words = (N + 31) / 32;
+        uint32_t* bm = (out_dev && out->kept_bitmap) ? out->kept_bitmap
+                                                     : c->bitmap.get<uint32_t>(n_words + 1);
+        if (do_solve) {
+            GDS_CUDA(cudaMemsetAsync(bm, 0, n_words * 4, st));
+            if (B) {
+                k_select<<<div_up(B, 256), 256, 0, st>>>(c->b_first.as<uint32_t>(), f, sorted_idx, B,
+                                                         bm, totals);
+                GDS_KERNEL_CHECK();
+            }
+        }
+        GDS_CUDA(cudaEventRecord(c->ev[EV_SELECT], st));
+
+        // ---------------- K6: verification (before find_pairs widens the set) ----------------
+        if (do_solve && (flags & GDS_VERIFY)) {
+            int32_t* vdiff = c->vdiff.get<int32_t>(n_nodes + 1);
+            uint32_t* vexcl = c->vexcl.get<uint32_t>(n_nodes + 1);
+            GDS_CUDA(cudaMemsetAsync(vdiff, 0, (n_nodes + 1) * 4, st));
+            if (n_words) {
+                k_verify_accumulate<<<div_up(n_words, 256), 256, 0, st>>>(bm, S, E, N, foff_dev,
+                                                                          base_d, ns, vdiff);
+                GDS_KERNEL_CHECK();
+            }
+            exclusive_scan_u32(reinterpret_cast<const uint32_t*>(vdiff), vexcl, n_nodes + 1, c->scan,
+                               st);
+            k_verify_compare<<<div_up(n_nodes, 256), 256, 0, st>>>(vexcl, vdiff, excl, diff, n_nodes,
+                                                                   max_coverage, totals);
+            GDS_KERNEL_CHECK();
+        }
+        if (do_solve && (flags & GDS_FIND_PAIRS) && n_words) {
+            k_find_pairs<<<div_up(n_words, 256), 256, 0, st>>>(bm, n_words);
+            GDS_KERNEL_CHECK();
+        }
+        GDS_CUDA(cudaEventRecord(c->ev[EV_VERIFY], st));
+
+        // ---------------- results ----------------
+        if (do_solve && !out_dev) deliver(c, out->kept_bitmap, bm, n_words, false);
+        unsigned long long htot[4] = {};
+        d2h_sync(c, htot, totals, 4);
+        out->fstar = (int64_t)htot[0];
+        out->n_kept = htot[1];
+        out->verify_violations = htot[2];
+        long long stuck = 0;
+        if (do_solve && n_comp) {
+            std::vector<CompStats> hs(n_comp);
+            d2h_sync(c, hs.data(), cstats, n_comp);
+            for (const CompStats& s : hs) {
+                out->flow_value += s.sink_flow;
+                out->rounds_total += s.rounds;
+                out->rounds_max = std::max<uint64_t>(out->rounds_max, s.rounds);
+                out->pushes += s.pushes;
+                out->relabels += s.relabels;
+                out->global_relabels += s.grs;
+                out->bfs_levels += s.bfs_levels;
+                out->max_frontier = std::max<uint64_t>(out->max_frontier, s.max_frontier);
+                stuck += s.stuck;
+            }
+        }
+        GDS_CUDA(cudaEventRecord(c->ev[EV_END], st));
+        GDS_CUDA(cudaStreamSynchronize(st));
+        auto ms = [&](int a, int b) {
+            float t = 0;
+            cudaEventElapsedTime(&t, c->ev[a], c->ev[b]);
+            return t;
+        };
+        out->ms_h2d = ms(EV_BEGIN, EV_H2D);
+        out->ms_filter = ms(EV_H2D, EV_FILTER);
+        out->ms_graph = ms(EV_FILTER, EV_GRAPH);
+        out->ms_maxflow = ms(EV_GRAPH, EV_MAXFLOW);
+        out->ms_select = ms(EV_MAXFLOW, EV_SELECT);
+        out->ms_verify = ms(EV_SELECT, EV_VERIFY);
+        out->ms_d2h = ms(EV_VERIFY, EV_END);
+        out->ms_total = ms(EV_BEGIN, EV_END);
+        if (do_solve && (out->flow_value != out->fstar || stuck != 0)) {
+            char buf[160];
+            snprintf(buf, sizeof buf, "max-flow did not converge: sink inflow %lld, F* %lld, stuck %lld",
+                     (long long)out->flow_value, (long long)out->fstar, stuck);
+            return fail(c, GDS_ERR_NOCONVERGE, buf);
+        }
+        return GDS_OK;
+    } catch (const CudaFail& f) {
+        return fail_cuda(c, f);
+    } catch (const std::bad_alloc&) {
+        return fail(c, GDS_ERR_NOMEM, "host allocation failed");
+    }
+}

@@ -1,0 +1,123 @@
+// prep.cuh — K1: pair filter (predicate + stable compaction) and read validation.
+// Restates, for the device, BamApi::should_be_filtered_out (bam_api.cpp:311-332):
+//   drop pair unless both mates have quality >= min_mapq, seq_length >= min_len and (FILTER mode)
+//   some amplicon [a0,a1] contains both mates (amplicon.cpp:5-7, amplicon_set.cpp:5-9).
+// "Some amplicon contains both" == max{a1 : a0 <= min(s1,s2)} >= max(e1,e2); the host ships the
+// amplicons sorted by a0 with a running max of a1, so the device does one binary search per pair.
+#pragma once
+#include "common.cuh"
+#include "scan.cuh"
+
+namespace gds {
+
+// sample lookup: largest k with off[k] <= i   (off[0] = 0, off[n_samples] = total)
+__device__ __forceinline__ uint32_t find_sample(const uint64_t* __restrict__ off,
+                                                uint32_t n_samples, uint64_t i) {
+    uint32_t lo = 0, hi = n_samples;  // invariant: off[lo] <= i < off[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (off[mid] <= i) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+struct FilterArgs {
+    uint32_t min_len, min_mapq;
+    uint32_t n_amp;
+    const uint32_t* amp_start_sorted;  // ascending
+    const uint32_t* amp_end_runmax;    // running max of the matching ends
+};
+
+__global__ void __launch_bounds__(256)
+k_filter_flags(const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
+               const uint8_t* __restrict__ mapq, const uint32_t* __restrict__ seq_len,
+               size_t n_pairs, FilterArgs fa, uint8_t* __restrict__ pair_pass,
+               uint32_t* __restrict__ flag32) {
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs;
+         p += (size_t)gridDim.x * blockDim.x) {
+        // mates are adjacent: one 8-byte load per array
+        uint2 s = reinterpret_cast<const uint2*>(start)[p];
+        uint2 e = reinterpret_cast<const uint2*>(end)[p];
+        uint2 l = reinterpret_cast<const uint2*>(seq_len)[p];
+        uchar2 q = reinterpret_cast<const uchar2*>(mapq)[p];
+        bool ok = q.x >= fa.min_mapq && q.y >= fa.min_mapq && l.x >= fa.min_len &&
+                  l.y >= fa.min_len;
+        if (ok && fa.n_amp) {
+            uint32_t lo_pos = min(s.x, s.y), hi_pos = max(e.x, e.y);
+            // last amplicon with start <= lo_pos
+            int lo = -1, hi = (int)fa.n_amp;
+            while (hi - lo > 1) {
+                int mid = (lo + hi) >> 1;
+                if (fa.amp_start_sorted[mid] <= lo_pos) lo = mid;
+                else hi = mid;
+            }
+            ok = lo >= 0 && fa.amp_end_runmax[lo] >= hi_pos;
+        }
+        pair_pass[p] = ok ? 1 : 0;
+        flag32[p] = ok ? 1u : 0u;
+    }
+}
+
+// pass_idx = exclusive scan of flag32.  Stable compaction: surviving pair p goes to 2*pass_idx[p].
+__global__ void __launch_bounds__(256)
+k_filter_compact(const uint32_t* __restrict__ start, const uint32_t* __restrict__ end,
+                 const uint8_t* __restrict__ pair_pass, const uint32_t* __restrict__ pass_idx,
+                 size_t n_pairs, uint32_t* __restrict__ out_start, uint32_t* __restrict__ out_end) {
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pairs;
+         p += (size_t)gridDim.x * blockDim.x) {
+        if (!pair_pass[p]) continue;
+        size_t o = pass_idx[p];
+        reinterpret_cast<uint2*>(out_start)[o] = reinterpret_cast<const uint2*>(start)[p];
+        reinterpret_cast<uint2*>(out_end)[o] = reinterpret_cast<const uint2*>(end)[p];
+    }
+}
+
+// post-filter read offsets per sample: foff[k] = 2 * (#surviving pairs before pair off[k]/2)
+__global__ void k_filter_offsets(const uint64_t* __restrict__ off, uint32_t n_samples,
+                                 const uint32_t* __restrict__ pass_idx,
+                                 const uint8_t* __restrict__ pair_pass, size_t n_pairs,
+                                 uint64_t* __restrict__ foff) {
+    uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > n_samples) return;
+    size_t p = off[k] / 2;
+    uint64_t cnt;
+    if (n_pairs == 0) cnt = 0;
+    else if (p < n_pairs) cnt = pass_idx[p];
+    else cnt = (uint64_t)pass_idx[n_pairs - 1] + pair_pass[n_pairs - 1];
+    foff[k] = 2 * cnt;
+}
+
+// Validation + read-length range over the (post-filter) reads.  stats[0]=min len, [1]=max len,
+// [2]=error count.
+__global__ void __launch_bounds__(256)
+k_validate(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, size_t n,
+           const uint64_t* __restrict__ off, const uint32_t* __restrict__ ref_len,
+           uint32_t n_samples, uint32_t* __restrict__ stats) {
+    uint32_t mn = 0xffffffffu, mx = 0, bad = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        uint32_t s = ld_stream(S + i), e = ld_stream(E + i);
+        uint32_t k = n_samples == 1 ? 0 : find_sample(off, n_samples, i);
+        if (s > e || e >= ref_len[k]) {
+            ++bad;
+            continue;
+        }
+        uint32_t len = e - s + 1;
+        mn = min(mn, len);
+        mx = max(mx, len);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    if (lane_id() == 0) {
+        if (mn != 0xffffffffu) atomicMin(&stats[0], mn);
+        if (mx) atomicMax(&stats[1], mx);
+        if (bad) atomicAdd(&stats[2], bad);
+    }
+}
+
+}  // namespace gds

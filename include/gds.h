@@ -1,0 +1,128 @@
+/*
+ * gds.h — C ABI of the B200-native quasi-MCP downsampler (libgds_b200.so).
+ *
+ * This is the drop-in boundary for ONE path of migoox/genome-downsampler: what a
+ * qmcp::Solver::solve(max_coverage, BamApi&) implementation
+ * (libs/qmcp-solver/include/qmcp-solver/solver.hpp:15-20) needs from the device:
+ *   filter -> coverage/demand -> flow graph -> max-flow -> read selection.
+ * Plain pointers and sizes only; no C++ or torch types cross it.  Every entry point cites the
+ * reference interface it replaces.  There is NO CPU fallback: every call fails with
+ * GDS_ERR_CUDA when no sm_100 device / driver is usable.
+ *
+ * Index conventions are the reference's: positions are 0-based inclusive [start, end]
+ * (libs/bam-api/include/bam-api/read.hpp:19-30), mates are adjacent (first at even index,
+ * libs/bam-api/src/bam_api.cpp:456-461), returned read indices refer to the POST-FILTER arrays
+ * (what BamApi::get_paired_reads_soa() would hold, bam_api.cpp:212-233).
+ */
+#ifndef GDS_H
+#define GDS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GDS_ABI_VERSION 1
+
+/* status codes (the reference has none: it logs and exits, cuda_helpers.cuh:13-21) */
+enum {
+    GDS_OK = 0,
+    GDS_ERR_ARG = 1,       /* null pointer, odd read count with a filter, bad sizes */
+    GDS_ERR_RANGE = 2,     /* end >= ref_len, start > end, L or N beyond 32-bit device limits */
+    GDS_ERR_CUDA = 3,      /* CUDA runtime error (message in gds_last_error) */
+    GDS_ERR_NOMEM = 4,     /* device allocation failed */
+    GDS_ERR_NOCONVERGE = 5 /* max_rounds hit or sink inflow != F* (never on valid input) */
+};
+
+/* flags for gds_solve */
+enum {
+    GDS_INPUT_ON_DEVICE = 1u << 0,  /* start/end/mapq/seq_len are device pointers */
+    GDS_OUTPUT_ON_DEVICE = 1u << 1, /* kept_bitmap/pair_pass/cov/demand are device pointers */
+    GDS_VERIFY = 1u << 2,           /* recompute coverage of the kept set on device and compare */
+    GDS_FIND_PAIRS = 1u << 3,       /* also OR each kept read's mate into the bitmap
+                                       (BamApi::find_pairs, bam_api.cpp:239-273) */
+    GDS_NO_SOLVE = 1u << 4          /* stop after coverage/demand/graph (K1+K2 only) */
+};
+
+typedef struct gds_ctx gds_ctx;
+
+/* Input reads.  Replaces bam_api::SOAPairedReads (soa_paired_reads.hpp:18-24) narrowed to
+ * 32-bit; a batch is n_samples independent samples/contigs concatenated.  read_off and ref_len
+ * are always HOST arrays. */
+typedef struct {
+    uint32_t n_samples;       /* >= 1 */
+    const uint64_t* read_off; /* [n_samples+1], read_off[0] = 0 */
+    const uint32_t* ref_len;  /* [n_samples]  PairedReads::ref_genome_length */
+    const uint32_t* start;    /* [n_reads]    Read::start_ind */
+    const uint32_t* end;      /* [n_reads]    Read::end_ind (inclusive) */
+    const uint8_t* mapq;      /* [n_reads]    Read::quality (MAPQ); NULL if no filter */
+    const uint32_t* seq_len;  /* [n_reads]    Read::seq_length (l_qseq); NULL if no filter */
+} gds_reads;
+
+/* Pre-filter.  Replaces BamApi::should_be_filtered_out (bam_api.cpp:311-332) and the amplicon
+ * table built by set_amplicon_filter (bam_api.cpp:53-95).  n_amplicons == 0 means
+ * AmpliconBehaviour::IGNORE; otherwise FILTER.  Amplicon bounds are inclusive (amplicon.cpp:5-7).
+ * Host arrays. */
+typedef struct {
+    uint32_t min_seq_length; /* -l, BamApiConfig::min_seq_length */
+    uint32_t min_mapq;       /* -q, BamApiConfig::min_mapq */
+    uint32_t n_amplicons;
+    const uint32_t* amp_start;
+    const uint32_t* amp_end;
+} gds_filter;
+
+/* Deterministic schedule knobs.  Zero-initialised = defaults (64, 150, 1, 0). */
+typedef struct {
+    uint32_t gr_interval_min;
+    uint32_t gr_levels_pct;
+    uint32_t gr_relabel_pct;
+    uint32_t max_rounds;
+} gds_params;
+
+/* Results.  Buffers are caller-owned and optional (NULL = not wanted). */
+typedef struct {
+    /* ---- buffers ---- */
+    uint32_t* kept_bitmap;   /* [ceil(n_filtered/32)] bit i = post-filter read i kept
+                                (quasi_mcp_cpu_max_flow_solver.cpp:89-100) */
+    uint8_t* pair_pass;      /* [n_reads/2] 1 = pair survived the filter */
+    uint64_t* filt_off;      /* [n_samples+1] HOST: post-filter read offsets per sample */
+    uint32_t* cov_capped;    /* [n_nodes] min(cov, M) of the position right of each node */
+    int32_t* demand;         /* [n_nodes] create_demand_function (…cpu_max_flow_solver.cpp:75-87) */
+    /* ---- scalars ---- */
+    uint64_t n_reads_in, n_filtered, n_kept, n_bundles;
+    uint32_t n_nodes, n_components;
+    int64_t fstar;           /* closed form: sum of source capacities */
+    int64_t flow_value;      /* sink inflow reached by the solve (== fstar) */
+    uint64_t rounds_total, rounds_max, pushes, relabels, global_relabels, bfs_levels, max_frontier;
+    uint64_t verify_violations; /* GDS_VERIFY: positions with min(cov_out,M) != min(cov_in,M) */
+    uint32_t key_bits, sort_passes;
+    /* device-event milliseconds per phase */
+    float ms_h2d, ms_filter, ms_graph, ms_maxflow, ms_select, ms_verify, ms_d2h, ms_total;
+} gds_result;
+
+/* lifecycle: one context per host thread / per GPU; device arenas grow-only and are reused
+ * across calls (the reference re-enters one solver instance 5x, coverage_tester.cpp:28-43) */
+int gds_create(int device, gds_ctx** out);
+void gds_destroy(gds_ctx* ctx);
+const char* gds_last_error(const gds_ctx* ctx);
+int gds_abi_version(void);
+/* run all work on this cudaStream_t (as void*); NULL = the context's own stream */
+int gds_set_stream(gds_ctx* ctx, void* cuda_stream);
+
+/* The whole hot path.  Replaces QuasiMcpCpuMaxFlowSolver::solve
+ * (quasi_mcp_cpu_max_flow_solver.cpp:11-28) and QuasiMcpCudaMaxFlowSolver::solve
+ * (quasi_mcp_cuda_max_flow_solver.cu:319-435) plus the filter of BamApi::read_bam. */
+int gds_solve(gds_ctx* ctx, const gds_reads* reads, const gds_filter* filter /* NULL = none */,
+              uint32_t max_coverage, const gds_params* params /* NULL = defaults */,
+              uint32_t flags, gds_result* out);
+
+/* Expand a HOST bitmap into ascending indices (qmcp::Solution order).  Returns count. */
+uint64_t gds_bitmap_to_indices(const uint32_t* bitmap, uint64_t n_bits, uint64_t* indices,
+                               uint64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
