@@ -1,0 +1,2 @@
+/* stand-in, see sam.h */
+#include "sam.h"

@@ -1,0 +1,220 @@
+"""GPU parity tests proper: every call goes through the C ABI (include/gds.h) and is compared
+with the CPU oracle on the same seeded inputs — bit-exact for F*, demand vector, capped coverage,
+kept bitmap (deterministic schedule) and even the round count."""
+import numpy as np
+import pytest
+
+from conftest import PRM
+
+pytestmark = pytest.mark.gpu
+
+
+def assert_parity(O, r, s, e, ref_lens, read_off, M, prm=PRM):
+    bm, st, dem, cov = O.sync_solve(s, e, ref_lens, read_off, M, params=prm, want_vectors=True)
+    assert r.fstar == st.fstar == r.flow_value == st.flow_value
+    assert np.array_equal(r.demand, dem)
+    assert np.array_equal(r.cov_capped, np.minimum(cov, M))
+    assert r.n_bundles == st.n_bundles and r.n_components == st.n_components
+    assert r.n_kept == st.n_kept
+    assert np.array_equal(r.kept_bitmap, bm), "kept bitmap differs from the oracle"
+    assert r.rounds_total == st.rounds_total and r.relabels == st.relabels
+    assert r.pushes == st.pushes and r.bfs_levels == st.bfs_levels
+    assert r.verify_violations == 0
+    return st
+
+
+def test_small_example(solver, O):
+    ex = O.SMALL_EXAMPLE
+    r = solver.solve(ex["start"], ex["end"], ex["L"], ex["M"], params=PRM, verify=True,
+                     want_vectors=True)
+    assert r.fstar == 5 and r.n_kept == 14
+    assert r.demand.tolist() == [-3, -1, 0, 0, 0, 1, -1, 0, 0, 0, 1, 3]
+    assert r.cov_capped.tolist() == [3, 4, 4, 4, 4, 3, 4, 4, 4, 4, 3, 0]
+    assert_parity(O, r, ex["start"], ex["end"], [ex["L"]], [0, 16], ex["M"])
+
+
+def test_fuzz_ragged_batches(solver, O):
+    rng = np.random.default_rng(7)
+    for it in range(120):
+        ns = int(rng.integers(1, 6))
+        Ls = rng.integers(1, 400, size=ns).astype(np.uint32)
+        ss, ee, off = [], [], [0]
+        for L in Ls:
+            n = 2 * int(rng.integers(0, 300))  # empty samples happen
+            mode = int(rng.integers(0, 3))
+            if mode == 0:
+                s = rng.integers(0, L, size=n); ln = rng.integers(1, max(2, L // 2 + 1), size=n)
+            elif mode == 1:
+                s = rng.integers(0, max(1, L // 3), size=n); ln = rng.integers(1, 6, size=n)
+            else:
+                s = rng.integers(0, L, size=n); ln = np.full(n, rng.integers(1, 30))
+            e = np.minimum(s + ln - 1, L - 1)
+            ss.append(s); ee.append(e); off.append(off[-1] + n)
+        s = np.concatenate(ss).astype(np.uint32); e = np.concatenate(ee).astype(np.uint32)
+        M = int(rng.integers(1, 12))
+        prm = (int(rng.integers(1, 100)), int(rng.integers(0, 300)), int(rng.integers(0, 5)), 0)
+        off = np.array(off, np.uint64)
+        r = solver.solve(s, e, Ls, M, read_off=off, params=prm, verify=True, want_vectors=True)
+        assert_parity(O, r, s, e, Ls, off, M, prm)
+
+
+@pytest.mark.parametrize("name,pairs,M,shape", [
+    ("c3", 50_000, 100, "uniform"), ("c1", 500_000, 100, "uniform"),
+    ("ref_uniform", 1_000_000, 1000, "uniform"), ("ref_low_sides", 1_000_000, 8000, "low_sides"),
+    ("ref_hole", 1_000_000, 8000, "hole"), ("ref_zero_sides", 1_000_000, 8000, "zero_sides")])
+def test_configs_and_reference_shapes_full_size(solver, O, name, pairs, M, shape):
+    # BASELINE configs C1, C3 and the reference's own 4 random cases (coverage_tester.cpp:120-175)
+    s, e, q, l = O.gen_reads(12345, pairs, 30_000, 150, shape)
+    r = solver.solve(s, e, 30_000, M, params=PRM, verify=True, want_vectors=True)
+    st = assert_parity(O, r, s, e, [30_000], [0, len(s)], M)
+    # the reference's only assertion (is_out_cover_valid), from the bitmap on the host
+    mask = O.bitmap_to_mask(r.kept_bitmap, len(s))
+    cin = O.coverage_fast(s, e, 30_000); cout = O.coverage_fast(s, e, 30_000, mask)
+    assert np.all(np.minimum(cin, M) <= cout)
+    if name == "c3":  # optimality vs the mcp-cpu objective (greedy multicover == min-cost optimum)
+        _, nopt = O.greedy_multicover(s, e, 30_000, M)
+        assert nopt <= r.n_kept <= 1.05 * nopt
+    assert st.fstar == {"c3": 100, "c1": 100, "ref_uniform": 1000}.get(name, st.fstar)
+
+
+def test_variable_lengths_64bit_keys_and_wide_nodes(solver, O):
+    # lengths spread over 20 bits + 2^21 nodes -> key wider than 32 bits (u64 sort path)
+    rng = np.random.default_rng(5)
+    L = 2_000_000
+    n = 40_000
+    s = rng.integers(0, L - 1_000_001, size=n).astype(np.uint32)
+    ln = rng.integers(1, 1_000_000, size=n)
+    e = (s + ln - 1).astype(np.uint32)
+    r = solver.solve(s, e, L, 7, params=PRM, verify=True, want_vectors=True)
+    assert r.key_bits > 32
+    assert_parity(O, r, s, e, [L], [0, n], 7)
+
+
+def test_batch_of_samples(solver, O):
+    parts = [O.gen_reads(12345 + k, 100_000, 30_000, 150) for k in range(6)]
+    s = np.concatenate([p[0] for p in parts]); e = np.concatenate([p[1] for p in parts])
+    off = np.arange(7, dtype=np.uint64) * 200_000
+    r = solver.solve(s, e, [30_000] * 6, 100, read_off=off, params=PRM, verify=True,
+                     want_vectors=True)
+    assert r.n_components == 6
+    assert_parity(O, r, s, e, [30_000] * 6, off, 100)
+    # each sample's slice equals its stand-alone solve (sharding never changes results)
+    mask = O.bitmap_to_mask(r.kept_bitmap, len(s))
+    r0 = solver.solve(parts[3][0], parts[3][1], 30_000, 100, params=PRM)
+    assert np.array_equal(O.bitmap_to_mask(r0.kept_bitmap, 200_000), mask[600_000:800_000])
+
+
+def test_zero_coverage_cuts_make_components(solver, O):
+    # three islands of reads separated by uncovered stretches -> 3 components (K4)
+    parts = []
+    for lo in (0, 10_000, 25_000):
+        s, e, q, l = O.gen_reads(lo + 1, 4_000, 4_000, 100)
+        parts.append((s + lo, e + lo))
+    s = np.concatenate([p[0] for p in parts]).astype(np.uint32)
+    e = np.concatenate([p[1] for p in parts]).astype(np.uint32)
+    r = solver.solve(s, e, 30_000, 50, params=PRM, verify=True, want_vectors=True)
+    assert r.n_components == 3
+    assert_parity(O, r, s, e, [30_000], [0, len(s)], 50)
+
+
+def test_filter_path_c2_small(solver, O):
+    # config 2 at reduced size: -l 90 -q 30 + synthetic ARTIC BED/TSV, FILTER mode
+    bed, tsv = O.artic_scheme()
+    a0, a1 = O.parse_amplicons(bed, tsv)
+    s, e, q, l = O.gen_reads_amplicon(12345, 250_000, 30_000, a0, a1)
+    for filt in (dict(min_len=90, min_mapq=30, amp_start=a0, amp_end=a1),
+                 dict(min_len=90, min_mapq=30), dict(min_len=0, min_mapq=0, amp_start=a0, amp_end=a1)):
+        r = solver.solve(s, e, 30_000, 100, mapq=q.astype(np.uint8), seq_len=l, filt=filt,
+                         params=PRM, verify=True, want_vectors=True)
+        pp, kept = O.filter_pairs(s, e, q, l, filt["min_len"], filt["min_mapq"],
+                                  filt.get("amp_start"), filt.get("amp_end"))
+        assert np.array_equal(r.pair_pass, pp) and r.n_filtered == kept
+        assert r.filt_off.tolist() == [0, kept]
+        mask = np.repeat(pp, 2).astype(bool)
+        fs, fe = s[mask].copy(), e[mask].copy()
+        assert_parity(O, r, fs, fe, [30_000], [0, kept], 100)
+
+
+def test_filter_on_batches_keeps_sample_offsets(solver, O):
+    bed, tsv = O.artic_scheme()
+    a0, a1 = O.parse_amplicons(bed, tsv)
+    parts = [O.gen_reads_amplicon(50 + k, 20_000 + 1000 * k, 30_000, a0, a1) for k in range(3)]
+    s, e, q, l = [np.concatenate([p[i] for p in parts]) for i in range(4)]
+    off = np.cumsum([0] + [len(p[0]) for p in parts]).astype(np.uint64)
+    filt = dict(min_len=90, min_mapq=30, amp_start=a0, amp_end=a1)
+    r = solver.solve(s, e, [30_000] * 3, 40, read_off=off, mapq=q.astype(np.uint8), seq_len=l,
+                     filt=filt, params=PRM, verify=True, want_vectors=True)
+    pp, kept = O.filter_pairs(s, e, q, l, 90, 30, a0, a1)
+    mask = np.repeat(pp, 2).astype(bool)
+    foff = [0] + [int(mask[:int(o)].sum()) for o in off[1:]]
+    assert r.filt_off.tolist() == foff
+    assert_parity(O, r, s[mask].copy(), e[mask].copy(), [30_000] * 3, np.array(foff, np.uint64), 40)
+
+
+def test_edge_cases(solver, O, pkg):
+    # no reads at all
+    z = np.zeros(0, np.uint32)
+    r = solver.solve(z, z, 100, 5, params=PRM, verify=True, want_vectors=True)
+    assert r.n_kept == 0 and r.fstar == 0 and r.n_components == 0 and not r.demand.any()
+    # one read, M larger than any coverage: keep everything
+    s = np.array([3, 3, 3, 7], np.uint32); e = np.array([9, 9, 9, 7], np.uint32)
+    r = solver.solve(s, e, 12, 1000, params=PRM, verify=True, want_vectors=True)
+    assert r.n_kept == 4
+    assert_parity(O, r, s, e, [12], [0, 4], 1000)
+    # M = 0: nothing is required, nothing is kept
+    r = solver.solve(s, e, 12, 0, params=PRM, verify=True)
+    assert r.n_kept == 0 and r.fstar == 0
+    # read touching both ends of the reference; L = 1
+    r = solver.solve(np.array([0], np.uint32), np.array([0], np.uint32), 1, 1, params=PRM,
+                     verify=True, want_vectors=True)
+    assert r.n_kept == 1 and r.demand.tolist() == [-1, 1]
+    # all reads identical (one bundle of multiplicity 5000), M = 17 -> lowest 17 indices kept
+    s = np.full(5000, 10, np.uint32); e = np.full(5000, 60, np.uint32)
+    r = solver.solve(s, e, 100, 17, params=PRM, verify=True)
+    assert r.n_bundles == 1 and pkg.Solver.bitmap_to_indices(r.kept_bitmap, 5000).tolist() == \
+        list(range(17))
+    # out-of-range coordinates are rejected, not clamped (reference would write out of bounds)
+    with pytest.raises(pkg.GdsError) as ei:
+        solver.solve(np.array([5], np.uint32), np.array([100], np.uint32), 100, 3)
+    assert ei.value.code == 2
+    with pytest.raises(pkg.GdsError):
+        solver.solve(np.array([9], np.uint32), np.array([4], np.uint32), 100, 3)
+    # the context survives an error
+    ex = O.SMALL_EXAMPLE
+    assert solver.solve(ex["start"], ex["end"], ex["L"], ex["M"]).fstar == 5
+
+
+def test_determinism_and_reuse(solver, O):
+    # same instance re-entered (coverage_tester.cpp:28-43 calls solve 5x on one solver): identical
+    s, e, q, l = O.gen_reads(99, 200_000, 30_000, 150, "hole")
+    ref = None
+    for i in range(4):
+        r = solver.solve(s, e, 30_000, 1500, params=PRM)
+        if ref is None:
+            ref = r.kept_bitmap.copy()
+        assert np.array_equal(ref, r.kept_bitmap)
+        ex = O.SMALL_EXAMPLE  # interleave a different problem size
+        assert solver.solve(ex["start"], ex["end"], ex["L"], ex["M"]).n_kept == 14
+
+
+def test_find_pairs_flag(solver, O):
+    s, e, q, l = O.gen_reads(4, 50_000, 30_000, 150)
+    r1 = solver.solve(s, e, 30_000, 60, params=PRM)
+    r2 = solver.solve(s, e, 30_000, 60, params=PRM, find_pairs=True)
+    assert np.array_equal(O.find_pairs_bitmap(r1.kept_bitmap, len(s)), r2.kept_bitmap)
+
+
+def test_c4_full_size_properties(solver, O):
+    # BASELINE config 4: 50M reads / 5 Mb / M=500.  Size-independent properties at full size:
+    # F* closed form, sink inflow == F*, on-device recomputed capped coverage equals the input's,
+    # n_kept == total bundle flow; plus bit-exact bitmap against the oracle's replay.
+    s, e, q, l = O.gen_reads(12345, 25_000_000, 5_000_000, 150)
+    r = solver.solve(s, e, 5_000_000, 500, params=PRM, verify=True, want_vectors=True)
+    assert r.fstar == 500 == r.flow_value and r.verify_violations == 0
+    assert int(np.maximum(0, -r.demand.astype(np.int64)).sum()) == 500
+    assert int(r.demand.astype(np.int64).sum()) == 0
+    assert abs(r.n_kept - 500 * 5_000_000 / 150) / r.n_kept < 0.001  # ~ M*L/R, the minimum
+    mask_bits = int(np.unpackbits(r.kept_bitmap.view(np.uint8)).sum())
+    assert mask_bits == r.n_kept
+    bm, st = O.sync_solve(s, e, [5_000_000], [0, len(s)], 500, params=PRM)
+    assert np.array_equal(bm, r.kept_bitmap) and st.rounds_total == r.rounds_total
