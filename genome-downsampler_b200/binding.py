@@ -8,12 +8,13 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-GDS_FLAGS = dict(INPUT_ON_DEVICE=1, OUTPUT_ON_DEVICE=2, VERIFY=4, FIND_PAIRS=8, NO_SOLVE=16)
+GDS_FLAGS = dict(INPUT_ON_DEVICE=1, OUTPUT_ON_DEVICE=2, VERIFY=4, FIND_PAIRS=8, NO_SOLVE=16,
+                 PROFILE_KERNELS=32)
 _ERR = {1: "GDS_ERR_ARG", 2: "GDS_ERR_RANGE", 3: "GDS_ERR_CUDA", 4: "GDS_ERR_NOMEM",
         5: "GDS_ERR_NOCONVERGE"}
 
 ENTRY_POINTS = ["gds_abi_version", "gds_create", "gds_destroy", "gds_last_error", "gds_set_stream",
-                "gds_solve", "gds_bitmap_to_indices"]
+                "gds_solve", "gds_kernel_profile", "gds_bitmap_to_indices"]
 
 
 class GdsError(RuntimeError):
@@ -38,6 +39,11 @@ class _Params(C.Structure):
                 ("gr_relabel_pct", C.c_uint32), ("max_rounds", C.c_uint32)]
 
 
+class _KStat(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("ms", C.c_float), ("launches", C.c_uint32),
+                ("bytes", C.c_uint64)]
+
+
 class _Result(C.Structure):
     _fields_ = [("kept_bitmap", C.c_void_p), ("pair_pass", C.c_void_p), ("filt_off", C.c_void_p),
                 ("cov_capped", C.c_void_p), ("demand", C.c_void_p),
@@ -48,7 +54,7 @@ class _Result(C.Structure):
                 ("relabels", C.c_uint64), ("global_relabels", C.c_uint64),
                 ("bfs_levels", C.c_uint64), ("max_frontier", C.c_uint64),
                 ("verify_violations", C.c_uint64), ("key_bits", C.c_uint32),
-                ("sort_passes", C.c_uint32),
+                ("sort_passes", C.c_uint32), ("kernel_launches", C.c_uint64),
                 ("ms_h2d", C.c_float), ("ms_filter", C.c_float), ("ms_graph", C.c_float),
                 ("ms_maxflow", C.c_float), ("ms_select", C.c_float), ("ms_verify", C.c_float),
                 ("ms_d2h", C.c_float), ("ms_total", C.c_float)]
@@ -87,6 +93,8 @@ def load_library():
     L.gds_solve.argtypes = [C.c_void_p, C.POINTER(_Reads), C.POINTER(_Filter), C.c_uint32,
                             C.POINTER(_Params), C.c_uint32, C.POINTER(_Result)]
     L.gds_solve.restype = C.c_int
+    L.gds_kernel_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    L.gds_kernel_profile.restype = C.c_uint32
     L.gds_bitmap_to_indices.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
     L.gds_bitmap_to_indices.restype = C.c_uint64
     _LIB = L
@@ -129,6 +137,13 @@ class Solver:
     def set_stream(self, cuda_stream_ptr):
         self._lib.gds_set_stream(self._h, C.c_void_p(cuda_stream_ptr))
 
+    def kernel_profile(self):
+        """[{name, ms, launches, bytes}] of the last call made with profile=True."""
+        buf = (_KStat * 64)()
+        n = self._lib.gds_kernel_profile(self._h, buf, 64)
+        return [dict(name=buf[i].name.decode(), ms=float(buf[i].ms), launches=int(buf[i].launches),
+                     bytes=int(buf[i].bytes)) for i in range(min(n, 64))]
+
     def _check(self, rc):
         if rc != 0:
             raise GdsError(rc, self._lib.gds_last_error(self._h).decode())
@@ -136,7 +151,7 @@ class Solver:
     # ------------------------------------------------------------------ host-buffer path
     def solve(self, start, end, ref_len, max_coverage, read_off=None, mapq=None, seq_len=None,
               filt=None, params=None, verify=False, find_pairs=False, no_solve=False,
-              want_vectors=False):
+              want_vectors=False, profile=False):
         """Host numpy arrays in, host numpy arrays out (copies happen inside the C call).
 
         filt = dict(min_len=, min_mapq=, amp_start=None, amp_end=None) or None.
@@ -172,7 +187,8 @@ class Solver:
         dem = np.zeros(nn, np.int32) if want_vectors else None
         res.kept_bitmap, res.pair_pass = _ptr(bitmap), _ptr(pair_pass)
         res.filt_off, res.cov_capped, res.demand = _ptr(filt_off), _ptr(cov), _ptr(dem)
-        flags = (4 if verify else 0) | (8 if find_pairs else 0) | (16 if no_solve else 0)
+        flags = (4 if verify else 0) | (8 if find_pairs else 0) | (16 if no_solve else 0) | \
+                (32 if profile else 0)
         prm = _Params(*params) if params is not None else None
         rc = self._lib.gds_solve(self._h, C.byref(rd), C.byref(fl) if fl is not None else None,
                                  int(max_coverage), C.byref(prm) if prm is not None else None,
@@ -191,8 +207,11 @@ class Solver:
     # ------------------------------------------------------------------ device-pointer path
     def solve_device(self, start_ptr, end_ptr, n_reads, ref_len, max_coverage, bitmap_ptr,
                      read_off=None, mapq_ptr=None, seq_len_ptr=None, filt=None, params=None,
-                     verify=False, find_pairs=False, pair_pass_ptr=None):
-        """Inputs and the bitmap already live on the device (raw pointers, e.g. tensor.data_ptr())."""
+                     verify=False, find_pairs=False, pair_pass_ptr=None, profile=False,
+                     input_on_device=True):
+        """Raw-pointer path.  The bitmap (and pair_pass) are device pointers; the reads are device
+        pointers too (tensor.data_ptr()) unless input_on_device=False, in which case they are
+        HOST pointers (ideally pinned) and the library does the host->device copies itself."""
         ref_len = np.atleast_1d(np.ascontiguousarray(ref_len, np.uint32))
         ns = len(ref_len)
         if read_off is None:
@@ -214,7 +233,8 @@ class Solver:
         res.kept_bitmap = bitmap_ptr
         res.pair_pass = pair_pass_ptr
         res.filt_off = _ptr(filt_off)
-        flags = 1 | 2 | (4 if verify else 0) | (8 if find_pairs else 0)
+        flags = (1 if input_on_device else 0) | 2 | (4 if verify else 0) | \
+                (8 if find_pairs else 0) | (32 if profile else 0)
         prm = _Params(*params) if params is not None else None
         rc = self._lib.gds_solve(self._h, C.byref(rd), C.byref(fl) if fl is not None else None,
                                  int(max_coverage), C.byref(prm) if prm is not None else None,

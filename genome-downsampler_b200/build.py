@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libgds_b200.so")
 HOST_BIN = os.path.join(HERE, "gds_host_test")
+HOST_LIB = os.path.join(HERE, "libgds_host.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -51,12 +52,18 @@ def build_host(force=False):
     cpps = [s for s in srcs if s.endswith(".cpp")]
     if not cpps:
         return None
-    if not force and not _newer(HOST_BIN, srcs + [LIB]):
+    if not force and not _newer(HOST_BIN, srcs + [LIB]) and not _newer(HOST_LIB, srcs + [LIB]):
         return HOST_BIN
-    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"),
-           "-I" + os.path.join(hdir, "include"), "-o", HOST_BIN] + cpps + \
-          ["-L" + HERE, "-lgds_b200", "-Wl,-rpath,$ORIGIN"]
-    subprocess.check_call(cmd)
+    # the system g++ (the image's CXX wrapper links libstdc++ statically, which must not be
+    # dlopen()ed into a process that already has libstdc++)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    common = [cxx, "-O2", "-std=c++17", "-Wall", "-fPIC", "-I" + os.path.join(ROOT, "include"),
+              "-I" + os.path.join(hdir, "include")]
+    link = ["-L" + HERE, "-lgds_b200", "-Wl,-rpath,$ORIGIN"]
+    lib_srcs = [s for s in cpps if not s.endswith("host_test_main.cpp")]
+    bin_srcs = [s for s in cpps if not s.endswith("host_c_api.cpp")]
+    subprocess.check_call(common + ["-shared", "-o", HOST_LIB] + lib_srcs + link)
+    subprocess.check_call(common + ["-o", HOST_BIN] + bin_srcs + link)
     return HOST_BIN
 
 

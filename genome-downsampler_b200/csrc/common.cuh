@@ -5,6 +5,7 @@
 
 #include <cstdio>
 #include <string>
+#include <vector>
 
 namespace gds {
 
@@ -24,7 +25,71 @@ struct CudaFail {
         if (_e != cudaSuccess) throw gds::CudaFail{_e, #call, __FILE__, __LINE__}; \
     } while (0)
 
-#define GDS_KERNEL_CHECK() GDS_CUDA(cudaGetLastError())
+// follows every kernel launch: checks the launch and counts it (gds_result.kernel_launches)
+#define GDS_KERNEL_CHECK()            \
+    do {                              \
+        gds::count_launch();          \
+        GDS_CUDA(cudaGetLastError()); \
+    } while (0)
+inline unsigned long long& launch_counter() {
+    static thread_local unsigned long long n = 0;
+    return n;
+}
+inline void count_launch() { ++launch_counter(); }
+
+// Per-launch accounting.  Every kernel launch sits inside a KScope: it always counts the launch
+// and, when profiling is on (GDS_PROFILE_KERNELS), brackets it with CUDA events on the launching
+// stream so bench.py can report per-kernel time and achieved bytes/s measured live.
+struct KRec {
+    const char* name;
+    unsigned long long bytes;
+    cudaEvent_t e0, e1;
+};
+struct Profiler {
+    bool on = false;
+    unsigned long long launches = 0;
+    std::vector<KRec> recs;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    cudaEvent_t ev() {
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            pool.push_back(e);
+        }
+        return pool[used++];
+    }
+    void reset() {
+        recs.clear();
+        used = 0;
+        launches = 0;
+    }
+    void release() {
+        for (cudaEvent_t e : pool) cudaEventDestroy(e);
+        pool.clear();
+    }
+};
+inline Profiler*& cur_prof() {
+    static thread_local Profiler* p = nullptr;
+    return p;
+}
+struct KScope {
+    cudaStream_t st;
+    cudaEvent_t e1 = nullptr;
+    KScope(const char* name, unsigned long long bytes, cudaStream_t s) : st(s) {
+        Profiler* p = cur_prof();
+        if (!p) return;
+        if (p->on) {
+            KRec r{name, bytes, p->ev(), p->ev()};
+            cudaEventRecord(r.e0, st);
+            e1 = r.e1;
+            p->recs.push_back(r);
+        }
+    }
+    ~KScope() {
+        if (e1) cudaEventRecord(e1, st);
+    }
+};
 
 // Grow-only device buffer (arena slot).  Reused across gds_solve calls.
 struct DevBuf {

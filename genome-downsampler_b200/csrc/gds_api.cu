@@ -46,6 +46,7 @@ struct gds_ctx {
     DevBuf qF, qT, qN, work_counter, comp_stats;
     DevBuf bitmap, cov_tmp, dem_tmp, vdiff, vexcl;
     bool mf_attr_set = false;
+    Profiler prof;
 
     void release_all() {
         DevBuf* all[] = {&in_start, &in_end, &in_mapq, &in_len, &off_d, &reflen_d, &base_d, &foff_d,
@@ -117,16 +118,22 @@ void build_bundles(gds_ctx* c, const uint32_t* S, const uint32_t* E, const uint6
     uint32_t n_tiles = (uint32_t)((N + kHeadTile - 1) / kHeadTile);
     uint32_t* tc = c->tile_counts.get<uint32_t>(n_tiles + 1);
     GDS_CUDA(cudaMemsetAsync(tc + n_tiles, 0, sizeof(uint32_t), st));
-    k_heads_count<K><<<n_tiles, kHeadThreads, 0, st>>>(keys, N, tc);
-    GDS_KERNEL_CHECK();
+    {
+        KScope ks("heads_count", sizeof(K) * (unsigned long long)N, st);
+        k_heads_count<K><<<n_tiles, kHeadThreads, 0, st>>>(keys, N, tc);
+        GDS_KERNEL_CHECK();
+    }
     exclusive_scan_u32(tc, tc, n_tiles + 1, c->scan, st);
     uint32_t B = 0;
     d2h_sync(c, &B, tc + n_tiles, 1);
     B_out = B;
     uint32_t* b_first = c->b_first.get<uint32_t>(B + 1);
     K* b_key = c->b_key.get<K>(B + 1);
-    k_heads_write<K><<<n_tiles, kHeadThreads, 0, st>>>(keys, N, tc, b_first, b_key);
-    GDS_KERNEL_CHECK();
+    {
+        KScope ks("heads_write", sizeof(K) * (unsigned long long)N + (4ull + sizeof(K)) * B, st);
+        k_heads_write<K><<<n_tiles, kHeadThreads, 0, st>>>(keys, N, tc, b_first, b_key);
+        GDS_KERNEL_CHECK();
+    }
     uint32_t* b_s = c->b_s.get<uint32_t>(B + 1);
     uint32_t* b_t = c->b_t.get<uint32_t>(B + 1);
     uint32_t* b_mult = c->b_mult.get<uint32_t>(B + 1);
@@ -137,10 +144,13 @@ void build_bundles(gds_ctx* c, const uint32_t* S, const uint32_t* E, const uint6
     GDS_CUDA(cudaMemsetAsync(outdeg, 0, (n_nodes + 1) * sizeof(uint32_t), st));
     GDS_CUDA(cudaMemsetAsync(indeg, 0, (n_nodes + 1) * sizeof(uint32_t), st));
     if (B) {
-        k_bundle_fill<K><<<div_up(B, 256), 256, 0, st>>>(b_key, b_first, B, (uint32_t)N, lenbits,
-                                                         minlen, b_s, b_t, b_mult, diff, outdeg,
-                                                         indeg);
-        GDS_KERNEL_CHECK();
+        {
+            KScope ks("bundle_fill", (sizeof(K) + 4ull + 12ull + 16ull) * B, st);
+            k_bundle_fill<K><<<div_up(B, 256), 256, 0, st>>>(b_key, b_first, B, (uint32_t)N, lenbits,
+            minlen, b_s, b_t, b_mult, diff, outdeg,
+            indeg);
+            GDS_KERNEL_CHECK();
+        }
     }
 }
 
@@ -175,6 +185,7 @@ extern "C" void gds_destroy(gds_ctx* c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     c->release_all();
+    c->prof.release();
     for (int i = 0; i < EV_COUNT; ++i)
         if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     if (c->pinned) cudaFreeHost(c->pinned);
@@ -188,6 +199,33 @@ extern "C" int gds_set_stream(gds_ctx* c, void* cuda_stream) {
     if (!c) return GDS_ERR_ARG;
     c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
     return GDS_OK;
+}
+
+extern "C" uint32_t gds_kernel_profile(gds_ctx* c, gds_kernel_stat* outp, uint32_t cap) {
+    // aggregates the per-launch event pairs of the last GDS_PROFILE_KERNELS call by kernel name
+    if (!c) return 0;
+    std::vector<gds_kernel_stat> agg;
+    for (const KRec& r : c->prof.recs) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, r.e0, r.e1) != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        gds_kernel_stat* hit = nullptr;
+        for (auto& a : agg)
+            if (!strncmp(a.name, r.name, sizeof a.name)) hit = &a;
+        if (!hit) {
+            gds_kernel_stat z{};
+            strncpy(z.name, r.name, sizeof z.name - 1);
+            agg.push_back(z);
+            hit = &agg.back();
+        }
+        hit->ms += t;
+        hit->bytes += r.bytes;
+        hit->launches += 1;
+    }
+    for (uint32_t i = 0; i < agg.size() && i < cap && outp; ++i) outp[i] = agg[i];
+    return (uint32_t)agg.size();
 }
 
 extern "C" uint64_t gds_bitmap_to_indices(const uint32_t* bitmap, uint64_t n_bits,
@@ -263,6 +301,13 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
     out->n_reads_in = P;
     out->n_nodes = n_nodes;
 
+    struct ProfGuard {
+        ProfGuard(Profiler* p) { cur_prof() = p; }
+        ~ProfGuard() { cur_prof() = nullptr; }
+    } prof_guard(&c->prof);
+    c->prof.reset();
+    c->prof.on = (flags & GDS_PROFILE_KERNELS) != 0;
+    const unsigned long long launches0 = launch_counter();
     try {
         GDS_CUDA(cudaSetDevice(c->device));
         cudaStream_t st = c->stream;
@@ -342,18 +387,27 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
                                                       : c->pair_pass.get<uint8_t>(n_pairs);
             uint32_t* f32 = c->flag32.get<uint32_t>(n_pairs);
             int grid = std::min<long long>(div_up(n_pairs, 256), kNumSMs * 16);
-            k_filter_flags<<<grid, 256, 0, st>>>(dS, dE, dQ, dLen, n_pairs, fa, pp, f32);
-            GDS_KERNEL_CHECK();
+            {
+                KScope ks("filter_flags", 13ull * P + 5ull * n_pairs, st);
+                k_filter_flags<<<grid, 256, 0, st>>>(dS, dE, dQ, dLen, n_pairs, fa, pp, f32);
+                GDS_KERNEL_CHECK();
+            }
             exclusive_scan_u32(f32, f32, n_pairs, c->scan, st);
             uint64_t* foff = c->foff_d.get<uint64_t>(ns + 1);
-            k_filter_offsets<<<div_up(ns + 1, 128), 128, 0, st>>>(off_d, ns, f32, pp, n_pairs, foff);
-            GDS_KERNEL_CHECK();
+            {
+                KScope ks("filter_offsets", 16ull * (ns + 1), st);
+                k_filter_offsets<<<div_up(ns + 1, 128), 128, 0, st>>>(off_d, ns, f32, pp, n_pairs, foff);
+                GDS_KERNEL_CHECK();
+            }
             d2h_sync(c, foff_host.data(), foff, ns + 1);
             N = foff_host[ns];
             uint32_t* fS = c->fS.get<uint32_t>(N);
             uint32_t* fE = c->fE.get<uint32_t>(N);
-            k_filter_compact<<<grid, 256, 0, st>>>(dS, dE, pp, f32, n_pairs, fS, fE);
-            GDS_KERNEL_CHECK();
+            {
+                KScope ks("filter_compact", 5ull * n_pairs + 16ull * N, st);
+                k_filter_compact<<<grid, 256, 0, st>>>(dS, dE, pp, f32, n_pairs, fS, fE);
+                GDS_KERNEL_CHECK();
+            }
             S = fS;
             E = fE;
             foff_dev = foff;
@@ -372,8 +426,11 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         const int nodebits = bits_for(n_nodes ? n_nodes - 1 : 0);
         if (N > 0) {
             int grid = std::min<long long>(div_up(N, 256 * 8), kNumSMs * 16);
-            k_validate<<<grid, 256, 0, st>>>(S, E, N, foff_dev, reflen_d, ns, stats);
-            GDS_KERNEL_CHECK();
+            {
+                KScope ks("validate", 8ull * N, st);
+                k_validate<<<grid, 256, 0, st>>>(S, E, N, foff_dev, reflen_d, ns, stats);
+                GDS_KERNEL_CHECK();
+            }
             uint32_t hstats[3];
             d2h_sync(c, hstats, stats, 3);
             if (hstats[2] != 0) {
@@ -428,9 +485,12 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         int32_t* dem_dev = nullptr;
         if (out->cov_capped) cov_dev = out_dev ? out->cov_capped : c->cov_tmp.get<uint32_t>(n_nodes);
         if (out->demand) dem_dev = out_dev ? out->demand : c->dem_tmp.get<int32_t>(n_nodes);
-        k_node_finalize<<<div_up(n_nodes, 256), 256, 0, st>>>(excl, diff, n_nodes, max_coverage, na,
-                                                              cstart, cend, cov_dev, dem_dev, totals);
-        GDS_KERNEL_CHECK();
+        {
+            KScope ks("node_finalize", 44ull * n_nodes, st);
+            k_node_finalize<<<div_up(n_nodes, 256), 256, 0, st>>>(excl, diff, n_nodes, max_coverage, na,
+            cstart, cend, cov_dev, dem_dev, totals);
+            GDS_KERNEL_CHECK();
+        }
         uint32_t* sidx = c->comp_sidx.get<uint32_t>(n_nodes + 1);
         uint32_t* eidx = c->comp_eidx.get<uint32_t>(n_nodes + 1);
         exclusive_scan_u32(cstart, sidx, n_nodes + 1, c->scan, st);
@@ -440,9 +500,12 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         uint32_t* comp_lo = c->comp_lo.get<uint32_t>(n_comp + 1);
         uint32_t* comp_hi = c->comp_hi.get<uint32_t>(n_comp + 1);
         if (n_comp) {
-            k_comp_write<<<div_up(n_nodes, 256), 256, 0, st>>>(cstart, cend, sidx, eidx, n_nodes,
-                                                               comp_lo, comp_hi);
-            GDS_KERNEL_CHECK();
+            {
+                KScope ks("comp_write", 16ull * n_nodes, st);
+                k_comp_write<<<div_up(n_nodes, 256), 256, 0, st>>>(cstart, cend, sidx, eidx, n_nodes,
+                comp_lo, comp_hi);
+                GDS_KERNEL_CHECK();
+            }
         }
         // in-CSR: bundle ids ordered by (end node, start node) = stable sort of ids by b_t
         uint32_t* in_bid = nullptr;
@@ -481,9 +544,12 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
                 c->mf_attr_set = true;
             }
             int grid = std::min<uint32_t>(n_comp, kNumSMs);
-            k_maxflow<<<grid, kMfThreads, sizeof(MfShared), st>>>(na, bg, comp_lo, comp_hi, n_comp,
-                                                                  wc, qF, qT, qN, sp, cstats);
-            GDS_KERNEL_CHECK();
+            {
+                KScope ks("maxflow", 28ull * n_nodes + 24ull * B, st);
+                k_maxflow<<<grid, kMfThreads, sizeof(MfShared), st>>>(na, bg, comp_lo, comp_hi, n_comp,
+                wc, qF, qT, qN, sp, cstats);
+                GDS_KERNEL_CHECK();
+            }
         }
         GDS_CUDA(cudaEventRecord(c->ev[EV_MAXFLOW], st));
 
@@ -494,9 +560,12 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         if (do_solve) {
             GDS_CUDA(cudaMemsetAsync(bm, 0, n_words * 4, st));
             if (B) {
-                k_select<<<div_up(B, 256), 256, 0, st>>>(c->b_first.as<uint32_t>(), f, sorted_idx, B,
-                                                         bm, totals);
-                GDS_KERNEL_CHECK();
+                {
+                    KScope ks("select", 8ull * B + 8ull * N / 32, st);
+                    k_select<<<div_up(B, 256), 256, 0, st>>>(c->b_first.as<uint32_t>(), f, sorted_idx, B,
+                    bm, totals);
+                    GDS_KERNEL_CHECK();
+                }
             }
         }
         GDS_CUDA(cudaEventRecord(c->ev[EV_SELECT], st));
@@ -507,19 +576,28 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             uint32_t* vexcl = c->vexcl.get<uint32_t>(n_nodes + 1);
             GDS_CUDA(cudaMemsetAsync(vdiff, 0, (n_nodes + 1) * 4, st));
             if (n_words) {
-                k_verify_accumulate<<<div_up(n_words, 256), 256, 0, st>>>(bm, S, E, N, foff_dev,
-                                                                          base_d, ns, vdiff);
-                GDS_KERNEL_CHECK();
+                {
+                    KScope ks("verify_accumulate", 4ull * n_words, st);
+                    k_verify_accumulate<<<div_up(n_words, 256), 256, 0, st>>>(bm, S, E, N, foff_dev,
+                    base_d, ns, vdiff);
+                    GDS_KERNEL_CHECK();
+                }
             }
             exclusive_scan_u32(reinterpret_cast<const uint32_t*>(vdiff), vexcl, n_nodes + 1, c->scan,
                                st);
-            k_verify_compare<<<div_up(n_nodes, 256), 256, 0, st>>>(vexcl, vdiff, excl, diff, n_nodes,
-                                                                   max_coverage, totals);
-            GDS_KERNEL_CHECK();
+            {
+                KScope ks("verify_compare", 16ull * n_nodes, st);
+                k_verify_compare<<<div_up(n_nodes, 256), 256, 0, st>>>(vexcl, vdiff, excl, diff, n_nodes,
+                max_coverage, totals);
+                GDS_KERNEL_CHECK();
+            }
         }
         if (do_solve && (flags & GDS_FIND_PAIRS) && n_words) {
-            k_find_pairs<<<div_up(n_words, 256), 256, 0, st>>>(bm, n_words);
-            GDS_KERNEL_CHECK();
+            {
+                KScope ks("find_pairs", 8ull * n_words, st);
+                k_find_pairs<<<div_up(n_words, 256), 256, 0, st>>>(bm, n_words);
+                GDS_KERNEL_CHECK();
+            }
         }
         GDS_CUDA(cudaEventRecord(c->ev[EV_VERIFY], st));
 
@@ -561,6 +639,7 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         out->ms_verify = ms(EV_SELECT, EV_VERIFY);
         out->ms_d2h = ms(EV_VERIFY, EV_END);
         out->ms_total = ms(EV_BEGIN, EV_END);
+        out->kernel_launches = launch_counter() - launches0;
         if (do_solve && (out->flow_value != out->fstar || stuck != 0)) {
             char buf[160];
             snprintf(buf, sizeof buf, "max-flow did not converge: sink inflow %lld, F* %lld, stuck %lld",

@@ -125,20 +125,32 @@ inline int radix_sort_pairs(K* keys_a, uint32_t* vals_a, K* keys_b, uint32_t* va
         int shift = 8 * p;
         const uint32_t* vsrc = (p == 0 && iota_first) ? nullptr : vin;
         if (p == 0 && first_ks) {
-            k_rs_hist<K, KS0><<<n_tiles, kRsThreads, 0, st>>>(*first_ks, n, shift, n_tiles, hist);
-            GDS_KERNEL_CHECK();
+            {
+                KScope ks("rs_hist_reads", 8ull * n, st);
+                k_rs_hist<K, KS0><<<n_tiles, kRsThreads, 0, st>>>(*first_ks, n, shift, n_tiles, hist);
+                GDS_KERNEL_CHECK();
+            }
             exclusive_scan_u32(hist, hist, (size_t)256 * n_tiles, tmp.scan, st);
-            k_rs_scatter<K, KS0><<<n_tiles, kRsThreads, 0, st>>>(*first_ks, vsrc, kout, vout, n,
-                                                                 shift, n_tiles, hist);
-            GDS_KERNEL_CHECK();
+            {
+                KScope ks("rs_scatter_reads", (8ull + sizeof(K) + 4) * n, st);
+                k_rs_scatter<K, KS0><<<n_tiles, kRsThreads, 0, st>>>(*first_ks, vsrc, kout, vout, n,
+                                                                     shift, n_tiles, hist);
+                GDS_KERNEL_CHECK();
+            }
         } else {
             ArrayKeys<K> ak{kin};
-            k_rs_hist<K, ArrayKeys<K>><<<n_tiles, kRsThreads, 0, st>>>(ak, n, shift, n_tiles, hist);
-            GDS_KERNEL_CHECK();
+            {
+                KScope ks("rs_hist", sizeof(K) * (unsigned long long)n, st);
+                k_rs_hist<K, ArrayKeys<K>><<<n_tiles, kRsThreads, 0, st>>>(ak, n, shift, n_tiles, hist);
+                GDS_KERNEL_CHECK();
+            }
             exclusive_scan_u32(hist, hist, (size_t)256 * n_tiles, tmp.scan, st);
-            k_rs_scatter<K, ArrayKeys<K>><<<n_tiles, kRsThreads, 0, st>>>(ak, vsrc, kout, vout, n,
-                                                                          shift, n_tiles, hist);
-            GDS_KERNEL_CHECK();
+            {
+                KScope ks("rs_scatter", (2ull * sizeof(K) + (vsrc ? 8 : 4)) * n, st);
+                k_rs_scatter<K, ArrayKeys<K>><<<n_tiles, kRsThreads, 0, st>>>(ak, vsrc, kout, vout,
+                                                                              n, shift, n_tiles, hist);
+                GDS_KERNEL_CHECK();
+            }
         }
         cur ^= 1;
     }

@@ -77,6 +77,7 @@ struct ScanTemp {
 inline void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, ScanTemp& tmp,
                                cudaStream_t st) {
     if (n == 0) return;
+    KScope ks("scan_u32", 8ull * n, st);  // the whole hierarchical scan counts as one unit
     size_t t1 = (n + kScanTile - 1) / kScanTile;
     if (t1 == 1) {
         k_scan_tiles<<<1, kScanThreads, 0, st>>>(in, out, nullptr, n);

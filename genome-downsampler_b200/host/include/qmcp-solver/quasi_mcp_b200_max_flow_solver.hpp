@@ -1,0 +1,33 @@
+// qmcp::QuasiMcpB200MaxFlowSolver — the new algorithm ("quasi-mcp-b200") behind the reference's
+// Solver interface.  Host-only translation unit: it talks to the device exclusively through the
+// C ABI of include/gds.h (libgds_b200.so).  No CPU fallback: if the library cannot create a
+// device context the solver logs and exits like the reference's CUDA helpers do
+// (libs/qmcp-solver/include/qmcp-solver/cuda_helpers.cuh:13-21).
+#pragma once
+#include <cstdint>
+#include <memory>
+
+#include "gds.h"
+#include "qmcp-solver/solver.hpp"
+
+namespace qmcp {
+
+class QuasiMcpB200MaxFlowSolver : public Solver {
+   public:
+    explicit QuasiMcpB200MaxFlowSolver(int device = 0) : device_(device) {}
+    ~QuasiMcpB200MaxFlowSolver() override;
+    std::unique_ptr<Solution> solve(uint32_t max_coverage, bam_api::BamApi& bam_api) override;
+    bool uses_quality_of_reads() override { return false; }
+
+    // last call's device-side report (flow value, kept count, per-phase milliseconds, ...)
+    const gds_result& last_result() const { return last_; }
+    void set_verify(bool v) { verify_ = v; }
+
+   private:
+    int device_;
+    gds_ctx* ctx_ = nullptr;  // created lazily, reused across solve() calls
+    gds_result last_{};
+    bool verify_ = true;
+};
+
+}  // namespace qmcp

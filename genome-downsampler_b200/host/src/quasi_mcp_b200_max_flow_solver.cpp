@@ -1,0 +1,99 @@
+// Adapter: qmcp::Solver::solve(max_coverage, BamApi&) -> C ABI (include/gds.h) -> ascending
+// kept indices.  Narrowing size_t -> uint32 happens once, here, with range checks.
+#include "qmcp-solver/quasi_mcp_b200_max_flow_solver.hpp"
+
+#include <cstdlib>
+#include <limits>
+
+#include "logging/log.hpp"
+
+namespace qmcp {
+
+QuasiMcpB200MaxFlowSolver::~QuasiMcpB200MaxFlowSolver() {
+    if (ctx_) gds_destroy(ctx_);
+}
+
+std::unique_ptr<Solution> QuasiMcpB200MaxFlowSolver::solve(uint32_t max_coverage,
+                                                           bam_api::BamApi& bam_api) {
+    if (!ctx_ && gds_create(device_, &ctx_) != GDS_OK) {
+        LOG_WITH_LEVEL(logging::ERROR)
+            << "quasi-mcp-b200: no usable CUDA device " << device_ << " (there is no CPU fallback)";
+        std::exit(EXIT_FAILURE);
+    }
+    const bool device_filter = bam_api.has_pending_filter();
+    const bam_api::SOAPairedReads& in =
+        device_filter ? bam_api.unfiltered_soa() : bam_api.get_paired_reads_soa();
+    const uint64_t n = in.get_reads_count();
+    const uint64_t L = in.ref_genome_length;
+    constexpr uint64_t kMax32 = std::numeric_limits<uint32_t>::max();
+    if (L > kMax32 - 4 || n > kMax32 - 1) {
+        LOG_WITH_LEVEL(logging::ERROR) << "quasi-mcp-b200: input beyond 32-bit device limits";
+        std::exit(EXIT_FAILURE);
+    }
+    std::vector<uint32_t> start(n), end(n), seq_len;
+    std::vector<uint8_t> mapq;
+    for (uint64_t i = 0; i < n; ++i) {
+        start[i] = static_cast<uint32_t>(in.start_inds[i]);
+        end[i] = static_cast<uint32_t>(std::min<uint64_t>(in.end_inds[i], kMax32));
+    }
+    uint64_t off[2] = {0, n};
+    uint32_t ref_len = static_cast<uint32_t>(L);
+    gds_reads rd{1, off, &ref_len, start.data(), end.data(), nullptr, nullptr};
+    gds_filter flt{};
+    std::vector<uint32_t> amp_s, amp_e;
+    std::vector<uint8_t> pair_pass;
+    if (device_filter) {
+        seq_len.assign(in.seq_lengths.begin(), in.seq_lengths.end());
+        mapq.resize(n);
+        for (uint64_t i = 0; i < n; ++i) mapq[i] = static_cast<uint8_t>(std::min<uint32_t>(in.qualities[i], 255));
+        rd.mapq = mapq.data();
+        rd.seq_len = seq_len.data();
+        flt.min_seq_length = bam_api.min_seq_length();
+        flt.min_mapq = std::min<uint32_t>(bam_api.min_mapq(), 256);  // > 255 can never pass anyway
+        if (bam_api.amplicon_behaviour() == bam_api::AmpliconBehaviour::FILTER) {
+            for (const auto& a : bam_api.amplicon_set().amplicons) {
+                amp_s.push_back(static_cast<uint32_t>(std::min<uint64_t>(a.start, kMax32)));
+                amp_e.push_back(static_cast<uint32_t>(std::min<uint64_t>(a.end, kMax32)));
+            }
+            if (amp_s.empty()) {  // FILTER with an empty set drops every pair (any_of over nothing)
+                amp_s.push_back(1);
+                amp_e.push_back(0);
+            }
+            flt.n_amplicons = static_cast<uint32_t>(amp_s.size());
+            flt.amp_start = amp_s.data();
+            flt.amp_end = amp_e.data();
+        }
+        pair_pass.assign(n / 2 + 1, 0);
+    }
+    std::vector<uint32_t> bitmap((n + 31) / 32 + 1, 0);
+    last_ = gds_result{};
+    last_.kept_bitmap = bitmap.data();
+    last_.pair_pass = device_filter ? pair_pass.data() : nullptr;
+    int rc = gds_solve(ctx_, &rd, device_filter ? &flt : nullptr, max_coverage, nullptr,
+                       verify_ ? GDS_VERIFY : 0, &last_);
+    last_.kept_bitmap = nullptr;
+    last_.pair_pass = nullptr;
+    if (rc != GDS_OK) {
+        LOG_WITH_LEVEL(logging::ERROR) << "quasi-mcp-b200: " << gds_last_error(ctx_);
+        std::exit(EXIT_FAILURE);
+    }
+    if (verify_ && last_.verify_violations != 0) {
+        LOG_WITH_LEVEL(logging::ERROR) << "quasi-mcp-b200: device verification found "
+                                       << last_.verify_violations << " bad positions";
+        std::exit(EXIT_FAILURE);
+    }
+    if (device_filter) {
+        pair_pass.resize(n / 2);
+        bam_api.apply_pair_filter(pair_pass);  // BamApi now holds the post-filter arrays
+    }
+    auto sol = std::make_unique<Solution>(last_.n_kept);
+    static_assert(sizeof(bam_api::ReadIndex) == sizeof(uint64_t), "ReadIndex must be 64-bit");
+    uint64_t k = gds_bitmap_to_indices(bitmap.data(), last_.n_filtered,
+                                       reinterpret_cast<uint64_t*>(sol->data()), sol->size());
+    sol->resize(std::min<uint64_t>(k, sol->size()));
+    LOG_WITH_LEVEL(logging::DEBUG) << "quasi-mcp-b200: F*=" << last_.fstar << " kept=" << last_.n_kept
+                                   << " rounds=" << last_.rounds_total << " device ms=" << last_.ms_total;
+    return sol;
+}
+
+}  // namespace qmcp

@@ -1,0 +1,74 @@
+// Synthetic paired reads.  Law (not code) of libs/reads-gen/src/reads_gen.cpp:
+//   uniform  (:55-86): first ~ U{0..G-2R}, second ~ U{0..G-R}; order them; if they overlap the
+//                      second is moved to first+R; qualities ~ U{0..max_quality}
+//   weighted (:5-53) : both starts from a discrete distribution over G-R+1 start positions built
+//                      from dist_func on [0,1] (negative weights clamp to 0); if both fall in the
+//                      last 2R bases they are pinned to G-2R and G-R, else overlap is resolved as
+//                      above.
+// Draw order per pair: first, second, quality(first), quality(second).
+#include "reads_gen.hpp"
+
+#include <algorithm>
+#include <vector>
+
+namespace {
+template <typename StartDraw>
+bam_api::AOSPairedReads generate(std::mt19937& gen, bam_api::ReadIndex pairs, bam_api::Index G,
+                                 uint32_t R, int32_t max_quality, bool pin_tail, StartDraw draw) {
+    std::uniform_int_distribution<> quality(0, max_quality);
+    bam_api::AOSPairedReads out;
+    out.ref_genome_length = G;
+    out.reserve(2 * pairs);
+    for (bam_api::ReadIndex p = 0; p < pairs; ++p) {
+        auto [a, b] = draw(gen);
+        if (a > b) std::swap(a, b);
+        if (pin_tail && a > G - 2 * R && b > G - 2 * R) {
+            a = G - 2 * R;
+            b = G - R;
+        } else if (a + R > b) {
+            b = a + R;
+        }
+        uint32_t qa = static_cast<uint32_t>(quality(gen));
+        out.push_back(bam_api::Read(2 * p, a, a + R - 1, qa, R, true));
+        uint32_t qb = static_cast<uint32_t>(quality(gen));
+        out.push_back(bam_api::Read(2 * p + 1, b, b + R - 1, qb, R, false));
+    }
+    return out;
+}
+}  // namespace
+
+bam_api::AOSPairedReads reads_gen::rand_reads_uniform(std::mt19937& generator,
+                                                      bam_api::ReadIndex pairs_count,
+                                                      bam_api::Index genome_length,
+                                                      uint32_t read_length, int32_t max_quality) {
+    std::uniform_int_distribution<> d1(0, static_cast<int32_t>(genome_length - 2 * read_length));
+    std::uniform_int_distribution<> d2(0, static_cast<int32_t>(genome_length - read_length));
+    return generate(generator, pairs_count, genome_length, read_length, max_quality, false,
+                    [&](std::mt19937& g) {
+                        bam_api::Index a = d1(g);
+                        bam_api::Index b = d2(g);
+                        return std::pair<bam_api::Index, bam_api::Index>(a, b);
+                    });
+}
+
+bam_api::AOSPairedReads reads_gen::rand_reads(std::mt19937& generator,
+                                              bam_api::ReadIndex pairs_count,
+                                              bam_api::Index genome_length, uint32_t read_length,
+                                              const std::function<double(double)>& dist_func,
+                                              int32_t max_quality) {
+    const uint32_t n_starts = static_cast<uint32_t>(genome_length - read_length + 1);
+    std::vector<double> w(n_starts);
+    double total = 0;
+    for (uint32_t i = 0; i < n_starts; ++i) {
+        w[i] = std::max(0.0, dist_func(static_cast<double>(i) / static_cast<double>(n_starts - 1)));
+        total += w[i];
+    }
+    for (double& x : w) x /= total;
+    std::discrete_distribution<> dd(w.begin(), w.end());
+    return generate(generator, pairs_count, genome_length, read_length, max_quality, true,
+                    [&](std::mt19937& g) {
+                        bam_api::Index a = dd(g);
+                        bam_api::Index b = dd(g);
+                        return std::pair<bam_api::Index, bam_api::Index>(a, b);
+                    });
+}

@@ -43,7 +43,8 @@ enum {
     GDS_VERIFY = 1u << 2,           /* recompute coverage of the kept set on device and compare */
     GDS_FIND_PAIRS = 1u << 3,       /* also OR each kept read's mate into the bitmap
                                        (BamApi::find_pairs, bam_api.cpp:239-273) */
-    GDS_NO_SOLVE = 1u << 4          /* stop after coverage/demand/graph (K1+K2 only) */
+    GDS_NO_SOLVE = 1u << 4,         /* stop after coverage/demand/graph (K1+K2 only) */
+    GDS_PROFILE_KERNELS = 1u << 5   /* bracket every kernel with CUDA events (gds_kernel_profile) */
 };
 
 typedef struct gds_ctx gds_ctx;
@@ -98,6 +99,7 @@ typedef struct {
     uint64_t rounds_total, rounds_max, pushes, relabels, global_relabels, bfs_levels, max_frontier;
     uint64_t verify_violations; /* GDS_VERIFY: positions with min(cov_out,M) != min(cov_in,M) */
     uint32_t key_bits, sort_passes;
+    uint64_t kernel_launches; /* kernels this call launched (counted at the launch sites) */
     /* device-event milliseconds per phase */
     float ms_h2d, ms_filter, ms_graph, ms_maxflow, ms_select, ms_verify, ms_d2h, ms_total;
 } gds_result;
@@ -117,6 +119,17 @@ int gds_set_stream(gds_ctx* ctx, void* cuda_stream);
 int gds_solve(gds_ctx* ctx, const gds_reads* reads, const gds_filter* filter /* NULL = none */,
               uint32_t max_coverage, const gds_params* params /* NULL = defaults */,
               uint32_t flags, gds_result* out);
+
+/* Per-kernel device time of the last gds_solve that ran with GDS_PROFILE_KERNELS, aggregated by
+ * kernel name: CUDA-event milliseconds, launches, and the algorithmic bytes (once-through reads +
+ * writes) those launches had to move.  Returns the number of distinct kernels. */
+typedef struct {
+    char name[32];
+    float ms;
+    uint32_t launches;
+    uint64_t bytes;
+} gds_kernel_stat;
+uint32_t gds_kernel_profile(gds_ctx* ctx, gds_kernel_stat* out, uint32_t cap);
 
 /* Expand a HOST bitmap into ascending indices (qmcp::Solution order).  Returns count. */
 uint64_t gds_bitmap_to_indices(const uint32_t* bitmap, uint64_t n_bits, uint64_t* indices,
