@@ -1,0 +1,444 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the quasi-MCP downsampling hot path on B200 (one JSON line on stdout).
+
+    python bench.py --gpus N --steps K --warmup W [--workload c5|c4|c1] [--impl reference]
+
+A "step" is one pass of the whole hot path (validate -> bundle sort -> coverage/demand/CSR ->
+component split -> push-relabel max-flow -> kept-read bitmap) over one batch of synthetic reads.
+
+Workloads (BASELINE.json `configs`):
+  c5 (default)  config[4]: batch of independent 30 kb samples, 2 M reads each
+                (reads-gen uniform law, mt19937 seed 12345+k, R=150), MAX_COVERAGE=100.
+                512 samples per GPU; ranks own disjoint sample blocks, no data-path collective,
+                per-sample bitmaps all-gathered over NCCL at the end of every step (weak scaling).
+  c4            config[3]: 50 M reads over one 5 Mb reference, MAX_COVERAGE=500 (single GPU; N>1
+                runs independent replicas with different seeds).
+  c1            config[0]: 1 M reads over 30 kb, MAX_COVERAGE=100.
+
+`value`  = reads/s with the reads already resident in HBM (device-timed with CUDA events on the
+           stream the kernels are launched on, max over ranks).
+`e2e`    = the same metric through the C-ABI call with HOST (pinned) buffers: H2D of start/end and
+           D2H of the kept bitmap inside the timed region.
+`roofline` = the dominant kernel's algorithmic bytes / its CUDA-event duration, measured live in the
+           timed steps (GDS_PROFILE_KERNELS), against MEASURED_PEAKS.json.
+`cpu_baseline` = the oracle port of quasi-mcp-cpu (oracle/, single thread) on a bounded sample.
+
+--impl reference times the reference's CPU algorithm (oracle port; OR-Tools is absent so the
+reference solver itself cannot be built — DESIGN.md §3) on all host threads, same metric/config.
+No part of the product path touches oracle/; there is no CPU fallback (Solver() raises without a GPU).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c5": dict(L=30_000, R=150, pairs=1_000_000, M=100, samples=512, seed=12345,
+               name="config[4]: batch of independent 30 kb samples x 2M reads (reads-gen uniform, "
+                    "seed 12345+k, R=150), MAX_COVERAGE=100"),
+    "c4": dict(L=5_000_000, R=150, pairs=25_000_000, M=500, samples=1, seed=12345,
+               name="config[3]: 50M reads over a 5 Mb reference (reads-gen uniform, seed 12345, "
+                    "R=150), MAX_COVERAGE=500"),
+    "c1": dict(L=30_000, R=150, pairs=500_000, M=100, samples=1, seed=12345,
+               name="config[0]: 1M reads over a 30 kb reference (reads-gen uniform, seed 12345, "
+                    "R=150), MAX_COVERAGE=100"),
+}
+METRIC = "reads/sec downsampled (device-timed)"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_for(kernel, workload):
+    """dram bytes per launch of `kernel` from the committed ncu --set full capture, or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    t = json.load(open(p))
+    return t.get(workload, {}).get(kernel)
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clocks and throttle reasons of the GPUs in use DURING a timed region (NVML)."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown",
+               0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+    BAD = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown")
+
+    def __init__(self, devices, period=0.02):
+        self.devices, self.period = list(devices), period
+        self.sm, self.reasons, self.sm_max = [], set(), 0
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in self.devices]
+            self.sm_max = max(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+                              for h in self.h)
+        except Exception as ex:  # no NVML: report it, do not fake numbers
+            self.nv, self.h = None, []
+            self.err = repr(ex)
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            for h in self.h:
+                try:
+                    self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, name in self.REASONS.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+            self._stop.wait(self.period)
+
+    def start(self):
+        if self.nv:
+            self._stop.clear()
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        if self._t:
+            self._stop.set()
+            self._t.join()
+            self._t = None
+
+    def summary(self):
+        if not self.nv:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                "sm_max_mhz": int(self.sm_max), "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
+
+    def rejected(self):
+        return any(r in self.BAD for r in self.reasons)
+
+
+# ------------------------------------------------------------------------------- inputs
+def generate(wl, sample_ids, pinned):
+    """start/end of the given samples, concatenated, as int32 torch tensors on the host (the bits
+    are uint32).  Uses the host mirror's reads-gen (libgds_host.so) on all host threads."""
+    import torch
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    from genome_downsampler_b200 import hostlib
+    n_per = 2 * wl["pairs"]
+    n = n_per * len(sample_ids)
+    pin = pinned
+    try:
+        st = torch.empty(n, dtype=torch.int32, pin_memory=pin)
+        en = torch.empty(n, dtype=torch.int32, pin_memory=pin)
+    except RuntimeError as ex:
+        log("pinned allocation of %.1f GB failed (%s); using pageable host memory" % (8e-9 * n, ex))
+        pin = False
+        st = torch.empty(n, dtype=torch.int32)
+        en = torch.empty(n, dtype=torch.int32)
+    s_np = st.numpy().view(np.uint32)
+    e_np = en.numpy().view(np.uint32)
+    hostlib.gen_batch([wl["seed"] + k for k in sample_ids], wl["pairs"], wl["L"], wl["R"], s_np,
+                      e_np, threads=host_threads())
+    return st, en, pin
+
+
+# ------------------------------------------------------------------------------- reference arm
+def cpu_sample_spec(wl):
+    """One CPU solve of the bounded sample: (pairs, L).  c5/c1: one whole sample; c4: a 1/10 scale
+    cut of the same law (same coverage depth and M), because one full 50M-read solve takes minutes."""
+    if wl["pairs"] > 2_000_000:
+        return wl["pairs"] // 10, wl["L"] // 10
+    return wl["pairs"], wl["L"]
+
+
+def run_reference(args, wl, wname):
+    """The reference's CPU algorithm (oracle port of quasi-mcp-cpu) on all host threads."""
+    from concurrent.futures import ThreadPoolExecutor
+    from __graft_entry__ import load_oracle
+    O = load_oracle()
+    O.lib()
+    cores = host_threads()
+    pairs, L = cpu_sample_spec(wl)
+    M = wl["M"]
+    inputs = [O.gen_reads(wl["seed"] + k, pairs, L, wl["R"])[:2] for k in range(cores)]
+
+    def one(k):
+        kept, st = O.ref_solve(inputs[k][0], inputs[k][1], L, M)
+        return int(st.flow_value), int(st.n_kept)
+
+    def step():
+        with ThreadPoolExecutor(max_workers=cores) as ex:
+            return list(ex.map(one, range(cores)))
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = step()
+    dt = time.perf_counter() - t0
+    reads = 2 * pairs * cores * args.steps
+    value = reads / dt
+    sample = "%d independent solves per step (one per host thread), each %d reads over %d bp, M=%d" \
+             % (cores, 2 * pairs, L, M)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "reads/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": wname + " — " + wl["name"], "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "flow_value": res[0][0], "n_kept": res[0][1],
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(wl, budget_s=12.0, max_solves=32):
+    """Single-thread oracle port on a bounded sample (rank 0, N=1 only)."""
+    from __graft_entry__ import load_oracle
+    O = load_oracle()
+    O.lib()
+    pairs, L = cpu_sample_spec(wl)
+    done, t_solve = 0, 0.0
+    while done < max_solves and t_solve < budget_s:
+        s, e, _, _ = O.gen_reads(wl["seed"] + done, pairs, L, wl["R"])
+        t0 = time.perf_counter()
+        O.ref_solve(s, e, L, wl["M"])
+        t_solve += time.perf_counter() - t0
+        done += 1
+    return {"value": done * 2 * pairs / t_solve, "unit": "reads/s", "cores": 1, "kind": "port",
+            "sample": "%d sequential solves of %d reads over %d bp, M=%d (%.1f s)"
+                      % (done, 2 * pairs, L, wl["M"], t_solve)}
+
+
+# ------------------------------------------------------------------------------- B200 arm
+def run_b200(args, wl, wname):
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+    pkg = load_package()
+    from genome_downsampler_b200 import sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d" % args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    S = args.samples if args.samples else wl["samples"]
+    sample_ids = list(range(rank * S, (rank + 1) * S))   # weak scaling: S samples per rank
+    n_per = 2 * wl["pairs"]
+    n = n_per * S
+    t0 = time.time()
+    h_st, h_en, pinned = generate(wl, sample_ids, pinned=True)
+    log("[rank %d] generated %d reads (%d samples) in %.1f s, pinned=%s" %
+        (rank, n, S, time.time() - t0, pinned))
+    ref_len = np.full(S, wl["L"], np.uint32)
+    read_off = (np.arange(S + 1, dtype=np.uint64) * np.uint64(n_per))
+    words = (n + 31) // 32
+
+    stream = torch.cuda.Stream(device=dev)
+    solver = pkg.Solver(local_rank)   # raises without a usable GPU
+    with torch.cuda.stream(stream):
+        solver.set_stream(stream.cuda_stream)
+        d_st = h_st.to(dev, non_blocking=True)
+        d_en = h_en.to(dev, non_blocking=True)
+        bitmap = torch.zeros(words + 4, dtype=torch.int32, device=dev)
+        h_bitmap = torch.empty(words, dtype=torch.int32, pin_memory=True)
+        gathered = None
+        if world > 1:
+            gathered = torch.empty(world * words, dtype=torch.int32, device=dev)
+        stream.synchronize()
+
+        def step_device(profile):
+            r = solver.solve_device(d_st.data_ptr(), d_en.data_ptr(), n, ref_len, wl["M"],
+                                    bitmap.data_ptr(), read_off=read_off, profile=profile)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, bitmap[:words])
+            return r
+
+        def step_e2e():
+            r = solver.solve_device(h_st.data_ptr(), h_en.data_ptr(), n, ref_len, wl["M"],
+                                    bitmap.data_ptr(), read_off=read_off, input_on_device=False)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, bitmap[:words])
+            h_bitmap.copy_(bitmap[:words], non_blocking=True)
+            stream.synchronize()
+            return r
+
+        def barrier():
+            stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def max_over_ranks(x):
+            if world == 1:
+                return x
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        # correctness gate (untimed): the device re-derives coverage from the kept bitmap
+        rv = solver.solve_device(d_st.data_ptr(), d_en.data_ptr(), n, ref_len, wl["M"],
+                                 bitmap.data_ptr(), read_off=read_off, verify=True)
+        assert rv.verify_violations == 0 and rv.flow_value == rv.fstar, \
+            "device verification failed: %r" % dict(rv)
+
+        def timed(step_fn):
+            for _ in range(args.warmup):
+                step_fn()
+            sampler = ClockSampler(range(world) if rank == 0 else [])
+            barrier()
+            solver.kernel_profile_reset()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            sampler.start()
+            e0.record(stream)
+            launches, last = 0, None
+            for _ in range(args.steps):
+                last = step_fn()
+                launches += int(last.kernel_launches)
+            e1.record(stream)
+            barrier()
+            sampler.stop()
+            ms = max_over_ranks(e0.elapsed_time(e1))
+            return ms, launches, last, sampler
+
+        for attempt in range(2):
+            ms_dev, launches, r_last, clk = timed(lambda: step_device(True))
+            if not clk.rejected():
+                break
+            log("clock record shows %s — measuring once more" % sorted(clk.reasons))
+        prof = solver.kernel_profile()
+        ms_e2e, _, _, clk2 = timed(step_e2e)
+
+    total_reads = n * world
+    value = total_reads * args.steps / (ms_dev * 1e-3)
+    e2e_value = total_reads * args.steps / (ms_e2e * 1e-3)
+    peak, peak_src = peaks()
+    kernels = []
+    for k in sorted(prof, key=lambda k: -k["ms"]):
+        if k["launches"] == 0 or k["ms"] <= 0:
+            continue
+        gbs = k["bytes"] / (k["ms"] * 1e-3) / 1e9
+        kernels.append({"name": k["name"], "ms_per_step": k["ms"] / args.steps,
+                        "launches_per_step": k["launches"] / args.steps,
+                        "alg_bytes_per_step": k["bytes"] // args.steps,
+                        "gbs": round(gbs, 1), "frac": round(gbs / peak, 4)})
+    roofline = None
+    if kernels:
+        top = kernels[0]
+        roofline = {"bound": "hbm", "kernel": top["name"], "achieved": top["gbs"], "peak": peak,
+                    "unit": "GB/s", "frac": top["frac"], "traffic": traffic_for(top["name"], wname),
+                    "peak_source": peak_src,
+                    "alg_bytes_per_launch": int(top["alg_bytes_per_step"] /
+                                                max(top["launches_per_step"], 1)),
+                    "ms_per_launch": top["ms_per_step"] / max(top["launches_per_step"], 1)}
+        stream_k = [k for k in kernels if k["name"] != "maxflow"]
+        if stream_k:
+            b = sum(k["alg_bytes_per_step"] for k in stream_k)
+            t = sum(k["ms_per_step"] for k in stream_k)
+            roofline["streaming_kernels"] = {"gbs": round(b / (t * 1e-3) / 1e9, 1),
+                                             "frac": round(b / (t * 1e-3) / 1e9 / peak, 4),
+                                             "ms_per_step": t}
+        # whole-step figure from SURVEY §8d: B_alg = 8.125*P + 4*(L+1) per sample
+        b_alg = 8.125 * n + 4.0 * (wl["L"] + 1) * S
+        roofline["step_alg_gbs"] = round(b_alg / (ms_dev / args.steps * 1e-3) / 1e9, 1)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "data": "synthetic (reads-gen uniform law, mt19937 seed %d+k, generated on the host)"
+                % wl["seed"],
+        "config": {"workload": wname + " — " + wl["name"], "samples_per_gpu": S,
+                   "reads_per_gpu": n, "max_coverage": wl["M"], "ref_len": wl["L"],
+                   "l2": "inputs (%.0f MB per GPU) larger than the 126 MB L2; no flush needed"
+                         % (8e-6 * n) if 8 * n > 252e6 else
+                         "inputs fit L2: every step re-reads them after >126 MB of sort traffic",
+                   "parallelism": "samples sharded, %d per rank; NCCL all-gather of bitmaps" % S
+                   if world > 1 else "single GPU"},
+        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": 8 * n,
+                "d2h_bytes_per_step": 4 * words, "ms_per_step": ms_e2e / args.steps,
+                "pinned": bool(pinned)},
+        "gpu_launches": launches,
+        "clocks": clk.summary(), "clocks_e2e": clk2.summary(),
+        "roofline": roofline, "kernels": kernels[:12],
+        "result": {"fstar": int(r_last.fstar), "flow_value": int(r_last.flow_value),
+                   "n_kept": int(r_last.n_kept), "n_bundles": int(r_last.n_bundles),
+                   "n_components": int(r_last.n_components), "rounds_total": int(r_last.rounds_total),
+                   "rounds_max": int(r_last.rounds_max), "bfs_levels": int(r_last.bfs_levels),
+                   "sort_passes": int(r_last.sort_passes),
+                   "phase_ms": {"graph": r_last.ms_graph, "maxflow": r_last.ms_maxflow,
+                                "select": r_last.ms_select, "total": r_last.ms_total}},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(wl)
+    if world > 1:
+        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
+    ap.add_argument("--samples", type=int, default=0, help="samples per GPU (default: workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
+        run_reference(args, wl, args.workload)
+        return 0
+    args.warmup = max(args.warmup, 3)  # timing hygiene: never fewer than 3 warm-up steps
+    run_b200(args, wl, args.workload)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -14,7 +14,7 @@ _ERR = {1: "GDS_ERR_ARG", 2: "GDS_ERR_RANGE", 3: "GDS_ERR_CUDA", 4: "GDS_ERR_NOM
         5: "GDS_ERR_NOCONVERGE"}
 
 ENTRY_POINTS = ["gds_abi_version", "gds_create", "gds_destroy", "gds_last_error", "gds_set_stream",
-                "gds_solve", "gds_kernel_profile", "gds_bitmap_to_indices"]
+                "gds_solve", "gds_kernel_profile", "gds_kernel_profile_reset", "gds_bitmap_to_indices"]
 
 
 class GdsError(RuntimeError):
@@ -95,6 +95,8 @@ def load_library():
     L.gds_solve.restype = C.c_int
     L.gds_kernel_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
     L.gds_kernel_profile.restype = C.c_uint32
+    L.gds_kernel_profile_reset.argtypes = [C.c_void_p]
+    L.gds_kernel_profile_reset.restype = None
     L.gds_bitmap_to_indices.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
     L.gds_bitmap_to_indices.restype = C.c_uint64
     _LIB = L
@@ -137,8 +139,11 @@ class Solver:
     def set_stream(self, cuda_stream_ptr):
         self._lib.gds_set_stream(self._h, C.c_void_p(cuda_stream_ptr))
 
+    def kernel_profile_reset(self):
+        self._lib.gds_kernel_profile_reset(self._h)
+
     def kernel_profile(self):
-        """[{name, ms, launches, bytes}] of the last call made with profile=True."""
+        """[{name, ms, launches, bytes}] over the profile=True calls since the last reset."""
         buf = (_KStat * 64)()
         n = self._lib.gds_kernel_profile(self._h, buf, 64)
         return [dict(name=buf[i].name.decode(), ms=float(buf[i].ms), launches=int(buf[i].launches),

@@ -202,7 +202,7 @@ extern "C" int gds_set_stream(gds_ctx* c, void* cuda_stream) {
 }
 
 extern "C" uint32_t gds_kernel_profile(gds_ctx* c, gds_kernel_stat* outp, uint32_t cap) {
-    // aggregates the per-launch event pairs of the last GDS_PROFILE_KERNELS call by kernel name
+    // aggregates the per-launch event pairs of the GDS_PROFILE_KERNELS calls since the last reset
     if (!c) return 0;
     std::vector<gds_kernel_stat> agg;
     for (const KRec& r : c->prof.recs) {
@@ -226,6 +226,10 @@ extern "C" uint32_t gds_kernel_profile(gds_ctx* c, gds_kernel_stat* outp, uint32
     }
     for (uint32_t i = 0; i < agg.size() && i < cap && outp; ++i) outp[i] = agg[i];
     return (uint32_t)agg.size();
+}
+
+extern "C" void gds_kernel_profile_reset(gds_ctx* c) {
+    if (c) c->prof.reset();
 }
 
 extern "C" uint64_t gds_bitmap_to_indices(const uint32_t* bitmap, uint64_t n_bits,
@@ -305,8 +309,8 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         ProfGuard(Profiler* p) { cur_prof() = p; }
         ~ProfGuard() { cur_prof() = nullptr; }
     } prof_guard(&c->prof);
-    c->prof.reset();
     c->prof.on = (flags & GDS_PROFILE_KERNELS) != 0;
+    if (!c->prof.on) c->prof.reset();  // profiled calls accumulate until gds_kernel_profile_reset
     const unsigned long long launches0 = launch_counter();
     try {
         GDS_CUDA(cudaSetDevice(c->device));

@@ -16,32 +16,27 @@ int gdsh_gen_reads(uint32_t seed, uint64_t pairs, uint32_t genome_len, uint32_t 
                    uint32_t* start, uint32_t* end, uint8_t* mapq, uint32_t* seq_len) {
     if (genome_len < 2 * read_len || read_len == 0) return 1;
     std::mt19937 mt(seed);
-    bam_api::AOSPairedReads r;
+    reads_gen::SoaOut out{start, end, mapq, seq_len};
     switch (shape) {
         case 0:
-            r = reads_gen::rand_reads_uniform(mt, pairs, genome_len, read_len);
+            reads_gen::rand_reads_uniform_soa(mt, pairs, genome_len, read_len, out);
             break;
         case 1:
-            r = reads_gen::rand_reads(mt, pairs, genome_len, read_len, [](double x) { return x - x * x; });
+            reads_gen::rand_reads_soa(mt, pairs, genome_len, read_len,
+                                      [](double x) { return x - x * x; }, out);
             break;
         case 2:
-            r = reads_gen::rand_reads(mt, pairs, genome_len, read_len, [](double x) {
+            reads_gen::rand_reads_soa(mt, pairs, genome_len, read_len, [](double x) {
                 double c = x * x - x + 0.25;
                 return (x > 0.3684 && x < 0.6316) ? 1000.0 * c * c + 0.2 : 0.5;
-            });
+            }, out);
             break;
         case 3:
-            r = reads_gen::rand_reads(mt, pairs, genome_len, read_len,
-                                      [](double x) { return 1.0 - 10.0 * (x - 0.5) * (x - 0.5); });
+            reads_gen::rand_reads_soa(mt, pairs, genome_len, read_len,
+                                      [](double x) { return 1.0 - 10.0 * (x - 0.5) * (x - 0.5); }, out);
             break;
         default:
             return 2;
-    }
-    for (size_t i = 0; i < r.reads.size(); ++i) {
-        start[i] = static_cast<uint32_t>(r.reads[i].start_ind);
-        end[i] = static_cast<uint32_t>(r.reads[i].end_ind);
-        if (mapq) mapq[i] = static_cast<uint8_t>(r.reads[i].quality);
-        if (seq_len) seq_len[i] = r.reads[i].seq_length;
     }
     return 0;
 }

@@ -12,13 +12,26 @@
 #include <vector>
 
 namespace {
-template <typename StartDraw>
-bam_api::AOSPairedReads generate(std::mt19937& gen, bam_api::ReadIndex pairs, bam_api::Index G,
-                                 uint32_t R, int32_t max_quality, bool pin_tail, StartDraw draw) {
-    std::uniform_int_distribution<> quality(0, max_quality);
+// Sink = where generated reads go: the AoS container, or caller-owned SoA arrays (no allocation,
+// so many samples can be generated concurrently on host threads).
+struct AosSink {
     bam_api::AOSPairedReads out;
-    out.ref_genome_length = G;
-    out.reserve(2 * pairs);
+    void push_back(const bam_api::Read& r) { out.push_back(r); }
+};
+struct SoaSink {
+    reads_gen::SoaOut o;
+    void push_back(const bam_api::Read& r) {
+        o.start[r.bam_id] = static_cast<uint32_t>(r.start_ind);
+        o.end[r.bam_id] = static_cast<uint32_t>(r.end_ind);
+        if (o.mapq) o.mapq[r.bam_id] = static_cast<uint8_t>(r.quality);
+        if (o.seq_len) o.seq_len[r.bam_id] = r.seq_length;
+    }
+};
+
+template <typename Sink, typename StartDraw>
+void generate(Sink& out, std::mt19937& gen, bam_api::ReadIndex pairs, bam_api::Index G,
+              uint32_t R, int32_t max_quality, bool pin_tail, StartDraw draw) {
+    std::uniform_int_distribution<> quality(0, max_quality);
     for (bam_api::ReadIndex p = 0; p < pairs; ++p) {
         auto [a, b] = draw(gen);
         if (a > b) std::swap(a, b);
@@ -33,29 +46,25 @@ bam_api::AOSPairedReads generate(std::mt19937& gen, bam_api::ReadIndex pairs, ba
         uint32_t qb = static_cast<uint32_t>(quality(gen));
         out.push_back(bam_api::Read(2 * p + 1, b, b + R - 1, qb, R, false));
     }
-    return out;
 }
-}  // namespace
 
-bam_api::AOSPairedReads reads_gen::rand_reads_uniform(std::mt19937& generator,
-                                                      bam_api::ReadIndex pairs_count,
-                                                      bam_api::Index genome_length,
-                                                      uint32_t read_length, int32_t max_quality) {
+template <typename Sink>
+void uniform_into(Sink& sink, std::mt19937& generator, bam_api::ReadIndex pairs_count,
+                  bam_api::Index genome_length, uint32_t read_length, int32_t max_quality) {
     std::uniform_int_distribution<> d1(0, static_cast<int32_t>(genome_length - 2 * read_length));
     std::uniform_int_distribution<> d2(0, static_cast<int32_t>(genome_length - read_length));
-    return generate(generator, pairs_count, genome_length, read_length, max_quality, false,
-                    [&](std::mt19937& g) {
-                        bam_api::Index a = d1(g);
-                        bam_api::Index b = d2(g);
-                        return std::pair<bam_api::Index, bam_api::Index>(a, b);
-                    });
+    generate(sink, generator, pairs_count, genome_length, read_length, max_quality, false,
+             [&](std::mt19937& g) {
+                 bam_api::Index a = d1(g);
+                 bam_api::Index b = d2(g);
+                 return std::pair<bam_api::Index, bam_api::Index>(a, b);
+             });
 }
 
-bam_api::AOSPairedReads reads_gen::rand_reads(std::mt19937& generator,
-                                              bam_api::ReadIndex pairs_count,
-                                              bam_api::Index genome_length, uint32_t read_length,
-                                              const std::function<double(double)>& dist_func,
-                                              int32_t max_quality) {
+template <typename Sink>
+void weighted_into(Sink& sink, std::mt19937& generator, bam_api::ReadIndex pairs_count,
+                   bam_api::Index genome_length, uint32_t read_length,
+                   const std::function<double(double)>& dist_func, int32_t max_quality) {
     const uint32_t n_starts = static_cast<uint32_t>(genome_length - read_length + 1);
     std::vector<double> w(n_starts);
     double total = 0;
@@ -65,10 +74,49 @@ bam_api::AOSPairedReads reads_gen::rand_reads(std::mt19937& generator,
     }
     for (double& x : w) x /= total;
     std::discrete_distribution<> dd(w.begin(), w.end());
-    return generate(generator, pairs_count, genome_length, read_length, max_quality, true,
-                    [&](std::mt19937& g) {
-                        bam_api::Index a = dd(g);
-                        bam_api::Index b = dd(g);
-                        return std::pair<bam_api::Index, bam_api::Index>(a, b);
-                    });
+    generate(sink, generator, pairs_count, genome_length, read_length, max_quality, true,
+             [&](std::mt19937& g) {
+                 bam_api::Index a = dd(g);
+                 bam_api::Index b = dd(g);
+                 return std::pair<bam_api::Index, bam_api::Index>(a, b);
+             });
+}
+}  // namespace
+
+bam_api::AOSPairedReads reads_gen::rand_reads_uniform(std::mt19937& generator,
+                                                      bam_api::ReadIndex pairs_count,
+                                                      bam_api::Index genome_length,
+                                                      uint32_t read_length, int32_t max_quality) {
+    AosSink sink;
+    sink.out.ref_genome_length = genome_length;
+    sink.out.reserve(2 * pairs_count);
+    uniform_into(sink, generator, pairs_count, genome_length, read_length, max_quality);
+    return std::move(sink.out);
+}
+
+bam_api::AOSPairedReads reads_gen::rand_reads(std::mt19937& generator,
+                                              bam_api::ReadIndex pairs_count,
+                                              bam_api::Index genome_length, uint32_t read_length,
+                                              const std::function<double(double)>& dist_func,
+                                              int32_t max_quality) {
+    AosSink sink;
+    sink.out.ref_genome_length = genome_length;
+    sink.out.reserve(2 * pairs_count);
+    weighted_into(sink, generator, pairs_count, genome_length, read_length, dist_func, max_quality);
+    return std::move(sink.out);
+}
+
+void reads_gen::rand_reads_uniform_soa(std::mt19937& generator, bam_api::ReadIndex pairs_count,
+                                       bam_api::Index genome_length, uint32_t read_length,
+                                       const SoaOut& out, int32_t max_quality) {
+    SoaSink sink{out};
+    uniform_into(sink, generator, pairs_count, genome_length, read_length, max_quality);
+}
+
+void reads_gen::rand_reads_soa(std::mt19937& generator, bam_api::ReadIndex pairs_count,
+                               bam_api::Index genome_length, uint32_t read_length,
+                               const std::function<double(double)>& dist_func, const SoaOut& out,
+                               int32_t max_quality) {
+    SoaSink sink{out};
+    weighted_into(sink, generator, pairs_count, genome_length, read_length, dist_func, max_quality);
 }

@@ -120,8 +120,8 @@ int gds_solve(gds_ctx* ctx, const gds_reads* reads, const gds_filter* filter /* 
               uint32_t max_coverage, const gds_params* params /* NULL = defaults */,
               uint32_t flags, gds_result* out);
 
-/* Per-kernel device time of the last gds_solve that ran with GDS_PROFILE_KERNELS, aggregated by
- * kernel name: CUDA-event milliseconds, launches, and the algorithmic bytes (once-through reads +
+/* Per-kernel device time of the gds_solve calls that ran with GDS_PROFILE_KERNELS since the last
+ * gds_kernel_profile_reset (a call without the flag also resets), aggregated by kernel name: CUDA-event milliseconds, launches, and the algorithmic bytes (once-through reads +
  * writes) those launches had to move.  Returns the number of distinct kernels. */
 typedef struct {
     char name[32];
@@ -130,6 +130,7 @@ typedef struct {
     uint64_t bytes;
 } gds_kernel_stat;
 uint32_t gds_kernel_profile(gds_ctx* ctx, gds_kernel_stat* out, uint32_t cap);
+void gds_kernel_profile_reset(gds_ctx* ctx);
 
 /* Expand a HOST bitmap into ascending indices (qmcp::Solution order).  Returns count. */
 uint64_t gds_bitmap_to_indices(const uint32_t* bitmap, uint64_t n_bits, uint64_t* indices,
