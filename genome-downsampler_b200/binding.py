@@ -36,7 +36,8 @@ class _Filter(C.Structure):
 
 class _Params(C.Structure):
     _fields_ = [("gr_interval_min", C.c_uint32), ("gr_levels_pct", C.c_uint32),
-                ("gr_relabel_pct", C.c_uint32), ("max_rounds", C.c_uint32)]
+                ("gr_relabel_pct", C.c_uint32), ("max_rounds", C.c_uint32),
+                ("seg_len", C.c_uint32)]
 
 
 class _KStat(C.Structure):
@@ -48,7 +49,8 @@ class _Result(C.Structure):
     _fields_ = [("kept_bitmap", C.c_void_p), ("pair_pass", C.c_void_p), ("filt_off", C.c_void_p),
                 ("cov_capped", C.c_void_p), ("demand", C.c_void_p),
                 ("n_reads_in", C.c_uint64), ("n_filtered", C.c_uint64), ("n_kept", C.c_uint64),
-                ("n_bundles", C.c_uint64), ("n_nodes", C.c_uint32), ("n_components", C.c_uint32),
+                ("n_bundles", C.c_uint64), ("n_arc_items", C.c_uint64),
+                ("n_nodes", C.c_uint32), ("n_components", C.c_uint32),
                 ("fstar", C.c_int64), ("flow_value", C.c_int64),
                 ("rounds_total", C.c_uint64), ("rounds_max", C.c_uint64), ("pushes", C.c_uint64),
                 ("relabels", C.c_uint64), ("global_relabels", C.c_uint64),

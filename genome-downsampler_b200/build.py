@@ -49,6 +49,7 @@ def build_host(force=False):
     if not os.path.isdir(hdir):
         return None
     srcs = [os.path.join(dp, f) for dp, _, fs in os.walk(hdir) for f in fs]
+    srcs.append(os.path.join(ROOT, "include", "gds.h"))
     cpps = [s for s in srcs if s.endswith(".cpp")]
     if not cpps:
         return None

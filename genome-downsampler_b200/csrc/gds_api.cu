@@ -45,7 +45,8 @@ struct gds_ctx {
     DevBuf comp_start, comp_end, comp_sidx, comp_eidx, comp_lo, comp_hi;
     DevBuf qF, qT, qN, work_counter, comp_stats;
     DevBuf bitmap, cov_tmp, dem_tmp, vdiff, vexcl;
-    bool mf_attr_set = false;
+    DevBuf vs_d, cross_idx, cross_tc, odiff, oexcl, cut_nodes;
+    unsigned mf_attr_set = 0;  // bit i: smem attribute set for launch shape i
     Profiler prof;
 
     void release_all() {
@@ -56,7 +57,8 @@ struct gds_ctx {
                          &outdeg, &indeg, &excl, &tkA, &tkB, &tvA, &tvB, &n_dcur, &n_dsnap, &n_e,
                          &n_eadd, &n_snk, &n_g, &n_stamp, &comp_start, &comp_end, &comp_sidx,
                          &comp_eidx, &comp_lo, &comp_hi, &qF, &qT, &qN, &work_counter, &comp_stats,
-                         &bitmap, &cov_tmp, &dem_tmp, &vdiff, &vexcl};
+                         &bitmap, &cov_tmp, &dem_tmp, &vdiff, &vexcl, &vs_d, &cross_idx, &cross_tc,
+                         &odiff, &oexcl, &cut_nodes};
         for (DevBuf* b : all) b->release();
     }
 };
@@ -99,28 +101,62 @@ void deliver(gds_ctx* c, T* dst, const T* dev_src, size_t n, bool dst_on_device)
                              c->stream));
 }
 
+template <int I>
+void launch_maxflow_shape(gds_ctx* c, const NodeArrays& na, const BundleGraph& bg,
+                          const uint32_t* comp_lo, const uint32_t* comp_hi, uint32_t n_comp,
+                          uint32_t* wc, uint32_t* qF, uint32_t* qT, uint32_t* qN,
+                          const SolveParams& sp, CompStats* cstats) {
+    constexpr MfShape sh = kMfShapes[I];
+    auto kern = k_maxflow<sh.threads, sh.qcap, sh.ctas_per_sm>;
+    constexpr int smem = (int)sizeof(MfShared<sh.qcap>);
+    if (!(c->mf_attr_set & (1u << I))) {
+        GDS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        c->mf_attr_set |= 1u << I;
+    }
+    int grid = std::min<uint32_t>(n_comp, (uint32_t)kNumSMs * sh.ctas_per_sm);
+    kern<<<grid, sh.threads, smem, c->stream>>>(na, bg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN,
+                                                sp, cstats);
+}
+
+void launch_maxflow(gds_ctx* c, const NodeArrays& na, const BundleGraph& bg,
+                    const uint32_t* comp_lo, const uint32_t* comp_hi, uint32_t n_comp, uint32_t* wc,
+                    uint32_t* qF, uint32_t* qT, uint32_t* qN, const SolveParams& sp,
+                    CompStats* cstats, unsigned long long alg_bytes) {
+    KScope ks("maxflow", alg_bytes, c->stream);
+    const uint32_t sms = (uint32_t)kNumSMs;
+    if (n_comp <= sms * kMfShapes[0].ctas_per_sm)
+        launch_maxflow_shape<0>(c, na, bg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp, cstats);
+    else if (n_comp <= sms * kMfShapes[1].ctas_per_sm)
+        launch_maxflow_shape<1>(c, na, bg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp, cstats);
+    else if (n_comp <= sms * kMfShapes[2].ctas_per_sm)
+        launch_maxflow_shape<2>(c, na, bg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp, cstats);
+    else
+        launch_maxflow_shape<3>(c, na, bg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp, cstats);
+    GDS_KERNEL_CHECK();
+}
+
 template <typename K>
-void build_bundles(gds_ctx* c, const uint32_t* S, const uint32_t* E, const uint64_t* off_dev,
-                   const uint32_t* base_dev, uint32_t n_samples, size_t N, uint32_t n_nodes,
-                   int nodebits, int lenbits, uint32_t minlen, uint32_t& B_out,
+void build_bundles(gds_ctx* c, const uint32_t* S, const uint32_t* E, const VLayout& vl,
+                   const uint32_t* cross_idx, size_t N, size_t n_items, uint32_t n_nodes,
+                   int nodebits, int lenbits, uint32_t minlen, int32_t* odiff, uint32_t& B_out,
                    uint32_t*& sorted_idx_out, int& passes_out) {
     cudaStream_t st = c->stream;
-    K* kA = c->keysA.get<K>(N);
-    K* kB = c->keysB.get<K>(N);
-    uint32_t* vA = c->valsA.get<uint32_t>(N);
-    uint32_t* vB = c->valsB.get<uint32_t>(N);
-    ReadKeys<K> rk{S, E, off_dev, base_dev, n_samples, lenbits, minlen};
-    int where = radix_sort_pairs<K, ReadKeys<K>>(kA, vA, kB, vB, N, nodebits + lenbits, true,
+    K* kA = c->keysA.get<K>(n_items);
+    K* kB = c->keysB.get<K>(n_items);
+    uint32_t* vA = c->valsA.get<uint32_t>(n_items);
+    uint32_t* vB = c->valsB.get<uint32_t>(n_items);
+    ReadKeys<K> rk{S, E, vl, cross_idx, N, lenbits, minlen};
+    int where = radix_sort_pairs<K, ReadKeys<K>>(kA, vA, kB, vB, n_items, nodebits + lenbits, true,
                                                  c->radix, st, &passes_out, &rk);
     const K* keys = where ? kB : kA;
     sorted_idx_out = where ? vB : vA;
     // bundle heads
-    uint32_t n_tiles = (uint32_t)((N + kHeadTile - 1) / kHeadTile);
+    uint32_t n_tiles = (uint32_t)((n_items + kHeadTile - 1) / kHeadTile);
     uint32_t* tc = c->tile_counts.get<uint32_t>(n_tiles + 1);
     GDS_CUDA(cudaMemsetAsync(tc + n_tiles, 0, sizeof(uint32_t), st));
     {
-        KScope ks("heads_count", sizeof(K) * (unsigned long long)N, st);
-        k_heads_count<K><<<n_tiles, kHeadThreads, 0, st>>>(keys, N, tc);
+        KScope ks("heads_count", sizeof(K) * (unsigned long long)n_items, st);
+        k_heads_count<K><<<n_tiles, kHeadThreads, 0, st>>>(keys, n_items, tc);
         GDS_KERNEL_CHECK();
     }
     exclusive_scan_u32(tc, tc, n_tiles + 1, c->scan, st);
@@ -130,8 +166,8 @@ void build_bundles(gds_ctx* c, const uint32_t* S, const uint32_t* E, const uint6
     uint32_t* b_first = c->b_first.get<uint32_t>(B + 1);
     K* b_key = c->b_key.get<K>(B + 1);
     {
-        KScope ks("heads_write", sizeof(K) * (unsigned long long)N + (4ull + sizeof(K)) * B, st);
-        k_heads_write<K><<<n_tiles, kHeadThreads, 0, st>>>(keys, N, tc, b_first, b_key);
+        KScope ks("heads_write", sizeof(K) * (unsigned long long)n_items + (4ull + sizeof(K)) * B, st);
+        k_heads_write<K><<<n_tiles, kHeadThreads, 0, st>>>(keys, n_items, tc, b_first, b_key);
         GDS_KERNEL_CHECK();
     }
     uint32_t* b_s = c->b_s.get<uint32_t>(B + 1);
@@ -144,13 +180,11 @@ void build_bundles(gds_ctx* c, const uint32_t* S, const uint32_t* E, const uint6
     GDS_CUDA(cudaMemsetAsync(outdeg, 0, (n_nodes + 1) * sizeof(uint32_t), st));
     GDS_CUDA(cudaMemsetAsync(indeg, 0, (n_nodes + 1) * sizeof(uint32_t), st));
     if (B) {
-        {
-            KScope ks("bundle_fill", (sizeof(K) + 4ull + 12ull + 16ull) * B, st);
-            k_bundle_fill<K><<<div_up(B, 256), 256, 0, st>>>(b_key, b_first, B, (uint32_t)N, lenbits,
-            minlen, b_s, b_t, b_mult, diff, outdeg,
-            indeg);
-            GDS_KERNEL_CHECK();
-        }
+        KScope ks("bundle_fill", (sizeof(K) + 8ull + 12ull + 16ull) * B, st);
+        k_bundle_fill<K><<<div_up(B, 256), 256, 0, st>>>(b_key, b_first, sorted_idx_out, B,
+                                                         (uint32_t)n_items, lenbits, minlen, vl, b_s,
+                                                         b_t, b_mult, diff, outdeg, indeg, odiff);
+        GDS_KERNEL_CHECK();
     }
 }
 
@@ -276,13 +310,14 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             return fail(c, GDS_ERR_ARG, "null amplicon table");
     }
     uint64_t nn64 = 0;
-    std::vector<uint32_t> base(ns + 1, 0);
+    std::vector<uint32_t> base(ns + 1, 0);  // original node space: sample k owns ref_len[k]+1 nodes
     for (uint32_t k = 0; k < ns; ++k) {
         nn64 += (uint64_t)rd->ref_len[k] + 1;
         if (nn64 >= kLabelInf) return fail(c, GDS_ERR_RANGE, "total reference length beyond 2^30 nodes");
         base[k + 1] = (uint32_t)nn64;
     }
-    const uint32_t n_nodes = (uint32_t)nn64;
+    const uint32_t n_onodes = (uint32_t)nn64;
+    uint32_t n_nodes = n_onodes;  // virtual node space (grows when long references are segmented)
     const bool in_dev = flags & GDS_INPUT_ON_DEVICE;
     const bool out_dev = flags & GDS_OUTPUT_ON_DEVICE;
     SolveParams sp{64, 150, 1, 0};
@@ -292,6 +327,7 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         sp.gr_relabel_pct = prm->gr_relabel_pct;
         sp.max_rounds = prm->max_rounds;
     }
+    const uint32_t seg_len = (prm && prm->seg_len) ? prm->seg_len : 32768u;
     // scalars of the result start clean (buffers are left alone)
     {
         gds_result keep = *out;
@@ -303,7 +339,7 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         out->demand = keep.demand;
     }
     out->n_reads_in = P;
-    out->n_nodes = n_nodes;
+    out->n_nodes = n_onodes;
 
     struct ProfGuard {
         ProfGuard(Profiler* p) { cur_prof() = p; }
@@ -425,9 +461,8 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         uint32_t B = 0, n_comp = 0;
         uint32_t* sorted_idx = nullptr;
         int sort_passes = 0;
-        uint32_t minlen = 1;
+        uint32_t minlen = 1, maxlen = 1;
         int lenbits = 0;
-        const int nodebits = bits_for(n_nodes ? n_nodes - 1 : 0);
         if (N > 0) {
             int grid = std::min<long long>(div_up(N, 256 * 8), kNumSMs * 16);
             {
@@ -443,14 +478,81 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
                 return fail(c, GDS_ERR_RANGE, buf);
             }
             minlen = hstats[0];
-            lenbits = bits_for(hstats[1] - hstats[0]);
-            out->key_bits = nodebits + lenbits;
+            maxlen = hstats[1];
+            lenbits = bits_for(maxlen - minlen);
+        }
+        // K4 (generalised): virtual node space — references longer than seg are cut into segments
+        const uint32_t seg = seg_len >= maxlen ? seg_len : 0xffffffffu;  // a read crosses <= 1 cut
+        std::vector<VSample> hvs(ns);
+        std::vector<uint32_t> hcuts;
+        bool split = false;
+        {
+            uint64_t vb = 0;
+            for (uint32_t k = 0; k < ns; ++k) {
+                VSample& v = hvs[k];
+                v.obase = base[k];
+                v.vbase = (uint32_t)vb;
+                v.L = rd->ref_len[k];
+                v.nseg = v.L > seg ? (uint32_t)(((uint64_t)v.L + seg - 1) / seg) : 1;
+                v.P = v.nseg > 1 ? maxlen - 1 : 0;
+                v.W = v.nseg > 1 ? v.P + seg + 1 : 0;
+                uint64_t vn = v.nseg == 1 ? (uint64_t)v.L + 1
+                                          : (uint64_t)(v.nseg - 1) * v.W + v.P +
+                                                (v.L - (uint64_t)(v.nseg - 1) * seg) + 1;
+                vb += vn;
+                if (vb >= kLabelInf)
+                    return fail(c, GDS_ERR_RANGE, "segmented reference beyond 2^30 nodes");
+                if (v.nseg > 1) {
+                    split = true;
+                    for (uint32_t j = 1; j < v.nseg; ++j) hcuts.push_back(v.obase + j * seg);
+                }
+            }
+            n_nodes = (uint32_t)vb;
+        }
+        VSample* vs_d = c->vs_d.get<VSample>(ns);
+        GDS_CUDA(cudaMemcpyAsync(vs_d, hvs.data(), ns * sizeof(VSample), cudaMemcpyHostToDevice, st));
+        VLayout vl{vs_d, foff_dev, ns, seg};
+        const int nodebits = bits_for(n_nodes ? n_nodes - 1 : 0);
+        out->key_bits = nodebits + lenbits;
+        int32_t* odiff = nullptr;
+        uint32_t* oexcl = nullptr;
+        if (split) {
+            odiff = c->odiff.get<int32_t>(n_onodes + 1);
+            oexcl = c->oexcl.get<uint32_t>(n_onodes + 1);
+            GDS_CUDA(cudaMemsetAsync(odiff, 0, ((size_t)n_onodes + 1) * 4, st));
+        }
+        size_t n_items = N;
+        uint32_t* cross_idx = nullptr;
+        if (split && N > 0) {  // right parts of the reads that cross a cut
+            uint32_t n_ct = (uint32_t)((N + kCrossTile - 1) / kCrossTile);
+            uint32_t* ctc = c->cross_tc.get<uint32_t>(n_ct + 1);
+            GDS_CUDA(cudaMemsetAsync(ctc + n_ct, 0, 4, st));
+            {
+                KScope ks("cross_count", 8ull * N, st);
+                k_cross_count<<<n_ct, kCrossThreads, 0, st>>>(S, E, N, vl, ctc);
+                GDS_KERNEL_CHECK();
+            }
+            exclusive_scan_u32(ctc, ctc, n_ct + 1, c->scan, st);
+            uint32_t X = 0;
+            d2h_sync(c, &X, ctc + n_ct, 1);
+            cross_idx = c->cross_idx.get<uint32_t>(X + 1);
+            if (X) {
+                KScope ks("cross_write", 8ull * N + 4ull * X, st);
+                k_cross_write<<<n_ct, kCrossThreads, 0, st>>>(S, E, N, vl, ctc, cross_idx);
+                GDS_KERNEL_CHECK();
+            }
+            n_items = N + X;
+            if (n_items >= (1ull << 32) - 64)
+                return fail(c, GDS_ERR_RANGE, "more than 2^32 arc items after segmentation");
+        }
+        out->n_arc_items = n_items;
+        if (N > 0) {
             if (nodebits + lenbits <= 32)
-                build_bundles<uint32_t>(c, S, E, foff_dev, base_d, ns, N, n_nodes, nodebits, lenbits,
-                                        minlen, B, sorted_idx, sort_passes);
+                build_bundles<uint32_t>(c, S, E, vl, cross_idx, N, n_items, n_nodes, nodebits,
+                                        lenbits, minlen, odiff, B, sorted_idx, sort_passes);
             else
-                build_bundles<unsigned long long>(c, S, E, foff_dev, base_d, ns, N, n_nodes,
-                                                  nodebits, lenbits, minlen, B, sorted_idx,
+                build_bundles<unsigned long long>(c, S, E, vl, cross_idx, N, n_items, n_nodes,
+                                                  nodebits, lenbits, minlen, odiff, B, sorted_idx,
                                                   sort_passes);
         } else {
             int32_t* diff = c->diff.get<int32_t>(n_nodes + 1);
@@ -485,21 +587,43 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         uint32_t* cend = c->comp_end.get<uint32_t>(n_nodes + 1);
         GDS_CUDA(cudaMemsetAsync(cstart + n_nodes, 0, 4, st));
         GDS_CUDA(cudaMemsetAsync(cend + n_nodes, 0, 4, st));
+        // cov_capped / demand are reported on the ORIGINAL node space
         uint32_t* cov_dev = nullptr;
         int32_t* dem_dev = nullptr;
-        if (out->cov_capped) cov_dev = out_dev ? out->cov_capped : c->cov_tmp.get<uint32_t>(n_nodes);
-        if (out->demand) dem_dev = out_dev ? out->demand : c->dem_tmp.get<int32_t>(n_nodes);
+        if (out->cov_capped) cov_dev = out_dev ? out->cov_capped : c->cov_tmp.get<uint32_t>(n_onodes);
+        if (out->demand) dem_dev = out_dev ? out->demand : c->dem_tmp.get<int32_t>(n_onodes);
         {
             KScope ks("node_finalize", 44ull * n_nodes, st);
-            k_node_finalize<<<div_up(n_nodes, 256), 256, 0, st>>>(excl, diff, n_nodes, max_coverage, na,
-            cstart, cend, cov_dev, dem_dev, totals);
+            k_node_finalize<<<div_up(n_nodes, 256), 256, 0, st>>>(
+                excl, diff, n_nodes, max_coverage, na, cstart, cend, split ? nullptr : cov_dev,
+                split ? nullptr : dem_dev, totals);
             GDS_KERNEL_CHECK();
+        }
+        if (split) {
+            exclusive_scan_u32(reinterpret_cast<const uint32_t*>(odiff), oexcl, (size_t)n_onodes + 1,
+                               c->scan, st);
+            {
+                KScope ks("orig_outputs", 16ull * n_onodes, st);
+                k_orig_outputs<<<div_up(n_onodes, 256), 256, 0, st>>>(oexcl, odiff, n_onodes,
+                                                                      max_coverage, cov_dev, dem_dev,
+                                                                      totals);
+                GDS_KERNEL_CHECK();
+            }
+            uint32_t* cuts_d = c->cut_nodes.get<uint32_t>(hcuts.size());
+            GDS_CUDA(cudaMemcpyAsync(cuts_d, hcuts.data(), hcuts.size() * 4, cudaMemcpyHostToDevice,
+                                     st));
+            {
+                KScope ks("cut_through", 12ull * hcuts.size(), st);
+                k_cut_through<<<div_up(hcuts.size(), 128), 128, 0, st>>>(
+                    cuts_d, (uint32_t)hcuts.size(), oexcl, odiff, max_coverage, totals);
+                GDS_KERNEL_CHECK();
+            }
         }
         uint32_t* sidx = c->comp_sidx.get<uint32_t>(n_nodes + 1);
         uint32_t* eidx = c->comp_eidx.get<uint32_t>(n_nodes + 1);
         exclusive_scan_u32(cstart, sidx, n_nodes + 1, c->scan, st);
         exclusive_scan_u32(cend, eidx, n_nodes + 1, c->scan, st);
-        d2h_sync(c, &n_comp, sidx + n_nodes, 1);
+        d2h_sync(c, &n_comp, sidx + n_nodes, 1);  // also fences hvs/hcuts uploads
         out->n_components = n_comp;
         uint32_t* comp_lo = c->comp_lo.get<uint32_t>(n_comp + 1);
         uint32_t* comp_hi = c->comp_hi.get<uint32_t>(n_comp + 1);
@@ -511,7 +635,7 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
                 GDS_KERNEL_CHECK();
             }
         }
-        // in-CSR: bundle ids ordered by (end node, start node) = stable sort of ids by b_t
+        // in-CSR: bundle ids ordered by (end node, bundle id) = stable sort of ids by b_t
         uint32_t* in_bid = nullptr;
         uint32_t* f = c->b_f.get<uint32_t>(B + 1);
         GDS_CUDA(cudaMemsetAsync(f, 0, (B + 1) * 4, st));
@@ -526,8 +650,8 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             in_bid = w ? tvB : tvA;
         }
         if (!out_dev) {
-            deliver(c, out->cov_capped, cov_dev, n_nodes, false);
-            deliver(c, out->demand, dem_dev, n_nodes, false);
+            deliver(c, out->cov_capped, cov_dev, n_onodes, false);
+            deliver(c, out->demand, dem_dev, n_onodes, false);
         }
         GDS_CUDA(cudaEventRecord(c->ev[EV_GRAPH], st));
 
@@ -542,18 +666,8 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             uint32_t* qN = c->qN.get<uint32_t>(n_nodes);
             uint32_t* wc = c->work_counter.get<uint32_t>(1);
             GDS_CUDA(cudaMemsetAsync(wc, 0, 4, st));
-            if (!c->mf_attr_set) {
-                GDS_CUDA(cudaFuncSetAttribute(k_maxflow, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)sizeof(MfShared)));
-                c->mf_attr_set = true;
-            }
-            int grid = std::min<uint32_t>(n_comp, kNumSMs);
-            {
-                KScope ks("maxflow", 28ull * n_nodes + 24ull * B, st);
-                k_maxflow<<<grid, kMfThreads, sizeof(MfShared), st>>>(na, bg, comp_lo, comp_hi, n_comp,
-                wc, qF, qT, qN, sp, cstats);
-                GDS_KERNEL_CHECK();
-            }
+            launch_maxflow(c, na, bg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp, cstats,
+                           28ull * n_nodes + 24ull * B);
         }
         GDS_CUDA(cudaEventRecord(c->ev[EV_MAXFLOW], st));
 
@@ -576,9 +690,10 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
 
         // ---------------- K6: verification (before find_pairs widens the set) ----------------
         if (do_solve && (flags & GDS_VERIFY)) {
-            int32_t* vdiff = c->vdiff.get<int32_t>(n_nodes + 1);
-            uint32_t* vexcl = c->vexcl.get<uint32_t>(n_nodes + 1);
-            GDS_CUDA(cudaMemsetAsync(vdiff, 0, (n_nodes + 1) * 4, st));
+            // original node space: compares with the input coverage (odiff when segmented)
+            int32_t* vdiff = c->vdiff.get<int32_t>((size_t)n_onodes + 1);
+            uint32_t* vexcl = c->vexcl.get<uint32_t>((size_t)n_onodes + 1);
+            GDS_CUDA(cudaMemsetAsync(vdiff, 0, ((size_t)n_onodes + 1) * 4, st));
             if (n_words) {
                 {
                     KScope ks("verify_accumulate", 4ull * n_words, st);
@@ -587,12 +702,13 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
                     GDS_KERNEL_CHECK();
                 }
             }
-            exclusive_scan_u32(reinterpret_cast<const uint32_t*>(vdiff), vexcl, n_nodes + 1, c->scan,
-                               st);
+            exclusive_scan_u32(reinterpret_cast<const uint32_t*>(vdiff), vexcl, (size_t)n_onodes + 1,
+                               c->scan, st);
             {
-                KScope ks("verify_compare", 16ull * n_nodes, st);
-                k_verify_compare<<<div_up(n_nodes, 256), 256, 0, st>>>(vexcl, vdiff, excl, diff, n_nodes,
-                max_coverage, totals);
+                KScope ks("verify_compare", 16ull * n_onodes, st);
+                k_verify_compare<<<div_up(n_onodes, 256), 256, 0, st>>>(
+                    vexcl, vdiff, split ? oexcl : excl, split ? odiff : diff, n_onodes, max_coverage,
+                    totals);
                 GDS_KERNEL_CHECK();
             }
         }
@@ -607,9 +723,13 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
 
         // ---------------- results ----------------
         if (do_solve && !out_dev) deliver(c, out->kept_bitmap, bm, n_words, false);
-        unsigned long long htot[4] = {};
-        d2h_sync(c, htot, totals, 4);
-        out->fstar = (int64_t)htot[0];
+        unsigned long long htot[6] = {};
+        d2h_sync(c, htot, totals, 6);
+        // htot[0] = source capacity of the (virtual) network the kernel solved; when references
+        // were segmented the closed-form F* of the ORIGINAL network is htot[3] and htot[4] units
+        // pass straight through the cut nodes once the segment flows are stitched together
+        const long long fstar_virtual = (long long)htot[0];
+        out->fstar = (int64_t)(split ? htot[3] : htot[0]);
         out->n_kept = htot[1];
         out->verify_violations = htot[2];
         long long stuck = 0;
@@ -644,7 +764,9 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         out->ms_d2h = ms(EV_VERIFY, EV_END);
         out->ms_total = ms(EV_BEGIN, EV_END);
         out->kernel_launches = launch_counter() - launches0;
-        if (do_solve && (out->flow_value != out->fstar || stuck != 0)) {
+        const bool converged = out->flow_value == fstar_virtual && stuck == 0;
+        if (split) out->flow_value -= (int64_t)htot[4];
+        if (do_solve && !converged) {
             char buf[160];
             snprintf(buf, sizeof buf, "max-flow did not converge: sink inflow %lld, F* %lld, stuck %lld",
                      (long long)out->flow_value, (long long)out->fstar, stuck);

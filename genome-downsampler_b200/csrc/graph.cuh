@@ -21,36 +21,151 @@ __device__ __forceinline__ uint32_t* tile_sample_range() {
     return r;
 }
 
-// First-pass key source of the read sort: key = (node(start) << lenbits) | (len - minlen)
+// Per-sample layout of the virtual node space.  A reference longer than seg positions is cut
+// into nseg segments (the zero-coverage split of SURVEY App. A.3, generalised): a read crossing
+// a cut becomes two arcs truncated at the cut node, one per segment, and is kept if either part
+// carries flow.  Virtual id of original node x in segment j = vbase + j*W + P + (x - j*seg),
+// W = P + seg + 1, with P = maxlen-1 phantom ids in front of every segment.  Arc items are keyed
+// by (fake start id, original length); the right part of a crossing read uses the fake start
+// (end node - length), which lands on a phantom id, so the key width does not grow.  Decoding
+// clamps to the real node range of the segment.  nseg == 1: virtual == original, P = W = 0.
+// Restated on the CPU in oracle/gds_oracle.cpp: build_sync_graph.
+struct VSample {
+    uint32_t obase, vbase, L, nseg, P, W;
+};
+
+struct VLayout {
+    const VSample* vs;    // [n_samples]
+    const uint64_t* off;  // [n_samples+1] read offsets
+    uint32_t n_samples;
+    uint32_t seg;
+    __device__ __forceinline__ uint32_t fake_primary(const VSample& v, uint32_t s) const {
+        if (v.nseg == 1) return v.vbase + s;
+        uint32_t js = s / seg;
+        return v.vbase + js * v.W + v.P + (s - js * seg);
+    }
+    __device__ __forceinline__ bool crosses(const VSample& v, uint32_t s, uint32_t e) const {
+        return v.nseg > 1 && e / seg > s / seg;
+    }
+    __device__ __forceinline__ uint32_t fake_right(const VSample& v, uint32_t s, uint32_t e) const {
+        uint32_t je = e / seg;
+        uint32_t vt = v.vbase + je * v.W + v.P + (e + 1 - je * seg);
+        return vt - (e - s + 1);
+    }
+    // real node range [first, last] of the segment holding virtual id vid
+    __device__ __forceinline__ void seg_range(const VSample& v, uint32_t vid, uint32_t& first,
+                                              uint32_t& last) const {
+        if (v.nseg == 1) {
+            first = v.vbase;
+            last = v.vbase + v.L;
+            return;
+        }
+        uint32_t j = (vid - v.vbase) / v.W;
+        first = v.vbase + j * v.W + v.P;
+        last = first + min(seg, v.L - j * seg);
+    }
+    __device__ __forceinline__ uint32_t to_orig(const VSample& v, uint32_t vid) const {
+        if (v.nseg == 1) return v.obase + (vid - v.vbase);
+        uint32_t j = (vid - v.vbase) / v.W;
+        return v.obase + j * seg + ((vid - v.vbase) - j * v.W - v.P);
+    }
+};
+
+// First-pass key source of the arc sort.  Items [0, n_reads) are the reads themselves (left part
+// if they cross a cut), items [n_reads, n_reads + n_cross) the right parts of crossing reads
+// (cross_idx = their read indices, ascending).  key = (fake start << lenbits) | (len - minlen);
+// value = owner read index.
 template <typename K>
 struct ReadKeys {
     const uint32_t* S;
     const uint32_t* E;
-    const uint64_t* off;
-    const uint32_t* base;
-    uint32_t n_samples;
+    VLayout vl;
+    const uint32_t* cross_idx;
+    size_t n_reads;
     int lenbits;
     uint32_t minlen;
     __device__ __forceinline__ void begin_tile(size_t first, size_t n) const {
         if (threadIdx.x == 0) {
             uint32_t* r = tile_sample_range();
-            size_t last = min(first + (size_t)blockDim.x * 64, n) - 1;  // >= any index of the tile
-            if (n_samples == 1) {
+            size_t last = min(first + (size_t)blockDim.x * 64, n_reads) - 1;
+            if (vl.n_samples == 1 || first >= n_reads) {
                 r[0] = r[1] = 0;
             } else {
-                r[0] = find_sample(off, n_samples, first);
-                r[1] = find_sample(off, n_samples, last);
+                r[0] = find_sample(vl.off, vl.n_samples, first);
+                r[1] = find_sample(vl.off, vl.n_samples, last);
             }
         }
     }
+    __device__ __forceinline__ K get(size_t i, uint32_t& owner) const {
+        if (i < n_reads) {
+            const uint32_t* r = tile_sample_range();
+            uint32_t k = r[0];
+            if (r[0] != r[1]) k = find_sample(vl.off, vl.n_samples, i);
+            uint32_t s = S[i], e = E[i];
+            owner = (uint32_t)i;
+            return ((K)vl.fake_primary(vl.vs[k], s) << lenbits) | (K)(e - s + 1 - minlen);
+        }
+        uint32_t rd = cross_idx[i - n_reads];
+        uint32_t k = vl.n_samples == 1 ? 0 : find_sample(vl.off, vl.n_samples, rd);
+        uint32_t s = S[rd], e = E[rd];
+        owner = rd;
+        return ((K)vl.fake_right(vl.vs[k], s, e) << lenbits) | (K)(e - s + 1 - minlen);
+    }
     __device__ __forceinline__ K get(size_t i) const {
-        const uint32_t* r = tile_sample_range();
-        uint32_t k = r[0];
-        if (r[0] != r[1]) k = find_sample(off, n_samples, i);
-        uint32_t s = S[i], e = E[i];
-        return ((K)(base[k] + s) << lenbits) | (K)(e - s + 1 - minlen);
+        uint32_t o;
+        return get(i, o);
     }
 };
+
+// crossing reads -> ascending list of their indices (tile counts -> scan -> write)
+constexpr int kCrossThreads = 256;
+constexpr int kCrossItems = 8;
+constexpr int kCrossTile = kCrossThreads * kCrossItems;
+
+__global__ void __launch_bounds__(kCrossThreads)
+k_cross_count(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, size_t n, VLayout vl,
+              uint32_t* __restrict__ tile_counts) {
+    size_t base = (size_t)blockIdx.x * kCrossTile + (size_t)threadIdx.x * kCrossItems;
+    uint32_t c = 0;
+#pragma unroll
+    for (int q = 0; q < kCrossItems; ++q) {
+        size_t i = base + q;
+        if (i < n) {
+            uint32_t k = vl.n_samples == 1 ? 0 : find_sample(vl.off, vl.n_samples, i);
+            c += vl.crosses(vl.vs[k], S[i], E[i]) ? 1u : 0u;
+        }
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    __shared__ uint32_t tot;
+    if (threadIdx.x == 0) tot = 0;
+    __syncthreads();
+    if (lane_id() == 0 && c) atomicAdd(&tot, c);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(kCrossThreads)
+k_cross_write(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, size_t n, VLayout vl,
+              const uint32_t* __restrict__ tile_offs, uint32_t* __restrict__ cross_idx) {
+    __shared__ uint32_t total;
+    size_t base = (size_t)blockIdx.x * kCrossTile + (size_t)threadIdx.x * kCrossItems;
+    bool hit[kCrossItems];
+    uint32_t c = 0;
+#pragma unroll
+    for (int q = 0; q < kCrossItems; ++q) {
+        size_t i = base + q;
+        hit[q] = false;
+        if (i < n) {
+            uint32_t k = vl.n_samples == 1 ? 0 : find_sample(vl.off, vl.n_samples, i);
+            hit[q] = vl.crosses(vl.vs[k], S[i], E[i]);
+        }
+        c += hit[q] ? 1u : 0u;
+    }
+    uint32_t ex = block_excl_scan(c, &total) + tile_offs[blockIdx.x];
+#pragma unroll
+    for (int q = 0; q < kCrossItems; ++q)
+        if (hit[q]) cross_idx[ex++] = (uint32_t)(base + q);
+}
 
 constexpr int kHeadThreads = 1024;
 constexpr int kHeadItems = 4;
@@ -100,22 +215,32 @@ k_heads_write(const K* __restrict__ keys, size_t n, const uint32_t* __restrict__
     }
 }
 
-// Per bundle: decode (s, t), multiplicity, and accumulate the node-level difference array and the
-// CSR degree counters.  One atomic triple per BUNDLE, not per read.
+// Per bundle: decode the key to the real (s, t) of its segment, multiplicity, and accumulate the
+// node-level difference array (virtual space, and original space when some sample is split) and
+// the CSR degree counters.  One atomic group per BUNDLE, not per read.
 template <typename K>
 __global__ void __launch_bounds__(256)
-k_bundle_fill(const K* __restrict__ b_key, uint32_t* __restrict__ b_first, uint32_t B, uint32_t N,
-              int lenbits, uint32_t minlen, uint32_t* __restrict__ b_s, uint32_t* __restrict__ b_t,
+k_bundle_fill(const K* __restrict__ b_key, uint32_t* __restrict__ b_first,
+              const uint32_t* __restrict__ sorted_owner, uint32_t B, uint32_t n_items, int lenbits,
+              uint32_t minlen, VLayout vl, uint32_t* __restrict__ b_s, uint32_t* __restrict__ b_t,
               uint32_t* __restrict__ b_mult, int32_t* __restrict__ diff,
-              uint32_t* __restrict__ outdeg, uint32_t* __restrict__ indeg) {
+              uint32_t* __restrict__ outdeg, uint32_t* __restrict__ indeg,
+              int32_t* __restrict__ odiff /* null when virtual == original */) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     K key = b_key[b];
-    uint32_t s = (uint32_t)(key >> lenbits);
+    uint32_t fake = (uint32_t)(key >> lenbits);
     uint32_t len = (uint32_t)(key & (((K)1 << lenbits) - 1)) + minlen;
-    uint32_t t = s + len;
-    uint32_t nxt = (b + 1 < B) ? b_first[b + 1] : N;
-    uint32_t mult = nxt - b_first[b];
+    uint32_t first_item = b_first[b];
+    uint32_t owner = sorted_owner[first_item];
+    uint32_t k = vl.n_samples == 1 ? 0 : find_sample(vl.off, vl.n_samples, owner);
+    const VSample v = vl.vs[k];
+    uint32_t first, last;
+    vl.seg_range(v, fake, first, last);
+    uint32_t s = max(fake, first);
+    uint32_t t = min(fake + len, last);
+    uint32_t nxt = (b + 1 < B) ? b_first[b + 1] : n_items;
+    uint32_t mult = nxt - first_item;
     b_s[b] = s;
     b_t[b] = t;
     b_mult[b] = mult;
@@ -123,6 +248,45 @@ k_bundle_fill(const K* __restrict__ b_key, uint32_t* __restrict__ b_first, uint3
     atomicAdd(&diff[t], -(int32_t)mult);
     atomicAdd(&outdeg[s], 1u);
     atomicAdd(&indeg[t], 1u);
+    if (odiff) {
+        atomicAdd(&odiff[vl.to_orig(v, s)], (int32_t)mult);
+        atomicAdd(&odiff[vl.to_orig(v, t)], -(int32_t)mult);
+    }
+}
+
+// Original-space outputs when some sample is split: capped coverage, demand
+// (create_demand_function, quasi_mcp_cpu_max_flow_solver.cpp:75-87) and F* = sum of source
+// capacities of the ORIGINAL network (totals[3]).
+__global__ void __launch_bounds__(256)
+k_orig_outputs(const uint32_t* __restrict__ oexcl, const int32_t* __restrict__ odiff,
+               uint32_t n_onodes, uint32_t M, uint32_t* __restrict__ cov_capped_out,
+               int32_t* __restrict__ demand_out, unsigned long long* __restrict__ totals) {
+    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long src = 0;
+    if (v < n_onodes) {
+        uint32_t covL = oexcl[v];
+        uint32_t covR = covL + (uint32_t)odiff[v];
+        int32_t dem = (int32_t)min(covL, M) - (int32_t)min(covR, M);
+        if (cov_capped_out) cov_capped_out[v] = min(covR, M);
+        if (demand_out) demand_out[v] = dem;
+        if (dem < 0) src = (unsigned long long)(-dem);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) src += __shfl_xor_sync(0xffffffffu, src, o);
+    if (lane_id() == 0 && src) atomicAdd(&totals[3], src);
+}
+
+// Flow that passes straight through the cut nodes when the segment flows are stitched into a
+// flow of the original network: min(cov'(x-1), cov'(x)) per cut node x (totals[4]).
+__global__ void k_cut_through(const uint32_t* __restrict__ cut_nodes, uint32_t n_cuts,
+                              const uint32_t* __restrict__ oexcl, const int32_t* __restrict__ odiff,
+                              uint32_t M, unsigned long long* __restrict__ totals) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_cuts) return;
+    uint32_t x = cut_nodes[i];
+    uint32_t covL = oexcl[x];
+    uint32_t covR = covL + (uint32_t)odiff[x];
+    atomicAdd(&totals[4], (unsigned long long)min(min(covL, M), min(covR, M)));
 }
 
 struct NodeArrays {

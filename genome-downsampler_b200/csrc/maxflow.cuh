@@ -25,8 +25,16 @@
 namespace gds {
 namespace cg = cooperative_groups;
 
-constexpr int kMfThreads = 1024;
-constexpr uint32_t kQCap = 4096;
+// Launch shapes of the same kernel (the schedule does not depend on the thread count).  Every
+// round is latency-bound with a small frontier, so throughput comes from running ALL components
+// concurrently: the host picks the widest CTA whose resident count (CTAs/SM x 148) still covers
+// the number of components; beyond 8 CTAs/SM the work counter hands out the rest in waves.
+//   1024 threads x 1/SM (4096-entry staged queues) ... 128 threads x 8/SM (1024-entry queues)
+struct MfShape {
+    int threads, ctas_per_sm;
+    uint32_t qcap;
+};
+constexpr MfShape kMfShapes[4] = {{1024, 1, 4096}, {512, 2, 2048}, {256, 4, 1024}, {128, 8, 1024}};
 
 struct BundleGraph {
     const uint32_t* b_s;
@@ -47,18 +55,20 @@ struct CompStats {
     long long sink_flow, stuck;
 };
 
+template <uint32_t QCAP>
 struct Queue {
-    uint32_t* sm;  // kQCap entries in shared memory
+    uint32_t* sm;  // QCAP entries in shared memory
     uint32_t* gl;  // global spill (indexed by the same position)
-    __device__ __forceinline__ uint32_t get(uint32_t i) const { return i < kQCap ? sm[i] : gl[i]; }
+    __device__ __forceinline__ uint32_t get(uint32_t i) const { return i < QCAP ? sm[i] : gl[i]; }
     __device__ __forceinline__ void put(uint32_t i, uint32_t v) const {
-        if (i < kQCap) sm[i] = v;
+        if (i < QCAP) sm[i] = v;
         else gl[i] = v;
     }
 };
 
 // warp-aggregated append from divergent code
-__device__ __forceinline__ void q_append(const Queue& q, uint32_t* count, uint32_t v) {
+template <uint32_t QCAP>
+__device__ __forceinline__ void q_append(const Queue<QCAP>& q, uint32_t* count, uint32_t v) {
     auto g = cg::coalesced_threads();
     uint32_t base = 0;
     if (g.thread_rank() == 0) base = atomicAdd(count, g.size());
@@ -66,8 +76,9 @@ __device__ __forceinline__ void q_append(const Queue& q, uint32_t* count, uint32
     q.put(base + g.thread_rank(), v);
 }
 
+template <uint32_t QCAP>
 struct MfShared {
-    uint32_t qa[kQCap], qb[kQCap], qc[kQCap];
+    uint32_t qa[QCAP], qb[QCAP], qc[QCAP];
     uint32_t nF, nT, nN;
     uint32_t relabels_since;
     uint32_t comp;
@@ -76,9 +87,11 @@ struct MfShared {
 };
 
 // reverse BFS from the sink; T/N are used as the level queues.  returns the level counter
+template <int THREADS, uint32_t QCAP>
 __device__ uint32_t mf_global_relabel(const NodeArrays& na, const BundleGraph& bg, uint32_t lo,
-                                      uint32_t hi, Queue T, Queue N, MfShared& sh,
-                                      unsigned long long& bfs_levels) {
+                                      uint32_t hi, Queue<QCAP> T, Queue<QCAP> N,
+                                      MfShared<QCAP>& sh, unsigned long long& bfs_levels) {
+    constexpr uint32_t kMfThreads = THREADS;
     const uint32_t tid = threadIdx.x;
     for (uint32_t v = lo + tid; v <= hi; v += kMfThreads) na.d_cur[v] = kLabelInf;
     if (tid == 0) {
@@ -131,7 +144,7 @@ __device__ uint32_t mf_global_relabel(const NodeArrays& na, const BundleGraph& b
             sh.nT = cnt;
             sh.nN = 0;
         }
-        Queue tmp = T;
+        Queue<QCAP> tmp = T;
         T = N;
         N = tmp;
         ++level;
@@ -146,13 +159,15 @@ __device__ uint32_t mf_global_relabel(const NodeArrays& na, const BundleGraph& b
     return level;
 }
 
-__global__ void __launch_bounds__(kMfThreads, 1)
+template <int THREADS, uint32_t QCAP, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
 k_maxflow(NodeArrays na, BundleGraph bg, const uint32_t* __restrict__ comp_lo,
           const uint32_t* __restrict__ comp_hi, uint32_t n_comp, uint32_t* work_counter,
           uint32_t* qF_g, uint32_t* qT_g, uint32_t* qN_g, SolveParams P,
           CompStats* __restrict__ stats) {
+    constexpr uint32_t kMfThreads = THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    MfShared& sh = *reinterpret_cast<MfShared*>(smem_raw);
+    MfShared<QCAP>& sh = *reinterpret_cast<MfShared<QCAP>*>(smem_raw);
     const uint32_t tid = threadIdx.x;
 
     for (;;) {
@@ -162,7 +177,7 @@ k_maxflow(NodeArrays na, BundleGraph bg, const uint32_t* __restrict__ comp_lo,
         if (c >= n_comp) break;
         const uint32_t lo = comp_lo[c], hi = comp_hi[c];
         const uint32_t ncomp = hi - lo + 1;
-        Queue F{sh.qa, qF_g + lo}, T{sh.qb, qT_g + lo}, N{sh.qc, qN_g + lo};
+        Queue<QCAP> F{sh.qa, qF_g + lo}, T{sh.qb, qT_g + lo}, N{sh.qc, qN_g + lo};
         if (tid == 0) {
             sh.nF = 0;
             sh.relabels_since = 0;
@@ -174,7 +189,7 @@ k_maxflow(NodeArrays na, BundleGraph bg, const uint32_t* __restrict__ comp_lo,
         unsigned long long bfs_levels = 0, grs = 1, rounds = 0, max_frontier = 0;
         unsigned long long my_pushes = 0, my_relabels = 0;
         long long my_sink = 0, my_stuck = 0;
-        uint32_t last_levels = mf_global_relabel(na, bg, lo, hi, T, N, sh, bfs_levels);
+        uint32_t last_levels = mf_global_relabel<THREADS, QCAP>(na, bg, lo, hi, T, N, sh, bfs_levels);
         for (uint32_t v = lo + tid; v <= hi; v += kMfThreads) {
             if (na.e[v] > 0) {
                 na.stamp[v] = 1;
@@ -194,7 +209,7 @@ k_maxflow(NodeArrays na, BundleGraph bg, const uint32_t* __restrict__ comp_lo,
                 (unsigned long long)sh.relabels_since * 100 >=
                     (unsigned long long)P.gr_relabel_pct * ncomp) {
                 __syncthreads();  // everyone has read relabels_since
-                last_levels = mf_global_relabel(na, bg, lo, hi, T, N, sh, bfs_levels);
+                last_levels = mf_global_relabel<THREADS, QCAP>(na, bg, lo, hi, T, N, sh, bfs_levels);
                 ++grs;
                 if (tid == 0) sh.relabels_since = 0;
                 rounds_since = 0;
@@ -316,7 +331,7 @@ k_maxflow(NodeArrays na, BundleGraph bg, const uint32_t* __restrict__ comp_lo,
             }
             __syncthreads();
             {
-                Queue tmp = F;
+                Queue<QCAP> tmp = F;
                 F = N;
                 N = tmp;
             }

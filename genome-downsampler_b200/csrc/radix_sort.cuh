@@ -21,6 +21,10 @@ struct ArrayKeys {
     const K* keys;
     __device__ __forceinline__ void begin_tile(size_t, size_t) const {}
     __device__ __forceinline__ K get(size_t i) const { return keys[i]; }
+    __device__ __forceinline__ K get(size_t i, uint32_t& owner) const {
+        owner = (uint32_t)i;
+        return keys[i];
+    }
 };
 
 template <typename K, typename KS>
@@ -40,7 +44,7 @@ k_rs_hist(KS ks, size_t n, int shift, uint32_t n_tiles, uint32_t* __restrict__ t
     tile_hist[(size_t)threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
 }
 
-// vals_in == nullptr means "value = element index" (first pass).
+// vals_in == nullptr means "value = what the key source says" (first pass: the owner read).
 template <typename K, typename KS>
 __global__ void __launch_bounds__(kRsThreads)
 k_rs_scatter(KS ks, const uint32_t* __restrict__ vals_in,
@@ -59,11 +63,13 @@ k_rs_scatter(KS ks, const uint32_t* __restrict__ vals_in,
     const size_t wbase = (size_t)blockIdx.x * kRsTile + (size_t)warp * 32 * kRsItems;
     K key[kRsItems];
     uint32_t rank[kRsItems];
+    uint32_t own[kRsItems];
 #pragma unroll
     for (int k = 0; k < kRsItems; ++k) {
         size_t i = wbase + (size_t)k * 32 + lane;
         bool valid = i < n;
-        key[k] = valid ? ks.get(i) : (K)0;
+        own[k] = 0;
+        key[k] = valid ? ks.get(i, own[k]) : (K)0;
         uint32_t d = (uint32_t)(key[k] >> shift) & 255u;
         uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 256u + lane);
         uint32_t before = __popc(peers & lanemask_lt());
@@ -92,7 +98,7 @@ k_rs_scatter(KS ks, const uint32_t* __restrict__ vals_in,
             uint32_t d = (uint32_t)(key[k] >> shift) & 255u;
             size_t dst = (size_t)gbase[d] + whist[warp][d] + rank[k];
             keys_out[dst] = key[k];
-            vals_out[dst] = vals_in ? vals_in[i] : (uint32_t)i;
+            vals_out[dst] = vals_in ? vals_in[i] : own[k];
         }
     }
 }

@@ -22,13 +22,15 @@ k_select(const uint32_t* __restrict__ b_first, const uint32_t* __restrict__ f,
         fb = f[b];
         first = b_first[b];
     }
-    unsigned long long kept = fb;
+    // a read cut in two (segment split) can be chosen by both parts: count bits newly set
+    unsigned long long kept = 0;
     // small flows: each lane walks its own bundle; large flows: the warp shares the work
     const uint32_t kWide = 64;
     if (fb <= kWide) {
         for (uint32_t r = 0; r < fb; ++r) {
             uint32_t i = sorted_idx[first + r];
-            atomicOr(&bitmap[i >> 5], 1u << (i & 31));
+            uint32_t bit = 1u << (i & 31);
+            kept += (atomicOr(&bitmap[i >> 5], bit) & bit) ? 0 : 1;
         }
     }
     uint32_t wide = __ballot_sync(0xffffffffu, fb > kWide);
@@ -39,7 +41,8 @@ k_select(const uint32_t* __restrict__ b_first, const uint32_t* __restrict__ f,
         uint32_t wfirst = __shfl_sync(0xffffffffu, first, src);
         for (uint32_t r = lane_id(); r < wf; r += 32) {
             uint32_t i = sorted_idx[wfirst + r];
-            atomicOr(&bitmap[i >> 5], 1u << (i & 31));
+            uint32_t bit = 1u << (i & 31);
+            kept += (atomicOr(&bitmap[i >> 5], bit) & bit) ? 0 : 1;
         }
     }
 #pragma unroll

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GDS_ABI_VERSION 1
+#define GDS_ABI_VERSION 2
 
 /* status codes (the reference has none: it logs and exits, cuda_helpers.cuh:13-21) */
 enum {
@@ -74,12 +74,16 @@ typedef struct {
     const uint32_t* amp_end;
 } gds_filter;
 
-/* Deterministic schedule knobs.  Zero-initialised = defaults (64, 150, 1, 0). */
+/* Deterministic schedule knobs.  Zero-initialised = defaults (64, 150, 1, 0) and
+ * seg_len 32768.  seg_len: references longer than this many positions are cut into independent
+ * segments (reads crossing a cut are truncated into one arc per segment and kept if either part
+ * carries flow) — the zero-coverage split generalised; 0xffffffff = never cut. */
 typedef struct {
     uint32_t gr_interval_min;
     uint32_t gr_levels_pct;
     uint32_t gr_relabel_pct;
     uint32_t max_rounds;
+    uint32_t seg_len;
 } gds_params;
 
 /* Results.  Buffers are caller-owned and optional (NULL = not wanted). */
@@ -93,9 +97,10 @@ typedef struct {
     int32_t* demand;         /* [n_nodes] create_demand_function (…cpu_max_flow_solver.cpp:75-87) */
     /* ---- scalars ---- */
     uint64_t n_reads_in, n_filtered, n_kept, n_bundles;
+    uint64_t n_arc_items;    /* sorted arc items = n_filtered + reads cut in two by a segment cut */
     uint32_t n_nodes, n_components;
     int64_t fstar;           /* closed form: sum of source capacities */
-    int64_t flow_value;      /* sink inflow reached by the solve (== fstar) */
+    int64_t flow_value;      /* value of the flow found, on the original network (== fstar) */
     uint64_t rounds_total, rounds_max, pushes, relabels, global_relabels, bfs_levels, max_frontier;
     uint64_t verify_violations; /* GDS_VERIFY: positions with min(cov_out,M) != min(cov_in,M) */
     uint32_t key_bits, sort_passes;

@@ -534,33 +534,132 @@ extern "C" int orc_ref_solve(uint64_t n, const uint32_t* start, const uint32_t* 
 namespace {
 constexpr uint32_t LBL_INF = 0x3fffffffu;
 
+struct VSample {  // per-sample layout of the virtual node space
+    uint32_t obase, vbase, L, nseg, P, W, vn;
+};
+
 struct SyncGraph {
-    uint32_t n_nodes = 0;
-    std::vector<uint32_t> covR;    // coverage of the position between node v and v+1
-    std::vector<int32_t> demand;   // per node
+    uint32_t n_nodes = 0;   // virtual nodes (segments + phantom ids)
+    uint32_t n_onodes = 0;  // original nodes = sum(ref_len + 1)
+    std::vector<VSample> vs;
+    std::vector<uint32_t> covR;    // virtual: coverage of the position between node v and v+1
+    std::vector<int32_t> demand;   // virtual, per node
+    std::vector<uint32_t> ocov;    // original space covR
+    std::vector<int32_t> odemand;  // original space demand
+    int64_t through = 0;           // flow that passes straight through cut nodes when stitched
     std::vector<uint32_t> b_s, b_t, b_mult, b_first;
-    std::vector<uint32_t> sorted_idx;
+    std::vector<uint32_t> sorted_idx;  // owner read of every sorted arc item
     std::vector<uint32_t> out_ptr, in_ptr, in_bid;
     std::vector<uint32_t> comp_lo, comp_hi;
 };
 
+constexpr uint32_t kDefaultSegLen = 32768;
+
+// Long references are cut into segments of seg positions (a generalisation of the zero-coverage
+// split): a read crossing a cut becomes two arcs, truncated at the cut node, one
+// per segment, and is kept if either part carries flow.  Each segment is then an independent
+// max-flow problem; stitched together (surplus on the back arcs) they form a maximum flow of the
+// whole network, so F*, the demand vector and the capped coverage are unchanged.
+//
+// Virtual node ids: sample k, segment j, original node x  ->  vbase + j*W + P + (x - j*seg), with
+// W = P + seg + 1 and P = maxlen-1 phantom ids in front of every segment.  Every arc item is
+// keyed by (fake start id, original length): the right part of a crossing read gets the fake
+// start  (its end node - its length), which falls on a phantom id, so the key keeps the original
+// length and the key width does not grow.  Decoding clamps to the segment's real node range.
 int build_sync_graph(uint32_t n_samples, const uint64_t* read_off, const uint32_t* ref_len,
-                     const uint32_t* start, const uint32_t* end, uint32_t M, SyncGraph& G) {
-    std::vector<uint32_t> base(n_samples + 1, 0);
-    for (uint32_t k = 0; k < n_samples; ++k) base[k + 1] = base[k] + ref_len[k] + 1;
-    G.n_nodes = base[n_samples];
+                     const uint32_t* start, const uint32_t* end, uint32_t M, uint32_t seg_len,
+                     SyncGraph& G) {
     const uint64_t N = read_off[n_samples];
-    const uint32_t nn = G.n_nodes;
-    std::vector<uint32_t> hs(nn + 1, 0), ht(nn + 1, 0);
-    std::vector<uint32_t> rs(N), rt(N);
-    for (uint32_t k = 0; k < n_samples; ++k) {
+    uint32_t minlen = 0xffffffffu, maxlen = 0;
+    for (uint32_t k = 0; k < n_samples; ++k)
         for (uint64_t i = read_off[k]; i < read_off[k + 1]; ++i) {
             if (end[i] >= ref_len[k] || start[i] > end[i]) return -1;
-            rs[i] = base[k] + start[i];
-            rt[i] = base[k] + end[i] + 1;
-            ++hs[rs[i]];
-            ++ht[rt[i]];
+            uint32_t len = end[i] - start[i] + 1;
+            minlen = std::min(minlen, len);
+            maxlen = std::max(maxlen, len);
         }
+    if (N == 0) minlen = maxlen = 1;
+    if (seg_len == 0) seg_len = kDefaultSegLen;
+    const uint32_t seg = seg_len >= maxlen ? seg_len : 0xffffffffu;  // a read crosses <= 1 cut
+    G.vs.resize(n_samples);
+    uint32_t ob = 0, vb = 0;
+    for (uint32_t k = 0; k < n_samples; ++k) {
+        VSample& v = G.vs[k];
+        v.obase = ob;
+        v.vbase = vb;
+        v.L = ref_len[k];
+        v.nseg = v.L > seg ? (v.L + seg - 1) / seg : 1;
+        v.P = v.nseg > 1 ? maxlen - 1 : 0;
+        v.W = v.nseg > 1 ? v.P + seg + 1 : 0;
+        v.vn = v.nseg == 1 ? v.L + 1 : (v.nseg - 1) * v.W + v.P + (v.L - (v.nseg - 1) * seg) + 1;
+        ob += v.L + 1;
+        vb += v.vn;
+    }
+    G.n_onodes = ob;
+    G.n_nodes = vb;
+    const uint32_t nn = G.n_nodes;
+
+    struct Item {
+        uint32_t fake, len, owner, sample;
+    };
+    std::vector<Item> items;
+    items.reserve(N + N / 64);
+    std::vector<Item> extra;
+    for (uint32_t k = 0; k < n_samples; ++k) {
+        const VSample& v = G.vs[k];
+        for (uint64_t i = read_off[k]; i < read_off[k + 1]; ++i) {
+            const uint32_t s = start[i], e = end[i], len = e - s + 1;
+            if (v.nseg == 1) {
+                items.push_back({v.vbase + s, len, (uint32_t)i, k});
+                continue;
+            }
+            const uint32_t js = s / seg, je = e / seg;
+            items.push_back({v.vbase + js * v.W + v.P + (s - js * seg), len, (uint32_t)i, k});
+            if (je > js) {
+                uint32_t vt = v.vbase + je * v.W + v.P + (e + 1 - je * seg);
+                extra.push_back({vt - len, len, (uint32_t)i, k});
+            }
+        }
+    }
+    items.insert(items.end(), extra.begin(), extra.end());  // whole reads first, then right parts
+    std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) {
+        return a.fake != b.fake ? a.fake < b.fake : a.len < b.len;
+    });
+    const uint64_t NI = items.size();
+    G.sorted_idx.resize(NI);
+    std::vector<int64_t> diff(nn + 1, 0), odiff((size_t)G.n_onodes + 1, 0);
+    auto to_orig = [&](const VSample& v, uint32_t vid) -> uint32_t {
+        if (v.nseg == 1) return v.obase + (vid - v.vbase);
+        uint32_t j = (vid - v.vbase) / v.W;
+        return v.obase + j * seg + ((vid - v.vbase) - j * v.W - v.P);
+    };
+    for (uint64_t q = 0; q < NI; ++q) {
+        const Item& it = items[q];
+        G.sorted_idx[q] = it.owner;
+        if (q == 0 || it.fake != items[q - 1].fake || it.len != items[q - 1].len) {
+            const VSample& v = G.vs[it.sample];
+            uint32_t sr = it.fake, tr = it.fake + it.len;
+            if (v.nseg > 1) {
+                uint32_t j = (it.fake - v.vbase) / v.W;
+                uint32_t first = v.vbase + j * v.W + v.P;
+                uint32_t last = first + std::min(seg, v.L - j * seg);
+                sr = std::max(sr, first);
+                tr = std::min(tr, last);
+            }
+            G.b_s.push_back(sr);
+            G.b_t.push_back(tr);
+            G.b_mult.push_back(0);
+            G.b_first.push_back((uint32_t)q);
+        }
+        ++G.b_mult.back();
+    }
+    const uint32_t B = (uint32_t)G.b_s.size();
+    for (uint32_t b = 0; b < B; ++b) {
+        const VSample& v = G.vs[items[G.b_first[b]].sample];
+        diff[G.b_s[b]] += G.b_mult[b];
+        diff[G.b_t[b]] -= G.b_mult[b];
+        odiff[to_orig(v, G.b_s[b])] += G.b_mult[b];
+        odiff[to_orig(v, G.b_t[b])] -= G.b_mult[b];
     }
     G.covR.assign(nn, 0);
     G.demand.assign(nn, 0);
@@ -568,50 +667,45 @@ int build_sync_graph(uint32_t n_samples, const uint64_t* read_off, const uint32_
         int64_t run = 0;
         uint32_t prev_capped = 0;
         for (uint32_t v = 0; v < nn; ++v) {
-            run += (int64_t)hs[v] - (int64_t)ht[v];
+            run += diff[v];
             G.covR[v] = (uint32_t)run;
             uint32_t c = std::min((uint32_t)run, M);
             G.demand[v] = (int32_t)prev_capped - (int32_t)c;
             prev_capped = c;
         }
     }
-    // counting sort by s, then (t, idx) inside each start segment
-    std::vector<uint64_t> seg(nn + 1, 0);
-    for (uint32_t v = 0; v < nn; ++v) seg[v + 1] = seg[v] + hs[v];
-    std::vector<std::pair<uint32_t, uint32_t>> rec(N);  // (t, idx)
+    G.ocov.assign(G.n_onodes, 0);
+    G.odemand.assign(G.n_onodes, 0);
     {
-        std::vector<uint64_t> cursor(seg.begin(), seg.end() - 1);
-        for (uint64_t i = 0; i < N; ++i) rec[cursor[rs[i]]++] = {rt[i], (uint32_t)i};
-    }
-    G.sorted_idx.resize(N);
-    G.out_ptr.assign(nn + 1, 0);
-    for (uint32_t v = 0; v < nn; ++v) {
-        G.out_ptr[v] = (uint32_t)G.b_s.size();
-        uint64_t a = seg[v], b = seg[v + 1];
-        if (a == b) continue;
-        std::sort(rec.begin() + a, rec.begin() + b);  // idx already ascending for equal t (stable fill)
-        for (uint64_t k = a; k < b; ++k) {
-            if (k == a || rec[k].first != rec[k - 1].first) {
-                G.b_s.push_back(v);
-                G.b_t.push_back(rec[k].first);
-                G.b_mult.push_back(0);
-                G.b_first.push_back((uint32_t)k);
-            }
-            ++G.b_mult.back();
-            G.sorted_idx[k] = rec[k].second;
+        int64_t run = 0;
+        uint32_t prev_capped = 0;
+        for (uint32_t v = 0; v < G.n_onodes; ++v) {
+            run += odiff[v];
+            G.ocov[v] = (uint32_t)run;
+            uint32_t c = std::min((uint32_t)run, M);
+            G.odemand[v] = (int32_t)prev_capped - (int32_t)c;
+            prev_capped = c;
         }
     }
-    G.out_ptr[nn] = (uint32_t)G.b_s.size();
-    const uint32_t B = (uint32_t)G.b_s.size();
+    G.through = 0;
+    for (const VSample& v : G.vs)
+        for (uint32_t j = 1; j < v.nseg; ++j) {
+            uint32_t x = v.obase + j * seg;  // cut node: left position x-1, right position x
+            G.through += std::min(std::min(G.ocov[x - 1], M), std::min(G.ocov[x], M));
+        }
+    // out-CSR: bundles are sorted by key and the real start is monotone in the key
+    G.out_ptr.assign(nn + 1, 0);
+    for (uint32_t b = 0; b < B; ++b) ++G.out_ptr[G.b_s[b] + 1];
+    for (uint32_t v = 0; v < nn; ++v) G.out_ptr[v + 1] += G.out_ptr[v];
     G.in_ptr.assign(nn + 1, 0);
     for (uint32_t b = 0; b < B; ++b) ++G.in_ptr[G.b_t[b] + 1];
     for (uint32_t v = 0; v < nn; ++v) G.in_ptr[v + 1] += G.in_ptr[v];
     G.in_bid.resize(B);
     {
         std::vector<uint32_t> cursor(G.in_ptr.begin(), G.in_ptr.end() - 1);
-        for (uint32_t b = 0; b < B; ++b) G.in_bid[cursor[G.b_t[b]]++] = b;  // ascending s within t
+        for (uint32_t b = 0; b < B; ++b) G.in_bid[cursor[G.b_t[b]]++] = b;  // ascending bundle id
     }
-    // components: v and v+1 joined iff covR[v] > 0 (App. A.3)
+    // components: v and v+1 joined iff covR[v] > 0 (App. A.3); segment ends have covR == 0
     uint32_t lo = 0;
     for (uint32_t v = 0; v < nn; ++v) {
         if (G.covR[v] == 0) {
@@ -815,10 +909,10 @@ extern "C" int orc_sync_solve(uint32_t n_samples, const uint64_t* read_off, cons
                               const uint32_t* start, const uint32_t* end, uint32_t M,
                               const orc_sync_params* prm, uint32_t* kept_bitmap,
                               int32_t* demand_out, uint32_t* cov_out, orc_sync_stats* st) {
-    orc_sync_params P = prm ? *prm : orc_sync_params{64, 100, 10, 0};
+    orc_sync_params P = prm ? *prm : orc_sync_params{64, 150, 1, 0, 0};
     auto t0 = clk::now();
     SyncGraph G;
-    if (build_sync_graph(n_samples, read_off, ref_len, start, end, M, G) != 0) return -1;
+    if (build_sync_graph(n_samples, read_off, ref_len, start, end, M, P.seg_len, G) != 0) return -1;
     auto t1 = clk::now();
     const uint32_t nn = G.n_nodes;
     const uint32_t B = (uint32_t)G.b_s.size();
@@ -849,17 +943,18 @@ extern "C" int orc_sync_solve(uint32_t n_samples, const uint64_t* read_off, cons
     uint64_t nk = 0;
     for (uint32_t b = 0; b < B; ++b) {
         for (uint32_t r = 0; r < S.f[b]; ++r) {
-            uint32_t i = G.sorted_idx[G.b_first[b] + r];
+            uint32_t i = G.sorted_idx[G.b_first[b] + r];  // a crossing read may be chosen twice
+            if (!(kept_bitmap[i >> 5] >> (i & 31) & 1u)) ++nk;
             kept_bitmap[i >> 5] |= 1u << (i & 31);
-            ++nk;
         }
     }
     auto t3 = clk::now();
-    int64_t fstar = 0;
-    for (uint32_t v = 0; v < nn; ++v)
-        if (G.demand[v] < 0) fstar += -(int64_t)G.demand[v];
-    if (demand_out) std::copy(G.demand.begin(), G.demand.end(), demand_out);
-    if (cov_out) std::copy(G.covR.begin(), G.covR.end(), cov_out);
+    int64_t fstar = 0;  // closed form on the ORIGINAL network
+    for (uint32_t v = 0; v < G.n_onodes; ++v)
+        if (G.odemand[v] < 0) fstar += -(int64_t)G.odemand[v];
+    if (demand_out) std::copy(G.odemand.begin(), G.odemand.end(), demand_out);
+    if (cov_out) std::copy(G.ocov.begin(), G.ocov.end(), cov_out);
+    out.flow_value -= G.through;  // value of the stitched flow on the original network
     out.fstar = fstar;
     out.n_kept = nk;
     out.n_bundles = B;

@@ -29,7 +29,7 @@ class RefStats(C.Structure):
 class SyncParams(C.Structure):
     _fields_ = [("gr_interval_min", C.c_uint32), ("gr_levels_pct", C.c_uint32),
                 ("gr_relabel_pct", C.c_uint32),
-                ("max_rounds", C.c_uint32)]
+                ("max_rounds", C.c_uint32), ("seg_len", C.c_uint32)]
 
 
 class SyncStats(C.Structure):

@@ -52,10 +52,34 @@ def test_fuzz_ragged_batches(solver, O):
             ss.append(s); ee.append(e); off.append(off[-1] + n)
         s = np.concatenate(ss).astype(np.uint32); e = np.concatenate(ee).astype(np.uint32)
         M = int(rng.integers(1, 12))
-        prm = (int(rng.integers(1, 100)), int(rng.integers(0, 300)), int(rng.integers(0, 5)), 0)
+        # every third case also cuts the references into short segments (reads crossing a cut are
+        # truncated into one arc per segment); seg_len below the longest read disables the split
+        seg = int(rng.integers(1, 120)) if it % 3 == 0 else 0
+        prm = (int(rng.integers(1, 100)), int(rng.integers(0, 300)), int(rng.integers(0, 5)), 0, seg)
         off = np.array(off, np.uint64)
         r = solver.solve(s, e, Ls, M, read_off=off, params=prm, verify=True, want_vectors=True)
         assert_parity(O, r, s, e, Ls, off, M, prm)
+
+
+def test_segmented_reference_matches_oracle_and_unsplit_invariants(solver, O):
+    # one 200 kb reference cut into 4 kb segments: F*, demand and capped coverage must equal the
+    # unsplit solve bit for bit, the kept set must equal the oracle's replay of the same split
+    s, e, q, l = O.gen_reads(777, 300_000, 200_000, 150)
+    M = 40
+    prm = (64, 150, 1, 0, 4096)
+    r = solver.solve(s, e, 200_000, M, params=prm, verify=True, want_vectors=True)
+    assert r.n_components >= 49 and r.n_arc_items > len(s)
+    assert_parity(O, r, s, e, [200_000], [0, len(s)], M, prm)
+    r0 = solver.solve(s, e, 200_000, M, params=(64, 150, 1, 0, 0xffffffff), verify=True,
+                      want_vectors=True)
+    assert r0.n_components == 1 and r0.n_arc_items == len(s)
+    assert r.fstar == r0.fstar == r.flow_value == r0.flow_value
+    assert np.array_equal(r.demand, r0.demand) and np.array_equal(r.cov_capped, r0.cov_capped)
+    assert r0.n_kept <= r.n_kept <= 1.03 * r0.n_kept  # <= M extra reads per cut
+    mask = O.bitmap_to_mask(r.kept_bitmap, len(s))
+    assert int(mask.sum()) == r.n_kept
+    cin = O.coverage_fast(s, e, 200_000); cout = O.coverage_fast(s, e, 200_000, mask)
+    assert np.array_equal(np.minimum(cin, M), np.minimum(cout, M))
 
 
 @pytest.mark.parametrize("name,pairs,M,shape", [
@@ -213,7 +237,9 @@ def test_c4_full_size_properties(solver, O):
     assert r.fstar == 500 == r.flow_value and r.verify_violations == 0
     assert int(np.maximum(0, -r.demand.astype(np.int64)).sum()) == 500
     assert int(r.demand.astype(np.int64).sum()) == 0
-    assert abs(r.n_kept - 500 * 5_000_000 / 150) / r.n_kept < 0.001  # ~ M*L/R, the minimum
+    # ~ M*L/R (the minimum) plus at most M reads per segment cut (152 cuts of 32768 positions)
+    assert 0 <= r.n_kept - 500 * 5_000_000 / 150 < 1000 + 152 * 500
+    assert r.n_components == 153
     mask_bits = int(np.unpackbits(r.kept_bitmap.view(np.uint8)).sum())
     assert mask_bits == r.n_kept
     bm, st = O.sync_solve(s, e, [5_000_000], [0, len(s)], 500, params=PRM)

@@ -171,7 +171,10 @@ def test_sync_schedule_fuzz_invariants(O):
             ss.append(s); ee.append(e); off.append(off[-1] + len(s)); Ls.append(L)
         s = np.concatenate(ss); e = np.concatenate(ee)
         M = int(rng.integers(1, 8))
-        prm = (int(rng.integers(1, 8)), int(rng.integers(0, 300)), int(rng.integers(0, 5)), 0)
+        # every other case cuts the references into short segments: all invariants
+        # below are stated on the ORIGINAL network and must not notice
+        seg = int(rng.integers(1, 60)) if it % 2 else 0
+        prm = (int(rng.integers(1, 8)), int(rng.integers(0, 300)), int(rng.integers(0, 5)), 0, seg)
         bm, st, dem, cov = O.sync_solve(s, e, Ls, off, M, params=prm, want_vectors=True)
         assert st.flow_value == st.fstar
         mask = O.bitmap_to_mask(bm, len(s))
@@ -186,6 +189,31 @@ def test_sync_schedule_fuzz_invariants(O):
             assert np.array_equal(dem[pos:pos + L + 1], dk)
             assert np.array_equal(cov[pos:pos + L], cin) and cov[pos + L] == 0
             pos += L + 1
+
+
+def test_segment_split_is_exact_and_costs_at_most_M_reads_per_cut(O):
+    # config-3 input cut into ever shorter segments: F*, demand and coverage never change, every
+    # result is a valid downsample, the number of kept reads grows by <= M per cut
+    s, e, q, l = O.gen_reads(12345, 50_000, 30_000, 150)
+    M, L = 100, 30_000
+    base = None
+    for seg in (0xffffffff, 8192, 2048, 512, 100):   # 100 < read length: split disabled
+        bm, st, dem, cov = O.sync_solve(s, e, [L], [0, len(s)], M, params=(64, 150, 1, 0, seg),
+                                        want_vectors=True)
+        mask = O.bitmap_to_mask(bm, len(s))
+        cout = O.coverage_fast(s, e, L, mask)
+        assert np.array_equal(np.minimum(cov[:L], M), np.minimum(cout, M))
+        assert st.flow_value == st.fstar == 100 and int(mask.sum()) == st.n_kept
+        if base is None:
+            base = (st.n_kept, dem.copy(), cov.copy())
+            assert st.n_components == 1
+            continue
+        assert np.array_equal(dem, base[1]) and np.array_equal(cov, base[2])
+        cuts = (L + seg - 1) // seg - 1 if seg >= 150 else 0
+        assert st.n_components == cuts + 1
+        assert base[0] <= st.n_kept <= base[0] + M * cuts
+        if cuts == 0:
+            assert st.n_kept == base[0]
 
 
 def test_batch_equals_per_sample(O):
