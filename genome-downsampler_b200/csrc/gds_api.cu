@@ -45,7 +45,7 @@ struct gds_ctx {
     DevBuf comp_start, comp_end, comp_sidx, comp_eidx, comp_lo, comp_hi;
     DevBuf qF, qT, qN, work_counter, comp_stats;
     DevBuf bitmap, cov_tmp, dem_tmp, vdiff, vexcl;
-    DevBuf vs_d, cross_idx, cross_tc, odiff, oexcl, cut_nodes;
+    DevBuf vs_d, cross_idx, cross_tc, odiff, oexcl, cut_nodes, tile_off_d;
     unsigned mf_attr_set = 0;  // bit i: smem attribute set for launch shape i
     Profiler prof;
 
@@ -58,7 +58,7 @@ struct gds_ctx {
                          &n_eadd, &n_snk, &n_g, &n_stamp, &comp_start, &comp_end, &comp_sidx,
                          &comp_eidx, &comp_lo, &comp_hi, &qF, &qT, &qN, &work_counter, &comp_stats,
                          &bitmap, &cov_tmp, &dem_tmp, &vdiff, &vexcl, &vs_d, &cross_idx, &cross_tc,
-                         &odiff, &oexcl, &cut_nodes};
+                         &odiff, &oexcl, &cut_nodes, &tile_off_d};
         for (DevBuf* b : all) b->release();
     }
 };
@@ -137,26 +137,27 @@ void launch_maxflow(gds_ctx* c, const NodeArrays& na, const BundleGraph& bg,
 
 template <typename K>
 void build_bundles(gds_ctx* c, const uint32_t* S, const uint32_t* E, const VLayout& vl,
-                   const uint32_t* cross_idx, size_t N, size_t n_items, uint32_t n_nodes,
-                   int nodebits, int lenbits, uint32_t minlen, int32_t* odiff, uint32_t& B_out,
-                   uint32_t*& sorted_idx_out, int& passes_out) {
+                   const uint32_t* cross_idx, size_t N, const TileMap& tm, bool local_keys,
+                   uint32_t n_nodes, int keybits, int lenbits, uint32_t minlen, int32_t* odiff,
+                   uint32_t& B_out, uint32_t*& sorted_idx_out, int& passes_out) {
     cudaStream_t st = c->stream;
+    const size_t n_items = tm.n_items;
     K* kA = c->keysA.get<K>(n_items);
     K* kB = c->keysB.get<K>(n_items);
     uint32_t* vA = c->valsA.get<uint32_t>(n_items);
     uint32_t* vB = c->valsB.get<uint32_t>(n_items);
-    ReadKeys<K> rk{S, E, vl, cross_idx, N, lenbits, minlen};
-    int where = radix_sort_pairs<K, ReadKeys<K>>(kA, vA, kB, vB, n_items, nodebits + lenbits, true,
-                                                 c->radix, st, &passes_out, &rk);
+    ReadKeys<K> rk{S, E, vl, cross_idx, N, lenbits, minlen, local_keys};
+    int where = radix_sort_pairs<K, ReadKeys<K>>(kA, vA, kB, vB, tm, keybits, c->radix, st,
+                                                 &passes_out, &rk);
     const K* keys = where ? kB : kA;
     sorted_idx_out = where ? vB : vA;
     // bundle heads
-    uint32_t n_tiles = (uint32_t)((n_items + kHeadTile - 1) / kHeadTile);
+    const uint32_t n_tiles = tm.n_tiles;
     uint32_t* tc = c->tile_counts.get<uint32_t>(n_tiles + 1);
     GDS_CUDA(cudaMemsetAsync(tc + n_tiles, 0, sizeof(uint32_t), st));
     {
         KScope ks("heads_count", sizeof(K) * (unsigned long long)n_items, st);
-        k_heads_count<K><<<n_tiles, kHeadThreads, 0, st>>>(keys, n_items, tc);
+        k_heads_count<K><<<n_tiles, kHeadThreads, 0, st>>>(keys, tm, tc);
         GDS_KERNEL_CHECK();
     }
     exclusive_scan_u32(tc, tc, n_tiles + 1, c->scan, st);
@@ -167,7 +168,7 @@ void build_bundles(gds_ctx* c, const uint32_t* S, const uint32_t* E, const VLayo
     K* b_key = c->b_key.get<K>(B + 1);
     {
         KScope ks("heads_write", sizeof(K) * (unsigned long long)n_items + (4ull + sizeof(K)) * B, st);
-        k_heads_write<K><<<n_tiles, kHeadThreads, 0, st>>>(keys, n_items, tc, b_first, b_key);
+        k_heads_write<K><<<n_tiles, kHeadThreads, 0, st>>>(keys, tm, tc, b_first, b_key);
         GDS_KERNEL_CHECK();
     }
     uint32_t* b_s = c->b_s.get<uint32_t>(B + 1);
@@ -182,8 +183,9 @@ void build_bundles(gds_ctx* c, const uint32_t* S, const uint32_t* E, const VLayo
     if (B) {
         KScope ks("bundle_fill", (sizeof(K) + 8ull + 12ull + 16ull) * B, st);
         k_bundle_fill<K><<<div_up(B, 256), 256, 0, st>>>(b_key, b_first, sorted_idx_out, B,
-                                                         (uint32_t)n_items, lenbits, minlen, vl, b_s,
-                                                         b_t, b_mult, diff, outdeg, indeg, odiff);
+                                                         (uint32_t)n_items, lenbits, minlen, vl,
+                                                         local_keys, b_s, b_t, b_mult, diff, outdeg,
+                                                         indeg, odiff);
         GDS_KERNEL_CHECK();
     }
 }
@@ -547,12 +549,30 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         }
         out->n_arc_items = n_items;
         if (N > 0) {
-            if (nodebits + lenbits <= 32)
-                build_bundles<uint32_t>(c, S, E, vl, cross_idx, N, n_items, n_nodes, nodebits,
+            // the arc sort is segmented by sample unless some sample is cut into segments (then the
+            // right parts live after all reads and one group with global keys is sorted)
+            const bool local_keys = !split && ns > 1;
+            TileMap tm{nullptr, nullptr, 1, tiles_for(n_items), n_items};
+            int keybits = nodebits + lenbits;
+            if (local_keys) {
+                std::vector<uint32_t> toff(ns + 1, 0);
+                uint32_t maxvn = 1;
+                for (uint32_t k = 0; k < ns; ++k) {
+                    toff[k + 1] = toff[k] + tiles_for(foff_host[k + 1] - foff_host[k]);
+                    maxvn = std::max(maxvn, rd->ref_len[k] + 1);
+                }
+                uint32_t* toff_d = c->tile_off_d.get<uint32_t>(ns + 1);
+                GDS_CUDA(cudaMemcpy(toff_d, toff.data(), (ns + 1) * 4, cudaMemcpyHostToDevice));
+                tm = TileMap{toff_d, foff_dev, ns, toff[ns], n_items};
+                keybits = bits_for(maxvn - 1) + lenbits;
+            }
+            out->key_bits = keybits;
+            if (keybits <= 32)
+                build_bundles<uint32_t>(c, S, E, vl, cross_idx, N, tm, local_keys, n_nodes, keybits,
                                         lenbits, minlen, odiff, B, sorted_idx, sort_passes);
             else
-                build_bundles<unsigned long long>(c, S, E, vl, cross_idx, N, n_items, n_nodes,
-                                                  nodebits, lenbits, minlen, odiff, B, sorted_idx,
+                build_bundles<unsigned long long>(c, S, E, vl, cross_idx, N, tm, local_keys, n_nodes,
+                                                  keybits, lenbits, minlen, odiff, B, sorted_idx,
                                                   sort_passes);
         } else {
             int32_t* diff = c->diff.get<int32_t>(n_nodes + 1);
@@ -646,7 +666,8 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             uint32_t* tvB = c->tvB.get<uint32_t>(B);
             GDS_CUDA(cudaMemcpyAsync(tkA, c->b_t.as<uint32_t>(), (size_t)B * 4,
                                      cudaMemcpyDeviceToDevice, st));
-            int w = radix_sort_pairs<uint32_t>(tkA, tvA, tkB, tvB, B, nodebits, true, c->radix, st);
+            TileMap btm{nullptr, nullptr, 1, tiles_for(B), B};
+            int w = radix_sort_pairs<uint32_t>(tkA, tvA, tkB, tvB, btm, nodebits, c->radix, st);
             in_bid = w ? tvB : tvA;
         }
         if (!out_dev) {

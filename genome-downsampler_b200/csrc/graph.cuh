@@ -12,14 +12,10 @@
 #pragma once
 #include "common.cuh"
 #include "prep.cuh"
+#include "radix_sort.cuh"
 #include "scan.cuh"
 
 namespace gds {
-
-__device__ __forceinline__ uint32_t* tile_sample_range() {
-    __shared__ uint32_t r[2];
-    return r;
-}
 
 // Per-sample layout of the virtual node space.  A reference longer than seg positions is cut
 // into nseg segments (the zero-coverage split of SURVEY App. A.3, generalised): a read crossing
@@ -75,6 +71,9 @@ struct VLayout {
 // if they cross a cut), items [n_reads, n_reads + n_cross) the right parts of crossing reads
 // (cross_idx = their read indices, ascending).  key = (fake start << lenbits) | (len - minlen);
 // value = owner read index.
+//   local  (no sample is segmented): the sort is segmented by sample, so the key is relative to
+//          the sample — simply (start << lenbits) | (len - minlen), no sample lookup at all;
+//   global (some sample is segmented): one group, key on the global virtual node id.
 template <typename K>
 struct ReadKeys {
     const uint32_t* S;
@@ -84,36 +83,21 @@ struct ReadKeys {
     size_t n_reads;
     int lenbits;
     uint32_t minlen;
-    __device__ __forceinline__ void begin_tile(size_t first, size_t n) const {
-        if (threadIdx.x == 0) {
-            uint32_t* r = tile_sample_range();
-            size_t last = min(first + (size_t)blockDim.x * 64, n_reads) - 1;
-            if (vl.n_samples == 1 || first >= n_reads) {
-                r[0] = r[1] = 0;
-            } else {
-                r[0] = find_sample(vl.off, vl.n_samples, first);
-                r[1] = find_sample(vl.off, vl.n_samples, last);
-            }
-        }
-    }
-    __device__ __forceinline__ K get(size_t i, uint32_t& owner) const {
+    bool local;
+    __device__ __forceinline__ K get(size_t i) const {
         if (i < n_reads) {
-            const uint32_t* r = tile_sample_range();
-            uint32_t k = r[0];
-            if (r[0] != r[1]) k = find_sample(vl.off, vl.n_samples, i);
-            uint32_t s = S[i], e = E[i];
-            owner = (uint32_t)i;
+            uint32_t s = ld_stream(S + i), e = ld_stream(E + i);
+            if (local) return ((K)s << lenbits) | (K)(e - s + 1 - minlen);
+            uint32_t k = vl.n_samples == 1 ? 0 : find_sample(vl.off, vl.n_samples, i);
             return ((K)vl.fake_primary(vl.vs[k], s) << lenbits) | (K)(e - s + 1 - minlen);
         }
         uint32_t rd = cross_idx[i - n_reads];
         uint32_t k = vl.n_samples == 1 ? 0 : find_sample(vl.off, vl.n_samples, rd);
         uint32_t s = S[rd], e = E[rd];
-        owner = rd;
         return ((K)vl.fake_right(vl.vs[k], s, e) << lenbits) | (K)(e - s + 1 - minlen);
     }
-    __device__ __forceinline__ K get(size_t i) const {
-        uint32_t o;
-        return get(i, o);
+    __device__ __forceinline__ uint32_t owner(size_t i) const {
+        return i < n_reads ? (uint32_t)i : cross_idx[i - n_reads];
     }
 };
 
@@ -167,19 +151,25 @@ k_cross_write(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, si
         if (hit[q]) cross_idx[ex++] = (uint32_t)(base + q);
 }
 
+// Bundle heads over the sorted keys: item j starts a bundle if it is the first item of its group
+// or its key differs from its predecessor's.  Same tile geometry as the sort (tiles never
+// straddle a group).
 constexpr int kHeadThreads = 1024;
-constexpr int kHeadItems = 4;
-constexpr int kHeadTile = kHeadThreads * kHeadItems;
+constexpr int kHeadItems = kRsTile / kHeadThreads;
 
 template <typename K>
 __global__ void __launch_bounds__(kHeadThreads)
-k_heads_count(const K* __restrict__ keys, size_t n, uint32_t* __restrict__ tile_counts) {
-    size_t base = (size_t)blockIdx.x * kHeadTile + (size_t)threadIdx.x * kHeadItems;
+k_heads_count(const K* __restrict__ keys, TileMap tm, uint32_t* __restrict__ tile_counts) {
+    const TilePos tp = locate_tile(tm, blockIdx.x);
     uint32_t c = 0;
 #pragma unroll
     for (int k = 0; k < kHeadItems; ++k) {
-        size_t j = base + k;
-        if (j < n) c += (j == 0 || keys[j] != keys[j - 1]) ? 1u : 0u;
+        uint32_t j = threadIdx.x * kHeadItems + k;
+        if (j < tp.n_valid) {
+            size_t g = tp.first + j;
+            bool head = (j == 0 && tp.tile_in_g == 0) || keys[g] != keys[g - 1];
+            c += head ? 1u : 0u;
+        }
     }
     c = __reduce_add_sync(0xffffffffu, c);
     __shared__ uint32_t tot;
@@ -192,24 +182,29 @@ k_heads_count(const K* __restrict__ keys, size_t n, uint32_t* __restrict__ tile_
 
 template <typename K>
 __global__ void __launch_bounds__(kHeadThreads)
-k_heads_write(const K* __restrict__ keys, size_t n, const uint32_t* __restrict__ tile_offs,
+k_heads_write(const K* __restrict__ keys, TileMap tm, const uint32_t* __restrict__ tile_offs,
               uint32_t* __restrict__ b_first, K* __restrict__ b_key) {
     __shared__ uint32_t total;
-    size_t base = (size_t)blockIdx.x * kHeadTile + (size_t)threadIdx.x * kHeadItems;
+    const TilePos tp = locate_tile(tm, blockIdx.x);
     bool head[kHeadItems];
     uint32_t c = 0;
 #pragma unroll
     for (int k = 0; k < kHeadItems; ++k) {
-        size_t j = base + k;
-        head[k] = j < n && (j == 0 || keys[j] != keys[j - 1]);
+        uint32_t j = threadIdx.x * kHeadItems + k;
+        head[k] = false;
+        if (j < tp.n_valid) {
+            size_t g = tp.first + j;
+            head[k] = (j == 0 && tp.tile_in_g == 0) || keys[g] != keys[g - 1];
+        }
         c += head[k] ? 1u : 0u;
     }
     uint32_t ex = block_excl_scan(c, &total) + tile_offs[blockIdx.x];
 #pragma unroll
     for (int k = 0; k < kHeadItems; ++k) {
         if (head[k]) {
-            b_first[ex] = (uint32_t)(base + k);
-            b_key[ex] = keys[base + k];
+            size_t g = tp.first + threadIdx.x * kHeadItems + k;
+            b_first[ex] = (uint32_t)g;
+            b_key[ex] = keys[g];
             ++ex;
         }
     }
@@ -222,7 +217,8 @@ template <typename K>
 __global__ void __launch_bounds__(256)
 k_bundle_fill(const K* __restrict__ b_key, uint32_t* __restrict__ b_first,
               const uint32_t* __restrict__ sorted_owner, uint32_t B, uint32_t n_items, int lenbits,
-              uint32_t minlen, VLayout vl, uint32_t* __restrict__ b_s, uint32_t* __restrict__ b_t,
+              uint32_t minlen, VLayout vl, bool local_keys, uint32_t* __restrict__ b_s,
+              uint32_t* __restrict__ b_t,
               uint32_t* __restrict__ b_mult, int32_t* __restrict__ diff,
               uint32_t* __restrict__ outdeg, uint32_t* __restrict__ indeg,
               int32_t* __restrict__ odiff /* null when virtual == original */) {
@@ -235,6 +231,7 @@ k_bundle_fill(const K* __restrict__ b_key, uint32_t* __restrict__ b_first,
     uint32_t owner = sorted_owner[first_item];
     uint32_t k = vl.n_samples == 1 ? 0 : find_sample(vl.off, vl.n_samples, owner);
     const VSample v = vl.vs[k];
+    if (local_keys) fake += v.vbase;  // the segmented sort keys are relative to the sample
     uint32_t first, last;
     vl.seg_range(v, fake, first, last);
     uint32_t s = max(fake, first);
