@@ -146,9 +146,16 @@ void build_bundles(gds_ctx* c, const uint32_t* S, const uint32_t* E, const VLayo
     K* kB = c->keysB.get<K>(n_items);
     uint32_t* vA = c->valsA.get<uint32_t>(n_items);
     uint32_t* vB = c->valsB.get<uint32_t>(n_items);
-    ReadKeys<K> rk{S, E, vl, cross_idx, N, lenbits, minlen, local_keys};
-    int where = radix_sort_pairs<K, ReadKeys<K>>(kA, vA, kB, vB, tm, keybits, c->radix, st,
-                                                 &passes_out, &rk);
+    int where;
+    if (local_keys) {
+        ReadKeys<K, true> rk{S, E, vl, cross_idx, N, lenbits, minlen};
+        where = radix_sort_pairs<K, ReadKeys<K, true>>(kA, vA, kB, vB, tm, keybits, c->radix, st,
+                                                       &passes_out, &rk);
+    } else {
+        ReadKeys<K, false> rk{S, E, vl, cross_idx, N, lenbits, minlen};
+        where = radix_sort_pairs<K, ReadKeys<K, false>>(kA, vA, kB, vB, tm, keybits, c->radix, st,
+                                                        &passes_out, &rk);
+    }
     const K* keys = where ? kB : kA;
     sorted_idx_out = where ? vB : vA;
     // bundle heads
@@ -466,10 +473,10 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         uint32_t minlen = 1, maxlen = 1;
         int lenbits = 0;
         if (N > 0) {
-            int grid = std::min<long long>(div_up(N, 256 * 8), kNumSMs * 16);
             {
                 KScope ks("validate", 8ull * N, st);
-                k_validate<<<grid, 256, 0, st>>>(S, E, N, foff_dev, reflen_d, ns, stats);
+                k_validate<<<div_up(N, kValTile), kValThreads, 0, st>>>(S, E, N, foff_dev, reflen_d,
+                                                                        ns, stats);
                 GDS_KERNEL_CHECK();
             }
             uint32_t hstats[3];
@@ -551,10 +558,10 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         if (N > 0) {
             // the arc sort is segmented by sample unless some sample is cut into segments (then the
             // right parts live after all reads and one group with global keys is sorted)
-            const bool local_keys = !split && ns > 1;
+            const bool local_keys = !split;
             TileMap tm{nullptr, nullptr, 1, tiles_for(n_items), n_items};
             int keybits = nodebits + lenbits;
-            if (local_keys) {
+            if (local_keys && ns > 1) {
                 std::vector<uint32_t> toff(ns + 1, 0);
                 uint32_t maxvn = 1;
                 for (uint32_t k = 0; k < ns; ++k) {

@@ -71,11 +71,12 @@ struct VLayout {
 // if they cross a cut), items [n_reads, n_reads + n_cross) the right parts of crossing reads
 // (cross_idx = their read indices, ascending).  key = (fake start << lenbits) | (len - minlen);
 // value = owner read index.
-//   local  (no sample is segmented): the sort is segmented by sample, so the key is relative to
-//          the sample — simply (start << lenbits) | (len - minlen), no sample lookup at all;
+//   LOCAL  (no sample is segmented): the sort is segmented by sample, so the key is relative to
+//          the sample — simply (start << lenbits) | (len - minlen): branch-free, no lookups;
 //   global (some sample is segmented): one group, key on the global virtual node id.
-template <typename K>
+template <typename K, bool LOCAL>
 struct ReadKeys {
+    typedef uint2 Raw;  // (start, end) of the owner read
     const uint32_t* S;
     const uint32_t* E;
     VLayout vl;
@@ -83,22 +84,32 @@ struct ReadKeys {
     size_t n_reads;
     int lenbits;
     uint32_t minlen;
-    bool local;
-    __device__ __forceinline__ K get(size_t i) const {
+    __device__ __forceinline__ Raw load(size_t i) const {
+        if (LOCAL) return make_uint2(ld_stream(S + i), ld_stream(E + i));
+        size_t rd = i < n_reads ? i : (size_t)cross_idx[i - n_reads];
+        return make_uint2(S[rd], E[rd]);
+    }
+    __device__ __forceinline__ K make(Raw r, size_t i) const {
+        const K low = (K)(r.y - r.x + 1 - minlen);
+        if (LOCAL) return ((K)r.x << lenbits) | low;
         if (i < n_reads) {
-            uint32_t s = ld_stream(S + i), e = ld_stream(E + i);
-            if (local) return ((K)s << lenbits) | (K)(e - s + 1 - minlen);
             uint32_t k = vl.n_samples == 1 ? 0 : find_sample(vl.off, vl.n_samples, i);
-            return ((K)vl.fake_primary(vl.vs[k], s) << lenbits) | (K)(e - s + 1 - minlen);
+            return ((K)vl.fake_primary(vl.vs[k], r.x) << lenbits) | low;
         }
         uint32_t rd = cross_idx[i - n_reads];
         uint32_t k = vl.n_samples == 1 ? 0 : find_sample(vl.off, vl.n_samples, rd);
-        uint32_t s = S[rd], e = E[rd];
-        return ((K)vl.fake_right(vl.vs[k], s, e) << lenbits) | (K)(e - s + 1 - minlen);
+        return ((K)vl.fake_right(vl.vs[k], r.x, r.y) << lenbits) | low;
     }
     __device__ __forceinline__ uint32_t owner(size_t i) const {
+        if (LOCAL) return (uint32_t)i;
         return i < n_reads ? (uint32_t)i : cross_idx[i - n_reads];
     }
+    // LOCAL keys with 32-bit K are eligible for the TMA-staged first pass (radix_sort.cuh)
+    static constexpr bool kTmaReads = LOCAL && sizeof(K) == 4;
+    const uint32_t* tma_a() const { return S; }
+    const uint32_t* tma_b() const { return E; }
+    int tma_lenbits() const { return lenbits; }
+    uint32_t tma_minlen() const { return minlen; }
 };
 
 // crossing reads -> ascending list of their indices (tile counts -> scan -> write)
@@ -155,23 +166,46 @@ k_cross_write(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, si
 // or its key differs from its predecessor's.  Same tile geometry as the sort (tiles never
 // straddle a group).
 constexpr int kHeadThreads = 1024;
-constexpr int kHeadItems = kRsTile / kHeadThreads;
+constexpr int kHeadRows = kRsTile / kHeadThreads;  // warp w owns items [w*32*rows, (w+1)*32*rows)
+
+// head flags of this lane's items, one ballot word per row (coalesced 128-byte row loads; the
+// predecessor comes from the neighbouring lane, lane 0 re-reads one key)
+template <typename K>
+__device__ __forceinline__ void head_ballots(const K* __restrict__ keys, const TilePos& tp,
+                                             uint32_t (&bal)[kHeadRows]) {
+    const uint32_t lane = lane_id();
+    const uint32_t wofs = (threadIdx.x >> 5) * 32 * kHeadRows;
+    K kk[kHeadRows];
+#pragma unroll
+    for (int r = 0; r < kHeadRows; ++r) {
+        uint32_t j = wofs + r * 32 + lane;
+        kk[r] = keys[tp.first + (j < tp.n_valid ? j : 0u)];
+    }
+    // predecessor of the warp chunk's first item (unless it is the first item of the group)
+    K prev_chunk = (K)0;
+    const bool chunk_has_prev = !(wofs == 0 && tp.tile_in_g == 0) && wofs < tp.n_valid;
+    if (lane == 0 && chunk_has_prev) prev_chunk = keys[tp.first + wofs - 1];
+#pragma unroll
+    for (int r = 0; r < kHeadRows; ++r) {
+        uint32_t j = wofs + r * 32 + lane;
+        K up = __shfl_up_sync(0xffffffffu, kk[r], 1);
+        K last_prev_row = __shfl_sync(0xffffffffu, r ? kk[r ? r - 1 : 0] : prev_chunk, r ? 31 : 0);
+        K pred = lane ? up : last_prev_row;
+        bool first_of_group = j == 0 && tp.tile_in_g == 0;
+        bool head = j < tp.n_valid && (first_of_group || kk[r] != pred);
+        bal[r] = __ballot_sync(0xffffffffu, head);
+    }
+}
 
 template <typename K>
 __global__ void __launch_bounds__(kHeadThreads)
 k_heads_count(const K* __restrict__ keys, TileMap tm, uint32_t* __restrict__ tile_counts) {
     const TilePos tp = locate_tile(tm, blockIdx.x);
+    uint32_t bal[kHeadRows];
+    head_ballots<K>(keys, tp, bal);
     uint32_t c = 0;
 #pragma unroll
-    for (int k = 0; k < kHeadItems; ++k) {
-        uint32_t j = threadIdx.x * kHeadItems + k;
-        if (j < tp.n_valid) {
-            size_t g = tp.first + j;
-            bool head = (j == 0 && tp.tile_in_g == 0) || keys[g] != keys[g - 1];
-            c += head ? 1u : 0u;
-        }
-    }
-    c = __reduce_add_sync(0xffffffffu, c);
+    for (int r = 0; r < kHeadRows; ++r) c += __popc(bal[r]);
     __shared__ uint32_t tot;
     if (threadIdx.x == 0) tot = 0;
     __syncthreads();
@@ -184,29 +218,32 @@ template <typename K>
 __global__ void __launch_bounds__(kHeadThreads)
 k_heads_write(const K* __restrict__ keys, TileMap tm, const uint32_t* __restrict__ tile_offs,
               uint32_t* __restrict__ b_first, K* __restrict__ b_key) {
-    __shared__ uint32_t total;
+    __shared__ uint32_t wtot[32];
     const TilePos tp = locate_tile(tm, blockIdx.x);
-    bool head[kHeadItems];
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t wofs = warp * 32 * kHeadRows;
+    uint32_t bal[kHeadRows];
+    head_ballots<K>(keys, tp, bal);
     uint32_t c = 0;
 #pragma unroll
-    for (int k = 0; k < kHeadItems; ++k) {
-        uint32_t j = threadIdx.x * kHeadItems + k;
-        head[k] = false;
-        if (j < tp.n_valid) {
-            size_t g = tp.first + j;
-            head[k] = (j == 0 && tp.tile_in_g == 0) || keys[g] != keys[g - 1];
-        }
-        c += head[k] ? 1u : 0u;
+    for (int r = 0; r < kHeadRows; ++r) c += __popc(bal[r]);
+    if (lane == 0) wtot[warp] = c;
+    __syncthreads();
+    uint32_t ex = tile_offs[blockIdx.x];
+    {   // exclusive prefix over the 32 warp totals
+        uint32_t v = wtot[lane];
+        uint32_t incl = warp_incl_scan(v);
+        ex += __shfl_sync(0xffffffffu, incl - v, warp);
     }
-    uint32_t ex = block_excl_scan(c, &total) + tile_offs[blockIdx.x];
 #pragma unroll
-    for (int k = 0; k < kHeadItems; ++k) {
-        if (head[k]) {
-            size_t g = tp.first + threadIdx.x * kHeadItems + k;
-            b_first[ex] = (uint32_t)g;
-            b_key[ex] = keys[g];
-            ++ex;
+    for (int r = 0; r < kHeadRows; ++r) {
+        if (bal[r] >> lane & 1u) {
+            size_t g = tp.first + wofs + r * 32 + lane;
+            uint32_t slot = ex + __popc(bal[r] & lanemask_lt());
+            b_first[slot] = (uint32_t)g;
+            b_key[slot] = keys[g];
         }
+        ex += __popc(bal[r]);
     }
 }
 

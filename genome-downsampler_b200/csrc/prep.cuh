@@ -89,21 +89,46 @@ __global__ void k_filter_offsets(const uint64_t* __restrict__ off, uint32_t n_sa
 }
 
 // Validation + read-length range over the (post-filter) reads.  stats[0]=min len, [1]=max len,
-// [2]=error count.
-__global__ void __launch_bounds__(256)
+// [2]=error count.  One block covers a contiguous chunk of reads; the sample of a read is looked
+// up once per block when the chunk lies inside one sample (the common case).
+constexpr int kValThreads = 256;
+constexpr int kValItems = 16;
+constexpr int kValTile = kValThreads * kValItems;
+
+__global__ void __launch_bounds__(kValThreads)
 k_validate(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, size_t n,
            const uint64_t* __restrict__ off, const uint32_t* __restrict__ ref_len,
            uint32_t n_samples, uint32_t* __restrict__ stats) {
+    __shared__ uint32_t krange[2];
+    const size_t base = (size_t)blockIdx.x * kValTile;
+    if (threadIdx.x == 0) {
+        size_t last = min(base + kValTile, n) - 1;
+        krange[0] = n_samples == 1 ? 0 : find_sample(off, n_samples, base);
+        krange[1] = n_samples == 1 ? 0 : find_sample(off, n_samples, last);
+    }
+    __syncthreads();
+    const uint32_t k0 = krange[0];
+    const bool one = k0 == krange[1];
+    const uint32_t L0 = ref_len[k0];
+    uint32_t s[kValItems], e[kValItems];
+#pragma unroll
+    for (int q = 0; q < kValItems; ++q) {
+        size_t i = base + (size_t)q * kValThreads + threadIdx.x;
+        size_t ii = i < n ? i : base;
+        s[q] = ld_stream(S + ii);
+        e[q] = ld_stream(E + ii);
+    }
     uint32_t mn = 0xffffffffu, mx = 0, bad = 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (size_t)gridDim.x * blockDim.x) {
-        uint32_t s = ld_stream(S + i), e = ld_stream(E + i);
-        uint32_t k = n_samples == 1 ? 0 : find_sample(off, n_samples, i);
-        if (s > e || e >= ref_len[k]) {
+#pragma unroll
+    for (int q = 0; q < kValItems; ++q) {
+        size_t i = base + (size_t)q * kValThreads + threadIdx.x;
+        if (i >= n) continue;
+        uint32_t L = one ? L0 : ref_len[find_sample(off, n_samples, i)];
+        if (s[q] > e[q] || e[q] >= L) {
             ++bad;
             continue;
         }
-        uint32_t len = e - s + 1;
+        uint32_t len = e[q] - s[q] + 1;
         mn = min(mn, len);
         mx = max(mx, len);
     }
@@ -113,10 +138,23 @@ k_validate(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, size_
         mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         bad += __shfl_xor_sync(0xffffffffu, bad, o);
     }
+    __shared__ uint32_t red[3];
+    if (threadIdx.x == 0) {
+        red[0] = 0xffffffffu;
+        red[1] = 0;
+        red[2] = 0;
+    }
+    __syncthreads();
     if (lane_id() == 0) {
-        if (mn != 0xffffffffu) atomicMin(&stats[0], mn);
-        if (mx) atomicMax(&stats[1], mx);
-        if (bad) atomicAdd(&stats[2], bad);
+        atomicMin(&red[0], mn);
+        atomicMax(&red[1], mx);
+        if (bad) atomicAdd(&red[2], bad);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (red[0] != 0xffffffffu) atomicMin(&stats[0], red[0]);
+        if (red[1]) atomicMax(&stats[1], red[1]);
+        if (red[2]) atomicAdd(&stats[2], red[2]);
     }
 }
 

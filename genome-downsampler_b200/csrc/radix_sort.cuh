@@ -19,6 +19,9 @@
 #include "prep.cuh"
 #include "scan.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace gds {
 
 constexpr int kRsThreads = 512;
@@ -72,11 +75,22 @@ __device__ __forceinline__ TilePos locate_tile(const TileMap& tm, uint32_t tile)
 }
 
 // Key sources: a plain array, or a functor that builds the key from the reads (first pass).
+// Two-step interface so the kernels can issue ALL loads of a thread before any use:
+//   Raw load(i)      — the global loads, nothing else (branch-free on the hot paths)
+//   K   make(raw, i) — arithmetic on the loaded values
 template <typename K>
 struct ArrayKeys {
+    typedef K Raw;
     const K* keys;
-    __device__ __forceinline__ K get(size_t i) const { return keys[i]; }
+    __device__ __forceinline__ Raw load(size_t i) const { return keys[i]; }
+    __device__ __forceinline__ K make(Raw r, size_t) const { return r; }
     __device__ __forceinline__ uint32_t owner(size_t i) const { return (uint32_t)i; }
+    // not a (start, end) source: the TMA first-pass kernel does not apply
+    static constexpr bool kTmaReads = false;
+    const uint32_t* tma_a() const { return nullptr; }
+    const uint32_t* tma_b() const { return nullptr; }
+    int tma_lenbits() const { return 0; }
+    uint32_t tma_minlen() const { return 0; }
 };
 
 template <typename K, typename KS>
@@ -87,16 +101,18 @@ k_rs_hist(KS ks, TileMap tm, int shift, uint32_t* __restrict__ tile_hist) {
     const TilePos tp = locate_tile(tm, blockIdx.x);
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5;
-    K key[kRsItems];
+    typename KS::Raw raw[kRsItems];
 #pragma unroll
     for (int k = 0; k < kRsItems; ++k) {
         uint32_t j = (uint32_t)k * kRsThreads + threadIdx.x;
-        key[k] = j < tp.n_valid ? ks.get(tp.first + j) : (K)0;
+        // out-of-range lanes re-read the tile's first item: the load stays unconditional
+        raw[k] = ks.load(tp.first + (j < tp.n_valid ? j : 0u));
     }
 #pragma unroll
     for (int k = 0; k < kRsItems; ++k) {
         uint32_t j = (uint32_t)k * kRsThreads + threadIdx.x;
-        if (j < tp.n_valid) atomicAdd(&h[warp][(uint32_t)(key[k] >> shift) & 255u], 1u);
+        K key = ks.make(raw[k], tp.first + j);
+        if (j < tp.n_valid) atomicAdd(&h[warp][(uint32_t)(key >> shift) & 255u], 1u);
     }
     __syncthreads();
     if (threadIdx.x < 256) {
@@ -107,18 +123,40 @@ k_rs_hist(KS ks, TileMap tm, int shift, uint32_t* __restrict__ tile_hist) {
     }
 }
 
+// Lanes holding the same 8-bit digit, from 8 ballots (fixed latency; the MATCH.ANY instruction
+// measured ~35% slower here: it iterates once per distinct value, ~30 times for random digits).
+// Per bit: test, vote, conditional complement, and — hand-written so ptxas keeps it at 4 SASS.
+__device__ __forceinline__ uint32_t match_digit(uint32_t d, uint32_t valid_mask) {
+    uint32_t peers = valid_mask;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        asm("{\n"
+            ".reg .pred p;\n"
+            ".reg .b32 m;\n"
+            "and.b32 m, %1, %2;\n"
+            "setp.ne.u32 p, m, 0;\n"
+            "vote.sync.ballot.b32 m, p, 0xffffffff;\n"
+            "@!p not.b32 m, m;\n"
+            "and.b32 %0, %0, m;\n"
+            "}\n"
+            : "+r"(peers)
+            : "r"(d), "r"(1u << b));
+    }
+    return peers;
+}
+
 template <typename K>
 struct RsSmem {
     K skey[kRsTile];
     uint32_t sval[kRsTile];
-    uint16_t whist[kRsWarps][256];  // running per-warp digit counts (<= 512 per warp)
-    uint32_t dstart[256];           // first slot of each digit in the reordered tile
-    uint32_t gbase[256];            // global position of slot 0 of each digit's run, minus dstart
+    uint32_t whist[kRsWarps][256];  // per-warp digit counts, then first slot per (warp, digit)
+    uint32_t gbase[256];            // global position of the digit's run minus its first slot
+    uint32_t dstart[256];
     uint32_t wsum[8];
 };
 
-// vals_in == nullptr means "value = what the key source says" (first pass: the owner read).
-template <typename K, typename KS, int MIN_CTAS>
+// vals_in is read when HAS_VALS, else the value is what the key source says (the owner read).
+template <typename K, typename KS, bool HAS_VALS, int MIN_CTAS>
 __global__ void __launch_bounds__(kRsThreads, MIN_CTAS)
 k_rs_scatter(KS ks, const uint32_t* __restrict__ vals_in, K* __restrict__ keys_out,
              uint32_t* __restrict__ vals_out, TileMap tm, int shift,
@@ -126,88 +164,361 @@ k_rs_scatter(KS ks, const uint32_t* __restrict__ vals_in, K* __restrict__ keys_o
     extern __shared__ __align__(16) unsigned char rs_smem_raw[];
     RsSmem<K>& sm = *reinterpret_cast<RsSmem<K>*>(rs_smem_raw);
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-    for (int i = threadIdx.x; i < kRsWarps * 256 / 2; i += kRsThreads)
-        reinterpret_cast<uint32_t*>(&sm.whist[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < kRsWarps * 256; i += kRsThreads) (&sm.whist[0][0])[i] = 0;
     const TilePos tp = locate_tile(tm, blockIdx.x);
     if (threadIdx.x < 256)
         sm.gbase[threadIdx.x] = tile_off_scanned[(size_t)tp.hist_base +
                                                  (size_t)threadIdx.x * tp.tiles_g + tp.tile_in_g];
 
     // warp w owns the contiguous chunk [w*32*ITEMS, (w+1)*32*ITEMS) of the tile; row k covers 32
-    // consecutive keys, so (warp, row, lane) order == input order.  All loads are issued first.
-    const uint32_t wofs = warp * 32 * kRsItems;
+    // consecutive keys, so (warp, row, lane) order == input order.  Loads are batched 8 rows at a
+    // time (register budget) and never predicated: short tiles re-read their first item.
+    const uint32_t wofs = warp * 32 * kRsItems + lane;
+    const bool full = tp.n_valid == (uint32_t)kRsTile;
+    const size_t gfirst = tp.first + wofs;
     K key[kRsItems];
+    constexpr int kHalf = kRsItems / 2;
 #pragma unroll
-    for (int k = 0; k < kRsItems; ++k) {
-        uint32_t j = wofs + (uint32_t)k * 32 + lane;
-        key[k] = j < tp.n_valid ? ks.get(tp.first + j) : (K)0;
+    for (int h = 0; h < 2; ++h) {
+        typename KS::Raw raw[kHalf];
+#pragma unroll
+        for (int k = 0; k < kHalf; ++k) {
+            const uint32_t jo = (uint32_t)(h * kHalf + k) * 32;
+            raw[k] = ks.load((full || wofs + jo < tp.n_valid) ? gfirst + jo : tp.first);
+        }
+#pragma unroll
+        for (int k = 0; k < kHalf; ++k)
+            key[h * kHalf + k] = ks.make(raw[k], gfirst + (uint32_t)(h * kHalf + k) * 32);
     }
     __syncthreads();  // whist zeroed
+
+    // ---- stable ranks: peers by ballots (independent across rows), then one shared-memory
+    // atomic per peer group, issued by its lowest lane, hands out the group's base rank
     uint32_t rank2[kRsItems / 2];  // two 16-bit ranks per register
 #pragma unroll
-    for (int k = 0; k < kRsItems / 2; ++k) rank2[k] = 0;
+    for (int h = 0; h < 2; ++h) {
+        uint32_t peers[kHalf];
 #pragma unroll
-    for (int k = 0; k < kRsItems; ++k) {
-        uint32_t j = wofs + (uint32_t)k * 32 + lane;
-        bool valid = j < tp.n_valid;
-        uint32_t d = (uint32_t)(key[k] >> shift) & 255u;
-        uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 256u + lane);
-        uint32_t before = __popc(peers & lanemask_lt());
-        uint32_t prev = valid ? sm.whist[warp][d] : 0;
-        __syncwarp();
-        if (valid && before == 0) sm.whist[warp][d] = (uint16_t)(prev + __popc(peers));
-        __syncwarp();
-        rank2[k >> 1] |= (prev + before) << (16 * (k & 1));
+        for (int k = 0; k < kHalf; ++k) {
+            const int kk = h * kHalf + k;
+            const uint32_t d = (uint32_t)(key[kk] >> shift) & 255u;
+            const uint32_t vm = full ? 0xffffffffu
+                                     : __ballot_sync(0xffffffffu, wofs + (uint32_t)kk * 32 < tp.n_valid);
+            peers[k] = match_digit(d, vm);
+        }
+#pragma unroll
+        for (int k = 0; k < kHalf; ++k) {
+            const int kk = h * kHalf + k;
+            const uint32_t d = (uint32_t)(key[kk] >> shift) & 255u;
+            const uint32_t before = __popc(peers[k] & lanemask_lt());
+            const bool valid = full || wofs + (uint32_t)kk * 32 < tp.n_valid;
+            uint32_t prev = 0;
+            if (valid && before == 0) prev = atomicAdd(&sm.whist[warp][d], __popc(peers[k]));
+            prev = __shfl_sync(0xffffffffu, prev, __ffs(peers[k] | (valid ? 0u : 1u << lane)) - 1);
+            const uint32_t r = prev + before;
+            if (kk & 1) rank2[kk >> 1] |= r << 16;
+            else rank2[kk >> 1] = r;
+        }
     }
     __syncthreads();
+    // ---- first slot of every (warp, digit) in the reordered tile
     uint32_t tot = 0;
-    if (threadIdx.x < 256) {  // exclusive prefix over warps for digit == threadIdx.x
+    if (threadIdx.x < 256) {
 #pragma unroll
-        for (int w = 0; w < kRsWarps; ++w) {
-            uint32_t c = sm.whist[w][threadIdx.x];
-            sm.whist[w][threadIdx.x] = (uint16_t)tot;
-            tot += c;
-        }
-        // exclusive scan of the 256 digit totals (8 warps)
-        uint32_t incl = warp_incl_scan(tot);
+        for (int w = 0; w < kRsWarps; ++w) tot += sm.whist[w][threadIdx.x];
+        uint32_t incl = warp_incl_scan(tot);  // exclusive scan of the 256 digit totals (8 warps)
         if (lane == 31) sm.wsum[warp] = incl;
-        sm.dstart[threadIdx.x] = incl - tot;  // warp-local for now
+        sm.dstart[threadIdx.x] = incl - tot;
     }
     __syncthreads();
     if (threadIdx.x < 256) {
-        uint32_t add = 0;
+        uint32_t run = sm.dstart[threadIdx.x];
 #pragma unroll
-        for (int w = 0; w < 8; ++w) add += (w < (int)warp) ? sm.wsum[w] : 0u;
-        uint32_t ds = sm.dstart[threadIdx.x] + add;
-        sm.dstart[threadIdx.x] = ds;
-        sm.gbase[threadIdx.x] -= ds;
-    }
-    __syncthreads();
+        for (int w = 0; w < 8; ++w) run += (w < (int)warp) ? sm.wsum[w] : 0u;
+        sm.gbase[threadIdx.x] -= run;
 #pragma unroll
-    for (int k = 0; k < kRsItems; ++k) {
-        uint32_t j = wofs + (uint32_t)k * 32 + lane;
-        if (j < tp.n_valid) {
-            uint32_t d = (uint32_t)(key[k] >> shift) & 255u;
-            uint32_t p = sm.dstart[d] + sm.whist[warp][d] + ((rank2[k >> 1] >> (16 * (k & 1))) & 0xffffu);
-            sm.skey[p] = key[k];
-            sm.sval[p] = vals_in ? vals_in[tp.first + j] : ks.owner(tp.first + j);
+        for (int w = 0; w < kRsWarps; ++w) {
+            uint32_t c = sm.whist[w][threadIdx.x];
+            sm.whist[w][threadIdx.x] = run;
+            run += c;
         }
     }
     __syncthreads();
+    // ---- reorder the tile by digit in shared memory
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint32_t val[kHalf];
+#pragma unroll
+        for (int k = 0; k < kHalf; ++k) {
+            const uint32_t jo = (uint32_t)(h * kHalf + k) * 32;
+            const size_t i = (full || wofs + jo < tp.n_valid) ? gfirst + jo : tp.first;
+            val[k] = HAS_VALS ? vals_in[i] : ks.owner(i);
+        }
+#pragma unroll
+        for (int k = 0; k < kHalf; ++k) {
+            const int kk = h * kHalf + k;
+            if (full || wofs + (uint32_t)kk * 32 < tp.n_valid) {
+                const uint32_t d = (uint32_t)(key[kk] >> shift) & 255u;
+                const uint32_t p = sm.whist[warp][d] + ((rank2[kk >> 1] >> (16 * (kk & 1))) & 0xffffu);
+                sm.skey[p] = key[kk];
+                sm.sval[p] = val[k];
+            }
+        }
+    }
+    __syncthreads();
+    // ---- every digit run goes out as one contiguous segment
+    K* const ko = keys_out;
+    uint32_t* const vo = vals_out;
 #pragma unroll 4
     for (uint32_t j = threadIdx.x; j < tp.n_valid; j += kRsThreads) {
-        K kk = sm.skey[j];
-        uint32_t d = (uint32_t)(kk >> shift) & 255u;
-        size_t dst = (size_t)(sm.gbase[d] + j);
-        keys_out[dst] = kk;
-        vals_out[dst] = sm.sval[j];
+        const K kk = sm.skey[j];
+        const uint32_t dst = sm.gbase[(uint32_t)(kk >> shift) & 255u] + j;
+        ko[dst] = kk;
+        vo[dst] = sm.sval[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Persistent scatter with TMA-staged input (32-bit keys).  The per-tile scatter above is bound by
+// memory-level parallelism: each CTA exposes four dependent DRAM round trips per tile and only
+// ~32 KB are in flight per SM.  Here one CTA per SM walks its tiles; thread 0 prefetches the NEXT
+// tile's two input arrays into shared memory with 1-D bulk copies (cp.async.bulk, completion on an
+// mbarrier) while all warps rank / reorder / write the current tile out of registers, so a full
+// tile (64 KB) is always in flight without holding registers.
+//   MODE 0: A = keys, B = values          (later passes)
+//   MODE 1: A = keys, value = item index   (first pass over an existing key array)
+//   MODE 2: A = start, B = end of the reads; key = (start << lenbits) | (len - minlen),
+//           value = item index             (first pass of the arc sort, LOCAL keys)
+constexpr int kRpThreads = 1024;
+constexpr int kRpWarps = kRpThreads / 32;
+constexpr int kRpRows = kRsTile / kRpThreads;  // 8 items per thread
+constexpr int kRpStage = kRsTile + 8;          // + slack for 16-byte source alignment
+
+struct RpSmem {
+    uint32_t stA[kRpStage];
+    uint32_t stB[kRpStage];
+    uint32_t skey[kRsTile];
+    uint32_t sval[kRsTile];
+    uint32_t wh[kRpWarps][128];  // two 16-bit counters per word: digits 2p (low) and 2p+1 (high)
+    uint32_t gbase[256];
+    uint32_t wsum[4];
+    unsigned long long mbar;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes,
+                                            unsigned long long* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// element offset that makes (ptr + first - off) 16-byte aligned, and the byte count to copy
+__device__ __forceinline__ uint32_t tma_align(const uint32_t* ptr, size_t first, uint32_t n,
+                                              uint32_t& bytes) {
+    uint32_t off = (uint32_t)((reinterpret_cast<uintptr_t>(ptr + first) & 15u) >> 2);
+    bytes = ((off + n) * 4u + 15u) & ~15u;
+    return off;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kRpThreads, 1)
+k_rs_scatter_tma(const uint32_t* __restrict__ inA, const uint32_t* __restrict__ inB,
+                 uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, TileMap tm,
+                 int shift, const uint32_t* __restrict__ tile_off_scanned, int lenbits,
+                 uint32_t minlen) {
+    extern __shared__ __align__(128) unsigned char rp_smem_raw[];
+    RpSmem& sm = *reinterpret_cast<RpSmem*>(rp_smem_raw);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = lane_id();
+    constexpr bool kHasB = MODE != 1;
+
+    if (tid == 0) mbar_init(&sm.mbar, 1);
+    __syncthreads();
+
+    uint32_t tile = blockIdx.x;
+    if (tile >= tm.n_tiles) return;
+    TilePos tp = locate_tile(tm, tile);
+    uint32_t bytesA = 0, bytesB = 0;
+    uint32_t offA = tma_align(inA, tp.first, tp.n_valid, bytesA);
+    uint32_t offB = kHasB ? tma_align(inB, tp.first, tp.n_valid, bytesB) : 0;
+    if (tid == 0) {
+        mbar_expect_tx(&sm.mbar, bytesA + bytesB);
+        tma_load_1d(sm.stA, inA + tp.first - offA, bytesA, &sm.mbar);
+        if (kHasB) tma_load_1d(sm.stB, inB + tp.first - offB, bytesB, &sm.mbar);
+    }
+    uint32_t g_cur = 0;
+    if (tid < 256)
+        g_cur = tile_off_scanned[(size_t)tp.hist_base + (size_t)tid * tp.tiles_g + tp.tile_in_g];
+    const uint32_t wofs = warp * 32 * kRpRows + lane;
+    uint32_t parity = 0;
+
+    for (;;) {
+        // ---- phase A: the staged tile -> registers; counters cleared
+        for (int i = tid; i < kRpWarps * 128; i += kRpThreads) (&sm.wh[0][0])[i] = 0;
+        if (tid < 256) sm.gbase[tid] = g_cur;
+        mbar_wait(&sm.mbar, parity);
+        parity ^= 1;
+        const bool full = tp.n_valid == (uint32_t)kRsTile;
+        uint32_t key[kRpRows], val[kRpRows];
+#pragma unroll
+        for (int k = 0; k < kRpRows; ++k) {
+            const uint32_t j = wofs + (uint32_t)k * 32;
+            const uint32_t a = sm.stA[offA + j];
+            const uint32_t b = kHasB ? sm.stB[offB + j] : 0u;
+            if (MODE == 2) {
+                key[k] = (a << lenbits) | (b - a + 1 - minlen);
+                val[k] = (uint32_t)(tp.first + j);
+            } else if (MODE == 1) {
+                key[k] = a;
+                val[k] = (uint32_t)(tp.first + j);
+            } else {
+                key[k] = a;
+                val[k] = b;
+            }
+        }
+        __syncthreads();  // S1: stage consumed, counters cleared
+
+        // ---- prefetch the next tile into the (now free) stage
+        const uint32_t next = tile + gridDim.x;
+        const bool has_next = next < tm.n_tiles;
+        const TilePos tp_cur = tp;
+        uint32_t offA_n = 0, offB_n = 0;
+        if (has_next) {
+            tp = locate_tile(tm, next);
+            offA_n = tma_align(inA, tp.first, tp.n_valid, bytesA);
+            offB_n = kHasB ? tma_align(inB, tp.first, tp.n_valid, bytesB) : 0;
+            if (tid == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(&sm.mbar, bytesA + bytesB);
+                tma_load_1d(sm.stA, inA + tp.first - offA_n, bytesA, &sm.mbar);
+                if (kHasB) tma_load_1d(sm.stB, inB + tp.first - offB_n, bytesB, &sm.mbar);
+            }
+            if (tid < 256)
+                g_cur = tile_off_scanned[(size_t)tp.hist_base + (size_t)tid * tp.tiles_g +
+                                         tp.tile_in_g];
+        }
+
+        // ---- stable ranks (ballot peers, one packed shared atomic per peer group)
+        uint32_t rank[kRpRows];
+        {
+            uint32_t peers[kRpRows];
+#pragma unroll
+            for (int k = 0; k < kRpRows; ++k) {
+                const uint32_t d = (key[k] >> shift) & 255u;
+                const uint32_t vm =
+                    full ? 0xffffffffu
+                         : __ballot_sync(0xffffffffu, wofs + (uint32_t)k * 32 < tp_cur.n_valid);
+                peers[k] = match_digit(d, vm);
+            }
+#pragma unroll
+            for (int k = 0; k < kRpRows; ++k) {
+                const uint32_t d = (key[k] >> shift) & 255u;
+                const uint32_t sh16 = (d & 1u) * 16u;
+                const uint32_t before = __popc(peers[k] & lanemask_lt());
+                const bool valid = full || wofs + (uint32_t)k * 32 < tp_cur.n_valid;
+                uint32_t prev = 0;
+                if (valid && before == 0)
+                    prev = (atomicAdd(&sm.wh[warp][d >> 1], (uint32_t)__popc(peers[k]) << sh16) >>
+                            sh16) & 0xffffu;
+                prev = __shfl_sync(0xffffffffu, prev,
+                                   __ffs(peers[k] | (valid ? 0u : 1u << lane)) - 1);
+                rank[k] = prev + before;
+            }
+        }
+        __syncthreads();  // S2
+
+        // ---- first slot of every (warp, digit): 128 threads own a digit pair each
+        uint32_t tot0 = 0, tot1 = 0;
+        if (tid < 128) {
+#pragma unroll 8
+            for (int w = 0; w < kRpWarps; ++w) {
+                const uint32_t c = sm.wh[w][tid];
+                tot0 += c & 0xffffu;
+                tot1 += c >> 16;
+            }
+            const uint32_t both = tot0 + tot1;
+            const uint32_t incl = warp_incl_scan(both);
+            if (lane == 31) sm.wsum[warp] = incl;
+            tot1 = incl - both;  // warp-local exclusive start of the pair (reuse the register)
+        }
+        __syncthreads();  // S3
+        if (tid < 128) {
+            uint32_t run0 = tot1;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) run0 += (w < (int)warp) ? sm.wsum[w] : 0u;
+            uint32_t run1 = run0 + tot0;
+            sm.gbase[2 * tid] -= run0;
+            sm.gbase[2 * tid + 1] -= run1;
+#pragma unroll 8
+            for (int w = 0; w < kRpWarps; ++w) {
+                const uint32_t c = sm.wh[w][tid];
+                sm.wh[w][tid] = run0 | (run1 << 16);
+                run0 += c & 0xffffu;
+                run1 += c >> 16;
+            }
+        }
+        __syncthreads();  // S4
+
+        // ---- reorder the tile by digit in shared memory
+#pragma unroll
+        for (int k = 0; k < kRpRows; ++k) {
+            if (full || wofs + (uint32_t)k * 32 < tp_cur.n_valid) {
+                const uint32_t d = (key[k] >> shift) & 255u;
+                const uint32_t p = ((sm.wh[warp][d >> 1] >> ((d & 1u) * 16u)) & 0xffffu) + rank[k];
+                sm.skey[p] = key[k];
+                sm.sval[p] = val[k];
+            }
+        }
+        __syncthreads();  // S5
+
+        // ---- every digit run goes out as one contiguous segment
+#pragma unroll 4
+        for (uint32_t j = tid; j < tp_cur.n_valid; j += kRpThreads) {
+            const uint32_t kk = sm.skey[j];
+            const uint32_t dst = sm.gbase[(kk >> shift) & 255u] + j;
+            keys_out[dst] = kk;
+            vals_out[dst] = sm.sval[j];
+        }
+        if (!has_next) break;
+        tile = next;
+        offA = offA_n;
+        offB = offB_n;
+        __syncthreads();  // S6: skey/sval/wh/gbase free again
     }
 }
 
 struct RadixTemp {
     DevBuf hist;
     ScanTemp scan;
-    bool attr32 = false, attr64 = false;
 };
 
 inline uint32_t tiles_for(size_t n) { return (uint32_t)((n + kRsTile - 1) / kRsTile); }
@@ -229,13 +540,27 @@ inline int radix_sort_pairs(K* keys_a, uint32_t* vals_a, K* keys_b, uint32_t* va
     uint32_t* hist = tmp.hist.get<uint32_t>((size_t)256 * n_tiles);
     constexpr int kMinCtas = sizeof(K) == 4 ? 2 : 1;
     constexpr int smem = (int)sizeof(RsSmem<K>);
-    bool& attr = sizeof(K) == 4 ? tmp.attr32 : tmp.attr64;
-    if (!attr) {
-        GDS_CUDA(cudaFuncSetAttribute(k_rs_scatter<K, KS0, kMinCtas>,
+    {   // a few microseconds per call; the set of instantiations depends on KS0
+        GDS_CUDA(cudaFuncSetAttribute(k_rs_scatter<K, KS0, false, kMinCtas>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        GDS_CUDA(cudaFuncSetAttribute(k_rs_scatter<K, ArrayKeys<K>, kMinCtas>,
+        GDS_CUDA(cudaFuncSetAttribute(k_rs_scatter<K, ArrayKeys<K>, false, kMinCtas>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr = true;
+        GDS_CUDA(cudaFuncSetAttribute(k_rs_scatter<K, ArrayKeys<K>, true, kMinCtas>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
+    constexpr bool kTma = sizeof(K) == 4;
+    constexpr int rp_smem = (int)sizeof(RpSmem);
+    const int rp_grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)kNumSMs);
+    // Measured on B200 (profiles/): the first pass (keys built from start/end, value = index) is
+    // fastest with the two-CTA register-staged kernel; passes that also move values are fastest
+    // with the persistent TMA-staged kernel.  GDS_SORT_TMA=0/1 forces one of them (experiments).
+    static const char* force = getenv("GDS_SORT_TMA");
+    const bool tma_first = kTma && force && force[0] == '1';
+    const bool tma_later = kTma && !(force && force[0] == '0');
+    if (kTma) {
+        GDS_CUDA(cudaFuncSetAttribute(k_rs_scatter_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, rp_smem));
+        GDS_CUDA(cudaFuncSetAttribute(k_rs_scatter_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, rp_smem));
+        GDS_CUDA(cudaFuncSetAttribute(k_rs_scatter_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rp_smem));
     }
     int cur = 0;
     for (int p = 0; p < passes; ++p) {
@@ -253,8 +578,13 @@ inline int radix_sort_pairs(K* keys_a, uint32_t* vals_a, K* keys_b, uint32_t* va
             exclusive_scan_u32(hist, hist, (size_t)256 * n_tiles, tmp.scan, st);
             {
                 KScope ks("rs_scatter_reads", (8ull + sizeof(K) + 4) * n, st);
-                k_rs_scatter<K, KS0, kMinCtas><<<n_tiles, kRsThreads, smem, st>>>(
-                    *first_ks, nullptr, kout, vout, tm, shift, hist);
+                if (tma_first && KS0::kTmaReads)
+                    k_rs_scatter_tma<2><<<rp_grid, kRpThreads, rp_smem, st>>>(
+                        first_ks->tma_a(), first_ks->tma_b(), reinterpret_cast<uint32_t*>(kout), vout,
+                        tm, shift, hist, first_ks->tma_lenbits(), first_ks->tma_minlen());
+                else
+                    k_rs_scatter<K, KS0, false, kMinCtas><<<n_tiles, kRsThreads, smem, st>>>(
+                        *first_ks, nullptr, kout, vout, tm, shift, hist);
                 GDS_KERNEL_CHECK();
             }
         } else {
@@ -268,8 +598,20 @@ inline int radix_sort_pairs(K* keys_a, uint32_t* vals_a, K* keys_b, uint32_t* va
             exclusive_scan_u32(hist, hist, (size_t)256 * n_tiles, tmp.scan, st);
             {
                 KScope ks("rs_scatter", (2ull * sizeof(K) + (vsrc ? 8 : 4)) * n, st);
-                k_rs_scatter<K, ArrayKeys<K>, kMinCtas><<<n_tiles, kRsThreads, smem, st>>>(
-                    ak, vsrc, kout, vout, tm, shift, hist);
+                if (tma_later && vsrc)
+                    k_rs_scatter_tma<0><<<rp_grid, kRpThreads, rp_smem, st>>>(
+                        reinterpret_cast<const uint32_t*>(kin), vsrc,
+                        reinterpret_cast<uint32_t*>(kout), vout, tm, shift, hist, 0, 0);
+                else if (tma_first)
+                    k_rs_scatter_tma<1><<<rp_grid, kRpThreads, rp_smem, st>>>(
+                        reinterpret_cast<const uint32_t*>(kin), nullptr,
+                        reinterpret_cast<uint32_t*>(kout), vout, tm, shift, hist, 0, 0);
+                else if (vsrc)
+                    k_rs_scatter<K, ArrayKeys<K>, true, kMinCtas><<<n_tiles, kRsThreads, smem, st>>>(
+                        ak, vsrc, kout, vout, tm, shift, hist);
+                else
+                    k_rs_scatter<K, ArrayKeys<K>, false, kMinCtas><<<n_tiles, kRsThreads, smem, st>>>(
+                        ak, nullptr, kout, vout, tm, shift, hist);
                 GDS_KERNEL_CHECK();
             }
         }
