@@ -219,7 +219,7 @@ def run_reference(args, wl, wname):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "flow_value": res[0][0], "n_kept": res[0][1],
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def cpu_baseline(wl, budget_s=12.0, max_solves=32):
@@ -416,10 +416,23 @@ def run_b200(args, wl, wname):
         line["cpu_baseline"] = cpu_baseline(wl)
     if world > 1:
         dist.destroy_process_group()
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL's version banner, library
+    chatter) was redirected to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # C-level writes to stdout (e.g. "NCCL version ...") must not pollute the JSON
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

@@ -3,6 +3,7 @@
 #include "../../include/gds.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -764,6 +765,16 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         if (do_solve && n_comp) {
             std::vector<CompStats> hs(n_comp);
             d2h_sync(c, hs.data(), cstats, n_comp);
+            if (const char* dump = getenv("GDS_DUMP_COMP")) {  // diagnostics only
+                if (FILE* fp = fopen(dump, "w")) {
+                    fprintf(fp, "comp rounds pushes relabels grs bfs_levels max_frontier frontier_sum cycles\n");
+                    for (uint32_t i = 0; i < n_comp; ++i)
+                        fprintf(fp, "%u %llu %llu %llu %llu %llu %llu %llu %llu\n", i, hs[i].rounds,
+                                hs[i].pushes, hs[i].relabels, hs[i].grs, hs[i].bfs_levels,
+                                hs[i].max_frontier, hs[i].frontier_sum, hs[i].cycles);
+                    fclose(fp);
+                }
+            }
             for (const CompStats& s : hs) {
                 out->flow_value += s.sink_flow;
                 out->rounds_total += s.rounds;

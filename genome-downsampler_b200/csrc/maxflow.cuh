@@ -53,6 +53,7 @@ struct SolveParams {
 struct CompStats {
     unsigned long long rounds, pushes, relabels, grs, bfs_levels, max_frontier;
     long long sink_flow, stuck;
+    unsigned long long cycles, frontier_sum;  // diagnostics: SM clocks spent, sum of frontier sizes
 };
 
 template <uint32_t QCAP>
@@ -186,7 +187,8 @@ k_maxflow(NodeArrays na, BundleGraph bg, const uint32_t* __restrict__ comp_lo,
             sh.sink_flow = 0;
             sh.stuck = 0;
         }
-        unsigned long long bfs_levels = 0, grs = 1, rounds = 0, max_frontier = 0;
+        unsigned long long bfs_levels = 0, grs = 1, rounds = 0, max_frontier = 0, frontier_sum = 0;
+        const long long t_begin = clock64();
         unsigned long long my_pushes = 0, my_relabels = 0;
         long long my_sink = 0, my_stuck = 0;
         uint32_t last_levels = mf_global_relabel<THREADS, QCAP>(na, bg, lo, hi, T, N, sh, bfs_levels);
@@ -219,6 +221,7 @@ k_maxflow(NodeArrays na, BundleGraph bg, const uint32_t* __restrict__ comp_lo,
             ++rounds;
             ++rounds_since;
             if (cntF > max_frontier) max_frontier = cntF;
+            frontier_sum += cntF;
 
             // ---------------- phase A: pushes ----------------
             for (uint32_t i = tid; i < cntF; i += kMfThreads) {
@@ -369,6 +372,8 @@ k_maxflow(NodeArrays na, BundleGraph bg, const uint32_t* __restrict__ comp_lo,
             cs.max_frontier = max_frontier;
             cs.sink_flow = sh.sink_flow;
             cs.stuck = sh.stuck;
+            cs.cycles = (unsigned long long)(clock64() - t_begin);
+            cs.frontier_sum = frontier_sum;
             stats[c] = cs;
         }
         __syncthreads();
