@@ -71,13 +71,17 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def traffic_for(kernel, workload):
-    """dram bytes per launch of `kernel` from the committed ncu --set full capture, or None."""
+def traffic_for(kernel, alg_bytes_per_launch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed
+    ncu --set full capture (profiles/traffic.json holds measured DRAM bytes per sorted item; the
+    scatter kernels' algorithmic bytes are 16 per item), or None when no capture covers it."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(p):
         return None
-    t = json.load(open(p))
-    return t.get(workload, {}).get(kernel)
+    per_item = json.load(open(p)).get("per_item", {}).get(kernel)
+    if per_item is None:
+        return None
+    return int(per_item * alg_bytes_per_launch / 16.0)
 
 
 # ------------------------------------------------------------------------------- clocks
@@ -294,9 +298,21 @@ def run_b200(args, wl, wname):
                 dist.all_gather_into_tensor(gathered, bitmap[:words])
             return r
 
+        # e2e: host buffers in, kept bitmap back on the host.  A batch of many samples goes through
+        # the package's chunked host API (two contexts: H2D of chunk c+1 overlaps kernels of chunk c)
+        chunked = pkg.ChunkedSolver(local_rank) if S >= 2 * args.chunk_samples else None
+
         def step_e2e():
-            r = solver.solve_device(h_st.data_ptr(), h_en.data_ptr(), n, ref_len, wl["M"],
-                                    bitmap.data_ptr(), read_off=read_off, input_on_device=False)
+            if chunked is not None:
+                rs = chunked.solve_host_batch(h_st.data_ptr(), h_en.data_ptr(), read_off, ref_len,
+                                              wl["M"], bitmap.data_ptr(),
+                                              chunk_samples=args.chunk_samples)
+                r = rs[-1]
+                r["kernel_launches"] = sum(int(x.kernel_launches) for x in rs)
+            else:
+                r = solver.solve_device(h_st.data_ptr(), h_en.data_ptr(), n, ref_len, wl["M"],
+                                        bitmap.data_ptr(), read_off=read_off,
+                                        input_on_device=False)
             if world > 1:
                 dist.all_gather_into_tensor(gathered, bitmap[:words])
             h_bitmap.copy_(bitmap[:words], non_blocking=True)
@@ -365,11 +381,11 @@ def run_b200(args, wl, wname):
     roofline = None
     if kernels:
         top = kernels[0]
+        per_launch = int(top["alg_bytes_per_step"] / max(top["launches_per_step"], 1))
         roofline = {"bound": "hbm", "kernel": top["name"], "achieved": top["gbs"], "peak": peak,
-                    "unit": "GB/s", "frac": top["frac"], "traffic": traffic_for(top["name"], wname),
-                    "peak_source": peak_src,
-                    "alg_bytes_per_launch": int(top["alg_bytes_per_step"] /
-                                                max(top["launches_per_step"], 1)),
+                    "unit": "GB/s", "frac": top["frac"],
+                    "traffic": traffic_for(top["name"], per_launch),
+                    "peak_source": peak_src, "alg_bytes_per_launch": per_launch,
                     "ms_per_launch": top["ms_per_step"] / max(top["launches_per_step"], 1)}
         stream_k = [k for k in kernels if k["name"] != "maxflow"]
         if stream_k:
@@ -400,7 +416,9 @@ def run_b200(args, wl, wname):
                    if world > 1 else "single GPU"},
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": 8 * n,
                 "d2h_bytes_per_step": 4 * words, "ms_per_step": ms_e2e / args.steps,
-                "pinned": bool(pinned)},
+                "pinned": bool(pinned),
+                "api": ("ChunkedSolver.solve_host_batch, %d samples per chunk, 2 contexts"
+                        % args.chunk_samples) if chunked is not None else "Solver.solve_device(host)"},
         "gpu_launches": launches,
         "clocks": clk.summary(), "clocks_e2e": clk2.summary(),
         "roofline": roofline, "kernels": kernels[:12],
@@ -440,6 +458,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c5", choices=sorted(WORKLOADS))
     ap.add_argument("--samples", type=int, default=0, help="samples per GPU (default: workload's)")
+    ap.add_argument("--chunk-samples", type=int, default=64,
+                    help="samples per chunk of the end-to-end (host buffer) leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]

@@ -8,3 +8,4 @@ The directory name has a hyphen (it is the name the task fixes), so load it with
 from .binding import (  # noqa: F401
     GdsError, Solver, Result, lib_path, load_library, exported_symbols, GDS_FLAGS,
 )
+from .pipeline import ChunkedSolver  # noqa: F401

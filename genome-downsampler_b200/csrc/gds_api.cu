@@ -39,14 +39,14 @@ struct gds_ctx {
     DevBuf keysA, keysB, valsA, valsB, tile_counts;
     RadixTemp radix;
     ScanTemp scan;
-    DevBuf b_first, b_key, b_s, b_t, b_mult, b_f;
+    DevBuf b_first, b_key, b_t, bund;
     DevBuf diff, outdeg, indeg, excl;
     DevBuf tkA, tkB, tvA, tvB;
-    DevBuf n_dcur, n_dsnap, n_e, n_eadd, n_snk, n_g, n_stamp;
+    DevBuf node_rec, n_dsnap;
     DevBuf comp_start, comp_end, comp_sidx, comp_eidx, comp_lo, comp_hi;
     DevBuf qF, qT, qN, work_counter, comp_stats;
     DevBuf bitmap, cov_tmp, dem_tmp, vdiff, vexcl;
-    DevBuf vs_d, cross_idx, cross_tc, odiff, oexcl, cut_nodes, tile_off_d;
+    DevBuf vs_d, cross_idx, cross_tc, odiff, oexcl, cut_nodes, tile_off_d, head_bits;
     unsigned mf_attr_set = 0;  // bit i: smem attribute set for launch shape i
     Profiler prof;
 
@@ -54,12 +54,11 @@ struct gds_ctx {
         DevBuf* all[] = {&in_start, &in_end, &in_mapq, &in_len, &off_d, &reflen_d, &base_d, &foff_d,
                          &amp_s, &amp_e, &pair_pass, &flag32, &fS, &fE, &small, &keysA, &keysB,
                          &valsA, &valsB, &tile_counts, &radix.hist, &radix.scan.l1, &radix.scan.l2,
-                         &scan.l1, &scan.l2, &b_first, &b_key, &b_s, &b_t, &b_mult, &b_f, &diff,
-                         &outdeg, &indeg, &excl, &tkA, &tkB, &tvA, &tvB, &n_dcur, &n_dsnap, &n_e,
-                         &n_eadd, &n_snk, &n_g, &n_stamp, &comp_start, &comp_end, &comp_sidx,
+                         &scan.l1, &scan.l2, &b_first, &b_key, &b_t, &bund, &diff,
+                         &outdeg, &indeg, &excl, &tkA, &tkB, &tvA, &tvB, &node_rec, &n_dsnap, &comp_start, &comp_end, &comp_sidx,
                          &comp_eidx, &comp_lo, &comp_hi, &qF, &qT, &qN, &work_counter, &comp_stats,
                          &bitmap, &cov_tmp, &dem_tmp, &vdiff, &vexcl, &vs_d, &cross_idx, &cross_tc,
-                         &odiff, &oexcl, &cut_nodes, &tile_off_d};
+                         &odiff, &oexcl, &cut_nodes, &tile_off_d, &head_bits};
         for (DevBuf* b : all) b->release();
     }
 };
@@ -103,7 +102,7 @@ void deliver(gds_ctx* c, T* dst, const T* dev_src, size_t n, bool dst_on_device)
 }
 
 template <int I>
-void launch_maxflow_shape(gds_ctx* c, const NodeArrays& na, const BundleGraph& bg,
+void launch_maxflow_shape(gds_ctx* c, const MfGraph& mg,
                           const uint32_t* comp_lo, const uint32_t* comp_hi, uint32_t n_comp,
                           uint32_t* wc, uint32_t* qF, uint32_t* qT, uint32_t* qN,
                           const SolveParams& sp, CompStats* cstats) {
@@ -115,30 +114,31 @@ void launch_maxflow_shape(gds_ctx* c, const NodeArrays& na, const BundleGraph& b
         c->mf_attr_set |= 1u << I;
     }
     int grid = std::min<uint32_t>(n_comp, (uint32_t)kNumSMs * sh.ctas_per_sm);
-    kern<<<grid, sh.threads, smem, c->stream>>>(na, bg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN,
-                                                sp, cstats);
+    kern<<<grid, sh.threads, smem, c->stream>>>(mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp,
+                                                cstats);
 }
 
-void launch_maxflow(gds_ctx* c, const NodeArrays& na, const BundleGraph& bg,
+void launch_maxflow(gds_ctx* c, const MfGraph& mg,
                     const uint32_t* comp_lo, const uint32_t* comp_hi, uint32_t n_comp, uint32_t* wc,
                     uint32_t* qF, uint32_t* qT, uint32_t* qN, const SolveParams& sp,
                     CompStats* cstats, unsigned long long alg_bytes) {
     KScope ks("maxflow", alg_bytes, c->stream);
     const uint32_t sms = (uint32_t)kNumSMs;
     if (n_comp <= sms * kMfShapes[0].ctas_per_sm)
-        launch_maxflow_shape<0>(c, na, bg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp, cstats);
+        launch_maxflow_shape<0>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp, cstats);
     else if (n_comp <= sms * kMfShapes[1].ctas_per_sm)
-        launch_maxflow_shape<1>(c, na, bg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp, cstats);
+        launch_maxflow_shape<1>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp, cstats);
     else if (n_comp <= sms * kMfShapes[2].ctas_per_sm)
-        launch_maxflow_shape<2>(c, na, bg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp, cstats);
+        launch_maxflow_shape<2>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp, cstats);
     else
-        launch_maxflow_shape<3>(c, na, bg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp, cstats);
+        launch_maxflow_shape<3>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp, cstats);
     GDS_KERNEL_CHECK();
 }
 
 template <typename K>
 void build_bundles(gds_ctx* c, const uint32_t* S, const uint32_t* E, const VLayout& vl,
-                   const uint32_t* cross_idx, size_t N, const TileMap& tm, bool local_keys,
+                   const uint32_t* cross_idx, size_t N, const TileMap& tm, const TileMap& tm_small,
+                   bool local_keys,
                    uint32_t n_nodes, int keybits, int lenbits, uint32_t minlen, int32_t* odiff,
                    uint32_t& B_out, uint32_t*& sorted_idx_out, int& passes_out) {
     cudaStream_t st = c->stream;
@@ -150,12 +150,12 @@ void build_bundles(gds_ctx* c, const uint32_t* S, const uint32_t* E, const VLayo
     int where;
     if (local_keys) {
         ReadKeys<K, true> rk{S, E, vl, cross_idx, N, lenbits, minlen};
-        where = radix_sort_pairs<K, ReadKeys<K, true>>(kA, vA, kB, vB, tm, keybits, c->radix, st,
-                                                       &passes_out, &rk);
+        where = radix_sort_pairs<K, ReadKeys<K, true>>(kA, vA, kB, vB, tm, tm_small, keybits,
+                                                       c->radix, st, &passes_out, &rk);
     } else {
         ReadKeys<K, false> rk{S, E, vl, cross_idx, N, lenbits, minlen};
-        where = radix_sort_pairs<K, ReadKeys<K, false>>(kA, vA, kB, vB, tm, keybits, c->radix, st,
-                                                        &passes_out, &rk);
+        where = radix_sort_pairs<K, ReadKeys<K, false>>(kA, vA, kB, vB, tm, tm_small, keybits,
+                                                        c->radix, st, &passes_out, &rk);
     }
     const K* keys = where ? kB : kA;
     sorted_idx_out = where ? vB : vA;
@@ -163,9 +163,10 @@ void build_bundles(gds_ctx* c, const uint32_t* S, const uint32_t* E, const VLayo
     const uint32_t n_tiles = tm.n_tiles;
     uint32_t* tc = c->tile_counts.get<uint32_t>(n_tiles + 1);
     GDS_CUDA(cudaMemsetAsync(tc + n_tiles, 0, sizeof(uint32_t), st));
+    uint32_t* head_bits = c->head_bits.get<uint32_t>((size_t)n_tiles * (kRsTile / 32));
     {
-        KScope ks("heads_count", sizeof(K) * (unsigned long long)n_items, st);
-        k_heads_count<K><<<n_tiles, kHeadThreads, 0, st>>>(keys, tm, tc);
+        KScope ks("heads_count", (sizeof(K) * 8ull + 1ull) * n_items / 8, st);
+        k_heads_count<K><<<n_tiles, kHeadThreads, 0, st>>>(keys, tm, tc, head_bits);
         GDS_KERNEL_CHECK();
     }
     exclusive_scan_u32(tc, tc, n_tiles + 1, c->scan, st);
@@ -175,13 +176,13 @@ void build_bundles(gds_ctx* c, const uint32_t* S, const uint32_t* E, const VLayo
     uint32_t* b_first = c->b_first.get<uint32_t>(B + 1);
     K* b_key = c->b_key.get<K>(B + 1);
     {
-        KScope ks("heads_write", sizeof(K) * (unsigned long long)n_items + (4ull + sizeof(K)) * B, st);
-        k_heads_write<K><<<n_tiles, kHeadThreads, 0, st>>>(keys, tm, tc, b_first, b_key);
+        KScope ks("heads_write", n_items / 8ull + (4ull + 2 * sizeof(K)) * B, st);
+        k_heads_write<K><<<n_tiles, kHeadWriteThreads, 0, st>>>(keys, tm, tc, head_bits, b_first,
+                                                                  b_key);
         GDS_KERNEL_CHECK();
     }
-    uint32_t* b_s = c->b_s.get<uint32_t>(B + 1);
+    BundleRec* bund = c->bund.get<BundleRec>(B + 1);
     uint32_t* b_t = c->b_t.get<uint32_t>(B + 1);
-    uint32_t* b_mult = c->b_mult.get<uint32_t>(B + 1);
     int32_t* diff = c->diff.get<int32_t>(n_nodes + 1);
     uint32_t* outdeg = c->outdeg.get<uint32_t>(n_nodes + 1);
     uint32_t* indeg = c->indeg.get<uint32_t>(n_nodes + 1);
@@ -192,8 +193,8 @@ void build_bundles(gds_ctx* c, const uint32_t* S, const uint32_t* E, const VLayo
         KScope ks("bundle_fill", (sizeof(K) + 8ull + 12ull + 16ull) * B, st);
         k_bundle_fill<K><<<div_up(B, 256), 256, 0, st>>>(b_key, b_first, sorted_idx_out, B,
                                                          (uint32_t)n_items, lenbits, minlen, vl,
-                                                         local_keys, b_s, b_t, b_mult, diff, outdeg,
-                                                         indeg, odiff);
+                                                         local_keys, bund, b_t, diff, outdeg, indeg,
+                                                         odiff);
         GDS_KERNEL_CHECK();
     }
 }
@@ -560,26 +561,34 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             // the arc sort is segmented by sample unless some sample is cut into segments (then the
             // right parts live after all reads and one group with global keys is sorted)
             const bool local_keys = !split;
-            TileMap tm{nullptr, nullptr, 1, tiles_for(n_items), n_items};
+            TileMap tm{nullptr, nullptr, 1, tiles_for(n_items), n_items, (uint32_t)kRsTile};
+            TileMap tm_small{nullptr, nullptr, 1, tiles_for(n_items, kRsTileSmall), n_items,
+                             (uint32_t)kRsTileSmall};
             int keybits = nodebits + lenbits;
             if (local_keys && ns > 1) {
-                std::vector<uint32_t> toff(ns + 1, 0);
+                std::vector<uint32_t> toff(2 * (ns + 1), 0);  // big tiles, then small tiles
+                uint32_t* tb = toff.data();
+                uint32_t* ts = toff.data() + ns + 1;
                 uint32_t maxvn = 1;
                 for (uint32_t k = 0; k < ns; ++k) {
-                    toff[k + 1] = toff[k] + tiles_for(foff_host[k + 1] - foff_host[k]);
+                    const uint64_t nk = foff_host[k + 1] - foff_host[k];
+                    tb[k + 1] = tb[k] + tiles_for(nk);
+                    ts[k + 1] = ts[k] + tiles_for(nk, kRsTileSmall);
                     maxvn = std::max(maxvn, rd->ref_len[k] + 1);
                 }
-                uint32_t* toff_d = c->tile_off_d.get<uint32_t>(ns + 1);
-                GDS_CUDA(cudaMemcpy(toff_d, toff.data(), (ns + 1) * 4, cudaMemcpyHostToDevice));
-                tm = TileMap{toff_d, foff_dev, ns, toff[ns], n_items};
+                uint32_t* toff_d = c->tile_off_d.get<uint32_t>(2 * (ns + 1));
+                GDS_CUDA(cudaMemcpy(toff_d, toff.data(), toff.size() * 4, cudaMemcpyHostToDevice));
+                tm = TileMap{toff_d, foff_dev, ns, tb[ns], n_items, (uint32_t)kRsTile};
+                tm_small = TileMap{toff_d + ns + 1, foff_dev, ns, ts[ns], n_items,
+                                   (uint32_t)kRsTileSmall};
                 keybits = bits_for(maxvn - 1) + lenbits;
             }
             out->key_bits = keybits;
             if (keybits <= 32)
-                build_bundles<uint32_t>(c, S, E, vl, cross_idx, N, tm, local_keys, n_nodes, keybits,
+                build_bundles<uint32_t>(c, S, E, vl, cross_idx, N, tm, tm_small, local_keys, n_nodes, keybits,
                                         lenbits, minlen, odiff, B, sorted_idx, sort_passes);
             else
-                build_bundles<unsigned long long>(c, S, E, vl, cross_idx, N, tm, local_keys, n_nodes,
+                build_bundles<unsigned long long>(c, S, E, vl, cross_idx, N, tm, tm_small, local_keys, n_nodes,
                                                   keybits, lenbits, minlen, odiff, B, sorted_idx,
                                                   sort_passes);
         } else {
@@ -590,9 +599,8 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             GDS_CUDA(cudaMemsetAsync(outdeg, 0, (n_nodes + 1) * 4, st));
             GDS_CUDA(cudaMemsetAsync(indeg, 0, (n_nodes + 1) * 4, st));
             c->b_first.get<uint32_t>(1);
-            c->b_s.get<uint32_t>(1);
             c->b_t.get<uint32_t>(1);
-            c->b_mult.get<uint32_t>(1);
+            c->bund.get<BundleRec>(1);
         }
         out->n_bundles = B;
         out->sort_passes = sort_passes;
@@ -603,14 +611,8 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         exclusive_scan_u32(reinterpret_cast<const uint32_t*>(diff), excl, n_nodes + 1, c->scan, st);
         exclusive_scan_u32(out_ptr, out_ptr, n_nodes + 1, c->scan, st);
         exclusive_scan_u32(in_ptr, in_ptr, n_nodes + 1, c->scan, st);
-        NodeArrays na;
-        na.d_cur = c->n_dcur.get<uint32_t>(n_nodes);
-        na.d_snap = c->n_dsnap.get<uint32_t>(n_nodes);
-        na.e = c->n_e.get<int32_t>(n_nodes);
-        na.eadd = c->n_eadd.get<int32_t>(n_nodes);
-        na.snk = c->n_snk.get<int32_t>(n_nodes);
-        na.g = c->n_g.get<int32_t>(n_nodes);
-        na.stamp = c->n_stamp.get<uint32_t>(n_nodes);
+        NodeRec* node = c->node_rec.get<NodeRec>((size_t)n_nodes + 1);
+        uint32_t* d_snap = c->n_dsnap.get<uint32_t>(n_nodes);
         uint32_t* cstart = c->comp_start.get<uint32_t>(n_nodes + 1);
         uint32_t* cend = c->comp_end.get<uint32_t>(n_nodes + 1);
         GDS_CUDA(cudaMemsetAsync(cstart + n_nodes, 0, 4, st));
@@ -621,10 +623,10 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         if (out->cov_capped) cov_dev = out_dev ? out->cov_capped : c->cov_tmp.get<uint32_t>(n_onodes);
         if (out->demand) dem_dev = out_dev ? out->demand : c->dem_tmp.get<int32_t>(n_onodes);
         {
-            KScope ks("node_finalize", 44ull * n_nodes, st);
-            k_node_finalize<<<div_up(n_nodes, 256), 256, 0, st>>>(
-                excl, diff, n_nodes, max_coverage, na, cstart, cend, split ? nullptr : cov_dev,
-                split ? nullptr : dem_dev, totals);
+            KScope ks("node_finalize", 60ull * n_nodes, st);
+            k_node_finalize<<<div_up((long long)n_nodes + 1, 256), 256, 0, st>>>(
+                excl, diff, out_ptr, in_ptr, n_nodes, max_coverage, node, d_snap, cstart, cend,
+                split ? nullptr : cov_dev, split ? nullptr : dem_dev, totals);
             GDS_KERNEL_CHECK();
         }
         if (split) {
@@ -665,8 +667,6 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         }
         // in-CSR: bundle ids ordered by (end node, bundle id) = stable sort of ids by b_t
         uint32_t* in_bid = nullptr;
-        uint32_t* f = c->b_f.get<uint32_t>(B + 1);
-        GDS_CUDA(cudaMemsetAsync(f, 0, (B + 1) * 4, st));
         if (B) {
             uint32_t* tkA = c->tkA.get<uint32_t>(B);
             uint32_t* tkB = c->tkB.get<uint32_t>(B);
@@ -674,8 +674,11 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             uint32_t* tvB = c->tvB.get<uint32_t>(B);
             GDS_CUDA(cudaMemcpyAsync(tkA, c->b_t.as<uint32_t>(), (size_t)B * 4,
                                      cudaMemcpyDeviceToDevice, st));
-            TileMap btm{nullptr, nullptr, 1, tiles_for(B), B};
-            int w = radix_sort_pairs<uint32_t>(tkA, tvA, tkB, tvB, btm, nodebits, c->radix, st);
+            TileMap btm{nullptr, nullptr, 1, tiles_for(B), B, (uint32_t)kRsTile};
+            TileMap btm_small{nullptr, nullptr, 1, tiles_for(B, kRsTileSmall), B,
+                              (uint32_t)kRsTileSmall};
+            int w = radix_sort_pairs<uint32_t>(tkA, tvA, tkB, tvB, btm, btm_small, nodebits, c->radix,
+                                               st);
             in_bid = w ? tvB : tvA;
         }
         if (!out_dev) {
@@ -685,8 +688,7 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         GDS_CUDA(cudaEventRecord(c->ev[EV_GRAPH], st));
 
         // ---------------- K3: max flow ----------------
-        BundleGraph bg{c->b_s.as<uint32_t>(), c->b_t.as<uint32_t>(), c->b_mult.as<uint32_t>(), f,
-                       out_ptr, in_ptr, in_bid};
+        MfGraph mg{node, d_snap, c->bund.as<BundleRec>(), in_bid};
         CompStats* cstats = c->comp_stats.get<CompStats>(n_comp + 1);
         const bool do_solve = !(flags & GDS_NO_SOLVE);
         if (do_solve && n_comp) {
@@ -695,8 +697,8 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             uint32_t* qN = c->qN.get<uint32_t>(n_nodes);
             uint32_t* wc = c->work_counter.get<uint32_t>(1);
             GDS_CUDA(cudaMemsetAsync(wc, 0, 4, st));
-            launch_maxflow(c, na, bg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp, cstats,
-                           28ull * n_nodes + 24ull * B);
+            launch_maxflow(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp, cstats,
+                           36ull * n_nodes + 20ull * B);
         }
         GDS_CUDA(cudaEventRecord(c->ev[EV_MAXFLOW], st));
 
@@ -709,7 +711,8 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             if (B) {
                 {
                     KScope ks("select", 8ull * B + 8ull * N / 32, st);
-                    k_select<<<div_up(B, 256), 256, 0, st>>>(c->b_first.as<uint32_t>(), f, sorted_idx, B,
+                    k_select<<<div_up(B, 256), 256, 0, st>>>(c->b_first.as<uint32_t>(),
+                                                             c->bund.as<BundleRec>(), sorted_idx, B,
                     bm, totals);
                     GDS_KERNEL_CHECK();
                 }

@@ -10,6 +10,7 @@
 //   * components = maximal runs of covered positions (a back arc over an uncovered position can
 //     carry no flow in any maximum flow, so it is cut)
 #pragma once
+#include <cstddef>
 #include "common.cuh"
 #include "prep.cuh"
 #include "radix_sort.cuh"
@@ -197,55 +198,80 @@ __device__ __forceinline__ void head_ballots(const K* __restrict__ keys, const T
     }
 }
 
+// pass 1: head flags of every item as a bitmap (one word per 32 consecutive items of a tile, tiles
+// padded to kRsTile/32 words) + heads per tile.  pass 2 reads the bitmap, not the keys again.
 template <typename K>
 __global__ void __launch_bounds__(kHeadThreads)
-k_heads_count(const K* __restrict__ keys, TileMap tm, uint32_t* __restrict__ tile_counts) {
+k_heads_count(const K* __restrict__ keys, TileMap tm, uint32_t* __restrict__ tile_counts,
+              uint32_t* __restrict__ head_bits) {
     const TilePos tp = locate_tile(tm, blockIdx.x);
     uint32_t bal[kHeadRows];
     head_ballots<K>(keys, tp, bal);
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
     uint32_t c = 0;
 #pragma unroll
     for (int r = 0; r < kHeadRows; ++r) c += __popc(bal[r]);
+    if (lane < kHeadRows) {
+        uint32_t w = bal[0];
+#pragma unroll
+        for (int r = 1; r < kHeadRows; ++r) w = lane == r ? bal[r] : w;
+        head_bits[(size_t)blockIdx.x * (kRsTile / 32) + warp * kHeadRows + lane] = w;
+    }
     __shared__ uint32_t tot;
     if (threadIdx.x == 0) tot = 0;
     __syncthreads();
-    if (lane_id() == 0 && c) atomicAdd(&tot, c);
+    if (lane == 0 && c) atomicAdd(&tot, c);
     __syncthreads();
     if (threadIdx.x == 0) tile_counts[blockIdx.x] = tot;
 }
 
+// pass 2: one lane per bitmap word (32 items): 256 threads cover a tile.  Only the keys at head
+// positions are gathered.
+constexpr int kHeadWriteThreads = kRsTile / 32;
+
 template <typename K>
-__global__ void __launch_bounds__(kHeadThreads)
+__global__ void __launch_bounds__(kHeadWriteThreads)
 k_heads_write(const K* __restrict__ keys, TileMap tm, const uint32_t* __restrict__ tile_offs,
-              uint32_t* __restrict__ b_first, K* __restrict__ b_key) {
-    __shared__ uint32_t wtot[32];
+              const uint32_t* __restrict__ head_bits, uint32_t* __restrict__ b_first,
+              K* __restrict__ b_key) {
+    __shared__ uint32_t wtot[kHeadWriteThreads / 32];
     const TilePos tp = locate_tile(tm, blockIdx.x);
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-    const uint32_t wofs = warp * 32 * kHeadRows;
-    uint32_t bal[kHeadRows];
-    head_ballots<K>(keys, tp, bal);
-    uint32_t c = 0;
-#pragma unroll
-    for (int r = 0; r < kHeadRows; ++r) c += __popc(bal[r]);
-    if (lane == 0) wtot[warp] = c;
+    uint32_t bits = head_bits[(size_t)blockIdx.x * (kRsTile / 32) + threadIdx.x];
+    const uint32_t c = __popc(bits);
+    const uint32_t incl = warp_incl_scan(c);
+    if (lane == 31) wtot[warp] = incl;
     __syncthreads();
-    uint32_t ex = tile_offs[blockIdx.x];
-    {   // exclusive prefix over the 32 warp totals
-        uint32_t v = wtot[lane];
-        uint32_t incl = warp_incl_scan(v);
-        ex += __shfl_sync(0xffffffffu, incl - v, warp);
-    }
+    uint32_t slot = tile_offs[blockIdx.x] + incl - c;
 #pragma unroll
-    for (int r = 0; r < kHeadRows; ++r) {
-        if (bal[r] >> lane & 1u) {
-            size_t g = tp.first + wofs + r * 32 + lane;
-            uint32_t slot = ex + __popc(bal[r] & lanemask_lt());
-            b_first[slot] = (uint32_t)g;
-            b_key[slot] = keys[g];
-        }
-        ex += __popc(bal[r]);
+    for (int w = 0; w < kHeadWriteThreads / 32; ++w) slot += (w < (int)warp) ? wtot[w] : 0u;
+    const size_t base = tp.first + (size_t)threadIdx.x * 32;
+    while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        b_first[slot] = (uint32_t)(base + b);
+        b_key[slot] = keys[base + b];
+        ++slot;
     }
 }
+
+// Max-flow state, one 32-byte sector per node and one 16-byte record per bundle, so that a
+// push touches: own node (1 sector, neighbours v-1 / v+1 adjacent) -> bundle (1 load) -> target
+// node (1 sector).  Everything a round decides on comes from these records; d_snap (the label
+// snapshot relabels read) is the only side array.
+struct __align__(32) NodeRec {
+    uint32_t d;        // label
+    uint32_t stamp;    // round in which v is in the frontier
+    int32_t e;         // excess                                    (e, eadd: one aligned 8-byte
+    int32_t eadd;      // excess received during the current round   store in phase B; 0 between rounds)
+    int32_t snk;       // remaining sink-arc capacity
+    int32_t g;         // flow on the back arc v -> v-1
+    uint32_t out_ptr;  // first bundle starting at v (bundles are sorted by start)
+    uint32_t in_ptr;   // first in-CSR slot of bundles ending at v
+};
+struct __align__(16) BundleRec {
+    uint32_t t, mult, f, s;  // end node, capacity, flow, start node
+};
 
 // Per bundle: decode the key to the real (s, t) of its segment, multiplicity, and accumulate the
 // node-level difference array (virtual space, and original space when some sample is split) and
@@ -254,9 +280,8 @@ template <typename K>
 __global__ void __launch_bounds__(256)
 k_bundle_fill(const K* __restrict__ b_key, uint32_t* __restrict__ b_first,
               const uint32_t* __restrict__ sorted_owner, uint32_t B, uint32_t n_items, int lenbits,
-              uint32_t minlen, VLayout vl, bool local_keys, uint32_t* __restrict__ b_s,
-              uint32_t* __restrict__ b_t,
-              uint32_t* __restrict__ b_mult, int32_t* __restrict__ diff,
+              uint32_t minlen, VLayout vl, bool local_keys, BundleRec* __restrict__ bund,
+              uint32_t* __restrict__ b_t, int32_t* __restrict__ diff,
               uint32_t* __restrict__ outdeg, uint32_t* __restrict__ indeg,
               int32_t* __restrict__ odiff /* null when virtual == original */) {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -275,9 +300,8 @@ k_bundle_fill(const K* __restrict__ b_key, uint32_t* __restrict__ b_first,
     uint32_t t = min(fake + len, last);
     uint32_t nxt = (b + 1 < B) ? b_first[b + 1] : n_items;
     uint32_t mult = nxt - first_item;
-    b_s[b] = s;
-    b_t[b] = t;
-    b_mult[b] = mult;
+    reinterpret_cast<uint4*>(bund)[b] = make_uint4(t, mult, 0u, s);  // {t, mult, f = 0, s}
+    b_t[b] = t;  // key of the in-CSR sort
     atomicAdd(&diff[s], (int32_t)mult);
     atomicAdd(&diff[t], -(int32_t)mult);
     atomicAdd(&outdeg[s], 1u);
@@ -323,36 +347,32 @@ __global__ void k_cut_through(const uint32_t* __restrict__ cut_nodes, uint32_t n
     atomicAdd(&totals[4], (unsigned long long)min(min(covL, M), min(covR, M)));
 }
 
-struct NodeArrays {
-    uint32_t* d_cur;   // labels
-    uint32_t* d_snap;  // label snapshot read by relabels
-    int32_t* e;        // excess
-    int32_t* eadd;     // excess received during the current round
-    int32_t* snk;      // remaining sink-arc capacity
-    int32_t* g;        // flow on the back arc v -> v-1
-    uint32_t* stamp;   // round in which v was queued
-};
-
 // covL[v] = coverage of the position left of node v = exclusive prefix; covR = inclusive prefix.
 // totals[0] (u64) accumulates F*.
 __global__ void __launch_bounds__(256)
 k_node_finalize(const uint32_t* __restrict__ excl, const int32_t* __restrict__ diff,
-                uint32_t n_nodes, uint32_t M, NodeArrays na, uint32_t* __restrict__ comp_start,
+                const uint32_t* __restrict__ out_ptr, const uint32_t* __restrict__ in_ptr,
+                uint32_t n_nodes, uint32_t M, NodeRec* __restrict__ node,
+                uint32_t* __restrict__ d_snap, uint32_t* __restrict__ comp_start,
                 uint32_t* __restrict__ comp_end, uint32_t* __restrict__ cov_capped_out,
                 int32_t* __restrict__ demand_out, unsigned long long* __restrict__ totals) {
     uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long src = 0;
+    if (v == n_nodes) {  // sentinel record: closes the CSR ranges of the last node
+        uint4* r = reinterpret_cast<uint4*>(&node[v]);
+        r[0] = make_uint4(kLabelInf, 0u, 0u, 0u);
+        r[1] = make_uint4(0u, 0u, out_ptr[v], in_ptr[v]);
+    }
+    static_assert(sizeof(NodeRec) == 32 && offsetof(NodeRec, e) == 8 && offsetof(NodeRec, snk) == 16,
+                  "NodeRec layout is relied on by the vector loads in maxflow.cuh");
     if (v < n_nodes) {
         uint32_t covL = excl[v];
         uint32_t covR = covL + (uint32_t)diff[v];
         int32_t dem = (int32_t)min(covL, M) - (int32_t)min(covR, M);
-        na.e[v] = dem < 0 ? -dem : 0;
-        na.snk[v] = dem > 0 ? dem : 0;
-        na.g[v] = 0;
-        na.eadd[v] = 0;
-        na.stamp[v] = 0;
-        na.d_cur[v] = kLabelInf;
-        na.d_snap[v] = kLabelInf;
+        uint4* r = reinterpret_cast<uint4*>(&node[v]);
+        r[0] = make_uint4(kLabelInf, 0u, (uint32_t)(dem < 0 ? -dem : 0), 0u);  // d, stamp, e, eadd
+        r[1] = make_uint4((uint32_t)(dem > 0 ? dem : 0), 0u, out_ptr[v], in_ptr[v]);  // snk, g, ptrs
+        d_snap[v] = kLabelInf;
         comp_start[v] = (covL == 0 && covR > 0) ? 1u : 0u;
         comp_end[v] = (covL > 0 && covR == 0) ? 1u : 0u;
         if (cov_capped_out) cov_capped_out[v] = min(covR, M);

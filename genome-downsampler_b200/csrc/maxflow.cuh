@@ -4,16 +4,18 @@
 // (quasi_mcp_cuda_max_flow_solver.cu:12-79, :101-155, :366-405) with a different design:
 //   * one CTA per connected component (K4), persistent over a work counter; all state stays in
 //     HBM/L2 for the whole solve, nothing goes back to the host between rounds;
-//   * frontier queues staged in shared memory (first kQCap entries) with a global spill slice;
+//   * state is packed so a push costs few DEPENDENT memory trips (rounds are latency-bound):
+//     NodeRec = one 32-byte sector per node, BundleRec = 16 bytes per bundle (graph.cuh);
+//   * frontier queues staged in shared memory (first QCAP entries) with a global spill slice;
 //     appends are warp-aggregated (one shared-memory atomic per coalesced group);
 //   * every round is a pure function of the previous state: phase A pushes along
 //     admissible arcs using the labels of the round start, received excess is accumulated with
-//     commutative atomics in a side array; phase B merges it, relabels from a label SNAPSHOT and
+//     commutative atomics in NodeRec.eadd; phase B merges it, relabels from a label SNAPSHOT and
 //     builds the next frontier.  The schedule is therefore independent of thread timing and the
 //     CPU oracle (oracle/gds_oracle.cpp: sync_solve_component) replays it bit-exactly;
 //   * global relabel = level-synchronous reverse BFS from the sink inside the same CTA, triggered
 //     by a deterministic state-only rule;
-//   * source arcs are consumed by the preflow (initial excess), the sink is implicit (snk[v]).
+//   * source arcs are consumed by the preflow (initial excess), the sink is implicit (snk).
 //     On this network every active node always has a residual path to the sink,
 //     so no excess ever has to return to the source.
 #pragma once
@@ -36,14 +38,11 @@ struct MfShape {
 };
 constexpr MfShape kMfShapes[4] = {{1024, 1, 4096}, {512, 2, 2048}, {256, 4, 1024}, {128, 8, 1024}};
 
-struct BundleGraph {
-    const uint32_t* b_s;
-    const uint32_t* b_t;
-    const uint32_t* b_mult;
-    uint32_t* f;  // bundle flows
-    const uint32_t* out_ptr;
-    const uint32_t* in_ptr;
-    const uint32_t* in_bid;
+struct MfGraph {
+    NodeRec* node;           // [n_nodes + 1] (sentinel closes the CSR ranges)
+    uint32_t* d_snap;        // [n_nodes] label snapshot read by relabels
+    BundleRec* bund;         // [B] sorted by (start node, key)
+    const uint32_t* in_bid;  // [B] bundle ids ordered by (end node, bundle id)
 };
 
 struct SolveParams {
@@ -55,6 +54,24 @@ struct CompStats {
     long long sink_flow, stuck;
     unsigned long long cycles, frontier_sum;  // diagnostics: SM clocks spent, sum of frontier sizes
 };
+
+// Record loads.  A component is owned by ONE CTA, i.e. one SM: plain (L1-allocating) loads are
+// coherent with the stores and atomics of the other threads of the CTA across __syncthreads, and
+// measured faster than L2-only loads (GDS_MF_LDCG=1 at build time selects the latter).
+#ifdef GDS_MF_LDCG
+#define GDS_MF_LD(p) __ldcg(p)
+#else
+#define GDS_MF_LD(p) (*(p))
+#endif
+__device__ __forceinline__ void ld_node(const NodeRec* p, uint4& lo, uint4& hi) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    lo = GDS_MF_LD(q);      // d, stamp, e, eadd
+    hi = GDS_MF_LD(q + 1);  // snk, g, out_ptr, in_ptr
+}
+__device__ __forceinline__ uint4 ld_bundle(const BundleRec* p) {  // t, mult, f, s
+    return GDS_MF_LD(reinterpret_cast<const uint4*>(p));
+}
+__device__ __forceinline__ uint32_t ld_u32(const uint32_t* p) { return GDS_MF_LD(p); }
 
 template <uint32_t QCAP>
 struct Queue {
@@ -89,22 +106,19 @@ struct MfShared {
 
 // reverse BFS from the sink; T/N are used as the level queues.  returns the level counter
 template <int THREADS, uint32_t QCAP>
-__device__ uint32_t mf_global_relabel(const NodeArrays& na, const BundleGraph& bg, uint32_t lo,
-                                      uint32_t hi, Queue<QCAP> T, Queue<QCAP> N,
-                                      MfShared<QCAP>& sh, unsigned long long& bfs_levels) {
-    constexpr uint32_t kMfThreads = THREADS;
+__device__ uint32_t mf_global_relabel(const MfGraph& G, uint32_t lo, uint32_t hi, Queue<QCAP> T,
+                                      Queue<QCAP> N, MfShared<QCAP>& sh,
+                                      unsigned long long& bfs_levels) {
     const uint32_t tid = threadIdx.x;
-    for (uint32_t v = lo + tid; v <= hi; v += kMfThreads) na.d_cur[v] = kLabelInf;
     if (tid == 0) {
         sh.nT = 0;
         sh.nN = 0;
     }
     __syncthreads();
-    for (uint32_t v = lo + tid; v <= hi; v += kMfThreads) {
-        if (na.snk[v] > 0) {
-            na.d_cur[v] = 1;
-            q_append(T, &sh.nT, v);
-        }
+    for (uint32_t v = lo + tid; v <= hi; v += THREADS) {
+        const bool is_sink = (int32_t)ld_u32(reinterpret_cast<const uint32_t*>(&G.node[v].snk)) > 0;
+        G.node[v].d = is_sink ? 1u : kLabelInf;
+        if (is_sink) q_append(T, &sh.nT, v);
     }
     __syncthreads();
     uint32_t level = 1;
@@ -112,30 +126,24 @@ __device__ uint32_t mf_global_relabel(const NodeArrays& na, const BundleGraph& b
     while (cnt > 0) {
         ++bfs_levels;
         const uint32_t nl = level + 1;
-        for (uint32_t i = tid; i < cnt; i += kMfThreads) {
-            uint32_t w = T.get(i);
-            if (w < hi) {  // back arc (w+1) -> w is always residual
-                if (atomicCAS(&na.d_cur[w + 1], kLabelInf, nl) == kLabelInf)
-                    q_append(N, &sh.nN, w + 1);
+        for (uint32_t i = tid; i < cnt; i += THREADS) {
+            const uint32_t w = T.get(i);
+            uint4 lo4, hi4;
+            ld_node(&G.node[w], lo4, hi4);
+            // CSR range ends live in the next record (w + 1 <= n_nodes: the sentinel exists)
+            const uint4 nx_hi = GDS_MF_LD(reinterpret_cast<const uint4*>(&G.node[w + 1]) + 1);
+            auto visit = [&](uint32_t u) {
+                if (atomicCAS(&G.node[u].d, kLabelInf, nl) == kLabelInf) q_append(N, &sh.nN, u);
+            };
+            if (w < hi) visit(w + 1);                              // back arc (w+1) -> w: residual
+            if (w > lo && (int32_t)hi4.y > 0) visit(w - 1);        // reverse of back arc w -> w-1
+            for (uint32_t k = hi4.w, ke = nx_hi.w; k < ke; ++k) {  // bundles s -> w with residual
+                const uint4 b = ld_bundle(&G.bund[ld_u32(&G.in_bid[k])]);
+                if (b.z < b.y) visit(b.w);
             }
-            if (w > lo && na.g[w] > 0) {  // reverse of back arc w -> w-1
-                if (atomicCAS(&na.d_cur[w - 1], kLabelInf, nl) == kLabelInf)
-                    q_append(N, &sh.nN, w - 1);
-            }
-            for (uint32_t k = bg.in_ptr[w], ke = bg.in_ptr[w + 1]; k < ke; ++k) {
-                uint32_t b = bg.in_bid[k];
-                if (bg.f[b] < bg.b_mult[b]) {
-                    uint32_t u = bg.b_s[b];
-                    if (atomicCAS(&na.d_cur[u], kLabelInf, nl) == kLabelInf)
-                        q_append(N, &sh.nN, u);
-                }
-            }
-            for (uint32_t b = bg.out_ptr[w], be = bg.out_ptr[w + 1]; b < be; ++b) {
-                if (bg.f[b] > 0) {
-                    uint32_t u = bg.b_t[b];
-                    if (atomicCAS(&na.d_cur[u], kLabelInf, nl) == kLabelInf)
-                        q_append(N, &sh.nN, u);
-                }
+            for (uint32_t b = hi4.z, be = nx_hi.z; b < be; ++b) {  // reverse arcs t -> w
+                const uint4 r = ld_bundle(&G.bund[b]);
+                if (r.z > 0) visit(r.x);
             }
         }
         __syncthreads();
@@ -151,7 +159,7 @@ __device__ uint32_t mf_global_relabel(const NodeArrays& na, const BundleGraph& b
         ++level;
         __syncthreads();
     }
-    for (uint32_t v = lo + tid; v <= hi; v += kMfThreads) na.d_snap[v] = na.d_cur[v];
+    for (uint32_t v = lo + tid; v <= hi; v += THREADS) G.d_snap[v] = ld_u32(&G.node[v].d);
     if (tid == 0) {
         sh.nT = 0;
         sh.nN = 0;
@@ -162,11 +170,9 @@ __device__ uint32_t mf_global_relabel(const NodeArrays& na, const BundleGraph& b
 
 template <int THREADS, uint32_t QCAP, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
-k_maxflow(NodeArrays na, BundleGraph bg, const uint32_t* __restrict__ comp_lo,
-          const uint32_t* __restrict__ comp_hi, uint32_t n_comp, uint32_t* work_counter,
-          uint32_t* qF_g, uint32_t* qT_g, uint32_t* qN_g, SolveParams P,
-          CompStats* __restrict__ stats) {
-    constexpr uint32_t kMfThreads = THREADS;
+k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __restrict__ comp_hi,
+          uint32_t n_comp, uint32_t* work_counter, uint32_t* qF_g, uint32_t* qT_g, uint32_t* qN_g,
+          SolveParams P, CompStats* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MfShared<QCAP>& sh = *reinterpret_cast<MfShared<QCAP>*>(smem_raw);
     const uint32_t tid = threadIdx.x;
@@ -191,10 +197,10 @@ k_maxflow(NodeArrays na, BundleGraph bg, const uint32_t* __restrict__ comp_lo,
         const long long t_begin = clock64();
         unsigned long long my_pushes = 0, my_relabels = 0;
         long long my_sink = 0, my_stuck = 0;
-        uint32_t last_levels = mf_global_relabel<THREADS, QCAP>(na, bg, lo, hi, T, N, sh, bfs_levels);
-        for (uint32_t v = lo + tid; v <= hi; v += kMfThreads) {
-            if (na.e[v] > 0) {
-                na.stamp[v] = 1;
+        uint32_t last_levels = mf_global_relabel<THREADS, QCAP>(G, lo, hi, T, N, sh, bfs_levels);
+        for (uint32_t v = lo + tid; v <= hi; v += THREADS) {
+            if ((int32_t)ld_u32(reinterpret_cast<const uint32_t*>(&G.node[v].e)) > 0) {
+                G.node[v].stamp = 1;
                 q_append(F, &sh.nF, v);
             }
         }
@@ -211,7 +217,7 @@ k_maxflow(NodeArrays na, BundleGraph bg, const uint32_t* __restrict__ comp_lo,
                 (unsigned long long)sh.relabels_since * 100 >=
                     (unsigned long long)P.gr_relabel_pct * ncomp) {
                 __syncthreads();  // everyone has read relabels_since
-                last_levels = mf_global_relabel<THREADS, QCAP>(na, bg, lo, hi, T, N, sh, bfs_levels);
+                last_levels = mf_global_relabel<THREADS, QCAP>(G, lo, hi, T, N, sh, bfs_levels);
                 ++grs;
                 if (tid == 0) sh.relabels_since = 0;
                 rounds_since = 0;
@@ -224,22 +230,32 @@ k_maxflow(NodeArrays na, BundleGraph bg, const uint32_t* __restrict__ comp_lo,
             frontier_sum += cntF;
 
             // ---------------- phase A: pushes ----------------
-            for (uint32_t i = tid; i < cntF; i += kMfThreads) {
+            // Labels and stamps are constant during this phase (only phase B writes them); a bundle
+            // flow or a back-arc flow is written only by the one node whose push/cancel is
+            // admissible this round (the two directions exclude each other by their labels).
+            for (uint32_t i = tid; i < cntF; i += THREADS) {
                 const uint32_t v = F.get(i);
-                const uint32_t dv = na.d_cur[v];
-                na.d_snap[v] = dv;  // re-sync the snapshot of a node relabelled last round
+                uint4 lo4, hi4, r_lo, r_hi;
+                ld_node(&G.node[v], lo4, hi4);
+                ld_node(&G.node[v + 1], r_lo, r_hi);  // neighbours' sectors come with the own one
+                const uint4 l_lo = v > lo ? GDS_MF_LD(reinterpret_cast<const uint4*>(&G.node[v - 1]))
+                                          : make_uint4(kLabelInf, 0, 0, 0);  // d, stamp of v-1
+                const uint32_t dv = lo4.x;
+                G.d_snap[v] = dv;  // re-sync the snapshot of a node relabelled last round
                 if (dv >= kLabelInf) continue;
-                int32_t ex = na.e[v];
-                auto give = [&](uint32_t w, int32_t dl) {
-                    atomicAdd(&na.eadd[w], dl);
-                    if (atomicExch(&na.stamp[w], round) != round) q_append(T, &sh.nT, w);
+                int32_t ex = (int32_t)lo4.z;
+                auto give = [&](uint32_t w, int32_t dl, uint32_t w_stamp) {
+                    // eadd is 0 between rounds and every delta is positive: the first giver of the
+                    // round sees 0 and queues w, unless w is already in the frontier
+                    const int32_t old = atomicAdd(&G.node[w].eadd, dl);
+                    if (old == 0 && w_stamp != round) q_append(T, &sh.nT, w);
                     ++my_pushes;
                 };
                 if (dv == 1) {  // 1. sink arc
-                    int32_t s = na.snk[v];
+                    const int32_t s = (int32_t)hi4.x;
                     if (s > 0) {
-                        int32_t dl = min(ex, s);
-                        na.snk[v] = s - dl;
+                        const int32_t dl = min(ex, s);
+                        G.node[v].snk = s - dl;
                         ex -= dl;
                         my_sink += dl;
                         ++my_pushes;
@@ -247,87 +263,93 @@ k_maxflow(NodeArrays na, BundleGraph bg, const uint32_t* __restrict__ comp_lo,
                 }
                 // 2. own bundles, farthest end first
                 {
-                    const uint32_t ob = bg.out_ptr[v];
-                    for (uint32_t b = bg.out_ptr[v + 1]; ex > 0 && b-- > ob;) {
-                        const uint32_t t = bg.b_t[b];
-                        if (na.d_cur[t] + 1 != dv) continue;
-                        const uint32_t fb = bg.f[b];
-                        const uint32_t r = bg.b_mult[b] - fb;
+                    const uint32_t ob = hi4.z;
+                    for (uint32_t b = r_hi.z; ex > 0 && b-- > ob;) {
+                        const uint4 br = ld_bundle(&G.bund[b]);
+                        const uint32_t r = br.y - br.z;
                         if (r == 0) continue;
+                        const uint32_t td = ld_u32(&G.node[br.x].d);
+                        const uint32_t tstamp = ld_u32(&G.node[br.x].stamp);
+                        if (td + 1 != dv) continue;
                         const int32_t dl = (int32_t)min((uint32_t)ex, r);
-                        bg.f[b] = fb + dl;
+                        G.bund[b].f = br.z + dl;
                         ex -= dl;
-                        give(t, dl);
+                        give(br.x, dl, tstamp);
                     }
                 }
                 // 3. cancel back-flow towards the right neighbour
-                if (ex > 0 && v < hi && na.d_cur[v + 1] + 1 == dv) {
-                    const int32_t gr = na.g[v + 1];
+                if (ex > 0 && v < hi && r_lo.x + 1 == dv) {
+                    const int32_t gr = (int32_t)r_hi.y;
                     if (gr > 0) {
                         const int32_t dl = min(ex, gr);
-                        na.g[v + 1] = gr - dl;
+                        G.node[v + 1].g = gr - dl;
                         ex -= dl;
-                        give(v + 1, dl);
+                        give(v + 1, dl, r_lo.y);
                     }
                 }
                 // 4. back arc to the left neighbour (infinite capacity)
-                if (ex > 0 && v > lo && na.d_cur[v - 1] + 1 == dv) {
-                    na.g[v] += ex;
-                    give(v - 1, ex);
+                if (ex > 0 && v > lo && l_lo.x + 1 == dv) {
+                    G.node[v].g = (int32_t)hi4.y + ex;
+                    give(v - 1, ex, l_lo.y);
                     ex = 0;
                 }
                 // 5. cancel flow on incoming bundles, nearest start first
                 if (ex > 0) {
-                    const uint32_t ib = bg.in_ptr[v];
-                    for (uint32_t k = bg.in_ptr[v + 1]; ex > 0 && k-- > ib;) {
-                        const uint32_t b = bg.in_bid[k];
-                        const uint32_t s = bg.b_s[b];
-                        if (na.d_cur[s] + 1 != dv) continue;
-                        const uint32_t fb = bg.f[b];
-                        if (fb == 0) continue;
-                        const int32_t dl = (int32_t)min((uint32_t)ex, fb);
-                        bg.f[b] = fb - dl;
+                    const uint32_t ib = hi4.w;
+                    for (uint32_t k = r_hi.w; ex > 0 && k-- > ib;) {
+                        const uint32_t b = ld_u32(&G.in_bid[k]);
+                        const uint4 br = ld_bundle(&G.bund[b]);
+                        if (br.z == 0) continue;
+                        const uint32_t sd = ld_u32(&G.node[br.w].d);
+                        const uint32_t sstamp = ld_u32(&G.node[br.w].stamp);
+                        if (sd + 1 != dv) continue;
+                        const int32_t dl = (int32_t)min((uint32_t)ex, br.z);
+                        G.bund[b].f = br.z - dl;
                         ex -= dl;
-                        give(s, dl);
+                        give(br.w, dl, sstamp);
                     }
                 }
-                na.e[v] = ex;
+                G.node[v].e = ex;
             }
             __syncthreads();
             const uint32_t cntT = sh.nT;
 
             // ---------------- phase B: merge, relabel from snapshot, next frontier ----------------
-            for (uint32_t i = tid; i < cntF + cntT; i += kMfThreads) {
+            for (uint32_t i = tid; i < cntF + cntT; i += THREADS) {
                 const bool in_front = i < cntF;
                 const uint32_t w = in_front ? F.get(i) : T.get(i - cntF);
-                const int32_t left = na.e[w];
-                const uint32_t dw = na.d_cur[w];
+                uint4 lo4, hi4;
+                ld_node(&G.node[w], lo4, hi4);
+                const int32_t left = (int32_t)lo4.z;
+                const uint32_t dw = lo4.x;
                 bool frozen = dw >= kLabelInf;
                 if (in_front && left > 0 && !frozen) {
+                    const uint4 r_hi = GDS_MF_LD(reinterpret_cast<const uint4*>(&G.node[w + 1]) + 1);
                     uint32_t mn = kLabelInf;
-                    if (na.snk[w] > 0) mn = 0;
-                    for (uint32_t b = bg.out_ptr[w], be = bg.out_ptr[w + 1]; b < be; ++b)
-                        if (bg.f[b] < bg.b_mult[b]) mn = min(mn, na.d_snap[bg.b_t[b]]);
-                    if (w < hi && na.g[w + 1] > 0) mn = min(mn, na.d_snap[w + 1]);
-                    if (w > lo) mn = min(mn, na.d_snap[w - 1]);
-                    for (uint32_t k = bg.in_ptr[w], ke = bg.in_ptr[w + 1]; k < ke; ++k) {
-                        const uint32_t b = bg.in_bid[k];
-                        if (bg.f[b] > 0) mn = min(mn, na.d_snap[bg.b_s[b]]);
+                    if ((int32_t)hi4.x > 0) mn = 0;
+                    for (uint32_t b = hi4.z, be = r_hi.z; b < be; ++b) {
+                        const uint4 br = ld_bundle(&G.bund[b]);
+                        if (br.z < br.y) mn = min(mn, ld_u32(&G.d_snap[br.x]));
                     }
-                    na.d_cur[w] = mn >= kLabelInf ? kLabelInf : mn + 1;
+                    if (w < hi && (int32_t)r_hi.y > 0) mn = min(mn, ld_u32(&G.d_snap[w + 1]));
+                    if (w > lo) mn = min(mn, ld_u32(&G.d_snap[w - 1]));
+                    for (uint32_t k = hi4.w, ke = r_hi.w; k < ke; ++k) {
+                        const uint4 br = ld_bundle(&G.bund[ld_u32(&G.in_bid[k])]);
+                        if (br.z > 0) mn = min(mn, ld_u32(&G.d_snap[br.w]));
+                    }
+                    G.node[w].d = mn >= kLabelInf ? kLabelInf : mn + 1;
                     ++my_relabels;
                     atomicAdd(&sh.relabels_since, 1u);
                     frozen = false;  // stays queued one more round so its snapshot is re-synced
                 }
-                const int32_t add = na.eadd[w];
-                const int32_t tot = left + add;
-                if (add) na.eadd[w] = 0;
-                na.e[w] = tot;
+                const int32_t tot = left + (int32_t)lo4.w;
+                // e and eadd in one 8-byte store (no atomics are in flight in this phase)
+                *reinterpret_cast<int2*>(&G.node[w].e) = make_int2(tot, 0);
                 if (tot > 0) {
                     if (frozen) {
                         my_stuck += tot;
                     } else {
-                        na.stamp[w] = round + 1;
+                        G.node[w].stamp = round + 1;
                         q_append(N, &sh.nN, w);
                     }
                 }

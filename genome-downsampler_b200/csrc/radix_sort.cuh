@@ -28,6 +28,7 @@ constexpr int kRsThreads = 512;
 constexpr int kRsWarps = kRsThreads / 32;
 constexpr int kRsItems = 16;
 constexpr int kRsTile = kRsThreads * kRsItems;  // 8192 keys per tile
+constexpr int kRsTileSmall = kRsTile / 2;
 
 // Where the tiles are.  n_groups == 1: items [0, n_items) in tiles of kRsTile.  Otherwise group g
 // owns items [item_off[g], item_off[g+1]) and tiles [tile_off[g], tile_off[g+1]).
@@ -37,6 +38,7 @@ struct TileMap {
     uint32_t n_groups;
     uint32_t n_tiles;
     size_t n_items;
+    uint32_t tile;  // items per tile: kRsTile, or kRsTileSmall for the two-CTA TMA scatter
 };
 
 struct TilePos {
@@ -51,8 +53,8 @@ struct TilePos {
 __device__ __forceinline__ TilePos locate_tile(const TileMap& tm, uint32_t tile) {
     TilePos p;
     if (tm.n_groups == 1) {
-        p.first = (size_t)tile * kRsTile;
-        p.n_valid = (uint32_t)min((size_t)kRsTile, tm.n_items - p.first);
+        p.first = (size_t)tile * tm.tile;
+        p.n_valid = (uint32_t)min((size_t)tm.tile, tm.n_items - p.first);
         p.hist_base = 0;
         p.tiles_g = tm.n_tiles;
         p.tile_in_g = tile;
@@ -68,8 +70,8 @@ __device__ __forceinline__ TilePos locate_tile(const TileMap& tm, uint32_t tile)
     const uint64_t i0 = tm.item_off[lo], i1 = tm.item_off[lo + 1];
     p.tile_in_g = tile - t0;
     p.tiles_g = tm.tile_off[lo + 1] - t0;
-    p.first = (size_t)i0 + (size_t)p.tile_in_g * kRsTile;
-    p.n_valid = (uint32_t)min((uint64_t)kRsTile, i1 - p.first);
+    p.first = (size_t)i0 + (size_t)p.tile_in_g * tm.tile;
+    p.n_valid = (uint32_t)min((uint64_t)tm.tile, i1 - p.first);
     p.hist_base = 256u * t0;
     return p;
 }
@@ -93,7 +95,7 @@ struct ArrayKeys {
     uint32_t tma_minlen() const { return 0; }
 };
 
-template <typename K, typename KS>
+template <typename K, typename KS, int ITEMS>
 __global__ void __launch_bounds__(kRsThreads)
 k_rs_hist(KS ks, TileMap tm, int shift, uint32_t* __restrict__ tile_hist) {
     __shared__ uint32_t h[kRsWarps][256];  // per-warp counts: conflicts only inside a warp
@@ -101,15 +103,15 @@ k_rs_hist(KS ks, TileMap tm, int shift, uint32_t* __restrict__ tile_hist) {
     const TilePos tp = locate_tile(tm, blockIdx.x);
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5;
-    typename KS::Raw raw[kRsItems];
+    typename KS::Raw raw[ITEMS];
 #pragma unroll
-    for (int k = 0; k < kRsItems; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
         uint32_t j = (uint32_t)k * kRsThreads + threadIdx.x;
         // out-of-range lanes re-read the tile's first item: the load stays unconditional
         raw[k] = ks.load(tp.first + (j < tp.n_valid ? j : 0u));
     }
 #pragma unroll
-    for (int k = 0; k < kRsItems; ++k) {
+    for (int k = 0; k < ITEMS; ++k) {
         uint32_t j = (uint32_t)k * kRsThreads + threadIdx.x;
         K key = ks.make(raw[k], tp.first + j);
         if (j < tp.n_valid) atomicAdd(&h[warp][(uint32_t)(key >> shift) & 255u], 1u);
@@ -126,10 +128,12 @@ k_rs_hist(KS ks, TileMap tm, int shift, uint32_t* __restrict__ tile_hist) {
 // Lanes holding the same 8-bit digit, from 8 ballots (fixed latency; the MATCH.ANY instruction
 // measured ~35% slower here: it iterates once per distinct value, ~30 times for random digits).
 // Per bit: test, vote, conditional complement, and — hand-written so ptxas keeps it at 4 SASS.
-__device__ __forceinline__ uint32_t match_digit(uint32_t d, uint32_t valid_mask) {
+// Only the low `nbits` bits of the digit can be set in this pass (uniform), the rest is skipped.
+__device__ __forceinline__ uint32_t match_digit(uint32_t d, uint32_t valid_mask, int nbits) {
     uint32_t peers = valid_mask;
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
+        if (b >= nbits) break;
         asm("{\n"
             ".reg .pred p;\n"
             ".reg .b32 m;\n"
@@ -159,7 +163,7 @@ struct RsSmem {
 template <typename K, typename KS, bool HAS_VALS, int MIN_CTAS>
 __global__ void __launch_bounds__(kRsThreads, MIN_CTAS)
 k_rs_scatter(KS ks, const uint32_t* __restrict__ vals_in, K* __restrict__ keys_out,
-             uint32_t* __restrict__ vals_out, TileMap tm, int shift,
+             uint32_t* __restrict__ vals_out, TileMap tm, int shift, int nbits,
              const uint32_t* __restrict__ tile_off_scanned) {
     extern __shared__ __align__(16) unsigned char rs_smem_raw[];
     RsSmem<K>& sm = *reinterpret_cast<RsSmem<K>*>(rs_smem_raw);
@@ -204,7 +208,7 @@ k_rs_scatter(KS ks, const uint32_t* __restrict__ vals_in, K* __restrict__ keys_o
             const uint32_t d = (uint32_t)(key[kk] >> shift) & 255u;
             const uint32_t vm = full ? 0xffffffffu
                                      : __ballot_sync(0xffffffffu, wofs + (uint32_t)kk * 32 < tp.n_valid);
-            peers[k] = match_digit(d, vm);
+            peers[k] = match_digit(d, vm, nbits);
         }
 #pragma unroll
         for (int k = 0; k < kHalf; ++k) {
@@ -289,17 +293,16 @@ k_rs_scatter(KS ks, const uint32_t* __restrict__ vals_in, K* __restrict__ keys_o
 //   MODE 1: A = keys, value = item index   (first pass over an existing key array)
 //   MODE 2: A = start, B = end of the reads; key = (start << lenbits) | (len - minlen),
 //           value = item index             (first pass of the arc sort, LOCAL keys)
-constexpr int kRpThreads = 1024;
-constexpr int kRpWarps = kRpThreads / 32;
-constexpr int kRpRows = kRsTile / kRpThreads;  // 8 items per thread
-constexpr int kRpStage = kRsTile + 8;          // + slack for 16-byte source alignment
+constexpr int kRpRows = 8;  // items per thread
 
+template <int THREADS>
 struct RpSmem {
-    uint32_t stA[kRpStage];
-    uint32_t stB[kRpStage];
-    uint32_t skey[kRsTile];
-    uint32_t sval[kRsTile];
-    uint32_t wh[kRpWarps][128];  // two 16-bit counters per word: digits 2p (low) and 2p+1 (high)
+    static constexpr int kTile = THREADS * kRpRows;
+    uint32_t stA[kTile + 8];  // + slack for 16-byte source alignment
+    uint32_t stB[kTile + 8];
+    uint32_t skey[kTile];
+    uint32_t sval[kTile];
+    uint32_t wh[THREADS / 32][128];  // two 16-bit counters per word: digits 2p (low), 2p+1 (high)
     uint32_t gbase[256];
     uint32_t wsum[4];
     unsigned long long mbar;
@@ -350,14 +353,17 @@ __device__ __forceinline__ uint32_t tma_align(const uint32_t* ptr, size_t first,
     return off;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(kRpThreads, 1)
+template <int MODE, int THREADS, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS)
 k_rs_scatter_tma(const uint32_t* __restrict__ inA, const uint32_t* __restrict__ inB,
                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, TileMap tm,
-                 int shift, const uint32_t* __restrict__ tile_off_scanned, int lenbits,
+                 int shift, int nbits, const uint32_t* __restrict__ tile_off_scanned, int lenbits,
                  uint32_t minlen) {
     extern __shared__ __align__(128) unsigned char rp_smem_raw[];
-    RpSmem& sm = *reinterpret_cast<RpSmem*>(rp_smem_raw);
+    constexpr int kRpThreads = THREADS;
+    constexpr int kRpWarps = THREADS / 32;
+    constexpr int kTile = THREADS * kRpRows;
+    RpSmem<THREADS>& sm = *reinterpret_cast<RpSmem<THREADS>*>(rp_smem_raw);
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = lane_id();
     constexpr bool kHasB = MODE != 1;
 
@@ -387,7 +393,7 @@ k_rs_scatter_tma(const uint32_t* __restrict__ inA, const uint32_t* __restrict__ 
         if (tid < 256) sm.gbase[tid] = g_cur;
         mbar_wait(&sm.mbar, parity);
         parity ^= 1;
-        const bool full = tp.n_valid == (uint32_t)kRsTile;
+        const bool full = tp.n_valid == (uint32_t)kTile;
         uint32_t key[kRpRows], val[kRpRows];
 #pragma unroll
         for (int k = 0; k < kRpRows; ++k) {
@@ -437,7 +443,7 @@ k_rs_scatter_tma(const uint32_t* __restrict__ inA, const uint32_t* __restrict__ 
                 const uint32_t vm =
                     full ? 0xffffffffu
                          : __ballot_sync(0xffffffffu, wofs + (uint32_t)k * 32 < tp_cur.n_valid);
-                peers[k] = match_digit(d, vm);
+                peers[k] = match_digit(d, vm, nbits);
             }
 #pragma unroll
             for (int k = 0; k < kRpRows; ++k) {
@@ -521,47 +527,75 @@ struct RadixTemp {
     ScanTemp scan;
 };
 
-inline uint32_t tiles_for(size_t n) { return (uint32_t)((n + kRsTile - 1) / kRsTile); }
+inline uint32_t tiles_for(size_t n, uint32_t tile = kRsTile) {
+    return (uint32_t)((n + tile - 1) / tile);
+}
 
-// Sorts the pairs by the low `bits` bits of the key inside every group of `tm`.  Buffers
-// ping-pong; returns 0 if the result is in (keys_a, vals_a), 1 if in (keys_b, vals_b).
-// The first pass takes key and value from *first_ks when it is non-null, else from keys_a with
-// value = item index.
+// One scatter launch of the TMA-staged kernel in the shape the tile size asks for:
+// kRsTile -> 1024 threads x 1 CTA/SM, kRsTileSmall -> 512 threads x 2 CTAs/SM.
+template <int MODE>
+inline void launch_scatter_tma(const TileMap& tm, const uint32_t* a, const uint32_t* b,
+                               uint32_t* kout, uint32_t* vout, int shift, int nbits,
+                               const uint32_t* hist, int lenbits, uint32_t minlen, cudaStream_t st) {
+    if (tm.tile == (uint32_t)kRsTile) {
+        auto kern = k_rs_scatter_tma<MODE, 1024, 1>;
+        constexpr int smem = (int)sizeof(RpSmem<1024>);
+        GDS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int grid = (int)std::min<uint32_t>(tm.n_tiles, (uint32_t)kNumSMs);
+        kern<<<grid, 1024, smem, st>>>(a, b, kout, vout, tm, shift, nbits, hist, lenbits, minlen);
+    } else {
+        auto kern = k_rs_scatter_tma<MODE, 512, 2>;
+        constexpr int smem = (int)sizeof(RpSmem<512>);
+        GDS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int grid = (int)std::min<uint32_t>(tm.n_tiles, 2u * (uint32_t)kNumSMs);
+        kern<<<grid, 512, smem, st>>>(a, b, kout, vout, tm, shift, nbits, hist, lenbits, minlen);
+    }
+}
+
+template <typename K, typename KS>
+inline void launch_hist(const KS& ks, const TileMap& tm, int shift, uint32_t* hist, cudaStream_t st) {
+    if (tm.tile == (uint32_t)kRsTile)
+        k_rs_hist<K, KS, kRsItems><<<tm.n_tiles, kRsThreads, 0, st>>>(ks, tm, shift, hist);
+    else
+        k_rs_hist<K, KS, kRsItems / 2><<<tm.n_tiles, kRsThreads, 0, st>>>(ks, tm, shift, hist);
+}
+
+// Sorts the pairs by the low `bits` bits of the key inside every group.  `tm` tiles the items in
+// kRsTile, `tm_small` (same groups) in kRsTileSmall.  Buffers ping-pong; returns 0 if the result
+// is in (keys_a, vals_a), 1 if in (keys_b, vals_b).  The first pass takes key and value from
+// *first_ks when it is non-null, else from keys_a with value = item index.
+//
+// Which scatter kernel runs which pass was chosen by measurement on B200 (profiles/):
+//   'R' register-staged, 2 CTAs x 512 threads, tile 8192   — fastest for every pass (default)
+//   '1' TMA-staged persistent, 1 CTA x 1024 threads, tile 8192
+//   '2' TMA-staged persistent, 2 CTAs x 512 threads, tile 4096
+// GDS_SORT_MODE=<first><later> overrides (experiments); 64-bit keys always use 'R'.
 template <typename K, typename KS0 = ArrayKeys<K>>
 inline int radix_sort_pairs(K* keys_a, uint32_t* vals_a, K* keys_b, uint32_t* vals_b,
-                            const TileMap& tm, int bits, RadixTemp& tmp, cudaStream_t st,
-                            int* passes_out = nullptr, const KS0* first_ks = nullptr) {
+                            const TileMap& tm, const TileMap& tm_small, int bits, RadixTemp& tmp,
+                            cudaStream_t st, int* passes_out = nullptr,
+                            const KS0* first_ks = nullptr) {
     int passes = (bits + 7) / 8;
     if (passes == 0) passes = 1;  // still need vals materialised
     if (passes_out) *passes_out = passes;
     const size_t n = tm.n_items;
     if (n == 0 || tm.n_tiles == 0) return 0;
-    const uint32_t n_tiles = tm.n_tiles;
-    uint32_t* hist = tmp.hist.get<uint32_t>((size_t)256 * n_tiles);
+    uint32_t* hist = tmp.hist.get<uint32_t>((size_t)256 * std::max(tm.n_tiles, tm_small.n_tiles));
     constexpr int kMinCtas = sizeof(K) == 4 ? 2 : 1;
     constexpr int smem = (int)sizeof(RsSmem<K>);
-    {   // a few microseconds per call; the set of instantiations depends on KS0
-        GDS_CUDA(cudaFuncSetAttribute(k_rs_scatter<K, KS0, false, kMinCtas>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        GDS_CUDA(cudaFuncSetAttribute(k_rs_scatter<K, ArrayKeys<K>, false, kMinCtas>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        GDS_CUDA(cudaFuncSetAttribute(k_rs_scatter<K, ArrayKeys<K>, true, kMinCtas>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GDS_CUDA(cudaFuncSetAttribute(k_rs_scatter<K, KS0, false, kMinCtas>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GDS_CUDA(cudaFuncSetAttribute(k_rs_scatter<K, ArrayKeys<K>, false, kMinCtas>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    GDS_CUDA(cudaFuncSetAttribute(k_rs_scatter<K, ArrayKeys<K>, true, kMinCtas>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    static const char* mode_env = getenv("GDS_SORT_MODE");
+    char first_mode = 'R', later_mode = 'R';
+    if (mode_env && mode_env[0] && mode_env[1]) {
+        first_mode = mode_env[0];
+        later_mode = mode_env[1];
     }
-    constexpr bool kTma = sizeof(K) == 4;
-    constexpr int rp_smem = (int)sizeof(RpSmem);
-    const int rp_grid = (int)std::min<uint32_t>(n_tiles, (uint32_t)kNumSMs);
-    // Measured on B200 (profiles/): the first pass (keys built from start/end, value = index) is
-    // fastest with the two-CTA register-staged kernel; passes that also move values are fastest
-    // with the persistent TMA-staged kernel.  GDS_SORT_TMA=0/1 forces one of them (experiments).
-    static const char* force = getenv("GDS_SORT_TMA");
-    const bool tma_first = kTma && force && force[0] == '1';
-    const bool tma_later = kTma && !(force && force[0] == '0');
-    if (kTma) {
-        GDS_CUDA(cudaFuncSetAttribute(k_rs_scatter_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, rp_smem));
-        GDS_CUDA(cudaFuncSetAttribute(k_rs_scatter_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, rp_smem));
-        GDS_CUDA(cudaFuncSetAttribute(k_rs_scatter_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, rp_smem));
-    }
+    if (sizeof(K) != 4) first_mode = later_mode = 'R';
     int cur = 0;
     for (int p = 0; p < passes; ++p) {
         K* kin = cur ? keys_b : keys_a;
@@ -569,49 +603,54 @@ inline int radix_sort_pairs(K* keys_a, uint32_t* vals_a, K* keys_b, uint32_t* va
         uint32_t* vin = cur ? vals_b : vals_a;
         uint32_t* vout = cur ? vals_a : vals_b;
         int shift = 8 * p;
+        const int nbits = std::max(1, std::min(8, bits - shift));  // significant digit bits
         if (p == 0 && first_ks) {
+            const char m = KS0::kTmaReads ? first_mode : 'R';
+            const TileMap& t = m == '2' ? tm_small : tm;
             {
                 KScope ks("rs_hist_reads", 8ull * n, st);
-                k_rs_hist<K, KS0><<<n_tiles, kRsThreads, 0, st>>>(*first_ks, tm, shift, hist);
+                launch_hist<K, KS0>(*first_ks, t, shift, hist, st);
                 GDS_KERNEL_CHECK();
             }
-            exclusive_scan_u32(hist, hist, (size_t)256 * n_tiles, tmp.scan, st);
+            exclusive_scan_u32(hist, hist, (size_t)256 * t.n_tiles, tmp.scan, st);
             {
                 KScope ks("rs_scatter_reads", (8ull + sizeof(K) + 4) * n, st);
-                if (tma_first && KS0::kTmaReads)
-                    k_rs_scatter_tma<2><<<rp_grid, kRpThreads, rp_smem, st>>>(
-                        first_ks->tma_a(), first_ks->tma_b(), reinterpret_cast<uint32_t*>(kout), vout,
-                        tm, shift, hist, first_ks->tma_lenbits(), first_ks->tma_minlen());
+                if (m == 'R')
+                    k_rs_scatter<K, KS0, false, kMinCtas><<<t.n_tiles, kRsThreads, smem, st>>>(
+                        *first_ks, nullptr, kout, vout, t, shift, nbits, hist);
                 else
-                    k_rs_scatter<K, KS0, false, kMinCtas><<<n_tiles, kRsThreads, smem, st>>>(
-                        *first_ks, nullptr, kout, vout, tm, shift, hist);
+                    launch_scatter_tma<2>(t, first_ks->tma_a(), first_ks->tma_b(),
+                                          reinterpret_cast<uint32_t*>(kout), vout, shift, nbits, hist,
+                                          first_ks->tma_lenbits(), first_ks->tma_minlen(), st);
                 GDS_KERNEL_CHECK();
             }
         } else {
             ArrayKeys<K> ak{kin};
             const uint32_t* vsrc = p == 0 ? nullptr : vin;
+            const char m = p == 0 ? first_mode : later_mode;
+            const TileMap& t = m == '2' ? tm_small : tm;
             {
                 KScope ks("rs_hist", sizeof(K) * (unsigned long long)n, st);
-                k_rs_hist<K, ArrayKeys<K>><<<n_tiles, kRsThreads, 0, st>>>(ak, tm, shift, hist);
+                launch_hist<K, ArrayKeys<K>>(ak, t, shift, hist, st);
                 GDS_KERNEL_CHECK();
             }
-            exclusive_scan_u32(hist, hist, (size_t)256 * n_tiles, tmp.scan, st);
+            exclusive_scan_u32(hist, hist, (size_t)256 * t.n_tiles, tmp.scan, st);
             {
                 KScope ks("rs_scatter", (2ull * sizeof(K) + (vsrc ? 8 : 4)) * n, st);
-                if (tma_later && vsrc)
-                    k_rs_scatter_tma<0><<<rp_grid, kRpThreads, rp_smem, st>>>(
-                        reinterpret_cast<const uint32_t*>(kin), vsrc,
-                        reinterpret_cast<uint32_t*>(kout), vout, tm, shift, hist, 0, 0);
-                else if (tma_first)
-                    k_rs_scatter_tma<1><<<rp_grid, kRpThreads, rp_smem, st>>>(
-                        reinterpret_cast<const uint32_t*>(kin), nullptr,
-                        reinterpret_cast<uint32_t*>(kout), vout, tm, shift, hist, 0, 0);
+                if (m != 'R' && vsrc)
+                    launch_scatter_tma<0>(t, reinterpret_cast<const uint32_t*>(kin), vsrc,
+                                          reinterpret_cast<uint32_t*>(kout), vout, shift, nbits, hist,
+                                          0, 0, st);
+                else if (m != 'R')
+                    launch_scatter_tma<1>(t, reinterpret_cast<const uint32_t*>(kin), nullptr,
+                                          reinterpret_cast<uint32_t*>(kout), vout, shift, nbits, hist,
+                                          0, 0, st);
                 else if (vsrc)
-                    k_rs_scatter<K, ArrayKeys<K>, true, kMinCtas><<<n_tiles, kRsThreads, smem, st>>>(
-                        ak, vsrc, kout, vout, tm, shift, hist);
+                    k_rs_scatter<K, ArrayKeys<K>, true, kMinCtas><<<t.n_tiles, kRsThreads, smem, st>>>(
+                        ak, vsrc, kout, vout, t, shift, nbits, hist);
                 else
-                    k_rs_scatter<K, ArrayKeys<K>, false, kMinCtas><<<n_tiles, kRsThreads, smem, st>>>(
-                        ak, nullptr, kout, vout, tm, shift, hist);
+                    k_rs_scatter<K, ArrayKeys<K>, false, kMinCtas><<<t.n_tiles, kRsThreads, smem, st>>>(
+                        ak, nullptr, kout, vout, t, shift, nbits, hist);
                 GDS_KERNEL_CHECK();
             }
         }

@@ -7,19 +7,20 @@
 // read order makes those the first f entries of the bundle's slice.
 #pragma once
 #include "common.cuh"
+#include "graph.cuh"
 
 namespace gds {
 
 // one warp per 32 bundles; lane b handles bundle b's slice cooperatively when f is large
 __global__ void __launch_bounds__(256)
-k_select(const uint32_t* __restrict__ b_first, const uint32_t* __restrict__ f,
+k_select(const uint32_t* __restrict__ b_first, const BundleRec* __restrict__ bund,
          const uint32_t* __restrict__ sorted_idx, uint32_t B, uint32_t* __restrict__ bitmap,
          unsigned long long* __restrict__ totals /* [1] += n_kept */) {
     const uint32_t b0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u;
     const uint32_t b = b0 + lane_id();
     uint32_t fb = 0, first = 0;
     if (b < B) {
-        fb = f[b];
+        fb = bund[b].f;
         first = b_first[b];
     }
     // a read cut in two (segment split) can be chosen by both parts: count bits newly set

@@ -1,0 +1,60 @@
+"""Host-buffer batches larger than one PCIe transfer is worth waiting for: solve them in chunks of
+independent samples on two device contexts, so the host->device copy of chunk c+1 overlaps the
+kernels of chunk c.  Samples are independent, so chunking never changes results:
+every chunk writes its slice of the one kept bitmap.
+
+This is host-side orchestration over the C ABI (include/gds.h); it adds no device code.
+"""
+import threading
+
+import numpy as np
+
+from .binding import Solver
+
+
+class ChunkedSolver:
+    def __init__(self, device=0, n_contexts=2):
+        self.solvers = [Solver(device) for _ in range(n_contexts)]
+
+    def close(self):
+        for s in self.solvers:
+            s.close()
+
+    def solve_host_batch(self, start_ptr, end_ptr, read_off, ref_len, max_coverage, bitmap_ptr,
+                         chunk_samples=64, params=None):
+        """start_ptr/end_ptr: HOST pointers (pinned for full PCIe speed) of the concatenated reads;
+        read_off [ns+1] (every chunk boundary must be a multiple of 32 reads so bitmap slices are
+        word-aligned), ref_len [ns]; bitmap_ptr: DEVICE pointer of ceil(n/32) words.
+        Returns the list of per-chunk results (in chunk order)."""
+        read_off = np.ascontiguousarray(read_off, np.uint64)
+        ref_len = np.ascontiguousarray(ref_len, np.uint32)
+        ns = len(ref_len)
+        chunks = [(a, min(a + chunk_samples, ns)) for a in range(0, ns, chunk_samples)]
+        for a, _ in chunks:
+            if int(read_off[a]) % 32:
+                raise ValueError("chunk boundaries must fall on multiples of 32 reads")
+        results = [None] * len(chunks)
+        errors = []
+
+        def worker(w):
+            sv = self.solvers[w]
+            try:
+                for ci in range(w, len(chunks), len(self.solvers)):
+                    a, b = chunks[ci]
+                    r0 = int(read_off[a])
+                    n = int(read_off[b]) - r0
+                    results[ci] = sv.solve_device(
+                        start_ptr + 4 * r0, end_ptr + 4 * r0, n, ref_len[a:b], max_coverage,
+                        bitmap_ptr + 4 * (r0 // 32), read_off=read_off[a:b + 1] - np.uint64(r0),
+                        params=params, input_on_device=False)
+            except Exception as ex:  # surfaced to the caller after the join
+                errors.append(ex)
+
+        threads = [threading.Thread(target=worker, args=(w,)) for w in range(len(self.solvers))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return results

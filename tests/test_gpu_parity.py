@@ -159,6 +159,27 @@ def test_filter_path_c2_small(solver, O):
         assert_parity(O, r, fs, fe, [30_000], [0, kept], 100)
 
 
+def test_c2_full_size_filter_and_solve(solver, O, R):
+    # BASELINE config 2 at full size: 10M reads, -l 90 -q 30, synthetic ARTIC BED/TSV, M=100.
+    # The device filter must equal the oracle's AND the reference's own read_bam filter (oracle/_ref
+    # on a 1/20 slice, the fake in-memory BAM is slow); the solve is checked bit for bit.
+    bed, tsv = O.artic_scheme()
+    a0, a1 = O.parse_amplicons(bed, tsv)
+    s, e, q, l = O.gen_reads_amplicon(12345, 5_000_000, 30_000, a0, a1)
+    filt = dict(min_len=90, min_mapq=30, amp_start=a0, amp_end=a1)
+    r = solver.solve(s, e, 30_000, 100, mapq=q.astype(np.uint8), seq_len=l, filt=filt, params=PRM,
+                     verify=True, want_vectors=True)
+    pp, kept = O.filter_pairs(s, e, q, l, 90, 30, a0, a1)
+    assert np.array_equal(r.pair_pass, pp) and r.n_filtered == kept and 0 < kept < len(s)
+    mask = np.repeat(pp, 2).astype(bool)
+    assert_parity(O, r, s[mask].copy(), e[mask].copy(), [30_000], [0, kept], 100)
+    n_ref = 500_000
+    ref = R.read_bam(s[:n_ref].copy(), e[:n_ref].copy(), q[:n_ref].copy(), l[:n_ref].copy(), 30_000,
+                     90, 30, bed, tsv)
+    assert np.array_equal(ref["start"], s[:n_ref][mask[:n_ref]])
+    assert np.array_equal(ref["end"], e[:n_ref][mask[:n_ref]])
+
+
 def test_filter_on_batches_keeps_sample_offsets(solver, O):
     bed, tsv = O.artic_scheme()
     a0, a1 = O.parse_amplicons(bed, tsv)
@@ -244,3 +265,25 @@ def test_c4_full_size_properties(solver, O):
     assert mask_bits == r.n_kept
     bm, st = O.sync_solve(s, e, [5_000_000], [0, len(s)], 500, params=PRM)
     assert np.array_equal(bm, r.kept_bitmap) and st.rounds_total == r.rounds_total
+
+
+def test_chunked_host_pipeline_equals_one_call(pkg, solver, O):
+    # two contexts, chunks of 2 samples: same bitmap as one gds_solve over the whole batch
+    import torch
+    parts = [O.gen_reads(500 + k, 16_000, 30_000, 150) for k in range(7)]
+    s = np.concatenate([p[0] for p in parts]); e = np.concatenate([p[1] for p in parts])
+    n_per = 32_000
+    off = np.arange(8, dtype=np.uint64) * n_per
+    r = solver.solve(s, e, [30_000] * 7, 40, read_off=off, params=PRM)
+    hs = torch.from_numpy(s.view(np.int32)).pin_memory()
+    he = torch.from_numpy(e.view(np.int32)).pin_memory()
+    bm = torch.zeros(len(s) // 32 + 4, dtype=torch.int32, device="cuda")
+    ch = pkg.ChunkedSolver(0)
+    try:
+        rs = ch.solve_host_batch(hs.data_ptr(), he.data_ptr(), off, [30_000] * 7, 40,
+                                 bm.data_ptr(), chunk_samples=2, params=PRM)
+    finally:
+        ch.close()
+    assert len(rs) == 4 and sum(int(x.n_kept) for x in rs) == r.n_kept
+    got = bm[:len(s) // 32].cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, r.kept_bitmap)
