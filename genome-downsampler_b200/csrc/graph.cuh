@@ -85,6 +85,18 @@ struct ReadKeys {
     size_t n_reads;
     int lenbits;
     uint32_t minlen;
+    // validation fused into the first histogram pass when the caller gave read-length hints
+    // (LOCAL keys only): range check against the sample's reference length + the hints themselves
+    const uint32_t* ref_len;  // [n_samples], null = no fused validation
+    uint32_t* stats;          // [2] += range errors, [3] += reads outside the hinted lengths
+    uint32_t hint_min, hint_max;
+    __device__ __forceinline__ bool checks() const { return LOCAL && ref_len != nullptr; }
+    __device__ __forceinline__ uint32_t check(Raw r, uint32_t group) const {
+        const uint32_t len = r.y - r.x + 1;
+        if (r.x > r.y || r.y >= ref_len[group]) return 1u;
+        return (len < hint_min || len > hint_max) ? 0x10000u : 0u;
+    }
+    __device__ __forceinline__ uint32_t* check_stats() const { return stats; }
     __device__ __forceinline__ Raw load(size_t i) const {
         if (LOCAL) return make_uint2(ld_stream(S + i), ld_stream(E + i));
         size_t rd = i < n_reads ? i : (size_t)cross_idx[i - n_reads];

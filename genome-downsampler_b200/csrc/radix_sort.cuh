@@ -47,6 +47,7 @@ struct TilePos {
     uint32_t hist_base;  // index of hist[group][digit 0][tile 0]
     uint32_t tiles_g;    // tiles in the group
     uint32_t tile_in_g;
+    uint32_t group;
 };
 
 // executed by every thread of the block (uniform result); the binary search is ~9 L1-cached steps
@@ -58,6 +59,7 @@ __device__ __forceinline__ TilePos locate_tile(const TileMap& tm, uint32_t tile)
         p.hist_base = 0;
         p.tiles_g = tm.n_tiles;
         p.tile_in_g = tile;
+        p.group = 0;
         return p;
     }
     uint32_t lo = 0, hi = tm.n_groups;  // largest g with tile_off[g] <= tile
@@ -73,6 +75,7 @@ __device__ __forceinline__ TilePos locate_tile(const TileMap& tm, uint32_t tile)
     p.first = (size_t)i0 + (size_t)p.tile_in_g * tm.tile;
     p.n_valid = (uint32_t)min((uint64_t)tm.tile, i1 - p.first);
     p.hist_base = 256u * t0;
+    p.group = lo;
     return p;
 }
 
@@ -87,6 +90,10 @@ struct ArrayKeys {
     __device__ __forceinline__ Raw load(size_t i) const { return keys[i]; }
     __device__ __forceinline__ K make(Raw r, size_t) const { return r; }
     __device__ __forceinline__ uint32_t owner(size_t i) const { return (uint32_t)i; }
+    // nothing to validate in a plain key array
+    __device__ __forceinline__ bool checks() const { return false; }
+    __device__ __forceinline__ uint32_t check(Raw, uint32_t) const { return 0; }
+    __device__ __forceinline__ uint32_t* check_stats() const { return nullptr; }
     // not a (start, end) source: the TMA first-pass kernel does not apply
     static constexpr bool kTmaReads = false;
     const uint32_t* tma_a() const { return nullptr; }
@@ -110,11 +117,22 @@ k_rs_hist(KS ks, TileMap tm, int shift, uint32_t* __restrict__ tile_hist) {
         // out-of-range lanes re-read the tile's first item: the load stays unconditional
         raw[k] = ks.load(tp.first + (j < tp.n_valid ? j : 0u));
     }
+    uint32_t bad = 0;  // input validation fused into the first pass (low half: range, high: hints)
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         uint32_t j = (uint32_t)k * kRsThreads + threadIdx.x;
         K key = ks.make(raw[k], tp.first + j);
-        if (j < tp.n_valid) atomicAdd(&h[warp][(uint32_t)(key >> shift) & 255u], 1u);
+        if (j < tp.n_valid) {
+            atomicAdd(&h[warp][(uint32_t)(key >> shift) & 255u], 1u);
+            if (ks.checks()) bad += ks.check(raw[k], tp.group);
+        }
+    }
+    if (ks.checks()) {
+        bad = __reduce_add_sync(0xffffffffu, bad);
+        if (bad && lane_id() == 0) {
+            if (bad & 0xffffu) atomicAdd(&ks.check_stats()[2], bad & 0xffffu);
+            if (bad >> 16) atomicAdd(&ks.check_stats()[3], bad >> 16);
+        }
     }
     __syncthreads();
     if (threadIdx.x < 256) {

@@ -32,13 +32,24 @@ std::unique_ptr<Solution> QuasiMcpB200MaxFlowSolver::solve(uint32_t max_coverage
     }
     std::vector<uint32_t> start(n), end(n), seq_len;
     std::vector<uint8_t> mapq;
+    // the narrowing loop also yields the exact read-length bounds the library can use to fold its
+    // input validation into the first sort pass (gds_reads.len_min / len_max)
+    uint32_t len_min = 0xffffffffu, len_max = 0;
+    bool lens_ok = n > 0;
     for (uint64_t i = 0; i < n; ++i) {
         start[i] = static_cast<uint32_t>(in.start_inds[i]);
         end[i] = static_cast<uint32_t>(std::min<uint64_t>(in.end_inds[i], kMax32));
+        if (end[i] < start[i]) {
+            lens_ok = false;  // the library reports it as GDS_ERR_RANGE
+        } else {
+            len_min = std::min(len_min, end[i] - start[i] + 1);
+            len_max = std::max(len_max, end[i] - start[i] + 1);
+        }
     }
     uint64_t off[2] = {0, n};
     uint32_t ref_len = static_cast<uint32_t>(L);
-    gds_reads rd{1, off, &ref_len, start.data(), end.data(), nullptr, nullptr};
+    gds_reads rd{1, off, &ref_len, start.data(), end.data(), nullptr, nullptr,
+                 lens_ok ? len_min : 0, lens_ok ? len_max : 0};
     gds_filter flt{};
     std::vector<uint32_t> amp_s, amp_e;
     std::vector<uint8_t> pair_pass;

@@ -21,7 +21,7 @@ class ChunkedSolver:
             s.close()
 
     def solve_host_batch(self, start_ptr, end_ptr, read_off, ref_len, max_coverage, bitmap_ptr,
-                         chunk_samples=64, params=None):
+                         chunk_samples=64, params=None, len_hint=None):
         """start_ptr/end_ptr: HOST pointers (pinned for full PCIe speed) of the concatenated reads;
         read_off [ns+1] (every chunk boundary must be a multiple of 32 reads so bitmap slices are
         word-aligned), ref_len [ns]; bitmap_ptr: DEVICE pointer of ceil(n/32) words.
@@ -46,7 +46,7 @@ class ChunkedSolver:
                     results[ci] = sv.solve_device(
                         start_ptr + 4 * r0, end_ptr + 4 * r0, n, ref_len[a:b], max_coverage,
                         bitmap_ptr + 4 * (r0 // 32), read_off=read_off[a:b + 1] - np.uint64(r0),
-                        params=params, input_on_device=False)
+                        params=params, input_on_device=False, len_hint=len_hint)
             except Exception as ex:  # surfaced to the caller after the join
                 errors.append(ex)
 

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GDS_ABI_VERSION 2
+#define GDS_ABI_VERSION 3
 
 /* status codes (the reference has none: it logs and exits, cuda_helpers.cuh:13-21) */
 enum {
@@ -60,6 +60,11 @@ typedef struct {
     const uint32_t* end;      /* [n_reads]    Read::end_ind (inclusive) */
     const uint8_t* mapq;      /* [n_reads]    Read::quality (MAPQ); NULL if no filter */
     const uint32_t* seq_len;  /* [n_reads]    Read::seq_length (l_qseq); NULL if no filter */
+    /* optional: exact bounds of end-start+1 over all reads (0,0 = unknown).  A caller that
+     * narrows the reference's size_t arrays anyway has them for free; with them the device folds
+     * input validation into the first pass of the sort instead of a separate pass over the
+     * reads.  Reads outside the bounds fail the call with GDS_ERR_ARG. */
+    uint32_t len_min, len_max;
 } gds_reads;
 
 /* Pre-filter.  Replaces BamApi::should_be_filtered_out (bam_api.cpp:311-332) and the amplicon

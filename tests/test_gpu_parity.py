@@ -287,3 +287,37 @@ def test_chunked_host_pipeline_equals_one_call(pkg, solver, O):
     assert len(rs) == 4 and sum(int(x.n_kept) for x in rs) == r.n_kept
     got = bm[:len(s) // 32].cpu().numpy().view(np.uint32)
     assert np.array_equal(got, r.kept_bitmap)
+
+
+def test_length_hints_fold_validation_into_the_sort(pkg, solver, O):
+    # gds_reads.len_min/len_max: same answer as the stand-alone validation pass, one kernel fewer
+    parts = [O.gen_reads(900 + k, 20_000, 30_000, 150) for k in range(3)]
+    s = np.concatenate([p[0] for p in parts]); e = np.concatenate([p[1] for p in parts])
+    off = np.arange(4, dtype=np.uint64) * 40_000
+    r0 = solver.solve(s, e, [30_000] * 3, 30, read_off=off, params=PRM, verify=True)
+    r1 = solver.solve(s, e, [30_000] * 3, 30, read_off=off, params=PRM, verify=True,
+                      len_hint=(150, 150))
+    assert np.array_equal(r0.kept_bitmap, r1.kept_bitmap) and r0.rounds_total == r1.rounds_total
+    assert r1.kernel_launches < r0.kernel_launches and r1.verify_violations == 0
+    # variable lengths with exact hints, single sample
+    rng = np.random.default_rng(3)
+    s2 = rng.integers(0, 29_000, size=50_000).astype(np.uint32)
+    e2 = (s2 + rng.integers(59, 200, size=50_000)).astype(np.uint32)
+    lens = e2 - s2 + 1
+    ra = solver.solve(s2, e2, 30_000, 25, params=PRM)
+    rb = solver.solve(s2, e2, 30_000, 25, params=PRM, len_hint=(int(lens.min()), int(lens.max())))
+    assert np.array_equal(ra.kept_bitmap, rb.kept_bitmap)
+    # a long reference (segmented path) honours hints too
+    s3, e3, _, _ = O.gen_reads(5, 100_000, 100_000, 150)
+    rc = solver.solve(s3, e3, 100_000, 40, params=(64, 150, 1, 0, 8192))
+    rd = solver.solve(s3, e3, 100_000, 40, params=(64, 150, 1, 0, 8192), len_hint=(150, 150))
+    assert np.array_equal(rc.kept_bitmap, rd.kept_bitmap) and rc.n_components == rd.n_components
+    # hints that do not hold, and bad coordinates under hints, fail loudly
+    with pytest.raises(pkg.GdsError) as ei:
+        solver.solve(s2, e2, 30_000, 25, len_hint=(100, 120))
+    assert ei.value.code == 1  # GDS_ERR_ARG
+    bad = e.copy(); bad[77] = 30_000
+    with pytest.raises(pkg.GdsError) as ei:
+        solver.solve(s, bad, [30_000] * 3, 30, read_off=off, len_hint=(150, 151))
+    assert ei.value.code == 2  # GDS_ERR_RANGE
+    assert solver.solve(s, e, [30_000] * 3, 30, read_off=off, params=PRM).n_kept == r0.n_kept
