@@ -48,6 +48,7 @@ struct gds_ctx {
     DevBuf bitmap, cov_tmp, dem_tmp, vdiff, vexcl;
     DevBuf vs_d, cross_idx, cross_tc, odiff, oexcl, cut_nodes, tile_off_d, head_bits;
     unsigned mf_attr_set = 0;  // bit i: smem attribute set for launch shape i
+    bool atomic_rank = false;  // shared-memory atomics rank in lane order on this device (probed)
     Profiler prof;
 
     void release_all() {
@@ -159,11 +160,13 @@ void build_bundles(gds_ctx* c, const uint32_t* S, const uint32_t* E, const VLayo
         ReadKeys<K, true> rk{S, E, vl, cross_idx, N, lenbits, minlen, fused_ref_len, stats,
                              hint_min, hint_max};
         where = radix_sort_pairs<K, ReadKeys<K, true>>(kA, vA, kB, vB, tm, tm_small, keybits,
-                                                       c->radix, st, &passes_out, &rk);
+                                                       c->radix, st, c->atomic_rank, &passes_out,
+                                                       &rk);
     } else {
         ReadKeys<K, false> rk{S, E, vl, cross_idx, N, lenbits, minlen, nullptr, stats, 0, 0};
         where = radix_sort_pairs<K, ReadKeys<K, false>>(kA, vA, kB, vB, tm, tm_small, keybits,
-                                                        c->radix, st, &passes_out, &rk);
+                                                        c->radix, st, c->atomic_rank, &passes_out,
+                                                        &rk);
     }
     const K* keys = where ? kB : kA;
     sorted_idx_out = where ? vB : vA;
@@ -235,6 +238,7 @@ extern "C" int gds_create(int device, gds_ctx** out) {
         return GDS_ERR_CUDA;
     }
     c->stream = c->own_stream;
+    c->atomic_rank = atomic_rank_is_stable(device, c->own_stream);
     *out = c;
     return GDS_OK;
 }
@@ -718,7 +722,7 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             TileMap btm_small{nullptr, nullptr, 1, tiles_for(B, kRsTileSmall), B,
                               (uint32_t)kRsTileSmall};
             int w = radix_sort_pairs<uint32_t>(tkA, tvA, tkB, tvB, btm, btm_small, nodebits, c->radix,
-                                               st);
+                                               st, c->atomic_rank);
             in_bid = w ? tvB : tvA;
         }
         if (!out_dev) {

@@ -167,6 +167,62 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d, uint32_t valid_mask,
     return peers;
 }
 
+// ------------------------------------------------------------------------------------------
+// Stable ranks from ONE shared-memory atomic per key.  When several lanes of a warp instruction
+// atomicAdd the same shared word, B200 serialises them in ascending lane order (measured:
+// 0 violations over 1.6e9 conflicting lanes, tools/atoms_order_probe.cu), so the value returned
+// to a lane is exactly its stable rank among the equal digits seen so far by the warp.  That
+// replaces ~45 instructions of ballot matching per 32 keys by one ATOMS.  The order is not an
+// architectural guarantee, so every context PROBES it once (k_atoms_order_probe below) and
+// falls back to the ballot ranking if a single violation shows up.
+__global__ void k_atoms_order_probe(uint32_t seed, int iters, unsigned int* violations) {
+    __shared__ uint32_t cnt[32][256];
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    uint32_t x = seed ^ (blockIdx.x * 9781u + threadIdx.x * 6271u + 1u);
+    uint32_t v = 0;
+    for (int it = 0; it < iters; ++it) {
+        for (int i = lane; i < 256; i += 32) cnt[warp][i] = 0;
+        __syncwarp();
+        x = x * 1664525u + 1013904223u;
+        const uint32_t nbins = (it & 3) == 0 ? 256u : (it & 3) == 1 ? 128u : (it & 3) == 2 ? 7u : 1u;
+        const uint32_t d = (x >> 13) % nbins;
+        const bool active = (it & 4) ? ((x >> 5) & 3) != 0 : true;  // divergent callers too
+        uint32_t r = 0;
+        if (active) r = atomicAdd(&cnt[warp][d], 1u);
+        __syncwarp();
+        const uint32_t peers = match_digit(d, __ballot_sync(0xffffffffu, active), 8);
+        if (active && r != (uint32_t)__popc(peers & lanemask_lt())) ++v;
+        __syncwarp();
+    }
+    if (v) atomicAdd(violations, v);
+}
+
+// true if shared-memory atomics hand out ranks in lane order on `device` (probed once per process
+// and device; GDS_RANK=ballot|atomic overrides)
+inline bool atomic_rank_is_stable(int device, cudaStream_t st) {
+    static int cached[64];  // 0 unknown, 1 stable, 2 not stable
+    if (const char* f = getenv("GDS_RANK")) {
+        if (f[0] == 'b') return false;
+        if (f[0] == 'a') return true;
+    }
+    int& c = cached[device & 63];
+    if (c == 0) {
+        unsigned int* d = nullptr;
+        unsigned int h = 1;
+        if (cudaMalloc(&d, sizeof h) == cudaSuccess) {
+            cudaMemsetAsync(d, 0, sizeof h, st);
+            k_atoms_order_probe<<<kNumSMs, 1024, 0, st>>>(0x9e3779b9u, 512, d);
+            if (cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                cudaStreamSynchronize(st) != cudaSuccess)
+                h = 1;
+            cudaFree(d);
+        }
+        cudaGetLastError();
+        c = h == 0 ? 1 : 2;
+    }
+    return c == 1;
+}
+
 template <typename K>
 struct RsSmem {
     K skey[kRsTile];
@@ -178,7 +234,7 @@ struct RsSmem {
 };
 
 // vals_in is read when HAS_VALS, else the value is what the key source says (the owner read).
-template <typename K, typename KS, bool HAS_VALS, int MIN_CTAS>
+template <typename K, typename KS, bool HAS_VALS, bool ATOMIC_RANK, int MIN_CTAS>
 __global__ void __launch_bounds__(kRsThreads, MIN_CTAS)
 k_rs_scatter(KS ks, const uint32_t* __restrict__ vals_in, K* __restrict__ keys_out,
              uint32_t* __restrict__ vals_out, TileMap tm, int shift, int nbits,
@@ -217,6 +273,19 @@ k_rs_scatter(KS ks, const uint32_t* __restrict__ vals_in, K* __restrict__ keys_o
     // ---- stable ranks: peers by ballots (independent across rows), then one shared-memory
     // atomic per peer group, issued by its lowest lane, hands out the group's base rank
     uint32_t rank2[kRsItems / 2];  // two 16-bit ranks per register
+    if (ATOMIC_RANK) {
+        // one ATOMS per key: same-digit lanes are served in lane order (probed), so the returned
+        // count is the stable rank; the 16 atomics of a thread are independent and pipeline
+#pragma unroll
+        for (int k = 0; k < kRsItems / 2; ++k) rank2[k] = 0;
+#pragma unroll
+        for (int kk = 0; kk < kRsItems; ++kk) {
+            const uint32_t d = (uint32_t)(key[kk] >> shift) & 255u;
+            uint32_t r = 0;
+            if (full || wofs + (uint32_t)kk * 32 < tp.n_valid) r = atomicAdd(&sm.whist[warp][d], 1u);
+            rank2[kk >> 1] |= r << (16 * (kk & 1));
+        }
+    } else
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         uint32_t peers[kHalf];
@@ -371,7 +440,7 @@ __device__ __forceinline__ uint32_t tma_align(const uint32_t* ptr, size_t first,
     return off;
 }
 
-template <int MODE, int THREADS, int MIN_CTAS>
+template <int MODE, int THREADS, int MIN_CTAS, bool ATOMIC_RANK>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 k_rs_scatter_tma(const uint32_t* __restrict__ inA, const uint32_t* __restrict__ inB,
                  uint32_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, TileMap tm,
@@ -453,7 +522,16 @@ k_rs_scatter_tma(const uint32_t* __restrict__ inA, const uint32_t* __restrict__ 
 
         // ---- stable ranks (ballot peers, one packed shared atomic per peer group)
         uint32_t rank[kRpRows];
-        {
+        if (ATOMIC_RANK) {
+#pragma unroll
+            for (int k = 0; k < kRpRows; ++k) {
+                const uint32_t d = (key[k] >> shift) & 255u;
+                const uint32_t sh16 = (d & 1u) * 16u;
+                rank[k] = 0;
+                if (full || wofs + (uint32_t)k * 32 < tp_cur.n_valid)
+                    rank[k] = (atomicAdd(&sm.wh[warp][d >> 1], 1u << sh16) >> sh16) & 0xffffu;
+            }
+        } else {
             uint32_t peers[kRpRows];
 #pragma unroll
             for (int k = 0; k < kRpRows; ++k) {
@@ -554,19 +632,39 @@ inline uint32_t tiles_for(size_t n, uint32_t tile = kRsTile) {
 template <int MODE>
 inline void launch_scatter_tma(const TileMap& tm, const uint32_t* a, const uint32_t* b,
                                uint32_t* kout, uint32_t* vout, int shift, int nbits,
-                               const uint32_t* hist, int lenbits, uint32_t minlen, cudaStream_t st) {
+                               const uint32_t* hist, int lenbits, uint32_t minlen, bool atomic_rank,
+                               cudaStream_t st) {
+    auto go = [&](auto kern, int threads, int smem, uint32_t per_sm) {
+        GDS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int grid = (int)std::min<uint32_t>(tm.n_tiles, per_sm * (uint32_t)kNumSMs);
+        kern<<<grid, threads, smem, st>>>(a, b, kout, vout, tm, shift, nbits, hist, lenbits, minlen);
+    };
     if (tm.tile == (uint32_t)kRsTile) {
-        auto kern = k_rs_scatter_tma<MODE, 1024, 1>;
-        constexpr int smem = (int)sizeof(RpSmem<1024>);
-        GDS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int grid = (int)std::min<uint32_t>(tm.n_tiles, (uint32_t)kNumSMs);
-        kern<<<grid, 1024, smem, st>>>(a, b, kout, vout, tm, shift, nbits, hist, lenbits, minlen);
+        if (atomic_rank) go(k_rs_scatter_tma<MODE, 1024, 1, true>, 1024, (int)sizeof(RpSmem<1024>), 1);
+        else go(k_rs_scatter_tma<MODE, 1024, 1, false>, 1024, (int)sizeof(RpSmem<1024>), 1);
     } else {
-        auto kern = k_rs_scatter_tma<MODE, 512, 2>;
-        constexpr int smem = (int)sizeof(RpSmem<512>);
+        if (atomic_rank) go(k_rs_scatter_tma<MODE, 512, 2, true>, 512, (int)sizeof(RpSmem<512>), 2);
+        else go(k_rs_scatter_tma<MODE, 512, 2, false>, 512, (int)sizeof(RpSmem<512>), 2);
+    }
+}
+
+// One scatter launch of the register-staged kernel.
+template <typename K, typename KS>
+inline void launch_scatter_reg(const KS& ks, const uint32_t* vals_in, K* kout, uint32_t* vout,
+                               const TileMap& t, int shift, int nbits, const uint32_t* hist,
+                               bool atomic_rank, cudaStream_t st) {
+    constexpr int kMinCtas = sizeof(K) == 4 ? 2 : 1;
+    constexpr int smem = (int)sizeof(RsSmem<K>);
+    auto go = [&](auto kern) {
         GDS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int grid = (int)std::min<uint32_t>(tm.n_tiles, 2u * (uint32_t)kNumSMs);
-        kern<<<grid, 512, smem, st>>>(a, b, kout, vout, tm, shift, nbits, hist, lenbits, minlen);
+        kern<<<t.n_tiles, kRsThreads, smem, st>>>(ks, vals_in, kout, vout, t, shift, nbits, hist);
+    };
+    if (vals_in) {
+        if (atomic_rank) go(k_rs_scatter<K, KS, true, true, kMinCtas>);
+        else go(k_rs_scatter<K, KS, true, false, kMinCtas>);
+    } else {
+        if (atomic_rank) go(k_rs_scatter<K, KS, false, true, kMinCtas>);
+        else go(k_rs_scatter<K, KS, false, false, kMinCtas>);
     }
 }
 
@@ -591,7 +689,7 @@ inline void launch_hist(const KS& ks, const TileMap& tm, int shift, uint32_t* hi
 template <typename K, typename KS0 = ArrayKeys<K>>
 inline int radix_sort_pairs(K* keys_a, uint32_t* vals_a, K* keys_b, uint32_t* vals_b,
                             const TileMap& tm, const TileMap& tm_small, int bits, RadixTemp& tmp,
-                            cudaStream_t st, int* passes_out = nullptr,
+                            cudaStream_t st, bool atomic_rank, int* passes_out = nullptr,
                             const KS0* first_ks = nullptr) {
     int passes = (bits + 7) / 8;
     if (passes == 0) passes = 1;  // still need vals materialised
@@ -599,14 +697,6 @@ inline int radix_sort_pairs(K* keys_a, uint32_t* vals_a, K* keys_b, uint32_t* va
     const size_t n = tm.n_items;
     if (n == 0 || tm.n_tiles == 0) return 0;
     uint32_t* hist = tmp.hist.get<uint32_t>((size_t)256 * std::max(tm.n_tiles, tm_small.n_tiles));
-    constexpr int kMinCtas = sizeof(K) == 4 ? 2 : 1;
-    constexpr int smem = (int)sizeof(RsSmem<K>);
-    GDS_CUDA(cudaFuncSetAttribute(k_rs_scatter<K, KS0, false, kMinCtas>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    GDS_CUDA(cudaFuncSetAttribute(k_rs_scatter<K, ArrayKeys<K>, false, kMinCtas>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    GDS_CUDA(cudaFuncSetAttribute(k_rs_scatter<K, ArrayKeys<K>, true, kMinCtas>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     static const char* mode_env = getenv("GDS_SORT_MODE");
     char first_mode = 'R', later_mode = 'R';
     if (mode_env && mode_env[0] && mode_env[1]) {
@@ -634,12 +724,13 @@ inline int radix_sort_pairs(K* keys_a, uint32_t* vals_a, K* keys_b, uint32_t* va
             {
                 KScope ks("rs_scatter_reads", (8ull + sizeof(K) + 4) * n, st);
                 if (m == 'R')
-                    k_rs_scatter<K, KS0, false, kMinCtas><<<t.n_tiles, kRsThreads, smem, st>>>(
-                        *first_ks, nullptr, kout, vout, t, shift, nbits, hist);
+                    launch_scatter_reg<K, KS0>(*first_ks, nullptr, kout, vout, t, shift, nbits, hist,
+                                               atomic_rank, st);
                 else
                     launch_scatter_tma<2>(t, first_ks->tma_a(), first_ks->tma_b(),
                                           reinterpret_cast<uint32_t*>(kout), vout, shift, nbits, hist,
-                                          first_ks->tma_lenbits(), first_ks->tma_minlen(), st);
+                                          first_ks->tma_lenbits(), first_ks->tma_minlen(),
+                                          atomic_rank, st);
                 GDS_KERNEL_CHECK();
             }
         } else {
@@ -658,17 +749,14 @@ inline int radix_sort_pairs(K* keys_a, uint32_t* vals_a, K* keys_b, uint32_t* va
                 if (m != 'R' && vsrc)
                     launch_scatter_tma<0>(t, reinterpret_cast<const uint32_t*>(kin), vsrc,
                                           reinterpret_cast<uint32_t*>(kout), vout, shift, nbits, hist,
-                                          0, 0, st);
+                                          0, 0, atomic_rank, st);
                 else if (m != 'R')
                     launch_scatter_tma<1>(t, reinterpret_cast<const uint32_t*>(kin), nullptr,
                                           reinterpret_cast<uint32_t*>(kout), vout, shift, nbits, hist,
-                                          0, 0, st);
-                else if (vsrc)
-                    k_rs_scatter<K, ArrayKeys<K>, true, kMinCtas><<<t.n_tiles, kRsThreads, smem, st>>>(
-                        ak, vsrc, kout, vout, t, shift, nbits, hist);
+                                          0, 0, atomic_rank, st);
                 else
-                    k_rs_scatter<K, ArrayKeys<K>, false, kMinCtas><<<t.n_tiles, kRsThreads, smem, st>>>(
-                        ak, nullptr, kout, vout, t, shift, nbits, hist);
+                    launch_scatter_reg<K, ArrayKeys<K>>(ak, vsrc, kout, vout, t, shift, nbits, hist,
+                                                        atomic_rank, st);
                 GDS_KERNEL_CHECK();
             }
         }
