@@ -1,3 +1,6 @@
+"""Diagnostics: per-component statistics of the max-flow kernel (rounds, pushes, BFS levels, SM
+cycles) for configs 4 and 1, written to gpurun_out/comp_<config>.txt via GDS_DUMP_COMP.
+Run from the repo root on a GPU box: python tools/diag_comp.py"""
 import os,sys,time
 sys.path.insert(0,'.')
 import numpy as np, torch
