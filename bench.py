@@ -264,6 +264,34 @@ def cpu_baseline(wl, budget_s=12.0, max_solves=32):
                       % (done, 2 * pairs, L, wl["M"], t_solve)}
 
 
+def reference_cuda_baseline(wl, timeout_s=180):
+    """The reference's OWN GPU backend (quasi-mcp-cuda, compiled unmodified for sm_100a into
+    oracle/_ref/libgds_refcuda.so) on one sample of the workload, on this box's GPU, in its own
+    process under a timeout (it has no iteration bound and terminates on CUDA errors).  A reported
+    baseline — "the thing to beat" of SURVEY §2.2 — never part of the product path."""
+    import subprocess
+    runner = os.path.join(ROOT, "oracle", "run_refcuda.py")
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libgds_refcuda.so")):
+        return {"unavailable": "oracle/_ref/libgds_refcuda.so not built"}
+    pairs, L = cpu_sample_spec(wl)
+    try:
+        out = subprocess.run([sys.executable, runner, "gen", str(wl["seed"]), str(pairs), str(L),
+                              str(wl["R"]), str(wl["M"]), "2"], capture_output=True, text=True,
+                             timeout=timeout_s)
+        if out.returncode != 0:
+            return {"unavailable": "quasi-mcp-cuda exited %d" % out.returncode}
+        d = json.loads(out.stdout.strip().splitlines()[-1])
+    except subprocess.TimeoutExpired:
+        return {"unavailable": "quasi-mcp-cuda did not finish in %d s" % timeout_s}
+    except Exception as ex:
+        return {"unavailable": repr(ex)}
+    return {"value": d["reads"] / d["best_s"], "unit": "reads/s", "kind": "reference",
+            "what": "reference's quasi-mcp-cuda (unmodified .cu, sm_100a) on this GPU, whole solve() "
+                    "incl. its host graph build and copies, best of 2 calls",
+            "sample": "1 solve of %d reads over %d bp, M=%d" % (d["reads"], d["L"], d["M"]),
+            "seconds": d["best_s"], "n_kept": d["n_kept"], "coverage_invariant_ok": d["invariant_ok"]}
+
+
 # ------------------------------------------------------------------------------- B200 arm
 def run_b200(args, wl, wname):
     import torch
@@ -454,11 +482,22 @@ def run_b200(args, wl, wname):
                    "n_components": int(r_last.n_components), "rounds_total": int(r_last.rounds_total),
                    "rounds_max": int(r_last.rounds_max), "bfs_levels": int(r_last.bfs_levels),
                    "sort_passes": int(r_last.sort_passes),
+                   # K3 is latency-bound, not HBM-bound: its own figures (SURVEY §8d iii)
+                   "k3": {"pushes": int(r_last.pushes), "relabels": int(r_last.relabels),
+                          "global_relabels": int(r_last.global_relabels),
+                          "max_frontier": int(r_last.max_frontier),
+                          "steps_per_component": (int(r_last.rounds_total) + int(r_last.bfs_levels))
+                          / max(int(r_last.n_components), 1),
+                          "us_per_step": 1e3 * r_last.ms_maxflow * max(int(r_last.n_components), 1)
+                          / max(int(r_last.rounds_total) + int(r_last.bfs_levels), 1),
+                          "pushes_relabels_per_s": (int(r_last.pushes) + int(r_last.relabels))
+                          / max(r_last.ms_maxflow * 1e-3, 1e-9)},
                    "phase_ms": {"graph": r_last.ms_graph, "maxflow": r_last.ms_maxflow,
                                 "select": r_last.ms_select, "total": r_last.ms_total}},
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(wl)
+        line["reference_cuda_baseline"] = reference_cuda_baseline(wl)
     if world > 1:
         dist.destroy_process_group()
     emit(line)

@@ -83,3 +83,36 @@ def test_host_test_binary_runs_the_five_cases_through_the_plugin(pkg):
     exe = os.path.join(os.path.dirname(pkg.lib_path()), "gds_host_test")
     out = subprocess.run([exe, "-a", "quasi-mcp-b200"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+@pytest.mark.gpu
+def test_same_capped_coverage_as_the_references_own_cuda_solver(solver, O, tmp_path):
+    # quasi-mcp-cuda itself (libs/qmcp-solver/src/quasi_mcp_cuda_max_flow_solver.cu compiled
+    # unmodified for sm_100a into oracle/_ref/libgds_refcuda.so) on the same box and input: kept
+    # sets may differ (SURVEY finding 3), the M-capped output coverage may not.
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    runner = os.path.join(root, "oracle", "run_refcuda.py")
+    if not os.path.exists(os.path.join(root, "oracle", "_ref", "libgds_refcuda.so")):
+        pytest.skip("oracle/_ref/libgds_refcuda.so not built (needs /root/reference + nvcc)")
+    ex = O.SMALL_EXAMPLE
+    cases = [(ex["start"], ex["end"], ex["L"], ex["M"])]
+    s, e, _, _ = O.gen_reads(12345, 50_000, 30_000, 150)   # config 3
+    cases.append((s, e, 30_000, 100))
+    for i, (s, e, L, M) in enumerate(cases):
+        inp = tmp_path / ("in%d.npz" % i)
+        outp = tmp_path / ("out%d.npy" % i)
+        np.savez(inp, s=s, e=e, L=L)
+        subprocess.run([sys.executable, runner, "npy", str(inp), str(outp), str(M)], check=True,
+                       timeout=300, capture_output=True)
+        ids = np.load(outp)
+        ref_mask = np.zeros(len(s), np.uint8); ref_mask[ids] = 1
+        r = solver.solve(s, e, L, M, verify=True)
+        ours = O.bitmap_to_mask(r.kept_bitmap, len(s))
+        cin = O.coverage_fast(s, e, L)
+        c_ref = O.coverage_fast(s, e, L, ref_mask); c_us = O.coverage_fast(s, e, L, ours)
+        assert np.all(np.minimum(cin, M) <= c_ref)          # the reference's own invariant
+        assert np.array_equal(np.minimum(c_ref, M), np.minimum(c_us, M))
+        assert np.array_equal(np.minimum(c_us, M), np.minimum(cin, M))
