@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — throughput of the quasi-MCP downsampling hot path on B200 (one JSON line on stdout).
 
-    python bench.py --gpus N --steps K --warmup W [--workload c5|c4|c1] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--workload c5|c4|c2|c1] [--impl reference]
 
 A "step" is one pass of the whole hot path (validate -> bundle sort -> coverage/demand/CSR ->
 component split -> push-relabel max-flow -> kept-read bitmap) over one batch of synthetic reads.
@@ -11,6 +11,8 @@ Workloads (BASELINE.json `configs`):
                 (reads-gen uniform law, mt19937 seed 12345+k, R=150), MAX_COVERAGE=100.
                 512 samples per GPU; ranks own disjoint sample blocks, no data-path collective,
                 per-sample bitmaps all-gathered over NCCL at the end of every step (weak scaling).
+  c2            config[1]: 10 M reads over 30 kb with the device pair filter (-l 90 -q 30 + ARTIC-style
+                amplicons); `value` counts PRE-filter reads.
   c4            config[3]: 50 M reads over one 5 Mb reference, MAX_COVERAGE=500 (single GPU; N>1
                 runs independent replicas with different seeds).
   c1            config[0]: 1 M reads over 30 kb, MAX_COVERAGE=100.
@@ -46,6 +48,11 @@ WORKLOADS = {
     "c4": dict(L=5_000_000, R=150, pairs=25_000_000, M=500, samples=1, seed=12345,
                name="config[3]: 50M reads over a 5 Mb reference (reads-gen uniform, seed 12345, "
                     "R=150), MAX_COVERAGE=500"),
+    "c2": dict(L=30_000, R=150, pairs=5_000_000, M=100, samples=1, seed=12345,
+               filter=dict(min_len=90, min_mapq=30), min_len=60, p_inside=0.9,
+               name="config[1]: 10M reads over a 30 kb reference with the pair filter -l 90 -q 30 + "
+                    "synthetic ARTIC-style amplicons (98 x 400 bp, 98 bp overlap; mates inside one "
+                    "amplicon with p=0.9, seq_length U{60..150}, MAPQ U{0..100}), MAX_COVERAGE=100"),
     "c1": dict(L=30_000, R=150, pairs=500_000, M=100, samples=1, seed=12345,
                name="config[0]: 1M reads over a 30 kb reference (reads-gen uniform, seed 12345, "
                     "R=150), MAX_COVERAGE=100"),
@@ -189,18 +196,52 @@ def generate(wl, sample_ids, pinned):
         en = torch.empty(n, dtype=torch.int32)
     s_np = st.numpy().view(np.uint32)
     e_np = en.numpy().view(np.uint32)
+    if "filter" in wl:  # config 2: one sample, amplicon-aware law, MAPQ and seq_length too
+        mq = torch.empty(n, dtype=torch.uint8, pin_memory=pin)
+        sl = torch.empty(n, dtype=torch.int32, pin_memory=pin)
+        a0, a1 = hostlib.artic_amplicons(wl["L"])
+        hostlib.gen_reads_amplicon_into(wl["seed"] + sample_ids[0], wl["pairs"], wl["L"], a0, a1,
+                                        s_np, e_np, mq.numpy(), sl.numpy().view(np.uint32),
+                                        p_inside=wl["p_inside"], min_len=wl["min_len"],
+                                        max_len=wl["R"])
+        return st, en, pin, dict(mapq=mq, seq_len=sl, amp_start=a0, amp_end=a1)
     hostlib.gen_batch([wl["seed"] + k for k in sample_ids], wl["pairs"], wl["L"], wl["R"], s_np,
                       e_np, threads=host_threads())
-    return st, en, pin
+    return st, en, pin, None
 
 
 # ------------------------------------------------------------------------------- reference arm
 def cpu_sample_spec(wl):
     """One CPU solve of the bounded sample: (pairs, L).  c5/c1: one whole sample; c4: a 1/10 scale
     cut of the same law (same coverage depth and M), because one full 50M-read solve takes minutes."""
-    if wl["pairs"] > 2_000_000:
+    if wl["pairs"] > 2_000_000 and "filter" not in wl:
         return wl["pairs"] // 10, wl["L"] // 10
     return wl["pairs"], wl["L"]
+
+
+def cpu_make_input(O, wl, k, pairs, L):
+    """Input k of the CPU legs (same laws and seeds as the B200 arm)."""
+    if "filter" in wl:
+        bed, tsv = O.artic_scheme(L)
+        a0, a1 = O.parse_amplicons(bed, tsv)
+        s, e, q, l = O.gen_reads_amplicon(wl["seed"] + k, pairs, L, a0, a1, wl["p_inside"],
+                                          wl["min_len"], wl["R"])
+        return (s, e, q, l, a0, a1)
+    return O.gen_reads(wl["seed"] + k, pairs, L, wl["R"])[:2]
+
+
+def cpu_solve_one(O, wl, inp, L):
+    """The reference's CPU path on one input: (filter,) coverage, graph, max-flow, selection."""
+    if "filter" in wl:
+        s, e, q, l, a0, a1 = inp
+        pp, kept = O.filter_pairs(s, e, q, l, wl["filter"]["min_len"], wl["filter"]["min_mapq"],
+                                  a0, a1)
+        m = np.repeat(pp, 2).astype(bool)
+        s, e = np.ascontiguousarray(s[m]), np.ascontiguousarray(e[m])
+    else:
+        s, e = inp
+    kept, st = O.ref_solve(s, e, L, wl["M"])
+    return int(st.flow_value), int(st.n_kept)
 
 
 def run_reference(args, wl, wname):
@@ -212,11 +253,10 @@ def run_reference(args, wl, wname):
     cores = host_threads()
     pairs, L = cpu_sample_spec(wl)
     M = wl["M"]
-    inputs = [O.gen_reads(wl["seed"] + k, pairs, L, wl["R"])[:2] for k in range(cores)]
+    inputs = [cpu_make_input(O, wl, k, pairs, L) for k in range(cores)]
 
     def one(k):
-        kept, st = O.ref_solve(inputs[k][0], inputs[k][1], L, M)
-        return int(st.flow_value), int(st.n_kept)
+        return cpu_solve_one(O, wl, inputs[k], L)
 
     def step():
         with ThreadPoolExecutor(max_workers=cores) as ex:
@@ -254,9 +294,9 @@ def cpu_baseline(wl, budget_s=12.0, max_solves=32):
     pairs, L = cpu_sample_spec(wl)
     done, t_solve = 0, 0.0
     while done < max_solves and t_solve < budget_s:
-        s, e, _, _ = O.gen_reads(wl["seed"] + done, pairs, L, wl["R"])
+        inp = cpu_make_input(O, wl, done, pairs, L)
         t0 = time.perf_counter()
-        O.ref_solve(s, e, L, wl["M"])
+        cpu_solve_one(O, wl, inp, L)
         t_solve += time.perf_counter() - t0
         done += 1
     return {"value": done * 2 * pairs / t_solve, "unit": "reads/s", "cores": 1, "kind": "port",
@@ -273,6 +313,8 @@ def reference_cuda_baseline(wl, timeout_s=180):
     runner = os.path.join(ROOT, "oracle", "run_refcuda.py")
     if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libgds_refcuda.so")):
         return {"unavailable": "oracle/_ref/libgds_refcuda.so not built"}
+    if "filter" in wl:
+        return {"unavailable": "the runner has no pair-filter stage (config 2)"}
     pairs, L = cpu_sample_spec(wl)
     try:
         out = subprocess.run([sys.executable, runner, "gen", str(wl["seed"]), str(pairs), str(L),
@@ -321,7 +363,7 @@ def run_b200(args, wl, wname):
     n_per = 2 * wl["pairs"]
     n = n_per * S
     t0 = time.time()
-    h_st, h_en, pinned = generate(wl, sample_ids, pinned=True)
+    h_st, h_en, pinned, fx = generate(wl, sample_ids, pinned=True)
     log("[rank %d] generated %d reads (%d samples) in %.1f s, pinned=%s" %
         (rank, n, S, time.time() - t0, pinned))
     ref_len = np.full(S, wl["L"], np.uint32)
@@ -334,6 +376,21 @@ def run_b200(args, wl, wname):
         solver.set_stream(stream.cuda_stream)
         d_st = h_st.to(dev, non_blocking=True)
         d_en = h_en.to(dev, non_blocking=True)
+        # config 2: MAPQ / seq_length columns, the amplicon table and the per-pair verdicts
+        filt = d_mq = d_sl = pair_pass = h_pair_pass = None
+        if fx is not None:
+            d_mq = fx["mapq"].to(dev, non_blocking=True)
+            d_sl = fx["seq_len"].to(dev, non_blocking=True)
+            pair_pass = torch.zeros(n // 2, dtype=torch.uint8, device=dev)
+            h_pair_pass = torch.empty(n // 2, dtype=torch.uint8, pin_memory=True)
+            filt = dict(wl["filter"], amp_start=fx["amp_start"], amp_end=fx["amp_end"])
+
+        def fkw(on_device):
+            if fx is None:
+                return {}
+            return dict(mapq_ptr=(d_mq if on_device else fx["mapq"]).data_ptr(),
+                        seq_len_ptr=(d_sl if on_device else fx["seq_len"]).data_ptr(), filt=filt,
+                        pair_pass_ptr=pair_pass.data_ptr())
         bitmap = torch.zeros(words + 4, dtype=torch.int32, device=dev)
         h_bitmap = torch.empty(words, dtype=torch.int32, pin_memory=True)
         gathered = None
@@ -343,12 +400,12 @@ def run_b200(args, wl, wname):
 
         # exact read-length bounds, as the C++ adapter passes them (it gets them for free while
         # narrowing the reference's size_t arrays): reads-gen emits fixed-length reads
-        hint = (wl["R"], wl["R"])
+        hint = (wl["R"], wl["R"]) if fx is None else None  # config 2 has variable lengths
 
         def step_device(profile):
             r = solver.solve_device(d_st.data_ptr(), d_en.data_ptr(), n, ref_len, wl["M"],
                                     bitmap.data_ptr(), read_off=read_off, profile=profile,
-                                    len_hint=hint)
+                                    len_hint=hint, **fkw(True))
             if world > 1:
                 dist.all_gather_into_tensor(gathered, bitmap[:words])
             return r
@@ -367,7 +424,9 @@ def run_b200(args, wl, wname):
             else:
                 r = solver.solve_device(h_st.data_ptr(), h_en.data_ptr(), n, ref_len, wl["M"],
                                         bitmap.data_ptr(), read_off=read_off,
-                                        input_on_device=False, len_hint=hint)
+                                        input_on_device=False, len_hint=hint, **fkw(False))
+                if fx is not None:
+                    h_pair_pass.copy_(pair_pass, non_blocking=True)
             if world > 1:
                 dist.all_gather_into_tensor(gathered, bitmap[:words])
             h_bitmap.copy_(bitmap[:words], non_blocking=True)
@@ -389,7 +448,8 @@ def run_b200(args, wl, wname):
 
         # correctness gate (untimed): the device re-derives coverage from the kept bitmap
         rv = solver.solve_device(d_st.data_ptr(), d_en.data_ptr(), n, ref_len, wl["M"],
-                                 bitmap.data_ptr(), read_off=read_off, verify=True, len_hint=hint)
+                                 bitmap.data_ptr(), read_off=read_off, verify=True, len_hint=hint,
+                                 **fkw(True))
         assert rv.verify_violations == 0 and rv.flow_value == rv.fstar, \
             "device verification failed: %r" % dict(rv)
 
@@ -450,7 +510,7 @@ def run_b200(args, wl, wname):
                                              "frac": round(b / (t * 1e-3) / 1e9 / peak, 4),
                                              "ms_per_step": t}
         # whole-step figure from SURVEY §8d: B_alg = 8.125*P + 4*(L+1) per sample
-        b_alg = 8.125 * n + 4.0 * (wl["L"] + 1) * S
+        b_alg = (13.125 if fx is not None else 8.125) * n + 4.0 * (wl["L"] + 1) * S
         roofline["step_alg_gbs"] = round(b_alg / (ms_dev / args.steps * 1e-3) / 1e9, 1)
     if rank != 0:
         if world > 1:
@@ -469,8 +529,9 @@ def run_b200(args, wl, wname):
                          "inputs fit L2: every step re-reads them after >126 MB of sort traffic",
                    "parallelism": "samples sharded, %d per rank; NCCL all-gather of bitmaps" % S
                    if world > 1 else "single GPU"},
-        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": 8 * n,
-                "d2h_bytes_per_step": 4 * words, "ms_per_step": ms_e2e / args.steps,
+        "e2e": {"value": e2e_value, "unit": "reads/s",
+                "h2d_bytes_per_step": (13 if fx is not None else 8) * n,
+                "d2h_bytes_per_step": 4 * words + (n // 2 if fx is not None else 0), "ms_per_step": ms_e2e / args.steps,
                 "pinned": bool(pinned),
                 "api": ("ChunkedSolver.solve_host_batch, %d samples per chunk, 2 contexts"
                         % args.chunk_samples) if chunked is not None else "Solver.solve_device(host)"},
@@ -478,6 +539,7 @@ def run_b200(args, wl, wname):
         "clocks": clk.summary(), "clocks_e2e": clk2.summary(),
         "roofline": roofline, "kernels": kernels[:12],
         "result": {"fstar": int(r_last.fstar), "flow_value": int(r_last.flow_value),
+                   "n_filtered": int(r_last.n_filtered),
                    "n_kept": int(r_last.n_kept), "n_bundles": int(r_last.n_bundles),
                    "n_components": int(r_last.n_components), "rounds_total": int(r_last.rounds_total),
                    "rounds_max": int(r_last.rounds_max), "bfs_levels": int(r_last.bfs_levels),

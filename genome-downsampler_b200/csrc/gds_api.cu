@@ -44,7 +44,7 @@ struct gds_ctx {
     DevBuf tkA, tkB, tvA, tvB;
     DevBuf node_rec, n_dsnap;
     DevBuf comp_start, comp_end, comp_sidx, comp_eidx, comp_lo, comp_hi;
-    DevBuf qF, qT, qN, work_counter, comp_stats;
+    DevBuf qF, qT, qN, qH, work_counter, comp_stats;
     DevBuf bitmap, cov_tmp, dem_tmp, vdiff, vexcl;
     DevBuf vs_d, cross_idx, cross_tc, odiff, oexcl, cut_nodes, tile_off_d, head_bits;
     unsigned mf_attr_set = 0;  // bit i: smem attribute set for launch shape i
@@ -57,7 +57,7 @@ struct gds_ctx {
                          &valsA, &valsB, &tile_counts, &radix.hist, &radix.scan.l1, &radix.scan.l2,
                          &scan.l1, &scan.l2, &b_first, &b_key, &b_t, &bund, &diff,
                          &outdeg, &indeg, &excl, &tkA, &tkB, &tvA, &tvB, &node_rec, &n_dsnap, &comp_start, &comp_end, &comp_sidx,
-                         &comp_eidx, &comp_lo, &comp_hi, &qF, &qT, &qN, &work_counter, &comp_stats,
+                         &comp_eidx, &comp_lo, &comp_hi, &qF, &qT, &qN, &qH, &work_counter, &comp_stats,
                          &bitmap, &cov_tmp, &dem_tmp, &vdiff, &vexcl, &vs_d, &cross_idx, &cross_tc,
                          &odiff, &oexcl, &cut_nodes, &tile_off_d, &head_bits};
         for (DevBuf* b : all) b->release();
@@ -111,7 +111,7 @@ void deliver(gds_ctx* c, T* dst, const T* dev_src, size_t n, bool dst_on_device)
 template <int I>
 void launch_maxflow_shape(gds_ctx* c, const MfGraph& mg,
                           const uint32_t* comp_lo, const uint32_t* comp_hi, uint32_t n_comp,
-                          uint32_t* wc, uint32_t* qF, uint32_t* qT, uint32_t* qN,
+                          uint32_t* wc, uint32_t* qF, uint32_t* qT, uint32_t* qN, uint32_t* qH,
                           const SolveParams& sp, CompStats* cstats) {
     constexpr MfShape sh = kMfShapes[I];
     auto kern = k_maxflow<sh.threads, sh.qcap, sh.ctas_per_sm>;
@@ -121,24 +121,24 @@ void launch_maxflow_shape(gds_ctx* c, const MfGraph& mg,
         c->mf_attr_set |= 1u << I;
     }
     int grid = std::min<uint32_t>(n_comp, (uint32_t)kNumSMs * sh.ctas_per_sm);
-    kern<<<grid, sh.threads, smem, c->stream>>>(mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp,
+    kern<<<grid, sh.threads, smem, c->stream>>>(mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp,
                                                 cstats);
 }
 
 void launch_maxflow(gds_ctx* c, const MfGraph& mg,
                     const uint32_t* comp_lo, const uint32_t* comp_hi, uint32_t n_comp, uint32_t* wc,
-                    uint32_t* qF, uint32_t* qT, uint32_t* qN, const SolveParams& sp,
+                    uint32_t* qF, uint32_t* qT, uint32_t* qN, uint32_t* qH, const SolveParams& sp,
                     CompStats* cstats, unsigned long long alg_bytes) {
     KScope ks("maxflow", alg_bytes, c->stream);
     const uint32_t sms = (uint32_t)kNumSMs;
     if (n_comp <= sms * kMfShapes[0].ctas_per_sm)
-        launch_maxflow_shape<0>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp, cstats);
+        launch_maxflow_shape<0>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats);
     else if (n_comp <= sms * kMfShapes[1].ctas_per_sm)
-        launch_maxflow_shape<1>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp, cstats);
+        launch_maxflow_shape<1>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats);
     else if (n_comp <= sms * kMfShapes[2].ctas_per_sm)
-        launch_maxflow_shape<2>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp, cstats);
+        launch_maxflow_shape<2>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats);
     else
-        launch_maxflow_shape<3>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp, cstats);
+        launch_maxflow_shape<3>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats);
     GDS_KERNEL_CHECK();
 }
 
@@ -739,9 +739,10 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             uint32_t* qF = c->qF.get<uint32_t>(n_nodes);
             uint32_t* qT = c->qT.get<uint32_t>(n_nodes);
             uint32_t* qN = c->qN.get<uint32_t>(n_nodes);
+            uint32_t* qH = c->qH.get<uint32_t>(n_nodes);
             uint32_t* wc = c->work_counter.get<uint32_t>(1);
             GDS_CUDA(cudaMemsetAsync(wc, 0, 4, st));
-            launch_maxflow(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, sp, cstats,
+            launch_maxflow(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats,
                            36ull * n_nodes + 20ull * B);
         }
         GDS_CUDA(cudaEventRecord(c->ev[EV_MAXFLOW], st));

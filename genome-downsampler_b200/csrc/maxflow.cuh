@@ -96,23 +96,42 @@ __device__ __forceinline__ void q_append(const Queue<QCAP>& q, uint32_t* count, 
 
 template <uint32_t QCAP>
 struct MfShared {
-    uint32_t qa[QCAP], qb[QCAP], qc[QCAP];
-    uint32_t nF, nT, nN;
+    uint32_t qa[QCAP], qb[QCAP], qc[QCAP], qd[QCAP];
+    uint32_t nF, nT, nN, nH;
     uint32_t relabels_since;
     uint32_t comp;
     unsigned long long pushes, relabels;
     long long sink_flow, stuck;
 };
 
+// Nodes with more than kHeavyDeg incident bundles are not walked by one thread (a serial chain of
+// dependent loads per bundle — variable read lengths give tens of bundles per node): the thread
+// pass puts them on the heavy list H and a second pass gives each a whole WARP, 32 bundles per
+// trip.  Semantics are unchanged: the sequential "push until the excess is gone" over the bundles
+// in their fixed order is an exclusive prefix sum of the admissible residuals across the lanes.
+constexpr uint32_t kHeavyDeg = 6;
+
+__device__ __forceinline__ uint32_t warp_excl_sum(uint32_t v, uint32_t& total) {
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane_id() >= o) incl += t;
+    }
+    total = __shfl_sync(0xffffffffu, incl, 31);
+    return incl - v;
+}
+
 // reverse BFS from the sink; T/N are used as the level queues.  returns the level counter
 template <int THREADS, uint32_t QCAP>
 __device__ uint32_t mf_global_relabel(const MfGraph& G, uint32_t lo, uint32_t hi, Queue<QCAP> T,
-                                      Queue<QCAP> N, MfShared<QCAP>& sh,
+                                      Queue<QCAP> N, Queue<QCAP> H, MfShared<QCAP>& sh,
                                       unsigned long long& bfs_levels) {
     const uint32_t tid = threadIdx.x;
     if (tid == 0) {
         sh.nT = 0;
         sh.nN = 0;
+        sh.nH = 0;
     }
     __syncthreads();
     for (uint32_t v = lo + tid; v <= hi; v += THREADS) {
@@ -126,17 +145,21 @@ __device__ uint32_t mf_global_relabel(const MfGraph& G, uint32_t lo, uint32_t hi
     while (cnt > 0) {
         ++bfs_levels;
         const uint32_t nl = level + 1;
+        auto visit = [&](uint32_t u) {
+            if (atomicCAS(&G.node[u].d, kLabelInf, nl) == kLabelInf) q_append(N, &sh.nN, u);
+        };
         for (uint32_t i = tid; i < cnt; i += THREADS) {
             const uint32_t w = T.get(i);
             uint4 lo4, hi4;
             ld_node(&G.node[w], lo4, hi4);
             // CSR range ends live in the next record (w + 1 <= n_nodes: the sentinel exists)
             const uint4 nx_hi = GDS_MF_LD(reinterpret_cast<const uint4*>(&G.node[w + 1]) + 1);
-            auto visit = [&](uint32_t u) {
-                if (atomicCAS(&G.node[u].d, kLabelInf, nl) == kLabelInf) q_append(N, &sh.nN, u);
-            };
             if (w < hi) visit(w + 1);                              // back arc (w+1) -> w: residual
             if (w > lo && (int32_t)hi4.y > 0) visit(w - 1);        // reverse of back arc w -> w-1
+            if ((nx_hi.w - hi4.w) + (nx_hi.z - hi4.z) > kHeavyDeg) {
+                q_append(H, &sh.nH, w);  // bundles of a heavy node: warp pass below
+                continue;
+            }
             for (uint32_t k = hi4.w, ke = nx_hi.w; k < ke; ++k) {  // bundles s -> w with residual
                 const uint4 b = ld_bundle(&G.bund[ld_u32(&G.in_bid[k])]);
                 if (b.z < b.y) visit(b.w);
@@ -145,6 +168,25 @@ __device__ uint32_t mf_global_relabel(const MfGraph& G, uint32_t lo, uint32_t hi
                 const uint4 r = ld_bundle(&G.bund[b]);
                 if (r.z > 0) visit(r.x);
             }
+        }
+        __syncthreads();
+        if (sh.nH) {  // uniform
+            const uint32_t nH = sh.nH, lane = lane_id();
+            for (uint32_t h = tid >> 5; h < nH; h += THREADS / 32) {
+                const uint32_t w = H.get(h);
+                const uint4 hi4 = GDS_MF_LD(reinterpret_cast<const uint4*>(&G.node[w]) + 1);
+                const uint4 nx_hi = GDS_MF_LD(reinterpret_cast<const uint4*>(&G.node[w + 1]) + 1);
+                for (uint32_t k = hi4.w + lane; k < nx_hi.w; k += 32) {
+                    const uint4 b = ld_bundle(&G.bund[ld_u32(&G.in_bid[k])]);
+                    if (b.z < b.y) visit(b.w);
+                }
+                for (uint32_t b = hi4.z + lane; b < nx_hi.z; b += 32) {
+                    const uint4 r = ld_bundle(&G.bund[b]);
+                    if (r.z > 0) visit(r.x);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) sh.nH = 0;
         }
         __syncthreads();
         cnt = sh.nN;
@@ -172,7 +214,7 @@ template <int THREADS, uint32_t QCAP, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __restrict__ comp_hi,
           uint32_t n_comp, uint32_t* work_counter, uint32_t* qF_g, uint32_t* qT_g, uint32_t* qN_g,
-          SolveParams P, CompStats* __restrict__ stats) {
+          uint32_t* qH_g, SolveParams P, CompStats* __restrict__ stats) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MfShared<QCAP>& sh = *reinterpret_cast<MfShared<QCAP>*>(smem_raw);
     const uint32_t tid = threadIdx.x;
@@ -184,7 +226,8 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
         if (c >= n_comp) break;
         const uint32_t lo = comp_lo[c], hi = comp_hi[c];
         const uint32_t ncomp = hi - lo + 1;
-        Queue<QCAP> F{sh.qa, qF_g + lo}, T{sh.qb, qT_g + lo}, N{sh.qc, qN_g + lo};
+        Queue<QCAP> F{sh.qa, qF_g + lo}, T{sh.qb, qT_g + lo}, N{sh.qc, qN_g + lo},
+            H{sh.qd, qH_g + lo};
         if (tid == 0) {
             sh.nF = 0;
             sh.relabels_since = 0;
@@ -197,7 +240,7 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
         const long long t_begin = clock64();
         unsigned long long my_pushes = 0, my_relabels = 0;
         long long my_sink = 0, my_stuck = 0;
-        uint32_t last_levels = mf_global_relabel<THREADS, QCAP>(G, lo, hi, T, N, sh, bfs_levels);
+        uint32_t last_levels = mf_global_relabel<THREADS, QCAP>(G, lo, hi, T, N, H, sh, bfs_levels);
         for (uint32_t v = lo + tid; v <= hi; v += THREADS) {
             if ((int32_t)ld_u32(reinterpret_cast<const uint32_t*>(&G.node[v].e)) > 0) {
                 G.node[v].stamp = 1;
@@ -217,7 +260,7 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
                 (unsigned long long)sh.relabels_since * 100 >=
                     (unsigned long long)P.gr_relabel_pct * ncomp) {
                 __syncthreads();  // everyone has read relabels_since
-                last_levels = mf_global_relabel<THREADS, QCAP>(G, lo, hi, T, N, sh, bfs_levels);
+                last_levels = mf_global_relabel<THREADS, QCAP>(G, lo, hi, T, N, H, sh, bfs_levels);
                 ++grs;
                 if (tid == 0) sh.relabels_since = 0;
                 rounds_since = 0;
@@ -243,6 +286,10 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
                 const uint32_t dv = lo4.x;
                 G.d_snap[v] = dv;  // re-sync the snapshot of a node relabelled last round
                 if (dv >= kLabelInf) continue;
+                if ((r_hi.z - hi4.z) + (r_hi.w - hi4.w) > kHeavyDeg) {
+                    q_append(H, &sh.nH, v);  // many bundles: a whole warp takes it below
+                    continue;
+                }
                 int32_t ex = (int32_t)lo4.z;
                 auto give = [&](uint32_t w, int32_t dl, uint32_t w_stamp) {
                     // eadd is 0 between rounds and every delta is positive: the first giver of the
@@ -312,6 +359,111 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
                 G.node[v].e = ex;
             }
             __syncthreads();
+            if (sh.nH) {  // ---- heavy nodes, one warp each (uniform branch)
+                const uint32_t nH = sh.nH, lane = lane_id();
+                for (uint32_t h = tid >> 5; h < nH; h += THREADS / 32) {
+                    const uint32_t v = H.get(h);
+                    uint4 lo4, hi4, r_lo, r_hi;  // every lane loads the same sectors (broadcast)
+                    ld_node(&G.node[v], lo4, hi4);
+                    ld_node(&G.node[v + 1], r_lo, r_hi);
+                    const uint4 l_lo = v > lo ? GDS_MF_LD(reinterpret_cast<const uint4*>(&G.node[v - 1]))
+                                              : make_uint4(kLabelInf, 0, 0, 0);
+                    const uint32_t dv = lo4.x;
+                    int32_t ex = (int32_t)lo4.z;  // uniform across the warp throughout
+                    auto give = [&](uint32_t w, int32_t dl, uint32_t w_stamp) {
+                        const int32_t old = atomicAdd(&G.node[w].eadd, dl);
+                        if (old == 0 && w_stamp != round) q_append(T, &sh.nT, w);
+                        ++my_pushes;
+                    };
+                    if (dv == 1) {  // 1. sink arc
+                        const int32_t sk = (int32_t)hi4.x;
+                        if (sk > 0) {
+                            const int32_t dl = min(ex, sk);
+                            ex -= dl;
+                            if (lane == 0) {
+                                G.node[v].snk = sk - dl;
+                                my_sink += dl;
+                                ++my_pushes;
+                            }
+                        }
+                    }
+                    // 2. own bundles, farthest end first: lane i looks at bundle (top - 1 - i);
+                    // "push until the excess is gone" = exclusive prefix sum of the residuals
+                    for (uint32_t top = r_hi.z; ex > 0 && top > hi4.z;
+                         top = top - hi4.z > 32 ? top - 32 : hi4.z) {
+                        const bool have = top - hi4.z > lane;
+                        const uint32_t b = top - 1 - lane;
+                        uint4 br = make_uint4(0, 0, 0, 0);
+                        uint32_t r = 0, tstamp = 0;
+                        if (have) {
+                            br = ld_bundle(&G.bund[b]);
+                            r = br.y - br.z;
+                            if (r) {
+                                const uint32_t td = ld_u32(&G.node[br.x].d);
+                                tstamp = ld_u32(&G.node[br.x].stamp);
+                                if (td + 1 != dv) r = 0;
+                            }
+                        }
+                        uint32_t tot;
+                        const uint32_t pre = warp_excl_sum(r, tot);
+                        if (r && pre < (uint32_t)ex) {
+                            const int32_t dl = (int32_t)min(r, (uint32_t)ex - pre);
+                            G.bund[b].f = br.z + dl;
+                            give(br.x, dl, tstamp);
+                        }
+                        ex -= (int32_t)min((uint32_t)ex, tot);
+                    }
+                    // 3. cancel back-flow towards the right neighbour
+                    if (ex > 0 && v < hi && r_lo.x + 1 == dv) {
+                        const int32_t gr = (int32_t)r_hi.y;
+                        if (gr > 0) {
+                            const int32_t dl = min(ex, gr);
+                            ex -= dl;
+                            if (lane == 0) {
+                                G.node[v + 1].g = gr - dl;
+                                give(v + 1, dl, r_lo.y);
+                            }
+                        }
+                    }
+                    // 4. back arc to the left neighbour (infinite capacity)
+                    if (ex > 0 && v > lo && l_lo.x + 1 == dv) {
+                        if (lane == 0) {
+                            G.node[v].g = (int32_t)hi4.y + ex;
+                            give(v - 1, ex, l_lo.y);
+                        }
+                        ex = 0;
+                    }
+                    // 5. cancel flow on incoming bundles, nearest start first
+                    for (uint32_t top = r_hi.w; ex > 0 && top > hi4.w;
+                         top = top - hi4.w > 32 ? top - 32 : hi4.w) {
+                        const bool have = top - hi4.w > lane;
+                        uint32_t b = 0, r = 0, sstamp = 0;
+                        uint4 br = make_uint4(0, 0, 0, 0);
+                        if (have) {
+                            b = ld_u32(&G.in_bid[top - 1 - lane]);
+                            br = ld_bundle(&G.bund[b]);
+                            r = br.z;
+                            if (r) {
+                                const uint32_t sd = ld_u32(&G.node[br.w].d);
+                                sstamp = ld_u32(&G.node[br.w].stamp);
+                                if (sd + 1 != dv) r = 0;
+                            }
+                        }
+                        uint32_t tot;
+                        const uint32_t pre = warp_excl_sum(r, tot);
+                        if (r && pre < (uint32_t)ex) {
+                            const int32_t dl = (int32_t)min(r, (uint32_t)ex - pre);
+                            G.bund[b].f = br.z - dl;
+                            give(br.w, dl, sstamp);
+                        }
+                        ex -= (int32_t)min((uint32_t)ex, tot);
+                    }
+                    if (lane == 0) G.node[v].e = ex;
+                }
+                __syncthreads();
+                if (tid == 0) sh.nH = 0;
+                __syncthreads();
+            }
             const uint32_t cntT = sh.nT;
 
             // ---------------- phase B: merge, relabel from snapshot, next frontier ----------------
@@ -325,19 +477,23 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
                 bool frozen = dw >= kLabelInf;
                 if (in_front && left > 0 && !frozen) {
                     const uint4 r_hi = GDS_MF_LD(reinterpret_cast<const uint4*>(&G.node[w + 1]) + 1);
-                    uint32_t mn = kLabelInf;
-                    if ((int32_t)hi4.x > 0) mn = 0;
-                    for (uint32_t b = hi4.z, be = r_hi.z; b < be; ++b) {
-                        const uint4 br = ld_bundle(&G.bund[b]);
-                        if (br.z < br.y) mn = min(mn, ld_u32(&G.d_snap[br.x]));
+                    if ((r_hi.z - hi4.z) + (r_hi.w - hi4.w) > kHeavyDeg) {
+                        q_append(H, &sh.nH, w);  // the min over many bundles: warp pass below
+                    } else {
+                        uint32_t mn = kLabelInf;
+                        if ((int32_t)hi4.x > 0) mn = 0;
+                        for (uint32_t b = hi4.z, be = r_hi.z; b < be; ++b) {
+                            const uint4 br = ld_bundle(&G.bund[b]);
+                            if (br.z < br.y) mn = min(mn, ld_u32(&G.d_snap[br.x]));
+                        }
+                        if (w < hi && (int32_t)r_hi.y > 0) mn = min(mn, ld_u32(&G.d_snap[w + 1]));
+                        if (w > lo) mn = min(mn, ld_u32(&G.d_snap[w - 1]));
+                        for (uint32_t k = hi4.w, ke = r_hi.w; k < ke; ++k) {
+                            const uint4 br = ld_bundle(&G.bund[ld_u32(&G.in_bid[k])]);
+                            if (br.z > 0) mn = min(mn, ld_u32(&G.d_snap[br.w]));
+                        }
+                        G.node[w].d = mn >= kLabelInf ? kLabelInf : mn + 1;
                     }
-                    if (w < hi && (int32_t)r_hi.y > 0) mn = min(mn, ld_u32(&G.d_snap[w + 1]));
-                    if (w > lo) mn = min(mn, ld_u32(&G.d_snap[w - 1]));
-                    for (uint32_t k = hi4.w, ke = r_hi.w; k < ke; ++k) {
-                        const uint4 br = ld_bundle(&G.bund[ld_u32(&G.in_bid[k])]);
-                        if (br.z > 0) mn = min(mn, ld_u32(&G.d_snap[br.w]));
-                    }
-                    G.node[w].d = mn >= kLabelInf ? kLabelInf : mn + 1;
                     ++my_relabels;
                     atomicAdd(&sh.relabels_since, 1u);
                     frozen = false;  // stays queued one more round so its snapshot is re-synced
@@ -355,6 +511,31 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
                 }
             }
             __syncthreads();
+            if (sh.nH) {  // ---- relabels of heavy nodes, one warp each (labels come from d_snap,
+                          //      bundle flows and g are not written in this phase)
+                const uint32_t nH = sh.nH, lane = lane_id();
+                for (uint32_t h = tid >> 5; h < nH; h += THREADS / 32) {
+                    const uint32_t w = H.get(h);
+                    const uint4 hi4 = GDS_MF_LD(reinterpret_cast<const uint4*>(&G.node[w]) + 1);
+                    const uint4 r_hi = GDS_MF_LD(reinterpret_cast<const uint4*>(&G.node[w + 1]) + 1);
+                    uint32_t mn = kLabelInf;
+                    if ((int32_t)hi4.x > 0) mn = 0;
+                    for (uint32_t b = hi4.z + lane; b < r_hi.z; b += 32) {
+                        const uint4 br = ld_bundle(&G.bund[b]);
+                        if (br.z < br.y) mn = min(mn, ld_u32(&G.d_snap[br.x]));
+                    }
+                    if (w < hi && (int32_t)r_hi.y > 0) mn = min(mn, ld_u32(&G.d_snap[w + 1]));
+                    if (w > lo) mn = min(mn, ld_u32(&G.d_snap[w - 1]));
+                    for (uint32_t k = hi4.w + lane; k < r_hi.w; k += 32) {
+                        const uint4 br = ld_bundle(&G.bund[ld_u32(&G.in_bid[k])]);
+                        if (br.z > 0) mn = min(mn, ld_u32(&G.d_snap[br.w]));
+                    }
+                    mn = __reduce_min_sync(0xffffffffu, mn);
+                    if (lane == 0) G.node[w].d = mn >= kLabelInf ? kLabelInf : mn + 1;
+                }
+                __syncthreads();
+                if (tid == 0) sh.nH = 0;
+            }
             {
                 Queue<QCAP> tmp = F;
                 F = N;

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <functional>
 #include <random>
+#include <vector>
 
 #include "bam-api/paired_reads.hpp"
 
@@ -34,4 +35,15 @@ void rand_reads_soa(std::mt19937& generator, bam_api::ReadIndex pairs_count,
                     bam_api::Index genome_length, uint32_t read_length,
                     const std::function<double(double)>& dist_func, const SoaOut& out,
                     int32_t max_quality = kMaxGenQuality);
+
+// Amplicon-aware extension for BASELINE config 2 (the reference's generator cannot express it:
+// constant seq_length and mates placed over the whole genome, reads_gen.cpp:46-49,79-82).
+// Per pair, in this draw order: len1, len2 ~ U{min_len..max_len}; u ~ U[0,1); amplicon k ~ U;
+// if u < p_inside and the amplicon holds both mates, both starts ~ U inside amplicon k, else
+// both starts ~ U over the genome; then quality1, quality2 ~ U{0..max_quality}.
+void rand_reads_amplicon_soa(std::mt19937& generator, bam_api::ReadIndex pairs_count,
+                             bam_api::Index genome_length, const std::vector<uint32_t>& amp_start,
+                             const std::vector<uint32_t>& amp_end, double p_inside,
+                             uint32_t min_len, uint32_t max_len, const SoaOut& out,
+                             int32_t max_quality = kMaxGenQuality);
 }  // namespace reads_gen

@@ -41,6 +41,19 @@ int gdsh_gen_reads(uint32_t seed, uint64_t pairs, uint32_t genome_len, uint32_t 
     return 0;
 }
 
+// config-2 style reads: mates inside a random amplicon with probability p_inside
+int gdsh_gen_reads_amplicon(uint32_t seed, uint64_t pairs, uint32_t genome_len, uint32_t n_amp,
+                            const uint32_t* amp_start, const uint32_t* amp_end, double p_inside,
+                            uint32_t min_len, uint32_t max_len, uint32_t* start, uint32_t* end,
+                            uint8_t* mapq, uint32_t* seq_len) {
+    if (n_amp == 0 || max_len < min_len || genome_len < 2 * max_len) return 1;
+    std::mt19937 mt(seed);
+    std::vector<uint32_t> a0(amp_start, amp_start + n_amp), a1(amp_end, amp_end + n_amp);
+    reads_gen::rand_reads_amplicon_soa(mt, pairs, genome_len, a0, a1, p_inside, min_len, max_len,
+                                       reads_gen::SoaOut{start, end, mapq, seq_len});
+    return 0;
+}
+
 // One downsample through the plugin interface exactly as App::execute drives it
 // (src/app.cpp:130-135): SolverManager.get(name).solve(max_coverage, bam_api).
 // Returns the number of kept indices written (ascending), or -1 for an unknown algorithm.

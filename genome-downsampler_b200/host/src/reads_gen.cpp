@@ -120,3 +120,47 @@ void reads_gen::rand_reads_soa(std::mt19937& generator, bam_api::ReadIndex pairs
     SoaSink sink{out};
     weighted_into(sink, generator, pairs_count, genome_length, read_length, dist_func, max_quality);
 }
+
+void reads_gen::rand_reads_amplicon_soa(std::mt19937& gen, bam_api::ReadIndex pairs,
+                                        bam_api::Index genome_length,
+                                        const std::vector<uint32_t>& amp_start,
+                                        const std::vector<uint32_t>& amp_end, double p_inside,
+                                        uint32_t min_len, uint32_t max_len, const SoaOut& out,
+                                        int32_t max_quality) {
+    std::uniform_int_distribution<> quality(0, max_quality);
+    std::uniform_int_distribution<> length(static_cast<int>(min_len), static_cast<int>(max_len));
+    std::uniform_int_distribution<> pick(0, static_cast<int>(amp_start.size()) - 1);
+    std::uniform_real_distribution<double> unit(0.0, 1.0);
+    for (bam_api::ReadIndex p = 0; p < pairs; ++p) {
+        const uint32_t l1 = static_cast<uint32_t>(length(gen));
+        const uint32_t l2 = static_cast<uint32_t>(length(gen));
+        const bool inside = unit(gen) < p_inside;
+        const uint32_t k = static_cast<uint32_t>(pick(gen));
+        const uint64_t a0 = amp_start[k], a1 = amp_end[k];
+        uint64_t s1, s2;
+        if (inside && a1 - a0 + 1 >= std::max(l1, l2)) {
+            std::uniform_int_distribution<uint64_t> d1(a0, a1 + 1 - l1), d2(a0, a1 + 1 - l2);
+            s1 = d1(gen);
+            s2 = d2(gen);
+        } else {
+            std::uniform_int_distribution<uint64_t> d1(0, genome_length - l1), d2(0, genome_length - l2);
+            s1 = d1(gen);
+            s2 = d2(gen);
+        }
+        const uint64_t i = 2 * p;
+        out.start[i] = static_cast<uint32_t>(s1);
+        out.end[i] = static_cast<uint32_t>(s1 + l1 - 1);
+        const uint32_t q1 = static_cast<uint32_t>(quality(gen));
+        out.start[i + 1] = static_cast<uint32_t>(s2);
+        out.end[i + 1] = static_cast<uint32_t>(s2 + l2 - 1);
+        const uint32_t q2 = static_cast<uint32_t>(quality(gen));
+        if (out.mapq) {
+            out.mapq[i] = static_cast<uint8_t>(q1);
+            out.mapq[i + 1] = static_cast<uint8_t>(q2);
+        }
+        if (out.seq_len) {
+            out.seq_len[i] = l1;
+            out.seq_len[i + 1] = l2;
+        }
+    }
+}

@@ -21,6 +21,11 @@ def load():
         L.gdsh_gen_reads.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gdsh_gen_reads.restype = C.c_int
+        L.gdsh_gen_reads_amplicon.argtypes = [C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32,
+                                              C.c_void_p, C.c_void_p, C.c_double, C.c_uint32,
+                                              C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p]
+        L.gdsh_gen_reads_amplicon.restype = C.c_int
         L.gdsh_plugin_solve.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p,
                                         C.c_uint32, C.c_void_p, C.c_uint64]
         L.gdsh_plugin_solve.restype = C.c_int64
@@ -37,6 +42,27 @@ def gen_reads_into(seed, pairs, genome_len, read_len, start, end, mapq=None, seq
                                seq_len.ctypes.data if seq_len is not None else None)
     if rc != 0:
         raise ValueError("gdsh_gen_reads rc=%d" % rc)
+
+
+def artic_amplicons(genome_len=30_000, n_amplicons=98, amp_len=400, overlap=98):
+    """Synthetic ARTIC-style tiling: amplicon k = [k*(amp_len-overlap), +amp_len-1]."""
+    k = np.arange(n_amplicons, dtype=np.uint32)
+    a0 = k * np.uint32(amp_len - overlap)
+    a1 = a0 + np.uint32(amp_len - 1)
+    assert int(a1[-1]) < genome_len
+    return a0, a1
+
+
+def gen_reads_amplicon_into(seed, pairs, genome_len, amp_start, amp_end, start, end, mapq, seq_len,
+                            p_inside=0.9, min_len=60, max_len=150):
+    a0 = np.ascontiguousarray(amp_start, np.uint32)
+    a1 = np.ascontiguousarray(amp_end, np.uint32)
+    rc = load().gdsh_gen_reads_amplicon(seed, pairs, genome_len, len(a0), a0.ctypes.data,
+                                        a1.ctypes.data, p_inside, min_len, max_len,
+                                        start.ctypes.data, end.ctypes.data, mapq.ctypes.data,
+                                        seq_len.ctypes.data)
+    if rc != 0:
+        raise ValueError("gdsh_gen_reads_amplicon rc=%d" % rc)
 
 
 def gen_batch(seeds, pairs, genome_len, read_len, start, end, threads=8):

@@ -116,3 +116,17 @@ def test_same_capped_coverage_as_the_references_own_cuda_solver(solver, O, tmp_p
         assert np.all(np.minimum(cin, M) <= c_ref)          # the reference's own invariant
         assert np.array_equal(np.minimum(c_ref, M), np.minimum(c_us, M))
         assert np.array_equal(np.minimum(c_us, M), np.minimum(cin, M))
+
+
+def test_host_amplicon_generator_matches_oracle(hostlib, O):
+    bed, tsv = O.artic_scheme()
+    a0, a1 = O.parse_amplicons(bed, tsv)
+    h0, h1 = hostlib.artic_amplicons()
+    assert np.array_equal(np.sort(a0), h0) and np.array_equal(np.sort(a1), h1)
+    n = 40_000
+    s = np.empty(n, np.uint32); e = np.empty(n, np.uint32)
+    q = np.empty(n, np.uint8); l = np.empty(n, np.uint32)
+    hostlib.gen_reads_amplicon_into(777, n // 2, 30_000, a0, a1, s, e, q, l)
+    s0, e0, q0, l0 = O.gen_reads_amplicon(777, n // 2, 30_000, a0, a1)
+    assert np.array_equal(s, s0) and np.array_equal(e, e0)
+    assert np.array_equal(q, q0.astype(np.uint8)) and np.array_equal(l, l0)

@@ -9,7 +9,7 @@ pkg=load_package()
 import bench
 for wname in ('c4','c1'):
     wl=bench.WORKLOADS[wname]
-    st,en,_=bench.generate(wl,[0],pinned=False)
+    st,en,_,_=bench.generate(wl,[0],pinned=False)
     s=st.numpy().view(np.uint32); e=en.numpy().view(np.uint32)
     solver=pkg.Solver(0)
     for i in range(2): r=solver.solve(s,e,wl['L'],wl['M'])
