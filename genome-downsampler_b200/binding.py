@@ -14,7 +14,8 @@ _ERR = {1: "GDS_ERR_ARG", 2: "GDS_ERR_RANGE", 3: "GDS_ERR_CUDA", 4: "GDS_ERR_NOM
         5: "GDS_ERR_NOCONVERGE"}
 
 ENTRY_POINTS = ["gds_abi_version", "gds_create", "gds_destroy", "gds_last_error", "gds_set_stream",
-                "gds_solve", "gds_kernel_profile", "gds_kernel_profile_reset", "gds_bitmap_to_indices"]
+                "gds_solve", "gds_kernel_profile", "gds_kernel_profile_reset", "gds_bitmap_to_indices",
+                "gds_host_alloc", "gds_host_free"]
 
 
 class GdsError(RuntimeError):

@@ -256,6 +256,19 @@ extern "C" void gds_destroy(gds_ctx* c) {
     delete c;
 }
 
+extern "C" void* gds_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" void gds_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
 extern "C" const char* gds_last_error(const gds_ctx* c) { return c ? c->err.c_str() : "null context"; }
 
 extern "C" int gds_set_stream(gds_ctx* c, void* cuda_stream) {

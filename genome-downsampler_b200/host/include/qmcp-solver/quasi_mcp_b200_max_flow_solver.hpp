@@ -24,6 +24,25 @@ class QuasiMcpB200MaxFlowSolver : public Solver {
     void set_verify(bool v) { verify_ = v; }
 
    private:
+    // grow-only page-locked staging buffer (gds_host_alloc): the narrowing loop writes straight
+    // into it and the library copies from it at full PCIe speed
+    struct Pinned {
+        void* p = nullptr;
+        size_t cap = 0;
+        template <typename T>
+        T* get(size_t n) {
+            size_t bytes = (n ? n : 1) * sizeof(T);
+            if (bytes > cap) {
+                gds_host_free(p);
+                p = gds_host_alloc(bytes + bytes / 8);
+                cap = p ? bytes + bytes / 8 : 0;
+            }
+            return static_cast<T*>(p);
+        }
+        ~Pinned() { gds_host_free(p); }
+    };
+    Pinned start_, end_, mapq_, seq_len_, bitmap_, pair_pass_;
+
     int device_;
     gds_ctx* ctx_ = nullptr;  // created lazily, reused across solve() calls
     gds_result last_{};

@@ -3,6 +3,7 @@
 // selected with -a through the qmcp::Solver interface, with LIVE checks (the reference's asserts
 // vanish under NDEBUG), plus a device-filter case (config 2 shape).
 //   gds_host_test [-a quasi-mcp-b200] [-o DIR]
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <filesystem>
@@ -46,13 +47,21 @@ static int run_case(qmcp::Solver& solver, const Case& c, const fs::path& outdir)
     auto input = c.make();
     bam_api::BamApi api(input);
     Cover in_cover = api.find_input_cover();
+    // wall time of solve() as the reference logs it (src/tests/scoped_timer.hpp:9-13, app.cpp:132-139)
+    auto t0 = std::chrono::steady_clock::now();
     auto ids = solver.solve(c.m, api);
+    double wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    double dev_ms = -1;
+    if (auto* b200 = dynamic_cast<qmcp::QuasiMcpB200MaxFlowSolver*>(&solver))
+        dev_ms = b200->last_result().ms_total;
     Cover out_cover = api.find_filtered_cover(*ids);
     bool ok = is_out_cover_valid(in_cover, out_cover, c.m);
     bool sorted = std::is_sorted(ids->begin(), ids->end()) &&
                   std::adjacent_find(ids->begin(), ids->end()) == ids->end();
     LOG_WITH_LEVEL(logging::INFO) << "  " << c.name << ": reads=" << input.reads.size()
-                                  << " kept=" << ids->size() << (ok && sorted ? " PASSED" : " FAILED");
+                                  << " kept=" << ids->size() << " solve() took " << wall_ms
+                                  << " ms (device " << dev_ms << " ms)"
+                                  << (ok && sorted ? " PASSED" : " FAILED");
     if (!outdir.empty()) {
         std::ofstream f(outdir / (c.name + ".cov"));
         for (size_t i = 0; i < in_cover.size(); ++i) f << i << "\t" << in_cover[i] << "\t" << out_cover[i] << "\n";

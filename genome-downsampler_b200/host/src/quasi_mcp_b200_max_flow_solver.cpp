@@ -30,8 +30,12 @@ std::unique_ptr<Solution> QuasiMcpB200MaxFlowSolver::solve(uint32_t max_coverage
         LOG_WITH_LEVEL(logging::ERROR) << "quasi-mcp-b200: input beyond 32-bit device limits";
         std::exit(EXIT_FAILURE);
     }
-    std::vector<uint32_t> start(n), end(n), seq_len;
-    std::vector<uint8_t> mapq;
+    uint32_t* start = start_.get<uint32_t>(n);
+    uint32_t* end = end_.get<uint32_t>(n);
+    if (!start || !end) {
+        LOG_WITH_LEVEL(logging::ERROR) << "quasi-mcp-b200: cannot allocate pinned staging buffers";
+        std::exit(EXIT_FAILURE);
+    }
     // the narrowing loop also yields the exact read-length bounds the library can use to fold its
     // input validation into the first sort pass (gds_reads.len_min / len_max)
     uint32_t len_min = 0xffffffffu, len_max = 0;
@@ -48,17 +52,25 @@ std::unique_ptr<Solution> QuasiMcpB200MaxFlowSolver::solve(uint32_t max_coverage
     }
     uint64_t off[2] = {0, n};
     uint32_t ref_len = static_cast<uint32_t>(L);
-    gds_reads rd{1, off, &ref_len, start.data(), end.data(), nullptr, nullptr,
+    gds_reads rd{1, off, &ref_len, start, end, nullptr, nullptr,
                  lens_ok ? len_min : 0, lens_ok ? len_max : 0};
     gds_filter flt{};
     std::vector<uint32_t> amp_s, amp_e;
-    std::vector<uint8_t> pair_pass;
+    uint8_t* pair_pass = nullptr;
     if (device_filter) {
-        seq_len.assign(in.seq_lengths.begin(), in.seq_lengths.end());
-        mapq.resize(n);
-        for (uint64_t i = 0; i < n; ++i) mapq[i] = static_cast<uint8_t>(std::min<uint32_t>(in.qualities[i], 255));
-        rd.mapq = mapq.data();
-        rd.seq_len = seq_len.data();
+        uint32_t* seq_len = seq_len_.get<uint32_t>(n);
+        uint8_t* mapq = mapq_.get<uint8_t>(n);
+        pair_pass = pair_pass_.get<uint8_t>(n / 2 + 1);
+        if (!seq_len || !mapq || !pair_pass) {
+            LOG_WITH_LEVEL(logging::ERROR) << "quasi-mcp-b200: cannot allocate pinned staging buffers";
+            std::exit(EXIT_FAILURE);
+        }
+        for (uint64_t i = 0; i < n; ++i) {
+            seq_len[i] = in.seq_lengths[i];
+            mapq[i] = static_cast<uint8_t>(std::min<uint32_t>(in.qualities[i], 255));
+        }
+        rd.mapq = mapq;
+        rd.seq_len = seq_len;
         flt.min_seq_length = bam_api.min_seq_length();
         flt.min_mapq = std::min<uint32_t>(bam_api.min_mapq(), 256);  // > 255 can never pass anyway
         if (bam_api.amplicon_behaviour() == bam_api::AmpliconBehaviour::FILTER) {
@@ -74,12 +86,15 @@ std::unique_ptr<Solution> QuasiMcpB200MaxFlowSolver::solve(uint32_t max_coverage
             flt.amp_start = amp_s.data();
             flt.amp_end = amp_e.data();
         }
-        pair_pass.assign(n / 2 + 1, 0);
     }
-    std::vector<uint32_t> bitmap((n + 31) / 32 + 1, 0);
+    uint32_t* bitmap = bitmap_.get<uint32_t>((n + 31) / 32 + 1);
+    if (!bitmap) {
+        LOG_WITH_LEVEL(logging::ERROR) << "quasi-mcp-b200: cannot allocate pinned staging buffers";
+        std::exit(EXIT_FAILURE);
+    }
     last_ = gds_result{};
-    last_.kept_bitmap = bitmap.data();
-    last_.pair_pass = device_filter ? pair_pass.data() : nullptr;
+    last_.kept_bitmap = bitmap;
+    last_.pair_pass = pair_pass;
     int rc = gds_solve(ctx_, &rd, device_filter ? &flt : nullptr, max_coverage, nullptr,
                        verify_ ? GDS_VERIFY : 0, &last_);
     last_.kept_bitmap = nullptr;
@@ -93,13 +108,11 @@ std::unique_ptr<Solution> QuasiMcpB200MaxFlowSolver::solve(uint32_t max_coverage
                                        << last_.verify_violations << " bad positions";
         std::exit(EXIT_FAILURE);
     }
-    if (device_filter) {
-        pair_pass.resize(n / 2);
-        bam_api.apply_pair_filter(pair_pass);  // BamApi now holds the post-filter arrays
-    }
+    if (device_filter)  // BamApi now holds the post-filter arrays
+        bam_api.apply_pair_filter(std::vector<uint8_t>(pair_pass, pair_pass + n / 2));
     auto sol = std::make_unique<Solution>(last_.n_kept);
     static_assert(sizeof(bam_api::ReadIndex) == sizeof(uint64_t), "ReadIndex must be 64-bit");
-    uint64_t k = gds_bitmap_to_indices(bitmap.data(), last_.n_filtered,
+    uint64_t k = gds_bitmap_to_indices(bitmap, last_.n_filtered,
                                        reinterpret_cast<uint64_t*>(sol->data()), sol->size());
     sol->resize(std::min<uint64_t>(k, sol->size()));
     LOG_WITH_LEVEL(logging::DEBUG) << "quasi-mcp-b200: F*=" << last_.fstar << " kept=" << last_.n_kept

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GDS_ABI_VERSION 3
+#define GDS_ABI_VERSION 4
 
 /* status codes (the reference has none: it logs and exits, cuda_helpers.cuh:13-21) */
 enum {
@@ -122,6 +122,12 @@ const char* gds_last_error(const gds_ctx* ctx);
 int gds_abi_version(void);
 /* run all work on this cudaStream_t (as void*); NULL = the context's own stream */
 int gds_set_stream(gds_ctx* ctx, void* cuda_stream);
+
+/* Page-locked host memory for staging buffers (a host-only caller needs no CUDA headers):
+ * gds_solve copies from/to pinned buffers at full PCIe speed, pageable ones take a bounce copy.
+ * The reference's CUDA solver copies from pageable std::vector (cuda_helpers.cuh:33-48). */
+void* gds_host_alloc(size_t bytes);
+void gds_host_free(void* p);
 
 /* The whole hot path.  Replaces QuasiMcpCpuMaxFlowSolver::solve
  * (quasi_mcp_cpu_max_flow_solver.cpp:11-28) and QuasiMcpCudaMaxFlowSolver::solve
