@@ -119,7 +119,7 @@ class ClockSampler:
                0x2: "applications_clocks_setting", 0x10: "sync_boost"}
     BAD = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown")
 
-    def __init__(self, devices, period=0.02):
+    def __init__(self, devices, period=0.01):
         self.devices, self.period = list(devices), period
         self.sm, self.reasons, self.sm_max = [], set(), 0
         self._stop = threading.Event()
@@ -131,6 +131,12 @@ class ClockSampler:
             self.h = [pynvml.nvmlDeviceGetHandleByIndex(i) for i in self.devices]
             self.sm_max = max(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
                               for h in self.h)
+            for h in self.h:  # prime the queries: the first call of each is slow
+                pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
         except Exception as ex:  # no NVML: report it, do not fake numbers
             self.nv, self.h = None, []
             self.err = repr(ex)
