@@ -1,0 +1,321 @@
+// direct.cuh — sort-free K2 (bundles) and K5 (selection) for samples whose key space fits in the
+// shared memory of one SM.
+//
+// A bundle is the set of reads with one (start node, length) key (graph.cuh).  When a sample has
+// at most kDirectMaxKeys possible keys (ref_len x #lengths: 30 000 for a 30 kb reference with
+// fixed-length reads, BASELINE configs 0/2/4), its bundle multiplicities are a HISTOGRAM of the
+// reads: one shared-memory atomic per read, every input byte read exactly once at HBM speed
+// (tools/hist_probe.cu: 7.0 TB/s on B200 — the atomic unit keeps up with the loads), instead of
+// the two-pass radix sort's 48 bytes per read.  Restates the same network as the sort path
+// (quasi_mcp_cpu_max_flow_solver.cpp:30-87 on bundles) — bundle order, node ids, difference array
+// and CSR are identical, so K3 and every parity test see the same graph.
+//
+// K5 without a sorted read order: "a bundle with flow f keeps its f lowest-index reads"
+// (select.cuh) becomes an ordered walk.  One CTA per sample holds the per-key quota (= f) in
+// shared memory and walks the reads in index order, tile by tile; a read whose key still has
+// quota is a candidate.  If a tile holds no more candidates of a key than its quota they are all
+// kept (order irrelevant); otherwise (each key at most once) the candidates of that key are
+// ranked by index.  The walk stops when every quota is used up — on uniform data after ~15-20 %
+// of the sample.
+#pragma once
+#include "common.cuh"
+#include "graph.cuh"
+#include "prep.cuh"
+#include "scan.cuh"
+
+namespace gds {
+
+constexpr uint32_t kDirectMaxKeys = 48 * 1024;  // u32 counters: 192 KB of shared memory
+constexpr int kDhThreads = 1024;
+constexpr int kDkThreads = 256;   // key tiles of the bundle kernels: 4 keys per thread
+constexpr int kDkTile = kDkThreads * 4;
+constexpr int kDsThreads = 1024;
+constexpr int kDsPer = 4;
+constexpr int kDsTile = kDsThreads * kDsPer;
+
+struct DirectLayout {
+    const uint64_t* off;       // [ns+1] read offsets
+    const uint32_t* ref_len;   // [ns]
+    const uint32_t* node_base; // [ns+1] first node id of sample k
+    const uint32_t* kbase;     // [ns+1] first histogram slot of sample k (regions padded to 32)
+    const uint32_t* item_off;  // [ns+1] first work item (sample part) of sample k
+    uint32_t ns, nlen, minlen, maxlen;
+};
+
+__device__ __forceinline__ uint32_t find_u32(const uint32_t* __restrict__ off, uint32_t n,
+                                             uint32_t i) {
+    uint32_t lo = 0, hi = n;  // invariant: off[lo] <= i < off[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (off[mid] <= i) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// ---- K2 direct: per-sample histogram of read keys -------------------------------------------
+// Work item = one part of one sample (parts balance the SMs when there are few samples).  The CTA
+// counts the part in shared memory and adds its non-zero counters to the sample's region of the
+// global histogram (coalesced reductions; the region must be zero on entry).  Validation (range,
+// length hints) rides along: bad reads are counted, never touch the histogram.
+__global__ void __launch_bounds__(kDhThreads, 1)
+k_direct_hist(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, DirectLayout dl,
+              uint32_t n_items, uint32_t* __restrict__ work_counter, uint32_t* __restrict__ ghist,
+              uint32_t kmax, uint32_t* __restrict__ stats) {
+    extern __shared__ uint32_t h[];
+    __shared__ uint32_t s_item;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = tid; i < kmax; i += kDhThreads) h[i] = 0;
+    uint32_t bad_range = 0, bad_hint = 0;
+    const uint32_t nlen = dl.nlen, minlen = dl.minlen, maxlen = dl.maxlen;
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= n_items) break;
+        const uint32_t k = find_u32(dl.item_off, dl.ns, item);
+        const uint32_t parts = dl.item_off[k + 1] - dl.item_off[k];
+        const uint32_t p = item - dl.item_off[k];
+        const uint64_t o0 = dl.off[k], o1 = dl.off[k + 1];
+        const uint64_t plen = (((o1 - o0) + parts - 1) / parts + 3) & ~3ull;
+        const uint64_t a = o0 + p * plen;
+        const uint64_t b = min(a + plen, o1);
+        const uint32_t L = dl.ref_len[k];
+        auto count = [&](uint32_t s, uint32_t e) {
+            if (s > e || e >= L) {
+                ++bad_range;
+                return;
+            }
+            const uint32_t len = e - s + 1;
+            if (len < minlen || len > maxlen) {
+                ++bad_hint;
+                return;
+            }
+            atomicAdd(&h[s * nlen + (len - minlen)], 1u);
+        };
+        if (a < b) {
+            // unaligned head and tail by single loads, the body by 16-byte loads
+            const uint64_t a4 = min((uint64_t)((a + 3) & ~3ull), b), b4 = max((uint64_t)(b & ~3ull), a4);
+            if (tid < a4 - a) count(S[a + tid], E[a + tid]);
+            if (tid < b - b4) count(S[b4 + tid], E[b4 + tid]);
+            const uint4* S4 = reinterpret_cast<const uint4*>(S);
+            const uint4* E4 = reinterpret_cast<const uint4*>(E);
+            for (uint64_t j = a4 / 4 + tid; j < b4 / 4; j += kDhThreads) {
+                const uint4 s = ld_stream4(S4 + j), e = ld_stream4(E4 + j);
+                count(s.x, e.x);
+                count(s.y, e.y);
+                count(s.z, e.z);
+                count(s.w, e.w);
+            }
+        }
+        __syncthreads();
+        uint32_t* gh = ghist + dl.kbase[k];
+        const uint32_t kk = dl.kbase[k + 1] - dl.kbase[k];
+        for (uint32_t i = tid; i < kk; i += kDhThreads) {
+            const uint32_t c = h[i];
+            if (c) {
+                atomicAdd(gh + i, c);
+                h[i] = 0;
+            }
+        }
+        __syncthreads();
+    }
+    bad_range = __reduce_add_sync(0xffffffffu, bad_range);
+    bad_hint = __reduce_add_sync(0xffffffffu, bad_hint);
+    if (lane_id() == 0) {
+        if (bad_range) atomicAdd(&stats[2], bad_range);
+        if (bad_hint) atomicAdd(&stats[3], bad_hint);
+    }
+}
+
+// ---- bundles = non-zero counters, in key order (sample, start, length) -------------------------
+__global__ void __launch_bounds__(kDkThreads)
+k_direct_count(const uint32_t* __restrict__ ghist, uint32_t ktot, uint32_t* __restrict__ tile_counts) {
+    const uint32_t i = (blockIdx.x * kDkThreads + threadIdx.x) * 4;
+    uint32_t c = 0;
+    if (i < ktot) {  // ktot is a multiple of 32
+        const uint4 v = reinterpret_cast<const uint4*>(ghist)[i / 4];
+        c = (v.x != 0) + (v.y != 0) + (v.z != 0) + (v.w != 0);
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    __shared__ uint32_t tot;
+    if (threadIdx.x == 0) tot = 0;
+    __syncthreads();
+    if (lane_id() == 0 && c) atomicAdd(&tot, c);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_counts[blockIdx.x] = tot;
+}
+
+// Writes what k_bundle_fill writes on the sort path (bundle record, in-CSR key, difference array,
+// CSR degrees) plus the bundle's histogram slot (K5 puts the bundle's flow there).
+__global__ void __launch_bounds__(kDkThreads)
+k_direct_bundles(const uint32_t* __restrict__ ghist, uint32_t ktot, DirectLayout dl,
+                 const uint32_t* __restrict__ tile_offs, BundleRec* __restrict__ bund,
+                 uint32_t* __restrict__ b_t, uint32_t* __restrict__ b_slot,
+                 uint32_t* __restrict__ in_bid /* identity when nlen == 1, else null */,
+                 int32_t* __restrict__ diff, uint32_t* __restrict__ outdeg,
+                 uint32_t* __restrict__ indeg) {
+    __shared__ uint32_t total;
+    const uint32_t i = (blockIdx.x * kDkThreads + threadIdx.x) * 4;
+    uint32_t v[4] = {0, 0, 0, 0};
+    if (i < ktot) {
+        const uint4 q = reinterpret_cast<const uint4*>(ghist)[i / 4];
+        v[0] = q.x;
+        v[1] = q.y;
+        v[2] = q.z;
+        v[3] = q.w;
+    }
+    const uint32_t c = (v[0] != 0) + (v[1] != 0) + (v[2] != 0) + (v[3] != 0);
+    uint32_t b = block_excl_scan(c, &total) + tile_offs[blockIdx.x];
+    if (c == 0) return;
+    const uint32_t k = find_u32(dl.kbase, dl.ns, i);  // regions are 32-aligned: same k for all 4
+    const uint32_t local = i - dl.kbase[k];
+    const uint32_t nb = dl.node_base[k];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (!v[q]) continue;
+        const uint32_t key = local + q;
+        const uint32_t s = nb + key / dl.nlen;
+        const uint32_t t = s + dl.minlen + key % dl.nlen;
+        const uint32_t mult = v[q];
+        reinterpret_cast<uint4*>(bund)[b] = make_uint4(t, mult, 0u, s);
+        b_t[b] = t;
+        b_slot[b] = i + q;
+        if (in_bid) in_bid[b] = b;
+        atomicAdd(&diff[s], (int32_t)mult);
+        atomicAdd(&diff[t], -(int32_t)mult);
+        atomicAdd(&outdeg[s], 1u);
+        atomicAdd(&indeg[t], 1u);
+        ++b;
+    }
+}
+
+// ---- K5 direct ---------------------------------------------------------------------------------
+// after K3: the histogram slot of every bundle receives the bundle's flow (its quota)
+__global__ void __launch_bounds__(256)
+k_direct_quota(const BundleRec* __restrict__ bund, const uint32_t* __restrict__ b_slot, uint32_t B,
+               uint32_t* __restrict__ ghist) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) ghist[b_slot[b]] = bund[b].f;
+}
+
+__global__ void __launch_bounds__(kDsThreads, 1)
+k_direct_select(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, DirectLayout dl,
+                uint32_t* __restrict__ work_counter, const uint32_t* __restrict__ ghist,
+                uint32_t* __restrict__ bitmap, unsigned long long* __restrict__ totals) {
+    extern __shared__ uint32_t quota[];  // per key: flow still to be handed out (as int32)
+    __shared__ uint32_t c_key[kDsTile];
+    __shared__ uint16_t c_pos[kDsTile];
+    __shared__ uint32_t s_k, s_nconf, s_remaining;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t nlen = dl.nlen, minlen = dl.minlen;
+    constexpr uint32_t kNone = 0xffffffffu;
+    for (;;) {
+        if (tid == 0) {
+            s_k = atomicAdd(work_counter, 1u);
+            s_remaining = 0;
+        }
+        __syncthreads();
+        const uint32_t k = s_k;
+        if (k >= dl.ns) break;
+        const uint64_t base = dl.off[k];
+        const uint64_t n_k = dl.off[k + 1] - base;
+        const uint32_t kk = dl.kbase[k + 1] - dl.kbase[k];
+        const uint32_t* gq = ghist + dl.kbase[k];
+        uint32_t want = 0;
+        for (uint32_t i = tid; i < kk; i += kDsThreads) {
+            const uint32_t f = gq[i];
+            quota[i] = f;
+            want += f;
+        }
+        want = __reduce_add_sync(0xffffffffu, want);
+        if (lane_id() == 0 && want) atomicAdd(&s_remaining, want);
+        __syncthreads();
+        const uint32_t total = s_remaining;
+        if (total != 0) {
+            const uint32_t n_tiles = (uint32_t)((n_k + kDsTile - 1) / kDsTile);
+            uint32_t ns_[kDsPer], ne_[kDsPer];
+            auto fetch = [&](uint32_t t) {
+#pragma unroll
+                for (int q = 0; q < kDsPer; ++q) {
+                    const uint64_t idx = (uint64_t)t * kDsTile + q * kDsThreads + tid;
+                    const bool in = idx < n_k;
+                    ns_[q] = in ? ld_stream(S + base + idx) : kNone;
+                    ne_[q] = (in && nlen > 1) ? ld_stream(E + base + idx) : 0u;
+                }
+            };
+            fetch(0);
+            for (uint32_t t = 0; t < n_tiles; ++t) {
+                uint32_t key[kDsPer];
+                bool cand[kDsPer];
+                bool any = false;
+#pragma unroll
+                for (int q = 0; q < kDsPer; ++q) {
+                    key[q] = kNone;
+                    if (ns_[q] != kNone) {
+                        const uint32_t kq = nlen > 1 ? ns_[q] * nlen + (ne_[q] - ns_[q] + 1 - minlen)
+                                                     : ns_[q];
+                        if (kq < kk) key[q] = kq;
+                    }
+                    cand[q] = key[q] != kNone && (int32_t)quota[key[q]] > 0;
+                    any |= cand[q];
+                }
+                if (t + 1 < n_tiles) fetch(t + 1);  // in flight while this tile is resolved
+                if (!__syncthreads_or(any)) continue;
+                if (tid == 0) s_nconf = 0;
+#pragma unroll
+                for (int q = 0; q < kDsPer; ++q)
+                    if (cand[q]) atomicSub(&quota[key[q]], 1u);
+                __syncthreads();
+                uint32_t kept = 0;
+                const uint64_t tile0 = base + (uint64_t)t * kDsTile;
+#pragma unroll
+                for (int q = 0; q < kDsPer; ++q) {
+                    if (!cand[q]) continue;
+                    const uint32_t pos = q * kDsThreads + tid;
+                    if ((int32_t)quota[key[q]] >= 0) {  // the tile did not exhaust the key
+                        const uint64_t g = tile0 + pos;
+                        atomicOr(&bitmap[g >> 5], 1u << (g & 31));
+                        ++kept;
+                    } else {
+                        const uint32_t slot = atomicAdd(&s_nconf, 1u);
+                        c_key[slot] = key[q];
+                        c_pos[slot] = (uint16_t)pos;
+                    }
+                }
+                __syncthreads();
+                const uint32_t nconf = s_nconf;
+                if (nconf) {
+                    // more candidates than quota: the lowest-index ones win (each key gets here
+                    // at most once, its quota is zero afterwards)
+                    for (uint32_t e = tid; e < nconf; e += kDsThreads) {
+                        const uint32_t ck = c_key[e];
+                        const uint32_t cp = c_pos[e];
+                        uint32_t rank = 0, cnt = 0;
+                        for (uint32_t j = 0; j < nconf; ++j) {
+                            const bool same = c_key[j] == ck;
+                            cnt += same;
+                            rank += same && c_pos[j] < cp;
+                        }
+                        const int32_t q0 = (int32_t)quota[ck] + (int32_t)cnt;
+                        if ((int32_t)rank < q0) {
+                            const uint64_t g = tile0 + cp;
+                            atomicOr(&bitmap[g >> 5], 1u << (g & 31));
+                            ++kept;
+                        }
+                    }
+                    __syncthreads();
+                    for (uint32_t e = tid; e < nconf; e += kDsThreads) quota[c_key[e]] = 0;
+                }
+                kept = __reduce_add_sync(0xffffffffu, kept);
+                if (lane_id() == 0 && kept) atomicSub(&s_remaining, kept);
+                __syncthreads();
+                if (s_remaining == 0) break;
+            }
+            if (tid == 0) atomicAdd(&totals[1], (unsigned long long)(total - s_remaining));
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace gds

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "direct.cuh"
 #include "graph.cuh"
 #include "maxflow.cuh"
 #include "prep.cuh"
@@ -47,6 +48,8 @@ struct gds_ctx {
     DevBuf qF, qT, qN, qH, work_counter, comp_stats;
     DevBuf bitmap, cov_tmp, dem_tmp, vdiff, vexcl;
     DevBuf vs_d, cross_idx, cross_tc, odiff, oexcl, cut_nodes, tile_off_d, head_bits;
+    DevBuf dhist, dlay, b_slot, ident, dwork;  // direct (sort-free) bundle path
+    unsigned direct_attr = 0;                  // bytes of dynamic smem the direct kernels are set up for
     unsigned mf_attr_set = 0;  // bit i: smem attribute set for launch shape i
     bool atomic_rank = false;  // shared-memory atomics rank in lane order on this device (probed)
     Profiler prof;
@@ -59,7 +62,8 @@ struct gds_ctx {
                          &outdeg, &indeg, &excl, &tkA, &tkB, &tvA, &tvB, &node_rec, &n_dsnap, &comp_start, &comp_end, &comp_sidx,
                          &comp_eidx, &comp_lo, &comp_hi, &qF, &qT, &qN, &qH, &work_counter, &comp_stats,
                          &bitmap, &cov_tmp, &dem_tmp, &vdiff, &vexcl, &vs_d, &cross_idx, &cross_tc,
-                         &odiff, &oexcl, &cut_nodes, &tile_off_d, &head_bits};
+                         &odiff, &oexcl, &cut_nodes, &tile_off_d, &head_bits, &dhist, &dlay, &b_slot,
+                         &ident, &dwork};
         for (DevBuf* b : all) b->release();
     }
 };
@@ -214,6 +218,122 @@ void build_bundles(gds_ctx* c, const uint32_t* S, const uint32_t* E, const VLayo
                                                          odiff);
         GDS_KERNEL_CHECK();
     }
+}
+
+// Sort-free K2 (direct.cuh).  Eligible when no sample is segmented and every sample's key space
+// (ref_len x number of distinct read lengths) fits in one SM's shared memory.
+struct DirectPlan {
+    bool on = false;
+    DirectLayout dl{};
+    uint32_t* ghist = nullptr;
+    uint32_t ktot = 0, kmax = 0;
+    uint32_t* in_bid = nullptr;  // identity in-CSR (single read length), else null
+};
+
+bool direct_eligible(const gds_reads* rd, uint32_t ns, uint32_t minlen, uint32_t maxlen,
+                     const uint32_t* S, const uint32_t* E) {
+    if (((uintptr_t)S | (uintptr_t)E) & 15) return false;  // 16-byte loads
+    const uint64_t nlen = (uint64_t)maxlen - minlen + 1;
+    uint64_t tot = 0;
+    for (uint32_t k = 0; k < ns; ++k) {
+        const uint64_t kk = (uint64_t)rd->ref_len[k] * nlen;
+        if (kk > kDirectMaxKeys) return false;
+        tot += (kk + 31) & ~31ull;
+    }
+    return tot < (1ull << 31);
+}
+
+void build_bundles_direct(gds_ctx* c, const gds_reads* rd, const uint32_t* S, const uint32_t* E,
+                          const uint64_t* foff_dev, const std::vector<uint64_t>& foff_host,
+                          const uint32_t* reflen_d, const uint32_t* base_d, uint32_t ns, size_t N,
+                          uint32_t n_nodes, uint32_t minlen, uint32_t maxlen, uint32_t* stats,
+                          DirectPlan& plan, uint32_t& B_out) {
+    cudaStream_t st = c->stream;
+    const uint32_t nlen = maxlen - minlen + 1;
+    // host-side layout: histogram regions and work items (sample parts)
+    std::vector<uint32_t> lay(2 * (ns + 1), 0);
+    uint32_t* kbase = lay.data();
+    uint32_t* item_off = lay.data() + ns + 1;
+    const uint64_t part_len = std::max<uint64_t>(65536, (N + 8ull * kNumSMs - 1) / (8ull * kNumSMs));
+    uint32_t kmax = 32;
+    for (uint32_t k = 0; k < ns; ++k) {
+        const uint32_t kk = (rd->ref_len[k] * nlen + 31u) & ~31u;
+        kmax = std::max(kmax, kk);
+        kbase[k + 1] = kbase[k] + kk;
+        const uint64_t nk = foff_host[k + 1] - foff_host[k];
+        item_off[k + 1] = item_off[k] + (uint32_t)((nk + part_len - 1) / part_len);
+    }
+    const uint32_t ktot = kbase[ns], n_items = item_off[ns];
+    uint32_t* lay_d = c->dlay.get<uint32_t>(lay.size());
+    GDS_CUDA(cudaMemcpy(lay_d, lay.data(), lay.size() * 4, cudaMemcpyHostToDevice));
+    uint32_t* ghist = c->dhist.get<uint32_t>(ktot);
+    uint32_t* wc = c->dwork.get<uint32_t>(2);
+    GDS_CUDA(cudaMemsetAsync(ghist, 0, (size_t)ktot * 4, st));
+    GDS_CUDA(cudaMemsetAsync(wc, 0, 8, st));
+    DirectLayout dl{foff_dev, reflen_d, base_d, lay_d, lay_d + ns + 1, ns, nlen, minlen, maxlen};
+    const unsigned smem = kmax * 4;
+    if (smem > c->direct_attr) {
+        GDS_CUDA(cudaFuncSetAttribute(k_direct_hist, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(kDirectMaxKeys * 4)));
+        GDS_CUDA(cudaFuncSetAttribute(k_direct_select, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(kDirectMaxKeys * 4)));
+        c->direct_attr = kDirectMaxKeys * 4;
+    }
+    {
+        KScope ks("direct_hist", 8ull * N + 4ull * ktot, st);
+        const int grid = (int)std::min<uint32_t>(n_items, (uint32_t)kNumSMs);
+        k_direct_hist<<<grid, kDhThreads, smem, st>>>(S, E, dl, n_items, wc, ghist, kmax, stats);
+        GDS_KERNEL_CHECK();
+    }
+    const uint32_t n_tiles = (uint32_t)div_up(ktot, kDkTile);
+    uint32_t* tc = c->tile_counts.get<uint32_t>(n_tiles + 1);
+    GDS_CUDA(cudaMemsetAsync(tc + n_tiles, 0, sizeof(uint32_t), st));
+    {
+        KScope ks("direct_count", 4ull * ktot, st);
+        k_direct_count<<<n_tiles, kDkThreads, 0, st>>>(ghist, ktot, tc);
+        GDS_KERNEL_CHECK();
+    }
+    exclusive_scan_u32(tc, tc, n_tiles + 1, c->scan, st);
+    uint32_t B = 0;
+    d2h_sync(c, &B, tc + n_tiles, 1);
+    B_out = B;
+    {
+        uint32_t hs[4];
+        d2h_sync(c, hs, stats, 4);
+        if (hs[2]) throw InputFail{GDS_ERR_RANGE, hs[2], "reads with start > end or end >= ref_len"};
+        if (hs[3]) throw InputFail{GDS_ERR_ARG, hs[3], "reads outside the len_min/len_max hints"};
+    }
+    BundleRec* bund = c->bund.get<BundleRec>(B + 1);
+    uint32_t* b_t = c->b_t.get<uint32_t>(B + 1);
+    uint32_t* b_slot = c->b_slot.get<uint32_t>(B + 1);
+    uint32_t* ident = nlen == 1 ? c->ident.get<uint32_t>(B + 1) : nullptr;
+    int32_t* diff = c->diff.get<int32_t>(n_nodes + 1);
+    uint32_t* outdeg = c->outdeg.get<uint32_t>(n_nodes + 1);
+    uint32_t* indeg = c->indeg.get<uint32_t>(n_nodes + 1);
+    GDS_CUDA(cudaMemsetAsync(diff, 0, (n_nodes + 1) * sizeof(int32_t), st));
+    GDS_CUDA(cudaMemsetAsync(outdeg, 0, (n_nodes + 1) * sizeof(uint32_t), st));
+    GDS_CUDA(cudaMemsetAsync(indeg, 0, (n_nodes + 1) * sizeof(uint32_t), st));
+    if (B) {
+        KScope ks("direct_bundles", 4ull * ktot + 40ull * B, st);
+        k_direct_bundles<<<n_tiles, kDkThreads, 0, st>>>(ghist, ktot, dl, tc, bund, b_t, b_slot,
+                                                        ident, diff, outdeg, indeg);
+        GDS_KERNEL_CHECK();
+    }
+    plan.on = true;
+    plan.dl = dl;
+    plan.ghist = ghist;
+    plan.ktot = ktot;
+    plan.kmax = kmax;
+    plan.in_bid = ident;
+}
+
+// 0 = choose, 1 = always the radix sort, 2 = the direct histogram whenever eligible
+int bundle_mode(const gds_params* prm) {
+    if (const char* e = getenv("GDS_BUNDLE")) {
+        if (!strcmp(e, "sort")) return 1;
+        if (!strcmp(e, "direct")) return 2;
+    }
+    return prm ? (int)prm->bundle_mode : 0;
 }
 
 }  // namespace
@@ -597,7 +717,13 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
                 return fail(c, GDS_ERR_RANGE, "more than 2^32 arc items after segmentation");
         }
         out->n_arc_items = n_items;
-        if (N > 0) {
+        DirectPlan direct;
+        const int bmode = bundle_mode(prm);
+        if (N > 0 && !split && bmode != 1 && direct_eligible(rd, ns, minlen, maxlen, S, E)) {
+            build_bundles_direct(c, rd, S, E, foff_dev, foff_host, reflen_d, base_d, ns, N, n_nodes,
+                                 minlen, maxlen, stats, direct, B);
+            out->key_bits = bits_for(direct.kmax - 1);
+        } else if (N > 0) {
             // the arc sort is segmented by sample unless some sample is cut into segments (then the
             // right parts live after all reads and one group with global keys is sorted)
             const bool local_keys = !split;
@@ -723,8 +849,8 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             }
         }
         // in-CSR: bundle ids ordered by (end node, bundle id) = stable sort of ids by b_t
-        uint32_t* in_bid = nullptr;
-        if (B) {
+        uint32_t* in_bid = direct.in_bid;  // single read length: bundle order is end order too
+        if (B && !in_bid) {
             uint32_t* tkA = c->tkA.get<uint32_t>(B);
             uint32_t* tkB = c->tkB.get<uint32_t>(B);
             uint32_t* tvA = c->tvA.get<uint32_t>(B);
@@ -766,7 +892,24 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
                                                      : c->bitmap.get<uint32_t>(n_words + 1);
         if (do_solve) {
             GDS_CUDA(cudaMemsetAsync(bm, 0, n_words * 4, st));
-            if (B) {
+            if (B && direct.on) {
+                {
+                    KScope ks("direct_quota", 24ull * B, st);
+                    k_direct_quota<<<div_up(B, 256), 256, 0, st>>>(c->bund.as<BundleRec>(),
+                                                                   c->b_slot.as<uint32_t>(), B,
+                                                                   direct.ghist);
+                    GDS_KERNEL_CHECK();
+                }
+                {
+                    // bytes: the quotas once; how far the ordered walk reads is data dependent
+                    KScope ks("direct_select", 4ull * direct.ktot + 8ull * N / 32, st);
+                    uint32_t* wc = c->dwork.as<uint32_t>() + 1;
+                    const int grid = (int)std::min<uint32_t>(ns, (uint32_t)kNumSMs);
+                    k_direct_select<<<grid, kDsThreads, direct.kmax * 4, st>>>(
+                        S, E, direct.dl, wc, direct.ghist, bm, totals);
+                    GDS_KERNEL_CHECK();
+                }
+            } else if (B) {
                 {
                     KScope ks("select", 8ull * B + 8ull * N / 32, st);
                     k_select<<<div_up(B, 256), 256, 0, st>>>(c->b_first.as<uint32_t>(),

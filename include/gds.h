@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GDS_ABI_VERSION 4
+#define GDS_ABI_VERSION 5
 
 /* status codes (the reference has none: it logs and exits, cuda_helpers.cuh:13-21) */
 enum {
@@ -80,7 +80,7 @@ typedef struct {
 } gds_filter;
 
 /* Deterministic schedule knobs.  Zero-initialised = defaults (64, 150, 1, 0) and
- * seg_len 32768.  seg_len: references longer than this many positions are cut into independent
+ * seg_len 32768, bundle_mode 0.  seg_len: references longer than this many positions are cut into independent
  * segments (reads crossing a cut are truncated into one arc per segment and kept if either part
  * carries flow) — the zero-coverage split generalised; 0xffffffff = never cut. */
 typedef struct {
@@ -89,6 +89,12 @@ typedef struct {
     uint32_t gr_relabel_pct;
     uint32_t max_rounds;
     uint32_t seg_len;
+    /* how K2 finds the bundles (reads with one (start, length) key): 0 = choose, 1 = always the
+     * segmented radix sort, 2 = the sort-free shared-memory histogram whenever it is eligible (no
+     * sample segmented, ref_len x #read-lengths <= 49152 per sample, 16-byte aligned start/end).
+     * Both give the same graph and the same kept set; gds_result.sort_passes == 0 tells that the
+     * histogram ran.  The environment variable GDS_BUNDLE=sort|direct overrides (benchmarks). */
+    uint32_t bundle_mode;
 } gds_params;
 
 /* Results.  Buffers are caller-owned and optional (NULL = not wanted). */

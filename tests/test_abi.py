@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(pkg):
     lib = ctypes.CDLL(pkg.lib_path())
     for fn in declared_functions():
         assert hasattr(lib, fn), "libgds_b200.so does not export %s" % fn
-    assert lib.gds_abi_version() == 4
+    assert lib.gds_abi_version() == 5
     assert sorted(pkg.exported_symbols()) == declared_functions()
 
 

@@ -57,8 +57,12 @@ def test_fuzz_ragged_batches(solver, O):
         seg = int(rng.integers(1, 120)) if it % 3 == 0 else 0
         prm = (int(rng.integers(1, 100)), int(rng.integers(0, 300)), int(rng.integers(0, 5)), 0, seg)
         off = np.array(off, np.uint64)
-        r = solver.solve(s, e, Ls, M, read_off=off, params=prm, verify=True, want_vectors=True)
-        assert_parity(O, r, s, e, Ls, off, M, prm)
+        # both ways of finding the bundles (gds_params.bundle_mode: radix sort / direct histogram)
+        for bmode in (1, 2):
+            r = solver.solve(s, e, Ls, M, read_off=off, params=prm + (bmode,), verify=True,
+                             want_vectors=True)
+            assert_parity(O, r, s, e, Ls, off, M, prm)
+            assert bmode == 2 or r.sort_passes > 0 or len(s) == 0
 
 
 def test_segmented_reference_matches_oracle_and_unsplit_invariants(solver, O):
@@ -321,3 +325,62 @@ def test_length_hints_fold_validation_into_the_sort(pkg, solver, O):
         solver.solve(s, bad, [30_000] * 3, 30, read_off=off, len_hint=(150, 151))
     assert ei.value.code == 2  # GDS_ERR_RANGE
     assert solver.solve(s, e, [30_000] * 3, 30, read_off=off, params=PRM).n_kept == r0.n_kept
+
+
+def test_direct_histogram_path_equals_sort_path(solver, O):
+    # gds_params.bundle_mode: 30 kb samples with one read length take the sort-free histogram by
+    # default (sort_passes == 0); forcing the radix sort must give the same graph and kept set
+    parts = [O.gen_reads(4242 + k, 150_000 + 7 * k, 30_000, 150, sh)
+             for k, sh in enumerate(["uniform", "hole", "low_sides"])]
+    s = np.concatenate([p[0] for p in parts]); e = np.concatenate([p[1] for p in parts])
+    off = np.cumsum([0] + [len(p[0]) for p in parts]).astype(np.uint64)
+    res = {}
+    for bmode in (0, 1, 2):
+        res[bmode] = solver.solve(s, e, [30_000] * 3, 300, read_off=off, params=PRM + (0, bmode),
+                                  verify=True, want_vectors=True)
+    assert res[0].sort_passes == 0 and res[2].sort_passes == 0 and res[1].sort_passes > 0
+    for bmode in (0, 2):
+        for key in ("fstar", "flow_value", "n_bundles", "n_components", "n_kept", "rounds_total",
+                    "pushes", "relabels", "bfs_levels"):
+            assert res[bmode][key] == res[1][key], key
+        assert np.array_equal(res[bmode].kept_bitmap, res[1].kept_bitmap)
+        assert np.array_equal(res[bmode].demand, res[1].demand)
+        assert np.array_equal(res[bmode].cov_capped, res[1].cov_capped)
+    assert_parity(O, res[0], s, e, [30_000] * 3, off, 300)
+    # a few read lengths (key = start x #lengths + length) still fit in shared memory
+    rng = np.random.default_rng(11)
+    s2 = rng.integers(0, 9_000, size=400_000).astype(np.uint32)
+    e2 = (s2 + rng.integers(148, 152, size=400_000)).astype(np.uint32)
+    ra = solver.solve(s2, e2, 9_200, 200, params=PRM + (0, 2), verify=True, want_vectors=True)
+    rb = solver.solve(s2, e2, 9_200, 200, params=PRM + (0, 1), verify=True, want_vectors=True)
+    assert ra.sort_passes == 0 and rb.sort_passes > 0
+    assert np.array_equal(ra.kept_bitmap, rb.kept_bitmap) and ra.rounds_total == rb.rounds_total
+    assert_parity(O, ra, s2, e2, [9_200], [0, len(s2)], 200)
+    # a key space beyond shared memory falls back to the sort even when the histogram is asked for
+    e3 = (s2 + rng.integers(100, 300, size=400_000)).astype(np.uint32)
+    rc = solver.solve(s2, e3, 9_400, 50, params=PRM + (0, 2), verify=True)
+    assert rc.sort_passes > 0 and rc.verify_violations == 0
+
+
+def test_direct_selection_walk_many_tiles_and_duplicates(solver, O):
+    # the ordered walk of K5 (direct path): tiny key spaces so that every 4096-read tile holds many
+    # reads of one key, quotas that run out in the middle of a tile or span several tiles, ragged
+    # sample offsets (unaligned 16-byte loads at part boundaries)
+    rng = np.random.default_rng(23)
+    for it in range(40):
+        ns = int(rng.integers(1, 4))
+        Ls = rng.integers(2, 60, size=ns).astype(np.uint32)
+        ss, ee, off = [], [], [0]
+        for L in Ls:
+            n = int(rng.integers(0, 30_000))
+            nl = int(rng.integers(1, 4))
+            s = rng.integers(0, L, size=n)
+            e = np.minimum(s + rng.integers(1, 1 + nl, size=n) * int(rng.integers(1, 8)) - 1, L - 1)
+            ss.append(s); ee.append(e); off.append(off[-1] + n)
+        s = np.concatenate(ss).astype(np.uint32); e = np.concatenate(ee).astype(np.uint32)
+        M = int(rng.choice([1, 3, 50, 700, 5000, 20000]))
+        off = np.array(off, np.uint64)
+        r = solver.solve(s, e, Ls, M, read_off=off, params=PRM + (0, 2), verify=True,
+                         want_vectors=True)
+        assert r.sort_passes == 0 or len(s) == 0
+        assert_parity(O, r, s, e, Ls, off, M)
