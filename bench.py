@@ -550,6 +550,9 @@ def run_b200(args, wl, wname):
                    "n_components": int(r_last.n_components), "rounds_total": int(r_last.rounds_total),
                    "rounds_max": int(r_last.rounds_max), "bfs_levels": int(r_last.bfs_levels),
                    "sort_passes": int(r_last.sort_passes),
+                   "bundle_path": "direct histogram" if int(r_last.sort_passes) == 0 else "radix sort",
+                   "partial_bundles": int(r_last.partial_bundles),
+                   "partial_candidates": int(r_last.partial_candidates),
                    # K3 is latency-bound, not HBM-bound: its own figures (SURVEY §8d iii)
                    "k3": {"pushes": int(r_last.pushes), "relabels": int(r_last.relabels),
                           "global_relabels": int(r_last.global_relabels),

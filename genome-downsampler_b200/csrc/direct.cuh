@@ -10,13 +10,7 @@
 // (quasi_mcp_cpu_max_flow_solver.cpp:30-87 on bundles) — bundle order, node ids, difference array
 // and CSR are identical, so K3 and every parity test see the same graph.
 //
-// K5 without a sorted read order: "a bundle with flow f keeps its f lowest-index reads"
-// (select.cuh) becomes an ordered walk.  One CTA per sample holds the per-key quota (= f) in
-// shared memory and walks the reads in index order, tile by tile; a read whose key still has
-// quota is a candidate.  If a tile holds no more candidates of a key than its quota they are all
-// kept (order irrelevant); otherwise (each key at most once) the candidates of that key are
-// ranked by index.  The walk stops when every quota is used up — on uniform data after ~15-20 %
-// of the sample.
+// K5 without a sorted read order: see the K5 section below.
 #pragma once
 #include "common.cuh"
 #include "graph.cuh"
@@ -27,6 +21,7 @@ namespace gds {
 
 constexpr uint32_t kDirectMaxKeys = 48 * 1024;  // u32 counters: 192 KB of shared memory
 constexpr int kDhThreads = 1024;
+constexpr int kDirectUnroll = 4;  // 16-byte loads per array in flight per thread
 constexpr int kDkThreads = 256;   // key tiles of the bundle kernels: 4 keys per thread
 constexpr int kDkTile = kDkThreads * 4;
 constexpr int kDsThreads = 1024;
@@ -100,7 +95,26 @@ k_direct_hist(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, Di
             if (tid < b - b4) count(S[b4 + tid], E[b4 + tid]);
             const uint4* S4 = reinterpret_cast<const uint4*>(S);
             const uint4* E4 = reinterpret_cast<const uint4*>(E);
-            for (uint64_t j = a4 / 4 + tid; j < b4 / 4; j += kDhThreads) {
+            uint64_t j = a4 / 4 + tid;
+            const uint64_t jend = b4 / 4;
+            // all loads of a round are issued before the first atomic (8 x 16 B in flight per
+            // thread: the kernel is bound by bytes in flight per SM, not by the atomics)
+            for (; j + (kDirectUnroll - 1) * kDhThreads < jend; j += kDirectUnroll * kDhThreads) {
+                uint4 s[kDirectUnroll], e[kDirectUnroll];
+#pragma unroll
+                for (int u = 0; u < kDirectUnroll; ++u) {
+                    s[u] = ld_stream4(S4 + j + u * kDhThreads);
+                    e[u] = ld_stream4(E4 + j + u * kDhThreads);
+                }
+#pragma unroll
+                for (int u = 0; u < kDirectUnroll; ++u) {
+                    count(s[u].x, e[u].x);
+                    count(s[u].y, e[u].y);
+                    count(s[u].z, e[u].z);
+                    count(s[u].w, e[u].w);
+                }
+            }
+            for (; j < jend; j += kDhThreads) {
                 const uint4 s = ld_stream4(S4 + j), e = ld_stream4(E4 + j);
                 count(s.x, e.x);
                 count(s.y, e.y);
@@ -191,7 +205,266 @@ k_direct_bundles(const uint32_t* __restrict__ ghist, uint32_t ktot, DirectLayout
 }
 
 // ---- K5 direct ---------------------------------------------------------------------------------
-// after K3: the histogram slot of every bundle receives the bundle's flow (its quota)
+// "A bundle with flow f keeps its f lowest-index reads" (select.cuh) without a sorted read order.
+// Push-relabel saturates most bundles it uses, so after K3 a key is in one of three states:
+//   f == 0        none of its reads is kept                                       (code 0)
+//   f == mult     all of its reads are kept — no order needed                     (code 1)
+//   0 < f < mult  "partial": the f lowest of its mult read indices are kept       (code 2)
+// k_direct_classify writes the 2-bit code of every key (16 per word; a 30 kb sample's table is
+// 7.5 KB) and gives every partial bundle a segment of mult slots in a candidate buffer.
+// k_direct_mark streams the reads once more (start only when there is one read length), in
+// parallel parts like the histogram: code 1 sets the kept bit, code 2 appends the read index to
+// the bundle's segment.  k_direct_partial then ranks each partial bundle's candidates (one warp per
+// bundle).  If the candidates do not fit the buffer or a partial bundle is huge (adversarial
+// input: millions of identical reads), ctl[2] is raised and the host runs the ordered walk below
+// instead — same kept set, one CTA per sample.
+constexpr uint32_t kSatCode = 1, kPartCode = 2;
+constexpr uint32_t kMaxPartialMult = 2048;  // candidates of one bundle ranked by one warp
+constexpr int kDmThreads = 1024;
+
+// ctl: [0] number of partial bundles, [1] candidate slots handed out, [2] fallback flag
+__global__ void __launch_bounds__(256)
+k_direct_classify(const BundleRec* __restrict__ bund, const uint32_t* __restrict__ b_slot, uint32_t B,
+                  uint32_t* __restrict__ ghist, uint32_t* __restrict__ kstat,
+                  uint32_t* __restrict__ pb_off, uint32_t* __restrict__ pb_f,
+                  uint32_t* __restrict__ pb_fill, uint32_t* __restrict__ ctl, uint32_t cand_cap) {
+    __shared__ uint32_t tot_n, tot_m, base_n, base_m;
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t mult = 0, f = 0;
+    if (b < B) {
+        const uint4 r = reinterpret_cast<const uint4*>(bund)[b];  // {t, mult, f, s}
+        mult = r.y;
+        f = r.z;
+    }
+    const bool partial = f != 0 && f < mult;
+    // one pair of global atomics per block hands out bundle ids and candidate segments
+    const uint32_t my_n = block_excl_scan(partial ? 1u : 0u, &tot_n);
+    const uint32_t my_m = block_excl_scan(partial ? mult : 0u, &tot_m);
+    if (threadIdx.x == 0 && tot_n) {
+        base_n = atomicAdd(&ctl[0], tot_n);
+        base_m = atomicAdd(&ctl[1], tot_m);
+    }
+    __syncthreads();
+    if (f == 0) return;
+    const uint32_t slot = b_slot[b];
+    uint32_t code = kSatCode;
+    if (partial) {
+        code = kPartCode;
+        const uint32_t pid = base_n + my_n;
+        const uint32_t o = base_m + my_m;
+        if (mult > kMaxPartialMult || (unsigned long long)o + mult > cand_cap) ctl[2] = 1;
+        pb_off[pid] = o;
+        pb_f[pid] = f;
+        pb_fill[pid] = 0;
+        ghist[slot] = pid;
+    }
+    atomicOr(&kstat[slot >> 4], code << (2 * (slot & 15)));
+}
+
+// Reads of partial bundles are rare (~2 %) but each costs a chain of dependent global accesses
+// (bundle id -> segment -> atomic slot -> store).  Taken inline that chain stalls the warp once per
+// hit; instead every warp parks its hits (key, read index) in its own shared-memory queue and
+// drains the queue 32 entries at a time when it is nearly full and at the end of the part.
+// The kernel was issue-bound in its first version (ncu: 43 instructions per read, 62 % issue
+// slots busy): the codes are expanded to one BYTE per key in shared memory (one LDS per read),
+// indices are 32-bit offsets from the part start, and nothing is re-validated (K2 already failed
+// the call on any bad read).
+constexpr int kDmUnroll = 4;                                    // 512 reads per warp and round
+constexpr uint32_t kDmQueue = 640;                              // entries per warp
+constexpr uint32_t kDmQueueBytes = (kDmThreads / 32) * kDmQueue * 8;
+
+template <bool ONE_LEN>
+__global__ void __launch_bounds__(kDmThreads, 1)
+k_direct_mark(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, DirectLayout dl,
+              uint32_t n_items, uint32_t* __restrict__ work_counter,
+              const uint32_t* __restrict__ ghist, const uint32_t* __restrict__ kstat,
+              const uint32_t* __restrict__ pb_off, uint32_t* __restrict__ pb_fill,
+              uint32_t* __restrict__ cand, const uint32_t* __restrict__ ctl,
+              uint32_t* __restrict__ bitmap, unsigned long long* __restrict__ totals) {
+    extern __shared__ __align__(16) uint32_t dm_smem[];
+    uint2* wq = reinterpret_cast<uint2*>(dm_smem) + (threadIdx.x >> 5) * kDmQueue;  // this warp's queue
+    uint32_t* st32 = dm_smem + kDmQueueBytes / 4;
+    const uint8_t* st = reinterpret_cast<const uint8_t*>(st32);  // code of every key of the sample
+    __shared__ uint32_t s_item;
+    __shared__ uint32_t wcnt[kDmThreads / 32];
+    if (ctl[2]) return;
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t nlen = dl.nlen, minlen = dl.minlen;
+    uint32_t kept = 0;
+    if (lane == 0) wcnt[warp] = 0;
+    __syncwarp();
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= n_items) break;
+        const uint32_t k = find_u32(dl.item_off, dl.ns, item);
+        const uint32_t parts = dl.item_off[k + 1] - dl.item_off[k];
+        const uint32_t p = item - dl.item_off[k];
+        const uint64_t o0 = dl.off[k], o1 = dl.off[k + 1];
+        const uint64_t plen = (((o1 - o0) + parts - 1) / parts + 3) & ~3ull;
+        const uint64_t a = o0 + p * plen;
+        const uint64_t b = min(a + plen, o1);
+        const uint32_t kb = dl.kbase[k];
+        const uint32_t kk = dl.kbase[k + 1] - kb;
+        for (uint32_t i = tid; i < (kk >> 4); i += kDmThreads) {  // 16 two-bit codes -> 16 bytes
+            const uint32_t w = kstat[(kb >> 4) + i];
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t x = w >> (8 * q);
+                o[q] = (x & 3u) | ((x & 12u) << 6) | ((x & 48u) << 12) | ((x & 192u) << 18);
+            }
+            reinterpret_cast<uint4*>(st32)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        __syncthreads();
+        auto key_of = [&](uint32_t s, uint32_t e) {
+            const uint32_t key = ONE_LEN ? s : s * nlen + (e - s + 1 - minlen);
+            return min(key, kk - 1);  // in range on validated input; never read past the table
+        };
+        // converged warp: hand the parked reads to their bundles' candidate segments
+        auto drain = [&](uint32_t min_pending) {
+            __syncwarp();
+            const uint32_t n = wcnt[warp];
+            if (n <= min_pending) return;
+            for (uint32_t i = lane; i < n; i += 32) {
+                const uint2 q = wq[i];
+                const uint32_t pid = ghist[kb + q.x];
+                const uint32_t pos = atomicAdd(&pb_fill[pid], 1u);
+                cand[pb_off[pid] + pos] = q.y;
+            }
+            __syncwarp();
+            if (lane == 0) wcnt[warp] = 0;
+            __syncwarp();
+        };
+        // rare path: some read of the group carries a key with flow
+        auto hit = [&](uint64_t g, uint32_t key, uint32_t code) -> uint32_t {
+            if (code == kPartCode) wq[atomicAdd(&wcnt[warp], 1u)] = make_uint2(key, (uint32_t)g);
+            return code == kSatCode ? 1u : 0u;
+        };
+        if (a < b) {
+            const uint64_t a4 = min((uint64_t)((a + 3) & ~3ull), b), b4 = max((uint64_t)(b & ~3ull), a4);
+            for (int side = 0; side < 2; ++side) {  // unaligned head and tail
+                const uint64_t lo = side ? b4 : a, hi = side ? b : a4;
+                if (tid < hi - lo) {
+                    const uint64_t g = lo + tid;
+                    const uint32_t s = S[g];
+                    const uint32_t key = key_of(s, ONE_LEN ? 0u : E[g]);
+                    if (hit(g, key, st[key])) {
+                        atomicOr(&bitmap[g >> 5], 1u << (g & 31));
+                        ++kept;
+                    }
+                }
+            }
+            const uint4* S4 = reinterpret_cast<const uint4*>(S) + a4 / 4;
+            const uint4* E4 = reinterpret_cast<const uint4*>(E) + a4 / 4;
+            auto mark4 = [&](uint32_t j, const uint4& s, const uint4& e) {
+                const uint32_t k0 = key_of(s.x, e.x), k1 = key_of(s.y, e.y), k2 = key_of(s.z, e.z),
+                               k3 = key_of(s.w, e.w);
+                const uint32_t c0 = st[k0], c1 = st[k1], c2 = st[k2], c3 = st[k3];
+                if ((c0 | c1 | c2 | c3) == 0) return;  // 94 % of the groups
+                const uint64_t g = a4 + 4ull * j;
+                const uint32_t nib = hit(g, k0, c0) | hit(g + 1, k1, c1) << 1 | hit(g + 2, k2, c2) << 2 |
+                                     hit(g + 3, k3, c3) << 3;
+                if (nib) {
+                    atomicOr(&bitmap[g >> 5], nib << (g & 31));
+                    kept += __popc(nib);
+                }
+            };
+            // the trip count is the same for every lane of a warp (the drain needs the warp
+            // converged): lanes past the end process nothing
+            const uint32_t jend = (uint32_t)((b4 - a4) / 4);
+            constexpr uint32_t kRound = 32 * 4 * kDmUnroll;  // reads one warp parks at most per round
+            for (uint32_t jw = warp * 32; jw < jend; jw += kDmUnroll * kDmThreads) {
+                uint4 s[kDmUnroll], e[kDmUnroll];
+#pragma unroll
+                for (int u = 0; u < kDmUnroll; ++u) {
+                    const uint32_t j = jw + lane + u * kDmThreads;
+                    if (j < jend) {
+                        s[u] = ld_stream4(S4 + j);
+                        if (!ONE_LEN) e[u] = ld_stream4(E4 + j);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kDmUnroll; ++u) {
+                    const uint32_t j = jw + lane + u * kDmThreads;
+                    if (j < jend) mark4(j, s[u], e[u]);
+                }
+                drain(kDmQueue - kRound);
+            }
+        }
+        drain(0);  // the next part may belong to another sample
+        __syncthreads();
+    }
+    kept = __reduce_add_sync(0xffffffffu, kept);
+    if (lane == 0 && kept) atomicAdd(&totals[1], (unsigned long long)kept);
+}
+
+// One warp per partial bundle: keep the f lowest of its candidate read indices.  The f-th lowest
+// index is found by bisection on the index value (count = ballots over the candidates, which sit
+// in registers for bundles of up to 128 reads), ~21 steps instead of an all-pairs ranking.
+__global__ void __launch_bounds__(256)
+k_direct_partial(const uint32_t* __restrict__ pb_off, const uint32_t* __restrict__ pb_f,
+                 const uint32_t* __restrict__ pb_fill, const uint32_t* __restrict__ cand,
+                 const uint32_t* __restrict__ ctl, uint32_t* __restrict__ bitmap,
+                 unsigned long long* __restrict__ totals) {
+    if (ctl[2]) return;
+    const uint32_t n_partial = ctl[0];
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t lane = lane_id();
+    uint32_t kept = 0;
+    constexpr int kReg = 4;
+    for (uint32_t pid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pid < n_partial; pid += warps) {
+        const uint32_t* c = cand + pb_off[pid];
+        const uint32_t n = pb_fill[pid], f = pb_f[pid];
+        uint32_t x[kReg];
+        uint32_t mn = 0xffffffffu, mx = 0;
+#pragma unroll
+        for (int r = 0; r < kReg; ++r) {
+            x[r] = r * 32 + lane < n ? c[r * 32 + lane] : 0xffffffffu;  // padding is never counted
+            if (r * 32 + lane < n) {
+                mn = min(mn, x[r]);
+                mx = max(mx, x[r]);
+            }
+        }
+        for (uint32_t i = kReg * 32 + lane; i < n; i += 32) {
+            mn = min(mn, c[i]);
+            mx = max(mx, c[i]);
+        }
+        uint32_t lo = __reduce_min_sync(0xffffffffu, mn), hi = __reduce_max_sync(0xffffffffu, mx);
+        while (lo < hi) {  // smallest T with #{c <= T} >= f  (indices are distinct)
+            const uint32_t mid = lo + (hi - lo) / 2;
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int r = 0; r < kReg; ++r) cnt += __popc(__ballot_sync(0xffffffffu, x[r] <= mid));
+            if (n > kReg * 32) {
+                uint32_t mine = 0;
+                for (uint32_t i = kReg * 32 + lane; i < n; i += 32) mine += c[i] <= mid;
+                cnt += __reduce_add_sync(0xffffffffu, mine);
+            }
+            if (cnt >= f) hi = mid;
+            else lo = mid + 1;
+        }
+        auto keep = [&](uint32_t v) {
+            atomicOr(&bitmap[v >> 5], 1u << (v & 31));
+            ++kept;
+        };
+#pragma unroll
+        for (int r = 0; r < kReg; ++r)
+            if (x[r] <= lo) keep(x[r]);  // the padding value is above every index
+        for (uint32_t i = kReg * 32 + lane; i < n; i += 32)
+            if (c[i] <= lo) keep(c[i]);
+    }
+    kept = __reduce_add_sync(0xffffffffu, kept);
+    if (lane == 0 && kept) atomicAdd(&totals[1], (unsigned long long)kept);
+}
+
+// ---- K5 direct, fallback: ordered walk -----------------------------------------------------------
+// One CTA per sample holds the per-key quota (= f) in shared memory and walks the reads in index
+// order, tile by tile; a read whose key still has quota is a candidate.  If a tile holds no more
+// candidates of a key than its quota they are all kept (order irrelevant); otherwise (each key at
+// most once) the candidates of that key are ranked by index.  The walk stops when every quota is
+// used up.
 __global__ void __launch_bounds__(256)
 k_direct_quota(const BundleRec* __restrict__ bund, const uint32_t* __restrict__ b_slot, uint32_t B,
                uint32_t* __restrict__ ghist) {

@@ -49,6 +49,7 @@ struct gds_ctx {
     DevBuf bitmap, cov_tmp, dem_tmp, vdiff, vexcl;
     DevBuf vs_d, cross_idx, cross_tc, odiff, oexcl, cut_nodes, tile_off_d, head_bits;
     DevBuf dhist, dlay, b_slot, ident, dwork;  // direct (sort-free) bundle path
+    DevBuf kstat, pbund, cand, dctl;
     unsigned direct_attr = 0;                  // bytes of dynamic smem the direct kernels are set up for
     unsigned mf_attr_set = 0;  // bit i: smem attribute set for launch shape i
     bool atomic_rank = false;  // shared-memory atomics rank in lane order on this device (probed)
@@ -63,7 +64,7 @@ struct gds_ctx {
                          &comp_eidx, &comp_lo, &comp_hi, &qF, &qT, &qN, &qH, &work_counter, &comp_stats,
                          &bitmap, &cov_tmp, &dem_tmp, &vdiff, &vexcl, &vs_d, &cross_idx, &cross_tc,
                          &odiff, &oexcl, &cut_nodes, &tile_off_d, &head_bits, &dhist, &dlay, &b_slot,
-                         &ident, &dwork};
+                         &ident, &dwork, &kstat, &pbund, &cand, &dctl};
         for (DevBuf* b : all) b->release();
     }
 };
@@ -226,7 +227,7 @@ struct DirectPlan {
     bool on = false;
     DirectLayout dl{};
     uint32_t* ghist = nullptr;
-    uint32_t ktot = 0, kmax = 0;
+    uint32_t ktot = 0, kmax = 0, n_items = 0;
     uint32_t* in_bid = nullptr;  // identity in-CSR (single read length), else null
 };
 
@@ -277,6 +278,10 @@ void build_bundles_direct(gds_ctx* c, const gds_reads* rd, const uint32_t* S, co
                                       (int)(kDirectMaxKeys * 4)));
         GDS_CUDA(cudaFuncSetAttribute(k_direct_select, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(kDirectMaxKeys * 4)));
+        GDS_CUDA(cudaFuncSetAttribute(k_direct_mark<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(kDmQueueBytes + kDirectMaxKeys)));
+        GDS_CUDA(cudaFuncSetAttribute(k_direct_mark<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(kDmQueueBytes + kDirectMaxKeys)));
         c->direct_attr = kDirectMaxKeys * 4;
     }
     {
@@ -324,7 +329,78 @@ void build_bundles_direct(gds_ctx* c, const gds_reads* rd, const uint32_t* S, co
     plan.ghist = ghist;
     plan.ktot = ktot;
     plan.kmax = kmax;
+    plan.n_items = n_items;
     plan.in_bid = ident;
+}
+
+// K5 on the direct path (direct.cuh): classify the bundles, mark the reads of saturated bundles in
+// one parallel streaming pass, rank the candidates of partial bundles; the ordered walk is the
+// fallback when the candidates do not fit (or GDS_DIRECT_SELECT=walk asks for it).
+void direct_select(gds_ctx* c, const DirectPlan& dp, const uint32_t* S, const uint32_t* E,
+                   uint32_t ns, size_t N, uint32_t B, uint32_t* bm, size_t n_words,
+                   unsigned long long* totals, gds_result* out) {
+    cudaStream_t st = c->stream;
+    BundleRec* bund = c->bund.as<BundleRec>();
+    uint32_t* b_slot = c->b_slot.as<uint32_t>();
+    uint32_t* wc = c->dwork.as<uint32_t>() + 1;
+    const char* env = getenv("GDS_DIRECT_SELECT");
+    bool walk = env && !strcmp(env, "walk");
+    if (!walk) {
+        const uint32_t cand_cap = (uint32_t)std::min<uint64_t>(N / 16 + (1u << 20), 0xffffff00ull);
+        uint32_t* kstat = c->kstat.get<uint32_t>(dp.ktot / 16 + 1);
+        uint32_t* pb = c->pbund.get<uint32_t>(3 * ((size_t)B + 1));
+        uint32_t* cand = c->cand.get<uint32_t>(cand_cap);
+        uint32_t* ctl = c->dctl.get<uint32_t>(4);
+        GDS_CUDA(cudaMemsetAsync(kstat, 0, ((size_t)dp.ktot / 16 + 1) * 4, st));
+        GDS_CUDA(cudaMemsetAsync(ctl, 0, 16, st));
+        {
+            KScope ks("direct_classify", 20ull * B, st);
+            k_direct_classify<<<div_up(B, 256), 256, 0, st>>>(bund, b_slot, B, dp.ghist, kstat, pb,
+                                                            pb + B + 1, pb + 2 * ((size_t)B + 1), ctl,
+                                                            cand_cap);
+            GDS_KERNEL_CHECK();
+        }
+        {
+            const unsigned long long per_read = dp.dl.nlen > 1 ? 8 : 4;
+            KScope ks("direct_mark", per_read * N + dp.ktot / 4 + 8ull * N / 32, st);
+            const int grid = (int)std::min<uint32_t>(dp.n_items, (uint32_t)kNumSMs);
+            const unsigned smem = kDmQueueBytes + dp.kmax;
+            uint32_t* fill = pb + 2 * ((size_t)B + 1);
+            if (dp.dl.nlen == 1)
+                k_direct_mark<true><<<grid, kDmThreads, smem, st>>>(S, E, dp.dl, dp.n_items, wc, dp.ghist,
+                                                                   kstat, pb, fill, cand, ctl, bm, totals);
+            else
+                k_direct_mark<false><<<grid, kDmThreads, smem, st>>>(S, E, dp.dl, dp.n_items, wc,
+                                                                    dp.ghist, kstat, pb, fill, cand, ctl,
+                                                                    bm, totals);
+            GDS_KERNEL_CHECK();
+        }
+        {
+            KScope ks("direct_partial", 16ull * B / 64, st);
+            k_direct_partial<<<kNumSMs * 32, 256, 0, st>>>(pb, pb + B + 1, pb + 2 * ((size_t)B + 1),
+                                                         cand, ctl, bm, totals);
+            GDS_KERNEL_CHECK();
+        }
+        uint32_t hctl[4];
+        d2h_sync(c, hctl, ctl, 4);
+        out->partial_bundles = hctl[0];
+        out->partial_candidates = hctl[1];
+        walk = hctl[2] != 0;
+        if (!walk) return;
+        GDS_CUDA(cudaMemsetAsync(wc, 0, 4, st));
+    }
+    // ordered walk: one CTA per sample, quota per key in shared memory
+    {
+        KScope ks("direct_quota", 24ull * B, st);
+        k_direct_quota<<<div_up(B, 256), 256, 0, st>>>(bund, b_slot, B, dp.ghist);
+        GDS_KERNEL_CHECK();
+    }
+    {
+        KScope ks("direct_walk", 4ull * dp.ktot + 8ull * N / 32, st);
+        const int grid = (int)std::min<uint32_t>(ns, (uint32_t)kNumSMs);
+        k_direct_select<<<grid, kDsThreads, dp.kmax * 4, st>>>(S, E, dp.dl, wc, dp.ghist, bm, totals);
+        GDS_KERNEL_CHECK();
+    }
 }
 
 // 0 = choose, 1 = always the radix sort, 2 = the direct histogram whenever eligible
@@ -892,24 +968,8 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
                                                      : c->bitmap.get<uint32_t>(n_words + 1);
         if (do_solve) {
             GDS_CUDA(cudaMemsetAsync(bm, 0, n_words * 4, st));
-            if (B && direct.on) {
-                {
-                    KScope ks("direct_quota", 24ull * B, st);
-                    k_direct_quota<<<div_up(B, 256), 256, 0, st>>>(c->bund.as<BundleRec>(),
-                                                                   c->b_slot.as<uint32_t>(), B,
-                                                                   direct.ghist);
-                    GDS_KERNEL_CHECK();
-                }
-                {
-                    // bytes: the quotas once; how far the ordered walk reads is data dependent
-                    KScope ks("direct_select", 4ull * direct.ktot + 8ull * N / 32, st);
-                    uint32_t* wc = c->dwork.as<uint32_t>() + 1;
-                    const int grid = (int)std::min<uint32_t>(ns, (uint32_t)kNumSMs);
-                    k_direct_select<<<grid, kDsThreads, direct.kmax * 4, st>>>(
-                        S, E, direct.dl, wc, direct.ghist, bm, totals);
-                    GDS_KERNEL_CHECK();
-                }
-            } else if (B) {
+            if (B && direct.on) direct_select(c, direct, S, E, ns, N, B, bm, n_words, totals, out);
+            else if (B) {
                 {
                     KScope ks("select", 8ull * B + 8ull * N / 32, st);
                     k_select<<<div_up(B, 256), 256, 0, st>>>(c->b_first.as<uint32_t>(),

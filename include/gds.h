@@ -116,6 +116,9 @@ typedef struct {
     uint64_t verify_violations; /* GDS_VERIFY: positions with min(cov_out,M) != min(cov_in,M) */
     uint32_t key_bits, sort_passes;
     uint64_t kernel_launches; /* kernels this call launched (counted at the launch sites) */
+    /* direct (histogram) path, K5: bundles with 0 < flow < multiplicity and the reads that carry
+     * their keys (ranked by index; every other kept read belongs to a saturated bundle) */
+    uint64_t partial_bundles, partial_candidates;
     /* device-event milliseconds per phase */
     float ms_h2d, ms_filter, ms_graph, ms_maxflow, ms_select, ms_verify, ms_d2h, ms_total;
 } gds_result;

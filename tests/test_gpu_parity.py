@@ -347,6 +347,16 @@ def test_direct_histogram_path_equals_sort_path(solver, O):
         assert np.array_equal(res[bmode].demand, res[1].demand)
         assert np.array_equal(res[bmode].cov_capped, res[1].cov_capped)
     assert_parity(O, res[0], s, e, [30_000] * 3, off, 300)
+    # K5 of the histogram path has two implementations (parallel mark + partial-bundle ranking,
+    # and the ordered walk it falls back to): same kept set
+    import os
+    os.environ["GDS_DIRECT_SELECT"] = "walk"
+    try:
+        rw = solver.solve(s, e, [30_000] * 3, 300, read_off=off, params=PRM + (0, 2), verify=True)
+    finally:
+        del os.environ["GDS_DIRECT_SELECT"]
+    assert rw.sort_passes == 0 and rw.n_kept == res[1].n_kept and rw.verify_violations == 0
+    assert np.array_equal(rw.kept_bitmap, res[1].kept_bitmap)
     # a few read lengths (key = start x #lengths + length) still fit in shared memory
     rng = np.random.default_rng(11)
     s2 = rng.integers(0, 9_000, size=400_000).astype(np.uint32)
@@ -384,3 +394,11 @@ def test_direct_selection_walk_many_tiles_and_duplicates(solver, O):
                          want_vectors=True)
         assert r.sort_passes == 0 or len(s) == 0
         assert_parity(O, r, s, e, Ls, off, M)
+        if it % 4 == 0:  # and the ordered walk on the same input
+            import os
+            os.environ["GDS_DIRECT_SELECT"] = "walk"
+            try:
+                rw = solver.solve(s, e, Ls, M, read_off=off, params=PRM + (0, 2), verify=True)
+            finally:
+                del os.environ["GDS_DIRECT_SELECT"]
+            assert np.array_equal(rw.kept_bitmap, r.kept_bitmap) and rw.n_kept == r.n_kept
