@@ -27,7 +27,8 @@ class GdsError(RuntimeError):
 class _Reads(C.Structure):
     _fields_ = [("n_samples", C.c_uint32), ("read_off", C.c_void_p), ("ref_len", C.c_void_p),
                 ("start", C.c_void_p), ("end", C.c_void_p), ("mapq", C.c_void_p),
-                ("seq_len", C.c_void_p), ("len_min", C.c_uint32), ("len_max", C.c_uint32)]
+                ("seq_len", C.c_void_p), ("len_min", C.c_uint32), ("len_max", C.c_uint32),
+                ("start16", C.c_void_p)]
 
 
 class _Filter(C.Structure):
@@ -165,9 +166,17 @@ class Solver:
 
         filt = dict(min_len=, min_mapq=, amp_start=None, amp_end=None) or None.
         """
-        start = np.ascontiguousarray(start, np.uint32)
-        end = np.ascontiguousarray(end, np.uint32)
-        n = len(start)
+        # compact transport (gds_reads.start16 / end == NULL): a uint16 start array is passed as
+        # start16, end=None means fixed-length reads of len_hint[0] == len_hint[1]
+        start16 = None
+        if isinstance(start, np.ndarray) and start.dtype == np.uint16:
+            start16 = np.ascontiguousarray(start)
+            start = None
+        else:
+            start = np.ascontiguousarray(start, np.uint32)
+        if end is not None:
+            end = np.ascontiguousarray(end, np.uint32)
+        n = len(start16 if start16 is not None else start)
         ref_len = np.atleast_1d(np.ascontiguousarray(ref_len, np.uint32))
         ns = len(ref_len)
         if read_off is None:
@@ -175,8 +184,8 @@ class Solver:
         read_off = np.ascontiguousarray(read_off, np.uint64)
         lh = len_hint or (0, 0)  # exact (min, max) of end-start+1, see gds_reads.len_min
         rd = _Reads(ns, _ptr(read_off), _ptr(ref_len), _ptr(start), _ptr(end), None, None,
-                    int(lh[0]), int(lh[1]))
-        keep = [start, end, ref_len, read_off]
+                    int(lh[0]), int(lh[1]), _ptr(start16))
+        keep = [start, start16, end, ref_len, read_off]
         fl = None
         if filt is not None:
             mapq = np.ascontiguousarray(mapq, np.uint8)
@@ -219,7 +228,7 @@ class Solver:
     def solve_device(self, start_ptr, end_ptr, n_reads, ref_len, max_coverage, bitmap_ptr,
                      read_off=None, mapq_ptr=None, seq_len_ptr=None, filt=None, params=None,
                      verify=False, find_pairs=False, pair_pass_ptr=None, profile=False,
-                     input_on_device=True, len_hint=None):
+                     input_on_device=True, len_hint=None, start16_ptr=None):
         """Raw-pointer path.  The bitmap (and pair_pass) are device pointers; the reads are device
         pointers too (tensor.data_ptr()) unless input_on_device=False, in which case they are
         HOST pointers (ideally pinned) and the library does the host->device copies itself."""
@@ -229,8 +238,9 @@ class Solver:
             read_off = np.array([0, n_reads], np.uint64)
         read_off = np.ascontiguousarray(read_off, np.uint64)
         lh = len_hint or (0, 0)
-        rd = _Reads(ns, _ptr(read_off), _ptr(ref_len), start_ptr, end_ptr, mapq_ptr, seq_len_ptr,
-                    int(lh[0]), int(lh[1]))
+        # start16_ptr: 16-bit starts instead of start_ptr; end_ptr None/0: fixed-length reads
+        rd = _Reads(ns, _ptr(read_off), _ptr(ref_len), start_ptr or None, end_ptr or None, mapq_ptr,
+                    seq_len_ptr, int(lh[0]), int(lh[1]), start16_ptr or None)
         fl = None
         keep = []
         if filt is not None:

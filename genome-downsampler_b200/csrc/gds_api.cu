@@ -33,7 +33,7 @@ struct gds_ctx {
     void* pinned = nullptr;  // small readback area
     static constexpr size_t kPinnedBytes = 1 << 16;
 
-    DevBuf in_start, in_end, in_mapq, in_len;
+    DevBuf in_start, in_end, in_mapq, in_len, in_raw;
     DevBuf off_d, reflen_d, base_d, foff_d, amp_s, amp_e;
     DevBuf pair_pass, flag32, fS, fE;
     DevBuf small;  // uint32 stats[8] + u64 totals[4]
@@ -56,7 +56,7 @@ struct gds_ctx {
     Profiler prof;
 
     void release_all() {
-        DevBuf* all[] = {&in_start, &in_end, &in_mapq, &in_len, &off_d, &reflen_d, &base_d, &foff_d,
+        DevBuf* all[] = {&in_start, &in_end, &in_mapq, &in_len, &in_raw, &off_d, &reflen_d, &base_d, &foff_d,
                          &amp_s, &amp_e, &pair_pass, &flag32, &fS, &fE, &small, &keysA, &keysB,
                          &valsA, &valsB, &tile_counts, &radix.hist, &radix.scan.l1, &radix.scan.l2,
                          &scan.l1, &scan.l2, &b_first, &b_key, &b_t, &bund, &diff,
@@ -535,7 +535,15 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
     for (uint32_t k = 0; k < ns; ++k)
         if (rd->read_off[k + 1] < rd->read_off[k])
             return fail(c, GDS_ERR_ARG, "read_off must be non-decreasing");
-    if (P > 0 && (!rd->start || !rd->end)) return fail(c, GDS_ERR_ARG, "null start/end");
+    if (P > 0 && !rd->start && !rd->start16) return fail(c, GDS_ERR_ARG, "null start");
+    const bool fixed_len = rd->len_min != 0 && rd->len_min == rd->len_max;
+    if (P > 0 && !rd->end && !fixed_len)
+        return fail(c, GDS_ERR_ARG, "end may only be omitted with len_min == len_max != 0");
+    if (rd->start16)
+        for (uint32_t k = 0; k < ns; ++k)
+            if (rd->ref_len[k] > 65536u)
+                return fail(c, GDS_ERR_ARG, "start16 needs every ref_len <= 65536");
+    const bool compact = P > 0 && (rd->start16 || !rd->end);
     if (P >= (1ull << 32) - 64) return fail(c, GDS_ERR_RANGE, "more than 2^32 reads in one call");
     const bool use_filter = flt != nullptr;
     if (use_filter) {
@@ -600,10 +608,16 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             dQ = rd->mapq;
             dLen = rd->seq_len;
         } else {
+            // compact transport: only the narrow start column (and the ends, if given) cross PCIe
             uint32_t* s = c->in_start.get<uint32_t>(P);
             uint32_t* e = c->in_end.get<uint32_t>(P);
-            GDS_CUDA(cudaMemcpyAsync(s, rd->start, P * 4, cudaMemcpyHostToDevice, st));
-            GDS_CUDA(cudaMemcpyAsync(e, rd->end, P * 4, cudaMemcpyHostToDevice, st));
+            if (rd->start16) {
+                uint16_t* raw = c->in_raw.get<uint16_t>(P + 8);
+                GDS_CUDA(cudaMemcpyAsync(raw, rd->start16, P * 2, cudaMemcpyHostToDevice, st));
+            } else {
+                GDS_CUDA(cudaMemcpyAsync(s, rd->start, P * 4, cudaMemcpyHostToDevice, st));
+            }
+            if (rd->end) GDS_CUDA(cudaMemcpyAsync(e, rd->end, P * 4, cudaMemcpyHostToDevice, st));
             dS = s;
             dE = e;
             if (use_filter) {
@@ -614,6 +628,33 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
                 dQ = q;
                 dLen = l;
             }
+        }
+        if (compact) {  // widen to the 32-bit columns (k_expand_reads)
+            const uint16_t* s16 = nullptr;
+            const uint32_t* s32 = nullptr;
+            const uint32_t* e32 = nullptr;
+            uint32_t* s = c->in_start.get<uint32_t>(P);
+            uint32_t* e = c->in_end.get<uint32_t>(P);
+            if (in_dev) {
+                s16 = rd->start16;
+                s32 = rd->start16 ? nullptr : rd->start;
+                e32 = rd->end;
+            } else {
+                s16 = rd->start16 ? c->in_raw.as<uint16_t>() : nullptr;
+                s32 = rd->start16 ? nullptr : s;
+                e32 = rd->end ? e : nullptr;
+            }
+            uint32_t* So = (s32 && ((uintptr_t)s32 & 15) == 0) ? const_cast<uint32_t*>(s32) : s;
+            uint32_t* Eo = e32 ? const_cast<uint32_t*>(e32) : e;
+            {
+                KScope ks("expand_reads", (s16 ? 2ull : 4ull) * P + (So != s32 ? 4ull : 0ull) * P +
+                                              (e32 ? 0ull : 4ull) * P, st);
+                k_expand_reads<<<div_up((long long)P, 256 * 8), 256, 0, st>>>(s16, s32, e32, rd->len_min,
+                                                                             P, So, Eo);
+                GDS_KERNEL_CHECK();
+            }
+            dS = So;
+            dE = Eo;
         }
         uint64_t* off_d = c->off_d.get<uint64_t>(ns + 1);
         uint32_t* reflen_d = c->reflen_d.get<uint32_t>(ns);

@@ -22,6 +22,46 @@ __device__ __forceinline__ uint32_t find_sample(const uint64_t* __restrict__ off
     return lo;
 }
 
+// Compact transport (gds_reads.start16 / end == NULL): widen to the 32-bit start/end columns the
+// pipeline works on.  8 reads per thread, 16-byte accesses.
+__global__ void __launch_bounds__(256)
+k_expand_reads(const uint16_t* __restrict__ s16, const uint32_t* __restrict__ s32,
+               const uint32_t* __restrict__ e32, uint32_t fixed_len, size_t n,
+               uint32_t* __restrict__ S, uint32_t* __restrict__ E) {
+    const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (i0 >= n) return;
+    uint32_t s[8];
+    if (i0 + 8 <= n && s16 && (reinterpret_cast<uintptr_t>(s16) & 15) == 0) {
+        const uint4 v = ld_stream4(reinterpret_cast<const uint4*>(s16 + i0));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            s[2 * q] = w[q] & 0xffffu;
+            s[2 * q + 1] = w[q] >> 16;
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            s[q] = i0 + q < n ? (s16 ? (uint32_t)s16[i0 + q] : s32[i0 + q]) : 0u;
+    }
+    if (i0 + 8 <= n) {
+        if (S != s32) {
+            reinterpret_cast<uint4*>(S + i0)[0] = make_uint4(s[0], s[1], s[2], s[3]);
+            reinterpret_cast<uint4*>(S + i0)[1] = make_uint4(s[4], s[5], s[6], s[7]);
+        }
+        if (!e32) {
+            const uint32_t d = fixed_len - 1;
+            reinterpret_cast<uint4*>(E + i0)[0] = make_uint4(s[0] + d, s[1] + d, s[2] + d, s[3] + d);
+            reinterpret_cast<uint4*>(E + i0)[1] = make_uint4(s[4] + d, s[5] + d, s[6] + d, s[7] + d);
+        }
+    } else {
+        for (int q = 0; q < 8 && i0 + q < n; ++q) {
+            if (S != s32) S[i0 + q] = s[q];
+            if (!e32) E[i0 + q] = s[q] + fixed_len - 1;
+        }
+    }
+}
+
 struct FilterArgs {
     uint32_t min_len, min_mapq;
     uint32_t n_amp;

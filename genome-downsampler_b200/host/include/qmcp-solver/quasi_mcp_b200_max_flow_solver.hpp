@@ -41,7 +41,7 @@ class QuasiMcpB200MaxFlowSolver : public Solver {
         }
         ~Pinned() { gds_host_free(p); }
     };
-    Pinned start_, end_, mapq_, seq_len_, bitmap_, pair_pass_;
+    Pinned start_, start16_, end_, mapq_, seq_len_, bitmap_, pair_pass_;
 
     int device_;
     gds_ctx* ctx_ = nullptr;  // created lazily, reused across solve() calls

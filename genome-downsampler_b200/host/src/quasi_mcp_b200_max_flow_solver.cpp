@@ -32,7 +32,11 @@ std::unique_ptr<Solution> QuasiMcpB200MaxFlowSolver::solve(uint32_t max_coverage
     }
     uint32_t* start = start_.get<uint32_t>(n);
     uint32_t* end = end_.get<uint32_t>(n);
-    if (!start || !end) {
+    // compact transport (gds_reads.start16): a reference of up to 65536 positions fits 16-bit
+    // starts; the column is written by the same narrowing loop
+    const bool narrow16 = L <= 65536;
+    uint16_t* start16 = narrow16 ? start16_.get<uint16_t>(n) : nullptr;
+    if (!start || !end || (narrow16 && !start16)) {
         LOG_WITH_LEVEL(logging::ERROR) << "quasi-mcp-b200: cannot allocate pinned staging buffers";
         std::exit(EXIT_FAILURE);
     }
@@ -40,8 +44,13 @@ std::unique_ptr<Solution> QuasiMcpB200MaxFlowSolver::solve(uint32_t max_coverage
     // input validation into the first sort pass (gds_reads.len_min / len_max)
     uint32_t len_min = 0xffffffffu, len_max = 0;
     bool lens_ok = n > 0;
+    bool fits16 = true;  // a start beyond 16 bits is an input error the device has to see as such
     for (uint64_t i = 0; i < n; ++i) {
         start[i] = static_cast<uint32_t>(in.start_inds[i]);
+        if (narrow16) {
+            fits16 &= in.start_inds[i] <= 0xffff;
+            start16[i] = static_cast<uint16_t>(in.start_inds[i]);
+        }
         end[i] = static_cast<uint32_t>(std::min<uint64_t>(in.end_inds[i], kMax32));
         if (end[i] < start[i]) {
             lens_ok = false;  // the library reports it as GDS_ERR_RANGE
@@ -53,7 +62,16 @@ std::unique_ptr<Solution> QuasiMcpB200MaxFlowSolver::solve(uint32_t max_coverage
     uint64_t off[2] = {0, n};
     uint32_t ref_len = static_cast<uint32_t>(L);
     gds_reads rd{1, off, &ref_len, start, end, nullptr, nullptr,
-                 lens_ok ? len_min : 0, lens_ok ? len_max : 0};
+                 lens_ok ? len_min : 0, lens_ok ? len_max : 0, nullptr};
+    // fixed-length reads (reads-gen, most short-read runs): the end column is implied; with
+    // 16-bit starts a read crosses PCIe as 2 bytes instead of 8.
+    if (lens_ok && len_min == len_max) {
+        rd.end = nullptr;
+        if (narrow16 && fits16) {
+            rd.start16 = start16;
+            rd.start = nullptr;
+        }
+    }
     gds_filter flt{};
     std::vector<uint32_t> amp_s, amp_e;
     uint8_t* pair_pass = nullptr;

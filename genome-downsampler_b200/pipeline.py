@@ -21,10 +21,15 @@ class ChunkedSolver:
             s.close()
 
     def solve_host_batch(self, start_ptr, end_ptr, read_off, ref_len, max_coverage, bitmap_ptr,
-                         chunk_samples=64, params=None, len_hint=None):
+                         chunk_samples=64, params=None, len_hint=None, start16_ptr=None,
+                         input_on_device=False):
         """start_ptr/end_ptr: HOST pointers (pinned for full PCIe speed) of the concatenated reads;
         read_off [ns+1] (every chunk boundary must be a multiple of 32 reads so bitmap slices are
         word-aligned), ref_len [ns]; bitmap_ptr: DEVICE pointer of ceil(n/32) words.
+        Compact transport (include/gds.h gds_reads.start16): start16_ptr = 16-bit starts instead
+        of start_ptr, end_ptr = None for fixed-length reads (len_hint[0] == len_hint[1]).
+        input_on_device=True: the pointers are device pointers (two contexts still overlap one
+        chunk's max-flow with the next chunk's streaming kernels).
         Returns the list of per-chunk results (in chunk order)."""
         read_off = np.ascontiguousarray(read_off, np.uint64)
         ref_len = np.ascontiguousarray(ref_len, np.uint32)
@@ -44,9 +49,11 @@ class ChunkedSolver:
                     r0 = int(read_off[a])
                     n = int(read_off[b]) - r0
                     results[ci] = sv.solve_device(
-                        start_ptr + 4 * r0, end_ptr + 4 * r0, n, ref_len[a:b], max_coverage,
+                        start_ptr + 4 * r0 if start_ptr else None,
+                        end_ptr + 4 * r0 if end_ptr else None, n, ref_len[a:b], max_coverage,
                         bitmap_ptr + 4 * (r0 // 32), read_off=read_off[a:b + 1] - np.uint64(r0),
-                        params=params, input_on_device=False, len_hint=len_hint)
+                        params=params, input_on_device=input_on_device, len_hint=len_hint,
+                        start16_ptr=start16_ptr + 2 * r0 if start16_ptr else None)
             except Exception as ex:  # surfaced to the caller after the join
                 errors.append(ex)
 

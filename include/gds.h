@@ -56,8 +56,9 @@ typedef struct {
     uint32_t n_samples;       /* >= 1 */
     const uint64_t* read_off; /* [n_samples+1], read_off[0] = 0 */
     const uint32_t* ref_len;  /* [n_samples]  PairedReads::ref_genome_length */
-    const uint32_t* start;    /* [n_reads]    Read::start_ind */
-    const uint32_t* end;      /* [n_reads]    Read::end_ind (inclusive) */
+    const uint32_t* start;    /* [n_reads]    Read::start_ind (ignored when start16 is given) */
+    const uint32_t* end;      /* [n_reads]    Read::end_ind (inclusive); NULL = every read has
+                                 length len_min == len_max (fixed-length reads: end = start+len-1) */
     const uint8_t* mapq;      /* [n_reads]    Read::quality (MAPQ); NULL if no filter */
     const uint32_t* seq_len;  /* [n_reads]    Read::seq_length (l_qseq); NULL if no filter */
     /* optional: exact bounds of end-start+1 over all reads (0,0 = unknown).  A caller that
@@ -65,6 +66,11 @@ typedef struct {
      * input validation into the first pass of the sort instead of a separate pass over the
      * reads.  Reads outside the bounds fail the call with GDS_ERR_ARG. */
     uint32_t len_min, len_max;
+    /* optional compact transport of the start column: 16-bit starts (every ref_len <= 65536).
+     * With fixed-length reads (end == NULL) a read then crosses PCIe as 2 bytes instead of 8; the
+     * device widens the columns again before anything else runs.  Same pointer kind (host or
+     * device) as start/end. */
+    const uint16_t* start16;
 } gds_reads;
 
 /* Pre-filter.  Replaces BamApi::should_be_filtered_out (bam_api.cpp:311-332) and the amplicon

@@ -402,3 +402,56 @@ def test_direct_selection_walk_many_tiles_and_duplicates(solver, O):
             finally:
                 del os.environ["GDS_DIRECT_SELECT"]
             assert np.array_equal(rw.kept_bitmap, r.kept_bitmap) and rw.n_kept == r.n_kept
+
+
+def test_compact_transport_start16_and_implied_end(pkg, solver, O):
+    # gds_reads.start16 / end == NULL: same answer as the 32-bit columns, 2 bytes per read over PCIe
+    parts = [O.gen_reads(7000 + k, 30_000 + 16 * k, 30_000, 150) for k in range(3)]
+    s = np.concatenate([p[0] for p in parts]); e = np.concatenate([p[1] for p in parts])
+    off = np.cumsum([0] + [len(p[0]) for p in parts]).astype(np.uint64)
+    Ls = [30_000] * 3
+    r0 = solver.solve(s, e, Ls, 40, read_off=off, params=PRM, verify=True, want_vectors=True)
+    r1 = solver.solve(s, None, Ls, 40, read_off=off, params=PRM, verify=True, want_vectors=True,
+                      len_hint=(150, 150))
+    r2 = solver.solve(s.astype(np.uint16), None, Ls, 40, read_off=off, params=PRM, verify=True,
+                      want_vectors=True, len_hint=(150, 150))
+    r3 = solver.solve(s.astype(np.uint16), e, Ls, 40, read_off=off, params=PRM + (0, 1), verify=True)
+    for r in (r1, r2, r3):
+        assert np.array_equal(r.kept_bitmap, r0.kept_bitmap) and r.n_kept == r0.n_kept
+        assert r.verify_violations == 0 and r.fstar == r0.fstar
+    assert np.array_equal(r2.cov_capped, r0.cov_capped) and np.array_equal(r2.demand, r0.demand)
+    assert_parity(O, r2, s, e, Ls, off, 40)
+    # odd sizes (the widening kernel's scalar tail) and a long reference with implied ends
+    s4, e4, _, _ = O.gen_reads(5, 50_003, 100_000, 150)
+    s4, e4 = s4[:100_003].copy(), e4[:100_003].copy()
+    ra = solver.solve(s4, e4, 100_000, 40, params=PRM)
+    rb = solver.solve(s4, None, 100_000, 40, params=PRM, len_hint=(150, 150))
+    assert np.array_equal(ra.kept_bitmap, rb.kept_bitmap)
+    # errors: end omitted without a fixed length, 16-bit starts on a long reference, bad range
+    with pytest.raises(pkg.GdsError) as ei:
+        solver.solve(s, None, Ls, 40, read_off=off)
+    assert ei.value.code == 1
+    with pytest.raises(pkg.GdsError) as ei:
+        solver.solve(s4.astype(np.uint16), None, 100_000, 40, len_hint=(150, 150))
+    assert ei.value.code == 1
+    bad = s.astype(np.uint16); bad[5] = 29_990
+    with pytest.raises(pkg.GdsError) as ei:
+        solver.solve(bad, None, Ls, 40, read_off=off, len_hint=(150, 150))
+    assert ei.value.code == 2
+    # chunked host pipeline with the compact columns
+    import torch
+    n32 = (len(s) // 32) * 32
+    parts = [O.gen_reads(8100 + k, 16_000, 30_000, 150) for k in range(5)]
+    s5 = np.concatenate([p[0] for p in parts]); e5 = np.concatenate([p[1] for p in parts])
+    off5 = np.arange(6, dtype=np.uint64) * 32_000
+    r5 = solver.solve(s5, e5, [30_000] * 5, 40, read_off=off5, params=PRM)
+    h16 = torch.from_numpy(s5.astype(np.uint16).view(np.int16)).pin_memory()
+    bm = torch.zeros(len(s5) // 32 + 4, dtype=torch.int32, device="cuda")
+    ch = pkg.ChunkedSolver(0)
+    try:
+        rs = ch.solve_host_batch(None, None, off5, [30_000] * 5, 40, bm.data_ptr(), chunk_samples=2,
+                                 params=PRM, len_hint=(150, 150), start16_ptr=h16.data_ptr())
+    finally:
+        ch.close()
+    assert sum(int(x.n_kept) for x in rs) == r5.n_kept
+    assert np.array_equal(bm[:len(s5) // 32].cpu().numpy().view(np.uint32), r5.kept_bitmap)
