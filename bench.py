@@ -105,10 +105,12 @@ def traffic_for(kernel, alg_bytes_per_launch):
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if not os.path.exists(p):
         return None
-    per_item = json.load(open(p)).get("per_item", {}).get(kernel)
-    if per_item is None:
-        return None
-    return int(per_item * alg_bytes_per_launch / 16.0)
+    t = json.load(open(p))
+    per_item = t.get("per_item", {}).get(kernel)
+    if per_item is not None:
+        return int(per_item * alg_bytes_per_launch / 16.0)
+    ratio = t.get("per_alg_byte", {}).get(kernel)  # measured DRAM bytes per algorithmic byte
+    return None if ratio is None else int(ratio * alg_bytes_per_launch)
 
 
 # ------------------------------------------------------------------------------- clocks
@@ -526,6 +528,9 @@ def run_b200(args, wl, wname):
                     "unit": "GB/s", "frac": top["frac"],
                     "traffic": traffic_for(top["name"], per_launch),
                     "peak_source": peak_src, "alg_bytes_per_launch": per_launch,
+                    "note": ("K3 is bound by the latency of its dependent rounds (rounds x us, see "
+                             "result.k3), not by HBM; the streaming kernels are listed in kernels[]")
+                    if top["name"] == "maxflow" else None,
                     "ms_per_launch": top["ms_per_step"] / max(top["launches_per_step"], 1)}
         stream_k = [k for k in kernels if k["name"] != "maxflow"]
         if stream_k:

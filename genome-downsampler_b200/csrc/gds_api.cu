@@ -136,7 +136,14 @@ void launch_maxflow(gds_ctx* c, const MfGraph& mg,
                     CompStats* cstats, unsigned long long alg_bytes) {
     KScope ks("maxflow", alg_bytes, c->stream);
     const uint32_t sms = (uint32_t)kNumSMs;
-    if (n_comp <= sms * kMfShapes[0].ctas_per_sm)
+    int force = -1;  // GDS_MF_SHAPE=0..3: measurement knob (the schedule does not depend on it)
+    if (const char* e = getenv("GDS_MF_SHAPE")) force = atoi(e);
+    if (force >= 0 && force <= 3) {
+        if (force == 0) launch_maxflow_shape<0>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats);
+        if (force == 1) launch_maxflow_shape<1>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats);
+        if (force == 2) launch_maxflow_shape<2>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats);
+        if (force == 3) launch_maxflow_shape<3>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats);
+    } else if (n_comp <= sms * kMfShapes[0].ctas_per_sm)
         launch_maxflow_shape<0>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats);
     else if (n_comp <= sms * kMfShapes[1].ctas_per_sm)
         launch_maxflow_shape<1>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats);
@@ -1072,11 +1079,12 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             d2h_sync(c, hs.data(), cstats, n_comp);
             if (const char* dump = getenv("GDS_DUMP_COMP")) {  // diagnostics only
                 if (FILE* fp = fopen(dump, "w")) {
-                    fprintf(fp, "comp rounds pushes relabels grs bfs_levels max_frontier frontier_sum cycles\n");
+                    fprintf(fp, "comp rounds pushes relabels grs bfs_levels max_frontier frontier_sum cycles gr_init gr_bfs gr_snap front\n");
                     for (uint32_t i = 0; i < n_comp; ++i)
-                        fprintf(fp, "%u %llu %llu %llu %llu %llu %llu %llu %llu\n", i, hs[i].rounds,
-                                hs[i].pushes, hs[i].relabels, hs[i].grs, hs[i].bfs_levels,
-                                hs[i].max_frontier, hs[i].frontier_sum, hs[i].cycles);
+                        fprintf(fp, "%u %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu\n", i,
+                                hs[i].rounds, hs[i].pushes, hs[i].relabels, hs[i].grs, hs[i].bfs_levels,
+                                hs[i].max_frontier, hs[i].frontier_sum, hs[i].cycles, hs[i].cyc_gr_init,
+                                hs[i].cyc_gr_bfs, hs[i].cyc_gr_snap, hs[i].cyc_front);
                     fclose(fp);
                 }
             }

@@ -53,6 +53,9 @@ struct CompStats {
     unsigned long long rounds, pushes, relabels, grs, bfs_levels, max_frontier;
     long long sink_flow, stuck;
     unsigned long long cycles, frontier_sum;  // diagnostics: SM clocks spent, sum of frontier sizes
+    // diagnostics: clocks of the first global relabel's label reset, its BFS levels, its snapshot
+    // copy, and of the initial frontier scan
+    unsigned long long cyc_gr_init, cyc_gr_bfs, cyc_gr_snap, cyc_front;
 };
 
 // Record loads.  A component is owned by ONE CTA, i.e. one SM: plain (L1-allocating) loads are
@@ -126,8 +129,9 @@ __device__ __forceinline__ uint32_t warp_excl_sum(uint32_t v, uint32_t& total) {
 template <int THREADS, uint32_t QCAP>
 __device__ uint32_t mf_global_relabel(const MfGraph& G, uint32_t lo, uint32_t hi, Queue<QCAP> T,
                                       Queue<QCAP> N, Queue<QCAP> H, MfShared<QCAP>& sh,
-                                      unsigned long long& bfs_levels) {
+                                      unsigned long long& bfs_levels, long long* tparts = nullptr) {
     const uint32_t tid = threadIdx.x;
+    const long long tp0 = clock64();
     if (tid == 0) {
         sh.nT = 0;
         sh.nN = 0;
@@ -140,6 +144,7 @@ __device__ uint32_t mf_global_relabel(const MfGraph& G, uint32_t lo, uint32_t hi
         if (is_sink) q_append(T, &sh.nT, v);
     }
     __syncthreads();
+    const long long tp1 = clock64();
     uint32_t level = 1;
     uint32_t cnt = sh.nT;
     while (cnt > 0) {
@@ -201,12 +206,18 @@ __device__ uint32_t mf_global_relabel(const MfGraph& G, uint32_t lo, uint32_t hi
         ++level;
         __syncthreads();
     }
+    const long long tp2 = clock64();
     for (uint32_t v = lo + tid; v <= hi; v += THREADS) G.d_snap[v] = ld_u32(&G.node[v].d);
     if (tid == 0) {
         sh.nT = 0;
         sh.nN = 0;
     }
     __syncthreads();
+    if (tparts) {
+        tparts[0] = tp1 - tp0;
+        tparts[1] = tp2 - tp1;
+        tparts[2] = clock64() - tp2;
+    }
     return level;
 }
 
@@ -240,7 +251,10 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
         const long long t_begin = clock64();
         unsigned long long my_pushes = 0, my_relabels = 0;
         long long my_sink = 0, my_stuck = 0;
-        uint32_t last_levels = mf_global_relabel<THREADS, QCAP>(G, lo, hi, T, N, H, sh, bfs_levels);
+        long long tparts[3];
+        uint32_t last_levels =
+            mf_global_relabel<THREADS, QCAP>(G, lo, hi, T, N, H, sh, bfs_levels, tparts);
+        const long long t_front = clock64();
         for (uint32_t v = lo + tid; v <= hi; v += THREADS) {
             if ((int32_t)ld_u32(reinterpret_cast<const uint32_t*>(&G.node[v].e)) > 0) {
                 G.node[v].stamp = 1;
@@ -248,6 +262,7 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
             }
         }
         __syncthreads();
+        const long long cyc_front = clock64() - t_front;
         uint32_t round = 0;
         unsigned long long rounds_since = 0;
         for (;;) {
@@ -577,6 +592,10 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
             cs.stuck = sh.stuck;
             cs.cycles = (unsigned long long)(clock64() - t_begin);
             cs.frontier_sum = frontier_sum;
+            cs.cyc_gr_init = (unsigned long long)tparts[0];
+            cs.cyc_gr_bfs = (unsigned long long)tparts[1];
+            cs.cyc_gr_snap = (unsigned long long)tparts[2];
+            cs.cyc_front = (unsigned long long)cyc_front;
             stats[c] = cs;
         }
         __syncthreads();
