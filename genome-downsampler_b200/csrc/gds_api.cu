@@ -49,7 +49,7 @@ struct gds_ctx {
     DevBuf bitmap, cov_tmp, dem_tmp, vdiff, vexcl;
     DevBuf vs_d, cross_idx, cross_tc, odiff, oexcl, cut_nodes, tile_off_d, head_bits;
     DevBuf dhist, dlay, b_slot, ident, dwork;  // direct (sort-free) bundle path
-    DevBuf kstat, pbund, cand, dctl;
+    DevBuf kstat, pbund, cand, dctl, in_src;
     unsigned direct_attr = 0;                  // bytes of dynamic smem the direct kernels are set up for
     unsigned mf_attr_set = 0;  // bit i: smem attribute set for launch shape i
     bool atomic_rank = false;  // shared-memory atomics rank in lane order on this device (probed)
@@ -64,7 +64,7 @@ struct gds_ctx {
                          &comp_eidx, &comp_lo, &comp_hi, &qF, &qT, &qN, &qH, &work_counter, &comp_stats,
                          &bitmap, &cov_tmp, &dem_tmp, &vdiff, &vexcl, &vs_d, &cross_idx, &cross_tc,
                          &odiff, &oexcl, &cut_nodes, &tile_off_d, &head_bits, &dhist, &dlay, &b_slot,
-                         &ident, &dwork, &kstat, &pbund, &cand, &dctl};
+                         &ident, &dwork, &kstat, &pbund, &cand, &dctl, &in_src};
         for (DevBuf* b : all) b->release();
     }
 };
@@ -995,7 +995,13 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         GDS_CUDA(cudaEventRecord(c->ev[EV_GRAPH], st));
 
         // ---------------- K3: max flow ----------------
-        MfGraph mg{node, d_snap, c->bund.as<BundleRec>(), in_bid};
+        uint32_t* in_src = c->in_src.get<uint32_t>((size_t)B + 1);
+        if (B) {
+            KScope ks("in_src", 24ull * B, st);
+            k_in_src<<<div_up(B, 256), 256, 0, st>>>(c->bund.as<BundleRec>(), in_bid, B, in_src);
+            GDS_KERNEL_CHECK();
+        }
+        MfGraph mg{node, d_snap, c->bund.as<BundleRec>(), in_bid, in_src};
         CompStats* cstats = c->comp_stats.get<CompStats>(n_comp + 1);
         const bool do_solve = !(flags & GDS_NO_SOLVE);
         if (do_solve && n_comp) {

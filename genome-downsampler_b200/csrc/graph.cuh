@@ -396,6 +396,14 @@ k_node_finalize(const uint32_t* __restrict__ excl, const int32_t* __restrict__ d
     if (lane_id() == 0 && src) atomicAdd(&totals[0], src);
 }
 
+// start node of every in-CSR slot (the first global relabel of K3 walks only this array)
+__global__ void __launch_bounds__(256)
+k_in_src(const BundleRec* __restrict__ bund, const uint32_t* __restrict__ in_bid, uint32_t B,
+         uint32_t* __restrict__ in_src) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < B) in_src[k] = bund[in_bid[k]].s;
+}
+
 __global__ void __launch_bounds__(256)
 k_comp_write(const uint32_t* __restrict__ comp_start, const uint32_t* __restrict__ comp_end,
              const uint32_t* __restrict__ start_idx, const uint32_t* __restrict__ end_idx,

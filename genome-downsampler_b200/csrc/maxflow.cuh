@@ -43,6 +43,7 @@ struct MfGraph {
     uint32_t* d_snap;        // [n_nodes] label snapshot read by relabels
     BundleRec* bund;         // [B] sorted by (start node, key)
     const uint32_t* in_bid;  // [B] bundle ids ordered by (end node, bundle id)
+    const uint32_t* in_src;  // [B] start node of in_bid[k]: the first relabel needs nothing else
 };
 
 struct SolveParams {
@@ -101,6 +102,7 @@ template <uint32_t QCAP>
 struct MfShared {
     uint32_t qa[QCAP], qb[QCAP], qc[QCAP], qd[QCAP];
     uint32_t nF, nT, nN, nH;
+    uint32_t lc[3];  // rotating level counters of the first global relabel
     uint32_t relabels_since;
     uint32_t comp;
     unsigned long long pushes, relabels;
@@ -221,6 +223,89 @@ __device__ uint32_t mf_global_relabel(const MfGraph& G, uint32_t lo, uint32_t hi
     return level;
 }
 
+// The FIRST global relabel of a component.  No flow exists yet (f = 0, g = 0), every bundle arc
+// is residual and there are no reverse arcs, all labels are still kLabelInf (k_node_finalize): the
+// reverse BFS needs only the in-CSR ranges and the start node of every in-arc (in_src).  A level's
+// critical path is node range -> in_src -> CAS (three dependent memory trips instead of five), the
+// CAS on the right neighbour is in flight meanwhile, the label snapshot is written as nodes are
+// labelled, and three rotating level counters leave ONE barrier per level.  Labels are exact BFS
+// distances, so they equal what mf_global_relabel computes (and the oracle's replay).
+template <int THREADS, uint32_t QCAP>
+__device__ uint32_t mf_first_relabel(const MfGraph& G, uint32_t lo, uint32_t hi, Queue<QCAP> T,
+                                     Queue<QCAP> N, Queue<QCAP> H, MfShared<QCAP>& sh,
+                                     unsigned long long& bfs_levels) {
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) {
+        sh.lc[0] = 0;
+        sh.lc[1] = 0;
+        sh.lc[2] = 0;
+        sh.nH = 0;
+    }
+    __syncthreads();
+    for (uint32_t v = lo + tid; v <= hi; v += THREADS) {
+        if ((int32_t)ld_u32(reinterpret_cast<const uint32_t*>(&G.node[v].snk)) > 0) {
+            G.node[v].d = 1u;
+            G.d_snap[v] = 1u;
+            q_append(T, &sh.lc[0], v);
+        }
+    }
+    __syncthreads();
+    uint32_t level = 1;
+    for (;;) {
+        const uint32_t cnt = sh.lc[(level - 1) % 3];
+        if (cnt == 0) break;
+        ++bfs_levels;
+        const uint32_t nl = level + 1;
+        uint32_t* nxt = &sh.lc[level % 3];
+        if (tid == 0) sh.lc[(level + 1) % 3] = 0;  // last level's counter: everyone has read it
+        auto label = [&](uint32_t u) {
+            G.d_snap[u] = nl;
+            q_append(N, nxt, u);
+        };
+        for (uint32_t i = tid; i < cnt; i += THREADS) {
+            const uint32_t w = T.get(i);
+            const uint32_t in_lo = ld_u32(&G.node[w].in_ptr), in_hi = ld_u32(&G.node[w + 1].in_ptr);
+            uint32_t old_r = 0;
+            if (w < hi) old_r = atomicCAS(&G.node[w + 1].d, kLabelInf, nl);  // back arc (w+1) -> w
+            if (in_hi - in_lo > kHeavyDeg) {
+                q_append(H, &sh.nH, w);
+            } else {
+                for (uint32_t k = in_lo; k < in_hi; ++k) {
+                    const uint32_t s = ld_u32(&G.in_src[k]);
+                    if (atomicCAS(&G.node[s].d, kLabelInf, nl) == kLabelInf) label(s);
+                }
+            }
+            if (w < hi && old_r == kLabelInf) label(w + 1);
+        }
+        __syncthreads();
+        if (sh.nH) {  // uniform: in-arcs of heavy nodes, one warp each
+            const uint32_t nH = sh.nH, lane = lane_id();
+            for (uint32_t h = tid >> 5; h < nH; h += THREADS / 32) {
+                const uint32_t w = H.get(h);
+                const uint32_t in_lo = ld_u32(&G.node[w].in_ptr), in_hi = ld_u32(&G.node[w + 1].in_ptr);
+                for (uint32_t k = in_lo + lane; k < in_hi; k += 32) {
+                    const uint32_t s = ld_u32(&G.in_src[k]);
+                    if (atomicCAS(&G.node[s].d, kLabelInf, nl) == kLabelInf) label(s);
+                }
+            }
+            __syncthreads();
+            if (tid == 0) sh.nH = 0;
+            __syncthreads();
+        }
+        Queue<QCAP> tmp = T;
+        T = N;
+        N = tmp;
+        ++level;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        sh.nT = 0;
+        sh.nN = 0;
+    }
+    __syncthreads();
+    return level;
+}
+
 template <int THREADS, uint32_t QCAP, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __restrict__ comp_hi,
@@ -251,9 +336,10 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
         const long long t_begin = clock64();
         unsigned long long my_pushes = 0, my_relabels = 0;
         long long my_sink = 0, my_stuck = 0;
-        long long tparts[3];
-        uint32_t last_levels =
-            mf_global_relabel<THREADS, QCAP>(G, lo, hi, T, N, H, sh, bfs_levels, tparts);
+        long long tparts[3] = {0, 0, 0};
+        const long long t_gr = clock64();
+        uint32_t last_levels = mf_first_relabel<THREADS, QCAP>(G, lo, hi, T, N, H, sh, bfs_levels);
+        tparts[1] = clock64() - t_gr;
         const long long t_front = clock64();
         for (uint32_t v = lo + tid; v <= hi; v += THREADS) {
             if ((int32_t)ld_u32(reinterpret_cast<const uint32_t*>(&G.node[v].e)) > 0) {
