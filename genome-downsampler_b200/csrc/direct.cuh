@@ -269,8 +269,12 @@ k_direct_classify(const BundleRec* __restrict__ bund, const uint32_t* __restrict
 // slots busy): the codes are expanded to one BYTE per key in shared memory (one LDS per read),
 // indices are 32-bit offsets from the part start, and nothing is re-validated (K2 already failed
 // the call on any bad read).
-constexpr int kDmUnroll = 4;                                    // 512 reads per warp and round
-constexpr uint32_t kDmQueue = 640;                              // entries per warp
+// ncu of the second version: issue slots 50 % busy, long-scoreboard stalls — with 64 KB of loads
+// in flight per SM the kernel sat at 3.5 TB/s where the histogram (128 KB in flight) reaches 6.4;
+// hence 8 x 16 B per thread and a queue that no longer has to hold a whole round (a hit that
+// finds it full takes the slow chain inline; only adversarial inputs get there).
+constexpr int kDmUnroll = 8;                                    // 1024 reads per warp and round
+constexpr uint32_t kDmQueue = 256;                              // entries per warp
 constexpr uint32_t kDmQueueBytes = (kDmThreads / 32) * kDmQueue * 8;
 
 template <bool ONE_LEN>
@@ -290,6 +294,7 @@ k_direct_mark(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, Di
     if (ctl[2]) return;
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = threadIdx.x >> 5;
     const uint32_t nlen = dl.nlen, minlen = dl.minlen;
+    constexpr int kU = ONE_LEN ? kDmUnroll : kDmUnroll / 2;  // two columns: half the rounds' depth
     uint32_t kept = 0;
     if (lane == 0) wcnt[warp] = 0;
     __syncwarp();
@@ -323,9 +328,14 @@ k_direct_mark(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, Di
             return min(key, kk - 1);  // in range on validated input; never read past the table
         };
         // converged warp: hand the parked reads to their bundles' candidate segments
+        auto park = [&](uint32_t key, uint32_t g) {
+            const uint32_t pid = ghist[kb + key];
+            const uint32_t pos = atomicAdd(&pb_fill[pid], 1u);
+            cand[pb_off[pid] + pos] = g;
+        };
         auto drain = [&](uint32_t min_pending) {
             __syncwarp();
-            const uint32_t n = wcnt[warp];
+            const uint32_t n = min(wcnt[warp], kDmQueue);
             if (n <= min_pending) return;
             for (uint32_t i = lane; i < n; i += 32) {
                 const uint2 q = wq[i];
@@ -339,7 +349,11 @@ k_direct_mark(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, Di
         };
         // rare path: some read of the group carries a key with flow
         auto hit = [&](uint64_t g, uint32_t key, uint32_t code) -> uint32_t {
-            if (code == kPartCode) wq[atomicAdd(&wcnt[warp], 1u)] = make_uint2(key, (uint32_t)g);
+            if (code == kPartCode) {
+                const uint32_t slot = atomicAdd(&wcnt[warp], 1u);
+                if (slot < kDmQueue) wq[slot] = make_uint2(key, (uint32_t)g);
+                else park(key, (uint32_t)g);  // queue full: take the chain now
+            }
             return code == kSatCode ? 1u : 0u;
         };
         if (a < b) {
@@ -374,11 +388,10 @@ k_direct_mark(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, Di
             // the trip count is the same for every lane of a warp (the drain needs the warp
             // converged): lanes past the end process nothing
             const uint32_t jend = (uint32_t)((b4 - a4) / 4);
-            constexpr uint32_t kRound = 32 * 4 * kDmUnroll;  // reads one warp parks at most per round
-            for (uint32_t jw = warp * 32; jw < jend; jw += kDmUnroll * kDmThreads) {
-                uint4 s[kDmUnroll], e[kDmUnroll];
+            for (uint32_t jw = warp * 32; jw < jend; jw += kU * kDmThreads) {
+                uint4 s[kU], e[kU];
 #pragma unroll
-                for (int u = 0; u < kDmUnroll; ++u) {
+                for (int u = 0; u < kU; ++u) {
                     const uint32_t j = jw + lane + u * kDmThreads;
                     if (j < jend) {
                         s[u] = ld_stream4(S4 + j);
@@ -386,11 +399,11 @@ k_direct_mark(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, Di
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < kDmUnroll; ++u) {
+                for (int u = 0; u < kU; ++u) {
                     const uint32_t j = jw + lane + u * kDmThreads;
                     if (j < jend) mark4(j, s[u], e[u]);
                 }
-                drain(kDmQueue - kRound);
+                drain(kDmQueue / 2);
             }
         }
         drain(0);  // the next part may belong to another sample

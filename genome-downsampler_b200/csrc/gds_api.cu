@@ -580,7 +580,7 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         sp.gr_relabel_pct = prm->gr_relabel_pct;
         sp.max_rounds = prm->max_rounds;
     }
-    const uint32_t seg_len = (prm && prm->seg_len) ? prm->seg_len : 32768u;
+    const uint32_t seg_len = (prm && prm->seg_len) ? prm->seg_len : 16384u;
     // scalars of the result start clean (buffers are left alone)
     {
         gds_result keep = *out;
@@ -788,7 +788,8 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
                 v.obase = base[k];
                 v.vbase = (uint32_t)vb;
                 v.L = rd->ref_len[k];
-                v.nseg = v.L > seg ? (uint32_t)(((uint64_t)v.L + seg - 1) / seg) : 1;
+                // only references longer than two segments are cut (a 30 kb sample stays whole)
+                v.nseg = (uint64_t)v.L > 2ull * seg ? (uint32_t)(((uint64_t)v.L + seg - 1) / seg) : 1;
                 v.P = v.nseg > 1 ? maxlen - 1 : 0;
                 v.W = v.nseg > 1 ? v.P + seg + 1 : 0;
                 uint64_t vn = v.nseg == 1 ? (uint64_t)v.L + 1

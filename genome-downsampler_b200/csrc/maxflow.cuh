@@ -127,33 +127,41 @@ __device__ __forceinline__ uint32_t warp_excl_sum(uint32_t v, uint32_t& total) {
     return incl - v;
 }
 
-// reverse BFS from the sink; T/N are used as the level queues.  returns the level counter
+// reverse BFS from the sink; T/N are used as the level queues.  returns the level counter.
+// Three rotating level counters (this level / next level / being reset) leave one barrier per
+// level; the label snapshot is written when a node is labelled.
 template <int THREADS, uint32_t QCAP>
 __device__ uint32_t mf_global_relabel(const MfGraph& G, uint32_t lo, uint32_t hi, Queue<QCAP> T,
                                       Queue<QCAP> N, Queue<QCAP> H, MfShared<QCAP>& sh,
-                                      unsigned long long& bfs_levels, long long* tparts = nullptr) {
+                                      unsigned long long& bfs_levels) {
     const uint32_t tid = threadIdx.x;
-    const long long tp0 = clock64();
     if (tid == 0) {
-        sh.nT = 0;
-        sh.nN = 0;
+        sh.lc[0] = 0;
+        sh.lc[1] = 0;
+        sh.lc[2] = 0;
         sh.nH = 0;
     }
     __syncthreads();
     for (uint32_t v = lo + tid; v <= hi; v += THREADS) {
         const bool is_sink = (int32_t)ld_u32(reinterpret_cast<const uint32_t*>(&G.node[v].snk)) > 0;
         G.node[v].d = is_sink ? 1u : kLabelInf;
-        if (is_sink) q_append(T, &sh.nT, v);
+        G.d_snap[v] = is_sink ? 1u : kLabelInf;
+        if (is_sink) q_append(T, &sh.lc[0], v);
     }
     __syncthreads();
-    const long long tp1 = clock64();
     uint32_t level = 1;
-    uint32_t cnt = sh.nT;
-    while (cnt > 0) {
+    for (;;) {
+        const uint32_t cnt = sh.lc[(level - 1) % 3];
+        if (cnt == 0) break;
         ++bfs_levels;
         const uint32_t nl = level + 1;
+        uint32_t* nxt = &sh.lc[level % 3];
+        if (tid == 0) sh.lc[(level + 1) % 3] = 0;  // last level's counter: everyone has read it
         auto visit = [&](uint32_t u) {
-            if (atomicCAS(&G.node[u].d, kLabelInf, nl) == kLabelInf) q_append(N, &sh.nN, u);
+            if (atomicCAS(&G.node[u].d, kLabelInf, nl) == kLabelInf) {
+                G.d_snap[u] = nl;
+                q_append(N, nxt, u);
+            }
         };
         for (uint32_t i = tid; i < cnt; i += THREADS) {
             const uint32_t w = T.get(i);
@@ -194,32 +202,19 @@ __device__ uint32_t mf_global_relabel(const MfGraph& G, uint32_t lo, uint32_t hi
             }
             __syncthreads();
             if (tid == 0) sh.nH = 0;
-        }
-        __syncthreads();
-        cnt = sh.nN;
-        __syncthreads();
-        if (tid == 0) {
-            sh.nT = cnt;
-            sh.nN = 0;
+            __syncthreads();
         }
         Queue<QCAP> tmp = T;
         T = N;
         N = tmp;
         ++level;
-        __syncthreads();
     }
-    const long long tp2 = clock64();
-    for (uint32_t v = lo + tid; v <= hi; v += THREADS) G.d_snap[v] = ld_u32(&G.node[v].d);
+    __syncthreads();
     if (tid == 0) {
         sh.nT = 0;
         sh.nN = 0;
     }
     __syncthreads();
-    if (tparts) {
-        tparts[0] = tp1 - tp0;
-        tparts[1] = tp2 - tp1;
-        tparts[2] = clock64() - tp2;
-    }
     return level;
 }
 

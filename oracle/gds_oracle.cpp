@@ -553,7 +553,7 @@ struct SyncGraph {
     std::vector<uint32_t> comp_lo, comp_hi;
 };
 
-constexpr uint32_t kDefaultSegLen = 32768;
+constexpr uint32_t kDefaultSegLen = 16384;
 
 // Long references are cut into segments of seg positions (a generalisation of the zero-coverage
 // split): a read crossing a cut becomes two arcs, truncated at the cut node, one
@@ -588,7 +588,8 @@ int build_sync_graph(uint32_t n_samples, const uint64_t* read_off, const uint32_
         v.obase = ob;
         v.vbase = vb;
         v.L = ref_len[k];
-        v.nseg = v.L > seg ? (v.L + seg - 1) / seg : 1;
+        // only references longer than two segments are cut (a 30 kb sample stays whole)
+        v.nseg = (uint64_t)v.L > 2ull * seg ? (uint32_t)(((uint64_t)v.L + seg - 1) / seg) : 1;
         v.P = v.nseg > 1 ? maxlen - 1 : 0;
         v.W = v.nseg > 1 ? v.P + seg + 1 : 0;
         v.vn = v.nseg == 1 ? v.L + 1 : (v.nseg - 1) * v.W + v.P + (v.L - (v.nseg - 1) * seg) + 1;

@@ -82,7 +82,7 @@ typedef struct {
     uint32_t gr_levels_pct;   /* ... and at least this % of the last BFS depth */
     uint32_t gr_relabel_pct;  /* trigger when relabels since last GR >= pct% of component nodes */
     uint32_t max_rounds;      /* safety stop (0 = unlimited) */
-    uint32_t seg_len;         /* cut references longer than this into segments (0 = 32768) */
+    uint32_t seg_len;         /* segment length: references longer than 2*seg_len are cut (0 = 16384) */
 } orc_sync_params;
 typedef struct {
     int64_t flow_value; /* total sink inflow over all components */

@@ -262,9 +262,9 @@ def test_c4_full_size_properties(solver, O):
     assert r.fstar == 500 == r.flow_value and r.verify_violations == 0
     assert int(np.maximum(0, -r.demand.astype(np.int64)).sum()) == 500
     assert int(r.demand.astype(np.int64).sum()) == 0
-    # ~ M*L/R (the minimum) plus at most M reads per segment cut (152 cuts of 32768 positions)
-    assert 0 <= r.n_kept - 500 * 5_000_000 / 150 < 1000 + 152 * 500
-    assert r.n_components == 153
+    # ~ M*L/R (the minimum) plus at most M reads per segment cut (305 cuts of 16384 positions)
+    assert 0 <= r.n_kept - 500 * 5_000_000 / 150 < 1000 + 305 * 500
+    assert r.n_components == 306
     mask_bits = int(np.unpackbits(r.kept_bitmap.view(np.uint8)).sum())
     assert mask_bits == r.n_kept
     bm, st = O.sync_solve(s, e, [5_000_000], [0, len(s)], 500, params=PRM)
