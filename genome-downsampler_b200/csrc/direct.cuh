@@ -3,7 +3,7 @@
 //
 // A bundle is the set of reads with one (start node, length) key (graph.cuh).  When a sample has
 // at most kDirectMaxKeys possible keys (ref_len x #lengths: 30 000 for a 30 kb reference with
-// fixed-length reads, BASELINE configs 0/2/4), its bundle multiplicities are a HISTOGRAM of the
+// fixed-length reads: configs 1, 3, 5 of SURVEY §8), its bundle multiplicities are a HISTOGRAM of the
 // reads: one shared-memory atomic per read, every input byte read exactly once at HBM speed
 // (tools/hist_probe.cu: 7.0 TB/s on B200 — the atomic unit keeps up with the loads), instead of
 // the two-pass radix sort's 48 bytes per read.  Restates the same network as the sort path
