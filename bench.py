@@ -10,7 +10,8 @@ Workloads (BASELINE.json `configs`):
   c5 (default)  config[4]: batch of independent 30 kb samples, 2 M reads each
                 (reads-gen uniform law, mt19937 seed 12345+k, R=150), MAX_COVERAGE=100.
                 512 samples per GPU; ranks own disjoint sample blocks, no data-path collective,
-                per-sample bitmaps all-gathered over NCCL at the end of every step (weak scaling).
+                per-sample bitmaps all-gathered over NCCL at the end of every step (weak scaling;
+                the gather of step i overlaps the kernels of step i+1, double-buffered).
   c2            config[1]: 10 M reads over 30 kb with the device pair filter (-l 90 -q 30 + ARTIC-style
                 amplicons); `value` counts PRE-filter reads.
   c4            config[3]: 50 M reads over one 5 Mb reference, MAX_COVERAGE=500 (single GPU; N>1
@@ -401,9 +402,25 @@ def run_b200(args, wl, wname):
                         pair_pass_ptr=pair_pass.data_ptr())
         bitmap = torch.zeros(words + 4, dtype=torch.int32, device=dev)
         h_bitmap = torch.empty(words, dtype=torch.int32, pin_memory=True)
-        gathered = None
+        # N > 1: every step ends with an NCCL all-gather of the ranks' kept bitmaps.  Two bitmap /
+        # gather buffers alternate so that the gather of step i (NCCL's own stream) runs under the
+        # kernels of step i+1; the timed region ends only when the last gather has landed.
+        gathered = bitmaps2 = None
+        pending = [None, None]
+        step_no = [0]
         if world > 1:
-            gathered = torch.empty(world * words, dtype=torch.int32, device=dev)
+            gathered = [torch.empty(world * words, dtype=torch.int32, device=dev) for _ in range(2)]
+            bitmaps2 = [bitmap, torch.zeros(words + 4, dtype=torch.int32, device=dev)]
+
+        def gather_async(buf_idx):
+            pending[buf_idx] = dist.all_gather_into_tensor(gathered[buf_idx],
+                                                           bitmaps2[buf_idx][:words], async_op=True)
+
+        def gather_wait(buf_idx=None):
+            for i in ([buf_idx] if buf_idx is not None else [0, 1]):
+                if pending[i] is not None:
+                    pending[i].wait()   # stream-level wait, the host does not block
+                    pending[i] = None
         stream.synchronize()
 
         # exact read-length bounds, as the C++ adapter passes them (it gets them for free while
@@ -411,11 +428,16 @@ def run_b200(args, wl, wname):
         hint = (wl["R"], wl["R"]) if fx is None else None  # config 2 has variable lengths
 
         def step_device(profile):
+            b = step_no[0] % 2 if world > 1 else 0
+            step_no[0] += 1
+            if world > 1:
+                gather_wait(b)  # the gather that read this buffer two steps ago
+            out_bm = bitmaps2[b] if world > 1 else bitmap
             r = solver.solve_device(d_st.data_ptr(), d_en.data_ptr(), n, ref_len, wl["M"],
-                                    bitmap.data_ptr(), read_off=read_off, profile=profile,
+                                    out_bm.data_ptr(), read_off=read_off, profile=profile,
                                     len_hint=hint, **fkw(True))
             if world > 1:
-                dist.all_gather_into_tensor(gathered, bitmap[:words])
+                gather_async(b)
             return r
 
         # e2e: host buffers in, kept bitmap back on the host.  A batch of many samples goes through
@@ -455,7 +477,8 @@ def run_b200(args, wl, wname):
                 if fx is not None:
                     h_pair_pass.copy_(pair_pass, non_blocking=True)
             if world > 1:
-                dist.all_gather_into_tensor(gathered, bitmap[:words])
+                gather_wait()
+                dist.all_gather_into_tensor(gathered[0], bitmap[:words])
             h_bitmap.copy_(bitmap[:words], non_blocking=True)
             stream.synchronize()
             return r
@@ -493,6 +516,7 @@ def run_b200(args, wl, wname):
             for _ in range(args.steps):
                 last = step_fn()
                 launches += int(last.kernel_launches)
+            gather_wait()  # N > 1: the stream waits for the gathers still in flight
             e1.record(stream)
             barrier()
             sampler.stop()

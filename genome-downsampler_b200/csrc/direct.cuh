@@ -269,11 +269,12 @@ k_direct_classify(const BundleRec* __restrict__ bund, const uint32_t* __restrict
 // slots busy): the codes are expanded to one BYTE per key in shared memory (one LDS per read),
 // indices are 32-bit offsets from the part start, and nothing is re-validated (K2 already failed
 // the call on any bad read).
-// ncu of the second version: issue slots 50 % busy, long-scoreboard stalls — with 64 KB of loads
-// in flight per SM the kernel sat at 3.5 TB/s where the histogram (128 KB in flight) reaches 6.4;
-// hence 8 x 16 B per thread and a queue that no longer has to hold a whole round (a hit that
-// finds it full takes the slow chain inline; only adversarial inputs get there).
-constexpr int kDmUnroll = 8;                                    // 1024 reads per warp and round
+// ncu of the second version: issue slots 50 % busy, long-scoreboard stalls, 3.6 TB/s.  Neither
+// doubling the loads in flight (8 x 16 B per thread: 1.24 -> 1.21 ms) nor draining 4 x 32 entries
+// per chain of dependent accesses (1.21 -> 1.39 ms, register pressure) helped; what remains is the
+// scattered traffic of 20 M candidates.  The queue does not have to hold a whole round: a hit that
+// finds it full takes the slow chain inline (only adversarial inputs get there).
+constexpr int kDmUnroll = 4;                                    // 512 reads per warp and round
 constexpr uint32_t kDmQueue = 256;                              // entries per warp
 constexpr uint32_t kDmQueueBytes = (kDmThreads / 32) * kDmQueue * 8;
 
@@ -294,7 +295,7 @@ k_direct_mark(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, Di
     if (ctl[2]) return;
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = threadIdx.x >> 5;
     const uint32_t nlen = dl.nlen, minlen = dl.minlen;
-    constexpr int kU = ONE_LEN ? kDmUnroll : kDmUnroll / 2;  // two columns: half the rounds' depth
+    constexpr int kU = kDmUnroll;
     uint32_t kept = 0;
     if (lane == 0) wcnt[warp] = 0;
     __syncwarp();
@@ -339,9 +340,7 @@ k_direct_mark(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, Di
             if (n <= min_pending) return;
             for (uint32_t i = lane; i < n; i += 32) {
                 const uint2 q = wq[i];
-                const uint32_t pid = ghist[kb + q.x];
-                const uint32_t pos = atomicAdd(&pb_fill[pid], 1u);
-                cand[pb_off[pid] + pos] = q.y;
+                park(q.x, q.y);
             }
             __syncwarp();
             if (lane == 0) wcnt[warp] = 0;
