@@ -133,7 +133,7 @@ __device__ __forceinline__ uint32_t warp_excl_sum(uint32_t v, uint32_t& total) {
 template <int THREADS, uint32_t QCAP>
 __device__ uint32_t mf_global_relabel(const MfGraph& G, uint32_t lo, uint32_t hi, Queue<QCAP> T,
                                       Queue<QCAP> N, Queue<QCAP> H, MfShared<QCAP>& sh,
-                                      unsigned long long& bfs_levels) {
+                                      unsigned long long& bfs_levels, bool warp_mode) {
     const uint32_t tid = threadIdx.x;
     if (tid == 0) {
         sh.lc[0] = 0;
@@ -163,7 +163,7 @@ __device__ uint32_t mf_global_relabel(const MfGraph& G, uint32_t lo, uint32_t hi
                 q_append(N, nxt, u);
             }
         };
-        for (uint32_t i = tid; i < cnt; i += THREADS) {
+        for (uint32_t i = tid; i < cnt && !warp_mode; i += THREADS) {
             const uint32_t w = T.get(i);
             uint4 lo4, hi4;
             ld_node(&G.node[w], lo4, hi4);
@@ -184,13 +184,18 @@ __device__ uint32_t mf_global_relabel(const MfGraph& G, uint32_t lo, uint32_t hi
                 if (r.z > 0) visit(r.x);
             }
         }
-        __syncthreads();
-        if (sh.nH) {  // uniform
-            const uint32_t nH = sh.nH, lane = lane_id();
+        if (!warp_mode) __syncthreads();
+        const uint32_t nH = warp_mode ? cnt : sh.nH;  // uniform
+        if (nH) {
+            const uint32_t lane = lane_id();
             for (uint32_t h = tid >> 5; h < nH; h += THREADS / 32) {
-                const uint32_t w = H.get(h);
+                const uint32_t w = warp_mode ? T.get(h) : H.get(h);
                 const uint4 hi4 = GDS_MF_LD(reinterpret_cast<const uint4*>(&G.node[w]) + 1);
                 const uint4 nx_hi = GDS_MF_LD(reinterpret_cast<const uint4*>(&G.node[w + 1]) + 1);
+                if (warp_mode && lane == 0) {  // the thread pass was skipped: neighbours here
+                    if (w < hi) visit(w + 1);
+                    if (w > lo && (int32_t)hi4.y > 0) visit(w - 1);
+                }
                 for (uint32_t k = hi4.w + lane; k < nx_hi.w; k += 32) {
                     const uint4 b = ld_bundle(&G.bund[ld_u32(&G.in_bid[k])]);
                     if (b.z < b.y) visit(b.w);
@@ -201,8 +206,10 @@ __device__ uint32_t mf_global_relabel(const MfGraph& G, uint32_t lo, uint32_t hi
                 }
             }
             __syncthreads();
-            if (tid == 0) sh.nH = 0;
-            __syncthreads();
+            if (!warp_mode) {
+                if (tid == 0) sh.nH = 0;
+                __syncthreads();
+            }
         }
         Queue<QCAP> tmp = T;
         T = N;
@@ -228,7 +235,7 @@ __device__ uint32_t mf_global_relabel(const MfGraph& G, uint32_t lo, uint32_t hi
 template <int THREADS, uint32_t QCAP>
 __device__ uint32_t mf_first_relabel(const MfGraph& G, uint32_t lo, uint32_t hi, Queue<QCAP> T,
                                      Queue<QCAP> N, Queue<QCAP> H, MfShared<QCAP>& sh,
-                                     unsigned long long& bfs_levels) {
+                                     unsigned long long& bfs_levels, bool warp_mode) {
     const uint32_t tid = threadIdx.x;
     if (tid == 0) {
         sh.lc[0] = 0;
@@ -257,7 +264,7 @@ __device__ uint32_t mf_first_relabel(const MfGraph& G, uint32_t lo, uint32_t hi,
             G.d_snap[u] = nl;
             q_append(N, nxt, u);
         };
-        for (uint32_t i = tid; i < cnt; i += THREADS) {
+        for (uint32_t i = tid; i < cnt && !warp_mode; i += THREADS) {
             const uint32_t w = T.get(i);
             const uint32_t in_lo = ld_u32(&G.node[w].in_ptr), in_hi = ld_u32(&G.node[w + 1].in_ptr);
             uint32_t old_r = 0;
@@ -272,20 +279,26 @@ __device__ uint32_t mf_first_relabel(const MfGraph& G, uint32_t lo, uint32_t hi,
             }
             if (w < hi && old_r == kLabelInf) label(w + 1);
         }
-        __syncthreads();
-        if (sh.nH) {  // uniform: in-arcs of heavy nodes, one warp each
-            const uint32_t nH = sh.nH, lane = lane_id();
+        if (!warp_mode) __syncthreads();
+        const uint32_t nH = warp_mode ? cnt : sh.nH;  // uniform
+        if (nH) {  // in-arcs of heavy nodes (warp mode: of every node), one warp each
+            const uint32_t lane = lane_id();
             for (uint32_t h = tid >> 5; h < nH; h += THREADS / 32) {
-                const uint32_t w = H.get(h);
+                const uint32_t w = warp_mode ? T.get(h) : H.get(h);
                 const uint32_t in_lo = ld_u32(&G.node[w].in_ptr), in_hi = ld_u32(&G.node[w + 1].in_ptr);
+                if (warp_mode && lane == 0 && w < hi &&
+                    atomicCAS(&G.node[w + 1].d, kLabelInf, nl) == kLabelInf)
+                    label(w + 1);
                 for (uint32_t k = in_lo + lane; k < in_hi; k += 32) {
                     const uint32_t s = ld_u32(&G.in_src[k]);
                     if (atomicCAS(&G.node[s].d, kLabelInf, nl) == kLabelInf) label(s);
                 }
             }
             __syncthreads();
-            if (tid == 0) sh.nH = 0;
-            __syncthreads();
+            if (!warp_mode) {
+                if (tid == 0) sh.nH = 0;
+                __syncthreads();
+            }
         }
         Queue<QCAP> tmp = T;
         T = N;
@@ -331,9 +344,17 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
         const long long t_begin = clock64();
         unsigned long long my_pushes = 0, my_relabels = 0;
         long long my_sink = 0, my_stuck = 0;
+        // Components whose nodes are mostly "heavy" (variable read lengths: tens of bundles per
+        // node) skip the per-thread passes: every frontier node goes straight to a warp, one pass
+        // and two barriers fewer per phase.  Same schedule (the warp pass is the thread pass's
+        // arithmetic spread over lanes).
+        const bool warp_mode =
+            2ull * (ld_u32(&G.node[hi + 1].out_ptr) - ld_u32(&G.node[lo].out_ptr)) >
+            (unsigned long long)kHeavyDeg * ncomp;
         long long tparts[3] = {0, 0, 0};
         const long long t_gr = clock64();
-        uint32_t last_levels = mf_first_relabel<THREADS, QCAP>(G, lo, hi, T, N, H, sh, bfs_levels);
+        uint32_t last_levels =
+            mf_first_relabel<THREADS, QCAP>(G, lo, hi, T, N, H, sh, bfs_levels, warp_mode);
         tparts[1] = clock64() - t_gr;
         const long long t_front = clock64();
         for (uint32_t v = lo + tid; v <= hi; v += THREADS) {
@@ -356,7 +377,8 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
                 (unsigned long long)sh.relabels_since * 100 >=
                     (unsigned long long)P.gr_relabel_pct * ncomp) {
                 __syncthreads();  // everyone has read relabels_since
-                last_levels = mf_global_relabel<THREADS, QCAP>(G, lo, hi, T, N, H, sh, bfs_levels);
+                last_levels =
+                    mf_global_relabel<THREADS, QCAP>(G, lo, hi, T, N, H, sh, bfs_levels, warp_mode);
                 ++grs;
                 if (tid == 0) sh.relabels_since = 0;
                 rounds_since = 0;
@@ -372,7 +394,7 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
             // Labels and stamps are constant during this phase (only phase B writes them); a bundle
             // flow or a back-arc flow is written only by the one node whose push/cancel is
             // admissible this round (the two directions exclude each other by their labels).
-            for (uint32_t i = tid; i < cntF; i += THREADS) {
+            for (uint32_t i = tid; i < cntF && !warp_mode; i += THREADS) {
                 const uint32_t v = F.get(i);
                 uint4 lo4, hi4, r_lo, r_hi;
                 ld_node(&G.node[v], lo4, hi4);
@@ -454,17 +476,22 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
                 }
                 G.node[v].e = ex;
             }
-            __syncthreads();
-            if (sh.nH) {  // ---- heavy nodes, one warp each (uniform branch)
-                const uint32_t nH = sh.nH, lane = lane_id();
+            if (!warp_mode) __syncthreads();
+            const uint32_t nHA = warp_mode ? cntF : sh.nH;  // uniform
+            if (nHA) {  // ---- heavy nodes (warp mode: the whole frontier), one warp each
+                const uint32_t nH = nHA, lane = lane_id();
                 for (uint32_t h = tid >> 5; h < nH; h += THREADS / 32) {
-                    const uint32_t v = H.get(h);
+                    const uint32_t v = warp_mode ? F.get(h) : H.get(h);
                     uint4 lo4, hi4, r_lo, r_hi;  // every lane loads the same sectors (broadcast)
                     ld_node(&G.node[v], lo4, hi4);
                     ld_node(&G.node[v + 1], r_lo, r_hi);
                     const uint4 l_lo = v > lo ? GDS_MF_LD(reinterpret_cast<const uint4*>(&G.node[v - 1]))
                                               : make_uint4(kLabelInf, 0, 0, 0);
                     const uint32_t dv = lo4.x;
+                    if (warp_mode) {  // what the skipped thread pass does first
+                        if (lane == 0) G.d_snap[v] = dv;
+                        if (dv >= kLabelInf) continue;
+                    }
                     int32_t ex = (int32_t)lo4.z;  // uniform across the warp throughout
                     auto give = [&](uint32_t w, int32_t dl, uint32_t w_stamp) {
                         const int32_t old = atomicAdd(&G.node[w].eadd, dl);
@@ -557,8 +584,10 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
                     if (lane == 0) G.node[v].e = ex;
                 }
                 __syncthreads();
-                if (tid == 0) sh.nH = 0;
-                __syncthreads();
+                if (!warp_mode) {
+                    if (tid == 0) sh.nH = 0;
+                    __syncthreads();
+                }
             }
             const uint32_t cntT = sh.nT;
 
