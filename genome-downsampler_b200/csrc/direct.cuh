@@ -198,8 +198,13 @@ k_direct_bundles(const uint32_t* __restrict__ ghist, uint32_t ktot, DirectLayout
         if (in_bid) in_bid[b] = b;
         atomicAdd(&diff[s], (int32_t)mult);
         atomicAdd(&diff[t], -(int32_t)mult);
-        atomicAdd(&outdeg[s], 1u);
-        atomicAdd(&indeg[t], 1u);
+        if (in_bid) {  // one read length: at most one bundle starts / ends at a node
+            outdeg[s] = 1u;
+            indeg[t] = 1u;
+        } else {
+            atomicAdd(&outdeg[s], 1u);
+            atomicAdd(&indeg[t], 1u);
+        }
         ++b;
     }
 }

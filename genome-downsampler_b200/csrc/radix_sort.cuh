@@ -121,7 +121,9 @@ k_rs_hist(KS ks, TileMap tm, int shift, uint32_t* __restrict__ tile_hist) {
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         uint32_t j = (uint32_t)k * kRsThreads + threadIdx.x;
-        K key = ks.make(raw[k], tp.first + j);
+        // lanes past the tile's end get the first item's index too: make() may index side arrays
+        // (the crossing-read list of the global key source) with it
+        K key = ks.make(raw[k], tp.first + (j < tp.n_valid ? j : 0u));
         if (j < tp.n_valid) {
             atomicAdd(&h[warp][(uint32_t)(key >> shift) & 255u], 1u);
             if (ks.checks()) bad += ks.check(raw[k], tp.group);
@@ -265,8 +267,11 @@ k_rs_scatter(KS ks, const uint32_t* __restrict__ vals_in, K* __restrict__ keys_o
             raw[k] = ks.load((full || wofs + jo < tp.n_valid) ? gfirst + jo : tp.first);
         }
 #pragma unroll
-        for (int k = 0; k < kHalf; ++k)
-            key[h * kHalf + k] = ks.make(raw[k], gfirst + (uint32_t)(h * kHalf + k) * 32);
+        for (int k = 0; k < kHalf; ++k) {
+            const uint32_t jo = (uint32_t)(h * kHalf + k) * 32;
+            key[h * kHalf + k] =
+                ks.make(raw[k], (full || wofs + jo < tp.n_valid) ? gfirst + jo : tp.first);
+        }
     }
     __syncthreads();  // whist zeroed
 

@@ -1,5 +1,7 @@
 """Randomised parity campaign (GPU vs oracle replay), wider than the pytest fuzz: batches, ragged and
-empty samples, variable lengths (heavy nodes), short segments, read-length hints, the pair filter.
+empty samples, variable lengths (heavy nodes), short segments, read-length hints, both bundle paths
+(radix sort / shared-memory histogram), both K5 variants of the histogram path (mark + partial
+ranking / ordered walk) and the compact transport (16-bit starts, implied ends).
 Run from the repo root on a GPU box:  python tools/gpu_fuzz.py [N_CASES] [SEED]"""
 import os
 import sys
@@ -41,12 +43,22 @@ def main():
         seg = int(rng.choice([0, 0, 37, 150, 1000, 0xffffffff]))
         prm = (int(rng.integers(1, 100)), int(rng.integers(0, 300)), int(rng.integers(0, 5)), 0, seg)
         hint = None
+        lens = e - s + 1
         if len(s) and rng.integers(0, 2):
-            lens = e - s + 1
             hint = (int(lens.min()), int(lens.max()))
+        bmode = int(rng.integers(0, 3))  # gds_params.bundle_mode: choose / sort / histogram
+        walk = bool(rng.integers(0, 4) == 0)
+        if walk:
+            os.environ["GDS_DIRECT_SELECT"] = "walk"
+        s_in, e_in = s, e
+        if len(s) and lens.min() == lens.max() and rng.integers(0, 2):  # compact transport
+            hint = (int(lens.min()), int(lens.max()))
+            e_in = None
+            if Ls.max() <= 65536 and rng.integers(0, 2):
+                s_in = s.astype(np.uint16)
         try:
-            r = solver.solve(s, e, Ls, M, read_off=off, params=prm, verify=True, want_vectors=True,
-                             len_hint=hint)
+            r = solver.solve(s_in, e_in, Ls, M, read_off=off, params=prm + (bmode,), verify=True,
+                             want_vectors=True, len_hint=hint)
             bm, st, dem, cov = O.sync_solve(s, e, Ls, off, M, params=prm, want_vectors=True)
             ok = (r.fstar == st.fstar == r.flow_value == st.flow_value and
                   np.array_equal(r.demand, dem) and np.array_equal(r.cov_capped, np.minimum(cov, M))
@@ -58,10 +70,13 @@ def main():
         except Exception as ex:  # noqa: BLE001
             ok = False
             print("case %d raised %r" % (it, ex))
+        finally:
+            os.environ.pop("GDS_DIRECT_SELECT", None)
         if not ok:
             bad += 1
-            print("MISMATCH case %d: ns=%d n=%d Ls=%s M=%d prm=%s hint=%s" %
-                  (it, ns, len(s), Ls.tolist(), M, prm, hint), flush=True)
+            print("MISMATCH case %d: ns=%d n=%d Ls=%s M=%d prm=%s hint=%s bundle_mode=%d walk=%s "
+                  "compact=%s" % (it, ns, len(s), Ls.tolist(), M, prm, hint, bmode, walk,
+                                  (e_in is None, s_in.dtype.name)), flush=True)
             if bad > 5:
                 break
     print("fuzz: %d cases, %d mismatches" % (it + 1, bad))
