@@ -598,7 +598,8 @@ def run_b200(args, wl, wname):
                    "n_components": int(r_last.n_components), "rounds_total": int(r_last.rounds_total),
                    "rounds_max": int(r_last.rounds_max), "bfs_levels": int(r_last.bfs_levels),
                    "sort_passes": int(r_last.sort_passes),
-                   "bundle_path": "direct histogram" if int(r_last.sort_passes) == 0 else "radix sort",
+                   "bundle_path": ["radix sort", "histogram in shared memory",
+                                   "histogram in global memory"][int(r_last.bundle_path)],
                    "partial_bundles": int(r_last.partial_bundles),
                    "partial_candidates": int(r_last.partial_candidates),
                    # K3 is latency-bound, not HBM-bound: its own figures (SURVEY §8d iii)

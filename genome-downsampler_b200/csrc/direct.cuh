@@ -220,9 +220,9 @@ k_direct_bundles(const uint32_t* __restrict__ ghist, uint32_t ktot, DirectLayout
 // k_direct_mark streams the reads once more (start only when there is one read length), in
 // parallel parts like the histogram: code 1 sets the kept bit, code 2 appends the read index to
 // the bundle's segment.  k_direct_partial then ranks each partial bundle's candidates (one warp per
-// bundle).  If the candidates do not fit the buffer or a partial bundle is huge (adversarial
-// input: millions of identical reads), ctl[2] is raised and the host runs the ordered walk below
-// instead — same kept set, one CTA per sample.
+// bundle; the host sizes the candidate buffer from ctl[1] between the two kernels).  If a partial
+// bundle is huge (adversarial input: millions of identical reads), ctl[2] is raised and the host
+// runs the ordered walk below instead — same kept set, one CTA per sample.
 constexpr uint32_t kSatCode = 1, kPartCode = 2;
 constexpr uint32_t kMaxPartialMult = 2048;  // candidates of one bundle ranked by one warp
 constexpr int kDmThreads = 1024;
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(256)
 k_direct_classify(const BundleRec* __restrict__ bund, const uint32_t* __restrict__ b_slot, uint32_t B,
                   uint32_t* __restrict__ ghist, uint32_t* __restrict__ kstat,
                   uint32_t* __restrict__ pb_off, uint32_t* __restrict__ pb_f,
-                  uint32_t* __restrict__ pb_fill, uint32_t* __restrict__ ctl, uint32_t cand_cap) {
+                  uint32_t* __restrict__ pb_fill, uint32_t* __restrict__ ctl, uint32_t max_mult) {
     __shared__ uint32_t tot_n, tot_m, base_n, base_m;
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t mult = 0, f = 0;
@@ -257,7 +257,7 @@ k_direct_classify(const BundleRec* __restrict__ bund, const uint32_t* __restrict
         code = kPartCode;
         const uint32_t pid = base_n + my_n;
         const uint32_t o = base_m + my_m;
-        if (mult > kMaxPartialMult || (unsigned long long)o + mult > cand_cap) ctl[2] = 1;
+        if (mult > max_mult) ctl[2] = 1;  // too many candidates for one warp: ordered walk instead
         pb_off[pid] = o;
         pb_f[pid] = f;
         pb_fill[pid] = 0;
@@ -417,9 +417,10 @@ k_direct_mark(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, Di
     if (lane == 0 && kept) atomicAdd(&totals[1], (unsigned long long)kept);
 }
 
-// One warp per partial bundle: keep the f lowest of its candidate read indices.  The f-th lowest
-// index is found by bisection on the index value (count = ballots over the candidates, which sit
-// in registers for bundles of up to 128 reads), ~21 steps instead of an all-pairs ranking.
+// One warp per partial bundle: keep the f lowest of its candidate read indices.  Up to 32
+// candidates (the common case; config 4 has 1.7 M partial bundles of ~10 reads) are ranked against
+// each other through shuffles, n steps; larger bundles find the f-th lowest index by bisection on
+// the index value (count = ballots over the candidates, in registers up to 128 of them).
 __global__ void __launch_bounds__(256)
 k_direct_partial(const uint32_t* __restrict__ pb_off, const uint32_t* __restrict__ pb_f,
                  const uint32_t* __restrict__ pb_fill, const uint32_t* __restrict__ cand,
@@ -430,10 +431,21 @@ k_direct_partial(const uint32_t* __restrict__ pb_off, const uint32_t* __restrict
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t lane = lane_id();
     uint32_t kept = 0;
+    auto keep = [&](uint32_t v) {  // a read cut in two by a segment cut can be chosen twice
+        const uint32_t bit = 1u << (v & 31);
+        kept += (atomicOr(&bitmap[v >> 5], bit) & bit) ? 0u : 1u;
+    };
     constexpr int kReg = 4;
     for (uint32_t pid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pid < n_partial; pid += warps) {
         const uint32_t* c = cand + pb_off[pid];
         const uint32_t n = pb_fill[pid], f = pb_f[pid];
+        if (n <= 32) {
+            const uint32_t x = lane < n ? c[lane] : 0xffffffffu;
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < n; ++j) rank += __shfl_sync(0xffffffffu, x, j) < x;
+            if (lane < n && rank < f) keep(x);
+            continue;
+        }
         uint32_t x[kReg];
         uint32_t mn = 0xffffffffu, mx = 0;
 #pragma unroll
@@ -462,10 +474,6 @@ k_direct_partial(const uint32_t* __restrict__ pb_off, const uint32_t* __restrict
             if (cnt >= f) hi = mid;
             else lo = mid + 1;
         }
-        auto keep = [&](uint32_t v) {
-            atomicOr(&bitmap[v >> 5], 1u << (v & 31));
-            ++kept;
-        };
 #pragma unroll
         for (int r = 0; r < kReg; ++r)
             if (x[r] <= lo) keep(x[r]);  // the padding value is above every index
@@ -606,6 +614,238 @@ k_direct_select(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, 
         }
         __syncthreads();
     }
+}
+
+
+// ---- the same idea with the histogram in global memory ------------------------------------------
+// When a sample's key space does not fit one SM (several read lengths: config 2) or the reference is
+// cut into segments (config 4), the counters live in global memory instead: up to kGDirectMaxKeys of
+// them (96 MB, resident in the 126 MB L2), one RED.ADD per read (tools/hist_probe.cu: 170 G keys/s)
+// and a second one for the right part of a read that crosses a segment cut.  Keys are the sort
+// path's keys, (virtual fake start id, length) — graph.cuh: ReadKeys / VLayout — so bundles come
+// out in the same order with the same clamping to the segment's node range.
+constexpr unsigned long long kGDirectMaxKeys = 24ull << 20;
+constexpr int kGdThreads = 256;
+constexpr int kGdItems = 8;
+constexpr int kGdTile = kGdThreads * kGdItems;
+
+struct GDirectLayout {
+    VLayout vl;
+    uint32_t nlen, minlen, maxlen;
+};
+
+// largest k with vs[k].vbase <= vid
+__device__ __forceinline__ uint32_t find_vsample(const VLayout& vl, uint32_t vid) {
+    uint32_t lo = 0, hi = vl.n_samples;
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (vl.vs[mid].vbase <= vid) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// per block: a tile of consecutive reads; sample lookups once per block when the tile lies in one
+// sample.  f(i, sample, start, end) is called for every read of the tile by the thread that owns it
+// (thread t owns reads base + q*256 + t: a warp covers 32 consecutive reads per q).
+template <typename F>
+__device__ __forceinline__ void gd_for_tile(const uint32_t* __restrict__ S,
+                                            const uint32_t* __restrict__ E, size_t n,
+                                            const VLayout& vl, F f) {
+    __shared__ uint32_t krange[2];
+    const size_t base = (size_t)blockIdx.x * kGdTile;
+    if (threadIdx.x == 0) {
+        const size_t last = min(base + kGdTile, n) - 1;
+        krange[0] = vl.n_samples == 1 ? 0 : find_sample(vl.off, vl.n_samples, base);
+        krange[1] = vl.n_samples == 1 ? 0 : find_sample(vl.off, vl.n_samples, last);
+    }
+    __syncthreads();
+    const uint32_t k0 = krange[0];
+    const bool one = k0 == krange[1];
+    const VSample v0 = vl.vs[k0];
+    uint32_t s[kGdItems], e[kGdItems];
+#pragma unroll
+    for (int q = 0; q < kGdItems; ++q) {
+        const size_t i = base + (size_t)q * kGdThreads + threadIdx.x;
+        const size_t ii = i < n ? i : base;
+        s[q] = ld_stream(S + ii);
+        e[q] = ld_stream(E + ii);
+    }
+#pragma unroll
+    for (int q = 0; q < kGdItems; ++q) {
+        const size_t i = base + (size_t)q * kGdThreads + threadIdx.x;
+        const bool in = i < n;
+        const VSample v = (one || !in) ? v0 : vl.vs[find_sample(vl.off, vl.n_samples, i)];
+        f(q, i, in, v, s[q], e[q]);
+    }
+}
+
+__global__ void __launch_bounds__(kGdThreads)
+k_gdirect_hist(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, size_t n,
+               GDirectLayout gl, uint32_t* __restrict__ ghist, uint32_t* __restrict__ stats) {
+    uint32_t bad_range = 0, bad_hint = 0, n_cross = 0;
+    gd_for_tile(S, E, n, gl.vl, [&](int, size_t, bool in, const VSample& v, uint32_t s, uint32_t e) {
+        if (!in) return;
+        if (s > e || e >= v.L) {
+            ++bad_range;
+            return;
+        }
+        const uint32_t len = e - s + 1;
+        if (len < gl.minlen || len > gl.maxlen) {
+            ++bad_hint;
+            return;
+        }
+        const uint32_t dl = len - gl.minlen;
+        atomicAdd(&ghist[gl.vl.fake_primary(v, s) * gl.nlen + dl], 1u);
+        if (gl.vl.crosses(v, s, e)) {
+            atomicAdd(&ghist[gl.vl.fake_right(v, s, e) * gl.nlen + dl], 1u);
+            ++n_cross;
+        }
+    });
+    bad_range = __reduce_add_sync(0xffffffffu, bad_range);
+    bad_hint = __reduce_add_sync(0xffffffffu, bad_hint);
+    n_cross = __reduce_add_sync(0xffffffffu, n_cross);
+    if (lane_id() == 0) {
+        if (bad_range) atomicAdd(&stats[2], bad_range);
+        if (bad_hint) atomicAdd(&stats[3], bad_hint);
+        if (n_cross) atomicAdd(&stats[4], n_cross);  // reads cut in two (gds_result.n_arc_items)
+    }
+}
+
+// bundles = non-zero counters in key order; decoding as k_bundle_fill (graph.cuh)
+__global__ void __launch_bounds__(kDkThreads)
+k_gdirect_bundles(const uint32_t* __restrict__ ghist, uint32_t ktot, GDirectLayout gl,
+                  const uint32_t* __restrict__ tile_offs, BundleRec* __restrict__ bund,
+                  uint32_t* __restrict__ b_t, uint32_t* __restrict__ b_slot,
+                  uint32_t* __restrict__ in_bid /* identity when nlen == 1, else null */,
+                  int32_t* __restrict__ diff, uint32_t* __restrict__ outdeg,
+                  uint32_t* __restrict__ indeg, int32_t* __restrict__ odiff) {
+    __shared__ uint32_t total;
+    const uint32_t i = (blockIdx.x * kDkThreads + threadIdx.x) * 4;
+    uint32_t cnt[4] = {0, 0, 0, 0};
+    if (i < ktot) {
+        const uint4 q = reinterpret_cast<const uint4*>(ghist)[i / 4];
+        cnt[0] = q.x;
+        cnt[1] = q.y;
+        cnt[2] = q.z;
+        cnt[3] = q.w;
+    }
+    const uint32_t c = (cnt[0] != 0) + (cnt[1] != 0) + (cnt[2] != 0) + (cnt[3] != 0);
+    uint32_t b = block_excl_scan(c, &total) + tile_offs[blockIdx.x];
+    if (c == 0) return;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (!cnt[q]) continue;
+        const uint32_t key = i + q;
+        const uint32_t fake = key / gl.nlen;
+        const uint32_t len = gl.minlen + key % gl.nlen;
+        const VSample v = gl.vl.vs[find_vsample(gl.vl, fake)];
+        uint32_t first, last;
+        gl.vl.seg_range(v, fake, first, last);
+        const uint32_t s = max(fake, first);
+        const uint32_t t = min(fake + len, last);
+        const uint32_t mult = cnt[q];
+        reinterpret_cast<uint4*>(bund)[b] = make_uint4(t, mult, 0u, s);
+        b_t[b] = t;
+        b_slot[b] = key;
+        if (in_bid) in_bid[b] = b;
+        atomicAdd(&diff[s], (int32_t)mult);
+        atomicAdd(&diff[t], -(int32_t)mult);
+        atomicAdd(&outdeg[s], 1u);
+        atomicAdd(&indeg[t], 1u);
+        if (odiff) {
+            atomicAdd(&odiff[gl.vl.to_orig(v, s)], (int32_t)mult);
+            atomicAdd(&odiff[gl.vl.to_orig(v, t)], -(int32_t)mult);
+        }
+        ++b;
+    }
+}
+
+// K5: codes from the global 2-bit table (L1/L2 resident), one kept-bitmap word per warp and q.
+// With segments of a long reference a third of the reads belong to partial bundles (config 4:
+// 19 M of 50 M), so the candidate chain (bundle id -> segment, slot -> store) is staged across the
+// thread's 8 reads: all lookups of a stage are in flight together.  The right part of a read that
+// crosses a cut (1 % of the reads) takes the chain inline.
+__global__ void __launch_bounds__(kGdThreads)
+k_gdirect_mark(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, size_t n,
+               GDirectLayout gl, const uint32_t* __restrict__ ghist,
+               const uint32_t* __restrict__ kstat, const uint32_t* __restrict__ pb_off,
+               uint32_t* __restrict__ pb_fill, uint32_t* __restrict__ cand,
+               uint32_t* __restrict__ bitmap, unsigned long long* __restrict__ totals) {
+    __shared__ uint32_t krange[2];
+    const VLayout& vl = gl.vl;
+    const size_t base = (size_t)blockIdx.x * kGdTile;
+    if (threadIdx.x == 0) {
+        const size_t last = min(base + kGdTile, n) - 1;
+        krange[0] = vl.n_samples == 1 ? 0 : find_sample(vl.off, vl.n_samples, base);
+        krange[1] = vl.n_samples == 1 ? 0 : find_sample(vl.off, vl.n_samples, last);
+    }
+    __syncthreads();
+    const uint32_t k0 = krange[0];
+    const bool one = k0 == krange[1];
+    const VSample v0 = vl.vs[k0];
+    constexpr uint32_t kNone = 0xffffffffu;
+    uint32_t s[kGdItems], e[kGdItems], key[kGdItems], code[kGdItems];
+#pragma unroll
+    for (int q = 0; q < kGdItems; ++q) {
+        const size_t i = base + (size_t)q * kGdThreads + threadIdx.x;
+        const size_t ii = i < n ? i : base;
+        s[q] = ld_stream(S + ii);
+        e[q] = ld_stream(E + ii);
+    }
+    auto sample_of = [&](size_t i) { return one ? v0 : vl.vs[find_sample(vl.off, vl.n_samples, i)]; };
+    uint32_t cross = 0;  // bit q: the read crosses a segment cut
+#pragma unroll
+    for (int q = 0; q < kGdItems; ++q) {
+        const size_t i = base + (size_t)q * kGdThreads + threadIdx.x;
+        key[q] = kNone;
+        if (i < n) {
+            const VSample v = sample_of(i);
+            const uint32_t dl = e[q] - s[q] + 1 - gl.minlen;
+            if (s[q] <= e[q] && e[q] < v.L && dl < gl.nlen) {  // validated by K2; never index with garbage
+                key[q] = vl.fake_primary(v, s[q]) * gl.nlen + dl;
+                if (vl.crosses(v, s[q], e[q])) cross |= 1u << q;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kGdItems; ++q)
+        code[q] = key[q] != kNone ? (kstat[key[q] >> 4] >> (2 * (key[q] & 15))) & 3u : 0u;
+    uint32_t pid[kGdItems], off[kGdItems], pos[kGdItems];
+#pragma unroll
+    for (int q = 0; q < kGdItems; ++q)
+        if (code[q] == kPartCode) pid[q] = ghist[key[q]];
+#pragma unroll
+    for (int q = 0; q < kGdItems; ++q)
+        if (code[q] == kPartCode) {
+            off[q] = pb_off[pid[q]];
+            pos[q] = atomicAdd(&pb_fill[pid[q]], 1u);
+        }
+    uint32_t kept = 0;
+#pragma unroll
+    for (int q = 0; q < kGdItems; ++q) {
+        const size_t i = base + (size_t)q * kGdThreads + threadIdx.x;
+        if (code[q] == kPartCode) cand[off[q] + pos[q]] = (uint32_t)i;
+        bool keep = code[q] == kSatCode;
+        if (cross >> q & 1) {  // right part: its own bundle
+            const VSample v = sample_of(i);
+            const uint32_t k2 = vl.fake_right(v, s[q], e[q]) * gl.nlen + (e[q] - s[q] + 1 - gl.minlen);
+            const uint32_t c2 = (kstat[k2 >> 4] >> (2 * (k2 & 15))) & 3u;
+            if (c2 == kPartCode) {
+                const uint32_t p2 = ghist[k2];
+                cand[pb_off[p2] + atomicAdd(&pb_fill[p2], 1u)] = (uint32_t)i;
+            }
+            keep |= c2 == kSatCode;
+        }
+        // tiles start at multiples of 32 reads: the 32 lanes of a warp hold one bitmap word
+        const uint32_t w = __ballot_sync(0xffffffffu, keep);
+        if (lane_id() == 0 && w) {
+            atomicOr(&bitmap[i >> 5], w);
+            kept += __popc(w);
+        }
+    }
+    kept = __reduce_add_sync(0xffffffffu, kept);
+    if (lane_id() == 0 && kept) atomicAdd(&totals[1], (unsigned long long)kept);
 }
 
 }  // namespace gds

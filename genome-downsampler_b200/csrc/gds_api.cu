@@ -236,6 +236,8 @@ struct DirectPlan {
     uint32_t* ghist = nullptr;
     uint32_t ktot = 0, kmax = 0, n_items = 0;
     uint32_t* in_bid = nullptr;  // identity in-CSR (single read length), else null
+    bool global = false;         // counters in global memory (several lengths / segmented reference)
+    GDirectLayout gl{};
 };
 
 bool direct_eligible(const gds_reads* rd, uint32_t ns, uint32_t minlen, uint32_t maxlen,
@@ -340,6 +342,66 @@ void build_bundles_direct(gds_ctx* c, const gds_reads* rd, const uint32_t* S, co
     plan.in_bid = ident;
 }
 
+// The same with the counters in global memory (direct.cuh: k_gdirect_*): any layout whose key space
+// (virtual nodes x read lengths) stays L2-sized.
+void build_bundles_gdirect(gds_ctx* c, const uint32_t* S, const uint32_t* E, const VLayout& vl,
+                           size_t N, uint32_t n_nodes, uint32_t minlen, uint32_t maxlen,
+                           int32_t* odiff, uint32_t* stats, DirectPlan& plan, uint32_t& B_out,
+                           uint64_t& n_cross_out) {
+    cudaStream_t st = c->stream;
+    const uint32_t nlen = maxlen - minlen + 1;
+    const uint32_t ktot = (uint32_t)((((uint64_t)n_nodes * nlen) + 31) & ~31ull);
+    uint32_t* ghist = c->dhist.get<uint32_t>(ktot);
+    GDS_CUDA(cudaMemsetAsync(ghist, 0, (size_t)ktot * 4, st));
+    GDirectLayout gl{vl, nlen, minlen, maxlen};
+    {
+        KScope ks("gdirect_hist", 8ull * N + 4ull * ktot, st);
+        k_gdirect_hist<<<div_up((long long)N, kGdTile), kGdThreads, 0, st>>>(S, E, N, gl, ghist, stats);
+        GDS_KERNEL_CHECK();
+    }
+    const uint32_t n_tiles = (uint32_t)div_up(ktot, kDkTile);
+    uint32_t* tc = c->tile_counts.get<uint32_t>(n_tiles + 1);
+    GDS_CUDA(cudaMemsetAsync(tc + n_tiles, 0, sizeof(uint32_t), st));
+    {
+        KScope ks("direct_count", 4ull * ktot, st);
+        k_direct_count<<<n_tiles, kDkThreads, 0, st>>>(ghist, ktot, tc);
+        GDS_KERNEL_CHECK();
+    }
+    exclusive_scan_u32(tc, tc, n_tiles + 1, c->scan, st);
+    uint32_t B = 0;
+    d2h_sync(c, &B, tc + n_tiles, 1);
+    B_out = B;
+    {
+        uint32_t hs[5];
+        d2h_sync(c, hs, stats, 5);
+        if (hs[2]) throw InputFail{GDS_ERR_RANGE, hs[2], "reads with start > end or end >= ref_len"};
+        if (hs[3]) throw InputFail{GDS_ERR_ARG, hs[3], "reads outside the len_min/len_max hints"};
+        n_cross_out = hs[4];
+    }
+    BundleRec* bund = c->bund.get<BundleRec>(B + 1);
+    uint32_t* b_t = c->b_t.get<uint32_t>(B + 1);
+    uint32_t* b_slot = c->b_slot.get<uint32_t>(B + 1);
+    uint32_t* ident = nlen == 1 ? c->ident.get<uint32_t>(B + 1) : nullptr;
+    int32_t* diff = c->diff.get<int32_t>(n_nodes + 1);
+    uint32_t* outdeg = c->outdeg.get<uint32_t>(n_nodes + 1);
+    uint32_t* indeg = c->indeg.get<uint32_t>(n_nodes + 1);
+    GDS_CUDA(cudaMemsetAsync(diff, 0, (n_nodes + 1) * sizeof(int32_t), st));
+    GDS_CUDA(cudaMemsetAsync(outdeg, 0, (n_nodes + 1) * sizeof(uint32_t), st));
+    GDS_CUDA(cudaMemsetAsync(indeg, 0, (n_nodes + 1) * sizeof(uint32_t), st));
+    if (B) {
+        KScope ks("gdirect_bundles", 4ull * ktot + 40ull * B, st);
+        k_gdirect_bundles<<<n_tiles, kDkThreads, 0, st>>>(ghist, ktot, gl, tc, bund, b_t, b_slot, ident,
+                                                         diff, outdeg, indeg, odiff);
+        GDS_KERNEL_CHECK();
+    }
+    plan.on = true;
+    plan.global = true;
+    plan.gl = gl;
+    plan.ghist = ghist;
+    plan.ktot = ktot;
+    plan.in_bid = ident;
+}
+
 // K5 on the direct path (direct.cuh): classify the bundles, mark the reads of saturated bundles in
 // one parallel streaming pass, rank the candidates of partial bundles; the ordered walk is the
 // fallback when the candidates do not fit (or GDS_DIRECT_SELECT=walk asks for it).
@@ -349,52 +411,60 @@ void direct_select(gds_ctx* c, const DirectPlan& dp, const uint32_t* S, const ui
     cudaStream_t st = c->stream;
     BundleRec* bund = c->bund.as<BundleRec>();
     uint32_t* b_slot = c->b_slot.as<uint32_t>();
-    uint32_t* wc = c->dwork.as<uint32_t>() + 1;
     const char* env = getenv("GDS_DIRECT_SELECT");
-    bool walk = env && !strcmp(env, "walk");
+    bool walk = !dp.global && env && !strcmp(env, "walk");
     if (!walk) {
-        const uint32_t cand_cap = (uint32_t)std::min<uint64_t>(N / 16 + (1u << 20), 0xffffff00ull);
         uint32_t* kstat = c->kstat.get<uint32_t>(dp.ktot / 16 + 1);
         uint32_t* pb = c->pbund.get<uint32_t>(3 * ((size_t)B + 1));
-        uint32_t* cand = c->cand.get<uint32_t>(cand_cap);
+        uint32_t* fill = pb + 2 * ((size_t)B + 1);
         uint32_t* ctl = c->dctl.get<uint32_t>(4);
         GDS_CUDA(cudaMemsetAsync(kstat, 0, ((size_t)dp.ktot / 16 + 1) * 4, st));
         GDS_CUDA(cudaMemsetAsync(ctl, 0, 16, st));
         {
+            // a partial bundle beyond kMaxPartialMult reads sends the shared-memory path to the
+            // ordered walk; the global path has no walk and lets one warp grind through it
             KScope ks("direct_classify", 20ull * B, st);
             k_direct_classify<<<div_up(B, 256), 256, 0, st>>>(bund, b_slot, B, dp.ghist, kstat, pb,
-                                                            pb + B + 1, pb + 2 * ((size_t)B + 1), ctl,
-                                                            cand_cap);
-            GDS_KERNEL_CHECK();
-        }
-        {
-            const unsigned long long per_read = dp.dl.nlen > 1 ? 8 : 4;
-            KScope ks("direct_mark", per_read * N + dp.ktot / 4 + 8ull * N / 32, st);
-            const int grid = (int)std::min<uint32_t>(dp.n_items, (uint32_t)kNumSMs);
-            const unsigned smem = kDmQueueBytes + dp.kmax;
-            uint32_t* fill = pb + 2 * ((size_t)B + 1);
-            if (dp.dl.nlen == 1)
-                k_direct_mark<true><<<grid, kDmThreads, smem, st>>>(S, E, dp.dl, dp.n_items, wc, dp.ghist,
-                                                                   kstat, pb, fill, cand, ctl, bm, totals);
-            else
-                k_direct_mark<false><<<grid, kDmThreads, smem, st>>>(S, E, dp.dl, dp.n_items, wc,
-                                                                    dp.ghist, kstat, pb, fill, cand, ctl,
-                                                                    bm, totals);
-            GDS_KERNEL_CHECK();
-        }
-        {
-            KScope ks("direct_partial", 16ull * B / 64, st);
-            k_direct_partial<<<kNumSMs * 32, 256, 0, st>>>(pb, pb + B + 1, pb + 2 * ((size_t)B + 1),
-                                                         cand, ctl, bm, totals);
+                                                            pb + B + 1, fill, ctl,
+                                                            dp.global ? 0xffffffffu : kMaxPartialMult);
             GDS_KERNEL_CHECK();
         }
         uint32_t hctl[4];
-        d2h_sync(c, hctl, ctl, 4);
+        d2h_sync(c, hctl, ctl, 4);  // candidate buffer sized exactly
         out->partial_bundles = hctl[0];
         out->partial_candidates = hctl[1];
         walk = hctl[2] != 0;
-        if (!walk) return;
-        GDS_CUDA(cudaMemsetAsync(wc, 0, 4, st));
+        if (!walk) {
+            uint32_t* cand = c->cand.get<uint32_t>((size_t)hctl[1] + 1);
+            const unsigned long long per_read = (dp.global || dp.dl.nlen > 1) ? 8 : 4;
+            if (dp.global) {
+                KScope ks("gdirect_mark", per_read * N + dp.ktot / 4 + 8ull * N / 32, st);
+                k_gdirect_mark<<<div_up((long long)N, kGdTile), kGdThreads, 0, st>>>(
+                    S, E, N, dp.gl, dp.ghist, kstat, pb, fill, cand, bm, totals);
+                GDS_KERNEL_CHECK();
+            } else {
+                KScope ks("direct_mark", per_read * N + dp.ktot / 4 + 8ull * N / 32, st);
+                uint32_t* wc = c->dwork.as<uint32_t>() + 1;
+                const int grid = (int)std::min<uint32_t>(dp.n_items, (uint32_t)kNumSMs);
+                const unsigned smem = kDmQueueBytes + dp.kmax;
+                if (dp.dl.nlen == 1)
+                    k_direct_mark<true><<<grid, kDmThreads, smem, st>>>(S, E, dp.dl, dp.n_items, wc,
+                                                                       dp.ghist, kstat, pb, fill, cand,
+                                                                       ctl, bm, totals);
+                else
+                    k_direct_mark<false><<<grid, kDmThreads, smem, st>>>(S, E, dp.dl, dp.n_items, wc,
+                                                                        dp.ghist, kstat, pb, fill, cand,
+                                                                        ctl, bm, totals);
+                GDS_KERNEL_CHECK();
+            }
+            if (hctl[0]) {
+                KScope ks("direct_partial", 16ull * hctl[0] + 4ull * hctl[1], st);
+                k_direct_partial<<<kNumSMs * 32, 256, 0, st>>>(pb, pb + B + 1, fill, cand, ctl, bm,
+                                                              totals);
+                GDS_KERNEL_CHECK();
+            }
+            return;
+        }
     }
     // ordered walk: one CTA per sample, quota per key in shared memory
     {
@@ -404,6 +474,8 @@ void direct_select(gds_ctx* c, const DirectPlan& dp, const uint32_t* S, const ui
     }
     {
         KScope ks("direct_walk", 4ull * dp.ktot + 8ull * N / 32, st);
+        uint32_t* wc = c->dwork.as<uint32_t>() + 1;
+        GDS_CUDA(cudaMemsetAsync(wc, 0, 4, st));
         const int grid = (int)std::min<uint32_t>(ns, (uint32_t)kNumSMs);
         k_direct_select<<<grid, kDsThreads, dp.kmax * 4, st>>>(S, E, dp.dl, wc, dp.ghist, bm, totals);
         GDS_KERNEL_CHECK();
@@ -817,9 +889,15 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             oexcl = c->oexcl.get<uint32_t>(n_onodes + 1);
             GDS_CUDA(cudaMemsetAsync(odiff, 0, ((size_t)n_onodes + 1) * 4, st));
         }
+        // how K2 finds the bundles: shared-memory histogram, global-memory histogram, radix sort
+        const int bmode = bundle_mode(prm);
+        const bool use_direct =
+            N > 0 && !split && bmode != 1 && direct_eligible(rd, ns, minlen, maxlen, S, E);
+        const bool use_gdirect = N > 0 && !use_direct && bmode != 1 &&
+                                 (uint64_t)n_nodes * ((uint64_t)maxlen - minlen + 1) <= kGDirectMaxKeys;
         size_t n_items = N;
         uint32_t* cross_idx = nullptr;
-        if (split && N > 0) {  // right parts of the reads that cross a cut
+        if (split && N > 0 && !use_gdirect) {  // right parts of the reads that cross a cut
             uint32_t n_ct = (uint32_t)((N + kCrossTile - 1) / kCrossTile);
             uint32_t* ctc = c->cross_tc.get<uint32_t>(n_ct + 1);
             GDS_CUDA(cudaMemsetAsync(ctc + n_ct, 0, 4, st));
@@ -843,11 +921,18 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         }
         out->n_arc_items = n_items;
         DirectPlan direct;
-        const int bmode = bundle_mode(prm);
-        if (N > 0 && !split && bmode != 1 && direct_eligible(rd, ns, minlen, maxlen, S, E)) {
+        if (use_direct) {
             build_bundles_direct(c, rd, S, E, foff_dev, foff_host, reflen_d, base_d, ns, N, n_nodes,
                                  minlen, maxlen, stats, direct, B);
             out->key_bits = bits_for(direct.kmax - 1);
+            out->bundle_path = 1;
+        } else if (use_gdirect) {
+            uint64_t n_cross = 0;
+            build_bundles_gdirect(c, S, E, vl, N, n_nodes, minlen, maxlen, odiff, stats, direct, B,
+                                  n_cross);
+            out->n_arc_items = N + n_cross;
+            out->key_bits = bits_for((uint64_t)direct.ktot - 1);
+            out->bundle_path = 2;
         } else if (N > 0) {
             // the arc sort is segmented by sample unless some sample is cut into segments (then the
             // right parts live after all reads and one group with global keys is sorted)

@@ -99,10 +99,11 @@ typedef struct {
     uint32_t max_rounds;
     uint32_t seg_len;
     /* how K2 finds the bundles (reads with one (start, length) key): 0 = choose, 1 = always the
-     * segmented radix sort, 2 = the sort-free shared-memory histogram whenever it is eligible (no
-     * sample segmented, ref_len x #read-lengths <= 49152 per sample, 16-byte aligned start/end).
-     * Both give the same graph and the same kept set; gds_result.sort_passes == 0 tells that the
-     * histogram ran.  The environment variable GDS_BUNDLE=sort|direct overrides (benchmarks). */
+     * segmented radix sort, 2 = a sort-free histogram whenever one is eligible: counters in shared
+     * memory (no sample segmented, ref_len x #read-lengths <= 49152 per sample, 16-byte aligned
+     * start/end) or else in global memory (virtual nodes x #read-lengths <= 24 Mi).  All three give
+     * the same graph and the same kept set; gds_result.bundle_path tells which one ran.  The
+     * environment variable GDS_BUNDLE=sort|direct overrides (benchmarks). */
     uint32_t bundle_mode;
 } gds_params;
 
@@ -128,6 +129,9 @@ typedef struct {
     /* direct (histogram) path, K5: bundles with 0 < flow < multiplicity and the reads that carry
      * their keys (ranked by index; every other kept read belongs to a saturated bundle) */
     uint64_t partial_bundles, partial_candidates;
+    uint32_t bundle_path; /* how K2 found the bundles: 0 radix sort, 1 histogram in shared memory,
+                             2 histogram in global memory (gds_params.bundle_mode) */
+    uint32_t reserved0;
     /* device-event milliseconds per phase */
     float ms_h2d, ms_filter, ms_graph, ms_maxflow, ms_select, ms_verify, ms_d2h, ms_total;
 } gds_result;

@@ -51,7 +51,7 @@ def test_b200_arm_line():
     # compact transport: fixed-length reads on a 30 kb reference cross PCIe as 16-bit starts
     assert e["h2d_bytes_per_step"] == 2 * 1_000_000 and "u16" in e["input_encoding"]
     assert e["d2h_bytes_per_step"] > 0 and e["value"] > 0
-    assert d["result"]["bundle_path"] == "direct histogram"
+    assert d["result"]["bundle_path"] == "histogram in shared memory"
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     assert d["result"]["fstar"] == d["result"]["flow_value"] == 100
     assert d["config"]["workload"].startswith("c1")

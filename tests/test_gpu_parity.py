@@ -366,10 +366,28 @@ def test_direct_histogram_path_equals_sort_path(solver, O):
     assert ra.sort_passes == 0 and rb.sort_passes > 0
     assert np.array_equal(ra.kept_bitmap, rb.kept_bitmap) and ra.rounds_total == rb.rounds_total
     assert_parity(O, ra, s2, e2, [9_200], [0, len(s2)], 200)
-    # a key space beyond shared memory falls back to the sort even when the histogram is asked for
+    assert ra.bundle_path == 1 and rb.bundle_path == 0
+    # a key space beyond shared memory keeps its counters in global memory (L2): same answer again
     e3 = (s2 + rng.integers(100, 300, size=400_000)).astype(np.uint32)
-    rc = solver.solve(s2, e3, 9_400, 50, params=PRM + (0, 2), verify=True)
-    assert rc.sort_passes > 0 and rc.verify_violations == 0
+    rc = solver.solve(s2, e3, 9_400, 50, params=PRM + (0, 0), verify=True, want_vectors=True)
+    rd = solver.solve(s2, e3, 9_400, 50, params=PRM + (0, 1), verify=True)
+    assert rc.bundle_path == 2 and rc.sort_passes == 0 and rd.bundle_path == 0
+    assert np.array_equal(rc.kept_bitmap, rd.kept_bitmap) and rc.rounds_total == rd.rounds_total
+    assert rc.n_bundles == rd.n_bundles and rc.verify_violations == 0
+    assert_parity(O, rc, s2, e3, [9_400], [0, len(s2)], 50)
+    # and so does a segmented reference (reads crossing a cut count twice), batched with a short one
+    s4, e4, _, _ = O.gen_reads(77, 120_000, 150_000, 150)
+    s5, e5, _, _ = O.gen_reads(78, 30_000, 20_000, 150)
+    sb = np.concatenate([s4, s5]); eb = np.concatenate([e4, e5])
+    offb = np.array([0, len(s4), len(s4) + len(s5)], np.uint64)
+    prm_seg = (64, 150, 1, 0, 8192)
+    re = solver.solve(sb, eb, [150_000, 20_000], 60, read_off=offb, params=prm_seg + (0,), verify=True,
+                      want_vectors=True)
+    rf = solver.solve(sb, eb, [150_000, 20_000], 60, read_off=offb, params=prm_seg + (1,), verify=True)
+    assert re.bundle_path == 2 and rf.bundle_path == 0 and re.n_arc_items == rf.n_arc_items > len(sb)
+    assert np.array_equal(re.kept_bitmap, rf.kept_bitmap) and re.n_kept == rf.n_kept
+    assert re.n_components == rf.n_components and re.pushes == rf.pushes
+    assert_parity(O, re, sb, eb, [150_000, 20_000], offb, 60, prm_seg)
 
 
 def test_direct_selection_walk_many_tiles_and_duplicates(solver, O):
