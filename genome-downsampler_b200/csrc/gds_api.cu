@@ -51,7 +51,7 @@ struct gds_ctx {
     DevBuf dhist, dlay, b_slot, ident, dwork;  // direct (sort-free) bundle path
     DevBuf kstat, pbund, cand, dctl, in_src;
     unsigned direct_attr = 0;                  // bytes of dynamic smem the direct kernels are set up for
-    unsigned mf_attr_set = 0;  // bit i: smem attribute set for launch shape i
+    int mf_smem_set[4] = {0, 0, 0, 0};  // dynamic shared memory the launch shapes are set up for
     bool atomic_rank = false;  // shared-memory atomics rank in lane order on this device (probed)
     Profiler prof;
 
@@ -117,40 +117,54 @@ template <int I>
 void launch_maxflow_shape(gds_ctx* c, const MfGraph& mg,
                           const uint32_t* comp_lo, const uint32_t* comp_hi, uint32_t n_comp,
                           uint32_t* wc, uint32_t* qF, uint32_t* qT, uint32_t* qN, uint32_t* qH,
-                          const SolveParams& sp, CompStats* cstats) {
+                          const SolveParams& sp, CompStats* cstats, uint32_t max_comp_nodes) {
     constexpr MfShape sh = kMfShapes[I];
     auto kern = k_maxflow<sh.threads, sh.qcap, sh.ctas_per_sm>;
-    constexpr int smem = (int)sizeof(MfShared<sh.qcap>);
-    if (!(c->mf_attr_set & (1u << I))) {
+    // 16-bit labels of a whole component in shared memory for the first global relabel, when
+    // every resident CTA of this shape can have them (maxflow.cuh: mf_first_relabel)
+    uint32_t lab_cap = 0;
+    int smem = (int)sizeof(MfShared<sh.qcap>);
+    if (max_comp_nodes && max_comp_nodes < 0xfff0u) {
+        const int lab_bytes = (int)((2 * max_comp_nodes + 4 + 15) & ~15u);
+        // ... and the SM keeps at least ~100 KB of L1 for the rounds' plain loads (measured: with
+        // 4 x 49 KB per SM config 4 lost 13 %)
+        if ((smem + lab_bytes) * sh.ctas_per_sm <= 132 * 1024) {
+            smem += lab_bytes;
+            lab_cap = max_comp_nodes;
+        }
+    }
+    if (c->mf_smem_set[I] < smem) {
         GDS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        c->mf_attr_set |= 1u << I;
+        c->mf_smem_set[I] = smem;
     }
     int grid = std::min<uint32_t>(n_comp, (uint32_t)kNumSMs * sh.ctas_per_sm);
     kern<<<grid, sh.threads, smem, c->stream>>>(mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp,
-                                                cstats);
+                                                cstats, lab_cap);
 }
 
 void launch_maxflow(gds_ctx* c, const MfGraph& mg,
                     const uint32_t* comp_lo, const uint32_t* comp_hi, uint32_t n_comp, uint32_t* wc,
                     uint32_t* qF, uint32_t* qT, uint32_t* qN, uint32_t* qH, const SolveParams& sp,
-                    CompStats* cstats, unsigned long long alg_bytes) {
+                    CompStats* cstats, unsigned long long alg_bytes, uint32_t max_comp_nodes) {
     KScope ks("maxflow", alg_bytes, c->stream);
     const uint32_t sms = (uint32_t)kNumSMs;
-    int force = -1;  // GDS_MF_SHAPE=0..3: measurement knob (the schedule does not depend on it)
-    if (const char* e = getenv("GDS_MF_SHAPE")) force = atoi(e);
-    if (force >= 0 && force <= 3) {
-        if (force == 0) launch_maxflow_shape<0>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats);
-        if (force == 1) launch_maxflow_shape<1>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats);
-        if (force == 2) launch_maxflow_shape<2>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats);
-        if (force == 3) launch_maxflow_shape<3>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats);
-    } else if (n_comp <= sms * kMfShapes[0].ctas_per_sm)
-        launch_maxflow_shape<0>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats);
-    else if (n_comp <= sms * kMfShapes[1].ctas_per_sm)
-        launch_maxflow_shape<1>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats);
-    else if (n_comp <= sms * kMfShapes[2].ctas_per_sm)
-        launch_maxflow_shape<2>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats);
-    else
-        launch_maxflow_shape<3>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats);
+    int shape = 3;
+    for (int i = 0; i < 3; ++i)
+        if (n_comp <= sms * kMfShapes[i].ctas_per_sm) {
+            shape = i;
+            break;
+        }
+    // GDS_MF_SHAPE=0..3: measurement knob (the schedule does not depend on the launch shape)
+    if (const char* e = getenv("GDS_MF_SHAPE"))
+        if (e[0] >= '0' && e[0] <= '3' && !e[1]) shape = e[0] - '0';
+    if (const char* e = getenv("GDS_MF_SMEM_LABELS"))  // =0: labels stay in global memory
+        if (e[0] == '0') max_comp_nodes = 0;
+    switch (shape) {
+        case 0: launch_maxflow_shape<0>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes); break;
+        case 1: launch_maxflow_shape<1>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes); break;
+        case 2: launch_maxflow_shape<2>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes); break;
+        default: launch_maxflow_shape<3>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes); break;
+    }
     GDS_KERNEL_CHECK();
 }
 
@@ -1097,8 +1111,12 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             uint32_t* qH = c->qH.get<uint32_t>(n_nodes);
             uint32_t* wc = c->work_counter.get<uint32_t>(1);
             GDS_CUDA(cudaMemsetAsync(wc, 0, 4, st));
+            // no component is larger than a whole unsegmented sample or one segment
+            uint32_t max_comp_nodes = 0;
+            for (const VSample& v : hvs)
+                max_comp_nodes = std::max(max_comp_nodes, v.nseg == 1 ? v.L + 1 : seg + 1);
             launch_maxflow(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats,
-                           36ull * n_nodes + 20ull * B);
+                           36ull * n_nodes + 20ull * B, max_comp_nodes);
         }
         GDS_CUDA(cudaEventRecord(c->ev[EV_MAXFLOW], st));
 

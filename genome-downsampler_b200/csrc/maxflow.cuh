@@ -232,22 +232,33 @@ __device__ uint32_t mf_global_relabel(const MfGraph& G, uint32_t lo, uint32_t hi
 // CAS on the right neighbour is in flight meanwhile, the label snapshot is written as nodes are
 // labelled, and three rotating level counters leave ONE barrier per level.  Labels are exact BFS
 // distances, so they equal what mf_global_relabel computes (and the oracle's replay).
-template <int THREADS, uint32_t QCAP>
+template <int THREADS, uint32_t QCAP, bool LAB>
 __device__ uint32_t mf_first_relabel(const MfGraph& G, uint32_t lo, uint32_t hi, Queue<QCAP> T,
                                      Queue<QCAP> N, Queue<QCAP> H, MfShared<QCAP>& sh,
-                                     unsigned long long& bfs_levels, bool warp_mode) {
+                                     unsigned long long& bfs_levels, bool warp_mode,
+                                     uint16_t* lab /* LAB: [hi-lo+1] shared-memory labels */) {
     const uint32_t tid = threadIdx.x;
+    constexpr uint32_t kInf16 = 0xffffu;
     if (tid == 0) {
         sh.lc[0] = 0;
         sh.lc[1] = 0;
         sh.lc[2] = 0;
         sh.nH = 0;
     }
+    if (LAB) {  // 16-bit labels of the whole component next to the SM: the CAS of a level becomes
+                // a shared-memory operation (~60 cycles instead of a ~800-cycle L2 round trip)
+        uint32_t* lab32 = reinterpret_cast<uint32_t*>(lab);
+        for (uint32_t i = tid; i < (hi - lo + 2) / 2; i += THREADS) lab32[i] = 0xffffffffu;
+    }
     __syncthreads();
     for (uint32_t v = lo + tid; v <= hi; v += THREADS) {
         if ((int32_t)ld_u32(reinterpret_cast<const uint32_t*>(&G.node[v].snk)) > 0) {
-            G.node[v].d = 1u;
-            G.d_snap[v] = 1u;
+            if (LAB) {
+                lab[v - lo] = 1;
+            } else {
+                G.node[v].d = 1u;
+                G.d_snap[v] = 1u;
+            }
             q_append(T, &sh.lc[0], v);
         }
     }
@@ -261,23 +272,43 @@ __device__ uint32_t mf_first_relabel(const MfGraph& G, uint32_t lo, uint32_t hi,
         uint32_t* nxt = &sh.lc[level % 3];
         if (tid == 0) sh.lc[(level + 1) % 3] = 0;  // last level's counter: everyone has read it
         auto label = [&](uint32_t u) {
-            G.d_snap[u] = nl;
+            if (!LAB) G.d_snap[u] = nl;
             q_append(N, nxt, u);
+        };
+        // true: u was unlabelled and now carries nl (exactly one caller wins)
+        auto claim = [&](uint32_t u) -> bool {
+            if constexpr (!LAB) {
+                return atomicCAS(&G.node[u].d, kLabelInf, nl) == kLabelInf;
+            } else {
+                uint32_t* word = reinterpret_cast<uint32_t*>(lab) + ((u - lo) >> 1);
+                const uint32_t sh16 = ((u - lo) & 1u) * 16;
+                for (;;) {
+                    const uint32_t old = *reinterpret_cast<volatile uint32_t*>(word);
+                    if (((old >> sh16) & kInf16) != kInf16) return false;
+                    const uint32_t want = (old & ~(kInf16 << sh16)) | (nl << sh16);
+                    if (atomicCAS(word, old, want) == old) return true;
+                }
+            }
         };
         for (uint32_t i = tid; i < cnt && !warp_mode; i += THREADS) {
             const uint32_t w = T.get(i);
             const uint32_t in_lo = ld_u32(&G.node[w].in_ptr), in_hi = ld_u32(&G.node[w + 1].in_ptr);
+            // back arc (w+1) -> w.  Global labels: the CAS is issued here and its answer is only
+            // looked at after the in-arcs, so it is in flight meanwhile
             uint32_t old_r = 0;
-            if (w < hi) old_r = atomicCAS(&G.node[w + 1].d, kLabelInf, nl);  // back arc (w+1) -> w
+            bool got_r = false;
+            if constexpr (LAB) got_r = w < hi && claim(w + 1);
+            else if (w < hi) old_r = atomicCAS(&G.node[w + 1].d, kLabelInf, nl);
             if (in_hi - in_lo > kHeavyDeg) {
                 q_append(H, &sh.nH, w);
             } else {
                 for (uint32_t k = in_lo; k < in_hi; ++k) {
                     const uint32_t s = ld_u32(&G.in_src[k]);
-                    if (atomicCAS(&G.node[s].d, kLabelInf, nl) == kLabelInf) label(s);
+                    if (claim(s)) label(s);
                 }
             }
-            if (w < hi && old_r == kLabelInf) label(w + 1);
+            if constexpr (!LAB) got_r = w < hi && old_r == kLabelInf;
+            if (got_r) label(w + 1);
         }
         if (!warp_mode) __syncthreads();
         const uint32_t nH = warp_mode ? cnt : sh.nH;  // uniform
@@ -286,12 +317,10 @@ __device__ uint32_t mf_first_relabel(const MfGraph& G, uint32_t lo, uint32_t hi,
             for (uint32_t h = tid >> 5; h < nH; h += THREADS / 32) {
                 const uint32_t w = warp_mode ? T.get(h) : H.get(h);
                 const uint32_t in_lo = ld_u32(&G.node[w].in_ptr), in_hi = ld_u32(&G.node[w + 1].in_ptr);
-                if (warp_mode && lane == 0 && w < hi &&
-                    atomicCAS(&G.node[w + 1].d, kLabelInf, nl) == kLabelInf)
-                    label(w + 1);
+                if (warp_mode && lane == 0 && w < hi && claim(w + 1)) label(w + 1);
                 for (uint32_t k = in_lo + lane; k < in_hi; k += 32) {
                     const uint32_t s = ld_u32(&G.in_src[k]);
-                    if (atomicCAS(&G.node[s].d, kLabelInf, nl) == kLabelInf) label(s);
+                    if (claim(s)) label(s);
                 }
             }
             __syncthreads();
@@ -306,6 +335,14 @@ __device__ uint32_t mf_first_relabel(const MfGraph& G, uint32_t lo, uint32_t hi,
         ++level;
     }
     __syncthreads();
+    if (LAB) {  // labels and their snapshot go to the node records in one coalesced pass
+        for (uint32_t v = lo + tid; v <= hi; v += THREADS) {
+            const uint32_t d16 = lab[v - lo];
+            const uint32_t d = d16 == kInf16 ? kLabelInf : d16;
+            G.node[v].d = d;
+            G.d_snap[v] = d;
+        }
+    }
     if (tid == 0) {
         sh.nT = 0;
         sh.nN = 0;
@@ -318,9 +355,11 @@ template <int THREADS, uint32_t QCAP, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __restrict__ comp_hi,
           uint32_t n_comp, uint32_t* work_counter, uint32_t* qF_g, uint32_t* qT_g, uint32_t* qN_g,
-          uint32_t* qH_g, SolveParams P, CompStats* __restrict__ stats) {
+          uint32_t* qH_g, SolveParams P, CompStats* __restrict__ stats,
+          uint32_t lab_cap /* nodes the shared-memory label array behind MfShared holds (0: none) */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MfShared<QCAP>& sh = *reinterpret_cast<MfShared<QCAP>*>(smem_raw);
+    uint16_t* lab_base = reinterpret_cast<uint16_t*>(smem_raw + sizeof(MfShared<QCAP>));
     const uint32_t tid = threadIdx.x;
 
     for (;;) {
@@ -354,7 +393,11 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
         long long tparts[3] = {0, 0, 0};
         const long long t_gr = clock64();
         uint32_t last_levels =
-            mf_first_relabel<THREADS, QCAP>(G, lo, hi, T, N, H, sh, bfs_levels, warp_mode);
+            ncomp <= lab_cap
+                ? mf_first_relabel<THREADS, QCAP, true>(G, lo, hi, T, N, H, sh, bfs_levels, warp_mode,
+                                                        lab_base)
+                : mf_first_relabel<THREADS, QCAP, false>(G, lo, hi, T, N, H, sh, bfs_levels,
+                                                         warp_mode, nullptr);
         tparts[1] = clock64() - t_gr;
         const long long t_front = clock64();
         for (uint32_t v = lo + tid; v <= hi; v += THREADS) {
