@@ -130,10 +130,23 @@ __device__ __forceinline__ uint32_t warp_excl_sum(uint32_t v, uint32_t& total) {
 // reverse BFS from the sink; T/N are used as the level queues.  returns the level counter.
 // Three rotating level counters (this level / next level / being reset) leave one barrier per
 // level; the label snapshot is written when a node is labelled.
-template <int THREADS, uint32_t QCAP>
+// 16-bit claim of an unlabelled node in the shared-memory label array (two labels per word)
+__device__ __forceinline__ bool mf_claim16(uint16_t* lab, uint32_t idx, uint32_t nl) {
+    uint32_t* word = reinterpret_cast<uint32_t*>(lab) + (idx >> 1);
+    const uint32_t sh16 = (idx & 1u) * 16;
+    for (;;) {
+        const uint32_t old = *reinterpret_cast<volatile uint32_t*>(word);
+        if (((old >> sh16) & 0xffffu) != 0xffffu) return false;
+        const uint32_t want = (old & ~(0xffffu << sh16)) | (nl << sh16);
+        if (atomicCAS(word, old, want) == old) return true;
+    }
+}
+
+template <int THREADS, uint32_t QCAP, bool LAB>
 __device__ uint32_t mf_global_relabel(const MfGraph& G, uint32_t lo, uint32_t hi, Queue<QCAP> T,
                                       Queue<QCAP> N, Queue<QCAP> H, MfShared<QCAP>& sh,
-                                      unsigned long long& bfs_levels, bool warp_mode) {
+                                      unsigned long long& bfs_levels, bool warp_mode,
+                                      uint16_t* lab /* LAB: [hi-lo+1] shared-memory labels */) {
     const uint32_t tid = threadIdx.x;
     if (tid == 0) {
         sh.lc[0] = 0;
@@ -141,11 +154,19 @@ __device__ uint32_t mf_global_relabel(const MfGraph& G, uint32_t lo, uint32_t hi
         sh.lc[2] = 0;
         sh.nH = 0;
     }
+    if (LAB) {
+        uint32_t* lab32 = reinterpret_cast<uint32_t*>(lab);
+        for (uint32_t i = tid; i < (hi - lo + 2) / 2; i += THREADS) lab32[i] = 0xffffffffu;
+    }
     __syncthreads();
     for (uint32_t v = lo + tid; v <= hi; v += THREADS) {
         const bool is_sink = (int32_t)ld_u32(reinterpret_cast<const uint32_t*>(&G.node[v].snk)) > 0;
-        G.node[v].d = is_sink ? 1u : kLabelInf;
-        G.d_snap[v] = is_sink ? 1u : kLabelInf;
+        if (LAB) {
+            if (is_sink) lab[v - lo] = 1;
+        } else {
+            G.node[v].d = is_sink ? 1u : kLabelInf;
+            G.d_snap[v] = is_sink ? 1u : kLabelInf;
+        }
         if (is_sink) q_append(T, &sh.lc[0], v);
     }
     __syncthreads();
@@ -158,9 +179,13 @@ __device__ uint32_t mf_global_relabel(const MfGraph& G, uint32_t lo, uint32_t hi
         uint32_t* nxt = &sh.lc[level % 3];
         if (tid == 0) sh.lc[(level + 1) % 3] = 0;  // last level's counter: everyone has read it
         auto visit = [&](uint32_t u) {
-            if (atomicCAS(&G.node[u].d, kLabelInf, nl) == kLabelInf) {
-                G.d_snap[u] = nl;
-                q_append(N, nxt, u);
+            if constexpr (LAB) {
+                if (mf_claim16(lab, u - lo, nl)) q_append(N, nxt, u);
+            } else {
+                if (atomicCAS(&G.node[u].d, kLabelInf, nl) == kLabelInf) {
+                    G.d_snap[u] = nl;
+                    q_append(N, nxt, u);
+                }
             }
         };
         for (uint32_t i = tid; i < cnt && !warp_mode; i += THREADS) {
@@ -217,6 +242,14 @@ __device__ uint32_t mf_global_relabel(const MfGraph& G, uint32_t lo, uint32_t hi
         ++level;
     }
     __syncthreads();
+    if (LAB) {
+        for (uint32_t v = lo + tid; v <= hi; v += THREADS) {
+            const uint32_t d16 = lab[v - lo];
+            const uint32_t d = d16 == 0xffffu ? kLabelInf : d16;
+            G.node[v].d = d;
+            G.d_snap[v] = d;
+        }
+    }
     if (tid == 0) {
         sh.nT = 0;
         sh.nN = 0;
@@ -280,14 +313,7 @@ __device__ uint32_t mf_first_relabel(const MfGraph& G, uint32_t lo, uint32_t hi,
             if constexpr (!LAB) {
                 return atomicCAS(&G.node[u].d, kLabelInf, nl) == kLabelInf;
             } else {
-                uint32_t* word = reinterpret_cast<uint32_t*>(lab) + ((u - lo) >> 1);
-                const uint32_t sh16 = ((u - lo) & 1u) * 16;
-                for (;;) {
-                    const uint32_t old = *reinterpret_cast<volatile uint32_t*>(word);
-                    if (((old >> sh16) & kInf16) != kInf16) return false;
-                    const uint32_t want = (old & ~(kInf16 << sh16)) | (nl << sh16);
-                    if (atomicCAS(word, old, want) == old) return true;
-                }
+                return mf_claim16(lab, u - lo, nl);
             }
         };
         for (uint32_t i = tid; i < cnt && !warp_mode; i += THREADS) {
@@ -420,8 +446,11 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
                 (unsigned long long)sh.relabels_since * 100 >=
                     (unsigned long long)P.gr_relabel_pct * ncomp) {
                 __syncthreads();  // everyone has read relabels_since
-                last_levels =
-                    mf_global_relabel<THREADS, QCAP>(G, lo, hi, T, N, H, sh, bfs_levels, warp_mode);
+                last_levels = ncomp <= lab_cap
+                                  ? mf_global_relabel<THREADS, QCAP, true>(G, lo, hi, T, N, H, sh,
+                                                                           bfs_levels, warp_mode, lab_base)
+                                  : mf_global_relabel<THREADS, QCAP, false>(G, lo, hi, T, N, H, sh,
+                                                                            bfs_levels, warp_mode, nullptr);
                 ++grs;
                 if (tid == 0) sh.relabels_since = 0;
                 rounds_since = 0;
