@@ -1057,9 +1057,7 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             }
         }
         uint32_t* sidx = c->comp_sidx.get<uint32_t>(n_nodes + 1);
-        uint32_t* eidx = c->comp_eidx.get<uint32_t>(n_nodes + 1);
         exclusive_scan_u32(cstart, sidx, n_nodes + 1, c->scan, st);
-        exclusive_scan_u32(cend, eidx, n_nodes + 1, c->scan, st);
         d2h_sync(c, &n_comp, sidx + n_nodes, 1);  // also fences hvs/hcuts uploads
         out->n_components = n_comp;
         uint32_t* comp_lo = c->comp_lo.get<uint32_t>(n_comp + 1);
@@ -1067,7 +1065,7 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         if (n_comp) {
             {
                 KScope ks("comp_write", 16ull * n_nodes, st);
-                k_comp_write<<<div_up(n_nodes, 256), 256, 0, st>>>(cstart, cend, sidx, eidx, n_nodes,
+                k_comp_write<<<div_up(n_nodes, 256), 256, 0, st>>>(cstart, cend, sidx, n_nodes,
                 comp_lo, comp_hi);
                 GDS_KERNEL_CHECK();
             }

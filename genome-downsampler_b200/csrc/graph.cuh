@@ -404,14 +404,16 @@ k_in_src(const BundleRec* __restrict__ bund, const uint32_t* __restrict__ in_bid
     if (k < B) in_src[k] = bund[in_bid[k]].s;
 }
 
+// Components are disjoint runs, so starts and ends alternate: the end at v closes the component
+// opened by the last start before it, index (number of starts before v) - 1 — one scan serves both.
 __global__ void __launch_bounds__(256)
 k_comp_write(const uint32_t* __restrict__ comp_start, const uint32_t* __restrict__ comp_end,
-             const uint32_t* __restrict__ start_idx, const uint32_t* __restrict__ end_idx,
-             uint32_t n_nodes, uint32_t* __restrict__ comp_lo, uint32_t* __restrict__ comp_hi) {
+             const uint32_t* __restrict__ start_idx, uint32_t n_nodes,
+             uint32_t* __restrict__ comp_lo, uint32_t* __restrict__ comp_hi) {
     uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_nodes) return;
     if (comp_start[v]) comp_lo[start_idx[v]] = v;
-    if (comp_end[v]) comp_hi[end_idx[v]] = v;
+    if (comp_end[v]) comp_hi[start_idx[v] - 1] = v;
 }
 
 }  // namespace gds
