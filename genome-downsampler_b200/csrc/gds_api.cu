@@ -44,7 +44,7 @@ struct gds_ctx {
     DevBuf diff, outdeg, indeg, excl;
     DevBuf tkA, tkB, tvA, tvB;
     DevBuf node_rec, n_dsnap;
-    DevBuf comp_start, comp_end, comp_sidx, comp_eidx, comp_lo, comp_hi;
+    DevBuf comp_start, comp_end, comp_sidx, comp_lo, comp_hi;
     DevBuf qF, qT, qN, qH, work_counter, comp_stats;
     DevBuf bitmap, cov_tmp, dem_tmp, vdiff, vexcl;
     DevBuf vs_d, cross_idx, cross_tc, odiff, oexcl, cut_nodes, tile_off_d, head_bits;
@@ -61,7 +61,7 @@ struct gds_ctx {
                          &valsA, &valsB, &tile_counts, &radix.hist, &radix.scan.l1, &radix.scan.l2,
                          &scan.l1, &scan.l2, &b_first, &b_key, &b_t, &bund, &diff,
                          &outdeg, &indeg, &excl, &tkA, &tkB, &tvA, &tvB, &node_rec, &n_dsnap, &comp_start, &comp_end, &comp_sidx,
-                         &comp_eidx, &comp_lo, &comp_hi, &qF, &qT, &qN, &qH, &work_counter, &comp_stats,
+                         &comp_lo, &comp_hi, &qF, &qT, &qN, &qH, &work_counter, &comp_stats,
                          &bitmap, &cov_tmp, &dem_tmp, &vdiff, &vexcl, &vs_d, &cross_idx, &cross_tc,
                          &odiff, &oexcl, &cut_nodes, &tile_off_d, &head_bits, &dhist, &dlay, &b_slot,
                          &ident, &dwork, &kstat, &pbund, &cand, &dctl, &in_src};
@@ -420,8 +420,8 @@ void build_bundles_gdirect(gds_ctx* c, const uint32_t* S, const uint32_t* E, con
 // one parallel streaming pass, rank the candidates of partial bundles; the ordered walk is the
 // fallback when the candidates do not fit (or GDS_DIRECT_SELECT=walk asks for it).
 void direct_select(gds_ctx* c, const DirectPlan& dp, const uint32_t* S, const uint32_t* E,
-                   uint32_t ns, size_t N, uint32_t B, uint32_t* bm, size_t n_words,
-                   unsigned long long* totals, gds_result* out) {
+                   uint32_t ns, size_t N, uint32_t B, uint32_t* bm, unsigned long long* totals,
+                   gds_result* out) {
     cudaStream_t st = c->stream;
     BundleRec* bund = c->bund.as<BundleRec>();
     uint32_t* b_slot = c->b_slot.as<uint32_t>();
@@ -1124,7 +1124,7 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
                                                      : c->bitmap.get<uint32_t>(n_words + 1);
         if (do_solve) {
             GDS_CUDA(cudaMemsetAsync(bm, 0, n_words * 4, st));
-            if (B && direct.on) direct_select(c, direct, S, E, ns, N, B, bm, n_words, totals, out);
+            if (B && direct.on) direct_select(c, direct, S, E, ns, N, B, bm, totals, out);
             else if (B) {
                 {
                     KScope ks("select", 8ull * B + 8ull * N / 32, st);

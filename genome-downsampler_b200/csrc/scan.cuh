@@ -39,7 +39,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* total)
 }
 
 __global__ void __launch_bounds__(kScanThreads)
-k_scan_tiles(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+k_scan_tiles(const uint32_t* in, uint32_t* out /* may alias in: in-place scans */,
              uint32_t* __restrict__ tile_sums, size_t n) {
     __shared__ uint32_t total;
     size_t base = (size_t)blockIdx.x * kScanTile + (size_t)threadIdx.x * kScanItems;
