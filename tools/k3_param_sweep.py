@@ -11,7 +11,11 @@ from __graft_entry__ import load_package  # noqa: E402
 import bench  # noqa: E402
 
 pkg = load_package()
-wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "c4"]
+wname = sys.argv[1] if len(sys.argv) > 1 else "c4"
+if wname == "c3":  # config 3: 100 k reads over 30 kb, M=100 (same law as config 1)
+    wl = dict(bench.WORKLOADS["c1"], pairs=50_000)
+else:
+    wl = bench.WORKLOADS[wname]
 st, en, _, fx = bench.generate(wl, [0], pinned=False)
 dev = torch.device("cuda", 0)
 d_s, d_e = st.to(dev), en.to(dev)
@@ -33,9 +37,11 @@ def run(prm):
 
 
 base = None
-for seg in (32768, 16384, 8192, 65536):
+segs = (32768, 16384, 8192, 65536) if wl["L"] > 65536 else (0,)
+for seg in segs:
     for imin, lpct, rpct in ((64, 150, 1), (32, 100, 1), (16, 50, 1), (64, 50, 1), (128, 300, 1),
-                             (64, 150, 0), (64, 150, 5), (32, 50, 0)):
+                             (64, 150, 0), (64, 150, 5), (32, 50, 0), (256, 400, 1), (16, 25, 0),
+                             (8, 25, 0), (1000000, 150, 1)):
         r = run((imin, lpct, rpct, 0, seg))
         print("seg %6d interval_min %4d levels_pct %4d relabel_pct %d: K3 %7.3f ms total %7.3f ms "
               "comps %4d rounds_max %5d grs %4d bfs_levels %6d kept %d" %
