@@ -57,3 +57,31 @@ def test_no_cpu_fallback_without_a_device(pkg):
     with pytest.raises(pkg.GdsError) as ei:
         pkg.Solver(0)
     assert ei.value.code == 3  # GDS_ERR_CUDA
+
+
+def test_ctypes_structs_match_the_c_header(pkg, tmp_path):
+    # binding.py mirrors include/gds.h by hand: sizes and the offsets the binding relies on must be
+    # what a C compiler sees (a drifted struct would corrupt results silently)
+    import subprocess
+    from genome_downsampler_b200 import binding as B
+    probes = [("gds_reads", None), ("gds_filter", None), ("gds_params", None), ("gds_result", None),
+              ("gds_kernel_stat", None), ("gds_reads", "start16"), ("gds_reads", "len_min"),
+              ("gds_params", "bundle_mode"), ("gds_result", "n_reads_in"), ("gds_result", "fstar"),
+              ("gds_result", "kernel_launches"), ("gds_result", "bundle_path"), ("gds_result", "ms_h2d"),
+              ("gds_result", "ms_total")]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gds.h"', 'int main(void) {']
+    for st, fld in probes:
+        expr = "sizeof(%s)" % st if fld is None else "offsetof(%s, %s)" % (st, fld)
+        lines.append('  printf("%%zu\\n", (size_t)%s);' % expr)
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi_probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi_probe"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    mirror = {"gds_reads": B._Reads, "gds_filter": B._Filter, "gds_params": B._Params,
+              "gds_result": B._Result, "gds_kernel_stat": B._KStat}
+    want = [ctypes.sizeof(mirror[st]) if fld is None else getattr(mirror[st], fld).offset
+            for st, fld in probes]
+    assert got == want, list(zip(probes, got, want))
+
