@@ -279,6 +279,10 @@ k_direct_classify(const BundleRec* __restrict__ bund, const uint32_t* __restrict
 // per chain of dependent accesses (1.21 -> 1.39 ms, register pressure) helped; what remains is the
 // scattered traffic of 20 M candidates.  The queue does not have to hold a whole round: a hit that
 // finds it full takes the slow chain inline (only adversarial inputs get there).
+// Switching the parking off altogether (wrong results, timing only) takes 25 % off the kernel and
+// the kept-bit reductions cost nothing: what remains is one random shared-memory lookup per read,
+// 3.5 reads per clock and SM — the kernel handles 1.0 T reads/s where the histogram, at the HBM
+// bound with twice the bytes per read, handles 0.8 T.
 constexpr int kDmUnroll = 4;                                    // 512 reads per warp and round
 constexpr uint32_t kDmQueue = 256;                              // entries per warp
 constexpr uint32_t kDmQueueBytes = (kDmThreads / 32) * kDmQueue * 8;
