@@ -181,10 +181,25 @@ k_direct_bundles(const uint32_t* __restrict__ ghist, uint32_t ktot, DirectLayout
     }
     const uint32_t c = (v[0] != 0) + (v[1] != 0) + (v[2] != 0) + (v[3] != 0);
     uint32_t b = block_excl_scan(c, &total) + tile_offs[blockIdx.x];
-    if (c == 0) return;
+    const bool one_len = in_bid != nullptr;
+    if (i >= ktot || (c == 0 && !one_len)) return;
     const uint32_t k = find_u32(dl.kbase, dl.ns, i);  // regions are 32-aligned: same k for all 4
     const uint32_t local = i - dl.kbase[k];
     const uint32_t nb = dl.node_base[k];
+    if (one_len) {
+        // one read length: key == start node, so the difference array needs no atomics —
+        // diff[v] = (reads starting at v) - (reads ending before v) = hist[v] - hist[v - len];
+        // every node of the sample is written (the region covers ref_len + 1 slots)
+        const uint32_t L = dl.ref_len[k], len = dl.minlen;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t j = local + q;
+            if (j > L) continue;
+            const uint32_t ends = j >= len ? ghist[i + q - len] : 0u;
+            diff[nb + j] = (int32_t)v[q] - (int32_t)ends;
+        }
+        if (c == 0) return;
+    }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         if (!v[q]) continue;
@@ -195,13 +210,13 @@ k_direct_bundles(const uint32_t* __restrict__ ghist, uint32_t ktot, DirectLayout
         reinterpret_cast<uint4*>(bund)[b] = make_uint4(t, mult, 0u, s);
         b_t[b] = t;
         b_slot[b] = i + q;
-        if (in_bid) in_bid[b] = b;
-        atomicAdd(&diff[s], (int32_t)mult);
-        atomicAdd(&diff[t], -(int32_t)mult);
-        if (in_bid) {  // one read length: at most one bundle starts / ends at a node
+        if (one_len) {  // at most one bundle starts / ends at a node
+            in_bid[b] = b;
             outdeg[s] = 1u;
             indeg[t] = 1u;
         } else {
+            atomicAdd(&diff[s], (int32_t)mult);
+            atomicAdd(&diff[t], -(int32_t)mult);
             atomicAdd(&outdeg[s], 1u);
             atomicAdd(&indeg[t], 1u);
         }

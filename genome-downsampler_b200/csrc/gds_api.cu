@@ -260,7 +260,7 @@ bool direct_eligible(const gds_reads* rd, uint32_t ns, uint32_t minlen, uint32_t
     const uint64_t nlen = (uint64_t)maxlen - minlen + 1;
     uint64_t tot = 0;
     for (uint32_t k = 0; k < ns; ++k) {
-        const uint64_t kk = (uint64_t)rd->ref_len[k] * nlen;
+        const uint64_t kk = ((uint64_t)rd->ref_len[k] + 1) * nlen;  // one slot row per node
         if (kk > kDirectMaxKeys) return false;
         tot += (kk + 31) & ~31ull;
     }
@@ -281,7 +281,7 @@ void build_bundles_direct(gds_ctx* c, const gds_reads* rd, const uint32_t* S, co
     const uint64_t part_len = std::max<uint64_t>(65536, (N + 8ull * kNumSMs - 1) / (8ull * kNumSMs));
     uint32_t kmax = 32;
     for (uint32_t k = 0; k < ns; ++k) {
-        const uint32_t kk = (rd->ref_len[k] * nlen + 31u) & ~31u;
+        const uint32_t kk = ((rd->ref_len[k] + 1) * nlen + 31u) & ~31u;
         kmax = std::max(kmax, kk);
         kbase[k + 1] = kbase[k] + kk;
         const uint64_t nk = foff_host[k + 1] - foff_host[k];
@@ -338,7 +338,9 @@ void build_bundles_direct(gds_ctx* c, const gds_reads* rd, const uint32_t* S, co
     int32_t* diff = c->diff.get<int32_t>(n_nodes + 1);
     uint32_t* outdeg = c->outdeg.get<uint32_t>(n_nodes + 1);
     uint32_t* indeg = c->indeg.get<uint32_t>(n_nodes + 1);
-    GDS_CUDA(cudaMemsetAsync(diff, 0, (n_nodes + 1) * sizeof(int32_t), st));
+    // one read length: k_direct_bundles writes the difference array of every node itself
+    if (nlen == 1 && B) GDS_CUDA(cudaMemsetAsync(diff + n_nodes, 0, sizeof(int32_t), st));
+    else GDS_CUDA(cudaMemsetAsync(diff, 0, (n_nodes + 1) * sizeof(int32_t), st));
     GDS_CUDA(cudaMemsetAsync(outdeg, 0, (n_nodes + 1) * sizeof(uint32_t), st));
     GDS_CUDA(cudaMemsetAsync(indeg, 0, (n_nodes + 1) * sizeof(uint32_t), st));
     if (B) {
