@@ -15,7 +15,7 @@ HOST_BIN = os.path.join(HERE, "gds_host_test")
 HOST_LIB = os.path.join(HERE, "libgds_host.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC,-pthread", "-shared"]
 
 
 def _newer(target, sources):
@@ -58,8 +58,8 @@ def build_host(force=False):
     # the system g++ (the image's CXX wrapper links libstdc++ statically, which must not be
     # dlopen()ed into a process that already has libstdc++)
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    common = [cxx, "-O2", "-std=c++17", "-Wall", "-fPIC", "-I" + os.path.join(ROOT, "include"),
-              "-I" + os.path.join(hdir, "include")]
+    common = [cxx, "-O2", "-std=c++17", "-Wall", "-fPIC", "-pthread",
+              "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(hdir, "include")]
     link = ["-L" + HERE, "-lgds_b200", "-Wl,-rpath,$ORIGIN"]
     lib_srcs = [s for s in cpps if not s.endswith("host_test_main.cpp")]
     bin_srcs = [s for s in cpps if not s.endswith("host_c_api.cpp")]

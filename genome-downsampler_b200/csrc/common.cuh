@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -102,7 +103,10 @@ struct DevBuf {
         if (bytes > cap) {
             if (p) cudaFree(p);
             p = nullptr;
-            size_t want = bytes + bytes / 8 + 256;
+            // geometric growth: a context that is re-entered with slowly growing inputs (the
+            // reference's tester solves five cases on one instance) must not pay a cudaFree +
+            // cudaMalloc — tens of milliseconds with a device synchronisation — on every call
+            size_t want = std::max(bytes + bytes / 8 + 256, cap + cap / 2);
             cudaError_t e = cudaMalloc(&p, want);
             if (e != cudaSuccess) {
                 cap = 0;

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -451,7 +452,9 @@ void direct_select(gds_ctx* c, const DirectPlan& dp, const uint32_t* S, const ui
         out->partial_candidates = hctl[1];
         walk = hctl[2] != 0;
         if (!walk) {
-            uint32_t* cand = c->cand.get<uint32_t>((size_t)hctl[1] + 1);
+            // sized from the classification, but never below N/8 slots: the share of reads in
+            // partial bundles varies from call to call and regrowing the arena is expensive
+            uint32_t* cand = c->cand.get<uint32_t>(std::max<size_t>((size_t)hctl[1] + 1, N / 8));
             const unsigned long long per_read = (dp.global || dp.dl.nlen > 1) ? 8 : 4;
             if (dp.global) {
                 KScope ks("gdirect_mark", per_read * N + dp.ktot / 4 + 8ull * N / 32, st);
@@ -601,20 +604,50 @@ extern "C" void gds_kernel_profile_reset(gds_ctx* c) {
 
 extern "C" uint64_t gds_bitmap_to_indices(const uint32_t* bitmap, uint64_t n_bits,
                                           uint64_t* indices, uint64_t cap) {
-    uint64_t cnt = 0;
-    uint64_t words = (n_bits + 31) / 32;
-    for (uint64_t w = 0; w < words; ++w) {
+    // counts per chunk of words, then every chunk writes its slice: up to 16 host threads (a 50 M
+    // read solve keeps 17 M indices = 134 MB; one thread needs longer for that than the device
+    // for the whole path)
+    const uint64_t words = (n_bits + 31) / 32;
+    auto word_at = [&](uint64_t w) {
         uint32_t x = bitmap[w];
-        while (x) {
-            int bit = __builtin_ctz(x);
-            x &= x - 1;
-            uint64_t i = w * 32 + bit;
-            if (i >= n_bits) break;
-            if (cnt < cap && indices) indices[cnt] = i;
-            ++cnt;
+        if (w == words - 1 && (n_bits & 31)) x &= (1u << (n_bits & 31)) - 1u;  // bits past the end
+        return x;
+    };
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned nt = words < (1u << 16) ? 1u : std::min<unsigned>({hw, 16u, (unsigned)(words >> 14)});
+    const uint64_t per = (words + nt - 1) / nt;
+    std::vector<uint64_t> cnt(nt + 1, 0);
+    auto run = [&](auto fn) {
+        if (nt == 1) {
+            fn(0u);
+            return;
         }
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back([=, &fn] { fn(t); });
+        for (auto& t : th) t.join();
+    };
+    run([&](unsigned t) {
+        uint64_t c = 0;
+        for (uint64_t w = std::min(words, t * per), we = std::min(words, (t + 1) * per); w < we; ++w)
+            c += (uint64_t)__builtin_popcount(word_at(w));
+        cnt[t + 1] = c;
+    });
+    for (unsigned t = 0; t < nt; ++t) cnt[t + 1] += cnt[t];
+    if (indices && cap) {
+        run([&](unsigned t) {
+            uint64_t o = cnt[t];
+            for (uint64_t w = std::min(words, t * per), we = std::min(words, (t + 1) * per); w < we; ++w) {
+                uint32_t x = word_at(w);
+                while (x) {
+                    const int bit = __builtin_ctz(x);
+                    x &= x - 1;
+                    if (o < cap) indices[o] = w * 32 + bit;
+                    ++o;
+                }
+            }
+        });
     }
-    return cnt;
+    return cnt[nt];
 }
 
 extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,

@@ -12,11 +12,20 @@ import bench  # noqa: E402
 
 pkg = load_package()
 wname = sys.argv[1] if len(sys.argv) > 1 else "c4"
+SHAPES = ("uniform1000", "low_sides", "hole", "zero_sides")  # coverage_tester.cpp:120-175
 if wname == "c3":  # config 3: 100 k reads over 30 kb, M=100 (same law as config 1)
     wl = dict(bench.WORKLOADS["c1"], pairs=50_000)
+elif wname in SHAPES:  # the reference's own random test cases: 2 M reads / 30 kb, M = 8000 (1000)
+    from __graft_entry__ import load_oracle
+    wl = dict(bench.WORKLOADS["c1"], pairs=1_000_000, M=1000 if wname == "uniform1000" else 8000)
 else:
     wl = bench.WORKLOADS[wname]
-st, en, _, fx = bench.generate(wl, [0], pinned=False)
+if wname in SHAPES:
+    s_, e_, _, _ = load_oracle().gen_reads(12345, 1_000_000, 30_000, 150,
+                                           "uniform" if wname == "uniform1000" else wname)
+    st, en, fx = torch.from_numpy(s_.view(np.int32)), torch.from_numpy(e_.view(np.int32)), None
+else:
+    st, en, _, fx = bench.generate(wl, [0], pinned=False)
 dev = torch.device("cuda", 0)
 d_s, d_e = st.to(dev), en.to(dev)
 n = d_s.numel()
