@@ -60,7 +60,7 @@ def build_host(force=False):
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     common = [cxx, "-O2", "-std=c++17", "-Wall", "-fPIC", "-pthread",
               "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(hdir, "include")]
-    link = ["-L" + HERE, "-lgds_b200", "-Wl,-rpath,$ORIGIN"]
+    link = ["-L" + HERE, "-lgds_b200", "-lz", "-Wl,-rpath,$ORIGIN"]
     lib_srcs = [s for s in cpps if not s.endswith("host_test_main.cpp")]
     bin_srcs = [s for s in cpps if not s.endswith("host_c_api.cpp")]
     subprocess.check_call(common + ["-shared", "-o", HOST_LIB] + lib_srcs + link)

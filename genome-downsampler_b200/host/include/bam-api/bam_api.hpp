@@ -1,7 +1,7 @@
 // bam_api::BamApi — host-side data access mirror of libs/bam-api/include/bam-api/bam_api.hpp for
-// the quasi-MCP path.  In-memory construction (bam_api.cpp:44-47) carries all tests and
-// benchmarks; htslib BAM I/O (bam_api.cpp:359-656) is out of scope here (htslib is absent from
-// this image) and stays the reference's own code in an integration.
+// the quasi-MCP path.  In-memory construction (bam_api.cpp:44-47) carries the solver tests and
+// benchmarks; BAM files are read and written (bam_api.cpp:359-656) through the zlib-only scanner
+// of bam-api/bgzf_bam.hpp, since htslib is absent from this image.
 //
 // Addition for the B200 path: a BamApi can hold UNFILTERED pair-ordered reads plus the filter
 // settings ("pending filter").  A device solver then runs the filter on the GPU and hands the
@@ -43,6 +43,10 @@ struct AmpliconSet {
 
 class BamApi {
    public:
+    // file-backed, as in the reference: the BAM is read on the first request for its reads.  The
+    // reads stay UNFILTERED ("pending filter", below) until a device solver or a CPU consumer
+    // asks, so the filter can run on the GPU without changing what any caller observes.
+    BamApi(const std::filesystem::path& input_filepath, const BamApiConfig& config);
     explicit BamApi(const AOSPairedReads& paired_reads);
     explicit BamApi(const SOAPairedReads& paired_reads);
     // unfiltered pair-ordered reads + filter settings (BED/TSV parsed on the host, bam_api.cpp:53-187)
@@ -55,12 +59,30 @@ class BamApi {
     const PairedReads& get_paired_reads() const;
     const std::vector<BAMReadId>& get_filtered_out_reads() const { return filtered_out_reads_; }
     std::vector<ReadIndex> find_pairs(const std::vector<ReadIndex>& ids) const;
+    // returns number of reads written (bam_api.cpp:509-532)
+    std::uint32_t write_paired_reads(const std::filesystem::path& output_filepath,
+                                     std::vector<ReadIndex>& active_ids) const;
+    std::uint32_t write_bam_api_filtered_out_reads(const std::filesystem::path& output_filepath);
+    // private in the reference (bam_api.cpp:534-656); public here so tests can reach it
+    static std::uint32_t write_bam(const std::filesystem::path& input_filepath,
+                                   const std::filesystem::path& output_filepath,
+                                   std::vector<BAMReadId>& bam_ids, std::uint32_t hts_thread_count);
+
     std::vector<std::uint32_t> find_input_cover();
     std::vector<std::uint32_t> find_filtered_cover(const std::vector<ReadIndex>& active_ids);
 
     // ---- B200 path hooks ----
-    bool has_pending_filter() const { return pending_filter_; }
-    const SOAPairedReads& unfiltered_soa() const { return soa_paired_reads_; }
+    bool has_pending_filter() {
+        ensure_loaded();
+        return pending_filter_;
+    }
+    const SOAPairedReads& unfiltered_soa() {
+        ensure_loaded();
+        return soa_paired_reads_;
+    }
+    // records in the input BAM (0 for in-memory construction) and timings of the last read_bam
+    std::uint64_t bam_record_count() const { return bam_record_count_; }
+    double read_bam_seconds() const { return read_bam_seconds_; }
     std::uint32_t min_seq_length() const { return min_seq_length_; }
     std::uint32_t min_mapq() const { return min_mapq_; }
     AmpliconBehaviour amplicon_behaviour() const { return amplicon_behaviour_; }
@@ -73,7 +95,14 @@ class BamApi {
                                       const std::filesystem::path& tsv);
 
    private:
+    void ensure_loaded();
+    void read_bam(const std::filesystem::path& input_filepath, SOAPairedReads& unfiltered);
     void run_host_filter();
+    std::filesystem::path input_filepath_;
+    bool file_pending_ = false;
+    std::uint32_t hts_thread_count_ = 1;
+    std::uint64_t bam_record_count_ = 0;
+    double read_bam_seconds_ = 0;
     SOAPairedReads soa_paired_reads_;
     bool is_soa_loaded_ = false;
     AOSPairedReads aos_paired_reads_;

@@ -2,6 +2,7 @@
 // (same libstdc++ engines and distributions, same draw order => same streams for equal seeds).
 #pragma once
 #include <cstdint>
+#include <filesystem>
 #include <functional>
 #include <random>
 #include <vector>
@@ -46,4 +47,16 @@ void rand_reads_amplicon_soa(std::mt19937& generator, bam_api::ReadIndex pairs_c
                              const std::vector<uint32_t>& amp_end, double p_inside,
                              uint32_t min_len, uint32_t max_len, const SoaOut& out,
                              int32_t max_quality = kMaxGenQuality);
+
+// Synthetic reads as a single-contig BAM file, so the BAM front end of the path can be measured
+// and tested on the same inputs (the reference has no such writer: its generator only feeds the
+// in-memory BamApi constructors).  Read i becomes one record: QNAME "p<i/2>", FLAG paired +
+// first/second mate, CIGAR <seq_len>M (plus D or S so that it spans start..end exactly), random
+// bases and qualities, no tags.  coordinate_sorted orders the records by start (stable), which
+// separates mates the way a sorted BAM does; otherwise mates are adjacent in file order.
+// Returns the number of records written.
+uint64_t write_synthetic_bam(const std::filesystem::path& path, uint64_t n, uint32_t genome_length,
+                             const uint32_t* start, const uint32_t* end, const uint8_t* mapq,
+                             const uint32_t* seq_len, bool coordinate_sorted, uint32_t threads,
+                             uint32_t seed = 1);
 }  // namespace reads_gen

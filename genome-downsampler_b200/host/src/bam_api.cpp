@@ -3,11 +3,15 @@
 #include "bam-api/bam_api.hpp"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <map>
 #include <sstream>
+#include <stdexcept>
 
+#include "bam-api/bgzf_bam.hpp"
 #include "logging/log.hpp"
 
 namespace bam_api {
@@ -17,6 +21,17 @@ bool AmpliconSet::member_includes_both(const Read& a, const Read& b) const {
     for (const Amplicon& amp : amplicons)
         if (amp.includes(a) && amp.includes(b)) return true;
     return false;
+}
+
+BamApi::BamApi(const std::filesystem::path& input_filepath, const BamApiConfig& config)
+    : input_filepath_(input_filepath), file_pending_(true),
+      hts_thread_count_(config.hts_thread_count), min_seq_length_(config.min_seq_length),
+      min_mapq_(config.min_mapq) {
+    // bam_api.cpp:30-42
+    if (!config.bed_filepath.empty()) {
+        amplicon_set_ = load_amplicons(config.bed_filepath, config.tsv_filepath);
+        amplicon_behaviour_ = config.amplicon_behaviour;
+    }
 }
 
 BamApi::BamApi(const AOSPairedReads& paired_reads)
@@ -113,11 +128,20 @@ void BamApi::apply_pair_filter(const std::vector<std::uint8_t>& pair_pass) {
     kept.ref_genome_length = soa_paired_reads_.ref_genome_length;
     const ReadIndex n = soa_paired_reads_.get_reads_count();
     filtered_out_reads_.clear();
+    // file-backed: every record of the BAM that is not in a surviving pair is filtered out,
+    // never-paired records included (is_accepted, bam_api.cpp:430,461-478)
+    std::vector<bool> accepted(bam_record_count_, false);
     for (ReadIndex i = 0; i < n; ++i) {
         ReadIndex p = i / 2;
-        if (p < pair_pass.size() && pair_pass[p]) kept.push_back(soa_paired_reads_.get_read_by_index(i));
-        else filtered_out_reads_.push_back(soa_paired_reads_.ids[i]);
+        if (p < pair_pass.size() && pair_pass[p]) {
+            kept.push_back(soa_paired_reads_.get_read_by_index(i));
+            if (bam_record_count_) accepted[soa_paired_reads_.ids[i]] = true;
+        } else if (!bam_record_count_) {
+            filtered_out_reads_.push_back(soa_paired_reads_.ids[i]);
+        }
     }
+    for (BAMReadId id = 0; id < bam_record_count_; ++id)
+        if (!accepted[id]) filtered_out_reads_.push_back(id);
     soa_paired_reads_ = std::move(kept);
     is_aos_loaded_ = false;
     pending_filter_ = false;
@@ -133,6 +157,7 @@ void BamApi::run_host_filter() {
 }
 
 const SOAPairedReads& BamApi::get_paired_reads_soa() {
+    ensure_loaded();
     if (pending_filter_) run_host_filter();
     if (!is_soa_loaded_) {
         soa_paired_reads_.from(aos_paired_reads_);
@@ -142,6 +167,7 @@ const SOAPairedReads& BamApi::get_paired_reads_soa() {
 }
 
 const AOSPairedReads& BamApi::get_paired_reads_aos() {
+    ensure_loaded();
     if (pending_filter_) run_host_filter();
     if (!is_aos_loaded_) {
         aos_paired_reads_.from(soa_paired_reads_);
@@ -173,6 +199,7 @@ std::vector<ReadIndex> BamApi::find_pairs(const std::vector<ReadIndex>& ids) con
 }
 
 std::vector<std::uint32_t> BamApi::find_input_cover() {
+    ensure_loaded();
     if (pending_filter_) run_host_filter();
     const PairedReads& pr = get_paired_reads();
     std::vector<std::uint32_t> cov(pr.ref_genome_length, 0);
@@ -191,6 +218,168 @@ std::vector<std::uint32_t> BamApi::find_filtered_cover(const std::vector<ReadInd
         for (Index j = r.start_ind; j <= r.end_ind; ++j) ++cov[j];
     }
     return cov;
+}
+
+// ---------------------------------------------------------------- BAM files
+
+namespace {
+
+// QNAME -> first read seen with it.  The reference keeps a std::map<std::string, Read> that is
+// never erased from (bam_api.cpp:425-466); an open-addressed table over a byte arena does the
+// same job without a node allocation per read.
+class QnameTable {
+   public:
+    struct Slot {
+        std::uint64_t hash = 0;
+        std::uint64_t name_off = 0;
+        Read read;
+        Read partner;               // the later read whose arrival may have swapped the entry
+        std::uint8_t name_len = 0;
+        bool used = false;
+        bool swap_pending = false;  // entry becomes `partner` iff that pair passed the filter
+    };
+    QnameTable() : slots_(1u << 16) {}
+    Slot* find(std::uint64_t h, const char* name, std::uint8_t len) {
+        for (std::size_t i = h & (slots_.size() - 1);; i = (i + 1) & (slots_.size() - 1)) {
+            Slot& s = slots_[i];
+            if (!s.used) return nullptr;
+            if (s.hash == h && s.name_len == len && std::memcmp(arena_.data() + s.name_off, name, len) == 0)
+                return &s;
+        }
+    }
+    void insert(std::uint64_t h, const char* name, std::uint8_t len, const Read& r) {
+        if ((count_ + 1) * 10 > slots_.size() * 6) grow();
+        Slot s;
+        s.hash = h;
+        s.name_off = arena_.size();
+        s.name_len = len;
+        s.read = r;
+        s.used = true;
+        arena_.insert(arena_.end(), name, name + len);
+        place(slots_, s);
+        ++count_;
+    }
+
+   private:
+    static void place(std::vector<Slot>& t, const Slot& s) {
+        std::size_t i = s.hash & (t.size() - 1);
+        while (t[i].used) i = (i + 1) & (t.size() - 1);
+        t[i] = s;
+    }
+    void grow() {
+        std::vector<Slot> bigger(slots_.size() * 2);
+        for (const Slot& s : slots_)
+            if (s.used) place(bigger, s);
+        slots_.swap(bigger);
+    }
+    std::vector<Slot> slots_;
+    std::vector<char> arena_;
+    std::size_t count_ = 0;
+};
+
+}  // namespace
+
+void BamApi::ensure_loaded() {
+    if (!file_pending_) return;
+    file_pending_ = false;
+    read_bam(input_filepath_, soa_paired_reads_);
+    is_soa_loaded_ = true;
+    pending_filter_ = true;
+}
+
+// bam_api.cpp:359-507 without the filter: every QNAME-matched pair lands in `unfiltered` in
+// pair-completion order, first mate at the even index (the swap of :456-458).  The filter the
+// reference applies inside this loop (:438-441) runs afterwards over the pairs — on the device
+// for quasi-mcp-b200, on the host otherwise — and apply_pair_filter() leaves the same arrays and
+// the same filtered_out_reads_ the reference's loop does.
+void BamApi::read_bam(const std::filesystem::path& input_filepath, SOAPairedReads& unfiltered) {
+    LOG_WITH_LEVEL(logging::INFO) << "Reading " << input_filepath.filename() << " input file...";
+    auto t0 = std::chrono::high_resolution_clock::now();
+    try {
+        bgzf::BamScanner scanner(input_filepath, hts_thread_count_);
+        if (scanner.header().ref_lengths.empty()) throw std::runtime_error("BAM header lists no reference sequence");
+        unfiltered.clear();
+        unfiltered.ref_genome_length = scanner.header().ref_lengths[0];  // :421 target_len[0]
+        QnameTable table;
+        bgzf::RecordChunk chunk;
+        BAMReadId id = 0;
+        while (scanner.next(chunk)) {
+            for (const bgzf::RecordFields& f : chunk.records) {
+                // Read::Read(id, bam1_t*), read.cpp:5-14: end = pos + bam_cigar2rlen - 1
+                Read cur(id, static_cast<Index>(static_cast<std::int64_t>(f.pos)),
+                         static_cast<Index>(static_cast<std::uint64_t>(static_cast<std::int64_t>(f.pos)) + f.ref_len - 1),
+                         f.mapq, static_cast<std::uint32_t>(f.l_seq), (f.flag & 0x40) != 0);
+                const char* name = chunk.qname(f);
+                if (QnameTable::Slot* s = table.find(f.qname_hash, name, f.l_qname)) {
+                    // a QNAME seen a third time pairs with whatever the map holds by then: the
+                    // reference swaps the map entry with the second read only when that pair
+                    // survived the filter (the `continue` of :438-441 skips the swap)
+                    if (s->swap_pending) {
+                        if (!should_be_filtered_out(s->read, s->partner)) s->read = s->partner;
+                        s->swap_pending = false;
+                    }
+                    if (cur.is_first_read) {
+                        unfiltered.push_back(cur);
+                        unfiltered.push_back(s->read);
+                        s->partner = cur;
+                        s->swap_pending = true;
+                    } else {
+                        unfiltered.push_back(s->read);
+                        unfiltered.push_back(cur);
+                    }
+                } else {
+                    table.insert(f.qname_hash, name, f.l_qname, cur);
+                }
+                ++id;
+            }
+        }
+        bam_record_count_ = id;
+    } catch (const std::exception& e) {
+        LOG_WITH_LEVEL(logging::ERROR) << e.what();
+        std::exit(EXIT_FAILURE);
+    }
+    read_bam_seconds_ = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+    LOG_WITH_LEVEL(logging::DEBUG) << "BamApi: " << bam_record_count_ << " reads have been read, "
+                                   << unfiltered.get_reads_count() << " in pairs; read_bam took "
+                                   << read_bam_seconds_ << " seconds";
+}
+
+std::uint32_t BamApi::write_paired_reads(const std::filesystem::path& output_filepath,
+                                         std::vector<ReadIndex>& active_ids) const {
+    // bam_api.cpp:509-524: in-memory indices -> BAM ordinals
+    LOG_WITH_LEVEL(logging::INFO) << "Writing solution of size " << active_ids.size() << " reads "
+                                  << output_filepath.filename() << "...";
+    const PairedReads& paired_reads = get_paired_reads();
+    std::vector<BAMReadId> active_bam_ids;
+    active_bam_ids.reserve(active_ids.size());
+    for (const auto& id : active_ids) active_bam_ids.push_back(paired_reads.get_read_by_index(id).bam_id);
+    return write_bam(input_filepath_, output_filepath, active_bam_ids, hts_thread_count_);
+}
+
+std::uint32_t BamApi::write_bam_api_filtered_out_reads(const std::filesystem::path& output_filepath) {
+    // bam_api.cpp:526-532
+    LOG_WITH_LEVEL(logging::INFO) << "Writing " << filtered_out_reads_.size()
+                                  << " preprocessing filtered out reads to "
+                                  << output_filepath.filename() << "...";
+    return write_bam(input_filepath_, output_filepath, filtered_out_reads_, hts_thread_count_);
+}
+
+std::uint32_t BamApi::write_bam(const std::filesystem::path& input_filepath,
+                                const std::filesystem::path& output_filepath,
+                                std::vector<BAMReadId>& bam_ids, std::uint32_t hts_thread_count) {
+    if (output_filepath.extension() != ".bam") {
+        // the reference hands any other extension to htslib in SAM text mode (:566); the text
+        // formatter is not rebuilt here
+        LOG_WITH_LEVEL(logging::ERROR) << "Could not open " << output_filepath
+                                       << " (only .bam output is supported by the zlib-only writer)";
+        std::exit(EXIT_FAILURE);
+    }
+    try {
+        return bgzf::copy_bam_records(input_filepath, output_filepath, bam_ids, hts_thread_count);
+    } catch (const std::exception& e) {
+        LOG_WITH_LEVEL(logging::ERROR) << e.what();
+        std::exit(EXIT_FAILURE);
+    }
 }
 
 }  // namespace bam_api

@@ -3,7 +3,10 @@
 // Built into libgds_host.so next to libgds_b200.so.
 #include <cstdint>
 #include <cstring>
+#include <filesystem>
 #include <random>
+#include <stdexcept>
+#include <vector>
 
 #include "reads_gen.hpp"
 #include "solver_manager.hpp"
@@ -72,5 +75,114 @@ int64_t gdsh_plugin_solve(const char* algorithm, uint64_t n, uint32_t genome_len
     uint64_t k = sol->size() < cap ? sol->size() : cap;
     std::memcpy(kept_out, sol->data(), k * sizeof(uint64_t));
     return static_cast<int64_t>(sol->size());
+}
+// ---- BAM files: the file-backed BamApi behind a handle ----
+
+int64_t gdsh_write_synthetic_bam(const char* path, uint64_t n, uint32_t genome_len,
+                                 const uint32_t* start, const uint32_t* end, const uint8_t* mapq,
+                                 const uint32_t* seq_len, int coordinate_sorted, uint32_t threads,
+                                 uint32_t seed) {
+    try {
+        return static_cast<int64_t>(reads_gen::write_synthetic_bam(path, n, genome_len, start, end, mapq,
+                                                                   seq_len, coordinate_sorted != 0, threads, seed));
+    } catch (const std::exception&) {
+        return -1;
+    }
+}
+
+// BamApi(input_filepath, config) as App builds it (src/app.cpp:113-128); bed/tsv may be empty.
+// amplicon_behaviour: 0 IGNORE, 1 FILTER, 2 GRADE
+void* gdsh_bam_open(const char* path, const char* bed, const char* tsv, uint32_t min_len,
+                    uint32_t min_mapq, int amplicon_behaviour, uint32_t threads) {
+    bam_api::BamApiConfig cfg;
+    cfg.bed_filepath = bed ? bed : "";
+    cfg.tsv_filepath = tsv ? tsv : "";
+    cfg.min_seq_length = min_len;
+    cfg.min_mapq = min_mapq;
+    cfg.hts_thread_count = threads;
+    cfg.amplicon_behaviour = static_cast<bam_api::AmpliconBehaviour>(amplicon_behaviour);
+    return new bam_api::BamApi(std::filesystem::path(path), cfg);
+}
+
+void gdsh_bam_close(void* h) { delete static_cast<bam_api::BamApi*>(h); }
+
+static uint64_t copy_soa(const bam_api::SOAPairedReads& soa, uint64_t cap, uint64_t* ids,
+                         uint64_t* start, uint64_t* end, uint32_t* quality, uint32_t* seq_len,
+                         uint8_t* is_first) {
+    uint64_t n = soa.get_reads_count(), k = n < cap ? n : cap;
+    for (uint64_t i = 0; i < k; ++i) {
+        if (ids) ids[i] = soa.ids[i];
+        if (start) start[i] = soa.start_inds[i];
+        if (end) end[i] = soa.end_inds[i];
+        if (quality) quality[i] = soa.qualities[i];
+        if (seq_len) seq_len[i] = soa.seq_lengths[i];
+        if (is_first) is_first[i] = soa.is_first_reads[i];
+    }
+    return n;
+}
+
+// the pair-ordered reads BEFORE the filter (reads the file on first use); returns their count
+uint64_t gdsh_bam_unfiltered(void* h, uint64_t cap, uint64_t* ids, uint64_t* start, uint64_t* end,
+                             uint32_t* quality, uint32_t* seq_len, uint8_t* is_first) {
+    auto* api = static_cast<bam_api::BamApi*>(h);
+    if (!api->has_pending_filter()) return 0;
+    return copy_soa(api->unfiltered_soa(), cap, ids, start, end, quality, seq_len, is_first);
+}
+
+// get_paired_reads_soa(): the state read_bam leaves (host filter unless a device solve ran first)
+uint64_t gdsh_bam_reads(void* h, uint64_t cap, uint64_t* ids, uint64_t* start, uint64_t* end,
+                        uint32_t* quality, uint32_t* seq_len, uint8_t* is_first) {
+    auto* api = static_cast<bam_api::BamApi*>(h);
+    return copy_soa(api->get_paired_reads_soa(), cap, ids, start, end, quality, seq_len, is_first);
+}
+
+uint64_t gdsh_bam_filtered_out(void* h, uint64_t cap, uint64_t* out) {
+    const auto& v = static_cast<bam_api::BamApi*>(h)->get_filtered_out_reads();
+    std::memcpy(out, v.data(), (v.size() < cap ? v.size() : cap) * sizeof(uint64_t));
+    return v.size();
+}
+
+uint64_t gdsh_bam_ref_length(void* h) {
+    auto* api = static_cast<bam_api::BamApi*>(h);
+    api->has_pending_filter();
+    return api->get_paired_reads().ref_genome_length;
+}
+
+uint64_t gdsh_bam_record_count(void* h) {
+    auto* api = static_cast<bam_api::BamApi*>(h);
+    api->has_pending_filter();
+    return api->bam_record_count();
+}
+
+double gdsh_bam_read_seconds(void* h) { return static_cast<bam_api::BamApi*>(h)->read_bam_seconds(); }
+
+// solve through the plugin interface on the file-backed BamApi (src/app.cpp:130-135)
+int64_t gdsh_bam_solve(void* h, const char* algorithm, uint32_t max_coverage, uint64_t* kept_out,
+                       uint64_t cap) {
+    static SolverManager manager;
+    if (!manager.contains(algorithm)) return -1;
+    auto sol = manager.get(algorithm).solve(max_coverage, *static_cast<bam_api::BamApi*>(h));
+    uint64_t k = sol->size() < cap ? sol->size() : cap;
+    std::memcpy(kept_out, sol->data(), k * sizeof(uint64_t));
+    return static_cast<int64_t>(sol->size());
+}
+
+// find_pairs + write_paired_reads as App::execute chains them (src/app.cpp:141-147)
+int64_t gdsh_bam_write_solution(void* h, const char* out_path, const uint64_t* kept, uint64_t n,
+                                int with_pairs) {
+    auto* api = static_cast<bam_api::BamApi*>(h);
+    std::vector<bam_api::ReadIndex> ids(kept, kept + n);
+    if (with_pairs) ids = api->find_pairs(ids);
+    return api->write_paired_reads(out_path, ids);
+}
+
+int64_t gdsh_bam_write_filtered_out(void* h, const char* out_path) {
+    return static_cast<bam_api::BamApi*>(h)->write_bam_api_filtered_out_reads(out_path);
+}
+
+int64_t gdsh_write_bam(const char* in_path, const char* out_path, const uint64_t* bam_ids, uint64_t n,
+                       uint32_t threads) {
+    std::vector<bam_api::BAMReadId> ids(bam_ids, bam_ids + n);
+    return bam_api::BamApi::write_bam(in_path, out_path, ids, threads);
 }
 }

@@ -29,6 +29,31 @@ def load():
         L.gdsh_plugin_solve.argtypes = [C.c_char_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p,
                                         C.c_uint32, C.c_void_p, C.c_uint64]
         L.gdsh_plugin_solve.restype = C.c_int64
+        vp, u64, u32 = C.c_void_p, C.c_uint64, C.c_uint32
+        L.gdsh_write_synthetic_bam.argtypes = [C.c_char_p, u64, u32, vp, vp, vp, vp, C.c_int, u32, u32]
+        L.gdsh_write_synthetic_bam.restype = C.c_int64
+        L.gdsh_bam_open.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, u32, u32, C.c_int, u32]
+        L.gdsh_bam_open.restype = vp
+        L.gdsh_bam_close.argtypes = [vp]
+        L.gdsh_bam_close.restype = None
+        for f in (L.gdsh_bam_unfiltered, L.gdsh_bam_reads):
+            f.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp]
+            f.restype = u64
+        L.gdsh_bam_filtered_out.argtypes = [vp, u64, vp]
+        L.gdsh_bam_filtered_out.restype = u64
+        for f in (L.gdsh_bam_ref_length, L.gdsh_bam_record_count):
+            f.argtypes = [vp]
+            f.restype = u64
+        L.gdsh_bam_read_seconds.argtypes = [vp]
+        L.gdsh_bam_read_seconds.restype = C.c_double
+        L.gdsh_bam_solve.argtypes = [vp, C.c_char_p, u32, vp, u64]
+        L.gdsh_bam_solve.restype = C.c_int64
+        L.gdsh_bam_write_solution.argtypes = [vp, C.c_char_p, vp, u64, C.c_int]
+        L.gdsh_bam_write_solution.restype = C.c_int64
+        L.gdsh_bam_write_filtered_out.argtypes = [vp, C.c_char_p]
+        L.gdsh_bam_write_filtered_out.restype = C.c_int64
+        L.gdsh_write_bam.argtypes = [C.c_char_p, C.c_char_p, vp, u64, u32]
+        L.gdsh_write_bam.restype = C.c_int64
         _LIB = L
     return _LIB
 
@@ -87,3 +112,98 @@ def plugin_solve(algorithm, start, end, genome_len, max_coverage):
     if k < 0:
         raise KeyError("unknown algorithm %r" % algorithm)
     return out[:k]
+
+
+# ---- BAM files: the file-backed BamApi (bam_api.cpp:30-42, :359-656) ----
+
+AMPLICON_BEHAVIOUR = {"ignore": 0, "filter": 1, "grade": 2}
+
+
+def write_synthetic_bam(path, genome_len, start, end, mapq=None, seq_len=None, coordinate_sorted=False,
+                        threads=4, seed=1):
+    start = np.ascontiguousarray(start, np.uint32)
+    end = np.ascontiguousarray(end, np.uint32)
+    mapq = None if mapq is None else np.ascontiguousarray(mapq, np.uint8)
+    seq_len = None if seq_len is None else np.ascontiguousarray(seq_len, np.uint32)
+    rc = load().gdsh_write_synthetic_bam(str(path).encode(), len(start), genome_len, start.ctypes.data,
+                                         end.ctypes.data, mapq.ctypes.data if mapq is not None else None,
+                                         seq_len.ctypes.data if seq_len is not None else None,
+                                         int(coordinate_sorted), threads, seed)
+    if rc < 0:
+        raise IOError("cannot write %s" % path)
+    return rc
+
+
+class BamFile:
+    """BamApi(input_filepath, config).  Errors in the file end the process (the reference's
+    log-and-exit), so tests of broken inputs run in a subprocess."""
+
+    def __init__(self, path, min_len=0, min_mapq=0, bed=None, tsv=None, amplicon_behaviour="filter",
+                 threads=1):
+        self._L = load()
+        self._h = self._L.gdsh_bam_open(str(path).encode(), str(bed).encode() if bed else None,
+                                        str(tsv).encode() if tsv else None, min_len, min_mapq,
+                                        AMPLICON_BEHAVIOUR[amplicon_behaviour], threads)
+
+    def close(self):
+        if self._h:
+            self._L.gdsh_bam_close(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _columns(self, fn):
+        n = fn(self._h, 0, None, None, None, None, None, None)
+        cols = {"bam_id": np.empty(n, np.uint64), "start": np.empty(n, np.uint64),
+                "end": np.empty(n, np.uint64), "quality": np.empty(n, np.uint32),
+                "seq_length": np.empty(n, np.uint32), "is_first": np.empty(n, np.uint8)}
+        fn(self._h, n, *[c.ctypes.data for c in cols.values()])
+        return cols
+
+    def unfiltered(self):
+        """Pair-ordered reads before the filter ({} once the filter has been applied)."""
+        return self._columns(self._L.gdsh_bam_unfiltered)
+
+    def reads(self):
+        """get_paired_reads_soa(): post-filter arrays."""
+        return self._columns(self._L.gdsh_bam_reads)
+
+    def filtered_out(self):
+        n = self._L.gdsh_bam_filtered_out(self._h, 0, None)
+        out = np.empty(n, np.uint64)
+        self._L.gdsh_bam_filtered_out(self._h, n, out.ctypes.data)
+        return out
+
+    @property
+    def ref_length(self):
+        return self._L.gdsh_bam_ref_length(self._h)
+
+    @property
+    def record_count(self):
+        return self._L.gdsh_bam_record_count(self._h)
+
+    @property
+    def read_seconds(self):
+        return self._L.gdsh_bam_read_seconds(self._h)
+
+    def solve(self, algorithm, max_coverage):
+        cap = max(int(self.record_count), 1)
+        out = np.empty(cap, np.uint64)
+        k = self._L.gdsh_bam_solve(self._h, algorithm.encode(), max_coverage, out.ctypes.data, cap)
+        if k < 0:
+            raise KeyError("unknown algorithm %r" % algorithm)
+        return out[:k]
+
+    def write_solution(self, out_path, kept, with_pairs=True):
+        kept = np.ascontiguousarray(kept, np.uint64)
+        return self._L.gdsh_bam_write_solution(self._h, str(out_path).encode(), kept.ctypes.data,
+                                               len(kept), int(with_pairs))
+
+    def write_filtered_out(self, out_path):
+        return self._L.gdsh_bam_write_filtered_out(self._h, str(out_path).encode())
+
+
+def write_bam(in_path, out_path, bam_ids, threads=1):
+    ids = np.ascontiguousarray(bam_ids, np.uint64)
+    return load().gdsh_write_bam(str(in_path).encode(), str(out_path).encode(), ids.ctypes.data,
+                                 len(ids), threads)
