@@ -52,7 +52,7 @@ void rand_reads_amplicon_soa(std::mt19937& generator, bam_api::ReadIndex pairs_c
 // and tested on the same inputs (the reference has no such writer: its generator only feeds the
 // in-memory BamApi constructors).  Read i becomes one record: QNAME "p<i/2>", FLAG paired +
 // first/second mate, CIGAR <seq_len>M (plus D or S so that it spans start..end exactly), random
-// bases and qualities, no tags.  coordinate_sorted orders the records by start (stable), which
+// bases, binned qualities (37/25/11), no tags.  coordinate_sorted orders the records by start (stable), which
 // separates mates the way a sorted BAM does; otherwise mates are adjacent in file order.
 // Returns the number of records written.
 uint64_t write_synthetic_bam(const std::filesystem::path& path, uint64_t n, uint32_t genome_length,

@@ -300,38 +300,60 @@ void BamApi::read_bam(const std::filesystem::path& input_filepath, SOAPairedRead
         if (scanner.header().ref_lengths.empty()) throw std::runtime_error("BAM header lists no reference sequence");
         unfiltered.clear();
         unfiltered.ref_genome_length = scanner.header().ref_lengths[0];  // :421 target_len[0]
-        QnameTable table;
+        // QNAMEs are split over one table per thread by hash, so the lookups of a chunk run in
+        // parallel while every name still meets its earlier records in file order; the pairs are
+        // then appended serially in the order their second record appears (pair-completion order)
+        const std::uint32_t parts = std::max<std::uint32_t>(hts_thread_count_, 1);
+        std::vector<QnameTable> tables(parts);
+        std::vector<Read> mate;
+        std::vector<std::uint8_t> completes;  // 1: (map entry, record)  2: (record, map entry)
         bgzf::RecordChunk chunk;
         BAMReadId id = 0;
+        auto make_read = [](BAMReadId rid, const bgzf::RecordFields& f) {
+            // Read::Read(id, bam1_t*), read.cpp:5-14: end = pos + bam_cigar2rlen - 1
+            return Read(rid, static_cast<Index>(static_cast<std::int64_t>(f.pos)),
+                        static_cast<Index>(static_cast<std::uint64_t>(static_cast<std::int64_t>(f.pos)) + f.ref_len - 1),
+                        f.mapq, static_cast<std::uint32_t>(f.l_seq), (f.flag & 0x40) != 0);
+        };
         while (scanner.next(chunk)) {
-            for (const bgzf::RecordFields& f : chunk.records) {
-                // Read::Read(id, bam1_t*), read.cpp:5-14: end = pos + bam_cigar2rlen - 1
-                Read cur(id, static_cast<Index>(static_cast<std::int64_t>(f.pos)),
-                         static_cast<Index>(static_cast<std::uint64_t>(static_cast<std::int64_t>(f.pos)) + f.ref_len - 1),
-                         f.mapq, static_cast<std::uint32_t>(f.l_seq), (f.flag & 0x40) != 0);
-                const char* name = chunk.qname(f);
-                if (QnameTable::Slot* s = table.find(f.qname_hash, name, f.l_qname)) {
-                    // a QNAME seen a third time pairs with whatever the map holds by then: the
-                    // reference swaps the map entry with the second read only when that pair
-                    // survived the filter (the `continue` of :438-441 skips the swap)
-                    if (s->swap_pending) {
-                        if (!should_be_filtered_out(s->read, s->partner)) s->read = s->partner;
-                        s->swap_pending = false;
-                    }
-                    if (cur.is_first_read) {
-                        unfiltered.push_back(cur);
-                        unfiltered.push_back(s->read);
-                        s->partner = cur;
-                        s->swap_pending = true;
+            const std::size_t n = chunk.records.size();
+            mate.resize(n);
+            completes.assign(n, 0);
+            bgzf::parallel_for(parts, parts, [&](std::size_t part) {
+                QnameTable& table = tables[part];
+                for (std::size_t i = 0; i < n; ++i) {
+                    const bgzf::RecordFields& f = chunk.records[i];
+                    if ((f.qname_hash >> 40) % parts != part) continue;
+                    Read cur = make_read(id + i, f);
+                    const char* name = chunk.qname(f);
+                    if (QnameTable::Slot* s = table.find(f.qname_hash, name, f.l_qname)) {
+                        // a QNAME seen a third time pairs with whatever the map holds by then: the
+                        // reference swaps the map entry with the second read only when that pair
+                        // survived the filter (the `continue` of :438-441 skips the swap)
+                        if (s->swap_pending) {
+                            if (!should_be_filtered_out(s->read, s->partner)) s->read = s->partner;
+                            s->swap_pending = false;
+                        }
+                        mate[i] = s->read;
+                        if (cur.is_first_read) {
+                            completes[i] = 2;
+                            s->partner = cur;
+                            s->swap_pending = true;
+                        } else {
+                            completes[i] = 1;
+                        }
                     } else {
-                        unfiltered.push_back(s->read);
-                        unfiltered.push_back(cur);
+                        table.insert(f.qname_hash, name, f.l_qname, cur);
                     }
-                } else {
-                    table.insert(f.qname_hash, name, f.l_qname, cur);
                 }
-                ++id;
+            });
+            for (std::size_t i = 0; i < n; ++i) {
+                if (!completes[i]) continue;
+                Read cur = make_read(id + i, chunk.records[i]);
+                unfiltered.push_back(completes[i] == 2 ? cur : mate[i]);
+                unfiltered.push_back(completes[i] == 2 ? mate[i] : cur);
             }
+            id += n;
         }
         bam_record_count_ = id;
     } catch (const std::exception& e) {

@@ -106,7 +106,11 @@ uint64_t write_synthetic_bam(const std::filesystem::path& path, uint64_t n, uint
             uint64_t r = rnd();
             rec.push_back(uint8_t(nib[r & 3] << 4 | nib[(r >> 2) & 3]));
         }
-        for (uint32_t b = 0; b < lseq; ++b) rec.push_back(uint8_t(2 + (rnd() >> 40) % 39));
+        // binned qualities as current instruments report them: mostly 37, some 25 and 11
+        for (uint32_t b = 0; b < lseq; ++b) {
+            uint32_t r = uint32_t(rnd() >> 40) % 100;
+            rec.push_back(uint8_t(r < 90 ? 37 : r < 97 ? 25 : 11));
+        }
         out.flush_try(rec.size());
         out.write(rec.data(), rec.size());
     }
