@@ -117,7 +117,8 @@ class BgzfWriter {
 
 // BamApi::write_bam (bam_api.cpp:534-656): header of `input` followed by the records whose file
 // ordinals are in `bam_ids` (sorted in place, as the reference does), reading stops once the last
-// requested record is out.  Returns the number of records written.
+// requested record is out.  An output path that does not end in ".bam" gets SAM text, as the
+// reference's open mode "w" does (:566).  Returns the number of records written.
 std::uint32_t copy_bam_records(const std::filesystem::path& input,
                                const std::filesystem::path& output,
                                std::vector<std::size_t>& bam_ids, std::uint32_t threads);

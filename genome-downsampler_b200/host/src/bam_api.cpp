@@ -389,13 +389,7 @@ std::uint32_t BamApi::write_bam_api_filtered_out_reads(const std::filesystem::pa
 std::uint32_t BamApi::write_bam(const std::filesystem::path& input_filepath,
                                 const std::filesystem::path& output_filepath,
                                 std::vector<BAMReadId>& bam_ids, std::uint32_t hts_thread_count) {
-    if (output_filepath.extension() != ".bam") {
-        // the reference hands any other extension to htslib in SAM text mode (:566); the text
-        // formatter is not rebuilt here
-        LOG_WITH_LEVEL(logging::ERROR) << "Could not open " << output_filepath
-                                       << " (only .bam output is supported by the zlib-only writer)";
-        std::exit(EXIT_FAILURE);
-    }
+    // ".bam" -> BGZF-compressed BAM, anything else -> SAM text (open_mode, bam_api.cpp:566)
     try {
         return bgzf::copy_bam_records(input_filepath, output_filepath, bam_ids, hts_thread_count);
     } catch (const std::exception& e) {

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
+#include <string>
 #include <thread>
 
 namespace bam_api::bgzf {
@@ -394,11 +395,182 @@ void BgzfWriter::close() {
     if (!ok) fail("could not finish BAM output");
 }
 
+// ------------------------------------------------------------------ SAM text
+
+namespace {
+
+void put_int(std::string& o, long long v) { o += std::to_string(v); }
+
+void put_real(std::string& o, double v) {
+    char b[32];
+    std::snprintf(b, sizeof b, "%g", v);
+    o += b;
+}
+
+// one alignment line as sam_format1 prints it (SAMv1 §1.4 / §4.2.4); rec points at block_size
+void format_sam_record(const std::uint8_t* rec, std::uint32_t size, const BamHeader& h, std::string& o) {
+    const std::uint8_t* q = rec + 4;
+    const std::int32_t tid = std::int32_t(le32(q)), pos = std::int32_t(le32(q + 4));
+    const std::uint32_t l_name = q[8], mapq = q[9], n_cigar = le16(q + 12), flag = le16(q + 14);
+    const std::uint32_t l_seq = le32(q + 16);
+    const std::int32_t mtid = std::int32_t(le32(q + 20)), mpos = std::int32_t(le32(q + 24)), tlen = std::int32_t(le32(q + 28));
+    const std::uint8_t* name = q + 32;
+    const std::uint8_t* cig = name + l_name;
+    const std::uint8_t* seq = cig + 4 * std::size_t(n_cigar);
+    const std::uint8_t* qual = seq + (l_seq + 1) / 2;
+    const std::uint8_t* aux = qual + l_seq;
+    const std::uint8_t* end = rec + size;
+    if (aux > end) fail("corrupt BAM record (fields exceed block_size)");
+    auto ref_name = [&](std::int32_t t) -> std::string {
+        return (t >= 0 && std::size_t(t) < h.ref_names.size()) ? h.ref_names[std::size_t(t)] : std::string("*");
+    };
+    o.append(reinterpret_cast<const char*>(name), l_name ? strnlen(reinterpret_cast<const char*>(name), l_name) : 0);
+    o += '\t';
+    put_int(o, flag);
+    o += '\t';
+    o += ref_name(tid);
+    o += '\t';
+    put_int(o, (long long)pos + 1);
+    o += '\t';
+    put_int(o, mapq);
+    o += '\t';
+    if (n_cigar == 0) o += '*';
+    for (std::uint32_t k = 0; k < n_cigar; ++k) {
+        std::uint32_t v = le32(cig + 4 * k);
+        put_int(o, v >> 4);
+        o += "MIDNSHP=XB??????"[v & 15];
+    }
+    o += '\t';
+    if (mtid < 0) o += '*';
+    else if (mtid == tid) o += '=';
+    else o += ref_name(mtid);
+    o += '\t';
+    put_int(o, (long long)mpos + 1);
+    o += '\t';
+    put_int(o, tlen);
+    o += '\t';
+    if (l_seq == 0) o += '*';
+    for (std::uint32_t k = 0; k < l_seq; ++k) o += "=ACMGRSVTWYHKDBN"[(seq[k >> 1] >> ((~k & 1) << 2)) & 15];
+    o += '\t';
+    if (l_seq == 0 || qual[0] == 0xff) o += '*';
+    else
+        for (std::uint32_t k = 0; k < l_seq; ++k) o += char(qual[k] + 33);
+    auto scalar = [&](char type, const std::uint8_t*& p) {
+        auto need = [&](std::size_t n) {
+            if (p + n > end) fail("corrupt BAM record (truncated tag)");
+        };
+        switch (type) {
+            case 'c': need(1); put_int(o, std::int8_t(*p)); p += 1; break;
+            case 'C': need(1); put_int(o, *p); p += 1; break;
+            case 's': need(2); put_int(o, std::int16_t(le16(p))); p += 2; break;
+            case 'S': need(2); put_int(o, le16(p)); p += 2; break;
+            case 'i': need(4); put_int(o, std::int32_t(le32(p))); p += 4; break;
+            case 'I': need(4); put_int(o, le32(p)); p += 4; break;
+            case 'f': {
+                need(4);
+                float f;
+                std::uint32_t u = le32(p);
+                std::memcpy(&f, &u, 4);
+                put_real(o, f);
+                p += 4;
+                break;
+            }
+            case 'd': {
+                need(8);
+                double d;
+                std::uint64_t u = std::uint64_t(le32(p)) | (std::uint64_t(le32(p + 4)) << 32);
+                std::memcpy(&d, &u, 8);
+                put_real(o, d);
+                p += 8;
+                break;
+            }
+            default: fail("corrupt BAM record (unknown tag type)");
+        }
+    };
+    for (const std::uint8_t* p = aux; p + 3 <= end;) {
+        o += '\t';
+        o += char(p[0]);
+        o += char(p[1]);
+        o += ':';
+        const char type = char(p[2]);
+        p += 3;
+        if (type == 'A') {
+            if (p >= end) fail("corrupt BAM record (truncated tag)");
+            o += "A:";
+            o += char(*p++);
+        } else if (type == 'Z' || type == 'H') {
+            o += type;
+            o += ':';
+            while (p < end && *p) o += char(*p++);
+            if (p >= end) fail("corrupt BAM record (unterminated tag)");
+            ++p;
+        } else if (type == 'B') {
+            if (p + 5 > end) fail("corrupt BAM record (truncated tag)");
+            const char sub = char(*p);
+            std::uint32_t cnt = le32(p + 1);
+            p += 5;
+            o += "B:";
+            o += sub;
+            for (std::uint32_t k = 0; k < cnt; ++k) {
+                o += ',';
+                scalar(sub, p);
+            }
+        } else if (type == 'f' || type == 'd') {
+            o += type;
+            o += ':';
+            scalar(type, p);
+        } else {
+            o += "i:";
+            scalar(type, p);
+        }
+    }
+    o += '\n';
+}
+
+}  // namespace
+
 // ------------------------------------------------------------------ selective copy
+
+namespace {
+// the same loop with htslib's SAM text writer on the other end (any extension but .bam)
+std::uint32_t copy_as_sam(BamScanner& in, const std::filesystem::path& output, std::vector<std::size_t>& bam_ids) {
+    std::FILE* f = std::fopen(output.c_str(), "wb");
+    if (!f) fail("Could not open " + output.string());
+    std::string text = in.header().text;
+    text.resize(strnlen(text.c_str(), text.size()));  // NUL padding is not part of the text
+    std::string buf = text;
+    std::sort(bam_ids.begin(), bam_ids.end());
+    auto want = bam_ids.begin();
+    std::uint32_t written = 0;
+    RecordChunk chunk;
+    bool ok = true;
+    while (ok && want != bam_ids.end() && in.next(chunk, false)) {
+        std::uint64_t id = chunk.first_id;
+        for (const RecordFields& r : chunk.records) {
+            if (want == bam_ids.end()) break;
+            if (id == *want) {
+                format_sam_record(chunk.data + r.offset, r.size, in.header(), buf);
+                ++written;
+                ++want;
+                if (buf.size() > (1u << 20)) {
+                    ok = std::fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+                    buf.clear();
+                }
+            }
+            ++id;
+        }
+    }
+    ok = ok && std::fwrite(buf.data(), 1, buf.size(), f) == buf.size();
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok) fail("short write to " + output.string());
+    return written;
+}
+}  // namespace
 
 std::uint32_t copy_bam_records(const std::filesystem::path& input, const std::filesystem::path& output,
                                std::vector<std::size_t>& bam_ids, std::uint32_t threads) {
     BamScanner in(input, threads);
+    if (output.extension() != ".bam") return copy_as_sam(in, output, bam_ids);  // mode "w", :566
     BgzfWriter out(output, threads);
     // sam_hdr_write → bam_hdr_write: header bytes, then bgzf_flush
     out.write(in.header().raw.data(), in.header().raw.size());

@@ -201,3 +201,51 @@ def ref_write_bam(records, bam_ids):
             out.append(rec)
             k += 1
     return out
+
+
+# ----------------------------------------------------------------------------- SAM text
+
+def format_sam(rec, ref_names):
+    """One alignment line of SAM text for a BAM record (SAMv1 §1.4, §4.2.4) — what htslib's text
+    writer emits when the reference opens a non-.bam output with mode "w" (bam_api.cpp:566)."""
+    tid, pos, l_name, mapq, _bin, n_cig, flag, l_seq, mtid, mpos, tlen = struct.unpack_from("<iiBBHHHIiii", rec, 4)
+    p = 36
+    name = rec[p:p + l_name].split(b"\0")[0].decode("latin-1")
+    p += l_name
+    cigar = "".join("%d%s" % (v >> 4, CIGAR_OPS[v & 15]) for v in struct.unpack_from("<%dI" % n_cig, rec, p)) or "*"
+    p += 4 * n_cig
+    seq = "".join("=ACMGRSVTWYHKDBN"[(rec[p + k // 2] >> (0 if k & 1 else 4)) & 15] for k in range(l_seq)) or "*"
+    p += (l_seq + 1) // 2
+    qual = "*" if l_seq == 0 or rec[p] == 0xff else "".join(chr(q + 33) for q in rec[p:p + l_seq])
+    p += l_seq
+    rname = ref_names[tid] if 0 <= tid < len(ref_names) else "*"
+    rnext = "*" if mtid < 0 else "=" if mtid == tid else ref_names[mtid] if mtid < len(ref_names) else "*"
+    cols = [name, str(flag), rname, str(pos + 1), str(mapq), cigar, rnext, str(mpos + 1), str(tlen), seq, qual]
+    fmt = {"c": "<b", "C": "<B", "s": "<h", "S": "<H", "i": "<i", "I": "<I", "f": "<f", "d": "<d"}
+
+    def scalar(t, p):
+        v = struct.unpack_from(fmt[t], rec, p)[0]
+        return ("%g" % v if t in "fd" else str(v)), p + struct.calcsize(fmt[t])
+
+    while p + 3 <= len(rec):
+        tag, t = rec[p:p + 2].decode("latin-1"), chr(rec[p + 2])
+        p += 3
+        if t == "A":
+            cols.append("%s:A:%s" % (tag, chr(rec[p])))
+            p += 1
+        elif t in "ZH":
+            e = rec.index(b"\0", p)
+            cols.append("%s:%s:%s" % (tag, t, rec[p:e].decode("latin-1")))
+            p = e + 1
+        elif t == "B":
+            sub, cnt = chr(rec[p]), struct.unpack_from("<I", rec, p + 1)[0]
+            p += 5
+            vals = []
+            for _ in range(cnt):
+                v, p = scalar(sub, p)
+                vals.append(v)
+            cols.append("%s:B:%s%s" % (tag, sub, "".join("," + v for v in vals)))
+        else:
+            v, p = scalar(t, p)
+            cols.append("%s:%s:%s" % (tag, t if t in "fd" else "i", v))
+    return "\t".join(cols) + "\n"

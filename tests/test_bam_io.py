@@ -292,3 +292,34 @@ def test_bam_to_bam_through_the_b200_plugin(hostlib, O, tmp_path):
     assert b.write_filtered_out(fo) == len(want_out)
     assert pybam.read_bam(fo)[2] == [recs[i] for i in want_out]
     b.close()
+
+
+def test_non_bam_extension_gets_sam_text(hostlib, tmp_path):
+    # open_mode = extension == ".bam" ? "wb" : "w" (bam_api.cpp:566): anything else is SAM text
+    R = pybam.encode_record
+    tags = (b"NMC\x03" + b"XAA!" + b"XcC\xfe" + b"Xsc\xfe" + b"XSS\x10\x27" + b"Xhs\xf0\xd8" + b"XII\xff\xff\xff\xff" +
+            b"Xii\x00\x00\x00\x80" + b"Xff" + struct.pack("<f", 0.5) + b"RGZgroup one\0" + b"XHH1AE301\0" +
+            b"XBBs\x03\x00\x00\x00" + struct.pack("<3h", -1, 0, 300) + b"XFBf\x02\x00\x00\x00" + struct.pack("<2f", 1.5, -2e-7) +
+            b"XEBC\x00\x00\x00\x00")
+    recs = [
+        R("r1", 99, 10, 60, [(5, "S"), (20, "M"), (2, "I"), (3, "D"), (8, "=")], 35, next_ref=0, next_pos=200, tlen=240,
+          tags=tags, seq_fill=0x28, qual_fill=40),
+        R("r1", 147, 200, 0, [(50, "M")], 50, next_ref=1, next_pos=7, tlen=-240, seq_fill=0xf1, qual_fill=0xff),
+        R("unmapped", 77, -1, 0, [], 0, ref_id=-1, next_ref=-1, next_pos=-1),
+        R("odd", 65, 7, 255, [(7, "M")], 7, seq_fill=0x84, qual_fill=0),
+    ] + handmade_records()
+    src = tmp_path / "in.bam"
+    text = "@HD\tVN:1.6\n@SQ\tSN:chr\tLN:5000\n@SQ\tSN:other\tLN:77\n@CO\tfree text\n"
+    header = pybam.encode_header(text, [("chr", 5000), ("other", 77)])
+    pybam.write_bam(src, header, recs, member_payload=900)
+    ids = [0, 1, 2, 3, 5, 9, 16]
+    dst = tmp_path / "out.sam"
+    assert hostlib.write_bam(src, dst, ids, threads=2) == len(ids)
+    want = text + "".join(pybam.format_sam(recs[i], ["chr", "other"]) for i in ids)
+    got = open(dst, "rb").read().decode("latin-1")
+    assert got == want
+    lines = got.splitlines()
+    assert lines[4].startswith("r1\t99\tchr\t11\t60\t5S20M2I3D8=\t=\t201\t240\t" + "CT" * 17 + "C\t" + "I" * 35 + "\tNM:i:3\tXA:A:!\tXc:i:254")
+    assert "\tXB:B:s,-1,0,300\tXF:B:f,1.5,-2e-07\tXE:B:C" in lines[4]
+    assert lines[5].split("\t")[6:11] == ["other", "8", "-240", "NA" * 25, "*"]
+    assert lines[6].split("\t")[:11] == ["unmapped", "77", "*", "0", "0", "*", "*", "0", "0", "*", "*"]
