@@ -1050,9 +1050,10 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         uint32_t* out_ptr = c->outdeg.as<uint32_t>();
         uint32_t* in_ptr = c->indeg.as<uint32_t>();
         uint32_t* excl = c->excl.get<uint32_t>(n_nodes + 1);
-        exclusive_scan_u32(reinterpret_cast<const uint32_t*>(diff), excl, n_nodes + 1, c->scan, st);
-        exclusive_scan_u32(out_ptr, out_ptr, n_nodes + 1, c->scan, st);
-        exclusive_scan_u32(in_ptr, in_ptr, n_nodes + 1, c->scan, st);
+        {  // coverage from the difference array and both CSR row starts: one launch
+            ScanArrays sa{{reinterpret_cast<const uint32_t*>(diff), out_ptr, in_ptr}, {excl, out_ptr, in_ptr}};
+            exclusive_scan_u32_multi(sa, 3, n_nodes + 1, c->scan, st);
+        }
         NodeRec* node = c->node_rec.get<NodeRec>((size_t)n_nodes + 1);
         uint32_t* d_snap = c->n_dsnap.get<uint32_t>(n_nodes);
         uint32_t* cstart = c->comp_start.get<uint32_t>(n_nodes + 1);

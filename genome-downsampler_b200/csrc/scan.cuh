@@ -1,5 +1,9 @@
 // scan.cuh — device-wide exclusive prefix sum over uint32 (wrap-around add, so it also serves
-// int32 difference arrays).  Hierarchical reduce-then-scan: deterministic, no atomics.
+// int32 difference arrays).  One pass with decoupled look-back (each tile publishes its aggregate,
+// then its inclusive prefix, in one 64-bit status word; a tile's first warp walks back over its
+// predecessors' words): the data is read once and written once, 8 bytes per element, where the
+// hierarchical reduce-then-scan below it (kept for one-tile inputs and as GDS_SCAN=hier) moves 16.
+// Integer addition is associative, so the result does not depend on which tiles were ready when.
 #pragma once
 #include "common.cuh"
 
@@ -68,17 +72,189 @@ k_scan_add(uint32_t* __restrict__ out, const uint32_t* __restrict__ tile_offs, s
         if (base + k < n) out[base + k] += off;
 }
 
+// Up to three equally long arrays scanned by one launch (the node arrays of the graph build).
+struct ScanArrays {
+    const uint32_t* in[3];
+    uint32_t* out[3];  // out[k] may alias in[k]
+};
+
+// status word: [63:34] epoch of the launch, [33:32] 1 = aggregate / 2 = inclusive prefix, [31:0] value.
+// The epoch makes stale words of earlier launches invalid, so the array is never cleared.
+__device__ __forceinline__ unsigned long long scan_status(uint32_t epoch, uint32_t flag, uint32_t v) {
+    return ((unsigned long long)epoch << 34) | ((unsigned long long)flag << 32) | v;
+}
+
+// 256 threads x 16 elements: a tile is 16 KB, and six or more tiles per SM are resident, so the
+// wait of one tile for its predecessors is covered by the loads of the others (the first version,
+// 1024 threads x 4 elements and two tiles per SM, had 32 KB per SM in flight and ran at 1.3 TB/s,
+// slower than the three-kernel scan).  A warp owns 512 consecutive elements and reads them as
+// four fully coalesced 512-byte rows; lane l holds the l-th 16 bytes of each row.
+constexpr int kLbThreads = 256;
+constexpr int kLbRows = 4;
+constexpr int kLbWarpSpan = 32 * 4 * kLbRows;
+static_assert(kLbThreads / 32 * kLbWarpSpan == kScanTile, "same tile size as the hierarchical scan");
+
+__global__ void __launch_bounds__(kLbThreads, 6)
+k_scan_lookback(ScanArrays a, uint32_t n_arr, size_t n, uint32_t n_tiles,
+                unsigned long long* __restrict__ status, uint32_t* __restrict__ ticket, uint32_t epoch) {
+    __shared__ uint32_t s_ticket, s_prefix;
+    __shared__ uint32_t warp_tot[kLbThreads / 32];
+    // tiles are handed out in launch order, so every predecessor of a tile is already running
+    if (threadIdx.x == 0) s_ticket = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tk = s_ticket;
+    const uint32_t tile = tk / n_arr, arr = tk - tile * n_arr;
+    const uint32_t* in = arr == 0 ? a.in[0] : arr == 1 ? a.in[1] : a.in[2];
+    uint32_t* out = arr == 0 ? a.out[0] : arr == 1 ? a.out[1] : a.out[2];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t wbase = (size_t)tile * kScanTile + (size_t)warp * kLbWarpSpan;
+    const bool vec = wbase + kLbWarpSpan <= n && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(out) & 15) == 0;  // the same for a whole warp
+    uint32_t v[kLbRows][4];
+    if (vec) {
+        const uint4* in4 = reinterpret_cast<const uint4*>(in + wbase);
+#pragma unroll
+        for (int r = 0; r < kLbRows; ++r) {
+            const uint4 q = in4[r * 32 + lane];
+            v[r][0] = q.x; v[r][1] = q.y; v[r][2] = q.z; v[r][3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < kLbRows; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const size_t i = wbase + (size_t)(r * 32 + lane) * 4 + k;
+                v[r][k] = i < n ? in[i] : 0u;
+            }
+    }
+    uint32_t ex[kLbRows], wsum = 0;
+#pragma unroll
+    for (int r = 0; r < kLbRows; ++r) {
+        const uint32_t s = v[r][0] + v[r][1] + v[r][2] + v[r][3];
+        const uint32_t incl = warp_incl_scan(s);
+        ex[r] = wsum + incl - s;
+        wsum += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) warp_tot[warp] = wsum;
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kLbThreads / 32; ++w) {
+        const uint32_t t = warp_tot[w];
+        woff += w < (int)warp ? t : 0u;
+        total += t;
+    }
+    if (warp == 0) {
+        uint32_t prefix = 0;
+        volatile unsigned long long* st = status;
+        if (tile == 0) {
+            if (lane == 0) st[tk] = scan_status(epoch, 2, total);
+        } else {
+            if (lane == 0) st[tk] = scan_status(epoch, 1, total);
+            long long idx = (long long)tk - n_arr;  // the tile before this one in the same array
+            for (;;) {
+                const long long my = idx - (long long)lane * n_arr;
+                uint32_t flag = 2, val = 0;  // before the first tile: an inclusive prefix of zero
+                if (my >= 0) {
+                    unsigned long long w;
+                    do {
+                        w = st[my];
+                    } while ((uint32_t)(w >> 34) != epoch || ((w >> 32) & 3) == 0);
+                    flag = (uint32_t)(w >> 32) & 3;
+                    val = (uint32_t)w;
+                }
+                const uint32_t incl = __ballot_sync(0xffffffffu, flag == 2);
+                const int first = __ffs(incl) - 1;  // nearest predecessor that knows its prefix
+                prefix += __reduce_add_sync(0xffffffffu, (first < 0 || (int)lane <= first) ? val : 0u);
+                if (first >= 0) break;
+                idx -= 32ll * n_arr;
+            }
+            if (lane == 0) st[tk] = scan_status(epoch, 2, prefix + total);
+        }
+        if (lane == 0) s_prefix = prefix;
+    }
+    __syncthreads();
+    const uint32_t base_ex = s_prefix + woff;
+    if (vec) {
+        uint4* out4 = reinterpret_cast<uint4*>(out + wbase);
+#pragma unroll
+        for (int r = 0; r < kLbRows; ++r) {
+            uint4 q;
+            q.x = base_ex + ex[r];
+            q.y = q.x + v[r][0];
+            q.z = q.y + v[r][1];
+            q.w = q.z + v[r][2];
+            out4[r * 32 + lane] = q;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < kLbRows; ++r) {
+            uint32_t e = base_ex + ex[r];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const size_t i = wbase + (size_t)(r * 32 + lane) * 4 + k;
+                if (i < n) out[i] = e;
+                e += v[r][k];
+            }
+        }
+    }
+    if (threadIdx.x == 0 && tk == n_tiles * n_arr - 1) *ticket = 0;  // every ticket is out by now
+}
+
 struct ScanTemp {
     DevBuf l1, l2;
+    DevBuf status, ticket;
+    size_t status_cap = 0;
+    uint32_t epoch = 0;
+    int mode = -1;  // 0 = one pass, 1 = hierarchical (GDS_SCAN=hier: measurement knob)
 };
+
+inline void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, ScanTemp& tmp,
+                               cudaStream_t st);
+
+// k equally long arrays in one launch; falls back to one hierarchical scan each for short arrays
+inline void exclusive_scan_u32_multi(const ScanArrays& a, int n_arr, size_t n, ScanTemp& tmp,
+                                     cudaStream_t st) {
+    if (n == 0 || n_arr <= 0) return;
+    if (tmp.mode < 0) {
+        const char* e = getenv("GDS_SCAN");
+        tmp.mode = (e && e[0] == 'h') ? 1 : 0;
+    }
+    const size_t t1 = (n + kScanTile - 1) / kScanTile;
+    if (t1 == 1 || tmp.mode == 1 || t1 * n_arr > 0x7fffffffull) {
+        const int keep = tmp.mode;
+        tmp.mode = 1;
+        for (int k = 0; k < n_arr; ++k) exclusive_scan_u32(a.in[k], a.out[k], n, tmp, st);
+        tmp.mode = keep;
+        return;
+    }
+    KScope ks("scan_u32", 8ull * n * n_arr, st);
+    unsigned long long* status = tmp.status.get<unsigned long long>(t1 * n_arr);
+    uint32_t* ticket = tmp.ticket.get<uint32_t>(1);
+    if (tmp.status_cap != tmp.status.cap || tmp.epoch >= (1u << 30) - 1) {  // new buffer or epoch wrap
+        GDS_CUDA(cudaMemsetAsync(tmp.status.p, 0, tmp.status.cap, st));
+        GDS_CUDA(cudaMemsetAsync(ticket, 0, 4, st));
+        tmp.status_cap = tmp.status.cap;
+        tmp.epoch = 0;
+    }
+    ++tmp.epoch;
+    k_scan_lookback<<<(unsigned)(t1 * n_arr), kLbThreads, 0, st>>>(a, (uint32_t)n_arr, n, (uint32_t)t1,
+                                                                   status, ticket, tmp.epoch);
+    GDS_KERNEL_CHECK();
+}
 
 // out may alias in.  total (optional, device pointer) receives nothing here: callers that need
 // the grand total read out[n-1] + in[n-1] themselves or scan n+1 elements with a trailing zero.
 inline void exclusive_scan_u32(const uint32_t* in, uint32_t* out, size_t n, ScanTemp& tmp,
                                cudaStream_t st) {
     if (n == 0) return;
-    KScope ks("scan_u32", 8ull * n, st);  // the whole hierarchical scan counts as one unit
     size_t t1 = (n + kScanTile - 1) / kScanTile;
+    if (t1 > 1 && tmp.mode != 1) {
+        ScanArrays a{{in, nullptr, nullptr}, {out, nullptr, nullptr}};
+        exclusive_scan_u32_multi(a, 1, n, tmp, st);
+        return;
+    }
+    KScope ks("scan_u32", 8ull * n, st);  // the whole hierarchical scan counts as one unit
     if (t1 == 1) {
         k_scan_tiles<<<1, kScanThreads, 0, st>>>(in, out, nullptr, n);
         GDS_KERNEL_CHECK();
