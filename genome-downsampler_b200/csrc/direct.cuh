@@ -240,7 +240,12 @@ k_direct_bundles(const uint32_t* __restrict__ ghist, uint32_t ktot, DirectLayout
 // runs the ordered walk below instead — same kept set, one CTA per sample.
 constexpr uint32_t kSatCode = 1, kPartCode = 2;
 constexpr uint32_t kMaxPartialMult = 2048;  // candidates of one bundle ranked by one warp
-constexpr int kDmThreads = 1024;
+// 512 threads x 3 CTAs per SM at 40 registers (one read length): the kernel is bound by neither
+// issue slots nor HBM but by its stalls per instruction, so more resident warps pay — 1.27 ms with
+// one CTA of 1024 threads (48 registers, half occupancy), 1.14 ms this way (config 5)
+constexpr int kDmThreads = 512;
+constexpr int kDmCtasPerSm = 3;
+constexpr uint32_t kDmSplit = 3;
 
 // ctl: [0] number of partial bundles, [1] candidate slots handed out, [2] fallback flag
 __global__ void __launch_bounds__(256)
@@ -304,7 +309,7 @@ constexpr uint32_t kDmQueue = 256;                              // entries per w
 constexpr uint32_t kDmQueueBytes = (kDmThreads / 32) * kDmQueue * 8;
 
 template <bool ONE_LEN>
-__global__ void __launch_bounds__(kDmThreads, 1)
+__global__ void __launch_bounds__(kDmThreads, ONE_LEN ? kDmCtasPerSm : 2)
 k_direct_mark(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, DirectLayout dl,
               uint32_t n_items, uint32_t* __restrict__ work_counter,
               const uint32_t* __restrict__ ghist, const uint32_t* __restrict__ kstat,
@@ -327,15 +332,19 @@ k_direct_mark(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, Di
     for (;;) {
         if (tid == 0) s_item = atomicAdd(work_counter, 1u);
         __syncthreads();
-        const uint32_t item = s_item;
-        if (item >= n_items) break;
+        // the histogram's parts are cut in kDmSplit pieces each: three CTAs per SM share the work
+        // counter here, and with whole parts the last of ~3.5 items per CTA set the pace
+        if (s_item >= n_items * kDmSplit) break;
+        const uint32_t item = s_item / kDmSplit, sub = s_item % kDmSplit;
         const uint32_t k = find_u32(dl.item_off, dl.ns, item);
         const uint32_t parts = dl.item_off[k + 1] - dl.item_off[k];
         const uint32_t p = item - dl.item_off[k];
         const uint64_t o0 = dl.off[k], o1 = dl.off[k + 1];
         const uint64_t plen = (((o1 - o0) + parts - 1) / parts + 3) & ~3ull;
-        const uint64_t a = o0 + p * plen;
-        const uint64_t b = min(a + plen, o1);
+        const uint64_t pa = min(o0 + p * plen, o1), pb_ = min(pa + plen, o1);
+        const uint64_t slen = (((pb_ - pa) + kDmSplit - 1) / kDmSplit + 3) & ~3ull;
+        const uint64_t a = min(pa + sub * slen, pb_);
+        const uint64_t b = min(a + slen, pb_);
         const uint32_t kb = dl.kbase[k];
         const uint32_t kk = dl.kbase[k + 1] - kb;
         for (uint32_t i = tid; i < (kk >> 4); i += kDmThreads) {  // 16 two-bit codes -> 16 bytes

@@ -464,7 +464,8 @@ void direct_select(gds_ctx* c, const DirectPlan& dp, const uint32_t* S, const ui
             } else {
                 KScope ks("direct_mark", per_read * N + dp.ktot / 4 + 8ull * N / 32, st);
                 uint32_t* wc = c->dwork.as<uint32_t>() + 1;
-                const int grid = (int)std::min<uint32_t>(dp.n_items, (uint32_t)kNumSMs);
+                const int grid = (int)std::min<uint32_t>(
+                    dp.n_items * kDmSplit, (uint32_t)kNumSMs * (dp.dl.nlen == 1 ? kDmCtasPerSm : 2));
                 const unsigned smem = kDmQueueBytes + dp.kmax;
                 if (dp.dl.nlen == 1)
                     k_direct_mark<true><<<grid, kDmThreads, smem, st>>>(S, E, dp.dl, dp.n_items, wc,

@@ -8,7 +8,7 @@ for w in c1 c2 c4; do timeout 300 python bench.py --workload $w --no-cpu-baselin
 timeout 300 python bench.py --e2e-u32 --no-cpu-baseline --steps 5 > gpurun_out/${T}_bench_c5_e2e_u32.json 2> /dev/null
 timeout 300 env GDS_BUNDLE=sort python bench.py --no-cpu-baseline --steps 5 > gpurun_out/${T}_bench_c5_sortpath.json 2> /dev/null
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${T}_ncu_launches_c5.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_ncu_launches.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_maxflow|k_direct_hist|k_direct_mark" -c 3 -o gpurun_out/${T}_prof_c5 python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/${T}_ncu_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_maxflow|k_direct_hist|k_direct_mark|k_scan_lookback" -c 6 -o gpurun_out/${T}_prof_c5 python bench.py --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/${T}_ncu_full.log 2>&1
 tail -2 gpurun_out/${T}_pytest_gpu.txt
 python tools/show_bench.py gpurun_out/${T}_BENCH_c5.json gpurun_out/${T}_bench_c1.json gpurun_out/${T}_bench_c2.json gpurun_out/${T}_bench_c4.json gpurun_out/${T}_bench_c5_sortpath.json
 cat gpurun_out/${T}_BENCH_reference.json | cut -c1-600
