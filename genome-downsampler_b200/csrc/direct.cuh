@@ -297,7 +297,9 @@ k_direct_classify(const BundleRec* __restrict__ bund, const uint32_t* __restrict
 // ncu of the second version: issue slots 50 % busy, long-scoreboard stalls, 3.6 TB/s.  Neither
 // doubling the loads in flight (8 x 16 B per thread: 1.24 -> 1.21 ms) nor draining 4 x 32 entries
 // per chain of dependent accesses (1.21 -> 1.39 ms, register pressure) nor keeping the next batch's
-// loads in flight while this one is looked up (1.27 -> 1.32 ms, 64 registers) helped; what remains is the
+// loads in flight while this one is looked up (1.27 -> 1.32 ms, 64 registers) helped, and parking
+// the hits of a group warp-wide (ballots give every hit its queue slot, register counter, no
+// divergent per-hit path: 1.14 -> 1.27 ms) was slower than letting the few lanes with a hit diverge; what remains is the
 // scattered traffic of 20 M candidates.  The queue does not have to hold a whole round: a hit that
 // finds it full takes the slow chain inline (only adversarial inputs get there).
 // Switching the parking off altogether (wrong results, timing only) takes 25 % off the kernel and

@@ -12,3 +12,4 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_m
 tail -2 gpurun_out/${T}_pytest_gpu.txt
 python tools/show_bench.py gpurun_out/${T}_BENCH_c5.json gpurun_out/${T}_bench_c1.json gpurun_out/${T}_bench_c2.json gpurun_out/${T}_bench_c4.json gpurun_out/${T}_bench_c5_sortpath.json
 cat gpurun_out/${T}_BENCH_reference.json | cut -c1-600
+timeout 300 python tools/gpu_fuzz.py ${FUZZ_CASES:-1500} ${FUZZ_SEED:-77} 2>&1 | tail -2 > gpurun_out/${T}_gpu_fuzz.txt; cat gpurun_out/${T}_gpu_fuzz.txt
