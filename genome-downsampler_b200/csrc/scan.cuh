@@ -84,15 +84,21 @@ __device__ __forceinline__ unsigned long long scan_status(uint32_t epoch, uint32
     return ((unsigned long long)epoch << 34) | ((unsigned long long)flag << 32) | v;
 }
 
-// 256 threads x 16 elements: a tile is 16 KB, and six or more tiles per SM are resident, so the
-// wait of one tile for its predecessors is covered by the loads of the others (the first version,
-// 1024 threads x 4 elements and two tiles per SM, had 32 KB per SM in flight and ran at 1.3 TB/s,
-// slower than the three-kernel scan).  A warp owns 512 consecutive elements and reads them as
-// four fully coalesced 512-byte rows; lane l holds the l-th 16 bytes of each row.
+// 256 threads x 16 elements per step, kLbSub steps per tile: a tile is 64 KB, read twice (the
+// second time from L2): once to publish its aggregate, once to scan and write.  Six or more tiles
+// per SM are resident, so the wait of one tile for its predecessors is covered by the loads of the
+// others.  Two earlier shapes, measured on config 5 (15.4 M entries per array): 1024 threads x 4
+// elements with two tiles per SM had too few bytes in flight (1.3 TB/s, slower than the
+// three-kernel scan); 16 KB tiles were bound by the look-back relay itself — inclusive prefixes
+// travel 32 tiles per L2 round trip, 3 751 tiles took 117 trips = 48 us (ncu: 54 barrier-stall
+// cycles per issue) — hence the larger tile.  A warp owns 512 consecutive elements of a step and
+// reads them as four fully coalesced 512-byte rows; lane l holds the l-th 16 bytes of each row.
 constexpr int kLbThreads = 256;
 constexpr int kLbRows = 4;
 constexpr int kLbWarpSpan = 32 * 4 * kLbRows;
-static_assert(kLbThreads / 32 * kLbWarpSpan == kScanTile, "same tile size as the hierarchical scan");
+constexpr int kLbStep = kLbThreads / 32 * kLbWarpSpan;  // 4096 elements
+constexpr int kLbSub = 4;
+constexpr int kLbTile = kLbStep * kLbSub;
 
 __global__ void __launch_bounds__(kLbThreads, 6)
 k_scan_lookback(ScanArrays a, uint32_t n_arr, size_t n, uint32_t n_tiles,
@@ -107,44 +113,44 @@ k_scan_lookback(ScanArrays a, uint32_t n_arr, size_t n, uint32_t n_tiles,
     const uint32_t* in = arr == 0 ? a.in[0] : arr == 1 ? a.in[1] : a.in[2];
     uint32_t* out = arr == 0 ? a.out[0] : arr == 1 ? a.out[1] : a.out[2];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const size_t wbase = (size_t)tile * kScanTile + (size_t)warp * kLbWarpSpan;
-    const bool vec = wbase + kLbWarpSpan <= n && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
-                     (reinterpret_cast<uintptr_t>(out) & 15) == 0;  // the same for a whole warp
+    const size_t tbase = (size_t)tile * kLbTile + (size_t)warp * kLbWarpSpan;
+    const bool aligned = (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     uint32_t v[kLbRows][4];
-    if (vec) {
-        const uint4* in4 = reinterpret_cast<const uint4*>(in + wbase);
+    auto load = [&](size_t wbase, bool vec) {  // vec is the same for a whole warp
+        if (vec) {
+            const uint4* in4 = reinterpret_cast<const uint4*>(in + wbase);
 #pragma unroll
-        for (int r = 0; r < kLbRows; ++r) {
-            const uint4 q = in4[r * 32 + lane];
-            v[r][0] = q.x; v[r][1] = q.y; v[r][2] = q.z; v[r][3] = q.w;
-        }
-    } else {
-#pragma unroll
-        for (int r = 0; r < kLbRows; ++r)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const size_t i = wbase + (size_t)(r * 32 + lane) * 4 + k;
-                v[r][k] = i < n ? in[i] : 0u;
+            for (int r = 0; r < kLbRows; ++r) {
+                const uint4 q = in4[r * 32 + lane];
+                v[r][0] = q.x; v[r][1] = q.y; v[r][2] = q.z; v[r][3] = q.w;
             }
-    }
-    uint32_t ex[kLbRows], wsum = 0;
+        } else {
 #pragma unroll
-    for (int r = 0; r < kLbRows; ++r) {
-        const uint32_t s = v[r][0] + v[r][1] + v[r][2] + v[r][3];
-        const uint32_t incl = warp_incl_scan(s);
-        ex[r] = wsum + incl - s;
-        wsum += __shfl_sync(0xffffffffu, incl, 31);
+            for (int r = 0; r < kLbRows; ++r)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const size_t i = wbase + (size_t)(r * 32 + lane) * 4 + k;
+                    v[r][k] = i < n ? in[i] : 0u;
+                }
+        }
+    };
+    // pass 1: the tile's aggregate
+    uint32_t sum = 0;
+#pragma unroll 1
+    for (int sub = 0; sub < kLbSub; ++sub) {
+        const size_t wbase = tbase + (size_t)sub * kLbStep;
+        if (wbase >= n) break;
+        load(wbase, aligned && wbase + kLbWarpSpan <= n);
+#pragma unroll
+        for (int r = 0; r < kLbRows; ++r) sum += v[r][0] + v[r][1] + v[r][2] + v[r][3];
     }
-    if (lane == 0) warp_tot[warp] = wsum;
+    sum = __reduce_add_sync(0xffffffffu, sum);
+    if (lane == 0) warp_tot[warp] = sum;
     __syncthreads();
-    uint32_t woff = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < kLbThreads / 32; ++w) {
-        const uint32_t t = warp_tot[w];
-        woff += w < (int)warp ? t : 0u;
-        total += t;
-    }
     if (warp == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < kLbThreads / 32; ++w) total += warp_tot[w];
         uint32_t prefix = 0;
         volatile unsigned long long* st = status;
         if (tile == 0) {
@@ -174,27 +180,55 @@ k_scan_lookback(ScanArrays a, uint32_t n_arr, size_t n, uint32_t n_tiles,
         if (lane == 0) s_prefix = prefix;
     }
     __syncthreads();
-    const uint32_t base_ex = s_prefix + woff;
-    if (vec) {
-        uint4* out4 = reinterpret_cast<uint4*>(out + wbase);
+    // pass 2: scan and write, step by step, carrying the running prefix
+    uint32_t carry = s_prefix;
+#pragma unroll 1
+    for (int sub = 0; sub < kLbSub; ++sub) {
+        const size_t wbase = tbase + (size_t)sub * kLbStep;
+        if ((size_t)tile * kLbTile + (size_t)sub * kLbStep >= n) break;  // the same for the whole CTA
+        const bool vec = aligned && wbase + kLbWarpSpan <= n;
+        load(wbase, vec);
+        uint32_t ex[kLbRows], wsum = 0;
 #pragma unroll
         for (int r = 0; r < kLbRows; ++r) {
-            uint4 q;
-            q.x = base_ex + ex[r];
-            q.y = q.x + v[r][0];
-            q.z = q.y + v[r][1];
-            q.w = q.z + v[r][2];
-            out4[r * 32 + lane] = q;
+            const uint32_t s = v[r][0] + v[r][1] + v[r][2] + v[r][3];
+            const uint32_t incl = warp_incl_scan(s);
+            ex[r] = wsum + incl - s;
+            wsum += __shfl_sync(0xffffffffu, incl, 31);
         }
-    } else {
+        __syncthreads();  // warp_tot of the previous step (or of pass 1) has been read by everyone
+        if (lane == 0) warp_tot[warp] = wsum;
+        __syncthreads();
+        uint32_t woff = 0, total = 0;
 #pragma unroll
-        for (int r = 0; r < kLbRows; ++r) {
-            uint32_t e = base_ex + ex[r];
+        for (int w = 0; w < kLbThreads / 32; ++w) {
+            const uint32_t t = warp_tot[w];
+            woff += w < (int)warp ? t : 0u;
+            total += t;
+        }
+        const uint32_t base_ex = carry + woff;
+        carry += total;
+        if (vec) {
+            uint4* out4 = reinterpret_cast<uint4*>(out + wbase);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const size_t i = wbase + (size_t)(r * 32 + lane) * 4 + k;
-                if (i < n) out[i] = e;
-                e += v[r][k];
+            for (int r = 0; r < kLbRows; ++r) {
+                uint4 q;
+                q.x = base_ex + ex[r];
+                q.y = q.x + v[r][0];
+                q.z = q.y + v[r][1];
+                q.w = q.z + v[r][2];
+                out4[r * 32 + lane] = q;
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < kLbRows; ++r) {
+                uint32_t e = base_ex + ex[r];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const size_t i = wbase + (size_t)(r * 32 + lane) * 4 + k;
+                    if (i < n) out[i] = e;
+                    e += v[r][k];
+                }
             }
         }
     }
@@ -229,7 +263,8 @@ inline void exclusive_scan_u32_multi(const ScanArrays& a, int n_arr, size_t n, S
         return;
     }
     KScope ks("scan_u32", 8ull * n * n_arr, st);
-    unsigned long long* status = tmp.status.get<unsigned long long>(t1 * n_arr);
+    const size_t tl = (n + kLbTile - 1) / kLbTile;
+    unsigned long long* status = tmp.status.get<unsigned long long>(tl * n_arr);
     uint32_t* ticket = tmp.ticket.get<uint32_t>(1);
     if (tmp.status_cap != tmp.status.cap || tmp.epoch >= (1u << 30) - 1) {  // new buffer or epoch wrap
         GDS_CUDA(cudaMemsetAsync(tmp.status.p, 0, tmp.status.cap, st));
@@ -238,7 +273,7 @@ inline void exclusive_scan_u32_multi(const ScanArrays& a, int n_arr, size_t n, S
         tmp.epoch = 0;
     }
     ++tmp.epoch;
-    k_scan_lookback<<<(unsigned)(t1 * n_arr), kLbThreads, 0, st>>>(a, (uint32_t)n_arr, n, (uint32_t)t1,
+    k_scan_lookback<<<(unsigned)(tl * n_arr), kLbThreads, 0, st>>>(a, (uint32_t)n_arr, n, (uint32_t)tl,
                                                                    status, ticket, tmp.epoch);
     GDS_KERNEL_CHECK();
 }
