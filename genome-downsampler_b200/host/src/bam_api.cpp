@@ -238,7 +238,7 @@ class QnameTable {
         bool used = false;
         bool swap_pending = false;  // entry becomes `partner` iff that pair passed the filter
     };
-    QnameTable() : slots_(1u << 16) {}
+    QnameTable() : slots_(1u << 10) {}
     Slot* find(std::uint64_t h, const char* name, std::uint8_t len) {
         for (std::size_t i = h & (slots_.size() - 1);; i = (i + 1) & (slots_.size() - 1)) {
             Slot& s = slots_[i];

@@ -1,5 +1,5 @@
 """CPU restatement of the reference's BAM front and back ends — TEST INFRASTRUCTURE ONLY (imported
-by tests/ and tools/, never by the product path).
+by tests/ alone, never by the product path).
 
 Restates, in plain Python over the SAM/BAM specification (SAMv1 §4.1 BGZF, §4.2 BAM):
   * BamApi::read_bam           /root/reference libs/bam-api/src/bam_api.cpp:359-507

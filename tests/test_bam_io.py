@@ -323,3 +323,27 @@ def test_non_bam_extension_gets_sam_text(hostlib, tmp_path):
     assert "\tXB:B:s,-1,0,300\tXF:B:f,1.5,-2e-07\tXE:B:C" in lines[4]
     assert lines[5].split("\t")[6:11] == ["other", "8", "-240", "NA" * 25, "*"]
     assert lines[6].split("\t")[:11] == ["unmapped", "77", "*", "0", "0", "*", "*", "0", "0", "*", "*"]
+
+
+def test_header_only_bam_and_more_threads_than_records(hostlib, tmp_path):
+    empty = tmp_path / "empty.bam"
+    pybam.write_bam(empty, HEADER, [])
+    b = hostlib.BamFile(empty, threads=8)
+    assert b.record_count == 0 and b.ref_length == 5000
+    assert b.reads()["bam_id"].size == 0 and b.filtered_out().size == 0
+    out = tmp_path / "o.bam"
+    assert b.write_solution(out, [], with_pairs=True) == 0
+    header, refs, recs = pybam.read_bam(out)
+    assert header == HEADER and recs == []
+    b.close()
+    # two records, sixteen threads; no EOF member at the end of the input
+    two = tmp_path / "two.bam"
+    recs = handmade_records()[5:7]
+    pybam.write_bam(two, HEADER, recs, eof=False)
+    b = hostlib.BamFile(two, threads=16)
+    want, want_out = pybam.ref_read_bam(recs)
+    assert_same_reads(b.reads(), want)
+    assert b.filtered_out().tolist() == want_out == []
+    assert b.write_solution(out, [1], with_pairs=True) == 2
+    assert pybam.read_bam(out)[2] == recs
+    b.close()
