@@ -74,7 +74,6 @@ class BamScanner {
    private:
     bool refill();  // inflate the next group of members behind the carried tail
     void read_header();
-    std::filesystem::path path_;
     std::uint32_t threads_;
     std::size_t chunk_bytes_;
     int fd_ = -1;
@@ -106,7 +105,7 @@ class BgzfWriter {
     std::uint64_t bytes_written() const { return bytes_written_; }
 
    private:
-    void compress_pending(bool all);
+    void compress_pending();  // deflate the closed members on the pool and write them in order
     std::FILE* f_ = nullptr;
     std::uint32_t threads_;
     int level_;

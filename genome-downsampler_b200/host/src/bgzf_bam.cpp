@@ -148,7 +148,7 @@ void parallel_for(std::size_t n, std::uint32_t threads, const std::function<void
 // ------------------------------------------------------------------ scanner
 
 BamScanner::BamScanner(const std::filesystem::path& path, std::uint32_t threads, std::size_t chunk_bytes)
-    : path_(path), threads_(std::max<std::uint32_t>(threads, 1)), chunk_bytes_(std::max<std::size_t>(chunk_bytes, kMaxBlock)) {
+    : threads_(std::max<std::uint32_t>(threads, 1)), chunk_bytes_(std::max<std::size_t>(chunk_bytes, kMaxBlock)) {
     fd_ = ::open(path.c_str(), O_RDONLY);
     if (fd_ < 0) fail("Could not open " + path.string());
     struct stat st {};
@@ -326,7 +326,7 @@ void BgzfWriter::flush() {
     pending_.emplace_back(std::move(cur_));
     cur_.clear();
     cur_.reserve(kBlockPayload);
-    if (pending_.size() >= std::size_t(threads_) * 32) compress_pending(true);
+    if (pending_.size() >= std::size_t(threads_) * 32) compress_pending();
 }
 
 void BgzfWriter::flush_try(std::size_t n) {
@@ -344,7 +344,7 @@ void BgzfWriter::write(const void* data, std::size_t n) {
     }
 }
 
-void BgzfWriter::compress_pending(bool) {
+void BgzfWriter::compress_pending() {
     if (pending_.empty()) return;
     std::vector<std::vector<std::uint8_t>> out(pending_.size());
     parallel_for(pending_.size(), threads_, [&](std::size_t i) {
@@ -387,7 +387,7 @@ void BgzfWriter::compress_pending(bool) {
 void BgzfWriter::close() {
     if (!f_) return;
     flush();
-    compress_pending(true);
+    compress_pending();
     bool ok = std::fwrite(kEofMember, 1, sizeof kEofMember, f_) == sizeof kEofMember;
     bytes_written_ += sizeof kEofMember;
     ok = (std::fclose(f_) == 0) && ok;
