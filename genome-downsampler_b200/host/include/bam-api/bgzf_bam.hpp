@@ -65,14 +65,18 @@ class BamScanner {
 
     const BamHeader& header() const { return header_; }
     // next batch of whole records; false at end of file.  With fields == false only offset and
-    // size are filled (the copy pass needs nothing else).
+    // size are filled (the copy pass needs nothing else).  Chunks alternate between two buffers:
+    // the bytes of a chunk stay valid until the call AFTER the next one, so a caller can work on
+    // one chunk while another thread is inside next() for the following one (one next() at a time).
     bool next(RecordChunk& chunk, bool fields = true);
     bool saw_eof_marker() const { return saw_eof_marker_; }
     std::uint64_t compressed_bytes() const { return file_size_; }
     std::uint64_t uncompressed_bytes() const { return total_out_; }
 
    private:
-    bool refill();  // inflate the next group of members behind the carried tail
+    // inflate the next group of members behind the carried tail: into the other buffer, or (when
+    // one next() needs more than one group) appended to the current one
+    bool refill(bool in_place);
     void read_header();
     std::uint32_t threads_;
     std::size_t chunk_bytes_;
@@ -80,7 +84,8 @@ class BamScanner {
     const std::uint8_t* file_ = nullptr;
     std::size_t file_size_ = 0;
     std::size_t file_pos_ = 0;
-    std::vector<std::uint8_t> buf_;
+    std::vector<std::uint8_t> bufs_[2];
+    int cur_ = 0;
     std::size_t buf_len_ = 0;   // valid bytes in buf_
     std::size_t consumed_ = 0;  // bytes of buf_ already handed out
     std::uint64_t next_id_ = 0;

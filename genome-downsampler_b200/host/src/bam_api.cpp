@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <future>
 #include <map>
 #include <sstream>
 #include <stdexcept>
@@ -307,7 +308,7 @@ void BamApi::read_bam(const std::filesystem::path& input_filepath, SOAPairedRead
         std::vector<QnameTable> tables(parts);
         std::vector<Read> mate;
         std::vector<std::uint8_t> completes;  // 1: (map entry, record)  2: (record, map entry)
-        bgzf::RecordChunk chunk;
+        bgzf::RecordChunk chunks[2];
         BAMReadId id = 0;
         auto make_read = [](BAMReadId rid, const bgzf::RecordFields& f) {
             // Read::Read(id, bam1_t*), read.cpp:5-14: end = pos + bam_cigar2rlen - 1
@@ -315,7 +316,12 @@ void BamApi::read_bam(const std::filesystem::path& input_filepath, SOAPairedRead
                         static_cast<Index>(static_cast<std::uint64_t>(static_cast<std::int64_t>(f.pos)) + f.ref_len - 1),
                         f.mapq, static_cast<std::uint32_t>(f.l_seq), (f.flag & 0x40) != 0);
         };
-        while (scanner.next(chunk)) {
+        // the scanner inflates and indexes chunk k+1 on its own threads while chunk k is paired
+        int cur = 0;
+        bool have = scanner.next(chunks[0]);
+        while (have) {
+            const bgzf::RecordChunk& chunk = chunks[cur];
+            auto ahead = std::async(std::launch::async, [&scanner, &chunks, cur] { return scanner.next(chunks[1 - cur]); });
             const std::size_t n = chunk.records.size();
             mate.resize(n);
             completes.assign(n, 0);
@@ -354,6 +360,8 @@ void BamApi::read_bam(const std::filesystem::path& input_filepath, SOAPairedRead
                 unfiltered.push_back(completes[i] == 2 ? mate[i] : cur);
             }
             id += n;
+            have = ahead.get();
+            cur = 1 - cur;
         }
         bam_record_count_ = id;
     } catch (const std::exception& e) {

@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -149,6 +150,8 @@ void parallel_for(std::size_t n, std::uint32_t threads, const std::function<void
 
 BamScanner::BamScanner(const std::filesystem::path& path, std::uint32_t threads, std::size_t chunk_bytes)
     : threads_(std::max<std::uint32_t>(threads, 1)), chunk_bytes_(std::max<std::size_t>(chunk_bytes, kMaxBlock)) {
+    // testing knob: small chunks make short files cross many chunk boundaries
+    if (const char* e = std::getenv("GDS_BAM_CHUNK_BYTES")) chunk_bytes_ = std::max<std::size_t>(std::strtoull(e, nullptr, 10), 1);
     fd_ = ::open(path.c_str(), O_RDONLY);
     if (fd_ < 0) fail("Could not open " + path.string());
     struct stat st {};
@@ -180,14 +183,8 @@ BamScanner::~BamScanner() {
     if (fd_ >= 0) ::close(fd_);
 }
 
-bool BamScanner::refill() {
+bool BamScanner::refill(bool in_place) {
     if (file_pos_ >= file_size_) return false;
-    // keep the unconsumed tail at the front
-    if (consumed_ > 0) {
-        std::memmove(buf_.data(), buf_.data() + consumed_, buf_len_ - consumed_);
-        buf_len_ -= consumed_;
-        consumed_ = 0;
-    }
     std::vector<Member> members;
     std::size_t add = 0;
     while (file_pos_ < file_size_ && add < chunk_bytes_) {
@@ -199,8 +196,17 @@ bool BamScanner::refill() {
         add += m.isize;
         members.push_back(m);
     }
-    if (buf_.size() < buf_len_ + add) buf_.resize(std::max(buf_len_ + add, buf_.size() + buf_.size() / 2));
-    std::uint8_t* base = buf_.data();
+    // the unconsumed tail goes to the front of the target buffer, the new members behind it
+    const std::size_t tail = buf_len_ - consumed_;
+    std::vector<std::uint8_t>& src = bufs_[cur_];
+    std::vector<std::uint8_t>& dst = in_place ? src : bufs_[1 - cur_];
+    if (dst.size() < tail + add) dst.resize(std::max(tail + add, dst.size() + dst.size() / 2));
+    if (tail > 0 && (consumed_ > 0 || &dst != &src)) std::memmove(dst.data(), src.data() + consumed_, tail);
+    for (Member& m : members) m.out_off -= consumed_;
+    if (!in_place) cur_ = 1 - cur_;
+    buf_len_ = tail;
+    consumed_ = 0;
+    std::uint8_t* base = dst.data();
     // a few members per task so threads do not meet on the counter for every 64 KiB
     constexpr std::size_t kGroup = 8;
     std::size_t groups = (members.size() + kGroup - 1) / kGroup;
@@ -225,40 +231,41 @@ void BamScanner::read_header() {
     // bytes needed so far are pulled in chunk by chunk; headers are small next to a chunk
     auto need = [&](std::size_t n) {
         while (buf_len_ - consumed_ < n)
-            if (!refill()) fail("Failed to read header from file!");
+            if (!refill(true)) fail("Failed to read header from file!");
     };
     std::size_t start = 0;
     need(12);
-    const std::uint8_t* b = buf_.data() + consumed_;
+    const std::uint8_t* b = bufs_[cur_].data() + consumed_;
     if (std::memcmp(b, "BAM\1", 4) != 0) fail("Failed to read header from file! (not a BAM file)");
     std::uint32_t l_text = le32(b + 4);
     need(12 + std::size_t(l_text));
-    b = buf_.data() + consumed_;
+    b = bufs_[cur_].data() + consumed_;
     header_.text.assign(reinterpret_cast<const char*>(b + 8), l_text);
     std::uint32_t n_ref = le32(b + 8 + l_text);
     std::size_t off = 12 + std::size_t(l_text);
     for (std::uint32_t r = 0; r < n_ref; ++r) {
         need(off + 4);
-        b = buf_.data() + consumed_;
+        b = bufs_[cur_].data() + consumed_;
         std::uint32_t l_name = le32(b + off);
         need(off + 8 + std::size_t(l_name));
-        b = buf_.data() + consumed_;
+        b = bufs_[cur_].data() + consumed_;
         const char* nm = reinterpret_cast<const char*>(b + off + 4);
         header_.ref_names.emplace_back(nm, l_name ? strnlen(nm, l_name) : 0);
         header_.ref_lengths.push_back(le32(b + off + 4 + l_name));
         off += 8 + std::size_t(l_name);
     }
-    b = buf_.data() + consumed_;
+    b = bufs_[cur_].data() + consumed_;
     header_.raw.assign(reinterpret_cast<const char*>(b + start), off);
     consumed_ += off;
 }
 
 bool BamScanner::next(RecordChunk& chunk, bool fields) {
     chunk.records.clear();
+    bool switched = false;  // the previous chunk's buffer must survive this call
     for (;;) {
         // serial index of the whole records now in the buffer
         std::size_t p = consumed_;
-        const std::uint8_t* base = buf_.data();
+        const std::uint8_t* base = bufs_[cur_].data();
         while (p + 4 <= buf_len_) {
             std::uint32_t bs = le32(base + p);
             if (bs < 32) fail("corrupt BAM record (block_size < 32)");
@@ -276,10 +283,11 @@ bool BamScanner::next(RecordChunk& chunk, bool fields) {
             consumed_ = p;
             break;
         }
-        if (!refill()) {
+        if (!refill(switched)) {
             if (buf_len_ != consumed_) fail("truncated BAM record at end of file");
             return false;
         }
+        switched = true;
     }
     if (fields) {
         const std::uint8_t* base = chunk.data;

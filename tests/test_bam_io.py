@@ -347,3 +347,33 @@ def test_header_only_bam_and_more_threads_than_records(hostlib, tmp_path):
     assert b.write_solution(out, [1], with_pairs=True) == 2
     assert pybam.read_bam(out)[2] == recs
     b.close()
+
+
+@pytest.mark.parametrize("chunk_bytes", [1, 70_000, 1_000_000])
+def test_many_chunks_alternate_buffers_and_carry_records(hostlib, O, tmp_path, monkeypatch, chunk_bytes):
+    # GDS_BAM_CHUNK_BYTES (testing knob): a chunk per BGZF member / per few members, so records
+    # straddle chunks, the scanner's two buffers alternate hundreds of times while the pairing
+    # runs one chunk behind, and the 70 KB record needs several refills inside one call
+    monkeypatch.setenv("GDS_BAM_CHUNK_BYTES", str(chunk_bytes))
+    s, e, q, l = O.gen_reads(5, 15_000, 30_000, 150)
+    path = tmp_path / "sorted.bam"
+    hostlib.write_synthetic_bam(path, 30_000, s, e, q, l, coordinate_sorted=True, threads=4)
+    _, _, recs = pybam.read_bam(path)
+    want, want_out = pybam.ref_read_bam(recs, 0, 25)
+    for threads in (1, 5):
+        b = hostlib.BamFile(path, min_mapq=25, threads=threads)
+        assert_same_reads(b.reads(), want)
+        assert b.filtered_out().tolist() == want_out
+        ids = list(range(0, len(recs), 7))
+        out = tmp_path / "o.bam"
+        assert hostlib.write_bam(path, out, ids, threads=threads) == len(ids)
+        assert pybam.read_bam(out)[2] == [recs[i] for i in ids]
+        b.close()
+    recs = handmade_records()
+    small = tmp_path / "handmade.bam"
+    pybam.write_bam(small, HEADER, recs, member_payload=3000)
+    b = hostlib.BamFile(small, threads=3)
+    want, want_out = pybam.ref_read_bam(recs)
+    assert_same_reads(b.reads(), want)
+    assert b.filtered_out().tolist() == want_out
+    b.close()
