@@ -304,10 +304,12 @@ void BamApi::read_bam(const std::filesystem::path& input_filepath, SOAPairedRead
         // QNAMEs are split over one table per thread by hash, so the lookups of a chunk run in
         // parallel while every name still meets its earlier records in file order; the pairs are
         // then appended serially in the order their second record appears (pair-completion order)
-        const std::uint32_t parts = std::max<std::uint32_t>(hts_thread_count_, 1);
+        const std::uint32_t parts = std::min<std::uint32_t>(std::max<std::uint32_t>(hts_thread_count_, 1), 4096);
         std::vector<QnameTable> tables(parts);
         std::vector<Read> mate;
         std::vector<std::uint8_t> completes;  // 1: (map entry, record)  2: (record, map entry)
+        std::vector<std::uint16_t> part_of;
+        std::vector<std::uint32_t> order, counts, part_begin;
         bgzf::RecordChunk chunks[2];
         BAMReadId id = 0;
         auto make_read = [](BAMReadId rid, const bgzf::RecordFields& f) {
@@ -318,18 +320,53 @@ void BamApi::read_bam(const std::filesystem::path& input_filepath, SOAPairedRead
         };
         // the scanner inflates and indexes chunk k+1 on its own threads while chunk k is paired
         int cur = 0;
+        double t_pair = 0, t_append = 0, t_wait = 0;
         bool have = scanner.next(chunks[0]);
         while (have) {
             const bgzf::RecordChunk& chunk = chunks[cur];
             auto ahead = std::async(std::launch::async, [&scanner, &chunks, cur] { return scanner.next(chunks[1 - cur]); });
             const std::size_t n = chunk.records.size();
+            auto tp0 = std::chrono::steady_clock::now();
             mate.resize(n);
             completes.assign(n, 0);
+            // counting sort of the chunk's record numbers by table (stable, so every table sees
+            // its records in file order): each pairing thread then touches only its own records
+            constexpr std::size_t kGrain = 8192;
+            const std::size_t grains = (n + kGrain - 1) / kGrain;
+            part_of.resize(n);
+            order.resize(n);
+            counts.assign(grains * parts + 1, 0);
+            bgzf::parallel_for(grains, parts, [&](std::size_t g) {
+                std::uint32_t* c = counts.data() + g * parts;
+                for (std::size_t i = g * kGrain; i < std::min(n, (g + 1) * kGrain); ++i) {
+                    const std::uint32_t pt = static_cast<std::uint32_t>((chunk.records[i].qname_hash >> 40) % parts);
+                    part_of[i] = static_cast<std::uint16_t>(pt);
+                    ++c[pt];
+                }
+            });
+            part_begin.assign(parts + 1, 0);
+            {
+                std::uint32_t run = 0;
+                for (std::uint32_t pt = 0; pt < parts; ++pt) {
+                    part_begin[pt] = run;
+                    for (std::size_t g = 0; g < grains; ++g) {
+                        const std::uint32_t c = counts[g * parts + pt];
+                        counts[g * parts + pt] = run;
+                        run += c;
+                    }
+                }
+                part_begin[parts] = run;
+            }
+            bgzf::parallel_for(grains, parts, [&](std::size_t g) {
+                std::uint32_t* cursor = counts.data() + g * parts;
+                for (std::size_t i = g * kGrain; i < std::min(n, (g + 1) * kGrain); ++i)
+                    order[cursor[part_of[i]]++] = static_cast<std::uint32_t>(i);
+            });
             bgzf::parallel_for(parts, parts, [&](std::size_t part) {
                 QnameTable& table = tables[part];
-                for (std::size_t i = 0; i < n; ++i) {
+                for (std::uint32_t k = part_begin[part]; k < part_begin[part + 1]; ++k) {
+                    const std::size_t i = order[k];
                     const bgzf::RecordFields& f = chunk.records[i];
-                    if ((f.qname_hash >> 40) % parts != part) continue;
                     Read cur = make_read(id + i, f);
                     const char* name = chunk.qname(f);
                     if (QnameTable::Slot* s = table.find(f.qname_hash, name, f.l_qname)) {
@@ -353,6 +390,7 @@ void BamApi::read_bam(const std::filesystem::path& input_filepath, SOAPairedRead
                     }
                 }
             });
+            auto tp1 = std::chrono::steady_clock::now();
             for (std::size_t i = 0; i < n; ++i) {
                 if (!completes[i]) continue;
                 Read cur = make_read(id + i, chunk.records[i]);
@@ -360,10 +398,17 @@ void BamApi::read_bam(const std::filesystem::path& input_filepath, SOAPairedRead
                 unfiltered.push_back(completes[i] == 2 ? mate[i] : cur);
             }
             id += n;
+            auto tp2 = std::chrono::steady_clock::now();
             have = ahead.get();
+            auto tp3 = std::chrono::steady_clock::now();
+            t_pair += std::chrono::duration<double>(tp1 - tp0).count();
+            t_append += std::chrono::duration<double>(tp2 - tp1).count();
+            t_wait += std::chrono::duration<double>(tp3 - tp2).count();
             cur = 1 - cur;
         }
         bam_record_count_ = id;
+        LOG_WITH_LEVEL(logging::DEBUG) << "BamApi: pairing " << t_pair << " s, pair append " << t_append
+                                       << " s, waiting for the scanner " << t_wait << " s";
     } catch (const std::exception& e) {
         LOG_WITH_LEVEL(logging::ERROR) << e.what();
         std::exit(EXIT_FAILURE);
