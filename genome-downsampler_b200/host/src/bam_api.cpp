@@ -230,52 +230,69 @@ namespace {
 // same job without a node allocation per read.
 class QnameTable {
    public:
-    struct Slot {
-        std::uint64_t hash = 0;
+    // what the map holds for a name; `partner` indexes partners_ while a swap is pending
+    struct Entry {
         std::uint64_t name_off = 0;
         Read read;
-        Read partner;               // the later read whose arrival may have swapped the entry
+        std::uint32_t partner = kNone;  // the later read whose arrival may have swapped the entry
         std::uint8_t name_len = 0;
-        bool used = false;
-        bool swap_pending = false;  // entry becomes `partner` iff that pair passed the filter
     };
+    static constexpr std::uint32_t kNone = 0xffffffffu;
     QnameTable() : slots_(1u << 10) {}
-    Slot* find(std::uint64_t h, const char* name, std::uint8_t len) {
+    Entry* find(std::uint64_t h, const char* name, std::uint8_t len) {
         for (std::size_t i = h & (slots_.size() - 1);; i = (i + 1) & (slots_.size() - 1)) {
-            Slot& s = slots_[i];
-            if (!s.used) return nullptr;
-            if (s.hash == h && s.name_len == len && std::memcmp(arena_.data() + s.name_off, name, len) == 0)
-                return &s;
+            const Slot& s = slots_[i];
+            if (!s.entry_plus1) return nullptr;
+            if (s.hash != h) continue;
+            Entry& e = entries_[s.entry_plus1 - 1];
+            if (e.name_len == len && std::memcmp(arena_.data() + e.name_off, name, len) == 0) return &e;
         }
     }
     void insert(std::uint64_t h, const char* name, std::uint8_t len, const Read& r) {
-        if ((count_ + 1) * 10 > slots_.size() * 6) grow();
-        Slot s;
-        s.hash = h;
-        s.name_off = arena_.size();
-        s.name_len = len;
-        s.read = r;
-        s.used = true;
+        if ((entries_.size() + 1) * 10 > slots_.size() * 6) grow();
+        Entry e;
+        e.name_off = arena_.size();
+        e.name_len = len;
+        e.read = r;
         arena_.insert(arena_.end(), name, name + len);
-        place(slots_, s);
-        ++count_;
+        entries_.push_back(e);
+        place(slots_, Slot{h, static_cast<std::uint32_t>(entries_.size())});
     }
+    // the entry becomes `partner` iff that pair passed the filter (resolved when the name returns)
+    bool swap_pending(const Entry& e) const { return e.partner != kNone; }
+    const Read& partner(const Entry& e) const { return partners_[e.partner]; }
+    void set_partner(Entry& e, const Read& r) {
+        if (e.partner == kNone) {
+            e.partner = static_cast<std::uint32_t>(partners_.size());
+            partners_.push_back(r);
+        } else {
+            partners_[e.partner] = r;
+        }
+    }
+    void clear_partner(Entry& e) { e.partner = kNone; }  // the slot in partners_ is simply left behind
 
    private:
+    // 16-byte probe records: the reads and names live in side arrays, so a table of a million
+    // names probes 32 MB instead of 200
+    struct Slot {
+        std::uint64_t hash = 0;
+        std::uint32_t entry_plus1 = 0;  // 0 = empty
+    };
     static void place(std::vector<Slot>& t, const Slot& s) {
         std::size_t i = s.hash & (t.size() - 1);
-        while (t[i].used) i = (i + 1) & (t.size() - 1);
+        while (t[i].entry_plus1) i = (i + 1) & (t.size() - 1);
         t[i] = s;
     }
     void grow() {
         std::vector<Slot> bigger(slots_.size() * 2);
         for (const Slot& s : slots_)
-            if (s.used) place(bigger, s);
+            if (s.entry_plus1) place(bigger, s);
         slots_.swap(bigger);
     }
     std::vector<Slot> slots_;
+    std::vector<Entry> entries_;
+    std::vector<Read> partners_;
     std::vector<char> arena_;
-    std::size_t count_ = 0;
 };
 
 }  // namespace
@@ -369,19 +386,19 @@ void BamApi::read_bam(const std::filesystem::path& input_filepath, SOAPairedRead
                     const bgzf::RecordFields& f = chunk.records[i];
                     Read cur = make_read(id + i, f);
                     const char* name = chunk.qname(f);
-                    if (QnameTable::Slot* s = table.find(f.qname_hash, name, f.l_qname)) {
+                    if (QnameTable::Entry* e = table.find(f.qname_hash, name, f.l_qname)) {
                         // a QNAME seen a third time pairs with whatever the map holds by then: the
                         // reference swaps the map entry with the second read only when that pair
                         // survived the filter (the `continue` of :438-441 skips the swap)
-                        if (s->swap_pending) {
-                            if (!should_be_filtered_out(s->read, s->partner)) s->read = s->partner;
-                            s->swap_pending = false;
+                        if (table.swap_pending(*e)) {
+                            const Read& p = table.partner(*e);
+                            if (!should_be_filtered_out(e->read, p)) e->read = p;
+                            table.clear_partner(*e);
                         }
-                        mate[i] = s->read;
+                        mate[i] = e->read;
                         if (cur.is_first_read) {
                             completes[i] = 2;
-                            s->partner = cur;
-                            s->swap_pending = true;
+                            table.set_partner(*e, cur);
                         } else {
                             completes[i] = 1;
                         }
