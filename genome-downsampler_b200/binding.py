@@ -70,7 +70,8 @@ _SCALARS = [n for n, _ in _Result._fields_[5:]]
 
 
 def lib_path():
-    return os.path.join(_HERE, "libgds_b200.so")
+    # GDS_LIB_PATH: an instrumented build of the same library (tools/, diagnostics only)
+    return os.environ.get("GDS_LIB_PATH") or os.path.join(_HERE, "libgds_b200.so")
 
 
 def exported_symbols():

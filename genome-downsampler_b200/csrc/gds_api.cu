@@ -14,6 +14,7 @@
 #include "direct.cuh"
 #include "graph.cuh"
 #include "maxflow.cuh"
+#include "maxflow_sm.cuh"
 #include "prep.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
@@ -50,7 +51,8 @@ struct gds_ctx {
     DevBuf bitmap, cov_tmp, dem_tmp, vdiff, vexcl;
     DevBuf vs_d, cross_idx, cross_tc, odiff, oexcl, cut_nodes, tile_off_d, head_bits;
     DevBuf dhist, dlay, b_slot, ident, dwork;  // direct (sort-free) bundle path
-    DevBuf kstat, pbund, cand, dctl, in_src;
+    DevBuf kstat, pbund, cand, dctl, in_src, dem_v, fb_list;
+    int mf2_smem_set[3] = {0, 0, 0};
     unsigned direct_attr = 0;                  // bytes of dynamic smem the direct kernels are set up for
     int mf_smem_set[4] = {0, 0, 0, 0};  // dynamic shared memory the launch shapes are set up for
     bool atomic_rank = false;  // shared-memory atomics rank in lane order on this device (probed)
@@ -65,7 +67,7 @@ struct gds_ctx {
                          &comp_lo, &comp_hi, &qF, &qT, &qN, &qH, &work_counter, &comp_stats,
                          &bitmap, &cov_tmp, &dem_tmp, &vdiff, &vexcl, &vs_d, &cross_idx, &cross_tc,
                          &odiff, &oexcl, &cut_nodes, &tile_off_d, &head_bits, &dhist, &dlay, &b_slot,
-                         &ident, &dwork, &kstat, &pbund, &cand, &dctl, &in_src};
+                         &ident, &dwork, &kstat, &pbund, &cand, &dctl, &in_src, &dem_v, &fb_list};
         for (DevBuf* b : all) b->release();
     }
 };
@@ -118,7 +120,8 @@ template <int I>
 void launch_maxflow_shape(gds_ctx* c, const MfGraph& mg,
                           const uint32_t* comp_lo, const uint32_t* comp_hi, uint32_t n_comp,
                           uint32_t* wc, uint32_t* qF, uint32_t* qT, uint32_t* qN, uint32_t* qH,
-                          const SolveParams& sp, CompStats* cstats, uint32_t max_comp_nodes) {
+                          const SolveParams& sp, CompStats* cstats, uint32_t max_comp_nodes,
+                          const uint32_t* comp_list, const uint32_t* comp_list_n) {
     constexpr MfShape sh = kMfShapes[I];
     auto kern = k_maxflow<sh.threads, sh.qcap, sh.ctas_per_sm>;
     // 16-bit labels of a whole component in shared memory for the first global relabel, when
@@ -140,14 +143,15 @@ void launch_maxflow_shape(gds_ctx* c, const MfGraph& mg,
     }
     int grid = std::min<uint32_t>(n_comp, (uint32_t)kNumSMs * sh.ctas_per_sm);
     kern<<<grid, sh.threads, smem, c->stream>>>(mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp,
-                                                cstats, lab_cap);
+                                                cstats, lab_cap, comp_list, comp_list_n);
 }
 
 void launch_maxflow(gds_ctx* c, const MfGraph& mg,
                     const uint32_t* comp_lo, const uint32_t* comp_hi, uint32_t n_comp, uint32_t* wc,
                     uint32_t* qF, uint32_t* qT, uint32_t* qN, uint32_t* qH, const SolveParams& sp,
-                    CompStats* cstats, unsigned long long alg_bytes, uint32_t max_comp_nodes) {
-    KScope ks("maxflow", alg_bytes, c->stream);
+                    CompStats* cstats, unsigned long long alg_bytes, uint32_t max_comp_nodes,
+                    const uint32_t* comp_list = nullptr, const uint32_t* comp_list_n = nullptr) {
+    KScope ks(comp_list ? "maxflow_fallback" : "maxflow", alg_bytes, c->stream);
     const uint32_t sms = (uint32_t)kNumSMs;
     int shape = 3;
     for (int i = 0; i < 3; ++i)
@@ -161,12 +165,104 @@ void launch_maxflow(gds_ctx* c, const MfGraph& mg,
     if (const char* e = getenv("GDS_MF_SMEM_LABELS"))  // =0: labels stay in global memory
         if (e[0] == '0') max_comp_nodes = 0;
     switch (shape) {
-        case 0: launch_maxflow_shape<0>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes); break;
-        case 1: launch_maxflow_shape<1>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes); break;
-        case 2: launch_maxflow_shape<2>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes); break;
-        default: launch_maxflow_shape<3>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes); break;
+        case 0: launch_maxflow_shape<0>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes, comp_list, comp_list_n); break;
+        case 1: launch_maxflow_shape<1>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes, comp_list, comp_list_n); break;
+        case 2: launch_maxflow_shape<2>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes, comp_list, comp_list_n); break;
+        default: launch_maxflow_shape<3>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes, comp_list, comp_list_n); break;
     }
     GDS_KERNEL_CHECK();
+}
+
+// K3 with the hot state in shared memory (maxflow_sm.cuh).  Returns false when no component of
+// this call can fit (then k_maxflow solves everything).  Components the kernel finds ineligible
+// (too large for the launch, supply beyond 16 bits) land on fb_list for k_maxflow.
+constexpr int kMf2MaxSmem = 227 * 1024;
+template <int THREADS, int SLOT>
+void launch_mf2_shape(gds_ctx* c, const Mf2Graph& g, const uint32_t* comp_lo, const uint32_t* comp_hi,
+                      uint32_t n_comp, uint32_t* wc, uint32_t* qF, uint32_t* qT, uint32_t* qN,
+                      uint32_t* qH, const SolveParams& sp, CompStats* cstats, int smem, uint32_t qcap,
+                      uint32_t* fb_list, uint32_t* fb_count, bool optr, int ctas_per_sm) {
+    auto kern = k_maxflow_sm<THREADS>;
+    if (c->mf2_smem_set[SLOT] < smem) {
+        GDS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        c->mf2_smem_set[SLOT] = smem;
+    }
+    const int grid = (int)std::min<uint32_t>(n_comp, (uint32_t)(kNumSMs * ctas_per_sm));
+    kern<<<grid, THREADS, smem, c->stream>>>(g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats,
+                                             (uint32_t)smem, qcap, fb_list, fb_count, optr ? 1u : 0u);
+}
+
+bool launch_maxflow_sm(gds_ctx* c, const Mf2Graph& g, const uint32_t* comp_lo, const uint32_t* comp_hi,
+                       uint32_t n_comp, uint32_t* wc, uint32_t* qF, uint32_t* qT, uint32_t* qN,
+                       uint32_t* qH, const SolveParams& sp, CompStats* cstats,
+                       unsigned long long alg_bytes, uint32_t max_comp_nodes, uint32_t* fb_list,
+                       uint32_t* fb_count) {
+    if (const char* e = getenv("GDS_MF"))  // =global: the round-1 kernel (state in global memory)
+        if (!strcmp(e, "global")) return false;
+    // shared memory per CTA: header + 4 staged queues + the node arrays of the largest component
+    // that should still fit.  Prefer the out-CSR cache unless leaving it out lets all components
+    // be resident at once (a batch of segments) where they otherwise would not be.
+    auto need = [&](uint32_t nodes, bool optr, uint32_t qcap) {
+        return (long long)kMf2HeaderBytes + 16ll * qcap + mf2_node_bytes(nodes, optr);
+    };
+    const uint32_t nmax = std::min<uint32_t>(max_comp_nodes, kMf2MaxNodes);
+    if (nmax == 0) return false;
+    uint32_t qcap = 2048;
+    bool optr = true;
+    if (const char* e = getenv("GDS_MF_OPTR")) optr = e[0] != '0';
+    // the queues shrink before the node arrays do
+    while (qcap > 256 && need(nmax, optr, qcap) > kMf2MaxSmem) qcap >>= 1;
+    if (need(nmax, optr, qcap) > kMf2MaxSmem) optr = false;
+    if (need(nmax, optr, qcap) > kMf2MaxSmem && max_comp_nodes > nmax) return false;
+    long long smem_ll = need(nmax, optr, qcap);
+    if (smem_ll > kMf2MaxSmem) {
+        // the largest component does not fit; smaller ones may: give the kernel everything
+        smem_ll = kMf2MaxSmem;
+    }
+    // CTAs per SM: by shared memory, and never more than two (128 registers x 256 threads each)
+    auto resident = [&](long long bytes) {
+        return std::min(2, std::max(1, (int)((228 * 1024) / (bytes + 1024))));
+    };
+    int per_sm = resident(smem_ll);
+    if (optr && n_comp > (uint32_t)kNumSMs * per_sm) {
+        uint32_t q2 = qcap;
+        while (q2 > 512 && resident(need(nmax, false, q2)) <= per_sm) q2 >>= 1;
+        const int alt = resident(need(nmax, false, q2));
+        if (alt > per_sm) {
+            optr = false;
+            qcap = q2;
+            smem_ll = need(nmax, false, qcap);
+            per_sm = alt;
+        }
+    }
+    const int smem = (int)((smem_ll + 15) & ~15ll);
+    // One CTA per component with the component's labels next to the SM is a LATENCY design: it wins
+    // while (nearly) all components are resident at once.  A batch beyond that (config 5: 512
+    // samples of 180 KB each, one per SM, four waves: 3.2 ms) is faster on k_maxflow, whose state
+    // lives in L2/HBM but which runs every component concurrently (1.84 ms).  GDS_MF=sm forces this
+    // kernel for measurements.
+    {
+        const char* e = getenv("GDS_MF");
+        const bool forced = e && !strcmp(e, "sm");
+        if (!forced && (unsigned long long)n_comp * 2 > 3ull * kNumSMs * per_sm) return false;
+    }
+    KScope ks("maxflow", alg_bytes, c->stream);
+    // 1024 threads would cap the kernel at 64 registers and make it spill: local memory is what this
+    // kernel must not touch (maxflow_sm.cuh), so it is a measurement knob only
+    int shape = per_sm >= 2 ? 0 : 1;
+    if (const char* e = getenv("GDS_MF2_THREADS")) {
+        if (!strcmp(e, "256")) shape = 0;
+        if (!strcmp(e, "512")) shape = 1;
+        if (!strcmp(e, "1024")) shape = 2;
+    }
+    if (shape != 0) per_sm = 1;
+    switch (shape) {
+        case 0: launch_mf2_shape<256, 0>(c, g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, smem, qcap, fb_list, fb_count, optr, per_sm); break;
+        case 1: launch_mf2_shape<512, 1>(c, g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, smem, qcap, fb_list, fb_count, optr, per_sm); break;
+        default: launch_mf2_shape<1024, 2>(c, g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, smem, qcap, fb_list, fb_count, optr, per_sm); break;
+    }
+    GDS_KERNEL_CHECK();
+    return true;
 }
 
 template <typename K>
@@ -1057,6 +1153,7 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         }
         NodeRec* node = c->node_rec.get<NodeRec>((size_t)n_nodes + 1);
         uint32_t* d_snap = c->n_dsnap.get<uint32_t>(n_nodes);
+        int32_t* dem_v = c->dem_v.get<int32_t>((size_t)n_nodes + 1);
         uint32_t* cstart = c->comp_start.get<uint32_t>(n_nodes + 1);
         uint32_t* cend = c->comp_end.get<uint32_t>(n_nodes + 1);
         GDS_CUDA(cudaMemsetAsync(cstart + n_nodes, 0, 4, st));
@@ -1070,7 +1167,7 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             KScope ks("node_finalize", 60ull * n_nodes, st);
             k_node_finalize<<<div_up((long long)n_nodes + 1, 256), 256, 0, st>>>(
                 excl, diff, out_ptr, in_ptr, n_nodes, max_coverage, node, d_snap, cstart, cend,
-                split ? nullptr : cov_dev, split ? nullptr : dem_dev, totals);
+                split ? nullptr : cov_dev, split ? nullptr : dem_dev, dem_v, totals);
             GDS_KERNEL_CHECK();
         }
         if (split) {
@@ -1133,10 +1230,11 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         uint32_t* in_src = c->in_src.get<uint32_t>((size_t)B + 1);
         if (B) {
             KScope ks("in_src", 24ull * B, st);
-            k_in_src<<<div_up(B, 256), 256, 0, st>>>(c->bund.as<BundleRec>(), in_bid, B, in_src);
+            k_in_src<<<div_up(B, 256), 256, 0, st>>>(c->bund.as<BundleRec>(), in_bid, in_ptr, B, in_src,
+                                                     node);
             GDS_KERNEL_CHECK();
         }
-        MfGraph mg{node, d_snap, c->bund.as<BundleRec>(), in_bid, in_src};
+        MfGraph mg{node, d_snap, c->bund.as<BundleRec>(), in_bid, in_src, dem_v};
         CompStats* cstats = c->comp_stats.get<CompStats>(n_comp + 1);
         const bool do_solve = !(flags & GDS_NO_SOLVE);
         if (do_solve && n_comp) {
@@ -1144,14 +1242,24 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             uint32_t* qT = c->qT.get<uint32_t>(n_nodes);
             uint32_t* qN = c->qN.get<uint32_t>(n_nodes);
             uint32_t* qH = c->qH.get<uint32_t>(n_nodes);
-            uint32_t* wc = c->work_counter.get<uint32_t>(1);
-            GDS_CUDA(cudaMemsetAsync(wc, 0, 4, st));
+            uint32_t* wc = c->work_counter.get<uint32_t>(4);  // [0] sm kernel, [1] fallback, [2] list size
+            GDS_CUDA(cudaMemsetAsync(wc, 0, 16, st));
             // no component is larger than a whole unsegmented sample or one segment
             uint32_t max_comp_nodes = 0;
             for (const VSample& v : hvs)
                 max_comp_nodes = std::max(max_comp_nodes, v.nseg == 1 ? v.L + 1 : seg + 1);
-            launch_maxflow(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats,
-                           36ull * n_nodes + 20ull * B, max_comp_nodes);
+            const unsigned long long mf_bytes = 36ull * n_nodes + 20ull * B;
+            uint32_t* fb_list = c->fb_list.get<uint32_t>(n_comp + 1);
+            Mf2Graph g2{node, c->bund.as<BundleRec>(), in_bid, in_src, out_ptr, in_ptr, dem_v};
+            if (launch_maxflow_sm(c, g2, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats,
+                                  mf_bytes, max_comp_nodes, fb_list, wc + 2)) {
+                // whatever the shared-memory kernel could not take (grid: at most one wave)
+                launch_maxflow(c, mg, comp_lo, comp_hi, std::min<uint32_t>(n_comp, kNumSMs), wc + 1, qF,
+                               qT, qN, qH, sp, cstats, 0, max_comp_nodes, fb_list, wc + 2);
+            } else {
+                launch_maxflow(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats,
+                               mf_bytes, max_comp_nodes);
+            }
         }
         GDS_CUDA(cudaEventRecord(c->ev[EV_MAXFLOW], st));
 
@@ -1224,12 +1332,12 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             d2h_sync(c, hs.data(), cstats, n_comp);
             if (const char* dump = getenv("GDS_DUMP_COMP")) {  // diagnostics only
                 if (FILE* fp = fopen(dump, "w")) {
-                    fprintf(fp, "comp rounds pushes relabels grs bfs_levels max_frontier frontier_sum cycles gr_init gr_bfs gr_snap front\n");
+                    fprintf(fp, "comp rounds pushes relabels grs bfs_levels max_frontier frontier_sum cycles gr_init gr_bfs gr_snap front gr_later\n");
                     for (uint32_t i = 0; i < n_comp; ++i)
-                        fprintf(fp, "%u %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu\n", i,
+                        fprintf(fp, "%u %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu\n", i,
                                 hs[i].rounds, hs[i].pushes, hs[i].relabels, hs[i].grs, hs[i].bfs_levels,
                                 hs[i].max_frontier, hs[i].frontier_sum, hs[i].cycles, hs[i].cyc_gr_init,
-                                hs[i].cyc_gr_bfs, hs[i].cyc_gr_snap, hs[i].cyc_front);
+                                hs[i].cyc_gr_bfs, hs[i].cyc_gr_snap, hs[i].cyc_front, hs[i].cyc_gr_later);
                     fclose(fp);
                 }
             }

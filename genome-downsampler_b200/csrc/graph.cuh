@@ -271,9 +271,13 @@ k_heads_write(const K* __restrict__ keys, TileMap tm, const uint32_t* __restrict
 // push touches: own node (1 sector, neighbours v-1 / v+1 adjacent) -> bundle (1 load) -> target
 // node (1 sector).  Everything a round decides on comes from these records; d_snap (the label
 // snapshot relabels read) is the only side array.
+// The first 16 bytes are written twice: K2 (k_in_src) leaves {start node, bundle id} of the node's
+// NEAREST in-arc there (0, 0 without in-arcs) for k_maxflow_sm, whose labels and excess live in shared
+// memory; k_maxflow (state in global memory) overwrites them with {d, stamp, e, eadd} when it takes
+// a component.
 struct __align__(32) NodeRec {
-    uint32_t d;        // label
-    uint32_t stamp;    // round in which v is in the frontier
+    uint32_t d;        // label                                      | start node of the nearest in-arc
+    uint32_t stamp;    // round in which v is in the frontier        | its bundle id
     int32_t e;         // excess                                    (e, eadd: one aligned 8-byte
     int32_t eadd;      // excess received during the current round   store in phase B; 0 between rounds)
     int32_t snk;       // remaining sink-arc capacity
@@ -367,12 +371,13 @@ k_node_finalize(const uint32_t* __restrict__ excl, const int32_t* __restrict__ d
                 uint32_t n_nodes, uint32_t M, NodeRec* __restrict__ node,
                 uint32_t* __restrict__ d_snap, uint32_t* __restrict__ comp_start,
                 uint32_t* __restrict__ comp_end, uint32_t* __restrict__ cov_capped_out,
-                int32_t* __restrict__ demand_out, unsigned long long* __restrict__ totals) {
+                int32_t* __restrict__ demand_out, int32_t* __restrict__ dem_v /* [n_nodes] always */,
+                unsigned long long* __restrict__ totals) {
     uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long src = 0;
     if (v == n_nodes) {  // sentinel record: closes the CSR ranges of the last node
         uint4* r = reinterpret_cast<uint4*>(&node[v]);
-        r[0] = make_uint4(kLabelInf, 0u, 0u, 0u);
+        r[0] = make_uint4(0u, 0u, 0u, 0u);
         r[1] = make_uint4(0u, 0u, out_ptr[v], in_ptr[v]);
     }
     static_assert(sizeof(NodeRec) == 32 && offsetof(NodeRec, e) == 8 && offsetof(NodeRec, snk) == 16,
@@ -382,9 +387,10 @@ k_node_finalize(const uint32_t* __restrict__ excl, const int32_t* __restrict__ d
         uint32_t covR = covL + (uint32_t)diff[v];
         int32_t dem = (int32_t)min(covL, M) - (int32_t)min(covR, M);
         uint4* r = reinterpret_cast<uint4*>(&node[v]);
-        r[0] = make_uint4(kLabelInf, 0u, (uint32_t)(dem < 0 ? -dem : 0), 0u);  // d, stamp, e, eadd
+        r[0] = make_uint4(0u, 0u, 0u, 0u);  // nearest in-arc: k_in_src
         r[1] = make_uint4((uint32_t)(dem > 0 ? dem : 0), 0u, out_ptr[v], in_ptr[v]);  // snk, g, ptrs
         d_snap[v] = kLabelInf;
+        dem_v[v] = dem;
         comp_start[v] = (covL == 0 && covR > 0) ? 1u : 0u;
         comp_end[v] = (covL > 0 && covR == 0) ? 1u : 0u;
         if (cov_capped_out) cov_capped_out[v] = min(covR, M);
@@ -396,12 +402,19 @@ k_node_finalize(const uint32_t* __restrict__ excl, const int32_t* __restrict__ d
     if (lane_id() == 0 && src) atomicAdd(&totals[0], src);
 }
 
-// start node of every in-CSR slot (the first global relabel of K3 walks only this array)
+// start node of every in-CSR slot (the first global relabel of K3 walks only this array), and for
+// every node with in-arcs {start node, bundle id} of its last in-CSR slot — the nearest start, the
+// first one a cancel tries — next to its other fields, so a push needs no in-CSR lookup
 __global__ void __launch_bounds__(256)
-k_in_src(const BundleRec* __restrict__ bund, const uint32_t* __restrict__ in_bid, uint32_t B,
-         uint32_t* __restrict__ in_src) {
+k_in_src(const BundleRec* __restrict__ bund, const uint32_t* __restrict__ in_bid,
+         const uint32_t* __restrict__ in_ptr, uint32_t B, uint32_t* __restrict__ in_src,
+         NodeRec* __restrict__ node) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < B) in_src[k] = bund[in_bid[k]].s;
+    if (k >= B) return;
+    const uint32_t b = in_bid[k];
+    const uint4 r = reinterpret_cast<const uint4*>(bund)[b];  // t, mult, f, s
+    in_src[k] = r.w;
+    if (k + 1 == in_ptr[r.x + 1]) *reinterpret_cast<uint2*>(&node[r.x]) = make_uint2(r.w, b);
 }
 
 // Components are disjoint runs, so starts and ends alternate: the end at v closes the component

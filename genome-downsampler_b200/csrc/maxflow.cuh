@@ -44,6 +44,7 @@ struct MfGraph {
     BundleRec* bund;         // [B] sorted by (start node, key)
     const uint32_t* in_bid;  // [B] bundle ids ordered by (end node, bundle id)
     const uint32_t* in_src;  // [B] start node of in_bid[k]: the first relabel needs nothing else
+    const int32_t* dem;      // [n_nodes] demand: the initial excess / sink capacity come from it
 };
 
 struct SolveParams {
@@ -56,7 +57,7 @@ struct CompStats {
     unsigned long long cycles, frontier_sum;  // diagnostics: SM clocks spent, sum of frontier sizes
     // diagnostics: clocks of the first global relabel's label reset, its BFS levels, its snapshot
     // copy, and of the initial frontier scan
-    unsigned long long cyc_gr_init, cyc_gr_bfs, cyc_gr_snap, cyc_front;
+    unsigned long long cyc_gr_init, cyc_gr_bfs, cyc_gr_snap, cyc_front, cyc_gr_later;
 };
 
 // Record loads.  A component is owned by ONE CTA, i.e. one SM: plain (L1-allocating) loads are
@@ -382,17 +383,21 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS)
 k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __restrict__ comp_hi,
           uint32_t n_comp, uint32_t* work_counter, uint32_t* qF_g, uint32_t* qT_g, uint32_t* qN_g,
           uint32_t* qH_g, SolveParams P, CompStats* __restrict__ stats,
-          uint32_t lab_cap /* nodes the shared-memory label array behind MfShared holds (0: none) */) {
+          uint32_t lab_cap /* nodes the shared-memory label array behind MfShared holds (0: none) */,
+          const uint32_t* __restrict__ comp_list /* null: all components; else the ids to solve */,
+          const uint32_t* __restrict__ comp_list_n) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MfShared<QCAP>& sh = *reinterpret_cast<MfShared<QCAP>*>(smem_raw);
     uint16_t* lab_base = reinterpret_cast<uint16_t*>(smem_raw + sizeof(MfShared<QCAP>));
     const uint32_t tid = threadIdx.x;
+    if (comp_list) n_comp = *comp_list_n;  // the components k_maxflow_sm left for this kernel
 
     for (;;) {
         if (tid == 0) sh.comp = atomicAdd(work_counter, 1u);
         __syncthreads();
-        const uint32_t c = sh.comp;
-        if (c >= n_comp) break;
+        const uint32_t ticket = sh.comp;
+        if (ticket >= n_comp) break;
+        const uint32_t c = comp_list ? comp_list[ticket] : ticket;
         const uint32_t lo = comp_lo[c], hi = comp_hi[c];
         const uint32_t ncomp = hi - lo + 1;
         Queue<QCAP> F{sh.qa, qF_g + lo}, T{sh.qb, qT_g + lo}, N{sh.qc, qN_g + lo},
@@ -407,6 +412,14 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
         }
         unsigned long long bfs_levels = 0, grs = 1, rounds = 0, max_frontier = 0, frontier_sum = 0;
         const long long t_begin = clock64();
+        // the first half of the node records holds K2's in-arc hints (graph.cuh): make it this
+        // kernel's {d, stamp, e, eadd}
+        for (uint32_t v = lo + tid; v <= hi; v += THREADS) {
+            const int32_t dm = G.dem[v];
+            *reinterpret_cast<uint4*>(&G.node[v]) =
+                make_uint4(kLabelInf, 0u, (uint32_t)(dm < 0 ? -dm : 0), 0u);
+        }
+        __syncthreads();
         unsigned long long my_pushes = 0, my_relabels = 0;
         long long my_sink = 0, my_stuck = 0;
         // Components whose nodes are mostly "heavy" (variable read lengths: tens of bundles per
@@ -778,6 +791,7 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
             cs.cyc_gr_bfs = (unsigned long long)tparts[1];
             cs.cyc_gr_snap = (unsigned long long)tparts[2];
             cs.cyc_front = (unsigned long long)cyc_front;
+            cs.cyc_gr_later = 0;
             stats[c] = cs;
         }
         __syncthreads();

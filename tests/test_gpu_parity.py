@@ -473,3 +473,92 @@ def test_compact_transport_start16_and_implied_end(pkg, solver, O):
         ch.close()
     assert sum(int(x.n_kept) for x in rs) == r5.n_kept
     assert np.array_equal(bm[:len(s5) // 32].cpu().numpy().view(np.uint32), r5.kept_bitmap)
+
+
+def test_c5_shape_batch_parity(solver, O):
+    # BASELINE config 5 at its real per-sample shape: 8 samples x 2 M reads / 30 kb / M=100, seeds
+    # 12345+k (what bench.py's default workload runs 512 of), one gds_solve, bit-exact against the
+    # oracle's replay; every sample's slice equals its stand-alone solve
+    ns, pairs = 8, 1_000_000
+    parts = [O.gen_reads(12345 + k, pairs, 30_000, 150) for k in range(ns)]
+    s = np.concatenate([p[0] for p in parts]); e = np.concatenate([p[1] for p in parts])
+    off = np.arange(ns + 1, dtype=np.uint64) * (2 * pairs)
+    r = solver.solve(s, e, [30_000] * ns, 100, read_off=off, params=PRM, verify=True,
+                     want_vectors=True, len_hint=(150, 150))
+    assert r.n_components == ns and r.fstar == 100 * ns and r.bundle_path == 1
+    assert_parity(O, r, s, e, [30_000] * ns, off, 100)
+    mask = O.bitmap_to_mask(r.kept_bitmap, len(s))
+    for k in (0, 5, 7):
+        rk = solver.solve(parts[k][0], parts[k][1], 30_000, 100, params=PRM)
+        lo = k * 2 * pairs
+        assert np.array_equal(O.bitmap_to_mask(rk.kept_bitmap, 2 * pairs), mask[lo:lo + 2 * pairs])
+    # the compact transport bench.py's e2e leg uses (16-bit starts, implied ends): same bits
+    rc = solver.solve(s.astype(np.uint16), None, [30_000] * ns, 100, read_off=off, params=PRM,
+                      len_hint=(150, 150))
+    assert np.array_equal(rc.kept_bitmap, r.kept_bitmap)
+
+
+def _solve_with_env(solver, env, *a, **kw):
+    import os
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        return solver.solve(*a, **kw)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                del os.environ[k]
+            else:
+                os.environ[k] = v
+
+
+COUNTERS = ("fstar", "flow_value", "n_bundles", "n_components", "n_kept", "rounds_total", "pushes",
+            "relabels", "bfs_levels", "global_relabels", "max_frontier")
+
+
+def test_maxflow_kernels_agree(solver, O):
+    # K3 exists twice: state in shared memory (maxflow_sm.cuh, default) and state in global memory
+    # (maxflow.cuh: GDS_MF=global, and the fallback for components the first cannot take).  Same
+    # deterministic schedule: every counter and the bitmap must be identical, and equal the oracle.
+    cases = []
+    s, e, _, _ = O.gen_reads(31, 150_000, 30_000, 150, "hole")
+    cases.append((s, e, [30_000], np.array([0, len(s)], np.uint64), 3000, PRM))
+    rng = np.random.default_rng(17)
+    s2 = rng.integers(0, 29_000, size=300_000).astype(np.uint32)
+    e2 = (s2 + rng.integers(60, 200, size=300_000)).astype(np.uint32)  # heavy nodes: warp mode
+    cases.append((s2, e2, [30_000], np.array([0, len(s2)], np.uint64), 80, PRM))
+    s3, e3, _, _ = O.gen_reads(32, 200_000, 120_000, 150)  # 8 kb segments: many small components
+    cases.append((s3, e3, [120_000], np.array([0, len(s3)], np.uint64), 60, (16, 50, 1, 0, 8192)))
+    for s, e, Ls, off, M, prm in cases:
+        a = solver.solve(s, e, Ls, M, read_off=off, params=prm, verify=True, want_vectors=True)
+        b = _solve_with_env(solver, {"GDS_MF": "global"}, s, e, Ls, M, read_off=off, params=prm,
+                            verify=True)
+        c = _solve_with_env(solver, {"GDS_MF_OPTR": "0"}, s, e, Ls, M, read_off=off, params=prm)
+        for key in COUNTERS:
+            assert a[key] == b[key] == c[key], key
+        assert np.array_equal(a.kept_bitmap, b.kept_bitmap)
+        assert np.array_equal(a.kept_bitmap, c.kept_bitmap)
+        assert_parity(O, a, s, e, Ls, off, M, prm)
+
+
+def test_maxflow_fallback_list(solver, O):
+    # components the shared-memory kernel cannot take go to k_maxflow through a device-side list:
+    # (a) supply beyond 16 bits (M above the coverage: every rise of the coverage is a source);
+    # (b) a component too long for one SM next to ones that fit
+    s, e, _, _ = O.gen_reads(41, 1_000_000, 30_000, 150)
+    sa, ea, _, _ = O.gen_reads(42, 100_000, 30_000, 150)
+    sb = np.concatenate([s, sa]); eb = np.concatenate([e, ea])
+    off = np.array([0, len(s), len(sb)], np.uint64)
+    r = solver.solve(sb, eb, [30_000, 30_000], 100_000, read_off=off, params=PRM, verify=True,
+                     want_vectors=True)
+    assert r.fstar > 65535 and r.n_kept == len(sb)  # M above every coverage: everything is kept
+    assert_parity(O, r, sb, eb, [30_000, 30_000], off, 100_000)
+    s2, e2, _, _ = O.gen_reads(43, 150_000, 90_000, 150)
+    s3, e3, _, _ = O.gen_reads(44, 50_000, 20_000, 150)
+    sc = np.concatenate([s2, s3]); ec = np.concatenate([e2, e3])
+    offc = np.array([0, len(s2), len(sc)], np.uint64)
+    prm = (64, 150, 1, 0, 0xffffffff)  # no segmentation: a 90 001-node component
+    r2 = solver.solve(sc, ec, [90_000, 20_000], 30, read_off=offc, params=prm, verify=True,
+                      want_vectors=True)
+    assert r2.n_components == 2
+    assert_parity(O, r2, sc, ec, [90_000, 20_000], offc, 30, prm)
