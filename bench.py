@@ -58,11 +58,29 @@ WORKLOADS = {
                name="config[0]: 1M reads over a 30 kb reference (reads-gen uniform, seed 12345, "
                     "R=150), MAX_COVERAGE=100"),
 }
+# the reference's own random test cases (src/tests/coverage_tester.cpp:120-175): 2 M reads over 30 kb,
+# M = 1000 (uniform law) or 8000 (three density shapes) — thousands of sources and sinks, F* = 12-30 k
+for _name, _shape, _m in (("ref_uniform", "uniform", 1000), ("ref_low_sides", "low_sides", 8000),
+                          ("ref_hole", "hole", 8000), ("ref_zero_sides", "zero_sides", 8000)):
+    WORKLOADS[_name] = dict(L=30_000, R=150, pairs=1_000_000, M=_m, samples=1, seed=12345, shape=_shape,
+                            name="reference test case %s (coverage_tester.cpp:120-175): 2M reads over "
+                                 "30 kb, reads-gen law '%s', seed 12345, R=150, MAX_COVERAGE=%d"
+                                 % (_name, _shape, _m))
 METRIC = "reads/sec downsampled (device-timed)"
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def config_for(wname, wl):
+    """The workload both arms run — the SAME dict in the B200 line and in the --impl reference line
+    (how many samples of it an arm takes per step is the arm's business: config['...'] never holds
+    it; see 'shard' / cpu_baseline.sample)."""
+    return {"workload": wname + " — " + wl["name"], "samples": wl["samples"],
+            "reads_per_sample": 2 * wl["pairs"], "ref_len": wl["L"], "read_len": wl["R"],
+            "max_coverage": wl["M"], "seed": wl["seed"],
+            "pair_filter": wl.get("filter"), "law": wl.get("shape", "uniform")}
 
 
 def host_threads():
@@ -214,6 +232,12 @@ def generate(wl, sample_ids, pinned):
                                         p_inside=wl["p_inside"], min_len=wl["min_len"],
                                         max_len=wl["R"])
         return st, en, pin, dict(mapq=mq, seq_len=sl, amp_start=a0, amp_end=a1)
+    if wl.get("shape", "uniform") != "uniform":
+        for j, k in enumerate(sample_ids):
+            hostlib.gen_reads_into(wl["seed"] + k, wl["pairs"], wl["L"], wl["R"],
+                                   s_np[j * n_per:(j + 1) * n_per], e_np[j * n_per:(j + 1) * n_per],
+                                   shape=wl["shape"])
+        return st, en, pin, None
     hostlib.gen_batch([wl["seed"] + k for k in sample_ids], wl["pairs"], wl["L"], wl["R"], s_np,
                       e_np, threads=host_threads())
     return st, en, pin, None
@@ -236,7 +260,7 @@ def cpu_make_input(O, wl, k, pairs, L):
         s, e, q, l = O.gen_reads_amplicon(wl["seed"] + k, pairs, L, a0, a1, wl["p_inside"],
                                           wl["min_len"], wl["R"])
         return (s, e, q, l, a0, a1)
-    return O.gen_reads(wl["seed"] + k, pairs, L, wl["R"])[:2]
+    return O.gen_reads(wl["seed"] + k, pairs, L, wl["R"], wl.get("shape", "uniform"))[:2]
 
 
 def cpu_solve_one(O, wl, inp, L):
@@ -285,7 +309,7 @@ def run_reference(args, wl, wname):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": {"workload": wname + " — " + wl["name"], "sample": sample},
+        "config": config_for(wname, wl),
         "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0,
@@ -367,8 +391,18 @@ def run_b200(args, wl, wname):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    S = args.samples if args.samples else wl["samples"]
-    sample_ids = list(range(rank * S, (rank + 1) * S))   # weak scaling: S samples per rank
+    # Default = the stated batch (BASELINE config[4]: ONE batch of 512 samples) sharded over the
+    # ranks with sharding.shard_samples — strong scaling.  --weak: every rank gets the whole
+    # workload's sample count (different seeds).  Single-sample workloads cannot be sharded
+    # (DESIGN.md §7): N > 1 runs independent replicas with different seeds ("weak").
+    S_total = args.samples if args.samples else wl["samples"]
+    shardable = S_total >= world and S_total % world == 0 and S_total > 1
+    strong = shardable and not args.weak
+    if strong:
+        sample_ids = sharding.shard_samples(S_total, world, rank)
+    else:
+        sample_ids = list(range(rank * S_total, (rank + 1) * S_total))
+    S = len(sample_ids)
     n_per = 2 * wl["pairs"]
     n = n_per * S
     t0 = time.time()
@@ -402,19 +436,23 @@ def run_b200(args, wl, wname):
                         pair_pass_ptr=pair_pass.data_ptr())
         bitmap = torch.zeros(words + 4, dtype=torch.int32, device=dev)
         h_bitmap = torch.empty(words, dtype=torch.int32, pin_memory=True)
-        # N > 1: every step ends with an NCCL all-gather of the ranks' kept bitmaps.  Two bitmap /
-        # gather buffers alternate so that the gather of step i (NCCL's own stream) runs under the
+        h_gathered = torch.empty((world, words), dtype=torch.int32, pin_memory=True) \
+            if world > 1 and rank == 0 else None
+        # N > 1: every step ends with an NCCL gather of the ranks' kept bitmaps ON RANK 0 (grouped
+        # send/recv: the other ranks receive nothing — sharding.gather_bitmaps_to_root).  Two bitmap
+        # / gather buffers alternate so that the gather of step i (NCCL's own stream) runs under the
         # kernels of step i+1; the timed region ends only when the last gather has landed.
         gathered = bitmaps2 = None
         pending = [None, None]
         step_no = [0]
         if world > 1:
-            gathered = [torch.empty(world * words, dtype=torch.int32, device=dev) for _ in range(2)]
+            gathered = [torch.empty((world, words), dtype=torch.int32, device=dev) if rank == 0
+                        else None for _ in range(2)]
             bitmaps2 = [bitmap, torch.zeros(words + 4, dtype=torch.int32, device=dev)]
 
         def gather_async(buf_idx):
-            pending[buf_idx] = dist.all_gather_into_tensor(gathered[buf_idx],
-                                                           bitmaps2[buf_idx][:words], async_op=True)
+            _, pending[buf_idx] = sharding.gather_bitmaps_to_root(
+                bitmaps2[buf_idx][:words].view(1, words), out=gathered[buf_idx], dst=0, async_op=True)
 
         def gather_wait(buf_idx=None):
             for i in ([buf_idx] if buf_idx is not None else [0, 1]):
@@ -440,48 +478,66 @@ def run_b200(args, wl, wname):
                 gather_async(b)
             return r
 
-        # e2e: host buffers in, kept bitmap back on the host.  A batch of many samples goes through
-        # the package's chunked host API (two contexts: H2D of chunk c+1 overlaps kernels of chunk c)
+        # e2e: HOST buffers in (the 32-bit SoA columns the C ABI defines, pinned), kept bitmap back on
+        # the host, everything inside the timed region — including, for the headline figure, the
+        # narrowing to the compact transport (include/gds.h gds_reads.start16 / end == NULL: 16-bit
+        # starts, ends implied by the one read length; 2 bytes per read cross PCIe instead of 8).
+        # Round 1 prepared that column outside the timed region; now the chunk workers do it
+        # (hostlib.encode_compact, what the C++ adapter's narrowing loop does) right before a chunk
+        # is sent.  "e2e_u32" is the same call with the 32-bit columns sent as they are, and
+        # "e2e_preencoded" the round-1 figure (a producer that writes 16-bit starts itself).
+        # A batch of many samples goes through the package's chunked host API (two contexts: H2D of
+        # chunk c+1 overlaps kernels of chunk c).
         chunked = pkg.ChunkedSolver(local_rank) if S >= 2 * args.chunk_samples else None
-        # compact transport (include/gds.h gds_reads.start16 / end == NULL), as the C++ adapter
-        # chooses it: fixed-length reads imply the end column, a reference of <= 65536 positions
-        # fits 16-bit starts -> 2 bytes per read cross PCIe instead of 8
-        h_st16 = None
-        if hint is not None and hint[0] == hint[1] and not args.e2e_u32:
-            if wl["L"] <= 65536:
-                h_st16 = torch.empty(n, dtype=torch.int16, pin_memory=True)
-                h_st16.numpy().view(np.uint16)[:] = h_st.numpy().view(np.uint32)
-                e2e_in = dict(start_ptr=None, end_ptr=None, start16_ptr=h_st16.data_ptr())
-                e2e_bytes, e2e_enc = 2 * n, "start u16, end implied by the fixed read length"
-            else:
-                e2e_in = dict(start_ptr=h_st.data_ptr(), end_ptr=None, start16_ptr=None)
-                e2e_bytes, e2e_enc = 4 * n, "start u32, end implied by the fixed read length"
-        else:
-            e2e_in = dict(start_ptr=h_st.data_ptr(), end_ptr=h_en.data_ptr(), start16_ptr=None)
-            e2e_bytes, e2e_enc = (13 if fx is not None else 8) * n, "start u32, end u32" + (
-                ", mapq u8, seq_len u32" if fx is not None else "")
+        compact_ok = hint is not None and hint[0] == hint[1] and wl["L"] <= 65536
+        h_st16 = torch.empty(n, dtype=torch.int16, pin_memory=True) if compact_ok else None
+        n_extra = (5 if fx is not None else 0) * n
+        enc_threads = max(2, host_threads() // (2 * max(1, min(world, 8))))
 
-        def step_e2e():
-            if chunked is not None:
-                rs = chunked.solve_host_batch(e2e_in["start_ptr"], e2e_in["end_ptr"], read_off,
-                                              ref_len, wl["M"], bitmap.data_ptr(),
-                                              chunk_samples=args.chunk_samples, len_hint=hint,
-                                              start16_ptr=e2e_in["start16_ptr"])
-                r = rs[-1]
-                r["kernel_launches"] = sum(int(x.kernel_launches) for x in rs)
-            else:
-                r = solver.solve_device(e2e_in["start_ptr"], e2e_in["end_ptr"], n, ref_len, wl["M"],
-                                        bitmap.data_ptr(), read_off=read_off,
-                                        input_on_device=False, len_hint=hint,
-                                        start16_ptr=e2e_in["start16_ptr"], **fkw(False))
-                if fx is not None:
-                    h_pair_pass.copy_(pair_pass, non_blocking=True)
-            if world > 1:
-                gather_wait()
-                dist.all_gather_into_tensor(gathered[0], bitmap[:words])
-            h_bitmap.copy_(bitmap[:words], non_blocking=True)
-            stream.synchronize()
-            return r
+        def make_e2e(mode):
+            """mode: 'encode' (u32 columns in, narrowed inside the step), 'u32', 'preencoded'."""
+            def step():
+                if mode == "preencoded":
+                    kw = dict(start_ptr=None, end_ptr=None, start16_ptr=h_st16.data_ptr(), len_hint=hint)
+                else:
+                    kw = dict(start_ptr=h_st.data_ptr(), end_ptr=h_en.data_ptr(), start16_ptr=None,
+                              len_hint=hint if mode == "u32" else None)
+                if chunked is not None:
+                    rs = chunked.solve_host_batch(kw["start_ptr"], kw["end_ptr"], read_off, ref_len,
+                                                  wl["M"], bitmap.data_ptr(),
+                                                  chunk_samples=args.chunk_samples,
+                                                  len_hint=kw["len_hint"], start16_ptr=kw["start16_ptr"],
+                                                  encode16_ptr=h_st16.data_ptr() if mode == "encode" else None,
+                                                  encode_threads=enc_threads)
+                    r = rs[-1]
+                    r["kernel_launches"] = sum(int(x.kernel_launches) for x in rs)
+                else:
+                    if mode == "encode":
+                        from genome_downsampler_b200 import hostlib
+                        fits, lo_, hi_ = hostlib.encode_compact(h_st.data_ptr(), h_en.data_ptr(), n,
+                                                                h_st16.data_ptr(), threads=enc_threads)
+                        if fits and lo_ == hi_:
+                            kw = dict(start_ptr=None, end_ptr=None, start16_ptr=h_st16.data_ptr(),
+                                      len_hint=(lo_, hi_))
+                        else:
+                            kw["len_hint"] = (lo_, hi_)
+                    r = solver.solve_device(kw["start_ptr"], kw["end_ptr"], n, ref_len, wl["M"],
+                                            bitmap.data_ptr(), read_off=read_off,
+                                            input_on_device=False, len_hint=kw["len_hint"],
+                                            start16_ptr=kw["start16_ptr"], **fkw(False))
+                    if fx is not None:
+                        h_pair_pass.copy_(pair_pass, non_blocking=True)
+                if world > 1:
+                    gather_wait()
+                    sharding.gather_bitmaps_to_root(bitmap[:words].view(1, words), out=gathered[0], dst=0)
+                    if rank == 0:  # the root hands the whole batch's bitmaps to the host
+                        h_gathered.copy_(gathered[0], non_blocking=True)
+                else:
+                    h_bitmap.copy_(bitmap[:words], non_blocking=True)
+                stream.synchronize()
+                torch.cuda.current_stream(dev).synchronize()
+                return r
+            return step
 
         def barrier():
             stream.synchronize()
@@ -529,11 +585,60 @@ def run_b200(args, wl, wname):
                 break
             log("clock record shows %s — measuring once more" % sorted(clk.reasons))
         prof = solver.kernel_profile()
-        ms_e2e, _, _, clk2 = timed(step_e2e)
+        e2e_runs = {}
+        if compact_ok:
+            h_st16.zero_()
+            e2e_runs["encode"] = timed(make_e2e("encode"))
+            enc_check = h_st16.numpy().view(np.uint16)[:min(n, 1 << 20)].astype(np.uint32)
+            assert np.array_equal(enc_check, h_st.numpy().view(np.uint32)[:len(enc_check)])
+        e2e_runs["u32"] = timed(make_e2e("u32"))
+        if compact_ok:
+            e2e_runs["preencoded"] = timed(make_e2e("preencoded"))
+        head = "encode" if compact_ok and e2e_runs["encode"][0] <= e2e_runs["u32"][0] else "u32"
+        ms_e2e, _, _, clk2 = e2e_runs[head]
+        # correctness of the e2e path's own output: the bitmap the host received equals the device one
+        if world == 1:
+            assert torch.equal(h_bitmap, bitmap[:words].cpu()), "e2e bitmap differs"
 
+    # quality of the answer, outside every timed region: kept reads of sample 0 against
+    # a lower bound on ANY valid answer — every kept read covers at most R positions, so at least
+    # ceil(sum_i min(cov_i, M) / R) reads are needed (for the uniform law the bound is the optimum
+    # up to a few reads).  Segmented references (config 4) pay at most M reads per cut on top.
+    quality = None
+    if fx is None:
+        with torch.cuda.stream(stream):
+            s0 = d_st[:n_per].long()
+            e0_ = d_en[:n_per].long()
+            dcov = torch.zeros(wl["L"] + 2, dtype=torch.int64, device=dev)
+            dcov.scatter_add_(0, s0, torch.ones_like(s0))
+            dcov.scatter_add_(0, e0_ + 1, -torch.ones_like(e0_))
+            need = int(torch.clamp(torch.cumsum(dcov[:wl["L"]], 0), max=wl["M"]).sum().item())
+            bits0 = bitmap[:n_per // 32].view(torch.uint8)
+            kept0 = int(torch.tensor([bin(i).count("1") for i in range(256)], device=dev)[bits0.long()]
+                        .sum().item())
+        lb = -(-need // wl["R"])
+        quality = {"sample": 0, "n_kept": kept0, "lower_bound": lb,
+                   "kept_over_lower_bound": round(kept0 / max(lb, 1), 5)}
     total_reads = n * world
     value = total_reads * args.steps / (ms_dev * 1e-3)
     e2e_value = total_reads * args.steps / (ms_e2e * 1e-3)
+
+    def e2e_entry(mode):
+        ms = e2e_runs[mode][0]
+        compact = mode in ("encode", "preencoded")
+        return {"value": total_reads * args.steps / (ms * 1e-3), "unit": "reads/s",
+                "ms_per_step": ms / args.steps,
+                "h2d_bytes_per_step": (2 * n if compact else 8 * n) + n_extra,
+                "d2h_bytes_per_step": 4 * words + (n // 2 if fx is not None else 0),
+                "host_input": "pinned uint32 start/end columns (the C ABI's gds_reads)" + (
+                    " + mapq u8, seq_len u32" if fx is not None else "") if mode != "preencoded"
+                else "pinned uint16 start column written by the producer, ends implied",
+                "transport": "start u16, end implied by the one read length" if compact
+                else "start u32, end u32",
+                "encode_in_timed_region": mode != "preencoded",
+                "pinned": bool(pinned),
+                "api": ("ChunkedSolver.solve_host_batch, %d samples per chunk, 2 contexts"
+                        % args.chunk_samples) if chunked is not None else "Solver.solve_device(host)"}
     peak, peak_src = peaks()
     kernels = []
     for k in sorted(prof, key=lambda k: -k["ms"]):
@@ -573,28 +678,29 @@ def run_b200(args, wl, wname):
     line = {
         "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32",
+        "higher_is_better": True, "scaling": "strong" if strong and world > 1 else "weak",
+        "vs_baseline": None, "dtype": "u32",
         "data": "synthetic (reads-gen uniform law, mt19937 seed %d+k, generated on the host)"
                 % wl["seed"],
-        "config": {"workload": wname + " — " + wl["name"], "samples_per_gpu": S,
-                   "reads_per_gpu": n, "max_coverage": wl["M"], "ref_len": wl["L"],
-                   "l2": "inputs (%.0f MB per GPU) larger than the 126 MB L2; no flush needed"
-                         % (8e-6 * n) if 8 * n > 252e6 else
-                         "inputs fit L2: every step re-reads them after >126 MB of sort traffic",
-                   "parallelism": "samples sharded, %d per rank; NCCL all-gather of bitmaps" % S
-                   if world > 1 else "single GPU"},
-        "e2e": {"value": e2e_value, "unit": "reads/s",
-                "h2d_bytes_per_step": e2e_bytes, "input_encoding": e2e_enc,
-                "d2h_bytes_per_step": 4 * words + (n // 2 if fx is not None else 0), "ms_per_step": ms_e2e / args.steps,
-                "pinned": bool(pinned),
-                "api": ("ChunkedSolver.solve_host_batch, %d samples per chunk, 2 contexts"
-                        % args.chunk_samples) if chunked is not None else "Solver.solve_device(host)"},
+        "config": config_for(wname, wl),
+        "shard": {"samples_total": S * world if not strong else S_total, "samples_per_gpu": S,
+                  "reads_per_gpu": n,
+                  "l2": "inputs (%.0f MB per GPU) larger than the 126 MB L2; no flush needed"
+                        % (8e-6 * n) if 8 * n > 252e6 else
+                        "inputs fit L2: every step re-reads them after >126 MB of other traffic",
+                  "parallelism": ("the batch of %d samples block-partitioned over %d ranks "
+                                  "(sharding.shard_samples), no data-path collective, kept bitmaps "
+                                  "gathered on rank 0 over NCCL (grouped send/recv)" % (S_total, world)
+                                  if strong else "%d samples per rank (independent replicas), kept "
+                                  "bitmaps gathered on rank 0 over NCCL" % S)
+                  if world > 1 else "single GPU"},
+        "e2e": e2e_entry(head),
         "gpu_launches": launches,
         "clocks": clk.summary(), "clocks_e2e": clk2.summary(),
         "roofline": roofline, "kernels": kernels[:12],
         "result": {"fstar": int(r_last.fstar), "flow_value": int(r_last.flow_value),
                    "n_filtered": int(r_last.n_filtered),
-                   "n_kept": int(r_last.n_kept), "n_bundles": int(r_last.n_bundles),
+                   "n_kept": int(r_last.n_kept), "quality": quality, "n_bundles": int(r_last.n_bundles),
                    "n_components": int(r_last.n_components), "rounds_total": int(r_last.rounds_total),
                    "rounds_max": int(r_last.rounds_max), "bfs_levels": int(r_last.bfs_levels),
                    "sort_passes": int(r_last.sort_passes),
@@ -615,6 +721,9 @@ def run_b200(args, wl, wname):
                    "phase_ms": {"graph": r_last.ms_graph, "maxflow": r_last.ms_maxflow,
                                 "select": r_last.ms_select, "total": r_last.ms_total}},
     }
+    for mode in e2e_runs:
+        if mode != head:
+            line["e2e_" + mode] = e2e_entry(mode)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(wl)
         line["reference_cuda_baseline"] = reference_cuda_baseline(wl)
@@ -647,8 +756,9 @@ def main():
     ap.add_argument("--chunk-samples", type=int, default=64,
                     help="samples per chunk of the end-to-end (host buffer) leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-u32", action="store_true",
-                    help="end-to-end leg with 32-bit start/end columns instead of the compact transport")
+    ap.add_argument("--weak", action="store_true",
+                    help="N > 1: every rank takes the workload's full sample count (weak scaling) "
+                         "instead of a share of the one batch (default, strong scaling)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -77,7 +77,7 @@ k_direct_hist(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, Di
         const uint64_t b = min(a + plen, o1);
         const uint32_t L = dl.ref_len[k];
         auto count = [&](uint32_t s, uint32_t e) {
-            if (s > e || e >= L) {
+            if (!read_in_range(s, e, L)) {
                 ++bad_range;
                 return;
             }
@@ -717,7 +717,7 @@ k_gdirect_hist(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, s
     uint32_t bad_range = 0, bad_hint = 0, n_cross = 0;
     gd_for_tile(S, E, n, gl.vl, [&](int, size_t, bool in, const VSample& v, uint32_t s, uint32_t e) {
         if (!in) return;
-        if (s > e || e >= v.L) {
+        if (!read_in_range(s, e, v.L)) {
             ++bad_range;
             return;
         }

@@ -151,7 +151,7 @@ void launch_maxflow(gds_ctx* c, const MfGraph& mg,
                     uint32_t* qF, uint32_t* qT, uint32_t* qN, uint32_t* qH, const SolveParams& sp,
                     CompStats* cstats, unsigned long long alg_bytes, uint32_t max_comp_nodes,
                     const uint32_t* comp_list = nullptr, const uint32_t* comp_list_n = nullptr) {
-    KScope ks(comp_list ? "maxflow_fallback" : "maxflow", alg_bytes, c->stream);
+    KScope ks("maxflow", alg_bytes, c->stream);
     const uint32_t sms = (uint32_t)kNumSMs;
     int shape = 3;
     for (int i = 0; i < 3; ++i)
@@ -192,13 +192,18 @@ void launch_mf2_shape(gds_ctx* c, const Mf2Graph& g, const uint32_t* comp_lo, co
                                              (uint32_t)smem, qcap, fb_list, fb_count, optr ? 1u : 0u);
 }
 
-bool launch_maxflow_sm(gds_ctx* c, const Mf2Graph& g, const uint32_t* comp_lo, const uint32_t* comp_hi,
-                       uint32_t n_comp, uint32_t* wc, uint32_t* qF, uint32_t* qT, uint32_t* qN,
-                       uint32_t* qH, const SolveParams& sp, CompStats* cstats,
-                       unsigned long long alg_bytes, uint32_t max_comp_nodes, uint32_t* fb_list,
-                       uint32_t* fb_count) {
-    if (const char* e = getenv("GDS_MF"))  // =global: the round-1 kernel (state in global memory)
-        if (!strcmp(e, "global")) return false;
+// Whether this call's components go to k_maxflow_sm, and with which launch shape.
+struct Mf2Plan {
+    bool on = false;
+    int smem = 0, per_sm = 1, shape = 1;
+    uint32_t qcap = 0;
+    bool optr = false;
+};
+
+Mf2Plan plan_maxflow_sm(uint32_t n_comp, uint32_t max_comp_nodes) {
+    Mf2Plan pl;
+    const char* env = getenv("GDS_MF");  // =global: the round-1 kernel only; =sm: this one whenever it fits
+    if (env && !strcmp(env, "global")) return pl;
     // shared memory per CTA: header + 4 staged queues + the node arrays of the largest component
     // that should still fit.  Prefer the out-CSR cache unless leaving it out lets all components
     // be resident at once (a batch of segments) where they otherwise would not be.
@@ -206,19 +211,16 @@ bool launch_maxflow_sm(gds_ctx* c, const Mf2Graph& g, const uint32_t* comp_lo, c
         return (long long)kMf2HeaderBytes + 16ll * qcap + mf2_node_bytes(nodes, optr);
     };
     const uint32_t nmax = std::min<uint32_t>(max_comp_nodes, kMf2MaxNodes);
-    if (nmax == 0) return false;
+    if (nmax == 0 || n_comp == 0) return pl;
     uint32_t qcap = 2048;
     bool optr = true;
     if (const char* e = getenv("GDS_MF_OPTR")) optr = e[0] != '0';
     // the queues shrink before the node arrays do
     while (qcap > 256 && need(nmax, optr, qcap) > kMf2MaxSmem) qcap >>= 1;
     if (need(nmax, optr, qcap) > kMf2MaxSmem) optr = false;
-    if (need(nmax, optr, qcap) > kMf2MaxSmem && max_comp_nodes > nmax) return false;
+    if (need(nmax, optr, qcap) > kMf2MaxSmem && max_comp_nodes > nmax) return pl;
     long long smem_ll = need(nmax, optr, qcap);
-    if (smem_ll > kMf2MaxSmem) {
-        // the largest component does not fit; smaller ones may: give the kernel everything
-        smem_ll = kMf2MaxSmem;
-    }
+    if (smem_ll > kMf2MaxSmem) smem_ll = kMf2MaxSmem;  // the largest does not fit; smaller ones may
     // CTAs per SM: by shared memory, and never more than two (128 registers x 256 threads each)
     auto resident = [&](long long bytes) {
         return std::min(2, std::max(1, (int)((228 * 1024) / (bytes + 1024))));
@@ -235,18 +237,12 @@ bool launch_maxflow_sm(gds_ctx* c, const Mf2Graph& g, const uint32_t* comp_lo, c
             per_sm = alt;
         }
     }
-    const int smem = (int)((smem_ll + 15) & ~15ll);
     // One CTA per component with the component's labels next to the SM is a LATENCY design: it wins
     // while (nearly) all components are resident at once.  A batch beyond that (config 5: 512
     // samples of 180 KB each, one per SM, four waves: 3.2 ms) is faster on k_maxflow, whose state
-    // lives in L2/HBM but which runs every component concurrently (1.84 ms).  GDS_MF=sm forces this
-    // kernel for measurements.
-    {
-        const char* e = getenv("GDS_MF");
-        const bool forced = e && !strcmp(e, "sm");
-        if (!forced && (unsigned long long)n_comp * 2 > 3ull * kNumSMs * per_sm) return false;
-    }
-    KScope ks("maxflow", alg_bytes, c->stream);
+    // lives in L2/HBM but which runs every component concurrently (1.84 ms).
+    const bool forced = env && !strcmp(env, "sm");
+    if (!forced && (unsigned long long)n_comp * 2 > 3ull * kNumSMs * per_sm) return pl;
     // 1024 threads would cap the kernel at 64 registers and make it spill: local memory is what this
     // kernel must not touch (maxflow_sm.cuh), so it is a measurement knob only
     int shape = per_sm >= 2 ? 0 : 1;
@@ -256,13 +252,27 @@ bool launch_maxflow_sm(gds_ctx* c, const Mf2Graph& g, const uint32_t* comp_lo, c
         if (!strcmp(e, "1024")) shape = 2;
     }
     if (shape != 0) per_sm = 1;
-    switch (shape) {
-        case 0: launch_mf2_shape<256, 0>(c, g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, smem, qcap, fb_list, fb_count, optr, per_sm); break;
-        case 1: launch_mf2_shape<512, 1>(c, g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, smem, qcap, fb_list, fb_count, optr, per_sm); break;
-        default: launch_mf2_shape<1024, 2>(c, g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, smem, qcap, fb_list, fb_count, optr, per_sm); break;
+    pl.on = true;
+    pl.smem = (int)((smem_ll + 15) & ~15ll);
+    pl.per_sm = per_sm;
+    pl.shape = shape;
+    pl.qcap = qcap;
+    pl.optr = optr;
+    return pl;
+}
+
+void launch_maxflow_sm(gds_ctx* c, const Mf2Plan& pl, const Mf2Graph& g, const uint32_t* comp_lo,
+                       const uint32_t* comp_hi, uint32_t n_comp, uint32_t* wc, uint32_t* qF,
+                       uint32_t* qT, uint32_t* qN, uint32_t* qH, const SolveParams& sp,
+                       CompStats* cstats, unsigned long long alg_bytes, uint32_t* fb_list,
+                       uint32_t* fb_count) {
+    KScope ks("maxflow", alg_bytes, c->stream);
+    switch (pl.shape) {
+        case 0: launch_mf2_shape<256, 0>(c, g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, pl.smem, pl.qcap, fb_list, fb_count, pl.optr, pl.per_sm); break;
+        case 1: launch_mf2_shape<512, 1>(c, g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, pl.smem, pl.qcap, fb_list, fb_count, pl.optr, pl.per_sm); break;
+        default: launch_mf2_shape<1024, 2>(c, g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, pl.smem, pl.qcap, fb_list, fb_count, pl.optr, pl.per_sm); break;
     }
     GDS_KERNEL_CHECK();
-    return true;
 }
 
 template <typename K>
@@ -386,7 +396,9 @@ void build_bundles_direct(gds_ctx* c, const gds_reads* rd, const uint32_t* S, co
     }
     const uint32_t ktot = kbase[ns], n_items = item_off[ns];
     uint32_t* lay_d = c->dlay.get<uint32_t>(lay.size());
-    GDS_CUDA(cudaMemcpy(lay_d, lay.data(), lay.size() * 4, cudaMemcpyHostToDevice));
+    // on the solve's own stream: a copy on the legacy stream is not ordered against it (pageable
+    // sources are staged before the call returns, so the vector may go out of scope)
+    GDS_CUDA(cudaMemcpyAsync(lay_d, lay.data(), lay.size() * 4, cudaMemcpyHostToDevice, st));
     uint32_t* ghist = c->dhist.get<uint32_t>(ktot);
     uint32_t* wc = c->dwork.get<uint32_t>(2);
     GDS_CUDA(cudaMemsetAsync(ghist, 0, (size_t)ktot * 4, st));
@@ -780,6 +792,10 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         if (flt->n_amplicons && (!flt->amp_start || !flt->amp_end))
             return fail(c, GDS_ERR_ARG, "null amplicon table");
     }
+    if (flags & GDS_FIND_PAIRS)  // mates are read 2i and 2i+1 of a sample: a pair must not straddle two
+        for (uint32_t k = 0; k <= ns; ++k)
+            if (rd->read_off[k] & 1)
+                return fail(c, GDS_ERR_ARG, "GDS_FIND_PAIRS needs an even read count per sample (mates adjacent)");
     uint64_t nn64 = 0;
     std::vector<uint32_t> base(ns + 1, 0);  // original node space: sample k owns ref_len[k]+1 nodes
     for (uint32_t k = 0; k < ns; ++k) {
@@ -922,8 +938,8 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
                 }
                 uint32_t* das = c->amp_s.get<uint32_t>(as.size());
                 uint32_t* dae = c->amp_e.get<uint32_t>(ae.size());
-                GDS_CUDA(cudaMemcpy(das, as.data(), as.size() * 4, cudaMemcpyHostToDevice));
-                GDS_CUDA(cudaMemcpy(dae, ae.data(), ae.size() * 4, cudaMemcpyHostToDevice));
+                GDS_CUDA(cudaMemcpyAsync(das, as.data(), as.size() * 4, cudaMemcpyHostToDevice, st));
+                GDS_CUDA(cudaMemcpyAsync(dae, ae.data(), ae.size() * 4, cudaMemcpyHostToDevice, st));
                 fa.amp_start_sorted = das;
                 fa.amp_end_runmax = dae;
             }
@@ -1114,7 +1130,7 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
                     maxvn = std::max(maxvn, rd->ref_len[k] + 1);
                 }
                 uint32_t* toff_d = c->tile_off_d.get<uint32_t>(2 * (ns + 1));
-                GDS_CUDA(cudaMemcpy(toff_d, toff.data(), toff.size() * 4, cudaMemcpyHostToDevice));
+                GDS_CUDA(cudaMemcpyAsync(toff_d, toff.data(), toff.size() * 4, cudaMemcpyHostToDevice, st));
                 tm = TileMap{toff_d, foff_dev, ns, tb[ns], n_items, (uint32_t)kRsTile};
                 tm_small = TileMap{toff_d + ns + 1, foff_dev, ns, ts[ns], n_items,
                                    (uint32_t)kRsTileSmall};
@@ -1227,16 +1243,21 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         GDS_CUDA(cudaEventRecord(c->ev[EV_GRAPH], st));
 
         // ---------------- K3: max flow ----------------
+        // no component is larger than a whole unsegmented sample or one segment
+        uint32_t max_comp_nodes = 0;
+        for (const VSample& v : hvs)
+            max_comp_nodes = std::max(max_comp_nodes, v.nseg == 1 ? v.L + 1 : seg + 1);
+        const bool do_solve = !(flags & GDS_NO_SOLVE);
+        const Mf2Plan mf2 = do_solve ? plan_maxflow_sm(n_comp, max_comp_nodes) : Mf2Plan{};
         uint32_t* in_src = c->in_src.get<uint32_t>((size_t)B + 1);
         if (B) {
             KScope ks("in_src", 24ull * B, st);
             k_in_src<<<div_up(B, 256), 256, 0, st>>>(c->bund.as<BundleRec>(), in_bid, in_ptr, B, in_src,
-                                                     node);
+                                                     mf2.on ? node : nullptr);
             GDS_KERNEL_CHECK();
         }
         MfGraph mg{node, d_snap, c->bund.as<BundleRec>(), in_bid, in_src, dem_v};
         CompStats* cstats = c->comp_stats.get<CompStats>(n_comp + 1);
-        const bool do_solve = !(flags & GDS_NO_SOLVE);
         if (do_solve && n_comp) {
             uint32_t* qF = c->qF.get<uint32_t>(n_nodes);
             uint32_t* qT = c->qT.get<uint32_t>(n_nodes);
@@ -1244,15 +1265,12 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             uint32_t* qH = c->qH.get<uint32_t>(n_nodes);
             uint32_t* wc = c->work_counter.get<uint32_t>(4);  // [0] sm kernel, [1] fallback, [2] list size
             GDS_CUDA(cudaMemsetAsync(wc, 0, 16, st));
-            // no component is larger than a whole unsegmented sample or one segment
-            uint32_t max_comp_nodes = 0;
-            for (const VSample& v : hvs)
-                max_comp_nodes = std::max(max_comp_nodes, v.nseg == 1 ? v.L + 1 : seg + 1);
             const unsigned long long mf_bytes = 36ull * n_nodes + 20ull * B;
-            uint32_t* fb_list = c->fb_list.get<uint32_t>(n_comp + 1);
-            Mf2Graph g2{node, c->bund.as<BundleRec>(), in_bid, in_src, out_ptr, in_ptr, dem_v};
-            if (launch_maxflow_sm(c, g2, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats,
-                                  mf_bytes, max_comp_nodes, fb_list, wc + 2)) {
+            if (mf2.on) {
+                uint32_t* fb_list = c->fb_list.get<uint32_t>(n_comp + 1);
+                Mf2Graph g2{node, c->bund.as<BundleRec>(), in_bid, in_src, out_ptr, in_ptr, dem_v};
+                launch_maxflow_sm(c, mf2, g2, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats,
+                                  mf_bytes, fb_list, wc + 2);
                 // whatever the shared-memory kernel could not take (grid: at most one wave)
                 launch_maxflow(c, mg, comp_lo, comp_hi, std::min<uint32_t>(n_comp, kNumSMs), wc + 1, qF,
                                qT, qN, qH, sp, cstats, 0, max_comp_nodes, fb_list, wc + 2);

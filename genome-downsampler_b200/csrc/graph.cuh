@@ -42,7 +42,7 @@ struct VLayout {
         return v.vbase + js * v.W + v.P + (s - js * seg);
     }
     __device__ __forceinline__ bool crosses(const VSample& v, uint32_t s, uint32_t e) const {
-        return v.nseg > 1 && e / seg > s / seg;
+        return v.nseg > 1 && e + 1u != s && e / seg > s / seg;  // a read of length 0 crosses nothing
     }
     __device__ __forceinline__ uint32_t fake_right(const VSample& v, uint32_t s, uint32_t e) const {
         uint32_t je = e / seg;
@@ -93,7 +93,7 @@ struct ReadKeys {
     __device__ __forceinline__ bool checks() const { return LOCAL && ref_len != nullptr; }
     __device__ __forceinline__ uint32_t check(Raw r, uint32_t group) const {
         const uint32_t len = r.y - r.x + 1;
-        if (r.x > r.y || r.y >= ref_len[group]) return 1u;
+        if (!read_in_range(r.x, r.y, ref_len[group])) return 1u;
         return (len < hint_min || len > hint_max) ? 0x10000u : 0u;
     }
     __device__ __forceinline__ uint32_t* check_stats() const { return stats; }
@@ -271,10 +271,10 @@ k_heads_write(const K* __restrict__ keys, TileMap tm, const uint32_t* __restrict
 // push touches: own node (1 sector, neighbours v-1 / v+1 adjacent) -> bundle (1 load) -> target
 // node (1 sector).  Everything a round decides on comes from these records; d_snap (the label
 // snapshot relabels read) is the only side array.
-// The first 16 bytes are written twice: K2 (k_in_src) leaves {start node, bundle id} of the node's
-// NEAREST in-arc there (0, 0 without in-arcs) for k_maxflow_sm, whose labels and excess live in shared
-// memory; k_maxflow (state in global memory) overwrites them with {d, stamp, e, eadd} when it takes
-// a component.
+// The first 16 bytes have two uses: {d, stamp, e, eadd} for k_maxflow (state in global memory), as
+// k_node_finalize writes them; when k_maxflow_sm runs (labels and excess in shared memory), k_in_src
+// puts {start node, bundle id} of the node's NEAREST in-arc over d and stamp, and k_maxflow restores
+// the four fields for the components it is handed afterwards.
 struct __align__(32) NodeRec {
     uint32_t d;        // label                                      | start node of the nearest in-arc
     uint32_t stamp;    // round in which v is in the frontier        | its bundle id
@@ -387,7 +387,7 @@ k_node_finalize(const uint32_t* __restrict__ excl, const int32_t* __restrict__ d
         uint32_t covR = covL + (uint32_t)diff[v];
         int32_t dem = (int32_t)min(covL, M) - (int32_t)min(covR, M);
         uint4* r = reinterpret_cast<uint4*>(&node[v]);
-        r[0] = make_uint4(0u, 0u, 0u, 0u);  // nearest in-arc: k_in_src
+        r[0] = make_uint4(kLabelInf, 0u, (uint32_t)(dem < 0 ? -dem : 0), 0u);  // d, stamp, e, eadd
         r[1] = make_uint4((uint32_t)(dem > 0 ? dem : 0), 0u, out_ptr[v], in_ptr[v]);  // snk, g, ptrs
         d_snap[v] = kLabelInf;
         dem_v[v] = dem;
@@ -408,13 +408,13 @@ k_node_finalize(const uint32_t* __restrict__ excl, const int32_t* __restrict__ d
 __global__ void __launch_bounds__(256)
 k_in_src(const BundleRec* __restrict__ bund, const uint32_t* __restrict__ in_bid,
          const uint32_t* __restrict__ in_ptr, uint32_t B, uint32_t* __restrict__ in_src,
-         NodeRec* __restrict__ node) {
+         NodeRec* __restrict__ node /* null: k_maxflow only, the records keep {d, stamp, e, eadd} */) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= B) return;
     const uint32_t b = in_bid[k];
     const uint4 r = reinterpret_cast<const uint4*>(bund)[b];  // t, mult, f, s
     in_src[k] = r.w;
-    if (k + 1 == in_ptr[r.x + 1]) *reinterpret_cast<uint2*>(&node[r.x]) = make_uint2(r.w, b);
+    if (node && k + 1 == in_ptr[r.x + 1]) *reinterpret_cast<uint2*>(&node[r.x]) = make_uint2(r.w, b);
 }
 
 // Components are disjoint runs, so starts and ends alternate: the end at v closes the component

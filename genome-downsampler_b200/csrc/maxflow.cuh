@@ -412,14 +412,16 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
         }
         unsigned long long bfs_levels = 0, grs = 1, rounds = 0, max_frontier = 0, frontier_sum = 0;
         const long long t_begin = clock64();
-        // the first half of the node records holds K2's in-arc hints (graph.cuh): make it this
-        // kernel's {d, stamp, e, eadd}
-        for (uint32_t v = lo + tid; v <= hi; v += THREADS) {
-            const int32_t dm = G.dem[v];
-            *reinterpret_cast<uint4*>(&G.node[v]) =
-                make_uint4(kLabelInf, 0u, (uint32_t)(dm < 0 ? -dm : 0), 0u);
+        if (comp_list) {
+            // components k_maxflow_sm left behind: the first half of their node records holds K2's
+            // in-arc hints (graph.cuh); make it this kernel's {d, stamp, e, eadd} again
+            for (uint32_t v = lo + tid; v <= hi; v += THREADS) {
+                const int32_t dm = G.dem[v];
+                *reinterpret_cast<uint4*>(&G.node[v]) =
+                    make_uint4(kLabelInf, 0u, (uint32_t)(dm < 0 ? -dm : 0), 0u);
+            }
+            __syncthreads();
         }
-        __syncthreads();
         unsigned long long my_pushes = 0, my_relabels = 0;
         long long my_sink = 0, my_stuck = 0;
         // Components whose nodes are mostly "heavy" (variable read lengths: tens of bundles per

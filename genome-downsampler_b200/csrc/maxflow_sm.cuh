@@ -507,6 +507,11 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
             C.N = Q2{kMf2HeaderBytes + 8u * qcap, qN_g + lo, qcap};
             C.H = Q2{kMf2HeaderBytes + 12u * qcap, qH_g + lo, qcap};
         }
+        if (!fits || warp_mode) {  // not for this kernel: k_maxflow takes it (see below)
+            if (tid == 0) fb_list[atomicAdd(fb_count, 1u)] = c;
+            __syncthreads();
+            continue;
+        }
         if (fits)  // the three bitmaps (inF, BFS A, BFS B) are contiguous
             for (uint32_t i = lay.o_inF + tid; i < lay.o_optr; i += THREADS) word[i] = 0;
         __syncthreads();
@@ -563,7 +568,7 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
         // k_maxflow takes what does not fit, and the components whose nodes are mostly heavy (variable
         // read lengths, tens of bundles per node): their time is the per-bundle global traffic of the
         // warp passes, which shared-memory labels do not shorten (config 2: 2.6 ms there, 3.4 ms here)
-        if (!fits || warp_mode || sh.supply > 0xffffu) {  // nothing has been written to global memory yet
+        if (sh.supply > 0xffffu) {  // nothing has been written to global memory yet
             if (tid == 0) fb_list[atomicAdd(fb_count, 1u)] = c;
             __syncthreads();
             continue;

@@ -128,6 +128,14 @@ __global__ void k_filter_offsets(const uint64_t* __restrict__ off, uint32_t n_sa
     foff[k] = 2 * cnt;
 }
 
+// A read [s, e] is acceptable when it lies inside the reference, or when it consumes no reference at
+// all (e == s - 1, CIGAR '*': an unmapped mate placed at its mate's position).  The reference keeps
+// such a read (Read::Read gives it end = pos + rlen - 1, read.cpp:5-14): its arc start -> end + 1 is a
+// self-loop that never carries flow, so it is never kept; here it becomes a bundle of length 0.
+__host__ __device__ __forceinline__ bool read_in_range(uint32_t s, uint32_t e, uint32_t L) {
+    return (e + 1u == s) ? s < L : (s <= e && e < L);
+}
+
 // Validation + read-length range over the (post-filter) reads.  stats[0]=min len, [1]=max len,
 // [2]=error count.  One block covers a contiguous chunk of reads; the sample of a read is looked
 // up once per block when the chunk lies inside one sample (the common case).
@@ -164,7 +172,7 @@ k_validate(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, size_
         size_t i = base + (size_t)q * kValThreads + threadIdx.x;
         if (i >= n) continue;
         uint32_t L = one ? L0 : ref_len[find_sample(off, n_samples, i)];
-        if (s[q] > e[q] || e[q] >= L) {
+        if (!read_in_range(s[q], e[q], L)) {
             ++bad;
             continue;
         }

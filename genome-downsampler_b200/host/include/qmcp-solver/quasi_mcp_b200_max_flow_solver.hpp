@@ -6,6 +6,7 @@
 #pragma once
 #include <cstdint>
 #include <memory>
+#include <vector>
 
 #include "gds.h"
 #include "qmcp-solver/solver.hpp"
@@ -19,9 +20,23 @@ class QuasiMcpB200MaxFlowSolver : public Solver {
     std::unique_ptr<Solution> solve(uint32_t max_coverage, bam_api::BamApi& bam_api) override;
     bool uses_quality_of_reads() override { return false; }
 
+    // A batch of independent samples (contigs, runs) in ONE device call: the narrowing loops of all
+    // samples fill one pinned staging area on the host threads, gds_solve gets n_samples = size of
+    // the batch, and every sample's ascending kept indices come back as its own Solution — what
+    // calling solve() on each BamApi in turn returns, minus a device round trip per sample.
+    // BamApis with a pending pair filter are solved one by one through solve().
+    std::vector<std::unique_ptr<Solution>> solve_batch(uint32_t max_coverage,
+                                                       const std::vector<bam_api::BamApi*>& bam_apis);
+
     // last call's device-side report (flow value, kept count, per-phase milliseconds, ...)
     const gds_result& last_result() const { return last_; }
     void set_verify(bool v) { verify_ = v; }
+    // gds_params.seg_len (include/gds.h): references longer than twice this many positions are solved
+    // as independent segments — same F*, demand and capped coverage as the reference's network, at
+    // most max_coverage extra kept reads per cut (+0.5 % at 50 M reads / 5 Mb).  0xffffffff = never cut
+    // (the reference's own network, ~120x slower on a 5 Mb reference); 0 = the library's default.
+    // The environment variable GDS_SEG_LEN sets it for a solver that came out of SolverManager.
+    void set_segment_length(uint32_t positions) { seg_len_ = positions; }
 
    private:
     // grow-only page-locked staging buffer (gds_host_alloc): the narrowing loop writes straight
@@ -47,6 +62,7 @@ class QuasiMcpB200MaxFlowSolver : public Solver {
     gds_ctx* ctx_ = nullptr;  // created lazily, reused across solve() calls
     gds_result last_{};
     bool verify_ = true;
+    uint32_t seg_len_ = 0;
 };
 
 }  // namespace qmcp

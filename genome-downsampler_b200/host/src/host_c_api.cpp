@@ -1,13 +1,18 @@
 // C doorway into the host mirror for Python callers (bench.py, tests): synthetic inputs from
 // reads_gen, and the whole plugin path (BamApi + SolverManager + qmcp::Solver) on plain arrays.
 // Built into libgds_host.so next to libgds_b200.so.
+#include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstring>
+#include <memory>
+#include <thread>
 #include <filesystem>
 #include <random>
 #include <stdexcept>
 #include <vector>
 
+#include "qmcp-solver/quasi_mcp_b200_max_flow_solver.hpp"
 #include "reads_gen.hpp"
 #include "solver_manager.hpp"
 
@@ -76,6 +81,88 @@ int64_t gdsh_plugin_solve(const char* algorithm, uint64_t n, uint32_t genome_len
     std::memcpy(kept_out, sol->data(), k * sizeof(uint64_t));
     return static_cast<int64_t>(sol->size());
 }
+// A batch of samples through the plugin: BamApi objects are built from the arrays (what a caller of
+// the reference API holds), then QuasiMcpB200MaxFlowSolver::solve_batch — the timed part, reported
+// in *solve_seconds — narrows the size_t columns, solves all samples in one device call and expands
+// the per-sample index lists.  kept_counts[k] = number of kept reads of sample k; kept_total
+// indices are written to kept_out sample after sample (cap permitting).  Returns total kept.
+int64_t gdsh_plugin_solve_batch(uint32_t n_samples, const uint64_t* read_off, uint32_t genome_len,
+                                const uint32_t* start, const uint32_t* end, uint32_t max_coverage,
+                                int repeats, double* solve_seconds, uint64_t* kept_counts,
+                                uint64_t* kept_out, uint64_t cap) {
+    static qmcp::QuasiMcpB200MaxFlowSolver solver;
+    std::vector<std::unique_ptr<bam_api::BamApi>> apis;
+    std::vector<bam_api::BamApi*> ptrs;
+    for (uint32_t k = 0; k < n_samples; ++k) {
+        bam_api::SOAPairedReads soa;
+        soa.ref_genome_length = genome_len;
+        const uint64_t b = read_off[k], e = read_off[k + 1];
+        soa.reserve(e - b);
+        for (uint64_t i = b; i < e; ++i)
+            soa.push_back(bam_api::Read(i - b, start[i], end[i], 0, end[i] - start[i] + 1, (i - b) % 2 == 0));
+        apis.push_back(std::make_unique<bam_api::BamApi>(soa));
+        ptrs.push_back(apis.back().get());
+    }
+    std::vector<std::unique_ptr<qmcp::Solution>> sols;
+    double best = 1e30;
+    for (int r = 0; r < (repeats > 0 ? repeats : 1); ++r) {
+        auto t0 = std::chrono::steady_clock::now();
+        sols = solver.solve_batch(max_coverage, ptrs);
+        best = std::min(best, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
+    if (solve_seconds) *solve_seconds = best;
+    uint64_t total = 0;
+    for (uint32_t k = 0; k < n_samples; ++k) {
+        if (kept_counts) kept_counts[k] = sols[k]->size();
+        for (uint64_t v : *sols[k]) {
+            if (kept_out && total < cap) kept_out[total] = v;
+            ++total;
+        }
+    }
+    return static_cast<int64_t>(total);
+}
+
+// The narrowing a caller with 32-bit columns has to do to use the compact transport
+// (include/gds.h gds_reads.start16 / end == NULL): 16-bit starts plus the exact read-length range,
+// on `threads` host threads.  Returns 1 when every start fits 16 bits.
+int gdsh_encode_compact(const uint32_t* start, const uint32_t* end, uint64_t n, uint16_t* start16,
+                        uint32_t* len_min, uint32_t* len_max, uint32_t threads) {
+    const unsigned nt = n < (1u << 18) ? 1u : std::max(1u, std::min(threads, 64u));
+    std::vector<uint32_t> mn(nt, 0xffffffffu), mx(nt, 0);
+    std::vector<int> fits(nt, 1);
+    const uint64_t per = ((n + nt - 1) / nt + 63) & ~uint64_t{63};
+    auto work = [&](unsigned t) {
+        const uint64_t b = std::min<uint64_t>(n, (uint64_t)t * per), e = std::min<uint64_t>(n, b + per);
+        uint32_t lo = 0xffffffffu, hi = 0, big = 0;
+        for (uint64_t i = b; i < e; ++i) {
+            const uint32_t s = start[i], len = end[i] - s + 1;
+            start16[i] = static_cast<uint16_t>(s);
+            big |= s;
+            lo = std::min(lo, len);
+            hi = std::max(hi, len);
+        }
+        mn[t] = lo;
+        mx[t] = hi;
+        fits[t] = big <= 0xffffu;
+    };
+    if (nt == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, t);
+        for (auto& t : th) t.join();
+    }
+    int ok = 1;
+    *len_min = 0xffffffffu;
+    *len_max = 0;
+    for (unsigned t = 0; t < nt; ++t) {
+        *len_min = std::min(*len_min, mn[t]);
+        *len_max = std::max(*len_max, mx[t]);
+        ok &= fits[t];
+    }
+    return ok;
+}
+
 // ---- BAM files: the file-backed BamApi behind a handle ----
 
 int64_t gdsh_write_synthetic_bam(const char* path, uint64_t n, uint32_t genome_len,

@@ -2,7 +2,7 @@
 // src/tests/coverage_tester.cpp): runs the "coverage" tester's five cases against the solvers
 // selected with -a through the qmcp::Solver interface, with LIVE checks (the reference's asserts
 // vanish under NDEBUG), plus a device-filter case (config 2 shape).
-//   gds_host_test [-a quasi-mcp-b200] [-o DIR]
+//   gds_host_test [-a quasi-mcp-b200] [-o DIR] [-b N_SAMPLES]   (-b: solve_batch throughput)
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -12,7 +12,10 @@
 #include <random>
 #include <string>
 
+#include <memory>
+
 #include "logging/log.hpp"
+#include "qmcp-solver/quasi_mcp_b200_max_flow_solver.hpp"
 #include "reads_gen.hpp"
 #include "solver_manager.hpp"
 
@@ -93,11 +96,52 @@ static int run_filter_case(qmcp::Solver& solver) {
     return ok ? 0 : 1;
 }
 
+// A batch of independent samples through QuasiMcpB200MaxFlowSolver::solve_batch (BASELINE config 5
+// shape: 2 M reads over 30 kb each, M = 100): wall time of the call — narrowing of the reference's
+// size_t columns, one device call, per-sample index lists — as reads/s, and each sample's result
+// against solve() on the same BamApi.
+static int run_batch(uint32_t n_samples) {
+    qmcp::QuasiMcpB200MaxFlowSolver solver;
+    std::vector<std::unique_ptr<bam_api::BamApi>> apis;
+    std::vector<bam_api::BamApi*> ptrs;
+    uint64_t reads = 0;
+    for (uint32_t k = 0; k < n_samples; ++k) {
+        std::mt19937 mt(12345 + k);
+        auto aos = reads_gen::rand_reads_uniform(mt, 1'000'000, 30'000, 150);
+        reads += aos.reads.size();
+        apis.push_back(std::make_unique<bam_api::BamApi>(aos));
+        apis.back()->get_paired_reads_soa();  // the AoS -> SoA conversion is the caller's, not the solver's
+        ptrs.push_back(apis.back().get());
+    }
+    double best = 1e30;
+    std::vector<std::unique_ptr<qmcp::Solution>> sols;
+    for (int rep = 0; rep < 3; ++rep) {
+        auto t0 = std::chrono::steady_clock::now();
+        sols = solver.solve_batch(100, ptrs);
+        best = std::min(best, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
+    bool ok = sols.size() == n_samples;
+    for (uint32_t k : {0u, n_samples / 2, n_samples - 1}) {
+        auto one = solver.solve(100, *ptrs[k]);
+        ok = ok && *one == *sols[k];
+    }
+    LOG_WITH_LEVEL(logging::INFO) << "  solve_batch: " << n_samples << " samples, " << reads << " reads in "
+                                  << best * 1e3 << " ms = " << reads / best / 1e9 << " G reads/s (device "
+                                  << solver.last_result().ms_total << " ms)" << (ok ? " PASSED" : " FAILED");
+    std::printf("solve_batch %u samples %.3f ms %.3f Greads/s\n", n_samples, best * 1e3, reads / best / 1e9);
+    return ok ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
     SolverManager manager;
     std::vector<std::string> algs;
     fs::path outdir;
+    uint32_t batch = 0;
     for (int i = 1; i < argc; ++i) {
+        if (!strcmp(argv[i], "-b") && i + 1 < argc) {
+            batch = static_cast<uint32_t>(std::atoi(argv[++i]));
+            continue;
+        }
         if (!strcmp(argv[i], "-a") && i + 1 < argc) algs.push_back(argv[++i]);
         else if (!strcmp(argv[i], "-o") && i + 1 < argc) outdir = argv[++i];
         else if (!strcmp(argv[i], "-v")) SET_LOG_LEVEL(logging::DEBUG);
@@ -134,6 +178,7 @@ int main(int argc, char** argv) {
         for (const auto& c : cases) failures += run_case(manager.get(a), c, outdir);
         failures += run_filter_case(manager.get(a));
     }
+    if (batch) failures += run_batch(batch);
     std::printf("%s\n", failures ? "FAILED" : "ALL PASSED");
     return failures ? 1 : 0;
 }

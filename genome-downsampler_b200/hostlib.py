@@ -30,6 +30,10 @@ def load():
                                         C.c_uint32, C.c_void_p, C.c_uint64]
         L.gdsh_plugin_solve.restype = C.c_int64
         vp, u64, u32 = C.c_void_p, C.c_uint64, C.c_uint32
+        L.gdsh_plugin_solve_batch.argtypes = [u32, vp, u32, vp, vp, u32, C.c_int, vp, vp, vp, u64]
+        L.gdsh_plugin_solve_batch.restype = C.c_int64
+        L.gdsh_encode_compact.argtypes = [vp, vp, u64, vp, vp, vp, u32]
+        L.gdsh_encode_compact.restype = C.c_int
         L.gdsh_write_synthetic_bam.argtypes = [C.c_char_p, u64, u32, vp, vp, vp, vp, C.c_int, u32, u32]
         L.gdsh_write_synthetic_bam.restype = C.c_int64
         L.gdsh_bam_open.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, u32, u32, C.c_int, u32]
@@ -112,6 +116,39 @@ def plugin_solve(algorithm, start, end, genome_len, max_coverage):
     if k < 0:
         raise KeyError("unknown algorithm %r" % algorithm)
     return out[:k]
+
+
+def plugin_solve_batch(start, end, read_off, genome_len, max_coverage, repeats=1, want_indices=True):
+    """QuasiMcpB200MaxFlowSolver::solve_batch on BamApi objects built from the arrays.  Returns
+    (list of per-sample ascending index arrays or None, per-sample kept counts, best seconds of the
+    solve_batch call itself: narrowing + device + index expansion)."""
+    start = np.ascontiguousarray(start, np.uint32)
+    end = np.ascontiguousarray(end, np.uint32)
+    read_off = np.ascontiguousarray(read_off, np.uint64)
+    ns = len(read_off) - 1
+    counts = np.zeros(ns, np.uint64)
+    secs = C.c_double(0)
+    cap = len(start) if want_indices else 0
+    out = np.zeros(max(cap, 1), np.uint64)
+    tot = load().gdsh_plugin_solve_batch(ns, read_off.ctypes.data, genome_len, start.ctypes.data,
+                                         end.ctypes.data, max_coverage, repeats, C.addressof(secs),
+                                         counts.ctypes.data, out.ctypes.data if want_indices else None,
+                                         cap)
+    per = None
+    if want_indices:
+        cuts = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        per = [out[cuts[k]:cuts[k + 1]] for k in range(ns)]
+    assert tot == int(counts.sum())
+    return per, counts, float(secs.value)
+
+
+def encode_compact(start_ptr, end_ptr, n, start16_ptr, threads=16):
+    """u32 start/end columns -> 16-bit starts + exact (len_min, len_max); raw pointers so it can
+    work on slices of pinned buffers.  Returns (fits16, len_min, len_max).  Releases the GIL."""
+    lo, hi = C.c_uint32(0), C.c_uint32(0)
+    ok = load().gdsh_encode_compact(start_ptr, end_ptr, n, start16_ptr, C.addressof(lo),
+                                    C.addressof(hi), threads)
+    return bool(ok), int(lo.value), int(hi.value)
 
 
 # ---- BAM files: the file-backed BamApi (bam_api.cpp:30-42, :359-656) ----

@@ -22,7 +22,7 @@ class ChunkedSolver:
 
     def solve_host_batch(self, start_ptr, end_ptr, read_off, ref_len, max_coverage, bitmap_ptr,
                          chunk_samples=64, params=None, len_hint=None, start16_ptr=None,
-                         input_on_device=False):
+                         input_on_device=False, encode16_ptr=None, encode_threads=8):
         """start_ptr/end_ptr: HOST pointers (pinned for full PCIe speed) of the concatenated reads;
         read_off [ns+1] (every chunk boundary must be a multiple of 32 reads so bitmap slices are
         word-aligned), ref_len [ns]; bitmap_ptr: DEVICE pointer of ceil(n/32) words.
@@ -30,6 +30,11 @@ class ChunkedSolver:
         of start_ptr, end_ptr = None for fixed-length reads (len_hint[0] == len_hint[1]).
         input_on_device=True: the pointers are device pointers (two contexts still overlap one
         chunk's max-flow with the next chunk's streaming kernels).
+        encode16_ptr: a HOST scratch buffer of n uint16 — every chunk's 32-bit columns are narrowed
+        into it by the worker that is about to send the chunk (hostlib.encode_compact: 16-bit
+        starts + exact read-length range) and the chunk travels compact when that is legal (one
+        read length, starts below 65536), as 32-bit columns otherwise: what the C++ adapter does
+        with the reference's size_t columns, for callers that hold uint32 arrays.
         Returns the list of per-chunk results (in chunk order)."""
         read_off = np.ascontiguousarray(read_off, np.uint64)
         ref_len = np.ascontiguousarray(ref_len, np.uint32)
@@ -48,12 +53,22 @@ class ChunkedSolver:
                     a, b = chunks[ci]
                     r0 = int(read_off[a])
                     n = int(read_off[b]) - r0
+                    sp = start_ptr + 4 * r0 if start_ptr else None
+                    ep = end_ptr + 4 * r0 if end_ptr else None
+                    s16 = start16_ptr + 2 * r0 if start16_ptr else None
+                    hint = len_hint
+                    if encode16_ptr and n and int(ref_len[a:b].max()) <= 65536:
+                        from . import hostlib
+                        fits, lo, hi = hostlib.encode_compact(sp, ep, n, encode16_ptr + 2 * r0,
+                                                              threads=encode_threads)
+                        hint = (lo, hi)
+                        if fits and lo == hi:
+                            sp, ep, s16 = None, None, encode16_ptr + 2 * r0
                     results[ci] = sv.solve_device(
-                        start_ptr + 4 * r0 if start_ptr else None,
-                        end_ptr + 4 * r0 if end_ptr else None, n, ref_len[a:b], max_coverage,
+                        sp, ep, n, ref_len[a:b], max_coverage,
                         bitmap_ptr + 4 * (r0 // 32), read_off=read_off[a:b + 1] - np.uint64(r0),
-                        params=params, input_on_device=input_on_device, len_hint=len_hint,
-                        start16_ptr=start16_ptr + 2 * r0 if start16_ptr else None)
+                        params=params, input_on_device=input_on_device, len_hint=hint,
+                        start16_ptr=s16)
             except Exception as ex:  # surfaced to the caller after the join
                 errors.append(ex)
 

@@ -42,7 +42,13 @@ enum {
     GDS_OUTPUT_ON_DEVICE = 1u << 1, /* kept_bitmap/pair_pass/cov/demand are device pointers */
     GDS_VERIFY = 1u << 2,           /* recompute coverage of the kept set on device and compare */
     GDS_FIND_PAIRS = 1u << 3,       /* also OR each kept read's mate into the bitmap
-                                       (BamApi::find_pairs, bam_api.cpp:239-273) */
+                                       (BamApi::find_pairs, bam_api.cpp:239-273).  The mate of read i
+                                       is i ^ 1 inside its sample, so every read_off must be even
+                                       (GDS_ERR_ARG otherwise).  The reference looks at is_first_read
+                                       (id + 1 or id - 1): the same thing whenever the first mate sits
+                                       at the even index, which is how BamApi lays pairs out
+                                       (bam_api.cpp:456-461).  gds_result.n_kept stays the number of
+                                       reads the flow selected, before their mates are added. */
     GDS_NO_SOLVE = 1u << 4,         /* stop after coverage/demand/graph (K1+K2 only) */
     GDS_PROFILE_KERNELS = 1u << 5   /* bracket every kernel with CUDA events (gds_kernel_profile) */
 };

@@ -278,11 +278,19 @@ extern "C" uint64_t orc_filter_pairs(uint64_t n_reads, const uint32_t* start, co
 // un-shifted: cov[j] == b[j+1]), find_input_cover / find_filtered_cover (bam_api.cpp:275-301)
 // and create_demand_function (:75-87).
 // =====================================================================================
+// a read that consumes no reference (end == start - 1, CIGAR '*') is legal: Read::Read gives it
+// end = pos + rlen - 1 (read.cpp:5-14), the coverage loops below never run for it and its arc
+// start -> end + 1 is a self-loop without flow
+static inline bool read_ok(uint32_t s, uint32_t e, uint32_t L) {
+    return (e + 1u == s) ? s < L : (s <= e && e < L);
+}
+
 extern "C" int orc_coverage_ref(uint64_t n, const uint32_t* start, const uint32_t* end, uint32_t L,
                                 uint32_t* cov) {
     std::fill(cov, cov + L, 0u);
     for (uint64_t i = 0; i < n; ++i) {
-        if (end[i] >= L || start[i] > end[i]) return -1;
+        if (!read_ok(start[i], end[i], L)) return -1;
+        if (end[i] + 1u == start[i]) continue;
         for (uint32_t j = start[i]; j <= end[i]; ++j) ++cov[j];
     }
     return 0;
@@ -293,7 +301,8 @@ extern "C" int orc_coverage_subset(uint64_t n, const uint32_t* start, const uint
     std::fill(cov, cov + L, 0u);
     for (uint64_t i = 0; i < n; ++i) {
         if (!kept[i]) continue;
-        if (end[i] >= L || start[i] > end[i]) return -1;
+        if (!read_ok(start[i], end[i], L)) return -1;
+        if (end[i] + 1u == start[i]) continue;
         for (uint32_t j = start[i]; j <= end[i]; ++j) ++cov[j];
     }
     return 0;
@@ -573,7 +582,7 @@ int build_sync_graph(uint32_t n_samples, const uint64_t* read_off, const uint32_
     uint32_t minlen = 0xffffffffu, maxlen = 0;
     for (uint32_t k = 0; k < n_samples; ++k)
         for (uint64_t i = read_off[k]; i < read_off[k + 1]; ++i) {
-            if (end[i] >= ref_len[k] || start[i] > end[i]) return -1;
+            if (!read_ok(start[i], end[i], ref_len[k])) return -1;
             uint32_t len = end[i] - start[i] + 1;
             minlen = std::min(minlen, len);
             maxlen = std::max(maxlen, len);
@@ -614,7 +623,7 @@ int build_sync_graph(uint32_t n_samples, const uint64_t* read_off, const uint32_
                 items.push_back({v.vbase + s, len, (uint32_t)i, k});
                 continue;
             }
-            const uint32_t js = s / seg, je = e / seg;
+            const uint32_t js = s / seg, je = len ? e / seg : js;  // length 0 crosses nothing
             items.push_back({v.vbase + js * v.W + v.P + (s - js * seg), len, (uint32_t)i, k});
             if (je > js) {
                 uint32_t vt = v.vbase + je * v.W + v.P + (e + 1 - je * seg);

@@ -170,7 +170,8 @@ def coverage_fast(start, end, L, kept=None):
         start, end = start[m], end[m]
     d = np.zeros(L + 1, np.int64)
     np.add.at(d, start, 1)
-    np.add.at(d, end.astype(np.int64) + 1, -1)
+    # end + 1 in 32-bit arithmetic: a read of length 0 (end == start - 1) cancels itself, also at 0
+    np.add.at(d, (np.asarray(end, np.uint32) + np.uint32(1)).astype(np.int64), -1)
     return np.cumsum(d[:L]).astype(np.uint32)
 
 

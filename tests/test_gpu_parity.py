@@ -562,3 +562,32 @@ def test_maxflow_fallback_list(solver, O):
                       want_vectors=True)
     assert r2.n_components == 2
     assert_parity(O, r2, sc, ec, [90_000, 20_000], offc, 30, prm)
+
+
+def test_zero_length_reads_are_accepted_and_never_kept(solver, O, pkg):
+    # a read that consumes no reference (end == start - 1: CIGAR '*', an unmapped mate placed at its
+    # mate's position) is legal in the reference (read.cpp:5-14; its arc is a self-loop without
+    # flow).  Every bundle path must take it, cover nothing with it and never keep it.
+    rng = np.random.default_rng(29)
+    s, e, _, _ = O.gen_reads(77, 40_000, 9_000, 150)
+    s = s.copy(); e = e.copy()
+    idx = rng.choice(len(s), size=600, replace=False)
+    e[idx] = s[idx] - np.uint32(1)            # includes wrap-around when a start is 0
+    s[idx[0]] = 0; e[idx[0]] = np.uint32(0xffffffff)
+    for prm in (PRM + (0, 0), PRM + (0, 1), PRM + (0, 2), (64, 150, 1, 0, 2048, 0), (64, 150, 1, 0, 2048, 1)):
+        r = solver.solve(s, e, 9_000, 30, params=prm, verify=True, want_vectors=True)
+        assert_parity(O, r, s, e, [9_000], [0, len(s)], 30, prm[:5])
+        mask = O.bitmap_to_mask(r.kept_bitmap, len(s))
+        assert not mask[idx].any()
+        cov = O.coverage_fast(s, e, 9_000)
+        assert np.array_equal(r.cov_capped[:9_000], np.minimum(cov, 30))
+    # only such reads: nothing to cover, nothing kept
+    z = np.array([5, 7], np.uint32)
+    r = solver.solve(z, z - np.uint32(1), 100, 3, params=PRM, verify=True)
+    assert r.n_kept == 0 and r.fstar == 0
+    # still out of range: a zero-length read at or beyond the end, and end < start - 1
+    with pytest.raises(pkg.GdsError) as ei:
+        solver.solve(np.array([100], np.uint32), np.array([99], np.uint32), 100, 3)
+    assert ei.value.code == 2
+    with pytest.raises(pkg.GdsError):
+        solver.solve(np.array([9], np.uint32), np.array([7], np.uint32), 100, 3)

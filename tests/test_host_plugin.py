@@ -59,6 +59,30 @@ def test_plugin_solve_through_solver_manager(hostlib, O):
 
 
 @pytest.mark.gpu
+def test_plugin_solve_batch_equals_one_by_one(hostlib, O):
+    # QuasiMcpB200MaxFlowSolver::solve_batch: ragged samples (different sizes, shapes and read
+    # lengths, so the batch travels as 32-bit columns) and a fixed-length batch (compact transport);
+    # every sample's index list equals solve() on that sample alone and the oracle's bitmap
+    parts = [O.gen_reads(300 + k, 20_000 + 37 * k, 30_000, 150, sh)
+             for k, sh in enumerate(["uniform", "hole", "uniform", "low_sides", "uniform"])]
+    rng = np.random.default_rng(4)
+    s5 = rng.integers(0, 29_000, size=30_001).astype(np.uint32)   # odd count, variable lengths
+    e5 = (s5 + rng.integers(80, 200, size=30_001)).astype(np.uint32)
+    for extra in ([], [(s5, e5)]):
+        ps = [(p[0], p[1]) for p in parts] + extra
+        s = np.concatenate([p[0] for p in ps]); e = np.concatenate([p[1] for p in ps])
+        off = np.cumsum([0] + [len(p[0]) for p in ps]).astype(np.uint64)
+        per, counts, secs = hostlib.plugin_solve_batch(s, e, off, 30_000, 60, repeats=2)
+        assert secs > 0 and len(per) == len(ps)
+        bm, st = O.sync_solve(s, e, [30_000] * len(ps), off, 60, params=(64, 150, 1, 0))
+        mask = O.bitmap_to_mask(bm, len(s))
+        for k, (sk, ek) in enumerate(ps):
+            one = hostlib.plugin_solve("quasi-mcp-b200", sk, ek, 30_000, 60)
+            assert np.array_equal(per[k], one) and counts[k] == len(one)
+            assert np.array_equal(np.flatnonzero(mask[int(off[k]):int(off[k + 1])]), per[k].astype(np.int64))
+
+
+@pytest.mark.gpu
 def test_reference_coverage_tester_runs_against_the_cuda_path(pkg, solver, R):
     # the reference's OWN CoverageTester::test (src/tests/coverage_tester.cpp:28-43, compiled
     # unmodified into oracle/_ref with live asserts) drives the CUDA solver through a callback:
@@ -81,8 +105,10 @@ def test_host_test_binary_runs_the_five_cases_through_the_plugin(pkg):
     import os
     import subprocess
     exe = os.path.join(os.path.dirname(pkg.lib_path()), "gds_host_test")
-    out = subprocess.run([exe, "-a", "quasi-mcp-b200"], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([exe, "-a", "quasi-mcp-b200", "-b", "4"], capture_output=True, text=True,
+                         timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
+    assert "solve_batch 4 samples" in out.stdout and "ALL PASSED" in out.stdout
 
 
 @pytest.mark.gpu

@@ -49,6 +49,14 @@ def _worker(rank, world, port, out_dir):
     assert sorted(got) == list(range(N_SAMPLES))
     for k in range(N_SAMPLES):
         assert torch.equal(got[k], _fake_bitmap(k, words))
+    # the gather the product uses: only the root receives, blocks arrive in rank order
+    root_out, work = sharding.gather_bitmaps_to_root(local, dst=0, async_op=True)
+    if work is not None:
+        work.wait()
+    if rank == 0:
+        assert root_out.shape == (world * per_rank, words) and torch.equal(root_out, gathered)
+    else:
+        assert root_out is None
     open(os.path.join(out_dir, "ok%d" % rank), "w").write("ok")
     dist.destroy_process_group()
 
