@@ -247,14 +247,21 @@ constexpr int kDmThreads = 512;
 constexpr int kDmCtasPerSm = 3;
 constexpr uint32_t kDmSplit = 3;
 
-// ctl: [0] number of partial bundles, [1] candidate slots handed out, [2] fallback flag
+// ctl: [0] number of partial bundles, [1] candidate slots handed out, [2] flags: the mark and
+// ranking kernels do nothing when any is set — 1 a partial bundle too large for one warp (ordered
+// walk instead), 2 the candidates do not fit cand_cap (the host grows the buffer and repeats the
+// selection), 4 K2 counted bad reads (the call fails; the mark kernels do not re-validate)
 __global__ void __launch_bounds__(256)
 k_direct_classify(const BundleRec* __restrict__ bund, const uint32_t* __restrict__ b_slot, uint32_t B,
                   uint32_t* __restrict__ ghist, uint32_t* __restrict__ kstat,
                   uint32_t* __restrict__ pb_off, uint32_t* __restrict__ pb_f,
-                  uint32_t* __restrict__ pb_fill, uint32_t* __restrict__ ctl, uint32_t max_mult) {
+                  uint32_t* __restrict__ pb_fill, uint32_t* __restrict__ ctl, uint32_t max_mult,
+                  const uint32_t* __restrict__ B_dev /* non-null: bundle count on the device */,
+                  uint32_t cand_cap, const uint32_t* __restrict__ stats) {
     __shared__ uint32_t tot_n, tot_m, base_n, base_m;
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (B_dev) B = *B_dev;
+    if (b == 0 && (stats[2] | stats[3])) atomicOr(&ctl[2], 4u);
     uint32_t mult = 0, f = 0;
     if (b < B) {
         const uint4 r = reinterpret_cast<const uint4*>(bund)[b];  // {t, mult, f, s}
@@ -268,6 +275,7 @@ k_direct_classify(const BundleRec* __restrict__ bund, const uint32_t* __restrict
     if (threadIdx.x == 0 && tot_n) {
         base_n = atomicAdd(&ctl[0], tot_n);
         base_m = atomicAdd(&ctl[1], tot_m);
+        if ((unsigned long long)base_m + tot_m > cand_cap) atomicOr(&ctl[2], 2u);
     }
     __syncthreads();
     if (f == 0) return;
@@ -277,7 +285,7 @@ k_direct_classify(const BundleRec* __restrict__ bund, const uint32_t* __restrict
         code = kPartCode;
         const uint32_t pid = base_n + my_n;
         const uint32_t o = base_m + my_m;
-        if (mult > max_mult) ctl[2] = 1;  // too many candidates for one warp: ordered walk instead
+        if (mult > max_mult) atomicOr(&ctl[2], 1u);  // too many candidates for one warp: ordered walk
         pb_off[pid] = o;
         pb_f[pid] = f;
         pb_fill[pid] = 0;
@@ -523,8 +531,9 @@ k_direct_partial(const uint32_t* __restrict__ pb_off, const uint32_t* __restrict
 // used up.
 __global__ void __launch_bounds__(256)
 k_direct_quota(const BundleRec* __restrict__ bund, const uint32_t* __restrict__ b_slot, uint32_t B,
-               uint32_t* __restrict__ ghist) {
+               uint32_t* __restrict__ ghist, const uint32_t* __restrict__ B_dev) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (B_dev) B = *B_dev;
     if (b < B) ghist[b_slot[b]] = bund[b].f;
 }
 
@@ -802,8 +811,10 @@ k_gdirect_mark(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, s
                GDirectLayout gl, const uint32_t* __restrict__ ghist,
                const uint32_t* __restrict__ kstat, const uint32_t* __restrict__ pb_off,
                uint32_t* __restrict__ pb_fill, uint32_t* __restrict__ cand,
-               uint32_t* __restrict__ bitmap, unsigned long long* __restrict__ totals) {
+               uint32_t* __restrict__ bitmap, unsigned long long* __restrict__ totals,
+               const uint32_t* __restrict__ ctl) {
     __shared__ uint32_t krange[2];
+    if (ctl[2]) return;
     const VLayout& vl = gl.vl;
     const size_t base = (size_t)blockIdx.x * kGdTile;
     if (threadIdx.x == 0) {

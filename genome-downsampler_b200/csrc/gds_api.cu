@@ -121,7 +121,8 @@ void launch_maxflow_shape(gds_ctx* c, const MfGraph& mg,
                           const uint32_t* comp_lo, const uint32_t* comp_hi, uint32_t n_comp,
                           uint32_t* wc, uint32_t* qF, uint32_t* qT, uint32_t* qN, uint32_t* qH,
                           const SolveParams& sp, CompStats* cstats, uint32_t max_comp_nodes,
-                          const uint32_t* comp_list, const uint32_t* comp_list_n) {
+                          const uint32_t* comp_list, const uint32_t* comp_list_n,
+                          const uint32_t* n_comp_dev, MfTotals* mft) {
     constexpr MfShape sh = kMfShapes[I];
     auto kern = k_maxflow<sh.threads, sh.qcap, sh.ctas_per_sm>;
     // 16-bit labels of a whole component in shared memory for the first global relabel, when
@@ -143,13 +144,14 @@ void launch_maxflow_shape(gds_ctx* c, const MfGraph& mg,
     }
     int grid = std::min<uint32_t>(n_comp, (uint32_t)kNumSMs * sh.ctas_per_sm);
     kern<<<grid, sh.threads, smem, c->stream>>>(mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp,
-                                                cstats, lab_cap, comp_list, comp_list_n);
+                                                cstats, lab_cap, comp_list, comp_list_n, n_comp_dev, mft);
 }
 
 void launch_maxflow(gds_ctx* c, const MfGraph& mg,
                     const uint32_t* comp_lo, const uint32_t* comp_hi, uint32_t n_comp, uint32_t* wc,
                     uint32_t* qF, uint32_t* qT, uint32_t* qN, uint32_t* qH, const SolveParams& sp,
                     CompStats* cstats, unsigned long long alg_bytes, uint32_t max_comp_nodes,
+                    const uint32_t* n_comp_dev, MfTotals* mft,
                     const uint32_t* comp_list = nullptr, const uint32_t* comp_list_n = nullptr) {
     KScope ks("maxflow", alg_bytes, c->stream);
     const uint32_t sms = (uint32_t)kNumSMs;
@@ -165,10 +167,10 @@ void launch_maxflow(gds_ctx* c, const MfGraph& mg,
     if (const char* e = getenv("GDS_MF_SMEM_LABELS"))  // =0: labels stay in global memory
         if (e[0] == '0') max_comp_nodes = 0;
     switch (shape) {
-        case 0: launch_maxflow_shape<0>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes, comp_list, comp_list_n); break;
-        case 1: launch_maxflow_shape<1>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes, comp_list, comp_list_n); break;
-        case 2: launch_maxflow_shape<2>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes, comp_list, comp_list_n); break;
-        default: launch_maxflow_shape<3>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes, comp_list, comp_list_n); break;
+        case 0: launch_maxflow_shape<0>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes, comp_list, comp_list_n, n_comp_dev, mft); break;
+        case 1: launch_maxflow_shape<1>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes, comp_list, comp_list_n, n_comp_dev, mft); break;
+        case 2: launch_maxflow_shape<2>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes, comp_list, comp_list_n, n_comp_dev, mft); break;
+        default: launch_maxflow_shape<3>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes, comp_list, comp_list_n, n_comp_dev, mft); break;
     }
     GDS_KERNEL_CHECK();
 }
@@ -181,7 +183,8 @@ template <int THREADS, int SLOT>
 void launch_mf2_shape(gds_ctx* c, const Mf2Graph& g, const uint32_t* comp_lo, const uint32_t* comp_hi,
                       uint32_t n_comp, uint32_t* wc, uint32_t* qF, uint32_t* qT, uint32_t* qN,
                       uint32_t* qH, const SolveParams& sp, CompStats* cstats, int smem, uint32_t qcap,
-                      uint32_t* fb_list, uint32_t* fb_count, bool optr, int ctas_per_sm) {
+                      uint32_t* fb_list, uint32_t* fb_count, bool optr, int ctas_per_sm,
+                      const uint32_t* n_comp_dev, MfTotals* mft) {
     auto kern = k_maxflow_sm<THREADS>;
     if (c->mf2_smem_set[SLOT] < smem) {
         GDS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -189,7 +192,8 @@ void launch_mf2_shape(gds_ctx* c, const Mf2Graph& g, const uint32_t* comp_lo, co
     }
     const int grid = (int)std::min<uint32_t>(n_comp, (uint32_t)(kNumSMs * ctas_per_sm));
     kern<<<grid, THREADS, smem, c->stream>>>(g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats,
-                                             (uint32_t)smem, qcap, fb_list, fb_count, optr ? 1u : 0u);
+                                             (uint32_t)smem, qcap, fb_list, fb_count, optr ? 1u : 0u,
+                                             n_comp_dev, mft);
 }
 
 // Whether this call's components go to k_maxflow_sm, and with which launch shape.
@@ -265,12 +269,12 @@ void launch_maxflow_sm(gds_ctx* c, const Mf2Plan& pl, const Mf2Graph& g, const u
                        const uint32_t* comp_hi, uint32_t n_comp, uint32_t* wc, uint32_t* qF,
                        uint32_t* qT, uint32_t* qN, uint32_t* qH, const SolveParams& sp,
                        CompStats* cstats, unsigned long long alg_bytes, uint32_t* fb_list,
-                       uint32_t* fb_count) {
+                       uint32_t* fb_count, const uint32_t* n_comp_dev, MfTotals* mft) {
     KScope ks("maxflow", alg_bytes, c->stream);
     switch (pl.shape) {
-        case 0: launch_mf2_shape<256, 0>(c, g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, pl.smem, pl.qcap, fb_list, fb_count, pl.optr, pl.per_sm); break;
-        case 1: launch_mf2_shape<512, 1>(c, g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, pl.smem, pl.qcap, fb_list, fb_count, pl.optr, pl.per_sm); break;
-        default: launch_mf2_shape<1024, 2>(c, g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, pl.smem, pl.qcap, fb_list, fb_count, pl.optr, pl.per_sm); break;
+        case 0: launch_mf2_shape<256, 0>(c, g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, pl.smem, pl.qcap, fb_list, fb_count, pl.optr, pl.per_sm, n_comp_dev, mft); break;
+        case 1: launch_mf2_shape<512, 1>(c, g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, pl.smem, pl.qcap, fb_list, fb_count, pl.optr, pl.per_sm, n_comp_dev, mft); break;
+        default: launch_mf2_shape<1024, 2>(c, g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, pl.smem, pl.qcap, fb_list, fb_count, pl.optr, pl.per_sm, n_comp_dev, mft); break;
     }
     GDS_KERNEL_CHECK();
 }
@@ -359,7 +363,15 @@ struct DirectPlan {
     uint32_t* in_bid = nullptr;  // identity in-CSR (single read length), else null
     bool global = false;         // counters in global memory (several lengths / segmented reference)
     GDirectLayout gl{};
+    // lazy: no readback between the kernels — B is an upper bound on the host, the exact count
+    // lives in *B_dev, and input errors are looked at with the final readback
+    bool lazy = false;
+    const uint32_t* B_dev = nullptr;
 };
+
+// slots of the small device array `stats` (uint32 x 64) beyond the validation counters [0..4] and the
+// 64-bit totals at [8..19]: counts that stay on the device in lazy mode, and the K3 totals
+constexpr int kStatB = 20, kStatNComp = 21, kStatCtl = 24, kStatMf = 32, kStatWords = 64;
 
 bool direct_eligible(const gds_reads* rd, uint32_t ns, uint32_t minlen, uint32_t maxlen,
                      const uint32_t* S, const uint32_t* E) {
@@ -432,14 +444,18 @@ void build_bundles_direct(gds_ctx* c, const gds_reads* rd, const uint32_t* S, co
     }
     exclusive_scan_u32(tc, tc, n_tiles + 1, c->scan, st);
     uint32_t B = 0;
-    d2h_sync(c, &B, tc + n_tiles, 1);
-    B_out = B;
-    {
+    if (plan.lazy) {  // the count stays on the device (stats[kStatB]); size everything by its bound
+        GDS_CUDA(cudaMemcpyAsync(stats + kStatB, tc + n_tiles, 4, cudaMemcpyDeviceToDevice, st));
+        plan.B_dev = stats + kStatB;
+        B = (uint32_t)std::min<uint64_t>(ktot, N);
+    } else {
+        d2h_sync(c, &B, tc + n_tiles, 1);
         uint32_t hs[4];
         d2h_sync(c, hs, stats, 4);
         if (hs[2]) throw InputFail{GDS_ERR_RANGE, hs[2], "reads with start > end or end >= ref_len"};
         if (hs[3]) throw InputFail{GDS_ERR_ARG, hs[3], "reads outside the len_min/len_max hints"};
     }
+    B_out = B;
     BundleRec* bund = c->bund.get<BundleRec>(B + 1);
     uint32_t* b_t = c->b_t.get<uint32_t>(B + 1);
     uint32_t* b_slot = c->b_slot.get<uint32_t>(B + 1);
@@ -494,15 +510,20 @@ void build_bundles_gdirect(gds_ctx* c, const uint32_t* S, const uint32_t* E, con
     }
     exclusive_scan_u32(tc, tc, n_tiles + 1, c->scan, st);
     uint32_t B = 0;
-    d2h_sync(c, &B, tc + n_tiles, 1);
-    B_out = B;
-    {
+    if (plan.lazy) {
+        GDS_CUDA(cudaMemcpyAsync(stats + kStatB, tc + n_tiles, 4, cudaMemcpyDeviceToDevice, st));
+        plan.B_dev = stats + kStatB;
+        B = (uint32_t)std::min<uint64_t>(ktot, 2 * (uint64_t)N);  // a read crossing a cut counts twice
+        n_cross_out = 0;  // known with the final readback
+    } else {
+        d2h_sync(c, &B, tc + n_tiles, 1);
         uint32_t hs[5];
         d2h_sync(c, hs, stats, 5);
         if (hs[2]) throw InputFail{GDS_ERR_RANGE, hs[2], "reads with start > end or end >= ref_len"};
         if (hs[3]) throw InputFail{GDS_ERR_ARG, hs[3], "reads outside the len_min/len_max hints"};
         n_cross_out = hs[4];
     }
+    B_out = B;
     BundleRec* bund = c->bund.get<BundleRec>(B + 1);
     uint32_t* b_t = c->b_t.get<uint32_t>(B + 1);
     uint32_t* b_slot = c->b_slot.get<uint32_t>(B + 1);
@@ -530,48 +551,60 @@ void build_bundles_gdirect(gds_ctx* c, const uint32_t* S, const uint32_t* E, con
 // K5 on the direct path (direct.cuh): classify the bundles, mark the reads of saturated bundles in
 // one parallel streaming pass, rank the candidates of partial bundles; the ordered walk is the
 // fallback when the candidates do not fit (or GDS_DIRECT_SELECT=walk asks for it).
+// force_walk: the ordered walk right away (the lazy path's second attempt after ctl flag 1).
+// Lazy mode (dp.lazy): nothing is read back here.  The candidate buffer keeps the size it has
+// (never below N/8 slots); k_direct_classify raises ctl flag 2 when the candidates do not fit and
+// flag 1 for a partial bundle too large for one warp, the mark / ranking kernels then do nothing,
+// and gds_solve — which sees the flags with its one final readback — repeats the selection.
 void direct_select(gds_ctx* c, const DirectPlan& dp, const uint32_t* S, const uint32_t* E,
                    uint32_t ns, size_t N, uint32_t B, uint32_t* bm, unsigned long long* totals,
-                   gds_result* out) {
+                   uint32_t* stats, gds_result* out, bool force_walk, size_t cand_need) {
     cudaStream_t st = c->stream;
     BundleRec* bund = c->bund.as<BundleRec>();
     uint32_t* b_slot = c->b_slot.as<uint32_t>();
     const char* env = getenv("GDS_DIRECT_SELECT");
-    bool walk = !dp.global && env && !strcmp(env, "walk");
+    bool walk = !dp.global && (force_walk || (env && !strcmp(env, "walk")));
+    uint32_t* ctl = c->dctl.get<uint32_t>(4);
+    GDS_CUDA(cudaMemsetAsync(ctl, 0, 16, st));
     if (!walk) {
         uint32_t* kstat = c->kstat.get<uint32_t>(dp.ktot / 16 + 1);
         uint32_t* pb = c->pbund.get<uint32_t>(3 * ((size_t)B + 1));
         uint32_t* fill = pb + 2 * ((size_t)B + 1);
-        uint32_t* ctl = c->dctl.get<uint32_t>(4);
         GDS_CUDA(cudaMemsetAsync(kstat, 0, ((size_t)dp.ktot / 16 + 1) * 4, st));
-        GDS_CUDA(cudaMemsetAsync(ctl, 0, 16, st));
+        // never below N/8 slots: the share of reads in partial bundles varies from call to call
+        // and regrowing the arena is expensive
+        size_t cand_cap = std::max<size_t>({cand_need, N / 8, c->cand.cap / 4, (size_t)1});
+        cand_cap = std::min<size_t>(cand_cap, 0xffffffffu);
+        uint32_t* cand = dp.lazy ? c->cand.get<uint32_t>(cand_cap) : nullptr;
         {
             // a partial bundle beyond kMaxPartialMult reads sends the shared-memory path to the
             // ordered walk; the global path has no walk and lets one warp grind through it
             KScope ks("direct_classify", 20ull * B, st);
-            k_direct_classify<<<div_up(B, 256), 256, 0, st>>>(bund, b_slot, B, dp.ghist, kstat, pb,
-                                                            pb + B + 1, fill, ctl,
-                                                            dp.global ? 0xffffffffu : kMaxPartialMult);
+            k_direct_classify<<<div_up(B, 256), 256, 0, st>>>(
+                bund, b_slot, B, dp.ghist, kstat, pb, pb + B + 1, fill, ctl,
+                dp.global ? 0xffffffffu : kMaxPartialMult, dp.B_dev,
+                dp.lazy ? (uint32_t)cand_cap : 0xffffffffu, stats);
             GDS_KERNEL_CHECK();
         }
-        uint32_t hctl[4];
-        d2h_sync(c, hctl, ctl, 4);  // candidate buffer sized exactly
-        out->partial_bundles = hctl[0];
-        out->partial_candidates = hctl[1];
-        walk = hctl[2] != 0;
+        uint32_t hctl[4] = {1, 0, 0, 0};  // lazy: the ranking kernel is launched unconditionally
+        if (!dp.lazy) {
+            d2h_sync(c, hctl, ctl, 4);  // candidate buffer sized exactly
+            out->partial_bundles = hctl[0];
+            out->partial_candidates = hctl[1];
+            walk = (hctl[2] & 1u) != 0;
+            if (!walk) cand = c->cand.get<uint32_t>(std::max<size_t>((size_t)hctl[1] + 1, N / 8));
+        }
         if (!walk) {
-            // sized from the classification, but never below N/8 slots: the share of reads in
-            // partial bundles varies from call to call and regrowing the arena is expensive
-            uint32_t* cand = c->cand.get<uint32_t>(std::max<size_t>((size_t)hctl[1] + 1, N / 8));
             const unsigned long long per_read = (dp.global || dp.dl.nlen > 1) ? 8 : 4;
             if (dp.global) {
                 KScope ks("gdirect_mark", per_read * N + dp.ktot / 4 + 8ull * N / 32, st);
                 k_gdirect_mark<<<div_up((long long)N, kGdTile), kGdThreads, 0, st>>>(
-                    S, E, N, dp.gl, dp.ghist, kstat, pb, fill, cand, bm, totals);
+                    S, E, N, dp.gl, dp.ghist, kstat, pb, fill, cand, bm, totals, ctl);
                 GDS_KERNEL_CHECK();
             } else {
                 KScope ks("direct_mark", per_read * N + dp.ktot / 4 + 8ull * N / 32, st);
                 uint32_t* wc = c->dwork.as<uint32_t>() + 1;
+                GDS_CUDA(cudaMemsetAsync(wc, 0, 4, st));
                 const int grid = (int)std::min<uint32_t>(
                     dp.n_items * kDmSplit, (uint32_t)kNumSMs * (dp.dl.nlen == 1 ? kDmCtasPerSm : 2));
                 const unsigned smem = kDmQueueBytes + dp.kmax;
@@ -586,18 +619,20 @@ void direct_select(gds_ctx* c, const DirectPlan& dp, const uint32_t* S, const ui
                 GDS_KERNEL_CHECK();
             }
             if (hctl[0]) {
-                KScope ks("direct_partial", 16ull * hctl[0] + 4ull * hctl[1], st);
+                KScope ks("direct_partial", dp.lazy ? 16ull * (N / 64) : 16ull * hctl[0] + 4ull * hctl[1], st);
                 k_direct_partial<<<kNumSMs * 32, 256, 0, st>>>(pb, pb + B + 1, fill, cand, ctl, bm,
                                                               totals);
                 GDS_KERNEL_CHECK();
             }
+            if (dp.lazy)
+                GDS_CUDA(cudaMemcpyAsync(stats + kStatCtl, ctl, 16, cudaMemcpyDeviceToDevice, st));
             return;
         }
     }
     // ordered walk: one CTA per sample, quota per key in shared memory
     {
         KScope ks("direct_quota", 24ull * B, st);
-        k_direct_quota<<<div_up(B, 256), 256, 0, st>>>(bund, b_slot, B, dp.ghist);
+        k_direct_quota<<<div_up(B, 256), 256, 0, st>>>(bund, b_slot, B, dp.ghist, dp.B_dev);
         GDS_KERNEL_CHECK();
     }
     {
@@ -608,6 +643,7 @@ void direct_select(gds_ctx* c, const DirectPlan& dp, const uint32_t* S, const ui
         k_direct_select<<<grid, kDsThreads, dp.kmax * 4, st>>>(S, E, dp.dl, wc, dp.ghist, bm, totals);
         GDS_KERNEL_CHECK();
     }
+    if (dp.lazy) GDS_CUDA(cudaMemcpyAsync(stats + kStatCtl, ctl, 16, cudaMemcpyDeviceToDevice, st));
 }
 
 // 0 = choose, 1 = always the radix sort, 2 = the direct histogram whenever eligible
@@ -903,10 +939,12 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         GDS_CUDA(cudaMemcpyAsync(off_d, rd->read_off, (ns + 1) * 8, cudaMemcpyHostToDevice, st));
         GDS_CUDA(cudaMemcpyAsync(reflen_d, rd->ref_len, ns * 4, cudaMemcpyHostToDevice, st));
         GDS_CUDA(cudaMemcpyAsync(base_d, base.data(), (ns + 1) * 4, cudaMemcpyHostToDevice, st));
-        uint32_t* stats = c->small.get<uint32_t>(32);
+        uint32_t* stats = c->small.get<uint32_t>(kStatWords);
         unsigned long long* totals = reinterpret_cast<unsigned long long*>(stats + 8);
+        MfTotals* mft = reinterpret_cast<MfTotals*>(stats + kStatMf);
+        static_assert(kStatMf * 4 + sizeof(MfTotals) <= kStatWords * 4 && kStatMf % 2 == 0, "stats layout");
         {
-            uint32_t init[32] = {};
+            uint32_t init[kStatWords] = {};
             init[0] = 0xffffffffu;
             memcpy(c->pinned, init, sizeof init);
             GDS_CUDA(cudaMemcpyAsync(stats, c->pinned, sizeof init, cudaMemcpyHostToDevice, st));
@@ -1083,6 +1121,15 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         }
         out->n_arc_items = n_items;
         DirectPlan direct;
+        // Lazy mode: one read length (the in-CSR is the identity, no second sort to size) on a
+        // histogram path, caller-provided length hints (no validation readback): nothing is read
+        // back until the end of the call, so the ~25 launches queue up behind each other instead
+        // of waiting for the host five times.  GDS_SYNC=1 keeps the readbacks (measurements).
+        {
+            const char* e = getenv("GDS_SYNC");
+            direct.lazy = (use_direct || use_gdirect) && fused_validation && minlen == maxlen &&
+                          !use_filter && !(e && e[0] == '1');
+        }
         if (use_direct) {
             build_bundles_direct(c, rd, S, E, foff_dev, foff_host, reflen_d, base_d, ns, N, n_nodes,
                                  minlen, maxlen, stats, direct, B);
@@ -1208,10 +1255,24 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         }
         uint32_t* sidx = c->comp_sidx.get<uint32_t>(n_nodes + 1);
         exclusive_scan_u32(cstart, sidx, n_nodes + 1, c->scan, st);
-        d2h_sync(c, &n_comp, sidx + n_nodes, 1);  // also fences hvs/hcuts uploads
+        const bool lazy = direct.lazy;
+        const uint32_t* n_comp_dev = nullptr;
+        if (lazy) {
+            // the count stays on the device; on the host an ESTIMATE (one component per sample or
+            // segment — zero-coverage gaps add more, empty samples take some away) picks the K3
+            // kernel and the grid, and the arrays are sized by the bound (a component has >= 2 nodes)
+            GDS_CUDA(cudaMemcpyAsync(stats + kStatNComp, sidx + n_nodes, 4, cudaMemcpyDeviceToDevice, st));
+            n_comp_dev = stats + kStatNComp;
+            uint64_t est = 0;
+            for (const VSample& v : hvs) est += v.nseg;
+            n_comp = (uint32_t)std::min<uint64_t>(est, n_nodes / 2 + 1);
+        } else {
+            d2h_sync(c, &n_comp, sidx + n_nodes, 1);  // also fences hvs/hcuts uploads
+        }
         out->n_components = n_comp;
-        uint32_t* comp_lo = c->comp_lo.get<uint32_t>(n_comp + 1);
-        uint32_t* comp_hi = c->comp_hi.get<uint32_t>(n_comp + 1);
+        const uint32_t n_comp_cap = lazy ? n_nodes / 2 + 1 : n_comp;
+        uint32_t* comp_lo = c->comp_lo.get<uint32_t>(n_comp_cap + 1);
+        uint32_t* comp_hi = c->comp_hi.get<uint32_t>(n_comp_cap + 1);
         if (n_comp) {
             {
                 KScope ks("comp_write", 16ull * n_nodes, st);
@@ -1253,11 +1314,14 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         if (B) {
             KScope ks("in_src", 24ull * B, st);
             k_in_src<<<div_up(B, 256), 256, 0, st>>>(c->bund.as<BundleRec>(), in_bid, in_ptr, B, in_src,
-                                                     mf2.on ? node : nullptr);
+                                                     mf2.on ? node : nullptr, direct.B_dev);
             GDS_KERNEL_CHECK();
         }
         MfGraph mg{node, d_snap, c->bund.as<BundleRec>(), in_bid, in_src, dem_v};
-        CompStats* cstats = c->comp_stats.get<CompStats>(n_comp + 1);
+        // per-component records only for the diagnostics dump; gds_result's counters are summed on
+        // the device (MfTotals)
+        const char* dump_comp = getenv("GDS_DUMP_COMP");
+        CompStats* cstats = dump_comp ? c->comp_stats.get<CompStats>(n_comp_cap + 1) : nullptr;
         if (do_solve && n_comp) {
             uint32_t* qF = c->qF.get<uint32_t>(n_nodes);
             uint32_t* qT = c->qT.get<uint32_t>(n_nodes);
@@ -1267,76 +1331,95 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             GDS_CUDA(cudaMemsetAsync(wc, 0, 16, st));
             const unsigned long long mf_bytes = 36ull * n_nodes + 20ull * B;
             if (mf2.on) {
-                uint32_t* fb_list = c->fb_list.get<uint32_t>(n_comp + 1);
+                uint32_t* fb_list = c->fb_list.get<uint32_t>(n_comp_cap + 1);
                 Mf2Graph g2{node, c->bund.as<BundleRec>(), in_bid, in_src, out_ptr, in_ptr, dem_v};
                 launch_maxflow_sm(c, mf2, g2, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats,
-                                  mf_bytes, fb_list, wc + 2);
+                                  mf_bytes, fb_list, wc + 2, n_comp_dev, mft);
                 // whatever the shared-memory kernel could not take (grid: at most one wave)
                 launch_maxflow(c, mg, comp_lo, comp_hi, std::min<uint32_t>(n_comp, kNumSMs), wc + 1, qF,
-                               qT, qN, qH, sp, cstats, 0, max_comp_nodes, fb_list, wc + 2);
+                               qT, qN, qH, sp, cstats, 0, max_comp_nodes, n_comp_dev, mft, fb_list,
+                               wc + 2);
             } else {
                 launch_maxflow(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats,
-                               mf_bytes, max_comp_nodes);
+                               mf_bytes, max_comp_nodes, n_comp_dev, mft);
             }
         }
         GDS_CUDA(cudaEventRecord(c->ev[EV_MAXFLOW], st));
 
-        // ---------------- K5: selection ----------------
+        // ---------------- K5 / K6 / results ----------------
+        // One pass in the normal case.  In lazy mode the selection may have to be repeated once: the
+        // final readback is the first time the host sees that the candidates of the partial bundles
+        // did not fit their buffer (it grows) or that a partial bundle needs the ordered walk.
         const size_t n_words = (N + 31) / 32;
         uint32_t* bm = (out_dev && out->kept_bitmap) ? out->kept_bitmap
                                                      : c->bitmap.get<uint32_t>(n_words + 1);
-        if (do_solve) {
-            GDS_CUDA(cudaMemsetAsync(bm, 0, n_words * 4, st));
-            if (B && direct.on) direct_select(c, direct, S, E, ns, N, B, bm, totals, out);
-            else if (B) {
-                {
+        uint32_t hstat[kStatWords] = {};
+        unsigned long long* htot = reinterpret_cast<unsigned long long*>(hstat + 8);
+        bool force_walk = false;
+        size_t cand_need = 0;
+        for (int attempt = 0;; ++attempt) {
+            if (do_solve) {
+                GDS_CUDA(cudaMemsetAsync(bm, 0, n_words * 4, st));
+                if (attempt) GDS_CUDA(cudaMemsetAsync(totals + 1, 0, 16, st));  // n_kept, violations
+                if (B && direct.on)
+                    direct_select(c, direct, S, E, ns, N, B, bm, totals, stats, out, force_walk, cand_need);
+                else if (B) {
                     KScope ks("select", 8ull * B + 8ull * N / 32, st);
                     k_select<<<div_up(B, 256), 256, 0, st>>>(c->b_first.as<uint32_t>(),
-                                                             c->bund.as<BundleRec>(), sorted_idx, B,
-                    bm, totals);
+                                                             c->bund.as<BundleRec>(), sorted_idx, B, bm,
+                                                             totals);
                     GDS_KERNEL_CHECK();
                 }
             }
-        }
-        GDS_CUDA(cudaEventRecord(c->ev[EV_SELECT], st));
+            if (!attempt) GDS_CUDA(cudaEventRecord(c->ev[EV_SELECT], st));
 
-        // ---------------- K6: verification (before find_pairs widens the set) ----------------
-        if (do_solve && (flags & GDS_VERIFY)) {
-            // original node space: compares with the input coverage (odiff when segmented)
-            int32_t* vdiff = c->vdiff.get<int32_t>((size_t)n_onodes + 1);
-            uint32_t* vexcl = c->vexcl.get<uint32_t>((size_t)n_onodes + 1);
-            GDS_CUDA(cudaMemsetAsync(vdiff, 0, ((size_t)n_onodes + 1) * 4, st));
-            if (n_words) {
-                {
+            // K6: verification (before find_pairs widens the set), on the original node space:
+            // compares with the input coverage (odiff when segmented)
+            if (do_solve && (flags & GDS_VERIFY)) {
+                int32_t* vdiff = c->vdiff.get<int32_t>((size_t)n_onodes + 1);
+                uint32_t* vexcl = c->vexcl.get<uint32_t>((size_t)n_onodes + 1);
+                GDS_CUDA(cudaMemsetAsync(vdiff, 0, ((size_t)n_onodes + 1) * 4, st));
+                if (n_words) {
                     KScope ks("verify_accumulate", 4ull * n_words, st);
                     k_verify_accumulate<<<div_up(n_words, 256), 256, 0, st>>>(bm, S, E, N, foff_dev,
-                    base_d, ns, vdiff);
+                                                                              base_d, ns, vdiff);
+                    GDS_KERNEL_CHECK();
+                }
+                exclusive_scan_u32(reinterpret_cast<const uint32_t*>(vdiff), vexcl,
+                                   (size_t)n_onodes + 1, c->scan, st);
+                {
+                    KScope ks("verify_compare", 16ull * n_onodes, st);
+                    k_verify_compare<<<div_up(n_onodes, 256), 256, 0, st>>>(
+                        vexcl, vdiff, split ? oexcl : excl, split ? odiff : diff, n_onodes,
+                        max_coverage, totals);
                     GDS_KERNEL_CHECK();
                 }
             }
-            exclusive_scan_u32(reinterpret_cast<const uint32_t*>(vdiff), vexcl, (size_t)n_onodes + 1,
-                               c->scan, st);
-            {
-                KScope ks("verify_compare", 16ull * n_onodes, st);
-                k_verify_compare<<<div_up(n_onodes, 256), 256, 0, st>>>(
-                    vexcl, vdiff, split ? oexcl : excl, split ? odiff : diff, n_onodes, max_coverage,
-                    totals);
-                GDS_KERNEL_CHECK();
-            }
-        }
-        if (do_solve && (flags & GDS_FIND_PAIRS) && n_words) {
-            {
+            if (do_solve && (flags & GDS_FIND_PAIRS) && n_words) {
                 KScope ks("find_pairs", 8ull * n_words, st);
                 k_find_pairs<<<div_up(n_words, 256), 256, 0, st>>>(bm, n_words);
                 GDS_KERNEL_CHECK();
             }
-        }
-        GDS_CUDA(cudaEventRecord(c->ev[EV_VERIFY], st));
+            if (!attempt) GDS_CUDA(cudaEventRecord(c->ev[EV_VERIFY], st));
 
-        // ---------------- results ----------------
-        if (do_solve && !out_dev) deliver(c, out->kept_bitmap, bm, n_words, false);
-        unsigned long long htot[6] = {};
-        d2h_sync(c, htot, totals, 6);
+            if (do_solve && !out_dev) deliver(c, out->kept_bitmap, bm, n_words, false);
+            d2h_sync(c, hstat, stats, (size_t)kStatWords);  // THE readback of a lazy call
+            if (!lazy) break;
+            if (hstat[2]) throw InputFail{GDS_ERR_RANGE, hstat[2], "reads with start > end or end >= ref_len"};
+            if (hstat[3]) throw InputFail{GDS_ERR_ARG, hstat[3], "reads outside the len_min/len_max hints"};
+            const uint32_t cflags = do_solve && B && direct.on ? hstat[kStatCtl + 2] : 0;
+            if (attempt || !(cflags & 3u)) break;
+            force_walk = (cflags & 1u) != 0;                  // ordered walk (shared-memory path)
+            cand_need = (size_t)hstat[kStatCtl + 1] + 1;      // or the buffer the candidates need
+        }
+        if (lazy) {
+            out->n_bundles = hstat[kStatB];
+            n_comp = hstat[kStatNComp];
+            out->n_components = n_comp;
+            out->partial_bundles = hstat[kStatCtl];
+            out->partial_candidates = hstat[kStatCtl + 1];
+            if (direct.global) out->n_arc_items = N + hstat[4];
+        }
         // htot[0] = source capacity of the (virtual) network the kernel solved; when references
         // were segmented the closed-form F* of the ORIGINAL network is htot[3] and htot[4] units
         // pass straight through the cut nodes once the segment flows are stitched together
@@ -1345,30 +1428,31 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         out->n_kept = htot[1];
         out->verify_violations = htot[2];
         long long stuck = 0;
-        if (do_solve && n_comp) {
+        if (do_solve) {
+            MfTotals ht;
+            memcpy(&ht, hstat + kStatMf, sizeof ht);
+            out->flow_value = ht.sink_flow;
+            out->rounds_total = ht.rounds_total;
+            out->rounds_max = ht.rounds_max;
+            out->pushes = ht.pushes;
+            out->relabels = ht.relabels;
+            out->global_relabels = ht.grs;
+            out->bfs_levels = ht.bfs_levels;
+            out->max_frontier = ht.max_frontier;
+            stuck = ht.stuck;
+            if (ht.n_solved != n_comp) stuck += 1;  // a component was never taken: cannot happen
+        }
+        if (do_solve && n_comp && dump_comp) {  // diagnostics only
             std::vector<CompStats> hs(n_comp);
             d2h_sync(c, hs.data(), cstats, n_comp);
-            if (const char* dump = getenv("GDS_DUMP_COMP")) {  // diagnostics only
-                if (FILE* fp = fopen(dump, "w")) {
-                    fprintf(fp, "comp rounds pushes relabels grs bfs_levels max_frontier frontier_sum cycles gr_init gr_bfs gr_snap front gr_later\n");
-                    for (uint32_t i = 0; i < n_comp; ++i)
-                        fprintf(fp, "%u %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu\n", i,
-                                hs[i].rounds, hs[i].pushes, hs[i].relabels, hs[i].grs, hs[i].bfs_levels,
-                                hs[i].max_frontier, hs[i].frontier_sum, hs[i].cycles, hs[i].cyc_gr_init,
-                                hs[i].cyc_gr_bfs, hs[i].cyc_gr_snap, hs[i].cyc_front, hs[i].cyc_gr_later);
-                    fclose(fp);
-                }
-            }
-            for (const CompStats& s : hs) {
-                out->flow_value += s.sink_flow;
-                out->rounds_total += s.rounds;
-                out->rounds_max = std::max<uint64_t>(out->rounds_max, s.rounds);
-                out->pushes += s.pushes;
-                out->relabels += s.relabels;
-                out->global_relabels += s.grs;
-                out->bfs_levels += s.bfs_levels;
-                out->max_frontier = std::max<uint64_t>(out->max_frontier, s.max_frontier);
-                stuck += s.stuck;
+            if (FILE* fp = fopen(dump_comp, "w")) {
+                fprintf(fp, "comp rounds pushes relabels grs bfs_levels max_frontier frontier_sum cycles gr_init gr_bfs gr_snap front gr_later\n");
+                for (uint32_t i = 0; i < n_comp; ++i)
+                    fprintf(fp, "%u %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu %llu\n", i,
+                            hs[i].rounds, hs[i].pushes, hs[i].relabels, hs[i].grs, hs[i].bfs_levels,
+                            hs[i].max_frontier, hs[i].frontier_sum, hs[i].cycles, hs[i].cyc_gr_init,
+                            hs[i].cyc_gr_bfs, hs[i].cyc_gr_snap, hs[i].cyc_front, hs[i].cyc_gr_later);
+                fclose(fp);
             }
         }
         GDS_CUDA(cudaEventRecord(c->ev[EV_END], st));

@@ -408,8 +408,10 @@ k_node_finalize(const uint32_t* __restrict__ excl, const int32_t* __restrict__ d
 __global__ void __launch_bounds__(256)
 k_in_src(const BundleRec* __restrict__ bund, const uint32_t* __restrict__ in_bid,
          const uint32_t* __restrict__ in_ptr, uint32_t B, uint32_t* __restrict__ in_src,
-         NodeRec* __restrict__ node /* null: k_maxflow only, the records keep {d, stamp, e, eadd} */) {
+         NodeRec* __restrict__ node /* null: k_maxflow only, the records keep {d, stamp, e, eadd} */,
+         const uint32_t* __restrict__ B_dev /* non-null: the bundle count lives on the device */) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (B_dev) B = *B_dev;
     if (k >= B) return;
     const uint32_t b = in_bid[k];
     const uint4 r = reinterpret_cast<const uint4*>(bund)[b];  // t, mult, f, s

@@ -51,6 +51,30 @@ struct SolveParams {
     uint32_t gr_interval_min, gr_levels_pct, gr_relabel_pct, max_rounds;
 };
 
+// Sums / maxima over the components of one call, accumulated on the device so that the host needs
+// no per-component readback (gds_result's counters come from here).
+struct MfTotals {
+    unsigned long long rounds_total, rounds_max, pushes, relabels, grs, bfs_levels, max_frontier;
+    long long sink_flow, stuck;
+    unsigned long long n_solved;
+};
+__device__ __forceinline__ void mf_totals_add(MfTotals* T, unsigned long long rounds,
+                                              unsigned long long pushes, unsigned long long relabels,
+                                              unsigned long long grs, unsigned long long bfs_levels,
+                                              unsigned long long max_frontier, long long sink_flow,
+                                              long long stuck) {
+    atomicAdd(&T->rounds_total, rounds);
+    atomicMax(&T->rounds_max, rounds);
+    atomicAdd(&T->pushes, pushes);
+    atomicAdd(&T->relabels, relabels);
+    atomicAdd(&T->grs, grs);
+    atomicAdd(&T->bfs_levels, bfs_levels);
+    atomicMax(&T->max_frontier, max_frontier);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&T->sink_flow), (unsigned long long)sink_flow);
+    atomicAdd(reinterpret_cast<unsigned long long*>(&T->stuck), (unsigned long long)stuck);
+    atomicAdd(&T->n_solved, 1ull);
+}
+
 struct CompStats {
     unsigned long long rounds, pushes, relabels, grs, bfs_levels, max_frontier;
     long long sink_flow, stuck;
@@ -385,11 +409,14 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
           uint32_t* qH_g, SolveParams P, CompStats* __restrict__ stats,
           uint32_t lab_cap /* nodes the shared-memory label array behind MfShared holds (0: none) */,
           const uint32_t* __restrict__ comp_list /* null: all components; else the ids to solve */,
-          const uint32_t* __restrict__ comp_list_n) {
+          const uint32_t* __restrict__ comp_list_n,
+          const uint32_t* __restrict__ n_comp_dev /* non-null: the component count lives on the device */,
+          MfTotals* __restrict__ totals) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MfShared<QCAP>& sh = *reinterpret_cast<MfShared<QCAP>*>(smem_raw);
     uint16_t* lab_base = reinterpret_cast<uint16_t*>(smem_raw + sizeof(MfShared<QCAP>));
     const uint32_t tid = threadIdx.x;
+    if (n_comp_dev) n_comp = *n_comp_dev;
     if (comp_list) n_comp = *comp_list_n;  // the components k_maxflow_sm left for this kernel
 
     for (;;) {
@@ -777,7 +804,9 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
             atomicAdd((unsigned long long*)&sh.stuck, (unsigned long long)my_stuck);
         }
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 0) mf_totals_add(totals, rounds, sh.pushes, sh.relabels, grs, bfs_levels, max_frontier,
+                                    sh.sink_flow, sh.stuck);
+        if (tid == 0 && stats) {  // per-component records: diagnostics only (GDS_DUMP_COMP)
             CompStats cs;
             cs.rounds = rounds;
             cs.pushes = sh.pushes;

@@ -79,6 +79,13 @@ __device__ __forceinline__ uint32_t g_ld(const void* p) {
     asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Load that nobody waits for: brings the 32-byte sector into this SM's L1 so that the round that
+// needs it finds it there (an L1 hit is ~40 clocks, a trip to L2 ~800 on this part — tools/lat_probe.cu;
+// only this CTA writes the sectors it touches, and its stores update the L1 copy).
+__device__ __forceinline__ void g_touch(const void* p) {
+    uint32_t dummy;
+    asm volatile("ld.global.u32 %0, [%1];" : "=r"(dummy) : "l"(p));
+}
 __device__ __forceinline__ void g_st(void* p, uint32_t v) {
     asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -148,11 +155,27 @@ constexpr uint32_t kMf2HeaderBytes = (sizeof(Mf2Shared) + 15u) & ~15u;
 
 __device__ __forceinline__ uint32_t mf2_label(const uint32_t* word, uint32_t w) { return word[w] & 0xffffu; }
 
+// Node w will be in the next frontier: start fetching what its push reads — its record, the
+// neighbour's half record and its farthest-end bundle — one round ahead.
+__device__ __forceinline__ void mf2_warm(const Mf2Comp& C, uint32_t w) {
+    const NodeRec* nr = C.G.node + C.lo + w;
+    g_touch(nr);
+    g_touch(reinterpret_cast<const uint4*>(nr + 1) + 1);
+    if (C.have_optr) {
+        const uint16_t* optr = reinterpret_cast<const uint16_t*>(mf2_smem(C.optr_off));
+        const uint32_t ob = optr[w], oe = optr[w + 1];
+        if (oe > ob) g_touch(C.G.bund + C.obase + oe - 1);
+    }
+}
+
 // receive dl units at node w: the first giver of the round queues w unless it is in the frontier
 __device__ __forceinline__ void mf2_give(Mf2Shared& sh, uint32_t w, uint32_t dl) {
     const Mf2Comp& C = sh.C;
     const uint32_t old = atomicAdd(&mf2_smem(C.word_off)[w], dl << 16);
-    if ((old >> 16) == 0 && !((mf2_smem(C.inF_off)[w >> 5] >> (w & 31)) & 1u)) q2_append(C.T, &sh.nT, w);
+    if ((old >> 16) == 0 && !((mf2_smem(C.inF_off)[w >> 5] >> (w & 31)) & 1u)) {
+        q2_append(C.T, &sh.nT, w);
+        mf2_warm(C, w);
+    }
 }
 
 // One level of the relabel BFS: label to hand out, counter and queue of the next level.
@@ -449,7 +472,9 @@ __global__ void __launch_bounds__(THREADS, THREADS == 256 ? 2 : 1)
 k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __restrict__ comp_hi,
              uint32_t n_comp, uint32_t* work_counter, uint32_t* qF_g, uint32_t* qT_g, uint32_t* qN_g,
              uint32_t* qH_g, SolveParams P, CompStats* __restrict__ stats, uint32_t smem_bytes,
-             uint32_t qcap, uint32_t* __restrict__ fb_list, uint32_t* fb_count, uint32_t allow_optr) {
+             uint32_t qcap, uint32_t* __restrict__ fb_list, uint32_t* fb_count, uint32_t allow_optr,
+             const uint32_t* __restrict__ n_comp_dev /* non-null: the count lives on the device */,
+             MfTotals* __restrict__ totals) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Mf2Shared& sh = *reinterpret_cast<Mf2Shared*>(smem_raw);
     const uint32_t word_off = kMf2HeaderBytes + 16u * qcap;
@@ -457,6 +482,7 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
     const uint32_t node_cap_bytes = smem_bytes - kMf2HeaderBytes - 16u * qcap;
     const uint32_t tid = threadIdx.x;
     const uint32_t lane = lane_id();
+    if (n_comp_dev) n_comp = *n_comp_dev;
 
     for (;;) {
         if (tid == 0) sh.comp = atomicAdd(work_counter, 1u);
@@ -666,6 +692,7 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
                 }
                 const uint32_t ib = hi4.w, ie = r_hi.w;
                 c_bid = ie > ib ? lo4.y : 0u;  // nodes without in-arcs carry no valid id
+                if (ie > ib) g_touch(G.bund + c_bid);  // a relabel in B1 reads its flow
                 if ((oe - ob) + (ie - ib) > kHeavyDeg) {
                     q2_append(H, &sh.nH, i);
                     continue;
@@ -842,7 +869,7 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
                 const uint32_t dnew = nl ? nl : (wv & 0xffffu);
                 if (nl) word[v] = nl;
                 if (tot > 0 && dnew != kInf16) {
-                    q2_append(N, &sh.nN, ent);
+                    q2_append(N, &sh.nN, ent);  // (its records are in L1 since phase A)
                 } else {
                     if (tot > 0) my_stuck += tot;
                     atomicAnd(&inF[v >> 5], ~(1u << (v & 31)));
@@ -879,7 +906,9 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
             atomicAdd((unsigned long long*)&sh.stuck, (unsigned long long)my_stuck);
         }
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 0) mf_totals_add(totals, rounds, sh.pushes, sh.relabels, grs, bfs_levels, max_frontier,
+                                    sh.sink_flow, sh.stuck);
+        if (tid == 0 && stats) {  // per-component records: diagnostics only (GDS_DUMP_COMP)
             CompStats cs;
             cs.rounds = rounds;
             cs.pushes = sh.pushes;

@@ -16,6 +16,8 @@ __device__ __forceinline__ void q_append(uint32_t* q, uint32_t* count, uint32_t 
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_probe(uint32_t* chain, uint32_t n_chain, long long* out) {
+    extern __shared__ uint32_t dyn[];
+    if (threadIdx.x == 0 && n_chain == 0xffffffffu) dyn[0] = 1;
     __shared__ uint32_t sm[4096];
     __shared__ uint32_t cnt, flag[3];
     const uint32_t tid = threadIdx.x;
@@ -151,6 +153,36 @@ __global__ void __launch_bounds__(THREADS) k_probe(uint32_t* chain, uint32_t n_c
         if (tid == 32) out[15] = (t1 - t0) / R + (p == 0xffffffffu);
     }
     __syncthreads();
+    // (16) touch a record (load nobody waits for), do ~1500 clocks of other work, then load it: L1 hit?
+    if (tid == 0) {
+        uint32_t p = 5, acc2 = 0;
+        long long tot = 0;
+        for (int r = 0; r < R; ++r) {
+            const uint32_t nxt = (p * 2654435761u >> 8) & (n_chain - 1);
+            uint32_t dummy;
+            asm volatile("ld.global.u32 %0, [%1];" : "=r"(dummy) : "l"(chain + (size_t)nxt * 8));
+            for (int k = 0; k < 60; ++k) acc2 = sm[(acc2 + k) & 4095];  // ~1700 clocks of LDS chain
+            const long long a = clock64();
+            uint32_t v;
+            asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(chain + (size_t)nxt * 8 + (acc2 & 0)) : "memory");
+            p = v + acc2 * 0 + nxt;
+            tot += clock64() - a + (p == 0xffffffffu);
+        }
+        out[16] = tot / R;
+        // (17) the same without the touch
+        tot = 0;
+        for (int r = 0; r < R; ++r) {
+            const uint32_t nxt = (p * 2654435761u >> 8) & (n_chain - 1);
+            for (int k = 0; k < 60; ++k) acc2 = sm[(acc2 + k) & 4095];
+            const long long a = clock64();
+            uint32_t v;
+            asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(chain + (size_t)nxt * 8 + (acc2 & 0)) : "memory");
+            p = v + acc2 * 0 + nxt;
+            tot += clock64() - a + (p == 0xffffffffu);
+        }
+        out[17] = tot / R;
+    }
+    __syncthreads();
     // (12) first touch of a cold line chain (DRAM): separate region never touched
     if (tid == 0) {
         uint32_t p = n_chain;  // second half of the buffer, cold
@@ -188,20 +220,23 @@ int main() {
     char* big;
     cudaMalloc(&big, 512u << 20);
     cudaMemset(big, 1, 512u << 20);
-    const char* names[16] = {"__syncthreads", "__syncthreads_or", "flag+__syncthreads", "LDS dependent",
+    const char* names[18] = {"__syncthreads", "__syncthreads_or", "flag+__syncthreads", "LDS dependent",
                              "ATOMS.ADD ret dependent", "ATOMS.CAS dependent", "coalesced append (5 lanes)+LDS",
                              "LDG dependent (L2 hit, via L1)", "LDG.cg dependent (L2)", "STG + LDG dependent",
-                             "ATOMG ret + LDG", "LDS + 2 ATOMS.OR + barrier", "LDG cold (DRAM)", "LDG.cg + barrier", "LDG.cg + STG + barrier", "STG, barrier, LDG by another warp, barrier"};
+                             "ATOMG ret + LDG", "LDS + 2 ATOMS.OR + barrier", "LDG cold (DRAM)", "LDG.cg + barrier", "LDG.cg + STG + barrier", "STG, barrier, LDG by another warp, barrier", "LDG 1700 clocks after a touch", "LDG without the touch"};
     long long ho[32];
     for (int pass = 0; pass < 2; ++pass) {
         cudaMemset(out, 0, 32 * 8);
         if (pass == 0) k_probe<256><<<1, 256>>>(d, n, out);
-        else k_probe<1024><<<1, 1024>>>(d, n, out);
+        else {
+            cudaFuncSetAttribute(k_probe<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            k_probe<256><<<1, 256, 200 * 1024>>>(d, n, out);
+        }
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
         cudaMemcpy(ho, out, 32 * 8, cudaMemcpyDeviceToHost);
-        printf("---- %d threads ----\n", pass == 0 ? 256 : 1024);
-        for (int i = 0; i < 16; ++i) printf("%-36s %6lld clocks\n", names[i], ho[i]);
+        printf("---- 256 threads, %s ----\n", pass == 0 ? "no dynamic shared memory" : "200 KB dynamic shared memory");
+        for (int i = 0; i < 18; ++i) printf("%-36s %6lld clocks\n", names[i], ho[i]);
         cudaMemset(big, 2, 512u << 20);
     }
     return 0;
