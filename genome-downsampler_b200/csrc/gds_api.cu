@@ -51,7 +51,7 @@ struct gds_ctx {
     DevBuf bitmap, cov_tmp, dem_tmp, vdiff, vexcl;
     DevBuf vs_d, cross_idx, cross_tc, odiff, oexcl, cut_nodes, tile_off_d, head_bits;
     DevBuf dhist, dlay, b_slot, ident, dwork;  // direct (sort-free) bundle path
-    DevBuf kstat, pbund, cand, dctl, in_src, dem_v, fb_list;
+    DevBuf kstat, pbund, cand, dctl, in_src, dem_v, fb_list, in1, lab_g;
     int mf2_smem_set[3] = {0, 0, 0};
     unsigned direct_attr = 0;                  // bytes of dynamic smem the direct kernels are set up for
     int mf_smem_set[4] = {0, 0, 0, 0};  // dynamic shared memory the launch shapes are set up for
@@ -67,7 +67,7 @@ struct gds_ctx {
                          &comp_lo, &comp_hi, &qF, &qT, &qN, &qH, &work_counter, &comp_stats,
                          &bitmap, &cov_tmp, &dem_tmp, &vdiff, &vexcl, &vs_d, &cross_idx, &cross_tc,
                          &odiff, &oexcl, &cut_nodes, &tile_off_d, &head_bits, &dhist, &dlay, &b_slot,
-                         &ident, &dwork, &kstat, &pbund, &cand, &dctl, &in_src, &dem_v, &fb_list};
+                         &ident, &dwork, &kstat, &pbund, &cand, &dctl, &in_src, &dem_v, &fb_list, &in1, &lab_g};
         for (DevBuf* b : all) b->release();
     }
 };
@@ -122,7 +122,7 @@ void launch_maxflow_shape(gds_ctx* c, const MfGraph& mg,
                           uint32_t* wc, uint32_t* qF, uint32_t* qT, uint32_t* qN, uint32_t* qH,
                           const SolveParams& sp, CompStats* cstats, uint32_t max_comp_nodes,
                           const uint32_t* comp_list, const uint32_t* comp_list_n,
-                          const uint32_t* n_comp_dev, MfTotals* mft) {
+                          const uint32_t* n_comp_dev, MfTotals* mft, uint16_t* lab_g) {
     constexpr MfShape sh = kMfShapes[I];
     auto kern = k_maxflow<sh.threads, sh.qcap, sh.ctas_per_sm>;
     // 16-bit labels of a whole component in shared memory for the first global relabel, when
@@ -144,14 +144,15 @@ void launch_maxflow_shape(gds_ctx* c, const MfGraph& mg,
     }
     int grid = std::min<uint32_t>(n_comp, (uint32_t)kNumSMs * sh.ctas_per_sm);
     kern<<<grid, sh.threads, smem, c->stream>>>(mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp,
-                                                cstats, lab_cap, comp_list, comp_list_n, n_comp_dev, mft);
+                                                cstats, lab_cap, comp_list, comp_list_n, n_comp_dev, mft,
+                                                lab_g);
 }
 
 void launch_maxflow(gds_ctx* c, const MfGraph& mg,
                     const uint32_t* comp_lo, const uint32_t* comp_hi, uint32_t n_comp, uint32_t* wc,
                     uint32_t* qF, uint32_t* qT, uint32_t* qN, uint32_t* qH, const SolveParams& sp,
                     CompStats* cstats, unsigned long long alg_bytes, uint32_t max_comp_nodes,
-                    const uint32_t* n_comp_dev, MfTotals* mft,
+                    const uint32_t* n_comp_dev, MfTotals* mft, uint16_t* lab_g,
                     const uint32_t* comp_list = nullptr, const uint32_t* comp_list_n = nullptr) {
     KScope ks("maxflow", alg_bytes, c->stream);
     const uint32_t sms = (uint32_t)kNumSMs;
@@ -167,10 +168,10 @@ void launch_maxflow(gds_ctx* c, const MfGraph& mg,
     if (const char* e = getenv("GDS_MF_SMEM_LABELS"))  // =0: labels stay in global memory
         if (e[0] == '0') max_comp_nodes = 0;
     switch (shape) {
-        case 0: launch_maxflow_shape<0>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes, comp_list, comp_list_n, n_comp_dev, mft); break;
-        case 1: launch_maxflow_shape<1>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes, comp_list, comp_list_n, n_comp_dev, mft); break;
-        case 2: launch_maxflow_shape<2>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes, comp_list, comp_list_n, n_comp_dev, mft); break;
-        default: launch_maxflow_shape<3>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes, comp_list, comp_list_n, n_comp_dev, mft); break;
+        case 0: launch_maxflow_shape<0>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes, comp_list, comp_list_n, n_comp_dev, mft, lab_g); break;
+        case 1: launch_maxflow_shape<1>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes, comp_list, comp_list_n, n_comp_dev, mft, lab_g); break;
+        case 2: launch_maxflow_shape<2>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes, comp_list, comp_list_n, n_comp_dev, mft, lab_g); break;
+        default: launch_maxflow_shape<3>(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, max_comp_nodes, comp_list, comp_list_n, n_comp_dev, mft, lab_g); break;
     }
     GDS_KERNEL_CHECK();
 }
@@ -1311,13 +1312,15 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         const bool do_solve = !(flags & GDS_NO_SOLVE);
         const Mf2Plan mf2 = do_solve ? plan_maxflow_sm(n_comp, max_comp_nodes) : Mf2Plan{};
         uint32_t* in_src = c->in_src.get<uint32_t>((size_t)B + 1);
+        uint32_t* in1 = c->in1.get<uint32_t>((size_t)n_nodes + 1);
+        GDS_CUDA(cudaMemsetAsync(in1, 0xff, ((size_t)n_nodes + 1) * 4, st));
         if (B) {
             KScope ks("in_src", 24ull * B, st);
             k_in_src<<<div_up(B, 256), 256, 0, st>>>(c->bund.as<BundleRec>(), in_bid, in_ptr, B, in_src,
-                                                     mf2.on ? node : nullptr, direct.B_dev);
+                                                     mf2.on ? node : nullptr, direct.B_dev, in1);
             GDS_KERNEL_CHECK();
         }
-        MfGraph mg{node, d_snap, c->bund.as<BundleRec>(), in_bid, in_src, dem_v};
+        MfGraph mg{node, d_snap, c->bund.as<BundleRec>(), in_bid, in_src, dem_v, in1};
         // per-component records only for the diagnostics dump; gds_result's counters are summed on
         // the device (MfTotals)
         const char* dump_comp = getenv("GDS_DUMP_COMP");
@@ -1330,6 +1333,12 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             uint32_t* wc = c->work_counter.get<uint32_t>(4);  // [0] sm kernel, [1] fallback, [2] list size
             GDS_CUDA(cudaMemsetAsync(wc, 0, 16, st));
             const unsigned long long mf_bytes = 36ull * n_nodes + 20ull * B;
+            // compact labels for k_maxflow's relabels (GDS_MF_GLABELS=0: node records, round 1)
+            uint16_t* lab_g = nullptr;
+            {
+                const char* e = getenv("GDS_MF_GLABELS");
+                if (!(e && e[0] == '0')) lab_g = c->lab_g.get<uint16_t>(2 * (size_t)n_nodes + 4);
+            }
             if (mf2.on) {
                 uint32_t* fb_list = c->fb_list.get<uint32_t>(n_comp_cap + 1);
                 Mf2Graph g2{node, c->bund.as<BundleRec>(), in_bid, in_src, out_ptr, in_ptr, dem_v};
@@ -1337,11 +1346,11 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
                                   mf_bytes, fb_list, wc + 2, n_comp_dev, mft);
                 // whatever the shared-memory kernel could not take (grid: at most one wave)
                 launch_maxflow(c, mg, comp_lo, comp_hi, std::min<uint32_t>(n_comp, kNumSMs), wc + 1, qF,
-                               qT, qN, qH, sp, cstats, 0, max_comp_nodes, n_comp_dev, mft, fb_list,
-                               wc + 2);
+                               qT, qN, qH, sp, cstats, 0, max_comp_nodes, n_comp_dev, mft, lab_g,
+                               fb_list, wc + 2);
             } else {
                 launch_maxflow(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats,
-                               mf_bytes, max_comp_nodes, n_comp_dev, mft);
+                               mf_bytes, max_comp_nodes, n_comp_dev, mft, lab_g);
             }
         }
         GDS_CUDA(cudaEventRecord(c->ev[EV_MAXFLOW], st));

@@ -409,13 +409,16 @@ __global__ void __launch_bounds__(256)
 k_in_src(const BundleRec* __restrict__ bund, const uint32_t* __restrict__ in_bid,
          const uint32_t* __restrict__ in_ptr, uint32_t B, uint32_t* __restrict__ in_src,
          NodeRec* __restrict__ node /* null: k_maxflow only, the records keep {d, stamp, e, eadd} */,
-         const uint32_t* __restrict__ B_dev /* non-null: the bundle count lives on the device */) {
+         const uint32_t* __restrict__ B_dev /* non-null: the bundle count lives on the device */,
+         uint32_t* __restrict__ in1 /* [n_nodes], preset to 0xffffffff: start node of a node's only
+                                       in-arc, 0xfffffffe when it has several */) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (B_dev) B = *B_dev;
     if (k >= B) return;
     const uint32_t b = in_bid[k];
     const uint4 r = reinterpret_cast<const uint4*>(bund)[b];  // t, mult, f, s
     in_src[k] = r.w;
+    if (k == in_ptr[r.x]) in1[r.x] = k + 1 == in_ptr[r.x + 1] ? r.w : 0xfffffffeu;
     if (node && k + 1 == in_ptr[r.x + 1]) *reinterpret_cast<uint2*>(&node[r.x]) = make_uint2(r.w, b);
 }
 

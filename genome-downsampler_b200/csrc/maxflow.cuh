@@ -45,7 +45,10 @@ struct MfGraph {
     const uint32_t* in_bid;  // [B] bundle ids ordered by (end node, bundle id)
     const uint32_t* in_src;  // [B] start node of in_bid[k]: the first relabel needs nothing else
     const int32_t* dem;      // [n_nodes] demand: the initial excess / sink capacity come from it
+    const uint32_t* in1;     // [n_nodes] start node of a node's ONLY in-arc, kIn1None without in-arcs,
+                             // kIn1Multi with several: one trip less per level of the first relabel
 };
+constexpr uint32_t kIn1None = 0xffffffffu, kIn1Multi = 0xfffffffeu;
 
 struct SolveParams {
     uint32_t gr_interval_min, gr_levels_pct, gr_relabel_pct, max_rounds;
@@ -343,19 +346,24 @@ __device__ uint32_t mf_first_relabel(const MfGraph& G, uint32_t lo, uint32_t hi,
         };
         for (uint32_t i = tid; i < cnt && !warp_mode; i += THREADS) {
             const uint32_t w = T.get(i);
-            const uint32_t in_lo = ld_u32(&G.node[w].in_ptr), in_hi = ld_u32(&G.node[w + 1].in_ptr);
+            const uint32_t one = ld_u32(&G.in1[w]);  // most nodes have one in-arc: its start node
             // back arc (w+1) -> w.  Global labels: the CAS is issued here and its answer is only
             // looked at after the in-arcs, so it is in flight meanwhile
             uint32_t old_r = 0;
             bool got_r = false;
             if constexpr (LAB) got_r = w < hi && claim(w + 1);
             else if (w < hi) old_r = atomicCAS(&G.node[w + 1].d, kLabelInf, nl);
-            if (in_hi - in_lo > kHeavyDeg) {
-                q_append(H, &sh.nH, w);
-            } else {
-                for (uint32_t k = in_lo; k < in_hi; ++k) {
-                    const uint32_t s = ld_u32(&G.in_src[k]);
-                    if (claim(s)) label(s);
+            if (one < kIn1Multi) {
+                if (claim(one)) label(one);
+            } else if (one == kIn1Multi) {
+                const uint32_t in_lo = ld_u32(&G.node[w].in_ptr), in_hi = ld_u32(&G.node[w + 1].in_ptr);
+                if (in_hi - in_lo > kHeavyDeg) {
+                    q_append(H, &sh.nH, w);
+                } else {
+                    for (uint32_t k = in_lo; k < in_hi; ++k) {
+                        const uint32_t s = ld_u32(&G.in_src[k]);
+                        if (claim(s)) label(s);
+                    }
                 }
             }
             if constexpr (!LAB) got_r = w < hi && old_r == kLabelInf;
@@ -411,10 +419,13 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
           const uint32_t* __restrict__ comp_list /* null: all components; else the ids to solve */,
           const uint32_t* __restrict__ comp_list_n,
           const uint32_t* __restrict__ n_comp_dev /* non-null: the component count lives on the device */,
-          MfTotals* __restrict__ totals) {
+          MfTotals* __restrict__ totals,
+          uint16_t* __restrict__ lab_g /* [2 * n_nodes + 2] or null: compact 16-bit labels in GLOBAL
+              memory for the relabel BFS of components whose labels get no shared memory — the BFS
+              then claims 16 nodes per sector instead of one 32-byte record per node */) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MfShared<QCAP>& sh = *reinterpret_cast<MfShared<QCAP>*>(smem_raw);
-    uint16_t* lab_base = reinterpret_cast<uint16_t*>(smem_raw + sizeof(MfShared<QCAP>));
+    uint16_t* lab_smem = reinterpret_cast<uint16_t*>(smem_raw + sizeof(MfShared<QCAP>));
     const uint32_t tid = threadIdx.x;
     if (n_comp_dev) n_comp = *n_comp_dev;
     if (comp_list) n_comp = *comp_list_n;  // the components k_maxflow_sm left for this kernel
@@ -427,6 +438,14 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
         const uint32_t c = comp_list ? comp_list[ticket] : ticket;
         const uint32_t lo = comp_lo[c], hi = comp_hi[c];
         const uint32_t ncomp = hi - lo + 1;
+        // 16-bit labels during a relabel: shared memory when the launch has it, else the compact
+        // global array (base 2*lo: 4-byte aligned, components never overlap)
+        uint16_t* lab_base = lab_smem;
+        uint32_t lcap = lab_cap;
+        if (ncomp > lcap && lab_g && ncomp < 0xfff0u) {
+            lab_base = lab_g + 2 * (size_t)lo;
+            lcap = 0xfff0u;
+        }
         Queue<QCAP> F{sh.qa, qF_g + lo}, T{sh.qb, qT_g + lo}, N{sh.qc, qN_g + lo},
             H{sh.qd, qH_g + lo};
         if (tid == 0) {
@@ -461,7 +480,7 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
         long long tparts[3] = {0, 0, 0};
         const long long t_gr = clock64();
         uint32_t last_levels =
-            ncomp <= lab_cap
+            ncomp <= lcap
                 ? mf_first_relabel<THREADS, QCAP, true>(G, lo, hi, T, N, H, sh, bfs_levels, warp_mode,
                                                         lab_base)
                 : mf_first_relabel<THREADS, QCAP, false>(G, lo, hi, T, N, H, sh, bfs_levels,
@@ -488,7 +507,7 @@ k_maxflow(MfGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __res
                 (unsigned long long)sh.relabels_since * 100 >=
                     (unsigned long long)P.gr_relabel_pct * ncomp) {
                 __syncthreads();  // everyone has read relabels_since
-                last_levels = ncomp <= lab_cap
+                last_levels = ncomp <= lcap
                                   ? mf_global_relabel<THREADS, QCAP, true>(G, lo, hi, T, N, H, sh,
                                                                            bfs_levels, warp_mode, lab_base)
                                   : mf_global_relabel<THREADS, QCAP, false>(G, lo, hi, T, N, H, sh,
