@@ -179,6 +179,16 @@ void launch_maxflow(gds_ctx* c, const MfGraph& mg,
 // K3 with the hot state in shared memory (maxflow_sm.cuh).  Returns false when no component of
 // this call can fit (then k_maxflow solves everything).  Components the kernel finds ineligible
 // (too large for the launch, supply beyond 16 bits) land on fb_list for k_maxflow.
+// Components whose nodes are mostly heavy (variable read lengths: tens of bundles per node) go to
+// k_maxflow: their frontiers hold tens of nodes with ~40 bundles each, the time is the per-bundle
+// global traffic of the warp passes, and 32 warps of 64 registers (k_maxflow) beat 16 warps with the
+// labels in shared memory (config 2 without its filter: 2.6 ms there, 3.0 ms here after batching the
+// loads of eight nodes per warp; 3.4 ms before).  GDS_MF_WARP=1 keeps them here (tests, measurements).
+inline uint32_t mf2_allow_warp() {
+    const char* e = getenv("GDS_MF_WARP");
+    return (e && e[0] == '1') ? 1u : 0u;
+}
+
 constexpr int kMf2MaxSmem = 227 * 1024;
 template <int THREADS, int SLOT>
 void launch_mf2_shape(gds_ctx* c, const Mf2Graph& g, const uint32_t* comp_lo, const uint32_t* comp_hi,
@@ -194,7 +204,7 @@ void launch_mf2_shape(gds_ctx* c, const Mf2Graph& g, const uint32_t* comp_lo, co
     const int grid = (int)std::min<uint32_t>(n_comp, (uint32_t)(kNumSMs * ctas_per_sm));
     kern<<<grid, THREADS, smem, c->stream>>>(g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats,
                                              (uint32_t)smem, qcap, fb_list, fb_count, optr ? 1u : 0u,
-                                             n_comp_dev, mft);
+                                             n_comp_dev, mft, mf2_allow_warp());
 }
 
 // Whether this call's components go to k_maxflow_sm, and with which launch shape.

@@ -217,8 +217,12 @@ __device__ __forceinline__ void mf2_expand_multi(Mf2Shared& sh, const Mf2Lvl& nx
         q2_append(C.H, &sh.nH, u);
         return;
     }
-#pragma unroll 1
-    for (uint32_t k = in_lo; k < in_hi; ++k) mf2_mark(C, nxt, g_ld(&C.G.in_src[k]) - C.lo);
+    uint32_t src[kHeavyDeg];  // all loads first: one memory trip instead of one per in-arc
+#pragma unroll
+    for (uint32_t q = 0; q < kHeavyDeg; ++q) src[q] = in_lo + q < in_hi ? g_ld(&C.G.in_src[in_lo + q]) : 0xffffffffu;
+#pragma unroll
+    for (uint32_t q = 0; q < kHeavyDeg; ++q)
+        if (src[q] != 0xffffffffu) mf2_mark(C, nxt, src[q] - C.lo);
 }
 
 // later relabels (flow exists), node u: residual arcs into u come from global memory
@@ -252,39 +256,71 @@ __device__ __forceinline__ void mf2_expand_flow(Mf2Shared& sh, const Mf2Lvl& nxt
     }
 }
 
-// relabel BFS, nodes with many arcs: one warp each
+// relabel BFS, nodes with many arcs: one warp each.  First relabel: a warp takes up to eight of the
+// level's heavy nodes at once — their in-CSR ranges in one memory trip (one lane per node), then the
+// first 64 in-arcs of all eight in a second one (16 loads in flight per lane) — because a level of a
+// component with variable read lengths holds ~150 nodes with ~40 in-arcs each and, taken one node
+// after the other, costs two dependent trips per node (config 2: 13 600 clocks per level in k_maxflow).
 template <int THREADS>
 __device__ __forceinline__ void mf2_bfs_heavy(Mf2Shared& sh, const Mf2Lvl& nxt, uint32_t nH, bool first) {
     const Mf2Comp& C = sh.C;
-    const uint32_t lane = lane_id(), lo = C.lo;
+    const uint32_t lane = lane_id(), lo = C.lo, warp = threadIdx.x >> 5;
+    constexpr uint32_t NW = THREADS / 32, kBatch = 8;
+    if (first) {
 #pragma unroll 1
-    for (uint32_t h = threadIdx.x >> 5; h < nH; h += THREADS / 32) {
+        for (uint32_t base = warp; base < nH; base += NW * kBatch) {
+            // lane j < kBatch owns node (base + j * NW): its in-CSR range
+            uint32_t my_lo = 0, my_hi = 0;
+            if (lane < kBatch && base + lane * NW < nH) {
+                const uint32_t u = C.H.get(base + lane * NW);
+                my_lo = g_ld(&C.G.in_ptr[lo + u]);
+                my_hi = g_ld(&C.G.in_ptr[lo + u + 1]);
+            }
+            uint32_t src[kBatch][2];
+#pragma unroll
+            for (uint32_t j = 0; j < kBatch; ++j) {
+                const uint32_t in_lo = __shfl_sync(0xffffffffu, my_lo, j);
+                const uint32_t in_hi = __shfl_sync(0xffffffffu, my_hi, j);
+                const uint32_t k0 = in_lo + lane, k1 = k0 + 32;
+                src[j][0] = k0 < in_hi ? g_ld(&C.G.in_src[k0]) : 0xffffffffu;
+                src[j][1] = k1 < in_hi ? g_ld(&C.G.in_src[k1]) : 0xffffffffu;
+            }
+#pragma unroll
+            for (uint32_t j = 0; j < kBatch; ++j) {
+                if (src[j][0] != 0xffffffffu) mf2_mark(C, nxt, src[j][0] - lo);
+                if (src[j][1] != 0xffffffffu) mf2_mark(C, nxt, src[j][1] - lo);
+                const uint32_t in_lo = __shfl_sync(0xffffffffu, my_lo, j);
+                const uint32_t in_hi = __shfl_sync(0xffffffffu, my_hi, j);
+#pragma unroll 1
+                for (uint32_t k = in_lo + 64 + lane; k < in_hi; k += 32)  // beyond 64 in-arcs
+                    mf2_mark(C, nxt, g_ld(&C.G.in_src[k]) - lo);
+            }
+        }
+        return;
+    }
+#pragma unroll 1
+    for (uint32_t h = warp; h < nH; h += NW) {
         const uint32_t u = C.H.get(h);
-        if (first) {
-            const uint32_t in_lo = g_ld(&C.G.in_ptr[lo + u]), in_hi = g_ld(&C.G.in_ptr[lo + u + 1]);
+        const uint4 hi4 = ld_node_hi(C.G.node + lo + u);
+        const uint4 nx = ld_node_hi(C.G.node + lo + u + 1);
 #pragma unroll 1
-            for (uint32_t k = in_lo + lane; k < in_hi; k += 32)
-                mf2_mark(C, nxt, g_ld(&C.G.in_src[k]) - lo);
-        } else {
-            const uint4 hi4 = ld_node_hi(C.G.node + lo + u);
-            const uint4 nx = ld_node_hi(C.G.node + lo + u + 1);
+        for (uint32_t k = hi4.w + lane; k < nx.w; k += 32) {
+            const uint4 b = ld_bund(&C.G.bund[g_ld(&C.G.in_bid[k])]);
+            if (b.z < b.y) mf2_mark(C, nxt, b.w - lo);
+        }
 #pragma unroll 1
-            for (uint32_t k = hi4.w + lane; k < nx.w; k += 32) {
-                const uint4 b = ld_bund(&C.G.bund[g_ld(&C.G.in_bid[k])]);
-                if (b.z < b.y) mf2_mark(C, nxt, b.w - lo);
-            }
-#pragma unroll 1
-            for (uint32_t b = hi4.z + lane; b < nx.z; b += 32) {
-                const uint4 r = ld_bund(&C.G.bund[b]);
-                if (r.z > 0) mf2_mark(C, nxt, r.x - lo);
-            }
+        for (uint32_t b = hi4.z + lane; b < nx.z; b += 32) {
+            const uint4 r = ld_bund(&C.G.bund[b]);
+            if (r.z > 0) mf2_mark(C, nxt, r.x - lo);
         }
     }
 }
 
 // phase A, nodes with many bundles (warp mode: the whole frontier), one warp each.  The sequential
 // "push until the excess is gone" over the bundles in their fixed order is an exclusive prefix sum
-// of the admissible residuals across the lanes (maxflow.cuh).
+// of the admissible residuals across the lanes (maxflow.cuh).  Memory trips per node: its records;
+// then its last 64 out-bundles and the start nodes of its last 64 in-arcs together (two of each per
+// lane in flight); the flow of an in-bundle only when the labels admit cancelling it.
 template <int THREADS>
 __device__ __forceinline__ void mf2_push_heavy(Mf2Shared& sh, uint32_t nHA, unsigned long long& my_pushes,
                                             long long& my_sink) {
@@ -303,6 +339,15 @@ __device__ __forceinline__ void mf2_push_heavy(Mf2Shared& sh, uint32_t nHA, unsi
         const uint4 hi4 = ld_node_hi(nr);
         const uint4 r_hi = ld_node_hi(nr + 1);
         const uint32_t ob = hi4.z, oe = r_hi.z, ib = hi4.w, ie = r_hi.w;
+        // second trip: everything the five steps may look at, at once
+        uint4 pre_b[2];
+        uint32_t pre_s[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const uint32_t off = lane + 32u * q;
+            pre_b[q] = oe - ob > off ? ld_bund(&C.G.bund[oe - 1 - off]) : make_uint4(0, 0, 0, 0);
+            pre_s[q] = ie - ib > off ? g_ld(&C.G.in_src[ie - 1 - off]) : 0xffffffffu;
+        }
         const uint32_t dL = v > 0 ? mf2_label(word, v - 1) : kInf16;
         const uint32_t dR = v + 1 < n ? mf2_label(word, v + 1) : kInf16;
         if (dv == 1) {  // 1. sink arc
@@ -318,14 +363,15 @@ __device__ __forceinline__ void mf2_push_heavy(Mf2Shared& sh, uint32_t nHA, unsi
             }
         }
         // 2. own bundles, farthest end first: lane j looks at bundle (top - 1 - j)
+        uint32_t chunk = 0;
 #pragma unroll 1
-        for (uint32_t top = oe; ex > 0 && top > ob; top = top - ob > 32 ? top - 32 : ob) {
+        for (uint32_t top = oe; ex > 0 && top > ob; top = top - ob > 32 ? top - 32 : ob, ++chunk) {
             const bool have = top - ob > lane;
             const uint32_t b = top - 1 - lane;
             uint4 br = make_uint4(0, 0, 0, 0);
             uint32_t r = 0;
             if (have) {
-                br = ld_bund(&C.G.bund[b]);
+                br = chunk == 0 ? pre_b[0] : chunk == 1 ? pre_b[1] : ld_bund(&C.G.bund[b]);
                 r = br.y - br.z;
                 if (r && mf2_label(word, br.x - lo) + 1 != dv) r = 0;
             }
@@ -362,12 +408,13 @@ __device__ __forceinline__ void mf2_push_heavy(Mf2Shared& sh, uint32_t nHA, unsi
             ex = 0;
         }
         // 5. cancel flow on incoming bundles, nearest start first
+        chunk = 0;
 #pragma unroll 1
-        for (uint32_t top = ie; ex > 0 && top > ib; top = top - ib > 32 ? top - 32 : ib) {
+        for (uint32_t top = ie; ex > 0 && top > ib; top = top - ib > 32 ? top - 32 : ib, ++chunk) {
             const bool have = top - ib > lane;
             uint32_t b = 0, r = 0, s = 0;
             if (have) {
-                s = g_ld(&C.G.in_src[top - 1 - lane]) - lo;
+                s = (chunk == 0 ? pre_s[0] : chunk == 1 ? pre_s[1] : g_ld(&C.G.in_src[top - 1 - lane])) - lo;
                 if (mf2_label(word, s) + 1 == dv) {  // only then is the flow worth a memory trip
                     b = g_ld(&C.G.in_bid[top - 1 - lane]);
                     r = g_ld(&C.G.bund[b].f);
@@ -387,7 +434,9 @@ __device__ __forceinline__ void mf2_push_heavy(Mf2Shared& sh, uint32_t nHA, unsi
     }
 }
 
-// phase B1, relabel of nodes with many bundles, one warp each: the new label waits in the high half
+// phase B1, relabel of nodes with many bundles, one warp each: the new label waits in the high half.
+// Trips: the records; the first 64 out-bundles and the ids of the first 64 in-bundles together; the
+// in-bundles themselves.
 template <int THREADS>
 __device__ __forceinline__ void mf2_relabel_heavy(Mf2Shared& sh, uint32_t nH) {
     const Mf2Comp& C = sh.C;
@@ -399,17 +448,34 @@ __device__ __forceinline__ void mf2_relabel_heavy(Mf2Shared& sh, uint32_t nH) {
         const NodeRec* nr = C.G.node + lo + v;
         const uint4 hi4 = ld_node_hi(nr);
         const uint4 r_hi = ld_node_hi(nr + 1);
+        uint4 ob2[2];
+        uint32_t id2[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const uint32_t b = hi4.z + lane + 32u * q, k = hi4.w + lane + 32u * q;
+            ob2[q] = b < r_hi.z ? ld_bund(&C.G.bund[b]) : make_uint4(0, 0, 0, 0);
+            id2[q] = k < r_hi.w ? g_ld(&C.G.in_bid[k]) : 0xffffffffu;
+        }
+        uint4 ib2[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+            ib2[q] = id2[q] != 0xffffffffu ? ld_bund(&C.G.bund[id2[q]]) : make_uint4(0, 0, 0, 0);
         uint32_t mn = kInf16;
         if ((int32_t)hi4.x > 0) mn = 0;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            if (ob2[q].z < ob2[q].y) mn = min(mn, mf2_label(word, ob2[q].x - lo));  // (0,0): not taken
+            if (ib2[q].z > 0) mn = min(mn, mf2_label(word, ib2[q].w - lo));
+        }
 #pragma unroll 1
-        for (uint32_t b = hi4.z + lane; b < r_hi.z; b += 32) {
+        for (uint32_t b = hi4.z + 64 + lane; b < r_hi.z; b += 32) {
             const uint4 br = ld_bund(&C.G.bund[b]);
             if (br.z < br.y) mn = min(mn, mf2_label(word, br.x - lo));
         }
         if (v + 1 < n && (int32_t)r_hi.y > 0) mn = min(mn, mf2_label(word, v + 1));
         if (v > 0) mn = min(mn, mf2_label(word, v - 1));
 #pragma unroll 1
-        for (uint32_t k = hi4.w + lane; k < r_hi.w; k += 32) {
+        for (uint32_t k = hi4.w + 64 + lane; k < r_hi.w; k += 32) {
             const uint4 br = ld_bund(&C.G.bund[g_ld(&C.G.in_bid[k])]);
             if (br.z > 0) mn = min(mn, mf2_label(word, br.w - lo));
         }
@@ -474,7 +540,7 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
              uint32_t* qH_g, SolveParams P, CompStats* __restrict__ stats, uint32_t smem_bytes,
              uint32_t qcap, uint32_t* __restrict__ fb_list, uint32_t* fb_count, uint32_t allow_optr,
              const uint32_t* __restrict__ n_comp_dev /* non-null: the count lives on the device */,
-             MfTotals* __restrict__ totals) {
+             MfTotals* __restrict__ totals, uint32_t allow_warp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Mf2Shared& sh = *reinterpret_cast<Mf2Shared*>(smem_raw);
     const uint32_t word_off = kMf2HeaderBytes + 16u * qcap;
@@ -533,7 +599,7 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
             C.N = Q2{kMf2HeaderBytes + 8u * qcap, qN_g + lo, qcap};
             C.H = Q2{kMf2HeaderBytes + 12u * qcap, qH_g + lo, qcap};
         }
-        if (!fits || warp_mode) {  // not for this kernel: k_maxflow takes it (see below)
+        if (!fits || (warp_mode && !allow_warp)) {  // not for this kernel: k_maxflow takes it
             if (tid == 0) fb_list[atomicAdd(fb_count, 1u)] = c;
             __syncthreads();
             continue;

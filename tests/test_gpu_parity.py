@@ -534,8 +534,12 @@ def test_maxflow_kernels_agree(solver, O):
         b = _solve_with_env(solver, {"GDS_MF": "global"}, s, e, Ls, M, read_off=off, params=prm,
                             verify=True)
         c = _solve_with_env(solver, {"GDS_MF_OPTR": "0"}, s, e, Ls, M, read_off=off, params=prm)
+        # heavy components stay in the shared-memory kernel (its warp passes) instead of k_maxflow
+        d = _solve_with_env(solver, {"GDS_MF_WARP": "1", "GDS_SYNC": "1"}, s, e, Ls, M, read_off=off,
+                            params=prm)
         for key in COUNTERS:
-            assert a[key] == b[key] == c[key], key
+            assert a[key] == b[key] == c[key] == d[key], key
+        assert np.array_equal(a.kept_bitmap, d.kept_bitmap)
         assert np.array_equal(a.kept_bitmap, b.kept_bitmap)
         assert np.array_equal(a.kept_bitmap, c.kept_bitmap)
         assert_parity(O, a, s, e, Ls, off, M, prm)
