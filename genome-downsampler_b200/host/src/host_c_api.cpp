@@ -2,6 +2,9 @@
 // reads_gen, and the whole plugin path (BamApi + SolverManager + qmcp::Solver) on plain arrays.
 // Built into libgds_host.so next to libgds_b200.so.
 #include <algorithm>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <chrono>
 #include <cstdint>
 #include <cstring>
@@ -122,28 +125,95 @@ int64_t gdsh_plugin_solve_batch(uint32_t n_samples, const uint64_t* read_off, ui
     return static_cast<int64_t>(total);
 }
 
+}  // extern "C"
+
 // The narrowing a caller with 32-bit columns has to do to use the compact transport
-// (include/gds.h gds_reads.start16 / end == NULL): 16-bit starts plus the exact read-length range,
-// on `threads` host threads.  Returns 1 when every start fits 16 bits.
-int gdsh_encode_compact(const uint32_t* start, const uint32_t* end, uint64_t n, uint16_t* start16,
-                        uint32_t* len_min, uint32_t* len_max, uint32_t threads) {
+// (include/gds.h gds_reads.start16 / end == NULL): 16-bit starts, on `threads` host threads.
+// end != NULL: the exact read-length range is computed as well (what the C++ adapter's narrowing loop
+// does with the reference's size_t columns).  end == NULL: the caller KNOWS the one read length (the
+// generator's read_length parameter, a run's metadata) and passes it as the hint; only the start
+// column is read.  Returns 1 when every start fits 16 bits.  AVX2 when the CPU has it: the loop is
+// memory-bound either way, but 8 threads of scalar code do not reach the memory system's rate.
+namespace {
+struct EncPart {
+    uint32_t lo = 0xffffffffu, hi = 0, big = 0;
+};
+
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void enc_range_avx2(const uint32_t* start, const uint32_t* end,
+                                                    uint16_t* out, uint64_t b, uint64_t e, EncPart& p) {
+    uint64_t i = b;
+    __m256i vbig = _mm256_setzero_si256();
+    __m256i vlo = _mm256_set1_epi32(-1), vhi = _mm256_setzero_si256();
+    for (; i + 16 <= e; i += 16) {
+        const __m256i s0 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(start + i));
+        const __m256i s1 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(start + i + 8));
+        vbig = _mm256_or_si256(vbig, _mm256_or_si256(s0, s1));
+        // packus saturates, which is fine: a start beyond 16 bits fails the call anyway
+        const __m256i pk = _mm256_permute4x64_epi64(_mm256_packus_epi32(s0, s1), 0xD8);
+        _mm256_storeu_si256(reinterpret_cast<__m256i*>(out + i), pk);
+        if (end) {
+            const __m256i one = _mm256_set1_epi32(1);
+            const __m256i l0 = _mm256_add_epi32(
+                _mm256_sub_epi32(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(end + i)), s0), one);
+            const __m256i l1 = _mm256_add_epi32(
+                _mm256_sub_epi32(_mm256_loadu_si256(reinterpret_cast<const __m256i*>(end + i + 8)), s1), one);
+            vlo = _mm256_min_epu32(vlo, _mm256_min_epu32(l0, l1));
+            vhi = _mm256_max_epu32(vhi, _mm256_max_epu32(l0, l1));
+        }
+    }
+    alignas(32) uint32_t t[8];
+    _mm256_store_si256(reinterpret_cast<__m256i*>(t), vbig);
+    for (uint32_t x : t) p.big |= x;
+    if (end) {
+        _mm256_store_si256(reinterpret_cast<__m256i*>(t), vlo);
+        for (uint32_t x : t) p.lo = std::min(p.lo, x);
+        _mm256_store_si256(reinterpret_cast<__m256i*>(t), vhi);
+        for (uint32_t x : t) p.hi = std::max(p.hi, x);
+    }
+    for (; i < e; ++i) {
+        const uint32_t s = start[i];
+        out[i] = static_cast<uint16_t>(s);
+        p.big |= s;
+        if (end) {
+            const uint32_t len = end[i] - s + 1;
+            p.lo = std::min(p.lo, len);
+            p.hi = std::max(p.hi, len);
+        }
+    }
+}
+#endif
+
+void enc_range(const uint32_t* start, const uint32_t* end, uint16_t* out, uint64_t b, uint64_t e,
+               EncPart& p) {
+#if defined(__x86_64__)
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) {
+        enc_range_avx2(start, end, out, b, e, p);
+        return;
+    }
+#endif
+    for (uint64_t i = b; i < e; ++i) {
+        const uint32_t s = start[i];
+        out[i] = static_cast<uint16_t>(s);
+        p.big |= s;
+        if (end) {
+            const uint32_t len = end[i] - s + 1;
+            p.lo = std::min(p.lo, len);
+            p.hi = std::max(p.hi, len);
+        }
+    }
+}
+}  // namespace
+
+extern "C" int gdsh_encode_compact(const uint32_t* start, const uint32_t* end, uint64_t n, uint16_t* start16,
+                                   uint32_t* len_min, uint32_t* len_max, uint32_t threads) {
     const unsigned nt = n < (1u << 18) ? 1u : std::max(1u, std::min(threads, 64u));
-    std::vector<uint32_t> mn(nt, 0xffffffffu), mx(nt, 0);
-    std::vector<int> fits(nt, 1);
+    std::vector<EncPart> parts(nt);
     const uint64_t per = ((n + nt - 1) / nt + 63) & ~uint64_t{63};
     auto work = [&](unsigned t) {
         const uint64_t b = std::min<uint64_t>(n, (uint64_t)t * per), e = std::min<uint64_t>(n, b + per);
-        uint32_t lo = 0xffffffffu, hi = 0, big = 0;
-        for (uint64_t i = b; i < e; ++i) {
-            const uint32_t s = start[i], len = end[i] - s + 1;
-            start16[i] = static_cast<uint16_t>(s);
-            big |= s;
-            lo = std::min(lo, len);
-            hi = std::max(hi, len);
-        }
-        mn[t] = lo;
-        mx[t] = hi;
-        fits[t] = big <= 0xffffu;
+        enc_range(start, end, start16, b, e, parts[t]);
     };
     if (nt == 1) {
         work(0);
@@ -155,14 +225,15 @@ int gdsh_encode_compact(const uint32_t* start, const uint32_t* end, uint64_t n, 
     int ok = 1;
     *len_min = 0xffffffffu;
     *len_max = 0;
-    for (unsigned t = 0; t < nt; ++t) {
-        *len_min = std::min(*len_min, mn[t]);
-        *len_max = std::max(*len_max, mx[t]);
-        ok &= fits[t];
+    for (const EncPart& p : parts) {
+        *len_min = std::min(*len_min, p.lo);
+        *len_max = std::max(*len_max, p.hi);
+        ok &= p.big <= 0xffffu;
     }
     return ok;
 }
 
+extern "C" {
 // ---- BAM files: the file-backed BamApi behind a handle ----
 
 int64_t gdsh_write_synthetic_bam(const char* path, uint64_t n, uint32_t genome_len,

@@ -59,10 +59,14 @@ class ChunkedSolver:
                     hint = len_hint
                     if encode16_ptr and n and int(ref_len[a:b].max()) <= 65536:
                         from . import hostlib
-                        fits, lo, hi = hostlib.encode_compact(sp, ep, n, encode16_ptr + 2 * r0,
+                        # a caller that KNOWS the one read length (len_hint) spares the end column
+                        known = hint is not None and hint[0] == hint[1] and hint[0] > 0
+                        fits, lo, hi = hostlib.encode_compact(sp, None if known else ep, n,
+                                                              encode16_ptr + 2 * r0,
                                                               threads=encode_threads)
-                        hint = (lo, hi)
-                        if fits and lo == hi:
+                        if not known:
+                            hint = (lo, hi)
+                        if fits and hint[0] == hint[1]:
                             sp, ep, s16 = None, None, encode16_ptr + 2 * r0
                     results[ci] = sv.solve_device(
                         sp, ep, n, ref_len[a:b], max_coverage,
