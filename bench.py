@@ -449,10 +449,19 @@ def run_b200(args, wl, wname):
             gathered = [torch.empty((world, words), dtype=torch.int32, device=dev) if rank == 0
                         else None for _ in range(2)]
             bitmaps2 = [bitmap, torch.zeros(words + 4, dtype=torch.int32, device=dev)]
+            gathered_all = [torch.empty(world * words, dtype=torch.int32, device=dev)
+                            for _ in range(2)] if args.gather == "all" else None
+
+        gl = [list(g.unbind(0)) if g is not None else None for g in gathered] if world > 1 else None
 
         def gather_async(buf_idx):
-            _, pending[buf_idx] = sharding.gather_bitmaps_to_root(
-                bitmaps2[buf_idx][:words].view(1, words), out=gathered[buf_idx], dst=0, async_op=True)
+            if args.gather == "none":      # measurement only: what the collective costs
+                return
+            if args.gather == "all":       # round 1: every rank receives every bitmap
+                pending[buf_idx] = dist.all_gather_into_tensor(
+                    gathered_all[buf_idx], bitmaps2[buf_idx][:words], async_op=True)
+                return
+            pending[buf_idx] = dist.gather(bitmaps2[buf_idx][:words], gl[buf_idx], dst=0, async_op=True)
 
         def gather_wait(buf_idx=None):
             for i in ([buf_idx] if buf_idx is not None else [0, 1]):
@@ -757,6 +766,9 @@ def main():
     ap.add_argument("--chunk-samples", type=int, default=64,
                     help="samples per chunk of the end-to-end (host buffer) leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="root", choices=["root", "all", "none"],
+                    help="N > 1: kept bitmaps gathered on rank 0 (default), all-gathered (round 1), or "
+                         "not at all (measures what the collective costs)")
     ap.add_argument("--weak", action="store_true",
                     help="N > 1: every rank takes the workload's full sample count (weak scaling) "
                          "instead of a share of the one batch (default, strong scaling)")

@@ -19,6 +19,7 @@
 #include "radix_sort.cuh"
 #include "scan.cuh"
 #include "select.cuh"
+#include "sweep.cuh"
 
 using namespace gds;
 
@@ -51,7 +52,8 @@ struct gds_ctx {
     DevBuf bitmap, cov_tmp, dem_tmp, vdiff, vexcl;
     DevBuf vs_d, cross_idx, cross_tc, odiff, oexcl, cut_nodes, tile_off_d, head_bits;
     DevBuf dhist, dlay, b_slot, ident, dwork;  // direct (sort-free) bundle path
-    DevBuf kstat, pbund, cand, dctl, in_src, dem_v, fb_list, in1, lab_g;
+    DevBuf kstat, pbund, cand, dctl, in_src, dem_v, fb_list, in1, lab_g, taken;
+    int sweep_smem_set = 0;
     int mf2_smem_set[3] = {0, 0, 0};
     unsigned direct_attr = 0;                  // bytes of dynamic smem the direct kernels are set up for
     int mf_smem_set[4] = {0, 0, 0, 0};  // dynamic shared memory the launch shapes are set up for
@@ -67,7 +69,7 @@ struct gds_ctx {
                          &comp_lo, &comp_hi, &qF, &qT, &qN, &qH, &work_counter, &comp_stats,
                          &bitmap, &cov_tmp, &dem_tmp, &vdiff, &vexcl, &vs_d, &cross_idx, &cross_tc,
                          &odiff, &oexcl, &cut_nodes, &tile_off_d, &head_bits, &dhist, &dlay, &b_slot,
-                         &ident, &dwork, &kstat, &pbund, &cand, &dctl, &in_src, &dem_v, &fb_list, &in1, &lab_g};
+                         &ident, &dwork, &kstat, &pbund, &cand, &dctl, &in_src, &dem_v, &fb_list, &in1, &lab_g, &taken};
         for (DevBuf* b : all) b->release();
     }
 };
@@ -286,6 +288,35 @@ void launch_maxflow_sm(gds_ctx* c, const Mf2Plan& pl, const Mf2Graph& g, const u
         case 0: launch_mf2_shape<256, 0>(c, g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, pl.smem, pl.qcap, fb_list, fb_count, pl.optr, pl.per_sm, n_comp_dev, mft); break;
         case 1: launch_mf2_shape<512, 1>(c, g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, pl.smem, pl.qcap, fb_list, fb_count, pl.optr, pl.per_sm, n_comp_dev, mft); break;
         default: launch_mf2_shape<1024, 2>(c, g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats, pl.smem, pl.qcap, fb_list, fb_count, pl.optr, pl.per_sm, n_comp_dev, mft); break;
+    }
+    GDS_KERNEL_CHECK();
+}
+
+// K3' (sweep.cuh): the minimum-cardinality solve.  One warp per component.
+template <int W, int CAP>
+void launch_sweep_shape(gds_ctx* c, const SweepGraph& g, const uint32_t* comp_lo, const uint32_t* comp_hi,
+                        uint32_t n_comp, const uint32_t* n_comp_dev, uint32_t M, uint32_t* wc,
+                        unsigned long long* fail) {
+    const int smem = kSweepWarps * (2 * W + 4 * CAP) * 4;
+    auto kern = k_sweep<W, CAP>;
+    GDS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int grid = std::max(1, std::min<int>(div_up(n_comp, kSweepWarps), kNumSMs * 8));
+    kern<<<grid, kSweepWarps * 32, smem, c->stream>>>(g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail);
+}
+
+void launch_sweep(gds_ctx* c, const SweepGraph& g, const uint32_t* comp_lo, const uint32_t* comp_hi,
+                  uint32_t n_comp, const uint32_t* n_comp_dev, uint32_t M, uint32_t* wc,
+                  unsigned long long* fail, uint32_t maxlen, bool one_len,
+                  unsigned long long alg_bytes) {
+    KScope ks("sweep", alg_bytes, c->stream);
+    const int w = maxlen < 256 ? 0 : maxlen < 1024 ? 1 : 2;
+    switch (w * 2 + (one_len ? 0 : 1)) {
+        case 0: launch_sweep_shape<256, 64>(c, g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail); break;
+        case 1: launch_sweep_shape<256, 1024>(c, g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail); break;
+        case 2: launch_sweep_shape<1024, 64>(c, g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail); break;
+        case 3: launch_sweep_shape<1024, 1024>(c, g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail); break;
+        case 4: launch_sweep_shape<4096, 64>(c, g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail); break;
+        default: launch_sweep_shape<4096, 1024>(c, g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail); break;
     }
     GDS_KERNEL_CHECK();
 }
@@ -862,6 +893,8 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         sp.max_rounds = prm->max_rounds;
     }
     const uint32_t seg_len = (prm && prm->seg_len) ? prm->seg_len : 16384u;
+    const uint32_t algorithm = prm ? prm->algorithm : 0u;
+    if (algorithm > 1) return fail(c, GDS_ERR_ARG, "gds_params.algorithm must be 0 (quasi-MCP) or 1 (minimum cardinality)");
     // scalars of the result start clean (buffers are left alone)
     {
         gds_result keep = *out;
@@ -1320,7 +1353,9 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         for (const VSample& v : hvs)
             max_comp_nodes = std::max(max_comp_nodes, v.nseg == 1 ? v.L + 1 : seg + 1);
         const bool do_solve = !(flags & GDS_NO_SOLVE);
-        const Mf2Plan mf2 = do_solve ? plan_maxflow_sm(n_comp, max_comp_nodes) : Mf2Plan{};
+        if (do_solve && algorithm == 1 && maxlen >= 4096)
+            return fail(c, GDS_ERR_ARG, "algorithm 1 (minimum cardinality) takes reads of up to 4095 positions");
+        const Mf2Plan mf2 = do_solve && algorithm == 0 ? plan_maxflow_sm(n_comp, max_comp_nodes) : Mf2Plan{};
         uint32_t* in_src = c->in_src.get<uint32_t>((size_t)B + 1);
         uint32_t* in1 = c->in1.get<uint32_t>((size_t)n_nodes + 1);
         GDS_CUDA(cudaMemsetAsync(in1, 0xff, ((size_t)n_nodes + 1) * 4, st));
@@ -1335,7 +1370,22 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         // the device (MfTotals)
         const char* dump_comp = getenv("GDS_DUMP_COMP");
         CompStats* cstats = dump_comp ? c->comp_stats.get<CompStats>(n_comp_cap + 1) : nullptr;
-        if (do_solve && n_comp) {
+        if (do_solve && n_comp && algorithm == 1) {
+            // K3': greedy interval multicover, one warp per component, then bundle flows
+            uint32_t* wc = c->work_counter.get<uint32_t>(4);
+            GDS_CUDA(cudaMemsetAsync(wc, 0, 16, st));
+            uint32_t* taken = c->taken.get<uint32_t>((size_t)n_nodes + 2);
+            GDS_CUDA(cudaMemsetAsync(taken, 0, ((size_t)n_nodes + 2) * 4, st));
+            SweepGraph sg{excl, diff, out_ptr, c->bund.as<BundleRec>(), taken};
+            launch_sweep(c, sg, comp_lo, comp_hi, n_comp, n_comp_dev, max_coverage, wc, totals + 5, maxlen,
+                         minlen == maxlen, 12ull * n_nodes + 8ull * B);
+            if (B) {
+                KScope ks("sweep_distribute", 12ull * n_nodes + 24ull * B, st);
+                k_sweep_distribute<<<div_up((long long)n_nodes, 256), 256, 0, st>>>(
+                    taken, in_ptr, in_bid, c->bund.as<BundleRec>(), n_nodes, totals + 5);
+                GDS_KERNEL_CHECK();
+            }
+        } else if (do_solve && n_comp) {
             uint32_t* qF = c->qF.get<uint32_t>(n_nodes);
             uint32_t* qT = c->qT.get<uint32_t>(n_nodes);
             uint32_t* qN = c->qN.get<uint32_t>(n_nodes);
@@ -1459,7 +1509,14 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             out->bfs_levels = ht.bfs_levels;
             out->max_frontier = ht.max_frontier;
             stuck = ht.stuck;
-            if (ht.n_solved != n_comp) stuck += 1;  // a component was never taken: cannot happen
+            if (algorithm == 1) {
+                // the sweep's cover IS a maximum flow (flow 1 on the kept reads, back arcs take the
+                // surplus); htot[5] counts deficits it could not fill and reads it could not place
+                out->flow_value = htot[5] ? -1 : fstar_virtual;
+                stuck = (long long)htot[5];
+            } else if (ht.n_solved != n_comp) {
+                stuck += 1;  // a component was never taken: cannot happen
+            }
         }
         if (do_solve && n_comp && dump_comp) {  // diagnostics only
             std::vector<CompStats> hs(n_comp);

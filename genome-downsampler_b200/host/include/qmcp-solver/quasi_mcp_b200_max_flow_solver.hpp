@@ -15,7 +15,8 @@ namespace qmcp {
 
 class QuasiMcpB200MaxFlowSolver : public Solver {
    public:
-    explicit QuasiMcpB200MaxFlowSolver(int device = 0) : device_(device) {}
+    explicit QuasiMcpB200MaxFlowSolver(int device = 0, uint32_t algorithm = 0)
+        : device_(device), algorithm_(algorithm) {}
     ~QuasiMcpB200MaxFlowSolver() override;
     std::unique_ptr<Solution> solve(uint32_t max_coverage, bam_api::BamApi& bam_api) override;
     bool uses_quality_of_reads() override { return false; }
@@ -63,6 +64,15 @@ class QuasiMcpB200MaxFlowSolver : public Solver {
     gds_result last_{};
     bool verify_ = true;
     uint32_t seg_len_ = 0;
+    uint32_t algorithm_ = 0;  // gds_params.algorithm
+};
+
+// "mcp-b200": the same adapter with gds_params.algorithm = 1 — the kept set of minimum size (what
+// mcp-cpu's min-cost flow with unit read costs returns as its optimal cost,
+// mcp_cpu_cost_scaling_solver.cpp:33-67).  Like mcp-cpu it does not look at read qualities.
+class McpB200SweepSolver : public QuasiMcpB200MaxFlowSolver {
+   public:
+    explicit McpB200SweepSolver(int device = 0) : QuasiMcpB200MaxFlowSolver(device, 1) {}
 };
 
 }  // namespace qmcp

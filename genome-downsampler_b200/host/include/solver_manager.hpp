@@ -13,6 +13,9 @@ class SolverManager {
    public:
     SolverManager() {
         solvers_map_.emplace("quasi-mcp-b200", std::make_unique<qmcp::QuasiMcpB200MaxFlowSolver>());
+        // the fewest reads that keep min(coverage, M) everywhere: mcp-cpu's objective
+        // (mcp_cpu_cost_scaling_solver.cpp:33-67) by the device sweep (gds_params.algorithm = 1)
+        solvers_map_.emplace("mcp-b200", std::make_unique<qmcp::McpB200SweepSolver>());
         for (const auto& kv : solvers_map_) algorithms_names_.push_back(kv.first);
     }
     qmcp::Solver& get(const std::string& name) const { return *solvers_map_.at(name); }

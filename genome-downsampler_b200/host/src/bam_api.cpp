@@ -3,6 +3,7 @@
 #include "bam-api/bam_api.hpp"
 
 #include <algorithm>
+#include <limits>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -143,6 +144,29 @@ void BamApi::apply_pair_filter(const std::vector<std::uint8_t>& pair_pass) {
     }
     for (BAMReadId id = 0; id < bam_record_count_; ++id)
         if (!accepted[id]) filtered_out_reads_.push_back(id);
+    if (amplicon_behaviour_ == AmpliconBehaviour::GRADE) {
+        // GRADE (bam_api.cpp:334-347, 444-454, 480-483): nothing is dropped for its amplicons;
+        // the qualities of the surviving pairs are shifted to start at 0 and a pair that lies
+        // inside one amplicon is lifted by the whole quality range, so a quality-aware solver
+        // prefers it
+        ReadQuality lo = std::numeric_limits<ReadQuality>::max(), hi = 0;
+        const ReadIndex m = kept.get_reads_count();
+        for (ReadIndex i = 0; i < m; ++i) {
+            lo = std::min(lo, kept.qualities[i]);
+            hi = std::max(hi, kept.qualities[i]);
+        }
+        if (hi > 0 && lo < std::numeric_limits<ReadQuality>::max()) {
+            for (ReadIndex i = 0; i + 1 < m; i += 2) {
+                const bool inside = amplicon_set_.member_includes_both(kept.get_read_by_index(i),
+                                                                       kept.get_read_by_index(i + 1));
+                for (ReadIndex j = i; j < i + 2; ++j) {
+                    ReadQuality q = kept.qualities[j] - lo;
+                    if (inside) q += hi - lo;
+                    kept.qualities[j] = q;
+                }
+            }
+        }
+    }
     soa_paired_reads_ = std::move(kept);
     is_aos_loaded_ = false;
     pending_filter_ = false;

@@ -163,6 +163,7 @@ std::unique_ptr<Solution> QuasiMcpB200MaxFlowSolver::solve(uint32_t max_coverage
     last_.pair_pass = pair_pass;
     gds_params prm{};  // zero = the library's defaults
     prm.seg_len = seg_len_;
+    prm.algorithm = algorithm_;
     if (const char* e = std::getenv("GDS_SEG_LEN")) prm.seg_len = static_cast<uint32_t>(std::strtoul(e, nullptr, 0));
     int rc = gds_solve(ctx_, &rd, device_filter ? &flt : nullptr, max_coverage, &prm,
                        verify_ ? GDS_VERIFY : 0, &last_);
@@ -289,6 +290,7 @@ std::vector<std::unique_ptr<Solution>> QuasiMcpB200MaxFlowSolver::solve_batch(
     }
     gds_params prm{};
     prm.seg_len = seg_len_;
+    prm.algorithm = algorithm_;
     if (const char* e = std::getenv("GDS_SEG_LEN")) prm.seg_len = static_cast<uint32_t>(std::strtoul(e, nullptr, 0));
     last_ = gds_result{};
     last_.kept_bitmap = bitmap;

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GDS_ABI_VERSION 5
+#define GDS_ABI_VERSION 6
 
 /* status codes (the reference has none: it logs and exits, cuda_helpers.cuh:13-21) */
 enum {
@@ -111,6 +111,14 @@ typedef struct {
      * the same graph and the same kept set; gds_result.bundle_path tells which one ran.  The
      * environment variable GDS_BUNDLE=sort|direct overrides (benchmarks). */
     uint32_t bundle_mode;
+    /* which solve runs on the graph:
+     *   0  quasi-MCP — maximum flow by push-relabel (quasi_mcp_cpu_max_flow_solver.cpp:11-100);
+     *   1  minimum cardinality — the objective of `mcp-cpu` (mcp_cpu_cost_scaling_solver.cpp:33-67:
+     *      the same network with cost 1 on every read arc), solved exactly by the greedy interval
+     *      multicover sweep (csrc/sweep.cuh).  Same F*, demand vector and capped coverage; the kept
+     *      set is the smallest one (per segment, when a long reference is cut).  Reads of up to 4095
+     *      positions.  rounds / pushes / relabels stay 0. */
+    uint32_t algorithm;
 } gds_params;
 
 /* Results.  Buffers are caller-owned and optional (NULL = not wanted). */

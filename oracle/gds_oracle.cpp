@@ -977,6 +977,85 @@ extern "C" int orc_sync_solve(uint32_t n_samples, const uint64_t* read_off, cons
 }
 
 // =====================================================================================
+// Minimum-cardinality solve on the bundled graph = what `mcp-cpu` computes
+// (mcp_cpu_cost_scaling_solver.cpp:33-67: every read arc costs 1, so the optimum is the fewest reads
+// with cov_S >= min(cov, M)), restated as the deterministic sweep the device runs (csrc/sweep.cuh):
+// per component, positions left to right; reads that have started are pooled BY END NODE; on a
+// deficit take from the farthest end first (greedy interval multicover, exact for this objective);
+// afterwards the reads taken with end node t are handed to the bundles ending at t in in-CSR order
+// (earliest start first — a read of the same end with an earlier start covers a superset).
+// Segmented references: every segment is swept on its own (at most M extra reads per cut).
+// =====================================================================================
+extern "C" int orc_sweep_solve(uint32_t n_samples, const uint64_t* read_off, const uint32_t* ref_len,
+                               const uint32_t* start, const uint32_t* end, uint32_t M,
+                               const orc_sync_params* prm, uint32_t* kept_bitmap,
+                               int32_t* demand_out, uint32_t* cov_out, orc_sync_stats* st) {
+    orc_sync_params P = prm ? *prm : orc_sync_params{64, 150, 1, 0, 0};
+    SyncGraph G;
+    if (build_sync_graph(n_samples, read_off, ref_len, start, end, M, P.seg_len, G) != 0) return -1;
+    const uint32_t nn = G.n_nodes;
+    const uint32_t B = (uint32_t)G.b_s.size();
+    std::vector<uint32_t> taken(nn + 1, 0), pool(nn + 1, 0), f(B, 0);
+    orc_sync_stats out{};
+    for (size_t c = 0; c < G.comp_lo.size(); ++c) {
+        const uint32_t lo = G.comp_lo[c], hi = G.comp_hi[c];
+        uint64_t have = 0;
+        uint32_t top = lo;
+        for (uint32_t p = lo; p < hi; ++p) {
+            have -= taken[p];  // reads whose end node is p stop covering here
+            pool[p] = 0;
+            for (uint32_t b = G.out_ptr[p]; b < G.out_ptr[p + 1]; ++b) {
+                if (G.b_t[b] == p) continue;  // length 0: covers nothing
+                pool[G.b_t[b]] += G.b_mult[b];
+                top = std::max(top, G.b_t[b]);
+            }
+            const uint64_t need = std::min(G.covR[p], M);
+            while (have < need) {
+                while (top > p && pool[top] == 0) --top;
+                if (top <= p) return -2;  // cannot happen: need <= coverage
+                const uint64_t k = std::min<uint64_t>(need - have, pool[top]);
+                pool[top] -= (uint32_t)k;
+                taken[top] += (uint32_t)k;
+                have += k;
+            }
+        }
+        out.flow_value += 0;
+    }
+    for (uint32_t t = 0; t < nn; ++t) {  // hand the reads taken per end node to the bundles ending there
+        uint32_t rem = taken[t];
+        for (uint32_t k = G.in_ptr[t]; k < G.in_ptr[t + 1] && rem; ++k) {
+            const uint32_t b = G.in_bid[k];
+            if (G.b_s[b] == G.b_t[b]) continue;
+            const uint32_t x = std::min(rem, G.b_mult[b]);
+            f[b] = x;
+            rem -= x;
+        }
+        if (rem) return -3;
+    }
+    const uint64_t N = read_off[n_samples];
+    std::fill(kept_bitmap, kept_bitmap + (N + 31) / 32, 0u);
+    uint64_t nk = 0;
+    for (uint32_t b = 0; b < B; ++b)
+        for (uint32_t r = 0; r < f[b]; ++r) {
+            uint32_t i = G.sorted_idx[G.b_first[b] + r];  // a crossing read may be chosen twice
+            if (!(kept_bitmap[i >> 5] >> (i & 31) & 1u)) ++nk;
+            kept_bitmap[i >> 5] |= 1u << (i & 31);
+        }
+    int64_t fstar = 0;
+    for (uint32_t v = 0; v < G.n_onodes; ++v)
+        if (G.odemand[v] < 0) fstar += -(int64_t)G.odemand[v];
+    if (demand_out) std::copy(G.odemand.begin(), G.odemand.end(), demand_out);
+    if (cov_out) std::copy(G.ocov.begin(), G.ocov.end(), cov_out);
+    out.flow_value = fstar;
+    out.fstar = fstar;
+    out.n_kept = nk;
+    out.n_bundles = B;
+    out.n_components = (uint32_t)G.comp_lo.size();
+    if (st) *st = out;
+    return 0;
+}
+
+// =====================================================================================
 // Greedy interval multicover = minimum number of kept reads subject to cov_S >= min(cov, M)
 // (the objective of mcp-cpu: read arcs cost 1, mcp_cpu_cost_scaling_solver.cpp:45-48).
 // Sweep left to right; on a deficit at position p take the available read covering p with the

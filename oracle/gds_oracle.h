@@ -103,6 +103,13 @@ int orc_sync_solve(uint32_t n_samples, const uint64_t* read_off, const uint32_t*
                    const orc_sync_params* prm, uint32_t* kept_bitmap, int32_t* demand_out,
                    uint32_t* cov_out, orc_sync_stats* st);
 
+/* The same inputs and outputs for the minimum-cardinality solve (mcp-cpu's objective,
+ * mcp_cpu_cost_scaling_solver.cpp:33-67) as the deterministic sweep of csrc/sweep.cuh. */
+int orc_sweep_solve(uint32_t n_samples, const uint64_t* read_off, const uint32_t* ref_len,
+                    const uint32_t* start, const uint32_t* end, uint32_t M,
+                    const orc_sync_params* prm, uint32_t* kept_bitmap, int32_t* demand_out,
+                    uint32_t* cov_out, orc_sync_stats* st);
+
 /* ---- min-cardinality optimum (objective of mcp-cpu, mcp_cpu_cost_scaling_solver.cpp:33-67) ---- */
 /* greedy interval multicover; returns number of reads kept, kept[] byte mask */
 uint64_t orc_greedy_multicover(uint64_t n, const uint32_t* start, const uint32_t* end, uint32_t L,

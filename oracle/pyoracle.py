@@ -86,6 +86,8 @@ def lib():
                                  C.POINTER(SyncParams), u32p, C.c_void_p, C.c_void_p,
                                  C.POINTER(SyncStats)]
     L.orc_sync_solve.restype = C.c_int
+    L.orc_sweep_solve.argtypes = L.orc_sync_solve.argtypes
+    L.orc_sweep_solve.restype = C.c_int
     L.orc_greedy_multicover.argtypes = [C.c_uint64, u32p, u32p, C.c_uint32, C.c_uint32, u8p]
     L.orc_greedy_multicover.restype = C.c_uint64
     L.orc_find_pairs_bitmap.argtypes = [C.c_uint64, u32p]
@@ -191,7 +193,12 @@ def ref_solve(start, end, L, M):
     return kept, st
 
 
-def sync_solve(start, end, ref_lens, read_off, M, params=None, want_vectors=False):
+def sweep_solve(start, end, ref_lens, read_off, M, params=None, want_vectors=False):
+    """Minimum-cardinality solve (mcp-cpu's objective) as the device's deterministic sweep."""
+    return sync_solve(start, end, ref_lens, read_off, M, params, want_vectors, _fn="orc_sweep_solve")
+
+
+def sync_solve(start, end, ref_lens, read_off, M, params=None, want_vectors=False, _fn="orc_sync_solve"):
     """Batch-aware deterministic schedule.  Returns (bitmap words, stats[, demand, covR])."""
     ref_lens = np.ascontiguousarray(ref_lens, np.uint32)
     read_off = np.ascontiguousarray(read_off, np.uint64)
@@ -202,12 +209,12 @@ def sync_solve(start, end, ref_lens, read_off, M, params=None, want_vectors=Fals
     nn = int(ref_lens.astype(np.int64).sum() + len(ref_lens))
     dem = np.zeros(nn, np.int32) if want_vectors else None
     cov = np.zeros(nn, np.uint32) if want_vectors else None
-    rc = lib().orc_sync_solve(len(ref_lens), read_off, ref_lens, start, end, M,
+    rc = getattr(lib(), _fn)(len(ref_lens), read_off, ref_lens, start, end, M,
                               C.byref(prm) if prm is not None else None, bm,
                               dem.ctypes.data if want_vectors else None,
                               cov.ctypes.data if want_vectors else None, C.byref(st))
     if rc != 0:
-        raise ValueError("orc_sync_solve rc=%d" % rc)
+        raise ValueError("%s rc=%d" % (_fn, rc))
     if want_vectors:
         return bm, st, dem, cov
     return bm, st

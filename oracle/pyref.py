@@ -72,7 +72,7 @@ def find_pairs(s, e, L, ids):
     return out[:k]
 
 
-def read_bam(s, e, q, l, L, min_len, min_mapq, bed_text=None, tsv_text=None):
+def read_bam(s, e, q, l, L, min_len, min_mapq, bed_text=None, tsv_text=None, grade=False):
     """Runs the reference's BamApi::read_bam on a fake in-memory BAM of these reads."""
     n = len(s)
     os_ = np.zeros(n, np.uint32); oe = np.zeros(n, np.uint32)
@@ -86,7 +86,7 @@ def read_bam(s, e, q, l, L, min_len, min_mapq, bed_text=None, tsv_text=None):
             bp = os.path.join(d, "scheme.bed")
             open(bp, "w").write(bed_text)
             bed = bp.encode()
-            mode = 1
+            mode = 2 if grade else 1
             if tsv_text:
                 tp = os.path.join(d, "pairs.tsv")
                 open(tp, "w").write(tsv_text)

@@ -102,8 +102,9 @@ int64_t ref_read_bam(uint64_t n, const uint32_t* s, const uint32_t* e, const uin
     b.add_min_mapq(min_mapq);
     b.add_min_seq_length(min_len);
     b.add_hts_thread_count(1);
-    if (amp_mode == 1 && bed_path && bed_path[0])
-        b.add_amplicon_filtering(bam_api::AmpliconBehaviour::FILTER, bed_path,
+    if ((amp_mode == 1 || amp_mode == 2) && bed_path && bed_path[0])
+        b.add_amplicon_filtering(amp_mode == 1 ? bam_api::AmpliconBehaviour::FILTER
+                                               : bam_api::AmpliconBehaviour::GRADE, bed_path,
                                  tsv_path ? std::filesystem::path(tsv_path) : std::filesystem::path());
     bam_api::BamApi api("fake.bam", b.build());
     const bam_api::SOAPairedReads& soa = api.get_paired_reads_soa();

@@ -377,3 +377,25 @@ def test_many_chunks_alternate_buffers_and_carry_records(hostlib, O, tmp_path, m
     assert_same_reads(b.reads(), want)
     assert b.filtered_out().tolist() == want_out
     b.close()
+
+
+def test_grade_mode_matches_the_references_read_bam(hostlib, O, R, tmp_path):
+    # AmpliconBehaviour::GRADE (bam_api.cpp:334-347, 444-454, 480-483): no pair is dropped for its
+    # amplicons; qualities are shifted to start at 0 and pairs inside one amplicon are lifted by the
+    # quality range.  The host mirror against the reference's own read_bam (oracle/_ref).
+    bed, tsv = O.artic_scheme()
+    a0, a1 = O.parse_amplicons(bed, tsv)
+    s, e, q, l = O.gen_reads_amplicon(31, 6_000, 30_000, a0, a1)
+    bedp, tsvp = tmp_path / "scheme.bed", tmp_path / "pairs.tsv"
+    bedp.write_text(bed); tsvp.write_text(tsv)
+    path = tmp_path / "grade.bam"
+    hostlib.write_synthetic_bam(path, 30_000, s, e, q.astype(np.uint8), l, coordinate_sorted=False, threads=2)
+    for min_len, min_mapq in ((0, 0), (90, 30)):
+        b = hostlib.BamFile(path, min_len=min_len, min_mapq=min_mapq, bed=bedp, tsv=tsvp,
+                            amplicon_behaviour="grade", threads=2)
+        got = b.reads()
+        b.close()
+        ref = R.read_bam(s, e, q, l, 30_000, min_len, min_mapq, bed, tsv, grade=True)
+        assert np.array_equal(got["start"], ref["start"]) and np.array_equal(got["bam_id"], ref["bam_id"])
+        assert np.array_equal(got["quality"], ref["quality"])
+        assert got["quality"].max() > q.max()  # pairs inside an amplicon were lifted

@@ -595,3 +595,65 @@ def test_zero_length_reads_are_accepted_and_never_kept(solver, O, pkg):
     assert ei.value.code == 2
     with pytest.raises(pkg.GdsError):
         solver.solve(np.array([9], np.uint32), np.array([7], np.uint32), 100, 3)
+
+
+def assert_sweep_parity(O, r, s, e, ref_lens, read_off, M, prm):
+    bm, st, dem, cov = O.sweep_solve(s, e, ref_lens, read_off, M, params=prm[:5], want_vectors=True)
+    assert r.fstar == st.fstar == r.flow_value
+    assert np.array_equal(r.demand, dem) and np.array_equal(r.cov_capped, np.minimum(cov, M))
+    assert r.n_bundles == st.n_bundles and r.n_components == st.n_components
+    assert r.n_kept == st.n_kept and np.array_equal(r.kept_bitmap, bm), "kept set differs from the oracle's sweep"
+    assert r.verify_violations == 0 and r.rounds_total == 0
+    return st
+
+
+def test_minimum_cardinality_sweep(solver, O):
+    # gds_params.algorithm = 1: mcp-cpu's objective (fewest reads) by the device sweep.  Bit-exact
+    # against the oracle's restatement of the sweep; the kept count equals the greedy-multicover
+    # optimum (== network-simplex optimum, tests/test_oracle.py) whenever nothing is segmented; same
+    # F*, demand and capped coverage as the push-relabel solve; never more reads than it keeps.
+    NOSEG = 0xffffffff
+    cases = []
+    for seed, (pairs, L, R, M, shape) in enumerate([(50_000, 30_000, 150, 100, "uniform"),
+                                                    (200_000, 30_000, 150, 3000, "hole"),
+                                                    (30_000, 9_000, 60, 17, "low_sides")]):
+        s, e, _, _ = O.gen_reads(500 + seed, pairs, L, R, shape)
+        cases.append((s, e, [L], np.array([0, len(s)], np.uint64), M))
+    rng = np.random.default_rng(71)
+    s2 = rng.integers(0, 29_000, size=300_000).astype(np.uint32)
+    e2 = (s2 + rng.integers(60, 200, size=300_000)).astype(np.uint32)  # 140 read lengths
+    cases.append((s2, e2, [30_000], np.array([0, len(s2)], np.uint64), 80))
+    s3 = rng.integers(0, 5_000, size=60_000).astype(np.uint32)
+    e3 = np.minimum(s3 + rng.integers(1, 900, size=60_000) - 1, 4_999).astype(np.uint32)  # ring 1024
+    cases.append((s3, e3, [5_000], np.array([0, len(s3)], np.uint64), 25))
+    for s, e, Ls, off, M in cases:
+        for bmode in (0, 1):
+            prm = (64, 150, 1, 0, NOSEG, bmode, 1)
+            r = solver.solve(s, e, Ls, M, read_off=off, params=prm, verify=True, want_vectors=True)
+            st = assert_sweep_parity(O, r, s, e, Ls, off, M, prm)
+        _, nopt = O.greedy_multicover(s, e, Ls[0], M)
+        assert r.n_kept == nopt
+        r0 = solver.solve(s, e, Ls, M, read_off=off, params=(64, 150, 1, 0, NOSEG), verify=True,
+                          want_vectors=True)
+        assert r0.fstar == r.fstar and np.array_equal(r0.demand, r.demand) and r.n_kept <= r0.n_kept
+    # a batch of samples, zero-length reads, and a segmented reference (every segment swept alone)
+    parts = [O.gen_reads(900 + k, 30_000 + 64 * k, 30_000, 150) for k in range(5)]
+    s = np.concatenate([p[0] for p in parts]).copy(); e = np.concatenate([p[1] for p in parts]).copy()
+    e[::997] = s[::997] - np.uint32(1)
+    off = np.cumsum([0] + [len(p[0]) for p in parts]).astype(np.uint64)
+    prm = (64, 150, 1, 0, NOSEG, 0, 1)
+    r = solver.solve(s, e, [30_000] * 5, 60, read_off=off, params=prm, verify=True, want_vectors=True,
+                     len_hint=None)
+    assert_sweep_parity(O, r, s, e, [30_000] * 5, off, 60, prm)
+    s4, e4, _, _ = O.gen_reads(33, 150_000, 150_000, 150)
+    prm = (64, 150, 1, 0, 8192, 0, 1)
+    r = solver.solve(s4, e4, 150_000, 40, params=prm, verify=True, want_vectors=True, len_hint=(150, 150))
+    st = assert_sweep_parity(O, r, s4, e4, [150_000], [0, len(s4)], 40, prm)
+    _, nopt = O.greedy_multicover(s4, e4, 150_000, 40)
+    assert nopt <= r.n_kept <= nopt + 40 * (st.n_components - 1)  # at most M reads per cut
+    # too long a read for the shared-memory ring: refused, not mis-solved
+    import pytest as _pt
+    from __graft_entry__ import load_package
+    with _pt.raises(load_package().GdsError):
+        solver.solve(np.array([0], np.uint32), np.array([4999], np.uint32), 6000, 1,
+                     params=(64, 150, 1, 0, NOSEG, 0, 1))

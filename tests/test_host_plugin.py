@@ -59,6 +59,20 @@ def test_plugin_solve_through_solver_manager(hostlib, O):
 
 
 @pytest.mark.gpu
+def test_mcp_b200_plugin_returns_the_minimum_cover(hostlib, O):
+    # SolverManager.get("mcp-b200"): the fewest reads with min(coverage, M) kept everywhere — what
+    # mcp-cpu's min-cost flow (unit read costs) reports as its optimal cost
+    for seed, pairs, L, M, shape in ((5, 40_000, 30_000, 100, "uniform"), (6, 20_000, 9_000, 700, "hole")):
+        s, e, q, l = O.gen_reads(seed, pairs, L, 150, shape)
+        ids = hostlib.plugin_solve("mcp-b200", s, e, L, M)
+        mask = np.zeros(len(s), np.uint8); mask[ids] = 1
+        cin = O.coverage_fast(s, e, L); cout = O.coverage_fast(s, e, L, mask)
+        assert np.all(np.minimum(cin, M) <= cout)
+        _, nopt = O.greedy_multicover(s, e, L, M)
+        assert len(ids) == nopt and len(ids) <= len(hostlib.plugin_solve("quasi-mcp-b200", s, e, L, M))
+
+
+@pytest.mark.gpu
 def test_plugin_solve_batch_equals_one_by_one(hostlib, O):
     # QuasiMcpB200MaxFlowSolver::solve_batch: ragged samples (different sizes, shapes and read
     # lengths, so the batch travels as 32-bit columns) and a fixed-length batch (compact transport);
