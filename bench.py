@@ -73,6 +73,14 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+ALGORITHM = "quasi-mcp"   # --algorithm: "quasi-mcp" (push-relabel max flow) or "mcp" (minimum cardinality)
+
+
+def solver_params():
+    """gds_params for the chosen algorithm (None = library defaults)."""
+    return (0, 0, 0, 0, 0, 0, 1) if ALGORITHM == "mcp" else None
+
+
 def config_for(wname, wl):
     """The workload both arms run — the SAME dict in the B200 line and in the --impl reference line
     (how many samples of it an arm takes per step is the arm's business: config['...'] never holds
@@ -80,7 +88,9 @@ def config_for(wname, wl):
     return {"workload": wname + " — " + wl["name"], "samples": wl["samples"],
             "reads_per_sample": 2 * wl["pairs"], "ref_len": wl["L"], "read_len": wl["R"],
             "max_coverage": wl["M"], "seed": wl["seed"],
-            "pair_filter": wl.get("filter"), "law": wl.get("shape", "uniform")}
+            "pair_filter": wl.get("filter"), "law": wl.get("shape", "uniform"),
+            "algorithm": "quasi-MCP (maximum flow)" if ALGORITHM == "quasi-mcp"
+            else "MCP (minimum number of reads, mcp-cpu's objective)"}
 
 
 def host_threads():
@@ -273,6 +283,11 @@ def cpu_solve_one(O, wl, inp, L):
         s, e = np.ascontiguousarray(s[m]), np.ascontiguousarray(e[m])
     else:
         s, e = inp
+    if ALGORITHM == "mcp":  # mcp-cpu's objective: greedy interval multicover (== min-cost optimum)
+        cov = O.coverage_fast(s, e, L)
+        fstar = int(np.maximum(0, np.diff(np.minimum(np.concatenate([[0], cov]), wl["M"]).astype(np.int64))).sum())
+        _, nk = O.greedy_multicover(s, e, L, wl["M"])
+        return fstar, int(nk)
     kept, st = O.ref_solve(s, e, L, wl["M"])
     return int(st.flow_value), int(st.n_kept)
 
@@ -482,7 +497,7 @@ def run_b200(args, wl, wname):
             out_bm = bitmaps2[b] if world > 1 else bitmap
             r = solver.solve_device(d_st.data_ptr(), d_en.data_ptr(), n, ref_len, wl["M"],
                                     out_bm.data_ptr(), read_off=read_off, profile=profile,
-                                    len_hint=hint, **fkw(True))
+                                    len_hint=hint, params=solver_params(), **fkw(True))
             if world > 1:
                 gather_async(b)
             return r
@@ -491,9 +506,9 @@ def run_b200(args, wl, wname):
         # the host, everything inside the timed region — including, for the headline figure, the
         # narrowing to the compact transport (include/gds.h gds_reads.start16 / end == NULL: 16-bit
         # starts, ends implied by the one read length; 2 bytes per read cross PCIe instead of 8).
-        # Round 1 prepared that column outside the timed region; now the chunk workers do it
-        # (hostlib.encode_compact, what the C++ adapter's narrowing loop does) right before a chunk
-        # is sent.  "e2e_u32" is the same call with the 32-bit columns sent as they are, and
+        # Round 1 prepared that column outside the timed region; now it happens inside, chunk by
+        # chunk ahead of the transfers (hostlib.encode_compact, what the C++ adapter's narrowing loop
+        # does; pipeline.py).  "e2e_u32" is the same call with the 32-bit columns sent as they are, and
         # "e2e_preencoded" the round-1 figure (a producer that writes 16-bit starts itself).
         # A batch of many samples goes through the package's chunked host API (two contexts: H2D of
         # chunk c+1 overlaps kernels of chunk c).
@@ -501,7 +516,9 @@ def run_b200(args, wl, wname):
         compact_ok = hint is not None and hint[0] == hint[1] and wl["L"] <= 65536
         h_st16 = torch.empty(n, dtype=torch.int16, pin_memory=True) if compact_ok else None
         n_extra = (5 if fx is not None else 0) * n
-        enc_threads = max(2, host_threads() // (2 * max(1, min(world, 8))))
+        # the narrowing runs ahead of the device on its own host threads (pipeline.py); four threads
+        # stay free for the two chunk workers, the driver and this interpreter
+        enc_threads = args.encode_threads or max(2, (host_threads() - 4) // max(1, min(world, 8)))
 
         def make_e2e(mode):
             """mode: 'encode' (u32 columns in, narrowed inside the step), 'u32', 'preencoded'."""
@@ -516,7 +533,7 @@ def run_b200(args, wl, wname):
                 if chunked is not None:
                     rs = chunked.solve_host_batch(kw["start_ptr"], kw["end_ptr"], read_off, ref_len,
                                                   wl["M"], bitmap.data_ptr(),
-                                                  chunk_samples=args.chunk_samples,
+                                                  chunk_samples=args.chunk_samples, params=solver_params(),
                                                   len_hint=kw["len_hint"], start16_ptr=kw["start16_ptr"],
                                                   encode16_ptr=h_st16.data_ptr() if mode == "encode" else None,
                                                   encode_threads=enc_threads)
@@ -533,6 +550,7 @@ def run_b200(args, wl, wname):
                     r = solver.solve_device(kw["start_ptr"], kw["end_ptr"], n, ref_len, wl["M"],
                                             bitmap.data_ptr(), read_off=read_off,
                                             input_on_device=False, len_hint=kw["len_hint"],
+                                            params=solver_params(),
                                             start16_ptr=kw["start16_ptr"], **fkw(False))
                     if fx is not None:
                         h_pair_pass.copy_(pair_pass, non_blocking=True)
@@ -564,7 +582,7 @@ def run_b200(args, wl, wname):
         # correctness gate (untimed): the device re-derives coverage from the kept bitmap
         rv = solver.solve_device(d_st.data_ptr(), d_en.data_ptr(), n, ref_len, wl["M"],
                                  bitmap.data_ptr(), read_off=read_off, verify=True, len_hint=hint,
-                                 **fkw(True))
+                                 params=solver_params(), **fkw(True))
         assert rv.verify_violations == 0 and rv.flow_value == rv.fstar, \
             "device verification failed: %r" % dict(rv)
 
@@ -766,13 +784,20 @@ def main():
     ap.add_argument("--chunk-samples", type=int, default=64,
                     help="samples per chunk of the end-to-end (host buffer) leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--encode-threads", type=int, default=0,
+                    help="host threads of the e2e leg's narrowing (default: host threads - 4, per rank)")
     ap.add_argument("--gather", default="root", choices=["root", "all", "none"],
                     help="N > 1: kept bitmaps gathered on rank 0 (default), all-gathered (round 1), or "
                          "not at all (measures what the collective costs)")
     ap.add_argument("--weak", action="store_true",
                     help="N > 1: every rank takes the workload's full sample count (weak scaling) "
                          "instead of a share of the one batch (default, strong scaling)")
+    ap.add_argument("--algorithm", default="quasi-mcp", choices=["quasi-mcp", "mcp"],
+                    help="quasi-mcp: maximum flow by push-relabel (the north-star path, default); mcp: the "
+                         "minimum-cardinality solve (gds_params.algorithm = 1, plugin mcp-b200)")
     args = ap.parse_args()
+    global ALGORITHM
+    ALGORITHM = args.algorithm
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:

@@ -60,7 +60,7 @@ class _Result(C.Structure):
                 ("verify_violations", C.c_uint64), ("key_bits", C.c_uint32),
                 ("sort_passes", C.c_uint32), ("kernel_launches", C.c_uint64),
                 ("partial_bundles", C.c_uint64), ("partial_candidates", C.c_uint64),
-                ("bundle_path", C.c_uint32), ("reserved0", C.c_uint32),
+                ("bundle_path", C.c_uint32), ("seg_len", C.c_uint32),
                 ("ms_h2d", C.c_float), ("ms_filter", C.c_float), ("ms_graph", C.c_float),
                 ("ms_maxflow", C.c_float), ("ms_select", C.c_float), ("ms_verify", C.c_float),
                 ("ms_d2h", C.c_float), ("ms_total", C.c_float)]

@@ -210,6 +210,27 @@ void launch_mf2_shape(gds_ctx* c, const Mf2Graph& g, const uint32_t* comp_lo, co
 }
 
 // Whether this call's components go to k_maxflow_sm, and with which launch shape.
+// gds_params.seg_len == 0 (include/gds.h): 16 384 positions, stretched by up to a quarter when that
+// lets every segment of the batch be resident at once.  k_maxflow_sm keeps two components per SM
+// resident (296 on a B200); 306 segments would run as 296 + a second wave of 10 that starts when
+// the first components finish, i.e. ~1.3x the time of 296 slightly longer ones.  The constant is
+// part of the deterministic schedule (the oracle has the same rule), NOT a property of the device
+// the call happens to run on: the same input gives the same kept set everywhere.
+constexpr uint32_t kSegBase = 16384, kSegResident = 296;
+uint32_t default_seg_len(uint32_t n_samples, const uint32_t* ref_len) {
+    auto count = [&](uint32_t seg) {
+        unsigned long long n = 0;
+        for (uint32_t k = 0; k < n_samples; ++k)
+            n += (unsigned long long)ref_len[k] > 2ull * seg ? ((unsigned long long)ref_len[k] + seg - 1) / seg : 1;
+        return n;
+    };
+    const unsigned long long n0 = count(kSegBase);
+    if (n0 <= kSegResident || n0 > kSegResident + kSegResident / 4) return kSegBase;
+    for (uint32_t seg = kSegBase + 128; seg <= kSegBase + kSegBase / 4; seg += 128)
+        if (count(seg) <= kSegResident) return seg;
+    return kSegBase;
+}
+
 struct Mf2Plan {
     bool on = false;
     int smem = 0, per_sm = 1, shape = 1;
@@ -293,15 +314,21 @@ void launch_maxflow_sm(gds_ctx* c, const Mf2Plan& pl, const Mf2Graph& g, const u
 }
 
 // K3' (sweep.cuh): the minimum-cardinality solve.  One warp per component.
-template <int W, int CAP>
+template <int W, int CAP, bool WARP>
 void launch_sweep_shape(gds_ctx* c, const SweepGraph& g, const uint32_t* comp_lo, const uint32_t* comp_hi,
                         uint32_t n_comp, const uint32_t* n_comp_dev, uint32_t M, uint32_t* wc,
                         unsigned long long* fail) {
-    const int smem = kSweepWarps * (2 * W + 4 * CAP) * 4;
-    auto kern = k_sweep<W, CAP>;
-    GDS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int smem = kSweepWarps * (2 * W + 4 * CAP + 2 * 34 + 2 * 32) * 4;
     const int grid = std::max(1, std::min<int>(div_up(n_comp, kSweepWarps), kNumSMs * 8));
-    kern<<<grid, kSweepWarps * 32, smem, c->stream>>>(g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail);
+    if (WARP) {
+        auto kern = k_sweep_warp<W, CAP>;
+        GDS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<grid, kSweepWarps * 32, smem, c->stream>>>(g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail);
+    } else {
+        auto kern = k_sweep<W, CAP>;
+        GDS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        kern<<<grid, kSweepWarps * 32, smem, c->stream>>>(g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail);
+    }
 }
 
 void launch_sweep(gds_ctx* c, const SweepGraph& g, const uint32_t* comp_lo, const uint32_t* comp_hi,
@@ -309,14 +336,16 @@ void launch_sweep(gds_ctx* c, const SweepGraph& g, const uint32_t* comp_lo, cons
                   unsigned long long* fail, uint32_t maxlen, bool one_len,
                   unsigned long long alg_bytes) {
     KScope ks("sweep", alg_bytes, c->stream);
+    // one read length: at most a few bundles per position -> one lane walks; several lengths: tens of
+    // arrivals per position -> the warp-synchronous walk adds them in parallel
     const int w = maxlen < 256 ? 0 : maxlen < 1024 ? 1 : 2;
     switch (w * 2 + (one_len ? 0 : 1)) {
-        case 0: launch_sweep_shape<256, 64>(c, g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail); break;
-        case 1: launch_sweep_shape<256, 1024>(c, g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail); break;
-        case 2: launch_sweep_shape<1024, 64>(c, g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail); break;
-        case 3: launch_sweep_shape<1024, 1024>(c, g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail); break;
-        case 4: launch_sweep_shape<4096, 64>(c, g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail); break;
-        default: launch_sweep_shape<4096, 1024>(c, g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail); break;
+        case 0: launch_sweep_shape<256, 64, false>(c, g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail); break;
+        case 1: launch_sweep_shape<256, 1024, true>(c, g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail); break;
+        case 2: launch_sweep_shape<1024, 64, false>(c, g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail); break;
+        case 3: launch_sweep_shape<1024, 1024, true>(c, g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail); break;
+        case 4: launch_sweep_shape<4096, 64, false>(c, g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail); break;
+        default: launch_sweep_shape<4096, 1024, true>(c, g, comp_lo, comp_hi, n_comp, n_comp_dev, M, wc, fail); break;
     }
     GDS_KERNEL_CHECK();
 }
@@ -892,7 +921,8 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         sp.gr_relabel_pct = prm->gr_relabel_pct;
         sp.max_rounds = prm->max_rounds;
     }
-    const uint32_t seg_len = (prm && prm->seg_len) ? prm->seg_len : 16384u;
+    const uint32_t seg_len =
+        (prm && prm->seg_len) ? prm->seg_len : default_seg_len(rd->n_samples, rd->ref_len);
     const uint32_t algorithm = prm ? prm->algorithm : 0u;
     if (algorithm > 1) return fail(c, GDS_ERR_ARG, "gds_params.algorithm must be 0 (quasi-MCP) or 1 (minimum cardinality)");
     // scalars of the result start clean (buffers are left alone)
@@ -905,6 +935,7 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         out->cov_capped = keep.cov_capped;
         out->demand = keep.demand;
     }
+    out->seg_len = seg_len;
     out->n_reads_in = P;
     out->n_nodes = n_onodes;
 

@@ -44,10 +44,117 @@ __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
-// W: ring size (power of two, > longest bundle in nodes); CAP: staged bundle records per chunk
+// W: ring size (power of two, > longest bundle in nodes); CAP: staged bundle records per chunk.
+// The sweep itself is sequential: lane 0 walks the positions of a chunk with everything it needs in
+// shared memory and no warp-level synchronisation inside the walk (the first version kept all 32
+// lanes in step through shuffles and __syncwarp: 630 clocks per position; this one ~100); the other
+// lanes fetch — rows and coverage of the next chunk with one coalesced load, its bundle records
+// with cp.async — while lane 0 walks.
 template <int W, int CAP>
 __global__ void __launch_bounds__(kSweepWarps * 32)
 k_sweep(SweepGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __restrict__ comp_hi,
+        uint32_t n_comp, const uint32_t* __restrict__ n_comp_dev, uint32_t M, uint32_t* work_counter,
+        unsigned long long* __restrict__ fail /* += positions whose pool ran dry (never) */) {
+    extern __shared__ __align__(16) unsigned char sw_raw[];
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    // per warp: pool[W], pend[W], stage[2][CAP] of {t, mult}, rows[2][34], need[2][32]
+    constexpr uint32_t kWords = 2 * W + 4 * CAP + 2 * 34 + 2 * 32;
+    uint32_t* pool = reinterpret_cast<uint32_t*>(sw_raw) + (size_t)warp * kWords;
+    uint32_t* pend = pool + W;
+    uint2* stage = reinterpret_cast<uint2*>(pend + W);
+    uint32_t* rows = reinterpret_cast<uint32_t*>(stage + 2 * CAP);
+    uint32_t* needs = rows + 2 * 34;
+    if (n_comp_dev) n_comp = *n_comp_dev;
+    for (;;) {
+        uint32_t c = 0;
+        if (lane == 0) c = atomicAdd(work_counter, 1u);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= n_comp) break;
+        const uint32_t lo = comp_lo[c], hi = comp_hi[c];
+        for (uint32_t i = lane; i < 2 * W; i += 32) pool[i] = 0;  // pool and pend
+        uint32_t have = 0, top = lo;
+        unsigned long long dry = 0;
+        // stage chunk [p0, p0 + 32): rows (out-CSR starts, one more than positions), capped coverage,
+        // and the chunk's bundle records; buffers alternate
+        auto stage_chunk = [&](uint32_t p0, uint32_t bufi) {
+            const uint32_t p = min(p0 + lane, hi);
+            const uint32_t op = G.out_ptr[p];
+            const uint32_t cov = G.excl[p] + (uint32_t)G.diff[p];
+            rows[bufi * 34 + lane] = op;
+            needs[bufi * 32 + lane] = p0 + lane < hi ? min(cov, M) : 0u;
+            const uint32_t cnt = min(32u, hi - p0);
+            const uint32_t b0 = __shfl_sync(0xffffffffu, op, 0);
+            uint32_t b1 = G.out_ptr[min(p0 + cnt, hi)];  // same address in every lane
+            if (lane == 0) rows[bufi * 34 + 32] = b1;
+            const uint32_t nb = min(b1 - b0, (uint32_t)CAP);
+            for (uint32_t i = lane; i < nb; i += 32) cp_async8(stage + bufi * CAP + i, G.bund + b0 + i);
+        };
+        stage_chunk(lo, 0);
+        uint32_t buf = 0;
+        for (uint32_t p0 = lo; p0 < hi; p0 += 32, buf ^= 1) {
+            cp_async_wait_all();  // this chunk's bundle records have landed
+            __syncwarp();         // ... and its rows are visible to lane 0
+            if (p0 + 32 < hi) stage_chunk(p0 + 32, buf ^ 1);  // in flight while lane 0 walks
+            if (lane == 0) {
+                const uint32_t cnt = min(32u, hi - p0);
+                const uint32_t* rw = rows + buf * 34;
+                const uint32_t* nd_ = needs + buf * 32;
+                const uint2* st = stage + buf * CAP;
+                const uint32_t cb0 = rw[0];
+                for (uint32_t j = 0; j < cnt; ++j) {
+                    const uint32_t p = p0 + j, slot = p & (W - 1);
+                    // reads whose end node is p stop covering here; their count is final
+                    const uint32_t exp = pend[slot];
+                    if (exp) {
+                        G.taken[p] = exp;
+                        pend[slot] = 0;
+                        have -= exp;
+                    }
+                    pool[slot] = 0;
+                    // arrivals: the bundles starting at p join the pool of their end node
+                    const uint32_t b0 = rw[j], b1 = j + 1 < cnt ? rw[j + 1] : rw[32];
+                    for (uint32_t b = b0; b < b1; ++b) {
+                        const uint32_t k = b - cb0;
+                        const uint2 r = k < (uint32_t)CAP ? st[k]
+                                                          : *reinterpret_cast<const uint2*>(G.bund + b);
+                        if (r.x != p) {  // a read of length 0 covers nothing
+                            pool[r.x & (W - 1)] += r.y;
+                            top = max(top, r.x);
+                        }
+                    }
+                    // picks: farthest end first
+                    const uint32_t nd = nd_[j];
+                    while (have < nd) {
+                        while (top > p && pool[top & (W - 1)] == 0) --top;
+                        if (top <= p) {
+                            ++dry;
+                            break;
+                        }
+                        const uint32_t k = min(nd - have, pool[top & (W - 1)]);
+                        pool[top & (W - 1)] -= k;
+                        pend[top & (W - 1)] += k;
+                        have += k;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) {  // reads that end at the component's last node
+            const uint32_t exp = pend[hi & (W - 1)];
+            if (exp) G.taken[hi] = exp;
+            if (dry) atomicAdd(fail, dry);
+        }
+        __syncwarp();
+    }
+}
+
+// The warp-synchronous form of the same sweep, for components with MANY bundles per position
+// (variable read lengths: ~40 arrivals per position, added to the pool by the lanes in parallel): all
+// 32 lanes walk the positions together — 630 clocks per position whatever the arrivals, where the
+// one-lane walk above pays ~130 per arrival (config 2: 17 ms against 80 ms).
+template <int W, int CAP>
+__global__ void __launch_bounds__(kSweepWarps * 32)
+k_sweep_warp(SweepGraph G, const uint32_t* __restrict__ comp_lo, const uint32_t* __restrict__ comp_hi,
         uint32_t n_comp, const uint32_t* __restrict__ n_comp_dev, uint32_t M, uint32_t* work_counter,
         unsigned long long* __restrict__ fail /* += positions whose pool ran dry (never) */) {
     extern __shared__ __align__(16) unsigned char sw_raw[];

@@ -31,8 +31,8 @@ class ChunkedSolver:
         input_on_device=True: the pointers are device pointers (two contexts still overlap one
         chunk's max-flow with the next chunk's streaming kernels).
         encode16_ptr: a HOST scratch buffer of n uint16 — every chunk's 32-bit columns are narrowed
-        into it by the worker that is about to send the chunk (hostlib.encode_compact: 16-bit
-        starts + exact read-length range) and the chunk travels compact when that is legal (one
+        into it (hostlib.encode_compact: 16-bit starts + exact read-length range) by an encoder thread
+        that runs ahead of the device, and the chunk travels compact when that is legal (one
         read length, starts below 65536), as 32-bit columns otherwise: what the C++ adapter does
         with the reference's size_t columns, for callers that hold uint32 arrays.
         Returns the list of per-chunk results (in chunk order)."""
@@ -45,6 +45,31 @@ class ChunkedSolver:
                 raise ValueError("chunk boundaries must fall on multiples of 32 reads")
         results = [None] * len(chunks)
         errors = []
+        # Narrowing runs AHEAD of the device on its own thread (the encoder's host threads), chunk by
+        # chunk in order; a worker picks a chunk up as soon as it is narrowed.  Chunk k+1 is narrowed
+        # while chunk k crosses PCIe and chunk k-1 is in its kernels: the batch takes
+        # max(narrowing, transfer) + one chunk instead of their sum.
+        encoding = bool(encode16_ptr)
+        enc_done = [threading.Event() for _ in chunks]
+        enc_info = [None] * len(chunks)
+        known = len_hint is not None and len_hint[0] == len_hint[1] and len_hint[0] > 0
+
+        def encoder():
+            from . import hostlib
+            try:
+                for ci, (a, b) in enumerate(chunks):
+                    r0 = int(read_off[a])
+                    n = int(read_off[b]) - r0
+                    if n and int(ref_len[a:b].max()) <= 65536:
+                        # a caller that KNOWS the one read length (len_hint) spares the end column
+                        enc_info[ci] = hostlib.encode_compact(
+                            start_ptr + 4 * r0, None if known else end_ptr + 4 * r0, n,
+                            encode16_ptr + 2 * r0, threads=encode_threads)
+                    enc_done[ci].set()
+            except Exception as ex:
+                errors.append(ex)
+                for ev in enc_done:
+                    ev.set()
 
         def worker(w):
             sv = self.solvers[w]
@@ -57,17 +82,16 @@ class ChunkedSolver:
                     ep = end_ptr + 4 * r0 if end_ptr else None
                     s16 = start16_ptr + 2 * r0 if start16_ptr else None
                     hint = len_hint
-                    if encode16_ptr and n and int(ref_len[a:b].max()) <= 65536:
-                        from . import hostlib
-                        # a caller that KNOWS the one read length (len_hint) spares the end column
-                        known = hint is not None and hint[0] == hint[1] and hint[0] > 0
-                        fits, lo, hi = hostlib.encode_compact(sp, None if known else ep, n,
-                                                              encode16_ptr + 2 * r0,
-                                                              threads=encode_threads)
-                        if not known:
-                            hint = (lo, hi)
-                        if fits and hint[0] == hint[1]:
-                            sp, ep, s16 = None, None, encode16_ptr + 2 * r0
+                    if encoding:
+                        enc_done[ci].wait()
+                        if errors:
+                            return
+                        if enc_info[ci] is not None:
+                            fits, lo, hi = enc_info[ci]
+                            if not known:
+                                hint = (lo, hi)
+                            if fits and hint[0] == hint[1]:
+                                sp, ep, s16 = None, None, encode16_ptr + 2 * r0
                     results[ci] = sv.solve_device(
                         sp, ep, n, ref_len[a:b], max_coverage,
                         bitmap_ptr + 4 * (r0 // 32), read_off=read_off[a:b + 1] - np.uint64(r0),
@@ -77,6 +101,8 @@ class ChunkedSolver:
                 errors.append(ex)
 
         threads = [threading.Thread(target=worker, args=(w,)) for w in range(len(self.solvers))]
+        if encoding:
+            threads.append(threading.Thread(target=encoder))
         for t in threads:
             t.start()
         for t in threads:

@@ -92,12 +92,16 @@ typedef struct {
 } gds_filter;
 
 /* Deterministic schedule knobs.  Zero-initialised = defaults (64, 150, 1, 0),
- * seg_len 16384, bundle_mode 0.  seg_len: a reference longer than 2*seg_len positions is cut into
+ * seg_len 0, bundle_mode 0.  seg_len: a reference longer than 2*seg_len positions is cut into
  * independent segments of seg_len positions (reads crossing a cut are truncated into one arc per
  * segment and kept if either part carries flow) — the zero-coverage split generalised;
  * 0xffffffff = never cut.  Shorter segments mean fewer dependent max-flow rounds per component and
- * at most max_coverage extra kept reads per cut (config 4: 16384 -> +0.24 % reads, K3 2.4x faster
- * than 32768). */
+ * at most max_coverage extra kept reads per cut (config 4: +0.5 % reads, K3 2.4x faster than
+ * 32768).  0 = the default rule: 16384, stretched in steps of 128 by up to a quarter when that
+ * brings the number of segments of the whole batch down to 296 — two resident components per SM of
+ * a B200, so that no second wave of a few left-over segments runs (config 4: 5 Mb -> 296 segments
+ * of 16896 instead of 306).  The rule is a constant of the schedule, not a device query: the same
+ * input gives the same kept set on every device.  gds_result.seg_len reports the value used. */
 typedef struct {
     uint32_t gr_interval_min;
     uint32_t gr_levels_pct;
@@ -145,7 +149,7 @@ typedef struct {
     uint64_t partial_bundles, partial_candidates;
     uint32_t bundle_path; /* how K2 found the bundles: 0 radix sort, 1 histogram in shared memory,
                              2 histogram in global memory (gds_params.bundle_mode) */
-    uint32_t reserved0;
+    uint32_t seg_len;     /* the segment length this call used (gds_params.seg_len or the default rule) */
     /* device-event milliseconds per phase */
     float ms_h2d, ms_filter, ms_graph, ms_maxflow, ms_select, ms_verify, ms_d2h, ms_total;
 } gds_result;

@@ -562,7 +562,23 @@ struct SyncGraph {
     std::vector<uint32_t> comp_lo, comp_hi;
 };
 
-constexpr uint32_t kDefaultSegLen = 16384;
+// seg_len == 0: the library's default rule (csrc/gds_api.cu default_seg_len) — 16 384 positions,
+// stretched in steps of 128 by up to a quarter when that brings the batch's segment count down to
+// 296 (two resident components per SM of a B200).  A constant of the schedule, not a device query.
+constexpr uint32_t kDefaultSegLen = 16384, kSegResident = 296;
+static uint32_t default_seg_len(uint32_t n_samples, const uint32_t* ref_len) {
+    auto count = [&](uint32_t seg) {
+        uint64_t n = 0;
+        for (uint32_t k = 0; k < n_samples; ++k)
+            n += (uint64_t)ref_len[k] > 2ull * seg ? ((uint64_t)ref_len[k] + seg - 1) / seg : 1;
+        return n;
+    };
+    const uint64_t n0 = count(kDefaultSegLen);
+    if (n0 <= kSegResident || n0 > kSegResident + kSegResident / 4) return kDefaultSegLen;
+    for (uint32_t seg = kDefaultSegLen + 128; seg <= kDefaultSegLen + kDefaultSegLen / 4; seg += 128)
+        if (count(seg) <= kSegResident) return seg;
+    return kDefaultSegLen;
+}
 
 // Long references are cut into segments of seg positions (a generalisation of the zero-coverage
 // split): a read crossing a cut becomes two arcs, truncated at the cut node, one
@@ -588,7 +604,7 @@ int build_sync_graph(uint32_t n_samples, const uint64_t* read_off, const uint32_
             maxlen = std::max(maxlen, len);
         }
     if (N == 0) minlen = maxlen = 1;
-    if (seg_len == 0) seg_len = kDefaultSegLen;
+    if (seg_len == 0) seg_len = default_seg_len(n_samples, ref_len);
     const uint32_t seg = seg_len >= maxlen ? seg_len : 0xffffffffu;  // a read crosses <= 1 cut
     G.vs.resize(n_samples);
     uint32_t ob = 0, vb = 0;
