@@ -39,7 +39,8 @@ class _Filter(C.Structure):
 class _Params(C.Structure):
     _fields_ = [("gr_interval_min", C.c_uint32), ("gr_levels_pct", C.c_uint32),
                 ("gr_relabel_pct", C.c_uint32), ("max_rounds", C.c_uint32),
-                ("seg_len", C.c_uint32), ("bundle_mode", C.c_uint32), ("algorithm", C.c_uint32)]
+                ("seg_len", C.c_uint32), ("bundle_mode", C.c_uint32), ("algorithm", C.c_uint32),
+                ("schedule", C.c_uint32)]
 
 
 class _KStat(C.Structure):

@@ -233,15 +233,18 @@ uint32_t default_seg_len(uint32_t n_samples, const uint32_t* ref_len) {
 
 struct Mf2Plan {
     bool on = false;
+    bool classic_ok = false;  // components outside the express schedule may run in k_maxflow_sm too
     int smem = 0, per_sm = 1, shape = 1;
     uint32_t qcap = 0;
     bool optr = false;
 };
 
-Mf2Plan plan_maxflow_sm(uint32_t n_comp, uint32_t max_comp_nodes) {
+Mf2Plan plan_maxflow_sm(uint32_t n_comp, uint32_t max_comp_nodes, bool express_possible) {
     Mf2Plan pl;
     const char* env = getenv("GDS_MF");  // =global: the round-1 kernel only; =sm: this one whenever it fits
-    if (env && !strcmp(env, "global")) return pl;
+    // (components of the express schedule exist only in k_maxflow_sm: with them in the call the
+    //  kernel always runs, and GDS_MF=global is ignored)
+    if (env && !strcmp(env, "global") && !express_possible) return pl;
     // shared memory per CTA: header + 4 staged queues + the node arrays of the largest component
     // that should still fit.  Prefer the out-CSR cache unless leaving it out lets all components
     // be resident at once (a batch of segments) where they otherwise would not be.
@@ -280,7 +283,9 @@ Mf2Plan plan_maxflow_sm(uint32_t n_comp, uint32_t max_comp_nodes) {
     // samples of 180 KB each, one per SM, four waves: 3.2 ms) is faster on k_maxflow, whose state
     // lives in L2/HBM but which runs every component concurrently (1.84 ms).
     const bool forced = env && !strcmp(env, "sm");
-    if (!forced && (unsigned long long)n_comp * 2 > 3ull * kNumSMs * per_sm) return pl;
+    pl.classic_ok = !(env && !strcmp(env, "global")) &&
+                    (forced || (unsigned long long)n_comp * 2 <= 3ull * kNumSMs * per_sm);
+    if (!pl.classic_ok && !express_possible) return pl;
     // 1024 threads would cap the kernel at 64 registers and make it spill: local memory is what this
     // kernel must not touch (maxflow_sm.cuh), so it is a measurement knob only
     int shape = per_sm >= 2 ? 0 : 1;
@@ -924,6 +929,8 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
     const uint32_t seg_len =
         (prm && prm->seg_len) ? prm->seg_len : default_seg_len(rd->n_samples, rd->ref_len);
     const uint32_t algorithm = prm ? prm->algorithm : 0u;
+    const uint32_t schedule = prm ? prm->schedule : 0u;
+    if (schedule > 2) return fail(c, GDS_ERR_ARG, "gds_params.schedule must be 0, 1 or 2");
     if (algorithm > 1) return fail(c, GDS_ERR_ARG, "gds_params.algorithm must be 0 (quasi-MCP) or 1 (minimum cardinality)");
     // scalars of the result start clean (buffers are left alone)
     {
@@ -1386,7 +1393,15 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         const bool do_solve = !(flags & GDS_NO_SOLVE);
         if (do_solve && algorithm == 1 && maxlen >= 4096)
             return fail(c, GDS_ERR_ARG, "algorithm 1 (minimum cardinality) takes reads of up to 4095 positions");
-        const Mf2Plan mf2 = do_solve && algorithm == 0 ? plan_maxflow_sm(n_comp, max_comp_nodes) : Mf2Plan{};
+        // the express schedule (maxflow_sm.cuh): segments of cut references whose segments fit
+        uint32_t express_on = schedule == 1 ? 0u : schedule == 2 ? 2u : 1u;
+        if (const char* e = getenv("GDS_EXPRESS")) express_on = (uint32_t)atoi(e);  // measurement knob
+        bool express_possible = express_on == 2;
+        for (const VSample& v : hvs) express_possible |= express_on && v.nseg > 1 && v.W <= kExpressMaxNodes;
+        if (!express_possible) express_on = 0;
+        const Mf2Plan mf2 = do_solve && algorithm == 0
+                                ? plan_maxflow_sm(n_comp, max_comp_nodes, express_possible)
+                                : Mf2Plan{};
         uint32_t* in_src = c->in_src.get<uint32_t>((size_t)B + 1);
         uint32_t* in1 = c->in1.get<uint32_t>((size_t)n_nodes + 1);
         GDS_CUDA(cudaMemsetAsync(in1, 0xff, ((size_t)n_nodes + 1) * 4, st));
@@ -1432,11 +1447,13 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             }
             if (mf2.on) {
                 uint32_t* fb_list = c->fb_list.get<uint32_t>(n_comp_cap + 1);
-                Mf2Graph g2{node, c->bund.as<BundleRec>(), in_bid, in_src, out_ptr, in_ptr, dem_v};
+                Mf2Graph g2{node, c->bund.as<BundleRec>(), in_bid, in_src, out_ptr, in_ptr, dem_v,
+                            vs_d, ns, express_on, mf2.classic_ok ? 1u : 0u};
                 launch_maxflow_sm(c, mf2, g2, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats,
                                   mf_bytes, fb_list, wc + 2, n_comp_dev, mft);
                 // whatever the shared-memory kernel could not take (grid: at most one wave)
-                launch_maxflow(c, mg, comp_lo, comp_hi, std::min<uint32_t>(n_comp, kNumSMs), wc + 1, qF,
+                launch_maxflow(c, mg, comp_lo, comp_hi,
+                               mf2.classic_ok ? std::min<uint32_t>(n_comp, kNumSMs) : n_comp, wc + 1, qF,
                                qT, qN, qH, sp, cstats, 0, max_comp_nodes, n_comp_dev, mft, lab_g,
                                fb_list, wc + 2);
             } else {

@@ -44,12 +44,29 @@ struct Mf2Graph {
     const uint32_t* out_ptr;  // [n_nodes + 1]  SoA copies for the coalesced set-up pass
     const uint32_t* in_ptr;   // [n_nodes + 1]
     const int32_t* dem;       // [n_nodes]      demand (< 0 supply, > 0 sink capacity)
+    // the express schedule (below): per-sample layout to tell segments of a cut reference from whole
+    // samples; express_on = the call allows it; classic_ok = components that do not take the express
+    // schedule may run here too (otherwise they go to k_maxflow)
+    const VSample* vs;
+    uint32_t n_samples, express_on, classic_ok;
 };
 
+// The EXPRESS schedule (oracle/gds_oracle.cpp: express_component, sync_solve_component): in the
+// distance labels a back arc v -> v-1 has length 0, every other residual arc length 1.  A segment of
+// a cut reference has all its supply at its left end and all its sinks at its right end: M units
+// have to spread over the read "lanes" (start modulo read length) and gather again, and changing
+// lane means stepping left.  With unit-length back arcs every step is a round and a label; with
+// length 0 a unit walks left past saturated nodes within ONE round (phase A, rule 4) and the relabel
+// BFS has one level per read hop instead of one per hop plus one per step.  Config 4: 370 -> 165
+// rounds and 290 -> 110 BFS levels per segment, no second global relabel, and the 1 400-round tail
+// of the last segment is gone.  Which components take it is decided from the data alone.
+constexpr uint32_t kExpressMaxNodes = 24576, kExpressEdge = 512;
+
 // Layout of the per-node arrays of an n-node component, in 32-bit words from `word`:
-//   word[n] | inF bitmap [W] | (16-byte aligned) BFS bitmap A [W4] | BFS bitmap B [W4] | optr u16[n+1]
+//   word[n] | inF bitmap [W] | (16-byte aligned) BFS bitmap A [W4] | saturated bits: snapshot [W4],
+//   next [W4] (express schedule) | optr u16[n+1]
 struct Mf2Layout {
-    uint32_t W, W4, o_inF, o_A, o_B, o_optr, words;
+    uint32_t W, W4, o_inF, o_A, o_B, o_Sn, o_optr, words;
 };
 __host__ __device__ inline Mf2Layout mf2_layout(uint32_t n, bool optr) {
     Mf2Layout L;
@@ -58,7 +75,8 @@ __host__ __device__ inline Mf2Layout mf2_layout(uint32_t n, bool optr) {
     L.o_inF = n;
     L.o_A = (n + L.W + 3u) & ~3u;
     L.o_B = L.o_A + L.W4;
-    L.o_optr = L.o_B + L.W4;
+    L.o_Sn = L.o_B + L.W4;
+    L.o_optr = L.o_Sn + L.W4;
     L.words = L.o_optr + (optr ? (n + 2u) / 2u : 0u);
     return L;
 }
@@ -88,6 +106,10 @@ __device__ __forceinline__ void g_touch(const void* p) {
 }
 __device__ __forceinline__ void g_st(void* p, uint32_t v) {
     asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// fire-and-forget add (several walkers of one round may add to the same back-arc flow)
+__device__ __forceinline__ void g_red_add(void* p, uint32_t v) {
+    asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 // Shared-memory arrays are addressed by BYTE OFFSET from the dynamic shared-memory base, never by
 // a pointer that went through memory: a pointer loaded from a struct is a generic pointer, and the
@@ -137,7 +159,8 @@ struct Mf2Comp {
     uint32_t lo, n, obase;
     uint32_t word_off, inF_off, bmA_off, bmB_off, optr_off;  // byte offsets (mf2_smem)
     uint32_t W4;
-    uint32_t have_optr, warp_mode;
+    uint32_t have_optr, warp_mode, express;
+    uint32_t satn_off;  // bmB_off holds the snapshot the walkers read
     Q2 F, T, N, H;
 };
 
@@ -146,6 +169,8 @@ struct Mf2Shared {
     uint32_t relabels_since;
     uint32_t comp;
     uint32_t supply;
+    uint32_t seg_sample;  // the component's sample is a cut reference (express schedule)
+    uint32_t not_benign;  // a supply beyond the left edge or a sink before the right edge
     uint32_t lc[3];  // rotating level counters of the relabel BFS
     unsigned long long pushes, relabels;
     long long sink_flow, stuck;
@@ -176,6 +201,32 @@ __device__ __forceinline__ void mf2_give(Mf2Shared& sh, uint32_t w, uint32_t dl)
         q2_append(C.T, &sh.nT, w);
         mf2_warm(C, w);
     }
+}
+
+// express schedule, "saturated" bits: no sink capacity and no residual on any own bundle, as far as
+// the three update rules know (0 is always safe).  Walkers read the snapshot of the round start
+// (bmB), updates go to the next one (satn), copied over at the end of the round.
+__device__ __forceinline__ void mf2_sat_set(const Mf2Comp& C, uint32_t v, bool on) {
+    uint32_t* p = mf2_smem(C.satn_off) + (v >> 5);
+    if (on) atomicOr(p, 1u << (v & 31));
+    else atomicAnd(p, ~(1u << (v & 31)));
+}
+// phase A rule 4, express: ex units leave v over the chain of zero-length back arcs and stop at the
+// first node that is not known to be saturated (or where the chain of equal labels ends).
+__device__ __forceinline__ uint32_t mf2_walk_left(const Mf2Comp& C, uint32_t v, uint32_t ex) {
+    const uint32_t* word = mf2_smem(C.word_off);
+    const uint32_t* sat = mf2_smem(C.bmB_off);
+    NodeRec* nr = C.G.node + C.lo;
+    uint32_t u = v;
+    uint32_t du = word[v] & 0xffffu;
+#pragma unroll 1
+    for (;;) {
+        g_red_add(&nr[u].g, ex);
+        --u;
+        if (u == 0 || !((sat[u >> 5] >> (u & 31)) & 1u)) break;
+        if ((word[u - 1] & 0xffffu) != du) break;  // (labels along the chain are all equal to du)
+    }
+    return u;
 }
 
 // One level of the relabel BFS: label to hand out, counter and queue of the next level.
@@ -350,10 +401,12 @@ __device__ __forceinline__ void mf2_push_heavy(Mf2Shared& sh, uint32_t nHA, unsi
         }
         const uint32_t dL = v > 0 ? mf2_label(word, v - 1) : kInf16;
         const uint32_t dR = v + 1 < n ? mf2_label(word, v + 1) : kInf16;
+        int32_t snk_now = (int32_t)hi4.x;
         if (dv == 1) {  // 1. sink arc
             const int32_t sk = (int32_t)hi4.x;
             if (sk > 0) {
                 const uint32_t dl = min(ex, (uint32_t)sk);
+                snk_now = sk - (int32_t)dl;
                 ex -= dl;
                 if (lane == 0) {
                     g_st(&nr->snk, (uint32_t)(sk - (int32_t)dl));
@@ -382,6 +435,7 @@ __device__ __forceinline__ void mf2_push_heavy(Mf2Shared& sh, uint32_t nHA, unsi
                 g_st(&C.G.bund[b].f, br.z + dl);
                 mf2_give(sh, br.x - lo, dl);
                 ++my_pushes;
+                if (C.express && dl == r && oe - ob == 1 && snk_now == 0) mf2_sat_set(C, v, true);  // U1
             }
             ex -= min(ex, tot);
         }
@@ -399,10 +453,14 @@ __device__ __forceinline__ void mf2_push_heavy(Mf2Shared& sh, uint32_t nHA, unsi
             }
         }
         // 4. back arc to the left neighbour
-        if (ex > 0 && v > 0 && dL + 1 == dv) {
+        if (ex > 0 && v > 0 && dL + (C.express ? 0u : 1u) == dv) {
             if (lane == 0) {
-                g_st(&nr->g, hi4.y + ex);
-                mf2_give(sh, v - 1, ex);
+                if (C.express) {
+                    mf2_give(sh, mf2_walk_left(C, v, ex), ex);
+                } else {
+                    g_st(&nr->g, hi4.y + ex);
+                    mf2_give(sh, v - 1, ex);
+                }
                 ++my_pushes;
             }
             ex = 0;
@@ -427,6 +485,7 @@ __device__ __forceinline__ void mf2_push_heavy(Mf2Shared& sh, uint32_t nHA, unsi
                 g_st(&C.G.bund[b].f, r - dl);
                 mf2_give(sh, s, dl);
                 ++my_pushes;
+                if (C.express) mf2_sat_set(C, s, false);  // U2
             }
             ex -= min(ex, tot);
         }
@@ -461,23 +520,34 @@ __device__ __forceinline__ void mf2_relabel_heavy(Mf2Shared& sh, uint32_t nH) {
         for (int q = 0; q < 2; ++q)
             ib2[q] = id2[q] != 0xffffffffu ? ld_bund(&C.G.bund[id2[q]]) : make_uint4(0, 0, 0, 0);
         uint32_t mn = kInf16;
+        bool res_any = false;  // some own bundle has residual capacity
         if ((int32_t)hi4.x > 0) mn = 0;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-            if (ob2[q].z < ob2[q].y) mn = min(mn, mf2_label(word, ob2[q].x - lo));  // (0,0): not taken
+            if (ob2[q].z < ob2[q].y) {  // (0,0): not taken
+                mn = min(mn, mf2_label(word, ob2[q].x - lo));
+                res_any = true;
+            }
             if (ib2[q].z > 0) mn = min(mn, mf2_label(word, ib2[q].w - lo));
         }
 #pragma unroll 1
         for (uint32_t b = hi4.z + 64 + lane; b < r_hi.z; b += 32) {
             const uint4 br = ld_bund(&C.G.bund[b]);
-            if (br.z < br.y) mn = min(mn, mf2_label(word, br.x - lo));
+            if (br.z < br.y) {
+                mn = min(mn, mf2_label(word, br.x - lo));
+                res_any = true;
+            }
         }
         if (v + 1 < n && (int32_t)r_hi.y > 0) mn = min(mn, mf2_label(word, v + 1));
-        if (v > 0) mn = min(mn, mf2_label(word, v - 1));
+        if (v > 0) mn = min(mn, mf2_label(word, v - 1) - (C.express ? 1u : 0u));  // labels are >= 1
 #pragma unroll 1
         for (uint32_t k = hi4.w + 64 + lane; k < r_hi.w; k += 32) {
             const uint4 br = ld_bund(&C.G.bund[g_ld(&C.G.in_bid[k])]);
             if (br.z > 0) mn = min(mn, mf2_label(word, br.w - lo));
+        }
+        if (C.express) {  // U3: every own bundle has just been looked at
+            const bool any = __any_sync(0xffffffffu, res_any) || (int32_t)hi4.x > 0;
+            if (lane == 0) mf2_sat_set(C, v, !any);
         }
         mn = __reduce_min_sync(0xffffffffu, mn);
         const uint32_t nl = mn >= kInf16 - 1 ? kInf16 : mn + 1;
@@ -498,17 +568,57 @@ __device__ __forceinline__ uint32_t mf2_bfs(Mf2Shared& sh, bool first, unsigned 
     const uint32_t* word = mf2_smem(C.word_off);
     const uint32_t n = C.n;
     Q2 T = C.T, N = C.N;
+    const bool express = C.express;
     uint32_t level = 1;
     for (;;) {
-        const uint32_t cnt = sh.lc[(level - 1) % 3];
+        uint32_t cnt = sh.lc[(level - 1) % 3];
         if (cnt == 0) break;
         ++bfs_levels;
+        if (express) {
+            // zero-length back arcs: the level is closed under "right neighbour" first.  One warp
+            // per seed: the run from the seed to the next visited node gets the seed's label, its
+            // visited bits, and joins this level's queue (runs of different seeds are disjoint).
+            uint32_t* vis = mf2_smem(C.bmA_off);
+            uint16_t* lab = reinterpret_cast<uint16_t*>(mf2_smem(C.word_off));
+            const uint32_t lane = lane_id();
+#pragma unroll 1
+            for (uint32_t i = tid >> 5; i < cnt; i += THREADS / 32) {
+                const uint32_t x = T.get(i) + 1;  // first node of the run
+                if (x >= n) continue;
+                uint32_t wi = x >> 5;
+                uint32_t m = vis[wi] & (0xffffffffu << (x & 31));
+                const uint32_t wn = (n + 31u) >> 5;
+#pragma unroll 1
+                while (m == 0 && ++wi < wn) m = vis[wi];
+                uint32_t e = m ? (wi << 5) + (uint32_t)__ffs((int)m) - 1u : n;
+                if (e > n) e = n;
+                const uint32_t len = e - x;
+                if (len == 0) continue;
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(&sh.lc[(level - 1) % 3], len);
+                base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll 1
+                for (uint32_t j = lane; j < len; j += 32) {
+                    lab[2 * (x + j)] = (uint16_t)level;
+                    T.put(base + j, x + j);
+                }
+#pragma unroll 1
+                for (uint32_t w2 = (x >> 5) + lane; w2 <= ((e - 1) >> 5); w2 += 32) {
+                    uint32_t mask = 0xffffffffu;
+                    if (w2 == (x >> 5)) mask &= 0xffffffffu << (x & 31);
+                    if (w2 == ((e - 1) >> 5)) mask &= 0xffffffffu >> (31u - ((e - 1) & 31));
+                    atomicOr(&vis[w2], mask);
+                }
+            }
+            __syncthreads();
+            cnt = sh.lc[(level - 1) % 3];
+        }
         const Mf2Lvl L{level + 1, &sh.lc[level % 3], N};
         if (tid == 0) sh.lc[(level + 1) % 3] = 0;  // last level's counter: everyone has read it
 #pragma unroll 1
         for (uint32_t i = mf2_slot<THREADS>(); i < cnt; i += THREADS) {
             const uint32_t u = T.get(i);
-            if (u + 1 < n) mf2_mark(C, L, u + 1);  // back arc (u+1) -> u: always residual
+            if (!express && u + 1 < n) mf2_mark(C, L, u + 1);  // back arc (u+1) -> u: always residual
             if (first) {
                 const uint32_t code = word[u] >> 16;
                 if (code < kIn16Multi) mf2_mark(C, L, code);
@@ -574,6 +684,8 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
             sh.nH = 0;
             sh.relabels_since = 0;
             sh.supply = 0;
+            sh.seg_sample = 0;
+            sh.not_benign = 0;
             sh.lc[0] = 0;
             sh.lc[1] = 0;
             sh.lc[2] = 0;
@@ -590,6 +702,8 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
             C.inF_off = word_off + 4u * lay.o_inF;
             C.bmA_off = word_off + 4u * lay.o_A;
             C.bmB_off = word_off + 4u * lay.o_B;
+            C.satn_off = word_off + 4u * lay.o_Sn;
+            C.express = 0;
             C.optr_off = word_off + 4u * lay.o_optr;
             C.W4 = lay.W4;
             C.have_optr = have_optr;
@@ -604,7 +718,7 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
             __syncthreads();
             continue;
         }
-        if (fits)  // the three bitmaps (inF, BFS A, BFS B) are contiguous
+        if (fits)  // the bitmaps (inF, BFS A, saturated x 2) are contiguous
             for (uint32_t i = lay.o_inF + tid; i < lay.o_optr; i += THREADS) word[i] = 0;
         __syncthreads();
         Q2 F = sh.C.F, N = sh.C.N;
@@ -636,6 +750,8 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
                     const uint32_t v = v0 + q * THREADS;
                     if (v >= n) continue;
                     if (dm[q] < 0) my_supply += (uint32_t)(-dm[q]);
+                    if ((dm[q] < 0 && v >= kExpressEdge) || (dm[q] > 0 && n - 1 - v >= kExpressEdge))
+                        sh.not_benign = 1;
                     if (!fits) continue;
                     uint32_t code = kIn16None;
                     if (ip1[q] - ip[q] == 1) code = src[q] - lo;
@@ -653,6 +769,12 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
                 }
             }
             if (have_optr && tid == 0) optr[n] = (uint16_t)n_bund;
+            if (G.express_on)  // is this a segment of a cut reference?
+                for (uint32_t k = tid; k < G.n_samples; k += THREADS) {
+                    const VSample vk = G.vs[k];
+                    const bool inside = lo >= vk.vbase && (k + 1 == G.n_samples || lo < G.vs[k + 1].vbase);
+                    if (inside && vk.nseg > 1 && vk.W <= kExpressMaxNodes) sh.seg_sample = 1;
+                }
             my_supply = __reduce_add_sync(0xffffffffu, my_supply);
             if (lane == 0 && my_supply) atomicAdd(&sh.supply, min(my_supply, 0x10000u));
         }
@@ -660,11 +782,18 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
         // k_maxflow takes what does not fit, and the components whose nodes are mostly heavy (variable
         // read lengths, tens of bundles per node): their time is the per-bundle global traffic of the
         // warp passes, which shared-memory labels do not shorten (config 2: 2.6 ms there, 3.4 ms here)
-        if (sh.supply > 0xffffu) {  // nothing has been written to global memory yet
+        // the express schedule: decided from the data alone (oracle: express_component)
+        const bool express = G.express_on && (G.express_on == 2 || sh.seg_sample) && !sh.not_benign &&
+                             !warp_mode && n <= kExpressMaxNodes && sh.supply <= 0xffffu;
+        const uint32_t bl = express ? 0u : 1u;  // length of a back arc in the labels
+        if (sh.supply > 0xffffu || (!express && !G.classic_ok)) {  // nothing has been written to global memory yet
+            __syncthreads();
             if (tid == 0) fb_list[atomicAdd(fb_count, 1u)] = c;
             __syncthreads();
             continue;
         }
+        if (tid == 0) sh.C.express = express;
+        __syncthreads();
         unsigned long long bfs_levels = 0, grs = 1, rounds = 0, max_frontier = 0, frontier_sum = 0;
         (void)t_begin;
         unsigned long long my_pushes = 0, my_relabels = 0;
@@ -765,11 +894,13 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
                 }
                 const uint32_t dL = v > 0 ? mf2_label(word, v - 1) : kInf16;
                 const uint32_t dR = v + 1 < n ? mf2_label(word, v + 1) : kInf16;
+                int32_t snk_now = (int32_t)hi4.x;
                 if (dv == 1) {  // 1. sink arc
                     const int32_t s = (int32_t)hi4.x;
                     if (s > 0) {
                         const uint32_t dl = min(ex, (uint32_t)s);
                         g_st(&nr->snk, (uint32_t)(s - (int32_t)dl));
+                        snk_now = s - (int32_t)dl;
                         ex -= dl;
                         my_sink += dl;
                         ++my_pushes;
@@ -788,6 +919,8 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
                     ex -= dl;
                     mf2_give(sh, t, dl);
                     ++my_pushes;
+                    // U1: the owner filled its only bundle (nobody else touches it this round)
+                    if (express && dl == r && oe - ob == 1 && snk_now == 0) mf2_sat_set(sh.C, v, true);
                 }
                 // 3. cancel back-flow towards the right neighbour
                 if (ex > 0 && v + 1 < n && dR + 1 == dv) {
@@ -801,9 +934,13 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
                     }
                 }
                 // 4. back arc to the left neighbour (infinite capacity)
-                if (ex > 0 && v > 0 && dL + 1 == dv) {
-                    g_st(&nr->g, hi4.y + ex);
-                    mf2_give(sh, v - 1, ex);
+                if (ex > 0 && v > 0 && dL + bl == dv) {
+                    if (express) {
+                        mf2_give(sh, mf2_walk_left(sh.C, v, ex), ex);
+                    } else {
+                        g_st(&nr->g, hi4.y + ex);
+                        mf2_give(sh, v - 1, ex);
+                    }
                     ++my_pushes;
                     ex = 0;
                 }
@@ -828,6 +965,7 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
                     ex -= dl;
                     mf2_give(sh, s - lo, dl);
                     ++my_pushes;
+                    if (express) mf2_sat_set(sh.C, s - lo, false);  // U2: s has residual capacity again
                 }
                 F.put(i, (ex << 16) | v);
             }
@@ -897,14 +1035,19 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
                             q2_append(H, &sh.nH, i);  // the min over many bundles: warp pass below
                         } else {
                             uint32_t mn = kInf16;
+                            bool res_any = (int32_t)hi4.x > 0;
                             if ((int32_t)hi4.x > 0) mn = 0;
 #pragma unroll 1
                             for (uint32_t b = ob; b < oe; ++b) {
                                 const uint4 br = (have_optr && b == ob) ? bo : ld_bund(&G.bund[b]);
-                                if (br.z < br.y) mn = min(mn, mf2_label(word, br.x - lo));
+                                if (br.z < br.y) {
+                                    mn = min(mn, mf2_label(word, br.x - lo));
+                                    res_any = true;
+                                }
                             }
+                            if (express) mf2_sat_set(sh.C, v, !res_any);  // U3: exact, after the barrier
                             if (v + 1 < n && (int32_t)r_hi.y > 0) mn = min(mn, mf2_label(word, v + 1));
-                            if (v > 0) mn = min(mn, mf2_label(word, v - 1));
+                            if (v > 0) mn = min(mn, mf2_label(word, v - 1) - (1u - bl));  // labels are >= 1
 #pragma unroll 1
                             for (uint32_t k = hi4.w; k < r_hi.w; ++k) {
                                 const uint4 br = (one_each && k + 1 == r_hi.w)
@@ -940,6 +1083,12 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
                     if (tot > 0) my_stuck += tot;
                     atomicAnd(&inF[v >> 5], ~(1u << (v & 31)));
                 }
+            }
+            if (express) {  // the saturation bits the next round's walkers read
+                const uint32_t* satn = mf2_smem(sh.C.satn_off);
+                uint32_t* sat = mf2_smem(sh.C.bmB_off);
+#pragma unroll 1
+                for (uint32_t i = tid; i < lay.W4; i += THREADS) sat[i] = satn[i];
             }
             __syncthreads();
             {

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define GDS_ABI_VERSION 6
+#define GDS_ABI_VERSION 7
 
 /* status codes (the reference has none: it logs and exits, cuda_helpers.cuh:13-21) */
 enum {
@@ -123,6 +123,16 @@ typedef struct {
      *      set is the smallest one (per segment, when a long reference is cut).  Reads of up to 4095
      *      positions.  rounds / pushes / relabels stay 0. */
     uint32_t algorithm;
+    /* which deterministic push-relabel schedule components run (algorithm 0):
+     *   0  the classic one, and the EXPRESS one for segments of a cut reference (seg_len above) whose
+     *      supply sits at their left and whose sinks sit at their right end: back arcs have length 0
+     *      in the distance labels, so flow changes read "lanes" within one round (csrc/maxflow_sm.cuh;
+     *      config 4: 370 -> 165 rounds and 290 -> 110 relabel levels per segment).  Decided from the
+     *      data alone; the oracle replays both (orc_sync_params.schedule);
+     *   1  classic only (round 1's results);
+     *   2  express for every component that is structurally eligible, cut reference or not
+     *      (experiments). */
+    uint32_t schedule;
 } gds_params;
 
 /* Results.  Buffers are caller-owned and optional (NULL = not wanted). */

@@ -750,16 +750,26 @@ struct SyncState {
     std::vector<int32_t> e, eadd, snk, g;
     std::vector<uint32_t> f;      // bundle flows
     std::vector<uint32_t> stamp;
+    std::vector<uint8_t> sat, satn;
 };
 
 struct CompStats {
     uint64_t rounds = 0, pushes = 0, relabels = 0, grs = 0, bfs_levels = 0, max_frontier = 0;
     int64_t sink_flow = 0;
     int64_t stuck = 0;
+    uint64_t express = 0;
 };
 
+// The EXPRESS schedule (csrc/maxflow_sm.cuh): back arcs v -> v-1 have length 0 in
+// the distance labels, every other residual arc length 1.  Excess then changes lane (moves left
+// past saturated nodes) at no label cost and in one round, which is what a segment of a long
+// reference needs: all its supply sits at the left end and all its sinks at the right end, so M
+// units must be spread over the read "lanes" and gathered again.  Chosen per component from the
+// data alone (express_component below), never from the device or the batch.
+constexpr uint32_t kExpressMaxNodes = 24576, kExpressEdge = 512, kHeavyDegOracle = 6;
+
 uint32_t sync_global_relabel(const SyncGraph& G, SyncState& S, uint32_t lo, uint32_t hi,
-                             CompStats& cs) {
+                             CompStats& cs, bool express) {
     ++cs.grs;
     for (uint32_t v = lo; v <= hi; ++v) S.d[v] = LBL_INF;
     std::vector<uint32_t> cur, nxt;
@@ -771,6 +781,14 @@ uint32_t sync_global_relabel(const SyncGraph& G, SyncState& S, uint32_t lo, uint
     uint32_t level = 1;
     while (!cur.empty()) {
         ++cs.bfs_levels;
+        if (express) {  // a level is closed under "right neighbour" (zero-length back arcs) first
+            const size_t seeds = cur.size();
+            for (size_t i = 0; i < seeds; ++i)
+                for (uint32_t u = cur[i] + 1; u <= hi && S.d[u] == LBL_INF; ++u) {
+                    S.d[u] = level;
+                    cur.push_back(u);
+                }
+        }
         nxt.clear();
         auto visit = [&](uint32_t u) {
             if (S.d[u] == LBL_INF) {
@@ -779,7 +797,7 @@ uint32_t sync_global_relabel(const SyncGraph& G, SyncState& S, uint32_t lo, uint
             }
         };
         for (uint32_t w : cur) {
-            if (w < hi) visit(w + 1);                       // back arc (w+1) -> w, always residual
+            if (!express && w < hi) visit(w + 1);           // back arc (w+1) -> w, always residual
             if (w > lo && S.g[w] > 0) visit(w - 1);         // reverse of back arc w -> w-1
             for (uint32_t k = G.in_ptr[w]; k < G.in_ptr[w + 1]; ++k) {
                 uint32_t b = G.in_bid[k];
@@ -794,9 +812,47 @@ uint32_t sync_global_relabel(const SyncGraph& G, SyncState& S, uint32_t lo, uint
     return level;
 }
 
+// Which components run the express schedule: segments of a cut reference (whose nodes fit the
+// shared-memory kernel by construction) with few bundles per node, a supply that fits 16 bits, every
+// supply within kExpressEdge nodes of the left end and every sink within kExpressEdge of the right.
+bool express_component(const SyncGraph& G, uint32_t lo, uint32_t hi, uint32_t schedule) {
+    if (schedule == 1) return false;
+    const uint32_t n = hi - lo + 1;
+    if (schedule != 2) {
+        bool seg = false;
+        for (const VSample& v : G.vs)
+            if (lo >= v.vbase && lo < v.vbase + v.vn) seg = v.nseg > 1 && v.W <= kExpressMaxNodes;
+        if (!seg) return false;
+    }
+    if (n > kExpressMaxNodes) return false;
+    const uint64_t n_bund = G.out_ptr[hi + 1] - G.out_ptr[lo];
+    if (2 * n_bund > (uint64_t)kHeavyDegOracle * n) return false;
+    uint64_t supply = 0;
+    for (uint32_t v = lo; v <= hi; ++v) {
+        const int32_t dm = G.demand[v];
+        if (dm < 0) {
+            supply += (uint32_t)(-dm);
+            if (v - lo >= kExpressEdge) return false;
+        } else if (dm > 0 && hi - v >= kExpressEdge) {
+            return false;
+        }
+    }
+    return supply <= 0xffffu;
+}
+
 void sync_solve_component(const SyncGraph& G, SyncState& S, uint32_t lo, uint32_t hi,
                           const orc_sync_params& P, CompStats& cs) {
     const uint32_t ncomp = hi - lo + 1;
+    const bool express = express_component(G, lo, hi, P.schedule);
+    const uint32_t bl = express ? 0u : 1u;  // length of a back arc in the labels
+    if (express) ++cs.express;
+    // express: "saturated" bits — no sink capacity and no residual on any own bundle, as far as
+    // the rules below know (0 is always safe).  Walkers read the snapshot of the round start.
+    std::vector<uint8_t>& sat = S.sat;
+    std::vector<uint8_t>& satn = S.satn;
+    std::vector<uint32_t> sat_touched;
+    if (express)
+        for (uint32_t v = lo; v <= hi; ++v) sat[v] = satn[v] = 0;
     for (uint32_t v = lo; v <= hi; ++v) {
         int32_t dm = G.demand[v];
         S.e[v] = dm < 0 ? -dm : 0;
@@ -804,7 +860,7 @@ void sync_solve_component(const SyncGraph& G, SyncState& S, uint32_t lo, uint32_
         S.g[v] = 0;
         S.eadd[v] = 0;
     }
-    uint32_t last_levels = sync_global_relabel(G, S, lo, hi, cs);
+    uint32_t last_levels = sync_global_relabel(G, S, lo, hi, cs, express);
     std::vector<uint32_t> F, T, NF;
     uint32_t round = 0;
     for (uint32_t v = lo; v <= hi; ++v)
@@ -820,7 +876,7 @@ void sync_solve_component(const SyncGraph& G, SyncState& S, uint32_t lo, uint32_
         uint64_t interval = std::max<uint64_t>(P.gr_interval_min, (uint64_t)last_levels * P.gr_levels_pct / 100);
         if (rounds_since >= interval &&
             relabels_since * 100 >= (uint64_t)P.gr_relabel_pct * ncomp) {
-            last_levels = sync_global_relabel(G, S, lo, hi, cs);
+            last_levels = sync_global_relabel(G, S, lo, hi, cs, express);
             relabels_since = 0;
             rounds_since = 0;
         }
@@ -860,6 +916,11 @@ void sync_solve_component(const SyncGraph& G, SyncState& S, uint32_t lo, uint32_
                 S.f[b] += dl;
                 ex -= dl;
                 give(t, dl);
+                // U1: the owner filled its only bundle (nobody else can touch it this round)
+                if (express && (uint32_t)dl == r && G.out_ptr[v + 1] - G.out_ptr[v] == 1 && S.snk[v] == 0) {
+                    satn[v] = 1;
+                    sat_touched.push_back(v);
+                }
             }
             // 3. cancel back-flow towards the right neighbour
             if (ex > 0 && v < hi && S.d[v + 1] + 1 == dv && S.g[v + 1] > 0) {
@@ -869,9 +930,19 @@ void sync_solve_component(const SyncGraph& G, SyncState& S, uint32_t lo, uint32_
                 give(v + 1, dl);
             }
             // 4. back arc to the left neighbour (infinite capacity)
-            if (ex > 0 && v > lo && S.d[v - 1] + 1 == dv) {
-                S.g[v] += ex;
-                give(v - 1, ex);
+            if (ex > 0 && v > lo && S.d[v - 1] + bl == dv) {
+                uint32_t u = v;
+                if (express) {  // walk the zero-length chain past nodes known to be saturated
+                    for (;;) {
+                        S.g[u] += ex;
+                        --u;
+                        if (u == lo || !sat[u] || S.d[u - 1] != S.d[u]) break;
+                    }
+                } else {
+                    S.g[v] += ex;
+                    --u;
+                }
+                give(u, ex);
                 ex = 0;
             }
             // 5. cancel flow on incoming bundles, nearest start first
@@ -883,6 +954,10 @@ void sync_solve_component(const SyncGraph& G, SyncState& S, uint32_t lo, uint32_
                 S.f[b] -= dl;
                 ex -= dl;
                 give(s, dl);
+                if (express) {  // U2: s has residual capacity again
+                    satn[s] = 0;
+                    sat_touched.push_back(s);
+                }
             }
             S.e[v] = ex;
         }
@@ -897,13 +972,20 @@ void sync_solve_component(const SyncGraph& G, SyncState& S, uint32_t lo, uint32_
                 for (uint32_t b = G.out_ptr[w]; b < G.out_ptr[w + 1]; ++b)
                     if (S.f[b] < G.b_mult[b]) mn = std::min(mn, S.d[G.b_t[b]]);
                 if (w < hi && S.g[w + 1] > 0) mn = std::min(mn, S.d[w + 1]);
-                if (w > lo) mn = std::min(mn, S.d[w - 1]);
+                if (w > lo) mn = std::min(mn, S.d[w - 1] - (1u - bl));  // labels are >= 1
                 for (uint32_t k = G.in_ptr[w]; k < G.in_ptr[w + 1]; ++k) {
                     uint32_t b = G.in_bid[k];
                     if (S.f[b] > 0) mn = std::min(mn, S.d[G.b_s[b]]);
                 }
                 uint32_t nl = mn >= LBL_INF ? LBL_INF : mn + 1;
                 newlab.emplace_back(w, nl);
+                if (express) {  // U3: the relabel has just looked at every own bundle
+                    bool any = S.snk[w] > 0;
+                    for (uint32_t b = G.out_ptr[w]; !any && b < G.out_ptr[w + 1]; ++b)
+                        any = S.f[b] < G.b_mult[b];
+                    satn[w] = any ? 0 : 1;
+                    sat_touched.push_back(w);
+                }
                 ++cs.relabels;
                 ++relabels_since;
             }
@@ -918,6 +1000,8 @@ void sync_solve_component(const SyncGraph& G, SyncState& S, uint32_t lo, uint32_
         for (uint32_t v : F) phase_b(v, true);
         for (uint32_t w : T) phase_b(w, false);
         for (auto& pr : newlab) S.d[pr.first] = pr.second;  // applied after all reads (snapshot)
+        for (uint32_t w : sat_touched) sat[w] = satn[w];    // the next round's snapshot
+        sat_touched.clear();
         // drop frozen nodes (cannot happen on this network — SURVEY App. A.1 — but stay safe)
         F.clear();
         for (uint32_t w : NF) {
@@ -935,7 +1019,7 @@ extern "C" int orc_sync_solve(uint32_t n_samples, const uint64_t* read_off, cons
                               const uint32_t* start, const uint32_t* end, uint32_t M,
                               const orc_sync_params* prm, uint32_t* kept_bitmap,
                               int32_t* demand_out, uint32_t* cov_out, orc_sync_stats* st) {
-    orc_sync_params P = prm ? *prm : orc_sync_params{64, 150, 1, 0, 0};
+    orc_sync_params P = prm ? *prm : orc_sync_params{64, 150, 1, 0, 0, 0};
     auto t0 = clk::now();
     SyncGraph G;
     if (build_sync_graph(n_samples, read_off, ref_len, start, end, M, P.seg_len, G) != 0) return -1;
@@ -950,6 +1034,8 @@ extern "C" int orc_sync_solve(uint32_t n_samples, const uint64_t* read_off, cons
     S.g.assign(nn, 0);
     S.f.assign(B, 0);
     S.stamp.assign(nn, 0);
+    S.sat.assign(nn, 0);
+    S.satn.assign(nn, 0);
     orc_sync_stats out{};
     for (size_t c = 0; c < G.comp_lo.size(); ++c) {
         CompStats cs;
@@ -962,6 +1048,7 @@ extern "C" int orc_sync_solve(uint32_t n_samples, const uint64_t* read_off, cons
         out.global_relabels += cs.grs;
         out.bfs_levels += cs.bfs_levels;
         out.max_frontier = std::max(out.max_frontier, cs.max_frontier);
+        out.n_express += (uint32_t)cs.express;
     }
     auto t2 = clk::now();
     const uint64_t N = read_off[n_samples];
@@ -1006,7 +1093,7 @@ extern "C" int orc_sweep_solve(uint32_t n_samples, const uint64_t* read_off, con
                                const uint32_t* start, const uint32_t* end, uint32_t M,
                                const orc_sync_params* prm, uint32_t* kept_bitmap,
                                int32_t* demand_out, uint32_t* cov_out, orc_sync_stats* st) {
-    orc_sync_params P = prm ? *prm : orc_sync_params{64, 150, 1, 0, 0};
+    orc_sync_params P = prm ? *prm : orc_sync_params{64, 150, 1, 0, 0, 0};
     SyncGraph G;
     if (build_sync_graph(n_samples, read_off, ref_len, start, end, M, P.seg_len, G) != 0) return -1;
     const uint32_t nn = G.n_nodes;

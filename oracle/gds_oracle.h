@@ -82,7 +82,9 @@ typedef struct {
     uint32_t gr_levels_pct;   /* ... and at least this % of the last BFS depth */
     uint32_t gr_relabel_pct;  /* trigger when relabels since last GR >= pct% of component nodes */
     uint32_t max_rounds;      /* safety stop (0 = unlimited) */
-    uint32_t seg_len;         /* segment length: references longer than 2*seg_len are cut (0 = 16384) */
+    uint32_t seg_len;         /* segment length: references longer than 2*seg_len are cut (0 = default rule) */
+    uint32_t schedule;        /* 0 = express schedule where eligible (gds_params.schedule), 1 = classic only,
+                                 2 = express for every component that is structurally eligible (lab) */
 } orc_sync_params;
 typedef struct {
     int64_t flow_value; /* total sink inflow over all components */
@@ -93,6 +95,7 @@ typedef struct {
     uint64_t rounds_total, rounds_max; /* summed / max over components */
     uint64_t pushes, relabels, global_relabels, bfs_levels;
     uint64_t max_frontier;
+    uint32_t n_express; /* components that ran the express schedule */
     double t_build_s, t_solve_s, t_select_s;
 } orc_sync_stats;
 /* Batch-aware: sample k owns reads [read_off[k], read_off[k+1]) and positions 0..ref_len[k]-1.

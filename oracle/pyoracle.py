@@ -29,7 +29,7 @@ class RefStats(C.Structure):
 class SyncParams(C.Structure):
     _fields_ = [("gr_interval_min", C.c_uint32), ("gr_levels_pct", C.c_uint32),
                 ("gr_relabel_pct", C.c_uint32),
-                ("max_rounds", C.c_uint32), ("seg_len", C.c_uint32)]
+                ("max_rounds", C.c_uint32), ("seg_len", C.c_uint32), ("schedule", C.c_uint32)]
 
 
 class SyncStats(C.Structure):
@@ -37,7 +37,7 @@ class SyncStats(C.Structure):
                 ("n_bundles", C.c_uint64), ("n_components", C.c_uint32),
                 ("rounds_total", C.c_uint64), ("rounds_max", C.c_uint64), ("pushes", C.c_uint64),
                 ("relabels", C.c_uint64), ("global_relabels", C.c_uint64),
-                ("bfs_levels", C.c_uint64), ("max_frontier", C.c_uint64),
+                ("bfs_levels", C.c_uint64), ("max_frontier", C.c_uint64), ("n_express", C.c_uint32),
                 ("t_build_s", C.c_double), ("t_solve_s", C.c_double), ("t_select_s", C.c_double)]
 
     def as_dict(self):

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(pkg):
     lib = ctypes.CDLL(pkg.lib_path())
     for fn in declared_functions():
         assert hasattr(lib, fn), "libgds_b200.so does not export %s" % fn
-    assert lib.gds_abi_version() == 6
+    assert lib.gds_abi_version() == 7
     assert sorted(pkg.exported_symbols()) == declared_functions()
 
 
@@ -66,7 +66,7 @@ def test_ctypes_structs_match_the_c_header(pkg, tmp_path):
     from genome_downsampler_b200 import binding as B
     probes = [("gds_reads", None), ("gds_filter", None), ("gds_params", None), ("gds_result", None),
               ("gds_kernel_stat", None), ("gds_reads", "start16"), ("gds_reads", "len_min"),
-              ("gds_params", "bundle_mode"), ("gds_params", "algorithm"), ("gds_result", "n_reads_in"), ("gds_result", "fstar"),
+              ("gds_params", "bundle_mode"), ("gds_params", "algorithm"), ("gds_params", "schedule"), ("gds_result", "n_reads_in"), ("gds_result", "fstar"),
               ("gds_result", "kernel_launches"), ("gds_result", "bundle_path"), ("gds_result", "ms_h2d"),
               ("gds_result", "ms_total")]
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "gds.h"', 'int main(void) {']

@@ -550,6 +550,45 @@ def test_maxflow_kernels_agree(solver, O):
         assert_parity(O, a, s, e, Ls, off, M, prm)
 
 
+def test_express_schedule_parity(solver, O):
+    # segments of a cut reference run the express schedule in k_maxflow_sm (zero-length back arcs,
+    # walks past saturated nodes, closed BFS levels): bit-exact against the oracle's replay, for the
+    # default rule, for "classic only", and next to whole samples in the same batch
+    L, M = 200_000, 500
+    s, e, _, _ = O.gen_reads(7, int(L * 1500 / 150 / 2), L, 150)
+    off = np.array([0, len(s)], np.uint64)
+    res = {}
+    for sched in (0, 1):
+        prm = (64, 150, 1, 0, 0, 0, 0, sched)
+        r = solver.solve(s, e, [L], M, read_off=off, params=prm, verify=True, want_vectors=True)
+        st = assert_parity(O, r, s, e, [L], off, M, (64, 150, 1, 0, 0, sched))
+        assert (st.n_express > 0) == (sched == 0)
+        res[sched] = r
+    assert res[0].rounds_total * 2 < res[1].rounds_total and res[0].n_kept != 0
+    # a hole inside some segments (classic there), a whole sample next to the cut one, M = 1000
+    s3, e3, _, _ = O.gen_reads(9, 400_000, 100_000, 150, "hole")
+    s4, e4, _, _ = O.gen_reads(10, 100_000, 30_000, 150)
+    sb = np.concatenate([s3, s4]); eb = np.concatenate([e3, e4])
+    offb = np.array([0, len(s3), len(sb)], np.uint64)
+    r = solver.solve(sb, eb, [100_000, 30_000], 1000, read_off=offb, params=PRM, verify=True,
+                     want_vectors=True)
+    st = assert_parity(O, r, sb, eb, [100_000, 30_000], offb, 1000)
+    assert 0 < st.n_express < st.n_components
+    # the whole sample's bits do not depend on the company it keeps
+    alone = solver.solve(s4, e4, [30_000], 1000, params=PRM)
+    n3 = len(s3)
+    assert n3 % 32 == 0
+    assert np.array_equal(r.kept_bitmap[n3 // 32:], alone.kept_bitmap)
+    # short segments, variable read lengths (heavy cut nodes, several bundles per node)
+    rng = np.random.default_rng(23)
+    s5 = rng.integers(0, 59_000, size=400_000).astype(np.uint32)
+    e5 = (s5 + rng.integers(100, 160, size=400_000)).astype(np.uint32)
+    for prm in ((16, 50, 1, 0, 4096), (64, 150, 1, 0, 8192, 0, 0, 2)):
+        r = solver.solve(s5, e5, [60_000], 300, params=prm, verify=True, want_vectors=True)
+        oprm = prm[:5] + ((prm[7],) if len(prm) > 5 else ())
+        assert_parity(O, r, s5, e5, [60_000], [0, len(s5)], 300, oprm)
+
+
 def test_maxflow_fallback_list(solver, O):
     # components the shared-memory kernel cannot take go to k_maxflow through a device-side list:
     # (a) supply beyond 16 bits (M above the coverage: every rise of the coverage is a source);

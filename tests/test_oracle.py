@@ -216,6 +216,40 @@ def test_segment_split_is_exact_and_costs_at_most_M_reads_per_cut(O):
             assert st.n_kept == base[0]
 
 
+def test_express_schedule_is_a_maximum_flow_with_fewer_rounds(O):
+    # segments of a cut reference take the EXPRESS schedule (zero-length back arcs in the labels):
+    # the same F*, a valid cover, and far fewer rounds and relabel levels than the classic schedule
+    L, M = 200_000, 500
+    s, e, _, _ = O.gen_reads(7, int(L * 1500 / 150 / 2), L, 150)
+    off = [0, len(s)]
+
+    def capped(ss, ee):
+        d = np.zeros(L + 1, np.int64)
+        np.add.at(d, ss, 1)
+        np.add.at(d, ee + 1, -1)
+        return np.minimum(np.cumsum(d)[:L], M)
+
+    want = capped(s, e)
+    out = {}
+    for sched in (0, 1):
+        bm, st = O.sync_solve(s, e, [L], off, M, params=(64, 150, 1, 0, 0, sched))
+        assert st.flow_value == st.fstar == M
+        keep = O.bitmap_to_mask(bm, len(s)) == 1
+        assert np.array_equal(capped(s[keep], e[keep]), want)
+        out[sched] = st.as_dict()
+    assert out[0]["n_express"] == out[0]["n_components"] == 13 and out[1]["n_express"] == 0
+    assert out[0]["rounds_total"] * 2 < out[1]["rounds_total"]
+    assert out[0]["bfs_levels"] * 2 < out[1]["bfs_levels"]
+    # an uncut reference never takes it (results of whole samples do not depend on the batch) ...
+    s2, e2, _, _ = O.gen_reads(8, 100_000, 30_000, 150)
+    _, st2 = O.sync_solve(s2, e2, [30_000], [0, len(s2)], 100, params=(64, 150, 1, 0, 0, 0))
+    assert st2.n_express == 0
+    # ... and a cut one with a hole inside a segment falls back to the classic schedule there
+    s3, e3, _, _ = O.gen_reads(9, 400_000, 100_000, 150, "hole")
+    bm3, st3 = O.sync_solve(s3, e3, [100_000], [0, len(s3)], 1000, params=(64, 150, 1, 0, 0, 0))
+    assert 0 < st3.n_express < st3.n_components and st3.flow_value == st3.fstar
+
+
 def test_batch_equals_per_sample(O):
     # a batch is exactly the concatenation of independent per-sample solves
     parts = [O.gen_reads(100 + k, 3000, 3000, 50) for k in range(3)]
