@@ -926,7 +926,7 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         sp.gr_relabel_pct = prm->gr_relabel_pct;
         sp.max_rounds = prm->max_rounds;
     }
-    const uint32_t seg_len =
+    uint32_t seg_len =
         (prm && prm->seg_len) ? prm->seg_len : default_seg_len(rd->n_samples, rd->ref_len);
     const uint32_t algorithm = prm ? prm->algorithm : 0u;
     const uint32_t schedule = prm ? prm->schedule : 0u;
@@ -1131,6 +1131,13 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             lenbits = bits_for(maxlen - minlen);
         }
         // K4 (generalised): virtual node space — references longer than seg are cut into segments
+        // default rule, one read length R: a whole number of reads per segment.  Every node then
+        // reaches the segment's end in the same number of read hops as its neighbours within one
+        // "lane block", the cut node's bundles are all admissible at once, and a segment of config 4
+        // needs 175 rounds instead of 255 (tools/k3_tail.py).  The oracle rounds the same way.
+        if (!(prm && prm->seg_len) && minlen == maxlen && maxlen > 1)
+            seg_len = (seg_len + maxlen - 1) / maxlen * maxlen;
+        out->seg_len = seg_len;
         const uint32_t seg = seg_len >= maxlen ? seg_len : 0xffffffffu;  // a read crosses <= 1 cut
         std::vector<VSample> hvs(ns);
         std::vector<uint32_t> hcuts;

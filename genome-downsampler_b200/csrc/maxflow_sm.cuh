@@ -575,35 +575,33 @@ __device__ __forceinline__ uint32_t mf2_bfs(Mf2Shared& sh, bool first, unsigned 
         if (cnt == 0) break;
         ++bfs_levels;
         if (express) {
-            // zero-length back arcs: the level is closed under "right neighbour" first.  One warp
-            // per seed: the run from the seed to the next visited node gets the seed's label, its
-            // visited bits, and joins this level's queue (runs of different seeds are disjoint).
+            // zero-length back arcs: the level is closed under "right neighbour" first: the run from
+            // a seed to the next visited node gets the seed's label and its visited bits and joins
+            // this level's queue (runs of different seeds are disjoint).  On dense data a level is
+            // the previous one shifted by a read length and nearly every seed's right neighbour is
+            // already visited: one thread per seed checks that bit and walks the rare run itself.
             uint32_t* vis = mf2_smem(C.bmA_off);
             uint16_t* lab = reinterpret_cast<uint16_t*>(mf2_smem(C.word_off));
-            const uint32_t lane = lane_id();
+            const uint32_t wn = (n + 31u) >> 5;
 #pragma unroll 1
-            for (uint32_t i = tid >> 5; i < cnt; i += THREADS / 32) {
+            for (uint32_t i = mf2_slot<THREADS>(); i < cnt; i += THREADS) {
                 const uint32_t x = T.get(i) + 1;  // first node of the run
                 if (x >= n) continue;
                 uint32_t wi = x >> 5;
                 uint32_t m = vis[wi] & (0xffffffffu << (x & 31));
-                const uint32_t wn = (n + 31u) >> 5;
+                if ((m >> (x & 31)) & 1u) continue;  // no run
 #pragma unroll 1
                 while (m == 0 && ++wi < wn) m = vis[wi];
                 uint32_t e = m ? (wi << 5) + (uint32_t)__ffs((int)m) - 1u : n;
                 if (e > n) e = n;
-                const uint32_t len = e - x;
-                if (len == 0) continue;
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(&sh.lc[(level - 1) % 3], len);
-                base = __shfl_sync(0xffffffffu, base, 0);
+                const uint32_t base = atomicAdd(&sh.lc[(level - 1) % 3], e - x);
 #pragma unroll 1
-                for (uint32_t j = lane; j < len; j += 32) {
-                    lab[2 * (x + j)] = (uint16_t)level;
-                    T.put(base + j, x + j);
+                for (uint32_t j = x; j < e; ++j) {
+                    lab[2 * j] = (uint16_t)level;
+                    T.put(base + (j - x), j);
                 }
 #pragma unroll 1
-                for (uint32_t w2 = (x >> 5) + lane; w2 <= ((e - 1) >> 5); w2 += 32) {
+                for (uint32_t w2 = x >> 5; w2 <= ((e - 1) >> 5); ++w2) {
                     uint32_t mask = 0xffffffffu;
                     if (w2 == (x >> 5)) mask &= 0xffffffffu << (x & 31);
                     if (w2 == ((e - 1) >> 5)) mask &= 0xffffffffu >> (31u - ((e - 1) & 31));
@@ -809,7 +807,8 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
             const uint32_t cntF = sh.nF;
             bool relabel = first;
             if (!first && cntF != 0 && !(P.max_rounds && rounds >= P.max_rounds)) {
-                unsigned long long interval = (unsigned long long)last_levels * P.gr_levels_pct / 100;
+                // (express: a level is a whole read hop, and lane changes cost rounds but no levels)
+                unsigned long long interval = (unsigned long long)last_levels * P.gr_levels_pct / 100 * (2u - bl);
                 if (interval < P.gr_interval_min) interval = P.gr_interval_min;
                 relabel = rounds_since >= interval &&
                           (unsigned long long)sh.relabels_since * 100 >=

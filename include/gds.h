@@ -70,7 +70,10 @@ typedef struct {
     /* optional: exact bounds of end-start+1 over all reads (0,0 = unknown).  A caller that
      * narrows the reference's size_t arrays anyway has them for free; with them the device folds
      * input validation into the first pass of the sort instead of a separate pass over the
-     * reads.  Reads outside the bounds fail the call with GDS_ERR_ARG. */
+     * reads.  Reads outside the bounds fail the call with GDS_ERR_ARG.  The bounds have to be the
+     * exact minimum and maximum: the default segment length of a long reference depends on whether
+     * all reads have one length (gds_params.seg_len), so looser bounds may select another — equally
+     * valid — kept set than a call without them. */
     uint32_t len_min, len_max;
     /* optional compact transport of the start column: 16-bit starts (every ref_len <= 65536).
      * With fixed-length reads (end == NULL) a read then crosses PCIe as 2 bytes instead of 8; the
@@ -100,8 +103,10 @@ typedef struct {
  * 32768).  0 = the default rule: 16384, stretched in steps of 128 by up to a quarter when that
  * brings the number of segments of the whole batch down to 296 — two resident components per SM of
  * a B200, so that no second wave of a few left-over segments runs (config 4: 5 Mb -> 296 segments
- * of 16896 instead of 306).  The rule is a constant of the schedule, not a device query: the same
- * input gives the same kept set on every device.  gds_result.seg_len reports the value used. */
+ * of 16896 instead of 306), then rounded up to a whole number of reads when all reads have one
+ * length (16950 = 113 x 150: 295 segments).  The rule is a constant of the schedule, not a device
+ * query: the same input gives the same kept set on every device.  gds_result.seg_len reports the
+ * value used. */
 typedef struct {
     uint32_t gr_interval_min;
     uint32_t gr_levels_pct;

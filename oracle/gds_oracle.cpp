@@ -604,7 +604,11 @@ int build_sync_graph(uint32_t n_samples, const uint64_t* read_off, const uint32_
             maxlen = std::max(maxlen, len);
         }
     if (N == 0) minlen = maxlen = 1;
-    if (seg_len == 0) seg_len = default_seg_len(n_samples, ref_len);
+    if (seg_len == 0) {
+        seg_len = default_seg_len(n_samples, ref_len);
+        // one read length: a whole number of reads per segment (csrc/gds_api.cu, same rounding)
+        if (minlen == maxlen && maxlen > 1) seg_len = (seg_len + maxlen - 1) / maxlen * maxlen;
+    }
     const uint32_t seg = seg_len >= maxlen ? seg_len : 0xffffffffu;  // a read crosses <= 1 cut
     G.vs.resize(n_samples);
     uint32_t ob = 0, vb = 0;
@@ -873,7 +877,9 @@ void sync_solve_component(const SyncGraph& G, SyncState& S, uint32_t lo, uint32_
     while (!F.empty()) {
         if (P.max_rounds && cs.rounds >= P.max_rounds) break;
         // deterministic global-relabel trigger (state-only)
-        uint64_t interval = std::max<uint64_t>(P.gr_interval_min, (uint64_t)last_levels * P.gr_levels_pct / 100);
+        // (express: a level is a whole read hop, and lane changes cost rounds but no levels: twice the interval)
+        uint64_t interval = std::max<uint64_t>(P.gr_interval_min,
+                                               (uint64_t)last_levels * P.gr_levels_pct / 100 * (2u - bl));
         if (rounds_since >= interval &&
             relabels_since * 100 >= (uint64_t)P.gr_relabel_pct * ncomp) {
             last_levels = sync_global_relabel(G, S, lo, hi, cs, express);

@@ -262,13 +262,13 @@ def test_c4_full_size_properties(solver, O):
     assert r.fstar == 500 == r.flow_value and r.verify_violations == 0
     assert int(np.maximum(0, -r.demand.astype(np.int64)).sum()) == 500
     assert int(r.demand.astype(np.int64).sum()) == 0
-    # the default segment rule (include/gds.h gds_params.seg_len): 296 segments of 16 896 positions —
-    # all resident at once on a B200 — instead of 306 of 16 384
-    assert r.seg_len == 16896 and r.n_components == 296
+    # the default segment rule (include/gds.h gds_params.seg_len): 295 segments of 16 950 positions
+    # (113 reads) — all resident at once on a B200 — instead of 306 of 16 384
+    assert r.seg_len == 16950 and r.n_components == 295
     # quality: every read covers R positions, so no valid answer keeps fewer than
     # M*L/R reads; each of the 295 cuts may cost up to M more.  Within 1 % of that lower bound.
     lower = 500 * 5_000_000 / 150
-    assert 0 <= r.n_kept - lower < 1000 + 295 * 500
+    assert 0 <= r.n_kept - lower < 1000 + 294 * 500
     assert r.n_kept <= 1.01 * lower
     mask_bits = int(np.unpackbits(r.kept_bitmap.view(np.uint8)).sum())
     assert mask_bits == r.n_kept
