@@ -145,13 +145,26 @@ __attribute__((target("avx2"))) void enc_range_avx2(const uint32_t* start, const
     uint64_t i = b;
     __m256i vbig = _mm256_setzero_si256();
     __m256i vlo = _mm256_set1_epi32(-1), vhi = _mm256_setzero_si256();
+    // the 16-bit column is read next by the copy engine, not by this core: once the output is
+    // 32-byte aligned it is written with streaming stores (no read-for-ownership of 2 bytes per
+    // read, nothing evicted from the caches)
+    for (; i < e && (reinterpret_cast<uintptr_t>(out + i) & 31u); ++i) {
+        const uint32_t s = start[i];
+        out[i] = static_cast<uint16_t>(s);
+        p.big |= s;
+        if (end) {
+            const uint32_t len = end[i] - s + 1;
+            p.lo = std::min(p.lo, len);
+            p.hi = std::max(p.hi, len);
+        }
+    }
     for (; i + 16 <= e; i += 16) {
         const __m256i s0 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(start + i));
         const __m256i s1 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(start + i + 8));
         vbig = _mm256_or_si256(vbig, _mm256_or_si256(s0, s1));
         // packus saturates, which is fine: a start beyond 16 bits fails the call anyway
         const __m256i pk = _mm256_permute4x64_epi64(_mm256_packus_epi32(s0, s1), 0xD8);
-        _mm256_storeu_si256(reinterpret_cast<__m256i*>(out + i), pk);
+        _mm256_stream_si256(reinterpret_cast<__m256i*>(out + i), pk);
         if (end) {
             const __m256i one = _mm256_set1_epi32(1);
             const __m256i l0 = _mm256_add_epi32(
@@ -162,6 +175,7 @@ __attribute__((target("avx2"))) void enc_range_avx2(const uint32_t* start, const
             vhi = _mm256_max_epu32(vhi, _mm256_max_epu32(l0, l1));
         }
     }
+    _mm_sfence();
     alignas(32) uint32_t t[8];
     _mm256_store_si256(reinterpret_cast<__m256i*>(t), vbig);
     for (uint32_t x : t) p.big |= x;
