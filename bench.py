@@ -127,7 +127,7 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def traffic_for(kernel, alg_bytes_per_launch):
+def traffic_for(kernel, alg_bytes_per_launch, workload=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed
     ncu --set full capture (profiles/traffic.json holds measured DRAM bytes per sorted item; the
     scatter kernels' algorithmic bytes are 16 per item), or None when no capture covers it."""
@@ -139,6 +139,7 @@ def traffic_for(kernel, alg_bytes_per_launch):
     if per_item is not None:
         return int(per_item * alg_bytes_per_launch / 16.0)
     ratio = t.get("per_alg_byte", {}).get(kernel)  # measured DRAM bytes per algorithmic byte
+    ratio = t.get("per_alg_byte_by_workload", {}).get(workload or "", {}).get(kernel, ratio)
     return None if ratio is None else int(ratio * alg_bytes_per_launch)
 
 
@@ -683,7 +684,7 @@ def run_b200(args, wl, wname):
         per_launch = int(top["alg_bytes_per_step"] / max(top["launches_per_step"], 1))
         roofline = {"bound": "hbm", "kernel": top["name"], "achieved": top["gbs"], "peak": peak,
                     "unit": "GB/s", "frac": top["frac"],
-                    "traffic": traffic_for(top["name"], per_launch),
+                    "traffic": traffic_for(top["name"], per_launch, args.workload),
                     "peak_source": peak_src, "alg_bytes_per_launch": per_launch,
                     "note": ("K3 is bound by the latency of its dependent rounds (rounds x us, see "
                              "result.k3), not by HBM; the streaming kernels are listed in kernels[]")

@@ -18,6 +18,7 @@ def main():
     pkg, O = load_package(), load_oracle()
     solver = pkg.Solver(0)
     bad = 0
+    n_express = 0
     for it in range(n_cases):
         ns = int(rng.integers(1, 6))
         Ls = rng.integers(1, int(rng.choice([50, 400, 5000, 40000])), size=ns).astype(np.uint32)
@@ -42,6 +43,9 @@ def main():
         M = int(rng.choice([1, 3, 10, 50, 400]))
         seg = int(rng.choice([0, 0, 37, 150, 1000, 0xffffffff]))
         prm = (int(rng.integers(1, 100)), int(rng.integers(0, 300)), int(rng.integers(0, 5)), 0, seg)
+        # gds_params.schedule: express where eligible / classic only / express for every component
+        # that is structurally eligible (not only segments of cut references)
+        sched = int(rng.choice([0, 0, 1, 2, 2]))
         hint = None
         lens = e - s + 1
         if len(s) and rng.integers(0, 2):
@@ -57,9 +61,10 @@ def main():
             if Ls.max() <= 65536 and rng.integers(0, 2):
                 s_in = s.astype(np.uint16)
         try:
-            r = solver.solve(s_in, e_in, Ls, M, read_off=off, params=prm + (bmode,), verify=True,
+            r = solver.solve(s_in, e_in, Ls, M, read_off=off, params=prm + (bmode, 0, sched), verify=True,
                              want_vectors=True, len_hint=hint)
-            bm, st, dem, cov = O.sync_solve(s, e, Ls, off, M, params=prm, want_vectors=True)
+            bm, st, dem, cov = O.sync_solve(s, e, Ls, off, M, params=prm + (sched,), want_vectors=True)
+            n_express += st.n_express
             ok = (r.fstar == st.fstar == r.flow_value == st.flow_value and
                   np.array_equal(r.demand, dem) and np.array_equal(r.cov_capped, np.minimum(cov, M))
                   and r.n_kept == st.n_kept and np.array_equal(r.kept_bitmap, bm)
@@ -75,11 +80,11 @@ def main():
         if not ok:
             bad += 1
             print("MISMATCH case %d: ns=%d n=%d Ls=%s M=%d prm=%s hint=%s bundle_mode=%d walk=%s "
-                  "compact=%s" % (it, ns, len(s), Ls.tolist(), M, prm, hint, bmode, walk,
-                                  (e_in is None, s_in.dtype.name)), flush=True)
+                  "compact=%s schedule=%d" % (it, ns, len(s), Ls.tolist(), M, prm, hint, bmode, walk,
+                                  (e_in is None, s_in.dtype.name), sched), flush=True)
             if bad > 5:
                 break
-    print("fuzz: %d cases, %d mismatches" % (it + 1, bad))
+    print("fuzz: %d cases, %d mismatches, %d components on the express schedule" % (it + 1, bad, n_express))
     return 1 if bad else 0
 
 
