@@ -76,9 +76,14 @@ def log(*a):
 ALGORITHM = "quasi-mcp"   # --algorithm: "quasi-mcp" (push-relabel max flow) or "mcp" (minimum cardinality)
 
 
+SEG_LEN = 0
+
+
 def solver_params():
-    """gds_params for the chosen algorithm (None = library defaults)."""
-    return (0, 0, 0, 0, 0, 0, 1) if ALGORITHM == "mcp" else None
+    """gds_params for the chosen algorithm and segment length (None = library defaults)."""
+    if ALGORITHM != "mcp" and not SEG_LEN:
+        return None
+    return (0, 0, 0, 0, SEG_LEN, 0, 1 if ALGORITHM == "mcp" else 0)
 
 
 def config_for(wname, wl):
@@ -90,7 +95,8 @@ def config_for(wname, wl):
             "max_coverage": wl["M"], "seed": wl["seed"],
             "pair_filter": wl.get("filter"), "law": wl.get("shape", "uniform"),
             "algorithm": "quasi-MCP (maximum flow)" if ALGORITHM == "quasi-mcp"
-            else "MCP (minimum number of reads, mcp-cpu's objective)"}
+            else "MCP (minimum number of reads, mcp-cpu's objective)",
+            **({"seg_len": SEG_LEN} if SEG_LEN else {})}
 
 
 def host_threads():
@@ -793,12 +799,16 @@ def main():
     ap.add_argument("--weak", action="store_true",
                     help="N > 1: every rank takes the workload's full sample count (weak scaling) "
                          "instead of a share of the one batch (default, strong scaling)")
+    ap.add_argument("--seg-len", type=int, default=0,
+                    help="gds_params.seg_len (0 = the library's default rule); an experiment knob: the "
+                         "config line then says so")
     ap.add_argument("--algorithm", default="quasi-mcp", choices=["quasi-mcp", "mcp"],
                     help="quasi-mcp: maximum flow by push-relabel (the north-star path, default); mcp: the "
                          "minimum-cardinality solve (gds_params.algorithm = 1, plugin mcp-b200)")
     args = ap.parse_args()
-    global ALGORITHM
+    global ALGORITHM, SEG_LEN
     ALGORITHM = args.algorithm
+    SEG_LEN = args.seg_len
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
