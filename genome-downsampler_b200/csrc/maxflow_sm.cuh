@@ -97,13 +97,6 @@ __device__ __forceinline__ uint32_t g_ld(const void* p) {
     asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// Load that nobody waits for: brings the 32-byte sector into this SM's L1 so that the round that
-// needs it finds it there (an L1 hit is ~40 clocks, a trip to L2 ~800 on this part — tools/lat_probe.cu;
-// only this CTA writes the sectors it touches, and its stores update the L1 copy).
-__device__ __forceinline__ void g_touch(const void* p) {
-    uint32_t dummy;
-    asm volatile("ld.global.u32 %0, [%1];" : "=r"(dummy) : "l"(p));
-}
 __device__ __forceinline__ void g_st(void* p, uint32_t v) {
     asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -180,26 +173,16 @@ constexpr uint32_t kMf2HeaderBytes = (sizeof(Mf2Shared) + 15u) & ~15u;
 
 __device__ __forceinline__ uint32_t mf2_label(const uint32_t* word, uint32_t w) { return word[w] & 0xffffu; }
 
-// Node w will be in the next frontier: start fetching what its push reads — its record, the
-// neighbour's half record and its farthest-end bundle — one round ahead.
-__device__ __forceinline__ void mf2_warm(const Mf2Comp& C, uint32_t w) {
-    const NodeRec* nr = C.G.node + C.lo + w;
-    g_touch(nr);
-    g_touch(reinterpret_cast<const uint4*>(nr + 1) + 1);
-    if (C.have_optr) {
-        const uint16_t* optr = reinterpret_cast<const uint16_t*>(mf2_smem(C.optr_off));
-        const uint32_t ob = optr[w], oe = optr[w + 1];
-        if (oe > ob) g_touch(C.G.bund + C.obase + oe - 1);
-    }
-}
-
+// (Prefetching the records of next round's frontier nodes into L1 was tried twice: as loads nobody
+// waits for — which ptxas removes, so that version never ran — and as prefetch.global.L1 (CCTL.PF1):
+// config 1's phase A 2 560 -> 2 690 clocks per round, the "hole" shape 6 850 -> 7 460, config 4
+// 5 640 -> 5 470.  Not kept.)
 // receive dl units at node w: the first giver of the round queues w unless it is in the frontier
 __device__ __forceinline__ void mf2_give(Mf2Shared& sh, uint32_t w, uint32_t dl) {
     const Mf2Comp& C = sh.C;
     const uint32_t old = atomicAdd(&mf2_smem(C.word_off)[w], dl << 16);
     if ((old >> 16) == 0 && !((mf2_smem(C.inF_off)[w >> 5] >> (w & 31)) & 1u)) {
         q2_append(C.T, &sh.nT, w);
-        mf2_warm(C, w);
     }
 }
 
@@ -886,7 +869,6 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
                 }
                 const uint32_t ib = hi4.w, ie = r_hi.w;
                 c_bid = ie > ib ? lo4.y : 0u;  // nodes without in-arcs carry no valid id
-                if (ie > ib) g_touch(G.bund + c_bid);  // a relabel in B1 reads its flow
                 if ((oe - ob) + (ie - ib) > kHeavyDeg) {
                     q2_append(H, &sh.nH, i);
                     continue;
