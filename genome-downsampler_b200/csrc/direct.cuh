@@ -456,10 +456,14 @@ k_direct_mark(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, Di
     if (lane == 0 && kept) atomicAdd(&totals[1], (unsigned long long)kept);
 }
 
-// One warp per partial bundle: keep the f lowest of its candidate read indices.  Up to 32
-// candidates (the common case; config 4 has 1.7 M partial bundles of ~10 reads) are ranked against
-// each other through shuffles, n steps; larger bundles find the f-th lowest index by bisection on
-// the index value (count = ballots over the candidates, in registers up to 128 of them).
+// Partial bundles: keep the f lowest of a bundle's candidate read indices.  Up to 16 candidates (the
+// common case with segments: config 4 has 1.7 M partial bundles of ~10 reads) take HALF a warp — two
+// bundles per warp and step, ranked against each other through 16 shuffles (0.29 -> 0.20 ms there);
+// larger ones get the whole warp: up to 32 candidates the same way, beyond that the f-th lowest index
+// by bisection on the index value (count = ballots over the candidates, in registers up to 128 of
+// them).  (Packing a bundle's segment start and fill count into one 64-bit word, parked with one
+// 64-bit atomic instead of a load and a 32-bit atomic, was measured too: the mark kernel of config 4
+// went 0.71 -> 0.79 ms.  Not kept.)
 __global__ void __launch_bounds__(256)
 k_direct_partial(const uint32_t* __restrict__ pb_off, const uint32_t* __restrict__ pb_f,
                  const uint32_t* __restrict__ pb_fill, const uint32_t* __restrict__ cand,
@@ -475,15 +479,16 @@ k_direct_partial(const uint32_t* __restrict__ pb_off, const uint32_t* __restrict
         kept += (atomicOr(&bitmap[v >> 5], bit) & bit) ? 0u : 1u;
     };
     constexpr int kReg = 4;
-    for (uint32_t pid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pid < n_partial; pid += warps) {
+    // the whole warp on one bundle
+    auto whole_warp = [&](uint32_t pid, uint32_t n) {
         const uint32_t* c = cand + pb_off[pid];
-        const uint32_t n = pb_fill[pid], f = pb_f[pid];
+        const uint32_t f = pb_f[pid];
         if (n <= 32) {
             const uint32_t x = lane < n ? c[lane] : 0xffffffffu;
             uint32_t rank = 0;
             for (uint32_t j = 0; j < n; ++j) rank += __shfl_sync(0xffffffffu, x, j) < x;
             if (lane < n && rank < f) keep(x);
-            continue;
+            return;
         }
         uint32_t x[kReg];
         uint32_t mn = 0xffffffffu, mx = 0;
@@ -518,6 +523,26 @@ k_direct_partial(const uint32_t* __restrict__ pb_off, const uint32_t* __restrict
             if (x[r] <= lo) keep(x[r]);  // the padding value is above every index
         for (uint32_t i = kReg * 32 + lane; i < n; i += 32)
             if (c[i] <= lo) keep(c[i]);
+    };
+    const uint32_t half = lane >> 4, hl = lane & 15u;
+    for (uint32_t p0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2; p0 < n_partial; p0 += 2 * warps) {
+        const uint32_t pid = p0 + half;
+        const bool valid = pid < n_partial;
+        const uint32_t n = valid ? pb_fill[pid] : 0u;
+        const bool small = valid && n <= 16;
+        if (__any_sync(0xffffffffu, small)) {  // (config 5's bundles hold ~67 candidates: never)
+            const uint32_t f = small ? pb_f[pid] : 0u;
+            const uint32_t x = small && hl < n ? cand[pb_off[pid] + hl] : 0xffffffffu;
+            uint32_t rank = 0;
+#pragma unroll
+            for (uint32_t j = 0; j < 16; ++j) rank += __shfl_sync(0xffffffffu, x, (lane & 16u) | j) < x;
+            if (small && hl < n && rank < f) keep(x);
+        }
+        // bundles beyond half a warp: one after the other, all lanes
+        const uint32_t big = __ballot_sync(0xffffffffu, valid && !small && hl == 0);
+        const uint32_t n0 = __shfl_sync(0xffffffffu, n, 0), n1 = __shfl_sync(0xffffffffu, n, 16);
+        if (big & 1u) whole_warp(p0, n0);
+        if (big & 0x10000u) whole_warp(p0 + 1, n1);
     }
     kept = __reduce_add_sync(0xffffffffu, kept);
     if (lane == 0 && kept) atomicAdd(&totals[1], (unsigned long long)kept);
