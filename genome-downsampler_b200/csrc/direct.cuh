@@ -464,6 +464,8 @@ k_direct_mark(const uint32_t* __restrict__ S, const uint32_t* __restrict__ E, Di
 // them).  (Packing a bundle's segment start and fill count into one 64-bit word, parked with one
 // 64-bit atomic instead of a load and a 32-bit atomic, was measured too: the mark kernel of config 4
 // went 0.71 -> 0.79 ms.  Not kept.)
+// HALF = false (bundles of whole 30 kb samples hold ~67 reads: config 5): one warp per bundle only.
+template <bool HALF>
 __global__ void __launch_bounds__(256)
 k_direct_partial(const uint32_t* __restrict__ pb_off, const uint32_t* __restrict__ pb_f,
                  const uint32_t* __restrict__ pb_fill, const uint32_t* __restrict__ cand,
@@ -524,8 +526,13 @@ k_direct_partial(const uint32_t* __restrict__ pb_off, const uint32_t* __restrict
         for (uint32_t i = kReg * 32 + lane; i < n; i += 32)
             if (c[i] <= lo) keep(c[i]);
     };
+    if (!HALF) {
+        for (uint32_t pid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; pid < n_partial; pid += warps)
+            whole_warp(pid, pb_fill[pid]);
+    }
     const uint32_t half = lane >> 4, hl = lane & 15u;
-    for (uint32_t p0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2; p0 < n_partial; p0 += 2 * warps) {
+    for (uint32_t p0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 2; HALF && p0 < n_partial;
+         p0 += 2 * warps) {
         const uint32_t pid = p0 + half;
         const bool valid = pid < n_partial;
         const uint32_t n = valid ? pb_fill[pid] : 0u;

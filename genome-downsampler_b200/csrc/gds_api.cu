@@ -696,8 +696,12 @@ void direct_select(gds_ctx* c, const DirectPlan& dp, const uint32_t* S, const ui
             }
             if (hctl[0]) {
                 KScope ks("direct_partial", dp.lazy ? 16ull * (N / 64) : 16ull * hctl[0] + 4ull * hctl[1], st);
-                k_direct_partial<<<kNumSMs * 32, 256, 0, st>>>(pb, pb + B + 1, fill, cand, ctl, bm,
-                                                              totals);
+                if (dp.global)  // segments of a long reference: ~10 reads per bundle, half a warp each
+                    k_direct_partial<true><<<kNumSMs * 32, 256, 0, st>>>(pb, pb + B + 1, fill, cand, ctl,
+                                                                        bm, totals);
+                else
+                    k_direct_partial<false><<<kNumSMs * 32, 256, 0, st>>>(pb, pb + B + 1, fill, cand, ctl,
+                                                                         bm, totals);
                 GDS_KERNEL_CHECK();
             }
             if (dp.lazy)
