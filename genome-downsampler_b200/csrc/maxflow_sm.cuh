@@ -750,12 +750,16 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
                 }
             }
             if (have_optr && tid == 0) optr[n] = (uint16_t)n_bund;
-            if (G.express_on)  // is this a segment of a cut reference?
-                for (uint32_t k = tid; k < G.n_samples; k += THREADS) {
-                    const VSample vk = G.vs[k];
-                    const bool inside = lo >= vk.vbase && (k + 1 == G.n_samples || lo < G.vs[k + 1].vbase);
-                    if (inside && vk.nseg > 1 && vk.W <= kExpressMaxNodes) sh.seg_sample = 1;
+            if (G.express_on && tid == 0) {  // is this a segment of a cut reference?
+                uint32_t a = 0, b = G.n_samples;  // largest k with vs[k].vbase <= lo
+                while (b - a > 1) {
+                    const uint32_t mid = (a + b) >> 1;
+                    if (G.vs[mid].vbase <= lo) a = mid;
+                    else b = mid;
                 }
+                const VSample vk = G.vs[a];
+                if (vk.nseg > 1 && vk.W <= kExpressMaxNodes) sh.seg_sample = 1;
+            }
             my_supply = __reduce_add_sync(0xffffffffu, my_supply);
             if (lane == 0 && my_supply) atomicAdd(&sh.supply, min(my_supply, 0x10000u));
         }

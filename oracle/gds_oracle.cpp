@@ -823,10 +823,14 @@ bool express_component(const SyncGraph& G, uint32_t lo, uint32_t hi, uint32_t sc
     if (schedule == 1) return false;
     const uint32_t n = hi - lo + 1;
     if (schedule != 2) {
-        bool seg = false;
-        for (const VSample& v : G.vs)
-            if (lo >= v.vbase && lo < v.vbase + v.vn) seg = v.nseg > 1 && v.W <= kExpressMaxNodes;
-        if (!seg) return false;
+        size_t a = 0, b = G.vs.size();  // the sample holding node lo (vbase ascending)
+        while (b - a > 1) {
+            const size_t mid = (a + b) / 2;
+            if (G.vs[mid].vbase <= lo) a = mid;
+            else b = mid;
+        }
+        const VSample& v = G.vs[a];
+        if (!(v.nseg > 1 && v.W <= kExpressMaxNodes)) return false;
     }
     if (n > kExpressMaxNodes) return false;
     const uint64_t n_bund = G.out_ptr[hi + 1] - G.out_ptr[lo];
