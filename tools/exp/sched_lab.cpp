@@ -2,6 +2,15 @@
 // oracle/gds_oracle.cpp on a single-length, single-component instance, with switches for
 // experimental variants.  Prints rounds / pushes / relabels and optionally a per-round trace.
 // build: g++ -O2 -std=c++17 -o tools/exp/sched_lab tools/exp/sched_lab.cpp
+// usage: sched_lab [L=..] [R=..] [cov=..] [M=..] [seed=..] [shape=0|1] [file=starts.u32] [trace=N]
+//                  [gri=..] [grl=..] [grr=..] [K=gate spacing] [variant=bits]
+// variant bits: 1 relabel count alone may trigger a global relabel; 2 walk the chain of admissible
+// back arcs (unit lengths); 4 back arcs have length 0 (+ walk); 8 no walk; 16 walk stops on
+// label-admissible bundles regardless of saturation; 32 walk stops on the saturation bit only (what
+// the device does: variant 36 = the express schedule); 64 warm start: bundles covering a position
+// with cov <= M start saturated; 128 the same bundles leave the graph and the back arcs over such
+// positions are cut (variant 164 = that + the express schedule).
+// file= takes the reference generator's reads (oracle: gen_reads(...)[0].tofile(path)).
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
@@ -15,6 +24,8 @@ struct G {
     uint32_t n;  // nodes 0..n-1 (n = L+1)
     vector<uint32_t> bs, bt, bm, out_ptr, in_ptr, in_bid;
     vector<int32_t> dem;
+    vector<uint32_t> unc;  // unc[v] = number of positions p < v with cov[p] <= M
+    vector<uint8_t> cut;   // cut[v]: the back arc v -> v-1 does not exist (position v-1 is not capped)
 };
 struct Opt {
     int K = 0;
@@ -43,11 +54,11 @@ static uint32_t global_relabel0(const G& g, vector<uint32_t>& d, const vector<in
         // closure: everything to the right of a level node, up to the next labelled node
         size_t k0 = cur.size();
         for (size_t i = 0; i < k0; ++i)
-            for (uint32_t u = cur[i] + 1; u < g.n && d[u] == INF && blen(u) == 0; ++u) { d[u] = level; cur.push_back(u); }
+            for (uint32_t u = cur[i] + 1; u < g.n && d[u] == INF && blen(u) == 0 && !g.cut[u]; ++u) { d[u] = level; cur.push_back(u); }
         nxt.clear();
         auto visit = [&](uint32_t u) { if (d[u] == INF) { d[u] = level + 1; nxt.push_back(u); } };
         for (uint32_t w : cur) {
-            if (w + 1 < g.n && blen(w + 1)) visit(w + 1);  // gate arc (w+1) -> w, length 1
+            if (w + 1 < g.n && blen(w + 1) && !g.cut[w + 1]) visit(w + 1);  // gate arc (w+1) -> w, length 1
             if (w > 0 && gb[w] > 0) visit(w - 1);
             for (uint32_t k = g.in_ptr[w]; k < g.in_ptr[w + 1]; ++k) { uint32_t b = g.in_bid[k]; if (f[b] < g.bm[b]) visit(g.bs[b]); }
             for (uint32_t b = g.out_ptr[w]; b < g.out_ptr[w + 1]; ++b) if (f[b] > 0) visit(g.bt[b]);
@@ -70,7 +81,7 @@ static uint32_t global_relabel(const G& g, vector<uint32_t>& d, const vector<int
         nxt.clear();
         auto visit = [&](uint32_t u) { if (d[u] == INF) { d[u] = level + 1; nxt.push_back(u); } };
         for (uint32_t w : cur) {
-            if (w + 1 < g.n) visit(w + 1);
+            if (w + 1 < g.n && !g.cut[w + 1]) visit(w + 1);
             if (w > 0 && gb[w] > 0) visit(w - 1);
             for (uint32_t k = g.in_ptr[w]; k < g.in_ptr[w + 1]; ++k) { uint32_t b = g.in_bid[k]; if (f[b] < g.bm[b]) visit(g.bs[b]); }
             for (uint32_t b = g.out_ptr[w]; b < g.out_ptr[w + 1]; ++b) if (f[b] > 0) visit(g.bt[b]);
@@ -85,7 +96,20 @@ static St solve(const G& g, const Opt& o) {
     const uint32_t n = g.n;
     vector<uint32_t> d(n), f(g.bs.size(), 0), stamp(n, 0);
     vector<int32_t> e(n), eadd(n, 0), snk(n), gb(n, 0);
-    for (uint32_t v = 0; v < n; ++v) { e[v] = g.dem[v] < 0 ? -g.dem[v] : 0; snk[v] = g.dem[v] > 0 ? g.dem[v] : 0; }
+    vector<int32_t> dem = g.dem;
+    if (o.variant & 64) {  // warm start: bundles that cover a position with cov <= M are saturated up front
+        uint64_t forced = 0, forced_reads = 0;
+        for (size_t b = 0; b < g.bs.size(); ++b)
+            if (g.unc[g.bt[b]] - g.unc[g.bs[b]] > 0) {
+                f[b] = g.bm[b];
+                dem[g.bs[b]] += (int32_t)g.bm[b];
+                dem[g.bt[b]] -= (int32_t)g.bm[b];
+                ++forced; forced_reads += g.bm[b];
+            }
+        printf("  warm start: %lu of %zu bundles forced (%lu reads)\n", (unsigned long)forced, g.bs.size(), (unsigned long)forced_reads);
+    }
+
+    for (uint32_t v = 0; v < n; ++v) { e[v] = dem[v] < 0 ? -dem[v] : 0; snk[v] = dem[v] > 0 ? dem[v] : 0; }
     const bool z = o.variant & 4;
     g_K = o.K;
     auto BL = [&](uint32_t v) -> uint32_t { return z ? blen(v) : 1u; };  // length of back arc v -> v-1
@@ -124,7 +148,7 @@ static St solve(const G& g, const Opt& o) {
                 int32_t dl = min<uint32_t>(ex, r); f[b] += dl; ex -= dl; give(t, dl);
             }
             if (ex > 0 && v + 1 < n && d[v + 1] + 1 == dv && gb[v + 1] > 0) { int32_t dl = min(ex, gb[v + 1]); gb[v + 1] -= dl; ex -= dl; give(v + 1, dl); }
-            if (ex > 0 && v > 0 && d[v - 1] + BL(v) == dv) {
+            if (ex > 0 && v > 0 && !g.cut[v] && d[v - 1] + BL(v) == dv) {
                 if ((o.variant & 6) && !(o.variant & 8)) {
                     // walk the chain of admissible back arcs until a node that could use the excess
                     // (decided from labels and the start-of-round saturation snapshot only)
@@ -133,9 +157,9 @@ static St solve(const G& g, const Opt& o) {
                         gb[u] += ex;
                         --u;
                         ++walk_steps;
-                        bool stop = u == 0 || (d[u] == 1 && snk0[u] > 0) || d[u - 1] + BL(u) != d[u];
+                        bool stop = u == 0 || g.cut[u] || (d[u] == 1 && snk0[u] > 0) || d[u - 1] + BL(u) != d[u];
                         if (o.variant & 32) {  // saturation bit only: sink capacity or any unsaturated own bundle
-                            stop = u == 0 || snk0[u] > 0 || d[u - 1] + BL(u) != d[u];
+                            stop = u == 0 || g.cut[u] || snk0[u] > 0 || d[u - 1] + BL(u) != d[u];
                             for (uint32_t b = g.out_ptr[u]; !stop && b < g.out_ptr[u + 1]; ++b)
                                 if (f0[b] < g.bm[b]) stop = true;
                         }
@@ -165,7 +189,7 @@ static St solve(const G& g, const Opt& o) {
                 if (snk[w] > 0) mn = 0;
                 for (uint32_t b = g.out_ptr[w]; b < g.out_ptr[w + 1]; ++b) if (f[b] < g.bm[b]) mn = min(mn, d[g.bt[b]]);
                 if (w + 1 < n && gb[w + 1] > 0) mn = min(mn, d[w + 1]);
-                if (w > 0) mn = min(mn, d[w - 1] + BL(w) - 1);
+                if (w > 0 && !g.cut[w]) mn = min(mn, d[w - 1] + BL(w) - 1);
                 for (uint32_t k = g.in_ptr[w]; k < g.in_ptr[w + 1]; ++k) { uint32_t b = g.in_bid[k]; if (f[b] > 0) mn = min(mn, d[g.bs[b]]); }
                 newlab.emplace_back(w, mn >= INF ? INF : mn + 1);
                 ++st.relabels; ++rel_since; ++rel_round;
@@ -212,7 +236,9 @@ static G make(uint32_t L, uint32_t R, uint32_t cov, uint32_t M, uint32_t seed, i
     for (uint32_t s = 0; s + R <= L; ++s) if (cnt[s]) { g.bs.push_back(s); g.bt.push_back(s + R); g.bm.push_back(cnt[s]); diff[s] += cnt[s]; diff[s + R] -= cnt[s]; }
     g.dem.assign(g.n, 0);
     int64_t run = 0; uint32_t prev = 0;
-    for (uint32_t v = 0; v < g.n; ++v) { run += diff[v]; uint32_t c = min<uint64_t>(run, M); g.dem[v] = (int32_t)prev - (int32_t)c; prev = c; }
+    g.unc.assign(g.n + 1, 0);
+    g.cut.assign(g.n + 1, 0);
+    for (uint32_t v = 0; v < g.n; ++v) { run += diff[v]; uint32_t c = min<uint64_t>(run, M); g.dem[v] = (int32_t)prev - (int32_t)c; prev = c; g.unc[v + 1] = g.unc[v] + ((uint64_t)run <= M ? 1u : 0u); }
     uint32_t B = g.bs.size();
     g.out_ptr.assign(g.n + 1, 0); g.in_ptr.assign(g.n + 1, 0);
     for (uint32_t b = 0; b < B; ++b) { ++g.out_ptr[g.bs[b] + 1]; ++g.in_ptr[g.bt[b] + 1]; }
@@ -221,6 +247,34 @@ static G make(uint32_t L, uint32_t R, uint32_t cov, uint32_t M, uint32_t seed, i
     vector<uint32_t> cur(g.in_ptr.begin(), g.in_ptr.end() - 1);
     for (uint32_t b = 0; b < B; ++b) g.in_bid[cur[g.bt[b]]++] = b;
     return g;
+}
+// Forced reads out, cuts in: a read that covers a position with cov <= M is in every valid answer, so
+// its flow is fixed (its ends' demands absorb it) and it leaves the graph; the back arc over such a
+// position carries cov_S - min(cov, M) = 0 in every valid answer, so it leaves the graph too.
+static G transform(const G& g) {
+    G h; h.n = g.n; h.dem = g.dem; h.unc = g.unc; h.cut.assign(g.n + 1, 0);
+    uint64_t forced = 0, reads = 0;
+    for (size_t b = 0; b < g.bs.size(); ++b) {
+        if (g.unc[g.bt[b]] - g.unc[g.bs[b]] > 0) {
+            h.dem[g.bs[b]] += (int32_t)g.bm[b];
+            h.dem[g.bt[b]] -= (int32_t)g.bm[b];
+            ++forced; reads += g.bm[b];
+        } else { h.bs.push_back(g.bs[b]); h.bt.push_back(g.bt[b]); h.bm.push_back(g.bm[b]); }
+    }
+    uint32_t ncut = 0;
+    for (uint32_t v = 1; v < g.n; ++v) if (g.unc[v] - g.unc[v - 1]) { h.cut[v] = 1; ++ncut; }
+    uint32_t B = h.bs.size();
+    h.out_ptr.assign(h.n + 1, 0); h.in_ptr.assign(h.n + 1, 0);
+    for (uint32_t b = 0; b < B; ++b) { ++h.out_ptr[h.bs[b] + 1]; ++h.in_ptr[h.bt[b] + 1]; }
+    for (uint32_t v = 0; v < h.n; ++v) { h.out_ptr[v + 1] += h.out_ptr[v]; h.in_ptr[v + 1] += h.in_ptr[v]; }
+    h.in_bid.resize(B);
+    vector<uint32_t> cur(h.in_ptr.begin(), h.in_ptr.end() - 1);
+    for (uint32_t b = 0; b < B; ++b) h.in_bid[cur[h.bt[b]]++] = b;
+    int64_t sup = 0; uint32_t nsup = 0, nsnk = 0;
+    for (uint32_t v = 0; v < h.n; ++v) { if (h.dem[v] < 0) { sup -= h.dem[v]; ++nsup; } if (h.dem[v] > 0) ++nsnk; }
+    printf("  transform: %lu bundles (%lu reads) forced, %u back arcs cut, residual supply %ld at %u nodes, %u sink nodes\n",
+           (unsigned long)forced, (unsigned long)reads, ncut, (long)sup, nsup, nsnk);
+    return h;
 }
 int main(int argc, char** argv) {
     uint32_t L = 16000, R = 150, cov = 1500, M = 500, seed = 1; int shape = 0;
@@ -231,6 +285,7 @@ int main(int argc, char** argv) {
         kv("L", L) || kv("R", R) || kv("cov", cov) || kv("M", M) || kv("seed", seed) || kv("shape", shape) || kv("gri", o.gri) || kv("grl", o.grl) || kv("grr", o.grr) || kv("variant", o.variant) || kv("K", o.K) || kv("trace", o.trace);
     }
     G g = make(L, R, cov, M, seed, shape);
+    if (o.variant & 128) g = transform(g);
     St st = solve(g, o);
     printf("L %u cov %u M %u variant %d: rounds %lu pushes %lu relabels %lu grs %lu levels %lu maxF %lu  (hops %u)\n", L, cov, M, o.variant,
            (unsigned long)st.rounds, (unsigned long)st.pushes, (unsigned long)st.relabels, (unsigned long)st.grs, (unsigned long)st.levels, (unsigned long)st.maxf, L / R);
