@@ -51,6 +51,7 @@ struct gds_ctx {
     DevBuf qF, qT, qN, qH, work_counter, comp_stats;
     DevBuf bitmap, cov_tmp, dem_tmp, vdiff, vexcl;
     DevBuf vs_d, cross_idx, cross_tc, odiff, oexcl, cut_nodes, tile_off_d, head_bits;
+    DevBuf unc, adj, fmult, dead;  // forced reads out, cuts in (graph.cuh)
     DevBuf dhist, dlay, b_slot, ident, dwork;  // direct (sort-free) bundle path
     DevBuf kstat, pbund, cand, dctl, in_src, dem_v, fb_list, in1, lab_g, taken;
     int sweep_smem_set = 0;
@@ -69,7 +70,7 @@ struct gds_ctx {
                          &comp_lo, &comp_hi, &qF, &qT, &qN, &qH, &work_counter, &comp_stats,
                          &bitmap, &cov_tmp, &dem_tmp, &vdiff, &vexcl, &vs_d, &cross_idx, &cross_tc,
                          &odiff, &oexcl, &cut_nodes, &tile_off_d, &head_bits, &dhist, &dlay, &b_slot,
-                         &ident, &dwork, &kstat, &pbund, &cand, &dctl, &in_src, &dem_v, &fb_list, &in1, &lab_g, &taken};
+                         &ident, &dwork, &kstat, &pbund, &cand, &dctl, &in_src, &dem_v, &fb_list, &in1, &lab_g, &taken, &unc, &adj, &fmult, &dead};
         for (DevBuf* b : all) b->release();
     }
 };
@@ -447,7 +448,7 @@ struct DirectPlan {
 
 // slots of the small device array `stats` (uint32 x 64) beyond the validation counters [0..4] and the
 // 64-bit totals at [8..19]: counts that stay on the device in lazy mode, and the K3 totals
-constexpr int kStatB = 20, kStatNComp = 21, kStatCtl = 24, kStatMf = 32, kStatWords = 64;
+constexpr int kStatB = 20, kStatNComp = 21, kStatCtl = 24, kStatMf = 32, kStatRes = 52, kStatWords = 64;
 
 bool direct_eligible(const gds_reads* rd, uint32_t ns, uint32_t minlen, uint32_t maxlen,
                      const uint32_t* S, const uint32_t* E) {
@@ -1319,11 +1320,49 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         int32_t* dem_dev = nullptr;
         if (out->cov_capped) cov_dev = out_dev ? out->cov_capped : c->cov_tmp.get<uint32_t>(n_onodes);
         if (out->demand) dem_dev = out_dev ? out->demand : c->dem_tmp.get<int32_t>(n_onodes);
+        // Forced reads out, cuts in (graph.cuh): bundles that cover a position with
+        // cov <= M get capacity 0 for the solve and their fixed flow goes into the demand; components
+        // are cut at every such position.  Not for the minimum-cardinality sweep (it walks all
+        // bundles itself) and not with gds_params.schedule = 1 (round 1's graph and schedule).
+        // ... and not below the supply at which the express schedule starts (kExpressMinSupply):
+        // with M = 100 (configs 1, 2, 5) the classic schedule on the uncut graph needs no more
+        // rounds than hops, and the three extra passes over nodes and bundles would cost config 5
+        // 0.25 ms of 5.75 (measured); gds_params.schedule = 2 applies them regardless.
+        bool forced_cuts = !(flags & GDS_NO_SOLVE) && algorithm == 0 && schedule != 1 &&
+                           (schedule == 2 || max_coverage >= kExpressMinSupply);
+        if (const char* e = getenv("GDS_EXPRESS")) forced_cuts = forced_cuts && atoi(e) != 0;
+        int32_t* adj = nullptr;
+        uint32_t* fmult = nullptr;
+        uint8_t* dead = nullptr;  // nodes without a live bundle of their own (express rule U4)
+        static_assert(kStatRes % 2 == 0 && kStatRes + 2 <= kStatWords, "stats layout");
+        unsigned long long* res_supply = reinterpret_cast<unsigned long long*>(stats + kStatRes);
+        if (forced_cuts && B) {
+            uint32_t* unc = c->unc.get<uint32_t>((size_t)n_nodes + 1);
+            adj = c->adj.get<int32_t>((size_t)n_nodes + 1);
+            fmult = c->fmult.get<uint32_t>((size_t)B + 1);
+            dead = c->dead.get<uint8_t>((size_t)n_nodes + 1);
+            GDS_CUDA(cudaMemsetAsync(adj, 0, ((size_t)n_nodes + 1) * 4, st));
+            GDS_CUDA(cudaMemsetAsync(dead, 0, (size_t)n_nodes + 1, st));
+            {
+                KScope ks("uncapped_flags", 12ull * n_nodes, st);
+                k_uncapped_flags<<<div_up((long long)n_nodes + 1, 256), 256, 0, st>>>(excl, diff, n_nodes,
+                                                                                     max_coverage, unc);
+                GDS_KERNEL_CHECK();
+            }
+            exclusive_scan_u32(unc, unc, (size_t)n_nodes + 1, c->scan, st);
+            {
+                KScope ks("forced_bundles", 8ull * n_nodes, st);
+                k_forced_bundles<<<div_up((long long)n_nodes, 256), 256, 0, st>>>(
+                    c->bund.as<BundleRec>(), out_ptr, n_nodes, maxlen, unc, adj, fmult, dead);
+                GDS_KERNEL_CHECK();
+            }
+        }
         {
             KScope ks("node_finalize", 60ull * n_nodes, st);
             k_node_finalize<<<div_up((long long)n_nodes + 1, 256), 256, 0, st>>>(
                 excl, diff, out_ptr, in_ptr, n_nodes, max_coverage, node, d_snap, cstart, cend,
-                split ? nullptr : cov_dev, split ? nullptr : dem_dev, dem_v, totals);
+                split ? nullptr : cov_dev, split ? nullptr : dem_dev, dem_v, totals, adj,
+                forced_cuts ? max_coverage : 0u, res_supply, dead);
             GDS_KERNEL_CHECK();
         }
         if (split) {
@@ -1404,12 +1443,12 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         const bool do_solve = !(flags & GDS_NO_SOLVE);
         if (do_solve && algorithm == 1 && maxlen >= 4096)
             return fail(c, GDS_ERR_ARG, "algorithm 1 (minimum cardinality) takes reads of up to 4095 positions");
-        // the express schedule (maxflow_sm.cuh): segments of cut references whose segments fit
+        // the express schedule (maxflow_sm.cuh): components with a supply of kExpressMinSupply or
+        // more — none when M is below that, and then nothing about the launch changes
         uint32_t express_on = schedule == 1 ? 0u : schedule == 2 ? 2u : 1u;
         if (const char* e = getenv("GDS_EXPRESS")) express_on = (uint32_t)atoi(e);  // measurement knob
-        bool express_possible = express_on == 2;
-        for (const VSample& v : hvs) express_possible |= express_on && v.nseg > 1 && v.W <= kExpressMaxNodes;
-        if (!express_possible) express_on = 0;
+        if (!forced_cuts || (express_on == 1 && max_coverage < kExpressMinSupply)) express_on = 0;
+        const bool express_possible = express_on != 0;
         const Mf2Plan mf2 = do_solve && algorithm == 0
                                 ? plan_maxflow_sm(n_comp, max_comp_nodes, express_possible)
                                 : Mf2Plan{};
@@ -1459,7 +1498,7 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             if (mf2.on) {
                 uint32_t* fb_list = c->fb_list.get<uint32_t>(n_comp_cap + 1);
                 Mf2Graph g2{node, c->bund.as<BundleRec>(), in_bid, in_src, out_ptr, in_ptr, dem_v,
-                            vs_d, ns, express_on, mf2.classic_ok ? 1u : 0u};
+                            vs_d, ns, express_on, mf2.classic_ok ? 1u : 0u, dead};
                 launch_maxflow_sm(c, mf2, g2, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats,
                                   mf_bytes, fb_list, wc + 2, n_comp_dev, mft);
                 // whatever the shared-memory kernel could not take (grid: at most one wave)
@@ -1471,6 +1510,12 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
                 launch_maxflow(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats,
                                mf_bytes, max_comp_nodes, n_comp_dev, mft, lab_g);
             }
+        }
+        if (fmult) {  // the forced bundles come back with their fixed flow: K5 keeps all their reads
+            KScope ks("forced_restore", 8ull * n_nodes, st);
+            k_forced_restore<<<div_up((long long)n_nodes, 256), 256, 0, st>>>(
+                c->bund.as<BundleRec>(), out_ptr, n_nodes, maxlen, c->unc.as<uint32_t>(), fmult);
+            GDS_KERNEL_CHECK();
         }
         GDS_CUDA(cudaEventRecord(c->ev[EV_MAXFLOW], st));
 
@@ -1559,7 +1604,11 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         if (do_solve) {
             MfTotals ht;
             memcpy(&ht, hstat + kStatMf, sizeof ht);
-            out->flow_value = ht.sink_flow;
+            // sink inflow of the residual problem + the forced bundles' fixed flows: whatever the
+            // residual problem left undelivered (nothing, on valid input) is missing from F*
+            unsigned long long hres = 0;
+            memcpy(&hres, hstat + kStatRes, sizeof hres);
+            out->flow_value = forced_cuts ? fstar_virtual - ((long long)hres - ht.sink_flow) : ht.sink_flow;
             out->rounds_total = ht.rounds_total;
             out->rounds_max = ht.rounds_max;
             out->pushes = ht.pushes;

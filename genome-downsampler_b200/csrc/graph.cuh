@@ -372,9 +372,13 @@ k_node_finalize(const uint32_t* __restrict__ excl, const int32_t* __restrict__ d
                 uint32_t* __restrict__ d_snap, uint32_t* __restrict__ comp_start,
                 uint32_t* __restrict__ comp_end, uint32_t* __restrict__ cov_capped_out,
                 int32_t* __restrict__ demand_out, int32_t* __restrict__ dem_v /* [n_nodes] always */,
-                unsigned long long* __restrict__ totals) {
+                unsigned long long* __restrict__ totals,
+                const int32_t* __restrict__ adj /* null or: what the forced bundles add to the demand */,
+                uint32_t cut_at /* v and v+1 belong to one component iff covR[v] > cut_at (0 or M) */,
+                unsigned long long* __restrict__ res_supply /* += supply of the residual problem */,
+                uint8_t* __restrict__ dead /* null or: |= 1 for nodes without bundles of their own */) {
     uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long src = 0;
+    unsigned long long src = 0, rsrc = 0;
     if (v == n_nodes) {  // sentinel record: closes the CSR ranges of the last node
         uint4* r = reinterpret_cast<uint4*>(&node[v]);
         r[0] = make_uint4(0u, 0u, 0u, 0u);
@@ -386,20 +390,28 @@ k_node_finalize(const uint32_t* __restrict__ excl, const int32_t* __restrict__ d
         uint32_t covL = excl[v];
         uint32_t covR = covL + (uint32_t)diff[v];
         int32_t dem = (int32_t)min(covL, M) - (int32_t)min(covR, M);
+        // what K3 solves: the demand with the forced bundles' fixed flows taken out
+        const int32_t dk = dem + (adj ? adj[v] : 0);
         uint4* r = reinterpret_cast<uint4*>(&node[v]);
-        r[0] = make_uint4(kLabelInf, 0u, (uint32_t)(dem < 0 ? -dem : 0), 0u);  // d, stamp, e, eadd
-        r[1] = make_uint4((uint32_t)(dem > 0 ? dem : 0), 0u, out_ptr[v], in_ptr[v]);  // snk, g, ptrs
+        r[0] = make_uint4(kLabelInf, 0u, (uint32_t)(dk < 0 ? -dk : 0), 0u);  // d, stamp, e, eadd
+        r[1] = make_uint4((uint32_t)(dk > 0 ? dk : 0), 0u, out_ptr[v], in_ptr[v]);  // snk, g, ptrs
         d_snap[v] = kLabelInf;
-        dem_v[v] = dem;
-        comp_start[v] = (covL == 0 && covR > 0) ? 1u : 0u;
-        comp_end[v] = (covL > 0 && covR == 0) ? 1u : 0u;
+        dem_v[v] = dk;
+        comp_start[v] = (covL <= cut_at && covR > cut_at) ? 1u : 0u;
+        comp_end[v] = (covL > cut_at && covR <= cut_at) ? 1u : 0u;
         if (cov_capped_out) cov_capped_out[v] = min(covR, M);
         if (demand_out) demand_out[v] = dem;
         if (dem < 0) src = (unsigned long long)(-dem);
+        if (dk < 0) rsrc = (unsigned long long)(-dk);
+        if (dead && out_ptr[v + 1] == out_ptr[v]) dead[v] = 1;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) src += __shfl_xor_sync(0xffffffffu, src, o);
+    for (int o = 16; o > 0; o >>= 1) {
+        src += __shfl_xor_sync(0xffffffffu, src, o);
+        rsrc += __shfl_xor_sync(0xffffffffu, rsrc, o);
+    }
     if (lane_id() == 0 && src) atomicAdd(&totals[0], src);
+    if (lane_id() == 0 && rsrc) atomicAdd(res_supply, rsrc);
 }
 
 // start node of every in-CSR slot (the first global relabel of K3 walks only this array), and for
@@ -417,9 +429,16 @@ k_in_src(const BundleRec* __restrict__ bund, const uint32_t* __restrict__ in_bid
     if (k >= B) return;
     const uint32_t b = in_bid[k];
     const uint4 r = reinterpret_cast<const uint4*>(bund)[b];  // t, mult, f, s
-    in_src[k] = r.w;
-    if (k == in_ptr[r.x]) in1[r.x] = k + 1 == in_ptr[r.x + 1] ? r.w : 0xfffffffeu;
-    if (node && k + 1 == in_ptr[r.x + 1]) *reinterpret_cast<uint2*>(&node[r.x]) = make_uint2(r.w, b);
+    // a forced bundle (capacity 0 while K3 runs) is no arc of the residual graph: the relabels that
+    // walk in_src without looking at the bundles must not see it
+    const bool inert = r.y == 0;
+    in_src[k] = inert ? 0xffffffffu : r.w;
+    if (k == in_ptr[r.x]) {
+        if (k + 1 != in_ptr[r.x + 1]) in1[r.x] = 0xfffffffeu;
+        else if (!inert) in1[r.x] = r.w;
+    }
+    if (node && k + 1 == in_ptr[r.x + 1])
+        *reinterpret_cast<uint2*>(&node[r.x]) = make_uint2(inert ? 0xffffffffu : r.w, b);
 }
 
 // Components are disjoint runs, so starts and ends alternate: the end at v closes the component
@@ -432,6 +451,68 @@ k_comp_write(const uint32_t* __restrict__ comp_start, const uint32_t* __restrict
     if (v >= n_nodes) return;
     if (comp_start[v]) comp_lo[start_idx[v]] = v;
     if (comp_end[v]) comp_hi[start_idx[v] - 1] = v;
+}
+
+// ---- forced reads out, cuts in -------------------------------------------------
+// A bundle that covers a position with cov <= M is in every valid answer: its flow is fixed at its
+// multiplicity.  flag -> exclusive scan = number of such positions left of a node; a bundle s -> t
+// is forced iff the count differs between t and s.  Forced bundles get capacity 0 for the solve
+// (their multiplicity waits in fmult), their ends' demands absorb the fixed flow (adj), and
+// k_node_finalize cuts the components at every such position.
+__global__ void __launch_bounds__(256)
+k_uncapped_flags(const uint32_t* __restrict__ excl, const int32_t* __restrict__ diff, uint32_t n_nodes,
+                 uint32_t M, uint32_t* __restrict__ flag /* [n_nodes + 1] */) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v > n_nodes) return;
+    flag[v] = v < n_nodes && excl[v] + (uint32_t)diff[v] <= M ? 1u : 0u;
+}
+
+// One thread per NODE: if no uncapped position lies within maxlen of v none of its bundles can be
+// forced — two reads of the prefix count and nothing else (config 4: all but the genome's two ends).
+// Otherwise its out-bundles are tested one by one.  fmult[b] is written for forced bundles only and
+// read back, after K3, by the same test: it needs no clearing.
+__device__ __forceinline__ bool node_may_be_forced(const uint32_t* __restrict__ unc, uint32_t v,
+                                                   uint32_t n_nodes, uint32_t maxlen) {
+    return unc[v] != unc[min(v + maxlen, n_nodes)];
+}
+
+__global__ void __launch_bounds__(256)
+k_forced_bundles(BundleRec* __restrict__ bund, const uint32_t* __restrict__ out_ptr, uint32_t n_nodes,
+                 uint32_t maxlen, const uint32_t* __restrict__ unc, int32_t* __restrict__ adj,
+                 uint32_t* __restrict__ fmult,
+                 uint8_t* __restrict__ dead /* [n_nodes], zero on entry: 1 = every own bundle is forced */) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes || !node_may_be_forced(unc, v, n_nodes, maxlen)) return;
+    const uint32_t uv = unc[v];
+    bool live = false;
+    for (uint32_t b = out_ptr[v]; b < out_ptr[v + 1]; ++b) {
+        const uint4 r = reinterpret_cast<const uint4*>(bund)[b];  // t, mult, f, s
+        const bool forced = unc[r.x] != uv;
+        fmult[b] = forced ? r.y : 0u;
+        if (forced) {
+            bund[b].mult = 0;
+            atomicAdd(&adj[v], (int32_t)r.y);
+            atomicAdd(&adj[r.x], -(int32_t)r.y);
+        } else {
+            live = true;
+        }
+    }
+    if (!live) dead[v] = 1;
+}
+
+// after K3: the forced bundles come back with their fixed flow (K5 keeps all their reads)
+__global__ void __launch_bounds__(256)
+k_forced_restore(BundleRec* __restrict__ bund, const uint32_t* __restrict__ out_ptr, uint32_t n_nodes,
+                 uint32_t maxlen, const uint32_t* __restrict__ unc, const uint32_t* __restrict__ fmult) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes || !node_may_be_forced(unc, v, n_nodes, maxlen)) return;
+    for (uint32_t b = out_ptr[v]; b < out_ptr[v + 1]; ++b) {
+        const uint32_t m = fmult[b];
+        if (m) {
+            bund[b].mult = m;
+            bund[b].f = m;
+        }
+    }
 }
 
 }  // namespace gds

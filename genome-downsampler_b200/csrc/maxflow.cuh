@@ -362,7 +362,7 @@ __device__ uint32_t mf_first_relabel(const MfGraph& G, uint32_t lo, uint32_t hi,
                 } else {
                     for (uint32_t k = in_lo; k < in_hi; ++k) {
                         const uint32_t s = ld_u32(&G.in_src[k]);
-                        if (claim(s)) label(s);
+                        if (s != 0xffffffffu && claim(s)) label(s);  // (forced bundles are no arcs)
                     }
                 }
             }
@@ -379,7 +379,7 @@ __device__ uint32_t mf_first_relabel(const MfGraph& G, uint32_t lo, uint32_t hi,
                 if (warp_mode && lane == 0 && w < hi && claim(w + 1)) label(w + 1);
                 for (uint32_t k = in_lo + lane; k < in_hi; k += 32) {
                     const uint32_t s = ld_u32(&G.in_src[k]);
-                    if (claim(s)) label(s);
+                    if (s != 0xffffffffu && claim(s)) label(s);
                 }
             }
             __syncthreads();

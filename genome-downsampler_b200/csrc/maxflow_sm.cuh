@@ -49,6 +49,7 @@ struct Mf2Graph {
     // schedule may run here too (otherwise they go to k_maxflow)
     const VSample* vs;
     uint32_t n_samples, express_on, classic_ok;
+    const uint8_t* dead;  // [n_nodes] 1 = the node has no live bundle of its own (null without express)
 };
 
 // The EXPRESS schedule (oracle/gds_oracle.cpp: express_component, sync_solve_component): in the
@@ -60,7 +61,7 @@ struct Mf2Graph {
 // BFS has one level per read hop instead of one per hop plus one per step.  Config 4: 370 -> 165
 // rounds and 290 -> 110 BFS levels per segment, no second global relabel, and the 1 400-round tail
 // of the last segment is gone.  Which components take it is decided from the data alone.
-constexpr uint32_t kExpressMaxNodes = 24576, kExpressEdge = 512;
+constexpr uint32_t kExpressMaxNodes = 40961, kExpressEdge = 512, kExpressMinSupply = 128;
 
 // Layout of the per-node arrays of an n-node component, in 32-bit words from `word`:
 //   word[n] | inF bitmap [W] | (16-byte aligned) BFS bitmap A [W4] | saturated bits: snapshot [W4],
@@ -327,7 +328,10 @@ __device__ __forceinline__ void mf2_bfs_heavy(Mf2Shared& sh, const Mf2Lvl& nxt, 
                 const uint32_t in_hi = __shfl_sync(0xffffffffu, my_hi, j);
 #pragma unroll 1
                 for (uint32_t k = in_lo + 64 + lane; k < in_hi; k += 32)  // beyond 64 in-arcs
-                    mf2_mark(C, nxt, g_ld(&C.G.in_src[k]) - lo);
+                {
+                    const uint32_t sa = g_ld(&C.G.in_src[k]);
+                    if (sa != 0xffffffffu) mf2_mark(C, nxt, sa - lo);
+                }
             }
         }
         return;
@@ -395,6 +399,7 @@ __device__ __forceinline__ void mf2_push_heavy(Mf2Shared& sh, uint32_t nHA, unsi
                     g_st(&nr->snk, (uint32_t)(sk - (int32_t)dl));
                     my_sink += dl;
                     ++my_pushes;
+                    if (C.express && snk_now == 0 && C.G.dead[lo + v]) mf2_sat_set(C, v, true);  // U4
                 }
             }
         }
@@ -455,8 +460,10 @@ __device__ __forceinline__ void mf2_push_heavy(Mf2Shared& sh, uint32_t nHA, unsi
             const bool have = top - ib > lane;
             uint32_t b = 0, r = 0, s = 0;
             if (have) {
-                s = (chunk == 0 ? pre_s[0] : chunk == 1 ? pre_s[1] : g_ld(&C.G.in_src[top - 1 - lane])) - lo;
-                if (mf2_label(word, s) + 1 == dv) {  // only then is the flow worth a memory trip
+                const uint32_t sa = chunk == 0 ? pre_s[0] : chunk == 1 ? pre_s[1] : g_ld(&C.G.in_src[top - 1 - lane]);
+                s = sa - lo;
+                // (a forced bundle's slot holds no start node: it carries nothing that could be cancelled)
+                if (sa != 0xffffffffu && mf2_label(word, s) + 1 == dv) {  // only then is the flow worth a memory trip
                     b = g_ld(&C.G.in_bid[top - 1 - lane]);
                     r = g_ld(&C.G.bund[b].f);
                 }
@@ -735,7 +742,7 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
                         sh.not_benign = 1;
                     if (!fits) continue;
                     uint32_t code = kIn16None;
-                    if (ip1[q] - ip[q] == 1) code = src[q] - lo;
+                    if (ip1[q] - ip[q] == 1) code = src[q] == 0xffffffffu ? kIn16None : src[q] - lo;
                     else if (ip1[q] - ip[q] > 1) code = kIn16Multi;
                     word[v] = (code << 16) | (dm[q] > 0 ? 1u : kInf16);
                     if (have_optr) optr[v] = (uint16_t)(op[q] - obase);
@@ -750,16 +757,6 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
                 }
             }
             if (have_optr && tid == 0) optr[n] = (uint16_t)n_bund;
-            if (G.express_on && tid == 0) {  // is this a segment of a cut reference?
-                uint32_t a = 0, b = G.n_samples;  // largest k with vs[k].vbase <= lo
-                while (b - a > 1) {
-                    const uint32_t mid = (a + b) >> 1;
-                    if (G.vs[mid].vbase <= lo) a = mid;
-                    else b = mid;
-                }
-                const VSample vk = G.vs[a];
-                if (vk.nseg > 1 && vk.W <= kExpressMaxNodes) sh.seg_sample = 1;
-            }
             my_supply = __reduce_add_sync(0xffffffffu, my_supply);
             if (lane == 0 && my_supply) atomicAdd(&sh.supply, min(my_supply, 0x10000u));
         }
@@ -768,8 +765,8 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
         // read lengths, tens of bundles per node): their time is the per-bundle global traffic of the
         // warp passes, which shared-memory labels do not shorten (config 2: 2.6 ms there, 3.4 ms here)
         // the express schedule: decided from the data alone (oracle: express_component)
-        const bool express = G.express_on && (G.express_on == 2 || sh.seg_sample) && !sh.not_benign &&
-                             !warp_mode && n <= kExpressMaxNodes && sh.supply <= 0xffffu;
+        const bool express = G.express_on && (G.express_on == 2 || sh.supply >= kExpressMinSupply) &&
+                             !sh.not_benign && !warp_mode && n <= kExpressMaxNodes && sh.supply <= 0xffffu;
         const uint32_t bl = express ? 0u : 1u;  // length of a back arc in the labels
         if (sh.supply > 0xffffu || (!express && !G.classic_ok)) {  // nothing has been written to global memory yet
             __syncthreads();
@@ -889,6 +886,8 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
                         ex -= dl;
                         my_sink += dl;
                         ++my_pushes;
+                        // U4: the sink of a node without a live bundle of its own is full: walkers pass it
+                        if (express && snk_now == 0 && G.dead[lo + v]) mf2_sat_set(sh.C, v, true);
                     }
                 }
                 // 2. own bundles, farthest end first
@@ -941,6 +940,8 @@ k_maxflow_sm(Mf2Graph G, const uint32_t* __restrict__ comp_lo, const uint32_t* _
                         s = g_ld(&G.in_src[k]);
                         b = 0xffffffffu;
                     }
+                    // a forced bundle (its start may lie in another component): nothing to cancel
+                    if (s == 0xffffffffu) continue;
                     if (mf2_label(word, s - lo) + 1 != dv) continue;
                     if (b == 0xffffffffu) b = g_ld(&G.in_bid[k]);
                     const uint4 br = ld_bund(&G.bund[b]);

@@ -128,15 +128,21 @@ typedef struct {
      *      set is the smallest one (per segment, when a long reference is cut).  Reads of up to 4095
      *      positions.  rounds / pushes / relabels stay 0. */
     uint32_t algorithm;
-    /* which deterministic push-relabel schedule components run (algorithm 0):
-     *   0  the classic one, and the EXPRESS one for segments of a cut reference (seg_len above) whose
-     *      supply sits at their left and whose sinks sit at their right end: back arcs have length 0
-     *      in the distance labels, so flow changes read "lanes" within one round (csrc/maxflow_sm.cuh;
-     *      config 4: 370 -> 165 rounds and 290 -> 110 relabel levels per segment).  Decided from the
-     *      data alone; the oracle replays both (orc_sync_params.schedule);
-     *   1  classic only (round 1's results);
-     *   2  express for every component that is structurally eligible, cut reference or not
-     *      (experiments). */
+    /* graph reduction and push-relabel schedule of algorithm 0 (csrc/graph.cuh, csrc/maxflow_sm.cuh,
+     * DESIGN.md §4; the oracle replays all three: orc_sync_params.schedule):
+     *   0  from max_coverage = 128 on: (a) FORCED READS OUT, CUTS IN — a read that covers a position
+     *      with coverage <= max_coverage is in every valid answer, so its flow is fixed and it leaves
+     *      the network, and the back arc over such a position carries nothing in any valid answer, so
+     *      the components are cut there (the zero-coverage rule with "<= max_coverage" for "== 0");
+     *      (b) the EXPRESS schedule for components with a supply of 128 or more that fit one SM: back
+     *      arcs have length 0 in the distance labels, flow changes read "lanes" within one round.
+     *      The reference's hole / low-sides / zero-sides shapes at M = 8000: 2 100-4 300 rounds ->
+     *      155-430, 13-19 ms -> 1.1-3.0 ms; config 4: 370 -> 175 rounds per segment.
+     *      Below 128 (configs 1, 2, 5: M = 100) the graph and the schedule are round 1's;
+     *   1  round 1's graph and classic schedule always;
+     *   2  (a) and (b) whatever max_coverage and the supply are (experiments).
+     * Every choice is a function of the data and these fields alone, never of the device or the
+     * batch a sample travels in. */
     uint32_t schedule;
 } gds_params;
 

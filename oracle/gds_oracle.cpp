@@ -560,6 +560,9 @@ struct SyncGraph {
     std::vector<uint32_t> sorted_idx;  // owner read of every sorted arc item
     std::vector<uint32_t> out_ptr, in_ptr, in_bid;
     std::vector<uint32_t> comp_lo, comp_hi;
+    std::vector<uint32_t> b_forced;  // forced bundles: their multiplicity (b_mult is 0 during the solve)
+    int64_t vsupply = 0;             // supply of the virtual network before the forced flows are taken out
+    uint32_t M = 0;
 };
 
 // seg_len == 0: the library's default rule (csrc/gds_api.cu default_seg_len) — 16 384 positions,
@@ -593,7 +596,7 @@ static uint32_t default_seg_len(uint32_t n_samples, const uint32_t* ref_len) {
 // length and the key width does not grow.  Decoding clamps to the segment's real node range.
 int build_sync_graph(uint32_t n_samples, const uint64_t* read_off, const uint32_t* ref_len,
                      const uint32_t* start, const uint32_t* end, uint32_t M, uint32_t seg_len,
-                     SyncGraph& G) {
+                     SyncGraph& G, bool forced_cuts = false) {
     const uint64_t N = read_off[n_samples];
     uint32_t minlen = 0xffffffffu, maxlen = 0;
     for (uint32_t k = 0; k < n_samples; ++k)
@@ -735,10 +738,32 @@ int build_sync_graph(uint32_t n_samples, const uint64_t* read_off, const uint32_
         std::vector<uint32_t> cursor(G.in_ptr.begin(), G.in_ptr.end() - 1);
         for (uint32_t b = 0; b < B; ++b) G.in_bid[cursor[G.b_t[b]]++] = b;  // ascending bundle id
     }
-    // components: v and v+1 joined iff covR[v] > 0 (App. A.3); segment ends have covR == 0
+    // Forced reads out, cuts in: a bundle that covers a position with cov <= M is in
+    // every valid answer — its flow is fixed at its multiplicity, its ends' demands absorb it and
+    // it leaves the residual graph (capacity 0 during the solve, b_forced remembers the reads) —
+    // and the back arc over such a position carries cov_S - min(cov, M) = 0 in every valid answer,
+    // so the component rule becomes "v and v+1 joined iff covR[v] > M".
+    G.b_forced.assign(B, 0);
+    G.M = M;
+    G.vsupply = 0;
+    for (uint32_t v = 0; v < nn; ++v)
+        if (G.demand[v] < 0) G.vsupply += -(int64_t)G.demand[v];
+    const uint32_t cut_at = forced_cuts ? M : 0;
+    if (forced_cuts) {
+        std::vector<uint32_t> unc(nn + 1, 0);  // positions p < v with covR[p] <= M
+        for (uint32_t v = 0; v < nn; ++v) unc[v + 1] = unc[v] + (G.covR[v] <= M ? 1u : 0u);
+        for (uint32_t b = 0; b < B; ++b)
+            if (unc[G.b_t[b]] - unc[G.b_s[b]] > 0) {
+                G.b_forced[b] = G.b_mult[b];
+                G.demand[G.b_s[b]] += (int32_t)G.b_mult[b];
+                G.demand[G.b_t[b]] -= (int32_t)G.b_mult[b];
+                G.b_mult[b] = 0;
+            }
+    }
+    // components: v and v+1 joined iff covR[v] > cut_at (App. A.3: 0); segment ends have covR == 0
     uint32_t lo = 0;
     for (uint32_t v = 0; v < nn; ++v) {
-        if (G.covR[v] == 0) {
+        if (G.covR[v] <= cut_at) {
             if (v > lo) {
                 G.comp_lo.push_back(lo);
                 G.comp_hi.push_back(v);
@@ -770,7 +795,7 @@ struct CompStats {
 // reference needs: all its supply sits at the left end and all its sinks at the right end, so M
 // units must be spread over the read "lanes" and gathered again.  Chosen per component from the
 // data alone (express_component below), never from the device or the batch.
-constexpr uint32_t kExpressMaxNodes = 24576, kExpressEdge = 512, kHeavyDegOracle = 6;
+constexpr uint32_t kExpressMaxNodes = 40961, kExpressEdge = 512, kHeavyDegOracle = 6;
 
 uint32_t sync_global_relabel(const SyncGraph& G, SyncState& S, uint32_t lo, uint32_t hi,
                              CompStats& cs, bool express) {
@@ -816,22 +841,16 @@ uint32_t sync_global_relabel(const SyncGraph& G, SyncState& S, uint32_t lo, uint
     return level;
 }
 
-// Which components run the express schedule: segments of a cut reference (whose nodes fit the
-// shared-memory kernel by construction) with few bundles per node, a supply that fits 16 bits, every
-// supply within kExpressEdge nodes of the left end and every sink within kExpressEdge of the right.
+// Which components run the express schedule — decided from the component's data alone: few
+// bundles per node, a supply of at least kExpressMinSupply (below that the classic schedule needs
+// no more rounds than hops: config 5's M = 100) that fits 16 bits, at most kExpressMaxNodes nodes
+// (what one SM holds), every supply within kExpressEdge nodes of the left end and every sink within
+// kExpressEdge of the right end (true by construction once the forced reads are out, for reads of up
+// to kExpressEdge positions).  schedule 2 drops the lower bound on the supply (experiments).
+constexpr uint32_t kExpressMinSupply = 128;
 bool express_component(const SyncGraph& G, uint32_t lo, uint32_t hi, uint32_t schedule) {
-    if (schedule == 1) return false;
+    if (schedule == 1 || (schedule != 2 && G.M < kExpressMinSupply)) return false;  // (the host's gate)
     const uint32_t n = hi - lo + 1;
-    if (schedule != 2) {
-        size_t a = 0, b = G.vs.size();  // the sample holding node lo (vbase ascending)
-        while (b - a > 1) {
-            const size_t mid = (a + b) / 2;
-            if (G.vs[mid].vbase <= lo) a = mid;
-            else b = mid;
-        }
-        const VSample& v = G.vs[a];
-        if (!(v.nseg > 1 && v.W <= kExpressMaxNodes)) return false;
-    }
     if (n > kExpressMaxNodes) return false;
     const uint64_t n_bund = G.out_ptr[hi + 1] - G.out_ptr[lo];
     if (2 * n_bund > (uint64_t)kHeavyDegOracle * n) return false;
@@ -845,7 +864,7 @@ bool express_component(const SyncGraph& G, uint32_t lo, uint32_t hi, uint32_t sc
             return false;
         }
     }
-    return supply <= 0xffffu;
+    return supply <= 0xffffu && (schedule == 2 || supply >= kExpressMinSupply);
 }
 
 void sync_solve_component(const SyncGraph& G, SyncState& S, uint32_t lo, uint32_t hi,
@@ -915,6 +934,16 @@ void sync_solve_component(const SyncGraph& G, SyncState& S, uint32_t lo, uint32_
                 ex -= dl;
                 cs.sink_flow += dl;
                 ++cs.pushes;
+                // U4: the sink of a node without a live bundle of its own (all forced, or none) is
+                // full — from now on walkers pass it
+                if (express && S.snk[v] == 0) {
+                    bool live = false;
+                    for (uint32_t b = G.out_ptr[v]; !live && b < G.out_ptr[v + 1]; ++b) live = G.b_mult[b] != 0;
+                    if (!live) {
+                        satn[v] = 1;
+                        sat_touched.push_back(v);
+                    }
+                }
             }
             // 2. own bundles, farthest end first
             for (uint32_t b = G.out_ptr[v + 1]; ex > 0 && b-- > G.out_ptr[v];) {
@@ -1032,7 +1061,10 @@ extern "C" int orc_sync_solve(uint32_t n_samples, const uint64_t* read_off, cons
     orc_sync_params P = prm ? *prm : orc_sync_params{64, 150, 1, 0, 0, 0};
     auto t0 = clk::now();
     SyncGraph G;
-    if (build_sync_graph(n_samples, read_off, ref_len, start, end, M, P.seg_len, G) != 0) return -1;
+    // forced reads out + cuts: from the supply at which the express schedule starts (the host's gate)
+    const bool forced_cuts = P.schedule == 2 || (P.schedule != 1 && M >= kExpressMinSupply);
+    if (build_sync_graph(n_samples, read_off, ref_len, start, end, M, P.seg_len, G, forced_cuts) != 0)
+        return -1;
     auto t1 = clk::now();
     const uint32_t nn = G.n_nodes;
     const uint32_t B = (uint32_t)G.b_s.size();
@@ -1060,6 +1092,17 @@ extern "C" int orc_sync_solve(uint32_t n_samples, const uint64_t* read_off, cons
         out.max_frontier = std::max(out.max_frontier, cs.max_frontier);
         out.n_express += (uint32_t)cs.express;
     }
+    // the forced bundles come back with their fixed flow; what the residual problem left
+    // undelivered (nothing, on valid input) is missing from the flow value
+    int64_t res_supply = 0;
+    for (uint32_t v = 0; v < nn; ++v)
+        if (G.demand[v] < 0) res_supply += -(int64_t)G.demand[v];
+    out.flow_value = G.vsupply - (res_supply - out.flow_value);
+    for (uint32_t b = 0; b < B; ++b)
+        if (G.b_forced[b]) {
+            G.b_mult[b] = G.b_forced[b];
+            S.f[b] = G.b_forced[b];
+        }
     auto t2 = clk::now();
     const uint64_t N = read_off[n_samples];
     std::fill(kept_bitmap, kept_bitmap + (N + 31) / 32, 0u);

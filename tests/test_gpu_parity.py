@@ -589,6 +589,42 @@ def test_express_schedule_parity(solver, O):
         assert_parity(O, r, s5, e5, [60_000], [0, len(s5)], 300, oprm)
 
 
+def test_forced_reads_out_and_cuts(solver, O):
+    # from M = 128 on, bundles that cover a position with cov <= M leave the network with their
+    # flow fixed and the components are cut at those positions (graph.cuh); what remains runs the
+    # express schedule.  Bit-exact against the oracle; the reference's hard shapes need hops.
+    for shape, M, max_rounds in (("hole", 8000, 400), ("zero_sides", 8000, 300), ("low_sides", 8000, 600)):
+        s, e, _, _ = O.gen_reads(12345, 1_000_000, 30_000, 150, shape)
+        off = np.array([0, len(s)], np.uint64)
+        r = solver.solve(s, e, [30_000], M, read_off=off, params=PRM, verify=True, want_vectors=True)
+        st = assert_parity(O, r, s, e, [30_000], off, M)
+        assert st.n_express >= 1 and r.rounds_max < max_rounds, (shape, r.rounds_max)
+        # schedule 1 = round 1's graph and schedule: the same F*, demand, capped coverage; a valid
+        # answer of (nearly) the same size, thousands of rounds
+        r1 = solver.solve(s, e, [30_000], M, read_off=off, params=(64, 150, 1, 0, 0, 0, 0, 1), verify=True,
+                          want_vectors=True)
+        assert_parity(O, r1, s, e, [30_000], off, M, (64, 150, 1, 0, 0, 1))
+        assert r1.fstar == r.fstar and np.array_equal(r1.demand, r.demand)
+        assert r1.rounds_max > 4 * r.rounds_max and abs(int(r1.n_kept) - int(r.n_kept)) <= 0.001 * r.n_kept
+    # M above the coverage everywhere: every read is forced, nothing is left to solve
+    s, e, _, _ = O.gen_reads(5, 50_000, 30_000, 150)
+    r = solver.solve(s, e, [30_000], 5000, params=PRM, verify=True, want_vectors=True)
+    assert r.n_components == 0 and r.n_kept == len(s) and r.rounds_total == 0
+    assert_parity(O, r, s, e, [30_000], [0, len(s)], 5000)
+    # a cut reference with a hole, short segments, next to a whole sample, several read lengths
+    rng = np.random.default_rng(3)
+    s2, e2, _, _ = O.gen_reads(9, 300_000, 90_000, 150, "hole")
+    e2 = np.maximum(s2, e2 - rng.integers(0, 30, size=len(e2)).astype(np.uint32))
+    s3, e3, _, _ = O.gen_reads(10, 100_000, 30_000, 150, "low_sides")
+    sb = np.concatenate([s2, s3]); eb = np.concatenate([e2, e3])
+    offb = np.array([0, len(s2), len(sb)], np.uint64)
+    for prm in (PRM, (64, 150, 1, 0, 8192), (16, 50, 1, 0, 8192, 0, 0, 2)):
+        r = solver.solve(sb, eb, [90_000, 30_000], 400, read_off=offb, params=prm, verify=True,
+                         want_vectors=True)
+        oprm = prm[:5] + ((prm[7],) if len(prm) > 5 else ())
+        assert_parity(O, r, sb, eb, [90_000, 30_000], offb, 400, oprm)
+
+
 def test_maxflow_fallback_list(solver, O):
     # components the shared-memory kernel cannot take go to k_maxflow through a device-side list:
     # (a) supply beyond 16 bits (M above the coverage: every rise of the coverage is a source);

@@ -250,6 +250,38 @@ def test_express_schedule_is_a_maximum_flow_with_fewer_rounds(O):
     assert 0 < st3.n_express < st3.n_components and st3.flow_value == st3.fstar
 
 
+def test_forced_reads_and_cuts_make_every_shape_a_transport(O):
+    # from M = 128 on, bundles that cover a position with cov <= M are taken out with their fixed
+    # flow and the components are cut at those positions: the same F*, a valid cover,
+    # and the reference's hard shapes need hops, not thousands of rounds
+    L, M = 30_000, 1600
+    for shape in ("hole", "low_sides", "zero_sides"):
+        s, e, _, _ = O.gen_reads(77, 200_000, L, 150, shape)
+        off = [0, len(s)]
+
+        def capped(ss, ee):
+            d = np.zeros(L + 1, np.int64)
+            np.add.at(d, ss, 1)
+            np.add.at(d, ee + 1, -1)
+            return np.minimum(np.cumsum(d)[:L], M)
+
+        res = {}
+        for sched in (1, 0):
+            bm, st = O.sync_solve(s, e, [L], off, M, params=(64, 150, 1, 0, 0, sched))
+            assert st.flow_value == st.fstar
+            keep = O.bitmap_to_mask(bm, len(s)) == 1
+            assert np.array_equal(capped(s[keep], e[keep]), capped(s, e))
+            res[sched] = st.as_dict()
+        assert res[1]["n_express"] == 0 and res[0]["n_express"] >= 1, shape
+        assert res[0]["rounds_max"] * 3 < res[1]["rounds_max"], (shape, res[0]["rounds_max"], res[1]["rounds_max"])
+        assert res[0]["n_kept"] <= 1.001 * res[1]["n_kept"]
+    # below M = 128 nothing changes: the uncut graph, the classic schedule
+    s, e, _, _ = O.gen_reads(78, 100_000, L, 150, "hole")
+    a = O.sync_solve(s, e, [L], [0, len(s)], 100, params=(64, 150, 1, 0, 0, 0))
+    b = O.sync_solve(s, e, [L], [0, len(s)], 100, params=(64, 150, 1, 0, 0, 1))
+    assert np.array_equal(a[0], b[0]) and a[1].rounds_total == b[1].rounds_total
+
+
 def test_batch_equals_per_sample(O):
     # a batch is exactly the concatenation of independent per-sample solves
     parts = [O.gen_reads(100 + k, 3000, 3000, 50) for k in range(3)]

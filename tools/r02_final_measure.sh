@@ -10,7 +10,7 @@ tail -3 $O/${T}_pytest.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > $O/${T}_smoke.txt 2>&1; tail -1 $O/${T}_smoke.txt
 timeout 900 python bench.py > $O/${T}_BENCH_c5.json 2> $O/${T}_BENCH_c5.err; echo "c5 rc=$?"
 timeout 900 python bench.py --impl reference > $O/${T}_BENCH_reference.json 2> $O/${T}_BENCH_reference.err; echo "ref rc=$?"
-for w in c4 c1 c2 ref_uniform ref_hole; do
+for w in c4 c1 c2 ref_uniform ref_low_sides ref_hole ref_zero_sides; do
   timeout 600 python bench.py --workload $w --no-cpu-baseline > $O/${T}_bench_$w.json 2> $O/${T}_bench_$w.err; echo "$w rc=$?"
 done
 GDS_EXPRESS=0 timeout 600 python bench.py --workload c4 --no-cpu-baseline > $O/${T}_bench_c4_classic.json 2>/dev/null; echo "c4 classic rc=$?"
