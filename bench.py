@@ -77,13 +77,14 @@ ALGORITHM = "quasi-mcp"   # --algorithm: "quasi-mcp" (push-relabel max flow) or 
 
 
 SEG_LEN = 0
+SCHEDULE = 0
 
 
 def solver_params():
     """gds_params for the chosen algorithm and segment length (None = library defaults)."""
-    if ALGORITHM != "mcp" and not SEG_LEN:
+    if ALGORITHM != "mcp" and not SEG_LEN and not SCHEDULE:
         return None
-    return (0, 0, 0, 0, SEG_LEN, 0, 1 if ALGORITHM == "mcp" else 0)
+    return (0, 0, 0, 0, SEG_LEN, 0, 1 if ALGORITHM == "mcp" else 0, SCHEDULE)
 
 
 def config_for(wname, wl):
@@ -96,7 +97,8 @@ def config_for(wname, wl):
             "pair_filter": wl.get("filter"), "law": wl.get("shape", "uniform"),
             "algorithm": "quasi-MCP (maximum flow)" if ALGORITHM == "quasi-mcp"
             else "MCP (minimum number of reads, mcp-cpu's objective)",
-            **({"seg_len": SEG_LEN} if SEG_LEN else {})}
+            **({"seg_len": SEG_LEN} if SEG_LEN else {}),
+            **({"schedule": SCHEDULE} if SCHEDULE else {})}
 
 
 def host_threads():
@@ -802,13 +804,16 @@ def main():
     ap.add_argument("--seg-len", type=int, default=0,
                     help="gds_params.seg_len (0 = the library's default rule); an experiment knob: the "
                          "config line then says so")
+    ap.add_argument("--schedule", type=int, default=0, choices=[0, 1, 2, 3],
+                    help="gds_params.schedule (include/gds.h); an experiment knob like --seg-len")
     ap.add_argument("--algorithm", default="quasi-mcp", choices=["quasi-mcp", "mcp"],
                     help="quasi-mcp: maximum flow by push-relabel (the north-star path, default); mcp: the "
                          "minimum-cardinality solve (gds_params.algorithm = 1, plugin mcp-b200)")
     args = ap.parse_args()
-    global ALGORITHM, SEG_LEN
+    global ALGORITHM, SEG_LEN, SCHEDULE
     ALGORITHM = args.algorithm
     SEG_LEN = args.seg_len
+    SCHEDULE = args.schedule
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:

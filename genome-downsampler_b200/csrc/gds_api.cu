@@ -935,7 +935,7 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         (prm && prm->seg_len) ? prm->seg_len : default_seg_len(rd->n_samples, rd->ref_len);
     const uint32_t algorithm = prm ? prm->algorithm : 0u;
     const uint32_t schedule = prm ? prm->schedule : 0u;
-    if (schedule > 2) return fail(c, GDS_ERR_ARG, "gds_params.schedule must be 0, 1 or 2");
+    if (schedule > 3) return fail(c, GDS_ERR_ARG, "gds_params.schedule must be 0, 1, 2 or 3");
     if (algorithm > 1) return fail(c, GDS_ERR_ARG, "gds_params.algorithm must be 0 (quasi-MCP) or 1 (minimum cardinality)");
     // scalars of the result start clean (buffers are left alone)
     {
@@ -1329,7 +1329,7 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
         // rounds than hops, and the three extra passes over nodes and bundles would cost config 5
         // 0.25 ms of 5.75 (measured); gds_params.schedule = 2 applies them regardless.
         bool forced_cuts = !(flags & GDS_NO_SOLVE) && algorithm == 0 && schedule != 1 &&
-                           (schedule == 2 || max_coverage >= kExpressMinSupply);
+                           (schedule >= 2 || max_coverage >= kExpressMinSupply);
         if (const char* e = getenv("GDS_EXPRESS")) forced_cuts = forced_cuts && atoi(e) != 0;
         int32_t* adj = nullptr;
         uint32_t* fmult = nullptr;
@@ -1445,7 +1445,7 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
             return fail(c, GDS_ERR_ARG, "algorithm 1 (minimum cardinality) takes reads of up to 4095 positions");
         // the express schedule (maxflow_sm.cuh): components with a supply of kExpressMinSupply or
         // more — none when M is below that, and then nothing about the launch changes
-        uint32_t express_on = schedule == 1 ? 0u : schedule == 2 ? 2u : 1u;
+        uint32_t express_on = schedule == 1 ? 0u : schedule == 2 ? 2u : 1u;  // (3: the usual supply rule)
         if (const char* e = getenv("GDS_EXPRESS")) express_on = (uint32_t)atoi(e);  // measurement knob
         if (!forced_cuts || (express_on == 1 && max_coverage < kExpressMinSupply)) express_on = 0;
         const bool express_possible = express_on != 0;

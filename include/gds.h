@@ -140,7 +140,11 @@ typedef struct {
      *      155-430, 13-19 ms -> 1.1-3.0 ms; config 4: 370 -> 175 rounds per segment.
      *      Below 128 (configs 1, 2, 5: M = 100) the graph and the schedule are round 1's;
      *   1  round 1's graph and classic schedule always;
-     *   2  (a) and (b) whatever max_coverage and the supply are (experiments).
+     *   2  (a) and (b) whatever max_coverage and the supply are (experiments);
+     *   3  (a) at every max_coverage, (b) by the usual rule.  Worth asking for when the coverage
+     *      dips below a SMALL max_coverage in many places and the batch is not huge (config 2 —
+     *      amplicon tiling, M = 100: 6.1 -> 3.6 ms; the three extra passes over nodes and bundles
+     *      cost config 5's 15 M nodes 0.25 ms, which is why 0 does not do it below 128).
      * Every choice is a function of the data and these fields alone, never of the device or the
      * batch a sample travels in. */
     uint32_t schedule;

@@ -1062,7 +1062,7 @@ extern "C" int orc_sync_solve(uint32_t n_samples, const uint64_t* read_off, cons
     auto t0 = clk::now();
     SyncGraph G;
     // forced reads out + cuts: from the supply at which the express schedule starts (the host's gate)
-    const bool forced_cuts = P.schedule == 2 || (P.schedule != 1 && M >= kExpressMinSupply);
+    const bool forced_cuts = P.schedule >= 2 || (P.schedule != 1 && M >= kExpressMinSupply);
     if (build_sync_graph(n_samples, read_off, ref_len, start, end, M, P.seg_len, G, forced_cuts) != 0)
         return -1;
     auto t1 = clk::now();

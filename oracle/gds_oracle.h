@@ -84,7 +84,8 @@ typedef struct {
     uint32_t max_rounds;      /* safety stop (0 = unlimited) */
     uint32_t seg_len;         /* segment length: references longer than 2*seg_len are cut (0 = default rule) */
     uint32_t schedule;        /* 0 = express schedule where eligible (gds_params.schedule), 1 = classic only,
-                                 2 = express for every component that is structurally eligible (lab) */
+                                 2 = express for every component that is structurally eligible (lab),
+                                 3 = the graph reduction at every M, express by the usual rule */
 } orc_sync_params;
 typedef struct {
     int64_t flow_value; /* total sink inflow over all components */

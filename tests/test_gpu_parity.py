@@ -606,6 +606,12 @@ def test_forced_reads_out_and_cuts(solver, O):
         assert_parity(O, r1, s, e, [30_000], off, M, (64, 150, 1, 0, 0, 1))
         assert r1.fstar == r.fstar and np.array_equal(r1.demand, r.demand)
         assert r1.rounds_max > 4 * r.rounds_max and abs(int(r1.n_kept) - int(r.n_kept)) <= 0.001 * r.n_kept
+    # schedule 3: the reduction below M = 128 too (classic schedule there): amplicon-like dips
+    s, e, _, _ = O.gen_reads(21, 300_000, 30_000, 150, "hole")
+    r3 = solver.solve(s, e, [30_000], 100, params=(64, 150, 1, 0, 0, 0, 0, 3), verify=True, want_vectors=True)
+    st3 = assert_parity(O, r3, s, e, [30_000], [0, len(s)], 100, (64, 150, 1, 0, 0, 3))
+    r0 = solver.solve(s, e, [30_000], 100, params=PRM, verify=True, want_vectors=True)
+    assert st3.n_express == 0 and r3.n_components >= r0.n_components and r3.fstar == r0.fstar
     # M above the coverage everywhere: every read is forced, nothing is left to solve
     s, e, _, _ = O.gen_reads(5, 50_000, 30_000, 150)
     r = solver.solve(s, e, [30_000], 5000, params=PRM, verify=True, want_vectors=True)
