@@ -161,6 +161,12 @@ def test_filter_path_c2_small(solver, O):
         mask = np.repeat(pp, 2).astype(bool)
         fs, fe = s[mask].copy(), e[mask].copy()
         assert_parity(O, r, fs, fe, [30_000], [0, kept], 100)
+        # the graph reduction behind the device filter: by default from M = 128 on (amplicon tiling
+        # dips below M between amplicons), at M = 100 on request (gds_params.schedule = 3)
+        for M, prm, oprm in ((400, PRM, PRM), (100, (64, 150, 1, 0, 0, 0, 0, 3), (64, 150, 1, 0, 0, 3))):
+            r = solver.solve(s, e, 30_000, M, mapq=q.astype(np.uint8), seq_len=l, filt=filt,
+                             params=prm, verify=True, want_vectors=True)
+            assert_parity(O, r, fs, fe, [30_000], [0, kept], M, oprm)
 
 
 def test_c2_full_size_filter_and_solve(solver, O, R):
