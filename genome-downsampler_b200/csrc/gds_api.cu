@@ -204,7 +204,11 @@ void launch_mf2_shape(gds_ctx* c, const Mf2Graph& g, const uint32_t* comp_lo, co
         GDS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         c->mf2_smem_set[SLOT] = smem;
     }
-    const int grid = (int)std::min<uint32_t>(n_comp, (uint32_t)(kNumSMs * ctas_per_sm));
+    // with the count on the device n_comp is an estimate (one component per sample or segment); the
+    // cuts at cov <= M can make many more (the reference's "low sides" shape: 11 from one sample,
+    // which a grid of one CTA solved one after the other).  A CTA without work exits at once.
+    const int grid = (int)std::min<uint32_t>(n_comp_dev ? 0xffffffffu : n_comp,
+                                             (uint32_t)(kNumSMs * ctas_per_sm));
     kern<<<grid, THREADS, smem, c->stream>>>(g, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats,
                                              (uint32_t)smem, qcap, fb_list, fb_count, optr ? 1u : 0u,
                                              n_comp_dev, mft, mf2_allow_warp());
@@ -1502,13 +1506,17 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
                 launch_maxflow_sm(c, mf2, g2, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats,
                                   mf_bytes, fb_list, wc + 2, n_comp_dev, mft);
                 // whatever the shared-memory kernel could not take (grid: at most one wave)
+                // (with the count on the device the list may be longer than the estimate says)
                 launch_maxflow(c, mg, comp_lo, comp_hi,
-                               mf2.classic_ok ? std::min<uint32_t>(n_comp, kNumSMs) : n_comp, wc + 1, qF,
+                               mf2.classic_ok && !n_comp_dev ? std::min<uint32_t>(n_comp, kNumSMs)
+                                                             : std::max<uint32_t>(n_comp, kNumSMs),
+                               wc + 1, qF,
                                qT, qN, qH, sp, cstats, 0, max_comp_nodes, n_comp_dev, mft, lab_g,
                                fb_list, wc + 2);
             } else {
-                launch_maxflow(c, mg, comp_lo, comp_hi, n_comp, wc, qF, qT, qN, qH, sp, cstats,
-                               mf_bytes, max_comp_nodes, n_comp_dev, mft, lab_g);
+                launch_maxflow(c, mg, comp_lo, comp_hi,
+                               n_comp_dev ? std::max<uint32_t>(n_comp, kNumSMs) : n_comp, wc, qF, qT, qN, qH,
+                               sp, cstats, mf_bytes, max_comp_nodes, n_comp_dev, mft, lab_g);
             }
         }
         if (fmult) {  // the forced bundles come back with their fixed flow: K5 keeps all their reads

@@ -137,7 +137,7 @@ typedef struct {
      *      (b) the EXPRESS schedule for components with a supply of 128 or more that fit one SM: back
      *      arcs have length 0 in the distance labels, flow changes read "lanes" within one round.
      *      The reference's hole / low-sides / zero-sides shapes at M = 8000: 2 100-4 300 rounds ->
-     *      155-430, 13-19 ms -> 1.1-3.0 ms; config 4: 370 -> 175 rounds per segment.
+     *      155-430, 13-19 ms -> 1.1-2.4 ms; config 4: 370 -> 175 rounds per segment.
      *      Below 128 (configs 1, 2, 5: M = 100) the graph and the schedule are round 1's;
      *   1  round 1's graph and classic schedule always;
      *   2  (a) and (b) whatever max_coverage and the supply are (experiments);
