@@ -938,8 +938,12 @@ extern "C" int gds_solve(gds_ctx* c, const gds_reads* rd, const gds_filter* flt,
     uint32_t seg_len =
         (prm && prm->seg_len) ? prm->seg_len : default_seg_len(rd->n_samples, rd->ref_len);
     const uint32_t algorithm = prm ? prm->algorithm : 0u;
-    const uint32_t schedule = prm ? prm->schedule : 0u;
+    uint32_t schedule = prm ? prm->schedule : 0u;
     if (schedule > 3) return fail(c, GDS_ERR_ARG, "gds_params.schedule must be 0, 1, 2 or 3");
+    // a call that filters by an amplicon table works on amplicon-tiled coverage, which dips between
+    // the amplicons whatever M is: the default then is the graph reduction at every M (config 2:
+    // 6.1 -> 3.6 ms).  A call-level choice like the filter itself, never a property of the batch.
+    if (schedule == 0 && flt && flt->n_amplicons > 0) schedule = 3;
     if (algorithm > 1) return fail(c, GDS_ERR_ARG, "gds_params.algorithm must be 0 (quasi-MCP) or 1 (minimum cardinality)");
     // scalars of the result start clean (buffers are left alone)
     {

@@ -138,7 +138,9 @@ typedef struct {
      *      arcs have length 0 in the distance labels, flow changes read "lanes" within one round.
      *      The reference's hole / low-sides / zero-sides shapes at M = 8000: 2 100-4 300 rounds ->
      *      155-430, 13-19 ms -> 1.1-2.4 ms; config 4: 370 -> 175 rounds per segment.
-     *      Below 128 (configs 1, 2, 5: M = 100) the graph and the schedule are round 1's;
+     *      Below 128 (configs 1, 5: M = 100) the graph and the schedule are round 1's — except
+     *      in a call that carries an amplicon table (gds_filter.n_amplicons > 0: amplicon-tiled
+     *      coverage dips between the amplicons), which gets (a) at every max_coverage, like 3;
      *   1  round 1's graph and classic schedule always;
      *   2  (a) and (b) whatever max_coverage and the supply are (experiments);
      *   3  (a) at every max_coverage, (b) by the usual rule.  Worth asking for when the coverage

@@ -281,7 +281,8 @@ def test_bam_to_bam_through_the_b200_plugin(hostlib, O, tmp_path):
     mask = np.zeros(len(want), np.uint8); mask[kept] = 1
     cin = O.coverage_fast(ws, we, L); cout = O.coverage_fast(ws, we, L, mask)
     assert np.array_equal(np.minimum(cin, M), np.minimum(cout, M))
-    bm, _ = O.sync_solve(ws, we, [L], [0, len(ws)], M, params=(64, 150, 1, 0))
+    # (the device filter carries the amplicon table: the graph reduction applies at every M)
+    bm, _ = O.sync_solve(ws, we, [L], [0, len(ws)], M, params=(64, 150, 1, 0, 0, 3))
     assert np.array_equal(O.bitmap_to_mask(bm, len(ws)), mask)
     out, fo = tmp_path / "out.bam", tmp_path / "filtered.bam"
     n = b.write_solution(out, kept, with_pairs=True)

@@ -160,10 +160,12 @@ def test_filter_path_c2_small(solver, O):
         assert r.filt_off.tolist() == [0, kept]
         mask = np.repeat(pp, 2).astype(bool)
         fs, fe = s[mask].copy(), e[mask].copy()
-        assert_parity(O, r, fs, fe, [30_000], [0, kept], 100)
-        # the graph reduction behind the device filter: by default from M = 128 on (amplicon tiling
-        # dips below M between amplicons), at M = 100 on request (gds_params.schedule = 3)
-        for M, prm, oprm in ((400, PRM, PRM), (100, (64, 150, 1, 0, 0, 0, 0, 3), (64, 150, 1, 0, 0, 3))):
+        # a call with an amplicon table gets the graph reduction at every M (gds_params.schedule:
+        # like 3), one without gets it from M = 128 on; schedule 1 is round 1's graph either way
+        AMP = (64, 150, 1, 0, 0, 3)
+        assert_parity(O, r, fs, fe, [30_000], [0, kept], 100, AMP if "amp_start" in filt else PRM)
+        for M, prm, oprm in ((400, PRM, PRM), (100, (64, 150, 1, 0, 0, 0, 0, 3), AMP),
+                             (100, (64, 150, 1, 0, 0, 0, 0, 1), (64, 150, 1, 0, 0, 1))):
             r = solver.solve(s, e, 30_000, M, mapq=q.astype(np.uint8), seq_len=l, filt=filt,
                              params=prm, verify=True, want_vectors=True)
             assert_parity(O, r, fs, fe, [30_000], [0, kept], M, oprm)
@@ -182,7 +184,7 @@ def test_c2_full_size_filter_and_solve(solver, O, R):
     pp, kept = O.filter_pairs(s, e, q, l, 90, 30, a0, a1)
     assert np.array_equal(r.pair_pass, pp) and r.n_filtered == kept and 0 < kept < len(s)
     mask = np.repeat(pp, 2).astype(bool)
-    assert_parity(O, r, s[mask].copy(), e[mask].copy(), [30_000], [0, kept], 100)
+    assert_parity(O, r, s[mask].copy(), e[mask].copy(), [30_000], [0, kept], 100, (64, 150, 1, 0, 0, 3))
     n_ref = 500_000
     ref = R.read_bam(s[:n_ref].copy(), e[:n_ref].copy(), q[:n_ref].copy(), l[:n_ref].copy(), 30_000,
                      90, 30, bed, tsv)
@@ -203,7 +205,8 @@ def test_filter_on_batches_keeps_sample_offsets(solver, O):
     mask = np.repeat(pp, 2).astype(bool)
     foff = [0] + [int(mask[:int(o)].sum()) for o in off[1:]]
     assert r.filt_off.tolist() == foff
-    assert_parity(O, r, s[mask].copy(), e[mask].copy(), [30_000] * 3, np.array(foff, np.uint64), 40)
+    assert_parity(O, r, s[mask].copy(), e[mask].copy(), [30_000] * 3, np.array(foff, np.uint64), 40,
+                  (64, 150, 1, 0, 0, 3))
 
 
 def test_edge_cases(solver, O, pkg):
